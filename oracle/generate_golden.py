@@ -1,0 +1,285 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only) and pin
+the oracle against it on the way.   python -m oracle.generate_golden
+
+Every fixture stores the seeded inputs and the REFERENCE's outputs; model parameters are not
+stored but regenerated from a seeded torch.Generator by oracle.nerf_mlp.init_mlp_params /
+oracle.tensorf.init_vm_params on both sides (they are loaded into the reference modules here).
+The script fails if any oracle stage differs from the reference (bit-exact on this host, because
+both run the same ATen CPU kernels in the same order).
+"""
+import copy
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import composite as C
+from . import nerf_mlp as M
+from . import pipeline as P
+from . import reference_harness as H
+from . import sampling as SP
+from . import tensorf as TF
+
+OUT = Path(__file__).resolve().parent.parent / 'tests' / 'golden'
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+
+
+def _check(name, ref, mine, exact=True, tol=0.0):
+    ref, mine = torch.as_tensor(ref), torch.as_tensor(mine)
+    assert ref.shape == mine.shape, (name, ref.shape, mine.shape)
+    if exact:
+        ok = torch.equal(ref, mine)
+    else:
+        ok = bool((ref.double() - mine.double()).abs().max() <= tol)
+    if not ok:
+        raise SystemExit(f'oracle != reference at {name}: max abs diff '
+                         f'{(ref.double() - mine.double()).abs().max().item():.3e}')
+
+
+def nerf_param_sets(configs, seed):
+    g = torch.Generator().manual_seed(seed)
+    mc = configs['model']
+    sets = {'coarse_model': M.init_mlp_params(mc['coarse_model'], g),
+            'fine_model': M.init_mlp_params(mc['fine_model'], g), 'augmentations': []}
+    for aug in mc.get('augmentations', []):
+        sets['augmentations'].append((aug['name'], aug['coarse_model'], M.init_mlp_params(aug['coarse_model'], g)))
+    # a sigma bias keeps the random-init field from being empty (weights/depths exercise the scan)
+    for p in [sets['coarse_model'], sets['fine_model']] + [a[2] for a in sets['augmentations']]:
+        p['pts_output_linear.bias'][0] += 2.0
+    return sets
+
+
+def load_nerf_params(model, sets):
+    def put(module, params):
+        sd = module.state_dict()
+        assert set(sd.keys()) == set(params.keys()), (sorted(sd.keys()), sorted(params.keys()))
+        module.load_state_dict(params)
+    put(model.coarse_model, sets['coarse_model'])
+    put(model.fine_model, sets['fine_model'])
+    for aug, (_, _, params) in zip(model.augmented_models, sets['augmentations']):
+        put(aug['coarse_model'], params)
+
+
+def random_pixels(n, num_views, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.stack([torch.randint(0, num_views, (n,), generator=g),
+                        torch.randint(0, w, (n,), generator=g),
+                        torch.randint(0, h, (n,), generator=g)], 1).int()
+
+
+def golden_nerf():
+    configs, model_configs = H.load_configs(1142, 'fern')
+    model_configs = H.shrink(model_configs, 4)
+    configs['model']['netchunk'] = 2048
+    model = H.build_model(configs, model_configs)
+    sets = nerf_param_sets(configs, seed=11)
+    load_nerf_params(model, sets)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    keep = ('rays_o', 'rays_d', 'rays_o_ndc', 'rays_d_ndc', 'view_dirs')
+    per_tag = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility',
+               'weights', 'raw_sigma', 'raw_rgb')
+    for mode, R, seed in (('eval', 48, 3), ('train', 40, 4)):
+        pixel_id = random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(100 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+        torch.manual_seed(100 + seed)
+        with torch.no_grad():
+            mine = P.nerf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        fixture = {'pixel_id': pixel_id, 'param_seed': 11, 'rng_seed': 100 + seed}
+        for k in keep + ('z_vals_coarse', 'z_vals_fine'):
+            _check(f'nerf/{mode}/{k}', ref[k], mine[k])
+            fixture[k] = ref[k]
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for tag in ('coarse', 'fine'):
+                if pre and tag == 'fine':
+                    continue
+                for k in per_tag:
+                    key = f'{pre}{k}_{tag}'
+                    _check(f'nerf/{mode}/{key}', ref[key], mine[key])
+                    fixture[key] = ref[key]
+        for k in ('_fine_u', '_fine_below', '_fine_above', '_fine_samples'):
+            fixture[k[1:]] = mine[k]
+        np.savez_compressed(OUT / f'nerf_{mode}.npz', **_np(fixture))
+        print(f'nerf_{mode}: {len(fixture)} arrays, oracle == reference')
+    return configs, model_configs
+
+
+def golden_sample_pdf():
+    """Stage-wise: the reference's own static sample_pdf + get_z_vals_fine on seeded inputs, both
+    the deterministic (eval) and the random-u (train) form, S in {64, 37}."""
+    get_model, _ = H.import_reference()
+    from models.SimpleNeRF17 import SimpleNeRF
+    fixture = {}
+    for tag, S, N, R, det in (('a', 64, 128, 64, True), ('b', 64, 128, 64, False), ('c', 37, 50, 33, False)):
+        g = torch.Generator().manual_seed(7 + S + N + det)
+        z = torch.sort(torch.rand(R, S, generator=g), -1)[0]
+        wts = torch.rand(R, S, generator=g) ** 4
+        wts[: R // 4] *= 1e-4                      # nearly-empty rays: cdf dominated by the 1e-5 floor
+        wts[R // 4: R // 2, S // 3:] = 0           # mass concentrated early: many repeated cdf values
+        if det:
+            torch.manual_seed(0)
+            u = SP.det_u(R, N)
+        else:
+            torch.manual_seed(31 + S)
+            u = torch.rand([R, N])
+            torch.manual_seed(31 + S)
+        mids = .5 * (z[..., 1:] + z[..., :-1])
+        ref_samples = SimpleNeRF.sample_pdf(mids, wts[..., 1:-1], N, det=det)
+        ref_fine = torch.sort(torch.cat([z, ref_samples], -1), -1)[0]
+        z_f, samples, below, above = SP.fine_depths(z, wts, u)
+        _check(f'sample_pdf/{tag}/samples', ref_samples, samples)
+        _check(f'sample_pdf/{tag}/z_fine', ref_fine, z_f)
+        fixture.update({f'{tag}_z': z, f'{tag}_weights': wts, f'{tag}_u': u, f'{tag}_samples': ref_samples,
+                        f'{tag}_z_fine': ref_fine, f'{tag}_below': below, f'{tag}_above': above})
+    np.savez_compressed(OUT / 'sample_pdf.npz', **_np(fixture))
+    print('sample_pdf: oracle == reference')
+
+
+def golden_composite(configs, model_configs):
+    """Stage-wise: reference volume_rendering (NDC and world) with autograd gradients."""
+    model = H.build_model(configs, model_configs)
+    fixture = {}
+    for tag, ndc, white, S in (('ndc', True, False, 64), ('world', False, True, 45)):
+        g = torch.Generator().manual_seed(5 + S)
+        R = 24
+        model.ndc = ndc
+        model.configs['model']['white_bkgd'] = white
+        sigma = (torch.relu(torch.randn(R, S, generator=g)) * 10).requires_grad_()
+        rgb = torch.rand(R, S, 3, generator=g).requires_grad_()
+        z = torch.sort(torch.rand(R, S, generator=g), -1)[0]
+        if not ndc:
+            z = 2 + 4 * z
+        rays_o = torch.randn(R, 3, generator=g) * 0.1
+        rays_d = torch.randn(R, 3, generator=g) * 0.3 - torch.tensor([0, 0, 1.])
+        d_ndc = torch.randn(R, 3, generator=g)
+        net = {'sigma': sigma[..., None], 'rgb': rgb}
+        if ndc:
+            ref = model.volume_rendering(net, z_vals_ndc=z, rays_d_ndc=d_ndc, rays_o=rays_o, rays_d=rays_d)
+        else:
+            ref = model.volume_rendering(net, z_vals=z, rays_d=rays_d)
+        mine = C.composite(sigma, rgb, z, rays_o, rays_d, d_ndc, ndc=ndc, white_bkgd=white)
+        ups = {}
+        loss = 0
+        for k in ('rgb', 'acc', 'depth', 'depth_var', 'weights') + (('depth_ndc', 'depth_var_ndc') if ndc else ()):
+            _check(f'composite/{tag}/{k}', ref[k], mine[k])
+            ups[k] = torch.rand(ref[k].shape, generator=g)
+            loss = loss + (ref[k] * ups[k]).sum()
+        gs, gc = torch.autograd.grad(loss, [sigma, rgb])
+        gs_o, gc_o = C.composite_backward(
+            sigma.detach().double(), rgb.detach().double(), z.double(), rays_o.double(), rays_d.double(),
+            d_ndc.double(), ndc=ndc, white_bkgd=white, g_rgb=ups['rgb'].double(), g_acc=ups['acc'].double(),
+            g_depth=ups['depth'].double(), g_depth_var=ups['depth_var'].double(),
+            g_depth_ndc=ups['depth_ndc'].double() if ndc else None,
+            g_depth_var_ndc=ups['depth_var_ndc'].double() if ndc else None, g_weights=ups['weights'].double())
+        scale = gs.abs().max().item()
+        _check(f'composite/{tag}/g_sigma', gs / scale, gs_o.float() / scale, exact=False, tol=2e-4)
+        _check(f'composite/{tag}/g_rgb', gc, gc_o.float(), exact=False, tol=1e-5)
+        fixture.update({f'{tag}_sigma': sigma, f'{tag}_rgb': rgb, f'{tag}_z': z, f'{tag}_rays_o': rays_o,
+                        f'{tag}_rays_d': rays_d, f'{tag}_rays_d_ndc': d_ndc, f'{tag}_g_sigma': gs, f'{tag}_g_rgb': gc})
+        for k, v in ups.items():
+            fixture[f'{tag}_up_{k}'] = v
+        for k in ('rgb', 'acc', 'depth', 'depth_var', 'weights', 'alpha', 'visibility') + (('depth_ndc', 'depth_var_ndc') if ndc else ()):
+            fixture[f'{tag}_out_{k}'] = ref[k]
+    np.savez_compressed(OUT / 'composite.npz', **_np(fixture))
+    print('composite: oracle == reference (forward exact, closed-form backward vs autograd)')
+
+
+def tensorf_sets(configs, seed, with_alpha):
+    g = torch.Generator().manual_seed(seed)
+    mc = configs['model']
+
+    def one(cfg):
+        bbox = torch.tensor(cfg['bounding_box'])
+        res = TF.vm_resolution(cfg['num_voxels_initial'], bbox)
+        t = {'params': TF.init_vm_params(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
+             'bbox': bbox, 'resolution': res, 'num_samples': TF.vm_num_samples(res, cfg['num_voxels_per_sample'], cfg['num_samples_max'])}
+        # random-init planes give sigma ~ 0; scale density up so weights cross the 1e-4 surface threshold
+        for i in range(3):
+            t['params'][f'matrices_density.{i}'] *= 6.0
+        if with_alpha:
+            X, Y, Z = [int(r) for r in res]
+            vol = (torch.rand(Z, Y, X, generator=g) < 0.35).float()
+            t['alpha_volume'] = vol.view(1, 1, Z, Y, X)
+            t['alpha_bbox'] = bbox.clone()
+        return t
+    sets = {'coarse_model': one(mc['coarse_model']), 'augmentations': []}
+    for aug in mc.get('augmentations', []):
+        sets['augmentations'].append((aug['name'], aug['coarse_model'], one(aug['coarse_model'])))
+    return sets
+
+
+def load_tensorf_params(model, sets):
+    from models.SimpleTensoRF09 import AlphaGridMask
+
+    def put(module, t):
+        sd = dict(module.named_parameters())
+        assert set(sd.keys()) == set(t['params'].keys()), (sorted(sd.keys()), sorted(t['params'].keys()))
+        for k, v in t['params'].items():
+            assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
+            sd[k].data.copy_(v)
+        assert int(module.num_samples) == t['num_samples']
+        module.alpha_mask = AlphaGridMask(t['alpha_volume'][0, 0], t['alpha_bbox']) if 'alpha_volume' in t else None
+    put(model.coarse_model, sets['coarse_model'])
+    for aug, (_, _, t) in zip(model.augmented_models, sets['augmentations']):
+        put(aug['coarse_model'], t)
+
+
+def golden_tensorf():
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    configs['model']['coarse_model']['num_voxels_initial'] = 40 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 20 ** 3
+    model = H.build_model(configs, model_configs)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    keys = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility', 'weights',
+            'raw_sigma', 'raw_rgb')
+    for mode, R, seed, with_alpha in (('eval', 40, 5, True), ('train', 32, 6, False)):
+        sets = tensorf_sets(configs, seed=21, with_alpha=with_alpha)
+        load_tensorf_params(model, sets)
+        pixel_id = random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(200 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+        torch.manual_seed(200 + seed)
+        with torch.no_grad():
+            mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        fixture = {'pixel_id': pixel_id, 'param_seed': 21, 'rng_seed': 200 + seed, 'with_alpha': with_alpha}
+        for k in ('rays_o', 'rays_d', 'rays_o_ndc', 'rays_d_ndc', 'view_dirs', 'z_vals_coarse'):
+            _check(f'tensorf/{mode}/{k}', ref[k], mine[k])
+            fixture[k] = ref[k]
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for k in keys:
+                key = f'{pre}{k}_coarse'
+                _check(f'tensorf/{mode}/{key}', ref[key], mine[key])
+                fixture[key] = ref[key]
+            fixture[f'{pre}validity_mask_coarse'] = mine[f'{pre}validity_mask_coarse']
+            fixture[f'{pre}surface_mask_coarse'] = mine[f'{pre}surface_mask_coarse']
+        frac = mine['validity_mask_coarse'].float().mean().item(), mine['surface_mask_coarse'].float().mean().item()
+        np.savez_compressed(OUT / f'tensorf_{mode}.npz', **_np(fixture))
+        print(f'tensorf_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f})')
+
+
+def main():
+    if not H.available():
+        sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    configs, model_configs = golden_nerf()
+    golden_sample_pdf()
+    golden_composite(copy.deepcopy(configs), model_configs)
+    golden_tensorf()
+
+
+if __name__ == '__main__':
+    main()
