@@ -1,0 +1,82 @@
+/* simple_rf_b200 — C ABI of the B200 (sm_100a) per-ray rendering hot path of Simple-RF.
+ *
+ * The reference (NagabhushanSN95/Simple-RF) is pure PyTorch and has no FFI of its own; the seam a
+ * maintainer binds to is the set of torch-op sequences inside its model classes.  Every entry point
+ * below names the reference lines it replaces (paths relative to the upstream checkout).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to densely packed row-major data, fp32 unless stated;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *  - return value 0 = success; otherwise srf_last_error() describes the failure (per host thread);
+ *  - "nullable" outputs may be NULL to skip that output;
+ *  - no CPU fallback exists: without a CUDA device every call fails with a CUDA error.
+ */
+#ifndef SIMPLE_RF_B200_H
+#define SIMPLE_RF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* srf_last_error(void);
+int srf_abi_version(void);
+
+/* Ray generation + NDC warp + unit view directions, one fused kernel.
+ * Replaces src/utils/CommonUtils04.py:73-95 (get_rays_tr), :120-138 (get_ndc_rays_tr), :147-149
+ * (get_view_dirs_tr) and the x-flip of src/models/SimpleTensoRF09.py:205-207.
+ *   pixel_id int32 [R,3] = (view, x, y);  k_inv [F,9] per-view inverse intrinsics;  c2w [F,16];
+ *   focal [F,2] = (fx, fy);  near, two_near = (float)near, (float)(2.0*near) as the reference's
+ *   python-double scalars round;  half_pixel: +0.5 px (`mip_nerf_used`);  flip_x: TensoRF x-flip;
+ *   viewdirs_from_ndc: normalise the NDC direction (SimpleTensoRF09.py:238) instead of the world one.
+ *   outputs [R,3]; rays_o_ndc / rays_d_ndc are required when ndc != 0. */
+int srf_raygen(const int32_t* pixel_id, int64_t num_rays, const float* k_inv, const float* c2w,
+               const float* focal, int num_views, int height, int width, float near, float two_near,
+               int half_pixel, int flip_x, int ndc, int viewdirs_from_ndc, float* rays_o, float* rays_d,
+               float* rays_o_ndc, float* rays_d_ndc, float* view_dirs, void* stream);
+
+/* Stratified depths.  Replaces src/models/SimpleNeRF17.py:347-357 (== SimpleTensoRF09.py:371-381).
+ *   ladder [S] = the un-jittered depths (:341-345);  jitter [R,S] = the reference's torch.rand draws
+ *   (parity mode), or NULL with use_philox=1 (in-kernel Philox4x32-10, NOT seed-compatible with the
+ *   reference) or NULL with use_philox=0 (eval: z = ladder broadcast).  z [R,S]. */
+int srf_stratified_z(const float* ladder, int num_samples, int64_t num_rays, const float* jitter,
+                     int use_philox, uint64_t seed, float* z, void* stream);
+
+/* Hierarchical resampling + merge.  Replaces src/models/SimpleNeRF17.py:360-371 (get_z_vals_fine) and
+ * :385-417 (sample_pdf).  Bit-exact against the reference's CPU path given identical inputs.
+ *   z_coarse, weights [R,S];  u [R,N] (u_row_stride = N), one shared row [N] (u_row_stride = 0, the
+ *   deterministic linspace of :394) or NULL (in-kernel Philox, not seed-compatible);
+ *   z_fine [R,S+N] sorted;  nullable: samples [R,N], below / above int64 [R,N]. */
+int srf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int64_t u_row_stride,
+                         uint64_t seed, int64_t num_rays, int num_coarse, int num_fine, float* z_fine,
+                         float* samples, int64_t* below, int64_t* above, void* stream);
+
+/* Volume-rendering compositing, forward.  Replaces src/models/SimpleNeRF17.py:486-539 and
+ * src/models/SimpleTensoRF09.py:767-819 (distance_scale = 25 there, 1 for NeRF).
+ *   sigma, z [R,S];  rgb [R,S,3] nullable (then rgb_map must be NULL);  rays_* [R,3];
+ *   ndc != 0: z are NDC depths, the last interval ends at 1, depth/depth_var are world depths
+ *   (CommonUtils04.py:208-224) and depth_ndc/depth_var_ndc the NDC ones;  otherwise the last interval
+ *   ends at 1e10 and the *_ndc outputs are ignored.
+ *   nullable: alpha, visibility [R,S];  weights [R,S] is required. */
+int srf_composite_fwd(const float* sigma, const float* rgb, const float* z, const float* rays_o,
+                      const float* rays_d, const float* rays_d_ndc, int64_t num_rays, int num_samples,
+                      int ndc, int white_bkgd, float distance_scale, float* alpha, float* visibility,
+                      float* weights, float* rgb_map, float* acc, float* depth, float* depth_var,
+                      float* depth_ndc, float* depth_var_ndc, void* stream);
+
+/* Compositing backward (what autograd derives from the lines above).  `visibility`, acc, depth,
+ * depth_ndc are the forward's outputs; upstream gradients are nullable; g_sigma [R,S];
+ * g_rgb_samples [R,S,3] nullable. */
+int srf_composite_bwd(const float* sigma, const float* rgb, const float* z, const float* visibility,
+                      const float* rays_o, const float* rays_d, const float* rays_d_ndc, const float* acc,
+                      const float* depth, const float* depth_ndc, const float* g_rgb, const float* g_acc,
+                      const float* g_depth, const float* g_depth_ndc, const float* g_depth_var,
+                      const float* g_depth_var_ndc, const float* g_weights, int64_t num_rays,
+                      int num_samples, int ndc, int white_bkgd, float distance_scale, float* g_sigma,
+                      float* g_rgb_samples, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLE_RF_B200_H */

@@ -36,11 +36,16 @@ def row_sum_f32(x):
     """x: 1-D float32 array (a contiguous reduced row with len(x) >= 8)."""
     x = np.asarray(x, dtype=F32)
     n = x.shape[0]
-    if n < LANES:                       # scalar_inner_sum path: plain sequential fp32
-        s = F32(0)
-        for v in x:
-            s = F32(s + v)
-        return s
+    if n < LANES:                       # scalar_inner_sum -> row_sum: 4 ILP partial sums, no SIMD lanes
+        part = np.zeros(ILP, dtype=F32)
+        full = n // ILP
+        for i in range(full):
+            part += x[i * ILP:(i + 1) * ILP]
+        for k in range(full * ILP, n):
+            part[0] = F32(part[0] + x[k])
+        for k in range(1, ILP):
+            part[0] = F32(part[0] + part[k])
+        return part[0]
     nvec = n // LANES
     vecs = x[:nvec * LANES].reshape(nvec, LANES)
     groups = nvec // ILP

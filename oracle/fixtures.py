@@ -1,0 +1,54 @@
+"""Seeded synthetic parameters / pixels shared by oracle/generate_golden.py and tests/ (test infrastructure).
+
+Model parameters are never stored in fixtures: both sides regenerate them from a seeded
+torch.Generator (CPU mt19937 streams are platform independent)."""
+import torch
+
+from . import nerf_mlp as M
+from . import tensorf as TF
+
+
+def nerf_param_sets(configs, seed):
+    g = torch.Generator().manual_seed(seed)
+    mc = configs['model']
+    sets = {'coarse_model': M.init_mlp_params(mc['coarse_model'], g),
+            'fine_model': M.init_mlp_params(mc['fine_model'], g), 'augmentations': []}
+    for aug in mc.get('augmentations', []):
+        sets['augmentations'].append((aug['name'], aug['coarse_model'], M.init_mlp_params(aug['coarse_model'], g)))
+    # a sigma bias keeps the random-init field from being empty (weights/depths exercise the scan)
+    for p in [sets['coarse_model'], sets['fine_model']] + [a[2] for a in sets['augmentations']]:
+        p['pts_output_linear.bias'][0] += 2.0
+    return sets
+
+
+def random_pixels(n, num_views, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.stack([torch.randint(0, num_views, (n,), generator=g),
+                        torch.randint(0, w, (n,), generator=g),
+                        torch.randint(0, h, (n,), generator=g)], 1).int()
+
+
+def tensorf_sets(configs, seed, with_alpha):
+    g = torch.Generator().manual_seed(seed)
+    mc = configs['model']
+
+    def one(cfg):
+        bbox = torch.tensor(cfg['bounding_box'])
+        res = TF.vm_resolution(cfg['num_voxels_initial'], bbox)
+        t = {'params': TF.init_vm_params(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
+             'bbox': bbox, 'resolution': res, 'num_samples': TF.vm_num_samples(res, cfg['num_voxels_per_sample'], cfg['num_samples_max'])}
+        # random-init planes give sigma ~ 0; scale density up so weights cross the 1e-4 surface threshold
+        for i in range(3):
+            t['params'][f'matrices_density.{i}'] *= 6.0
+        if with_alpha:
+            X, Y, Z = [int(r) for r in res]
+            vol = (torch.rand(Z, Y, X, generator=g) < 0.35).float()
+            t['alpha_volume'] = vol.view(1, 1, Z, Y, X)
+            t['alpha_bbox'] = bbox.clone()
+        return t
+    sets = {'coarse_model': one(mc['coarse_model']), 'augmentations': []}
+    for aug in mc.get('augmentations', []):
+        sets['augmentations'].append((aug['name'], aug['coarse_model'], one(aug['coarse_model'])))
+    return sets
+
+

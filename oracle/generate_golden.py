@@ -8,6 +8,7 @@ The script fails if any oracle stage differs from the reference (bit-exact on th
 both run the same ATen CPU kernels in the same order).
 """
 import copy
+import json
 import sys
 from pathlib import Path
 
@@ -15,6 +16,7 @@ import numpy as np
 import torch
 
 from . import composite as C
+from . import fixtures as FX
 from . import nerf_mlp as M
 from . import pipeline as P
 from . import reference_harness as H
@@ -40,19 +42,6 @@ def _check(name, ref, mine, exact=True, tol=0.0):
                          f'{(ref.double() - mine.double()).abs().max().item():.3e}')
 
 
-def nerf_param_sets(configs, seed):
-    g = torch.Generator().manual_seed(seed)
-    mc = configs['model']
-    sets = {'coarse_model': M.init_mlp_params(mc['coarse_model'], g),
-            'fine_model': M.init_mlp_params(mc['fine_model'], g), 'augmentations': []}
-    for aug in mc.get('augmentations', []):
-        sets['augmentations'].append((aug['name'], aug['coarse_model'], M.init_mlp_params(aug['coarse_model'], g)))
-    # a sigma bias keeps the random-init field from being empty (weights/depths exercise the scan)
-    for p in [sets['coarse_model'], sets['fine_model']] + [a[2] for a in sets['augmentations']]:
-        p['pts_output_linear.bias'][0] += 2.0
-    return sets
-
-
 def load_nerf_params(model, sets):
     def put(module, params):
         sd = module.state_dict()
@@ -64,19 +53,13 @@ def load_nerf_params(model, sets):
         put(aug['coarse_model'], params)
 
 
-def random_pixels(n, num_views, h, w, seed):
-    g = torch.Generator().manual_seed(seed)
-    return torch.stack([torch.randint(0, num_views, (n,), generator=g),
-                        torch.randint(0, w, (n,), generator=g),
-                        torch.randint(0, h, (n,), generator=g)], 1).int()
-
-
 def golden_nerf():
     configs, model_configs = H.load_configs(1142, 'fern')
     model_configs = H.shrink(model_configs, 4)
     configs['model']['netchunk'] = 2048
+    (OUT / 'nerf_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
     model = H.build_model(configs, model_configs)
-    sets = nerf_param_sets(configs, seed=11)
+    sets = FX.nerf_param_sets(configs, seed=11)
     load_nerf_params(model, sets)
     h, w = model_configs['resolution']
     nviews = len(model_configs['intrinsics'])
@@ -84,7 +67,7 @@ def golden_nerf():
     per_tag = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility',
                'weights', 'raw_sigma', 'raw_rgb')
     for mode, R, seed in (('eval', 48, 3), ('train', 40, 4)):
-        pixel_id = random_pixels(R, nviews, h, w, seed)
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
         model.train(mode == 'train')
         torch.manual_seed(100 + seed)
         with torch.no_grad():
@@ -192,30 +175,6 @@ def golden_composite(configs, model_configs):
     print('composite: oracle == reference (forward exact, closed-form backward vs autograd)')
 
 
-def tensorf_sets(configs, seed, with_alpha):
-    g = torch.Generator().manual_seed(seed)
-    mc = configs['model']
-
-    def one(cfg):
-        bbox = torch.tensor(cfg['bounding_box'])
-        res = TF.vm_resolution(cfg['num_voxels_initial'], bbox)
-        t = {'params': TF.init_vm_params(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
-             'bbox': bbox, 'resolution': res, 'num_samples': TF.vm_num_samples(res, cfg['num_voxels_per_sample'], cfg['num_samples_max'])}
-        # random-init planes give sigma ~ 0; scale density up so weights cross the 1e-4 surface threshold
-        for i in range(3):
-            t['params'][f'matrices_density.{i}'] *= 6.0
-        if with_alpha:
-            X, Y, Z = [int(r) for r in res]
-            vol = (torch.rand(Z, Y, X, generator=g) < 0.35).float()
-            t['alpha_volume'] = vol.view(1, 1, Z, Y, X)
-            t['alpha_bbox'] = bbox.clone()
-        return t
-    sets = {'coarse_model': one(mc['coarse_model']), 'augmentations': []}
-    for aug in mc.get('augmentations', []):
-        sets['augmentations'].append((aug['name'], aug['coarse_model'], one(aug['coarse_model'])))
-    return sets
-
-
 def load_tensorf_params(model, sets):
     from models.SimpleTensoRF09 import AlphaGridMask
 
@@ -237,15 +196,16 @@ def golden_tensorf():
     model_configs = H.shrink(model_configs, 4)
     configs['model']['coarse_model']['num_voxels_initial'] = 40 ** 3
     configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 20 ** 3
+    (OUT / 'tensorf_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
     model = H.build_model(configs, model_configs)
     h, w = model_configs['resolution']
     nviews = len(model_configs['intrinsics'])
     keys = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility', 'weights',
             'raw_sigma', 'raw_rgb')
     for mode, R, seed, with_alpha in (('eval', 40, 5, True), ('train', 32, 6, False)):
-        sets = tensorf_sets(configs, seed=21, with_alpha=with_alpha)
+        sets = FX.tensorf_sets(configs, seed=21, with_alpha=with_alpha)
         load_tensorf_params(model, sets)
-        pixel_id = random_pixels(R, nviews, h, w, seed)
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
         model.train(mode == 'train')
         torch.manual_seed(200 + seed)
         with torch.no_grad():

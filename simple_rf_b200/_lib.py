@@ -1,0 +1,87 @@
+"""ctypes binding of libsimple_rf_b200.so (the C ABI declared in include/simple_rf_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or a call fails,
+an exception is raised.  Tensors cross the boundary as raw device pointers + sizes + the current
+CUDA stream handle.
+"""
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / 'libsimple_rf_b200.so'
+_P = c_void_p
+
+_SIGNATURES = {
+    'srf_last_error': (c_char_p, []),
+    'srf_abi_version': (c_int, []),
+    'srf_raygen': (c_int, [_P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int,
+                           _P, _P, _P, _P, _P, _P]),
+    'srf_stratified_z': (c_int, [_P, c_int, c_int64, _P, c_int, c_uint64, _P, _P]),
+    'srf_sample_pdf_merge': (c_int, [_P, _P, _P, c_int64, c_uint64, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
+    'srf_composite_fwd': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float,
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'srf_composite_bwd': (c_int, [_P] * 17 + [c_int64, c_int, c_int, c_int, c_float, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class SimpleRFNativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SimpleRFNativeError(
+            f'{LIB_PATH} is missing: build it with `python -m simple_rf_b200.build` '
+            '(nvcc, sm_100a). simple_rf_b200 has no CPU / PyTorch fallback.')
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    return list(_SIGNATURES.keys())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_handle():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise SimpleRFNativeError(lib.srf_last_error().decode())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SimpleRFNativeError('simple_rf_b200 kernels take CUDA tensors only (no CPU fallback)')
+
+
+def f32c(t):
+    """Contiguous fp32 view/copy (None passes through)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

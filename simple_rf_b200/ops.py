@@ -1,0 +1,156 @@
+"""Tensor-level wrappers over the C ABI (device pointers in, tensors out) + autograd glue.
+
+Every function launches hand-written sm_100a kernels on the current CUDA stream; none has a
+CPU / eager fallback.
+"""
+import torch
+
+from . import _lib as L
+
+
+def _empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# rays (reference: utils/CommonUtils04.py:73-149)
+# ------------------------------------------------------------------------------------------------
+def camera_tables(intrinsics, c2w, device):
+    """Per-view tables the raygen kernel reads: K^-1 (torch.linalg.inv on the F host matrices, as the
+    reference inverts per-ray copies of them, CommonUtils04.py:87), c2w, (fx, fy)."""
+    k = torch.as_tensor(intrinsics, dtype=torch.float32).detach().cpu()
+    e = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()
+    k_inv = torch.linalg.inv(k).reshape(-1, 9)
+    focal = torch.stack([k[:, 0, 0], k[:, 1, 1]], 1)
+    return (k_inv.contiguous().to(device), e.reshape(-1, 16).contiguous().to(device), focal.contiguous().to(device))
+
+
+def raygen(pixel_id, tables, height, width, near, *, half_pixel, flip_x, ndc, viewdirs_from_ndc):
+    L.require_cuda(pixel_id)
+    k_inv, c2w, focal = tables
+    pid = pixel_id.to(torch.int32).contiguous()
+    R = pid.shape[0]
+    outs = [_empty((R, 3), pid) for _ in range(5)]
+    near = float(near)
+    near_f = torch.tensor(near, dtype=torch.float32).item()
+    two_near_f = torch.tensor(2.0 * near, dtype=torch.float32).item()
+    L.call('srf_raygen', L.ptr(pid), R, L.ptr(k_inv), L.ptr(c2w), L.ptr(focal), k_inv.shape[0], int(height), int(width),
+           near_f, two_near_f, int(half_pixel), int(flip_x), int(ndc), int(viewdirs_from_ndc),
+           *[L.ptr(o) for o in outs], L.stream_handle())
+    rays_o, rays_d, o_ndc, d_ndc, vd = outs
+    if not ndc:
+        o_ndc = d_ndc = None
+    return rays_o, rays_d, o_ndc, d_ndc, vd
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling (reference: models/SimpleNeRF17.py:330-417)
+# ------------------------------------------------------------------------------------------------
+def stratified_z(ladder, num_rays, jitter=None, philox_seed=None):
+    """ladder [S] device tensor; jitter [R,S] (the reference's CPU torch.rand draws, uploaded) for parity,
+    or philox_seed for the fast in-kernel RNG, or neither for eval."""
+    L.require_cuda(ladder, jitter)
+    ladder = L.f32c(ladder)
+    S = ladder.shape[0]
+    z = _empty((num_rays, S), ladder)
+    jitter = L.f32c(jitter)
+    if jitter is not None:
+        assert jitter.shape == (num_rays, S)
+    L.call('srf_stratified_z', L.ptr(ladder), S, num_rays, L.ptr(jitter), int(jitter is None and philox_seed is not None),
+           int(philox_seed or 0), L.ptr(z), L.stream_handle())
+    return z
+
+
+def sample_pdf_merge(z_coarse, weights, num_fine, u=None, philox_seed=0, return_indices=False):
+    """u: [R,N] tensor, [N] shared row (deterministic linspace) or None (in-kernel Philox).
+    Returns z_fine [R,S+N] (+ samples, below, above when return_indices)."""
+    L.require_cuda(z_coarse, weights, u)
+    z_coarse, weights, u = L.f32c(z_coarse), L.f32c(weights), L.f32c(u)
+    R, S = z_coarse.shape
+    assert weights.shape == (R, S)
+    stride = 0
+    if u is not None:
+        if u.dim() == 2:
+            assert u.shape == (R, num_fine)
+            stride = num_fine
+        else:
+            assert u.shape == (num_fine,)
+    z_fine = _empty((R, S + num_fine), z_coarse)
+    samples = below = above = None
+    if return_indices:
+        samples = _empty((R, num_fine), z_coarse)
+        below = _empty((R, num_fine), z_coarse, torch.int64)
+        above = _empty((R, num_fine), z_coarse, torch.int64)
+    L.call('srf_sample_pdf_merge', L.ptr(z_coarse), L.ptr(weights), L.ptr(u), stride, int(philox_seed), R, S, num_fine,
+           L.ptr(z_fine), L.ptr(samples), L.ptr(below), L.ptr(above), L.stream_handle())
+    if return_indices:
+        return z_fine, samples, below, above
+    return z_fine
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing (reference: models/SimpleNeRF17.py:486-539, models/SimpleTensoRF09.py:767-819)
+# ------------------------------------------------------------------------------------------------
+class _Composite(torch.autograd.Function):
+    """Outputs: alpha, visibility, weights, rgb_map, acc, depth, depth_var, depth_ndc, depth_var_ndc.
+    Differentiable w.r.t. sigma and rgb (depths and rays carry no gradient in the reference:
+    z_samples.detach(), SimpleNeRF17.py:368; frozen cameras)."""
+
+    @staticmethod
+    def forward(ctx, sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc, white_bkgd, distance_scale, per_sample):
+        L.require_cuda(sigma, rgb, z, rays_o, rays_d, rays_d_ndc)
+        sigma, rgb, z = L.f32c(sigma), L.f32c(rgb), L.f32c(z)
+        rays_o, rays_d, rays_d_ndc = L.f32c(rays_o), L.f32c(rays_d), L.f32c(rays_d_ndc)
+        R, S = sigma.shape
+        needs_grad = sigma.requires_grad or (rgb is not None and rgb.requires_grad)
+        keep = per_sample or needs_grad
+        weights = _empty((R, S), sigma)
+        alpha = _empty((R, S), sigma) if keep else None
+        vis = _empty((R, S), sigma) if keep else None
+        rgb_map = _empty((R, 3), sigma) if rgb is not None else None
+        acc, depth, depth_var = (_empty((R,), sigma) for _ in range(3))
+        depth_ndc = _empty((R,), sigma) if ndc else None
+        depth_var_ndc = _empty((R,), sigma) if ndc else None
+        L.call('srf_composite_fwd', L.ptr(sigma), L.ptr(rgb), L.ptr(z), L.ptr(rays_o), L.ptr(rays_d), L.ptr(rays_d_ndc),
+               R, S, int(ndc), int(white_bkgd), float(distance_scale), L.ptr(alpha), L.ptr(vis), L.ptr(weights),
+               L.ptr(rgb_map), L.ptr(acc), L.ptr(depth), L.ptr(depth_var), L.ptr(depth_ndc), L.ptr(depth_var_ndc),
+               L.stream_handle())
+        ctx.cfg = (bool(ndc), bool(white_bkgd), float(distance_scale), rgb is not None)
+        ctx.save_for_backward(sigma, rgb, z, vis, rays_o, rays_d, rays_d_ndc, acc, depth, depth_ndc)
+        outs = (alpha, vis, weights, rgb_map, acc, depth, depth_var, depth_ndc, depth_var_ndc)
+        ctx.mark_non_differentiable(*[t for t in (alpha, vis) if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_vis, g_weights, g_rgb, g_acc, g_depth, g_depth_var, g_depth_ndc, g_depth_var_ndc):
+        sigma, rgb, z, vis, rays_o, rays_d, rays_d_ndc, acc, depth, depth_ndc = ctx.saved_tensors
+        ndc, white, scale, has_rgb = ctx.cfg
+        R, S = sigma.shape
+        gs = [L.f32c(g) for g in (g_rgb, g_acc, g_depth, g_depth_ndc, g_depth_var, g_depth_var_ndc, g_weights)]
+        g_sigma = _empty((R, S), sigma)
+        want_rgb = has_rgb and ctx.needs_input_grad[1] and gs[0] is not None
+        g_rgb_s = _empty((R, S, 3), sigma) if want_rgb else None
+        L.call('srf_composite_bwd', L.ptr(sigma), L.ptr(rgb if gs[0] is not None else None), L.ptr(z), L.ptr(vis),
+               L.ptr(rays_o), L.ptr(rays_d), L.ptr(rays_d_ndc), L.ptr(acc), L.ptr(depth), L.ptr(depth_ndc),
+               *[L.ptr(g) for g in gs], R, S, int(ndc), int(white), scale, L.ptr(g_sigma), L.ptr(g_rgb_s),
+               L.stream_handle())
+        if has_rgb and ctx.needs_input_grad[1] and g_rgb_s is None:
+            g_rgb_s = torch.zeros((R, S, 3), dtype=torch.float32, device=sigma.device)
+        return g_sigma, g_rgb_s, None, None, None, None, None, None, None, None
+
+
+def composite(sigma, rgb, z, rays_o, rays_d, rays_d_ndc=None, *, ndc, white_bkgd=False, distance_scale=1.0,
+              per_sample=True):
+    """Returns a dict with the reference's volume_rendering keys.  sigma [R,S], rgb [R,S,3] or None."""
+    (alpha, vis, weights, rgb_map, acc, depth, depth_var, depth_ndc, depth_var_ndc) = _Composite.apply(
+        sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc, white_bkgd, distance_scale, per_sample)
+    out = {'acc': acc, 'weights': weights, 'depth': depth, 'depth_var': depth_var}
+    if rgb_map is not None:
+        out['rgb'] = rgb_map
+    if alpha is not None:
+        out['alpha'] = alpha
+        out['visibility'] = vis
+    if ndc:
+        out['depth_ndc'] = depth_ndc
+        out['depth_var_ndc'] = depth_var_ndc
+    return out
