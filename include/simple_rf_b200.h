@@ -76,6 +76,48 @@ int srf_composite_bwd(const float* sigma, const float* rgb, const float* z, cons
                       int num_samples, int ndc, int white_bkgd, float distance_scale, float* g_sigma,
                       float* g_rgb_samples, void* stream);
 
+/* Fused NeRF MLP forward (tcgen05 tensor cores, bf16 operands, fp32 accumulation in TMEM).
+ * Replaces src/models/SimpleNeRF17.py:213-215 (sample points), :581-613 (positional encoding), :419-484
+ * (run_network / batchify) and :696-785 (MLP.forward + heads) for one MLP.
+ *
+ * The MLP variant is described by a layer program (HOST pointer, copied at launch).  The A operand of a
+ * layer is a concatenation of 64-column shared-memory K-blocks ("regions"): 0 = point encoding E
+ * (3*(2*points_degree+1) columns, zero padded), 1..4 = the four 64-column blocks of the 256 hidden
+ * units, 5 = view-direction encoding V.  Weights: for every layer, for every K-block in program order,
+ * an image of n rows x 64 bf16 (row = output unit, column = input column of that block) in which the
+ * 16-byte unit u of row r is stored at unit position (u ^ (r & 7)) — the UMMA 128-byte swizzle — so one
+ * bulk copy lands it in shared memory ready for the tensor cores.  `side` is an fp32 table holding, per
+ * layer, the bias [n] and, for head layers, head weights [rows][n] followed by head biases [rows]. */
+typedef struct {
+  int32_t num_kblocks;
+  int32_t kblock_region[6];
+  int32_t kblock_ksteps[6];   /* 16-wide MMA K steps to issue for the block (1..4) */
+  int32_t n;                  /* 256 or 128 */
+  int32_t relu;
+  int32_t write_h;            /* keep the activation as the next layer's H blocks (n must be 256) */
+  int32_t head;               /* 0 none; 1 sigma = relu(w.h + b [+ noise]); 2 sigma + sigmoid rgb (4 rows); 3 sigmoid rgb (3 rows) */
+  int32_t bias_offset;        /* float offsets into `side` */
+  int32_t head_offset;
+  int64_t weight_offset;      /* byte offset into `weights` */
+} srf_mlp_layer;
+
+typedef struct {
+  int32_t num_layers;         /* <= 12 */
+  int32_t points_degree;      /* <= 10 */
+  int32_t views_degree;       /* <= 4, or < 0 when the variant has no view branch */
+  int32_t side_count;
+  srf_mlp_layer layers[12];
+} srf_mlp_program;
+
+/*   rays_o, rays_d [R,3]: origin / direction the sample points are built from (the NDC pair when ndc);
+ *   z [R,S];  view_dirs [R,3] (NULL iff views_degree < 0);  noise [R*S] nullable: the reference's
+ *   randn * raw_noise_std (SimpleNeRF17.py:739-741), added before the sigma ReLU;
+ *   sigma [R*S], rgb [R*S,3]: post-activation outputs. */
+int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
+                     const float* rays_d, const float* z, const float* view_dirs, const float* noise,
+                     int64_t num_rays, int num_samples, float* sigma, float* rgb, void* stream);
+int srf_nerf_mlp_program_bytes(void);   /* sizeof(srf_mlp_program) as compiled, for binding self-checks */
+
 #ifdef __cplusplus
 }
 #endif

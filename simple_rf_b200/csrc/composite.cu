@@ -294,12 +294,12 @@ SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float*
                               int ndc, int white_bkgd, float distance_scale, float* alpha, float* visibility,
                               float* weights, float* rgb_map, float* acc, float* depth, float* depth_var,
                               float* depth_ndc, float* depth_var_ndc, void* stream) {
+  if (num_rays == 0) return 0;
   SRF_REQUIRE(sigma && z && rays_d && weights && acc && depth && depth_var, "srf_composite_fwd", "null pointer");
   SRF_REQUIRE(!ndc || (rays_o && rays_d_ndc && depth_ndc && depth_var_ndc), "srf_composite_fwd",
               "ndc needs rays_o, rays_d_ndc, depth_ndc, depth_var_ndc");
   SRF_REQUIRE((rgb == nullptr) == (rgb_map == nullptr), "srf_composite_fwd", "rgb and rgb_map go together");
   SRF_REQUIRE(num_samples > 0 && num_rays >= 0, "srf_composite_fwd", "bad sizes");
-  if (num_rays == 0) return 0;
   CompositeFwd p{sigma, rgb, z, rays_o, rays_d, rays_d_ndc, alpha, visibility, weights, rgb_map, acc, depth,
                  depth_var, depth_ndc, depth_var_ndc, num_rays, num_samples, ndc, white_bkgd, distance_scale};
   const unsigned blocks = (unsigned)((num_rays + CMP_WARPS - 1) / CMP_WARPS);
@@ -314,11 +314,11 @@ SRF_API int srf_composite_bwd(const float* sigma, const float* rgb, const float*
                               const float* g_depth_var_ndc, const float* g_weights, int64_t num_rays,
                               int num_samples, int ndc, int white_bkgd, float distance_scale, float* g_sigma,
                               float* g_rgb_samples, void* stream) {
+  if (num_rays == 0) return 0;
   SRF_REQUIRE(sigma && z && visibility && rays_d && acc && depth && g_sigma, "srf_composite_bwd", "null pointer");
   SRF_REQUIRE(!ndc || (rays_o && rays_d_ndc && depth_ndc), "srf_composite_bwd", "ndc needs rays_o, rays_d_ndc, depth_ndc");
   SRF_REQUIRE(g_rgb_samples == nullptr || (rgb && g_rgb), "srf_composite_bwd", "g_rgb_samples needs rgb and g_rgb");
   SRF_REQUIRE(num_samples > 0 && num_rays >= 0, "srf_composite_bwd", "bad sizes");
-  if (num_rays == 0) return 0;
   CompositeBwd p{sigma, rgb, z, visibility, rays_o, rays_d, rays_d_ndc, acc, depth, depth_ndc, g_rgb, g_acc, g_depth,
                  g_depth_ndc, g_depth_var, g_depth_var_ndc, g_weights, g_sigma, g_rgb_samples, num_rays, num_samples,
                  ndc, white_bkgd, distance_scale};

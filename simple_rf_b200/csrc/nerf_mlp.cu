@@ -1,0 +1,387 @@
+// Fused NeRF MLP forward on tcgen05 tensor cores: sample points -> positional encoding -> 8x256 trunk
+// (+skip) -> sigma head -> feature -> view branch -> rgb, one persistent CTA per SM, 128 samples per tile.
+//
+// Replaces src/models/SimpleNeRF17.py:213-215 (pts = o + d z), :581-613 (PositionalEncoder), :419-484
+// (run_network / batchify chunk loop) and :696-785 (MLP.forward and both heads), for the three shipped
+// variants (main, points_augmentation with the degree-3 sigma input, views_augmentation with the 4-wide
+// head); the variant is a small "layer program" passed by the host (srf_mlp_layer in the header).
+//
+// Data flow per tile (nothing between the ray data and sigma/rgb touches HBM):
+//   epilogue warps: points + encoding -> bf16 A-operand K-blocks E (points) / V (views) in shared memory
+//   producer warp : streams pre-packed bf16 weight K-blocks (128B-swizzled images) through a ring with
+//                   cp.async.bulk + mbarrier complete_tx (TMA bulk engine)
+//   MMA thread    : tcgen05.mma M=128, N=256|128, K=16 from shared memory, fp32 accumulators in TMEM
+//                   (two 256-column buffers, alternating per layer)
+//   epilogue warps: tcgen05.ld -> +bias, ReLU -> bf16 -> swizzled st.shared as the next layer's A operand,
+//                   signalled per 64-column K-block so the next layer's MMAs start while the rest of the
+//                   epilogue is still running; the 1/3/4-wide heads are thread-local dot products.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace srf {
+
+constexpr int MLP_MAX_LAYERS = 12;
+constexpr int MLP_MAX_KBLOCKS = 6;
+
+struct MlpLayer {              // mirrors srf_mlp_layer in include/simple_rf_b200.h
+  int32_t num_kblocks;
+  int32_t kblock_region[MLP_MAX_KBLOCKS];   // 0 = E, 1..4 = H0..H3, 5 = V
+  int32_t kblock_ksteps[MLP_MAX_KBLOCKS];   // MMA K-steps (16 wide) issued for that block, 1..4
+  int32_t n;                                // 256 or 128
+  int32_t relu;                             // apply ReLU in the epilogue
+  int32_t write_h;                          // store the activation as the next A operand
+  int32_t head;                             // 0 none, 1 sigma (1 row), 2 sigma+rgb (4 rows), 3 rgb (3 rows)
+  int32_t bias_offset;                      // float offset in the side table
+  int32_t head_offset;                      // float offset of head weights [rows][n] followed by head bias [rows]
+  int64_t weight_offset;                    // byte offset of the layer's packed K-blocks in the blob
+};
+
+struct MlpProgram {
+  int32_t num_layers;
+  int32_t points_degree;        // positional-encoding degree of the points (<= 10)
+  int32_t views_degree;         // of the view directions (<= 4); < 0: no view branch
+  int32_t side_count;           // floats in the side table
+  MlpLayer layers[MLP_MAX_LAYERS];
+};
+
+struct MlpArgs {
+  const uint8_t* weights;       // packed bf16 blob
+  const float* side;            // fp32 side table: biases, head weights, head biases
+  const float* rays_o;          // [R,3]   origin used for the sample points (NDC origin when ndc)
+  const float* rays_d;          // [R,3]
+  const float* z;               // [R,S]
+  const float* view_dirs;       // [R,3] or nullptr
+  const float* noise;           // [R*S] or nullptr: added to raw sigma before the ReLU
+  float* sigma;                 // [R*S]
+  float* rgb;                   // [R*S,3]
+  long long total;              // R*S
+  int S;
+  int num_tiles;
+};
+
+constexpr int MLP_THREADS = 384;          // warp 0 producer, warp 1 MMA, warps 2-3 idle, warps 4-11 epilogue
+constexpr int EPI_WARP0 = 4;
+constexpr int KBLOCK_BYTES = 128 * 128;   // 128 rows x 64 bf16
+constexpr int STAGE_BYTES = 256 * 128;    // weight K-block for N = 256
+constexpr int NUM_STAGES = 3;
+constexpr int MAX_SIDE = 4608;            // floats
+
+struct alignas(1024) MlpSmem {
+  uint8_t a[6][KBLOCK_BYTES];             // E, H0..H3, V
+  uint8_t w[NUM_STAGES][STAGE_BYTES];
+  float side[MAX_SIDE];
+  float part[2][128][4];                  // head partial sums handed from column-half 1 to column-half 0
+  uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
+  uint64_t a_ready[6];                    // per A region: written and visible to the async proxy
+  uint64_t d_full[2];                     // accumulator buffer complete
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// sin/cos of 2^k x for k = k0 .. k0+count-1 by angle doubling from one accurate sincosf
+template <typename F>
+__device__ __forceinline__ void encode_octaves(float x, int k0, int count, F&& emit) {
+  float s, c;
+  sincosf(ldexpf(x, k0), &s, &c);
+  for (int k = 0; k < count; ++k) {
+    emit(k0 + k, s, c);
+    const float s2 = 2.f * s * c;
+    c = 1.f - 2.f * s * s;
+    s = s2;
+  }
+}
+
+__device__ __forceinline__ void store_bf16(uint8_t* block, int row, int col, float v) {
+  const uint32_t off = ptx::sw128_offset(row, col >> 3) + ((col & 7) << 1);
+  *reinterpret_cast<__nv_bfloat16*>(block + off) = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __grid_constant__ MlpProgram prog,
+                                                                      const MlpArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  MlpSmem& sm = *reinterpret_cast<MlpSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
+    for (int r = 0; r < 6; ++r) ptx::mbar_init(&sm.a_ready[r], 8);
+    ptx::mbar_init(&sm.d_full[0], 1);
+    ptx::mbar_init(&sm.d_full[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const int my_tiles = (args.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 0; l < prog.num_layers; ++l) {
+          const MlpLayer& L = prog.layers[l];
+          const uint32_t bytes = (uint32_t)L.n * 128u;
+          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
+            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
+            ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
+            ptx::mbar_arrive_expect_tx(&sm.w_full[st], bytes);
+            ptx::bulk_g2s(sm.w[st], args.weights + L.weight_offset + (size_t)kb * bytes, bytes, &sm.w_full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t it = 0, layer_count = 0;
+      uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
+      uint32_t a_seen = 0;               // bit r: region r already acquired for its current contents
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
+          const MlpLayer& L = prog.layers[l];
+          const uint32_t d_addr = tmem + (layer_count & 1) * 256;
+          const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
+          bool first = true;
+          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
+            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
+            const int reg = L.kblock_region[kb];
+            if (!((a_seen >> reg) & 1)) {
+              ptx::mbar_wait(&sm.a_ready[reg], (a_phase >> reg) & 1);
+              a_phase ^= 1u << reg;
+              a_seen |= 1u << reg;
+            }
+            ptx::mbar_wait(&sm.w_full[st], ph);
+            ptx::tc_fence_after();
+            const uint32_t a_base = ptx::smem_u32(sm.a[reg]);
+            const uint32_t b_base = ptx::smem_u32(sm.w[st]);
+            for (int k = 0; k < L.kblock_ksteps[kb]; ++k) {
+              ptx::umma_bf16(d_addr, ptx::make_sw128_desc(a_base + k * 32), ptx::make_sw128_desc(b_base + k * 32), idesc,
+                             first ? 0u : 1u);
+              first = false;
+            }
+            ptx::umma_commit(&sm.w_empty[st]);
+          }
+          ptx::umma_commit(&sm.d_full[layer_count & 1]);
+          // the epilogue of this layer rewrites H (write_h) - its blocks must be re-acquired
+          if (L.write_h) a_seen &= ~0x1Eu;
+        }
+        a_seen = 0;                      // next tile: E and V are rewritten as well
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ encoding + epilogue warps
+    const int ew = warp - EPI_WARP0;
+    const int quarter = ew & 3;          // TMEM lane quarter this warp may read
+    const int half = ew >> 2;            // column half of every 64-wide block this warp owns
+    const int row = quarter * 32 + lane;
+    uint32_t layer_count = 0;
+    uint32_t d_phase = 0;                // bit b: parity to wait for on d_full[b]
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long m = tile * 128 + row;
+      const bool valid = m < args.total;
+      // ---- sample point and encodings (split between the two column halves by octave)
+      {
+        float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
+        if (valid) {
+          const long long r = m / args.S;
+          const float zz = args.z[m];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(args.rays_o[r * 3 + c], __fmul_rn(args.rays_d[r * 3 + c], zz));
+          if (args.view_dirs != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) vd[c] = args.view_dirs[r * 3 + c];
+          }
+        }
+        uint8_t* E = sm.a[0];
+        const int deg = prog.points_degree;
+        const int split = (deg + 1) / 2;                 // octaves [0, split) by half 0, the rest by half 1
+        if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) store_bf16(E, row, c, p[c]);
+        } else {
+          for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
+        }
+        const int k0 = half == 0 ? 0 : split;
+        const int cnt = half == 0 ? split : deg - split;
+        if (cnt > 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            encode_octaves(p[c], k0, cnt, [&](int k, float s, float co) {
+              store_bf16(E, row, 3 + 6 * k + c, s);
+              store_bf16(E, row, 6 + 6 * k + c, co);
+            });
+        }
+        if (prog.views_degree >= 0) {
+          uint8_t* V = sm.a[5];
+          const int vdeg = prog.views_degree;
+          if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              store_bf16(V, row, c, vd[c]);
+              if (vdeg > 0)
+                encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
+                  store_bf16(V, row, 3 + 6 * k + c, s);
+                  store_bf16(V, row, 6 + 6 * k + c, co);
+                });
+            }
+          } else {
+            for (int c = 3 + 6 * vdeg; c < 64; ++c) store_bf16(V, row, c, 0.f);
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&sm.a_ready[0]);
+          if (prog.views_degree >= 0) ptx::mbar_arrive(&sm.a_ready[5]);
+        }
+      }
+      // ---- layer epilogues
+      for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
+        const MlpLayer& L = prog.layers[l];
+        const uint32_t buf = layer_count & 1;
+        ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
+        d_phase ^= 1u << buf;
+        ptx::tc_fence_after();
+        const float* bias = sm.side + L.bias_offset;
+        const int head_rows = L.head == 1 ? 1 : (L.head == 2 ? 4 : (L.head == 3 ? 3 : 0));
+        const float* hw = sm.side + L.head_offset;
+        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int nblocks = L.n >> 6;
+        for (int kb = 0; kb < nblocks; ++kb) {
+          const int col0 = kb * 64 + half * 32;
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + col0, v);
+          ptx::tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + bias[col0 + j];
+            f[j] = L.relu ? fmaxf(x, 0.f) : x;
+          }
+          if (head_rows > 0) {
+            for (int hr = 0; hr < head_rows; ++hr) {
+              const float* wr = hw + hr * L.n + col0;
+              float a = hacc[hr];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a = fmaf(f[j], wr[j], a);
+              hacc[hr] = a;
+            }
+          }
+          if (L.write_h) {
+            uint8_t* H = sm.a[1 + kb];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 q;
+              q.x = ptx::pack_bf16(f[u * 8 + 0], f[u * 8 + 1]);
+              q.y = ptx::pack_bf16(f[u * 8 + 2], f[u * 8 + 3]);
+              q.z = ptx::pack_bf16(f[u * 8 + 4], f[u * 8 + 5]);
+              q.w = ptx::pack_bf16(f[u * 8 + 6], f[u * 8 + 7]);
+              *reinterpret_cast<uint4*>(H + ptx::sw128_offset(row, half * 4 + u)) = q;
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
+          }
+        }
+        ptx::tc_fence_before();
+        if (head_rows > 0) {
+          const int slot = L.head == 3 ? 1 : 0;
+          if (half == 1) {
+#pragma unroll
+            for (int hr = 0; hr < 4; ++hr) sm.part[slot][row][hr] = hacc[hr];
+          }
+          epi_bar_sync();
+          if (half == 0 && valid) {
+            const float* hb = hw + head_rows * L.n;
+            float o[4];
+#pragma unroll
+            for (int hr = 0; hr < 4; ++hr) o[hr] = hacc[hr] + sm.part[slot][row][hr] + (hr < head_rows ? hb[hr] : 0.f);
+            if (L.head == 1 || L.head == 2) {
+              float s = o[0];
+              if (args.noise != nullptr) s += args.noise[m];
+              args.sigma[m] = fmaxf(s, 0.f);
+            }
+            if (L.head == 2 || L.head == 3) {
+              const int b = L.head == 2 ? 1 : 0;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) args.rgb[m * 3 + c] = 1.f / (1.f + expf(-o[b + c]));
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace srf
+
+using namespace srf;
+
+SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
+                             const float* rays_d, const float* z, const float* view_dirs, const float* noise,
+                             int64_t num_rays, int num_samples, float* sigma, float* rgb, void* stream) {
+  if (num_rays == 0) return 0;
+  SRF_REQUIRE(program && weights && side && rays_o && rays_d && z && sigma && rgb, "srf_nerf_mlp_fwd", "null pointer");
+  MlpProgram prog = *reinterpret_cast<const MlpProgram*>(program);
+  SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= MLP_MAX_LAYERS, "srf_nerf_mlp_fwd", "bad layer count");
+  SRF_REQUIRE(prog.points_degree >= 0 && prog.points_degree <= 10 && prog.views_degree <= 4, "srf_nerf_mlp_fwd",
+              "encoding degree out of range (points <= 10, views <= 4)");
+  SRF_REQUIRE(prog.side_count <= MAX_SIDE, "srf_nerf_mlp_fwd", "side table too large");
+  SRF_REQUIRE(prog.views_degree < 0 || view_dirs != nullptr, "srf_nerf_mlp_fwd", "view_dirs required by the program");
+  int used_any = 0;
+  for (int l = 0; l < prog.num_layers; ++l) {
+    const MlpLayer& L = prog.layers[l];
+    SRF_REQUIRE(L.n == 256 || L.n == 128, "srf_nerf_mlp_fwd", "layer width must be 128 or 256");
+    SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= MLP_MAX_KBLOCKS, "srf_nerf_mlp_fwd", "bad K-block count");
+    SRF_REQUIRE(!L.write_h || L.n == 256, "srf_nerf_mlp_fwd", "hidden activations are 256 wide");
+    int used = 0;
+    for (int kb = 0; kb < L.num_kblocks; ++kb) {
+      SRF_REQUIRE(L.kblock_region[kb] >= 0 && L.kblock_region[kb] <= 5 && L.kblock_ksteps[kb] >= 1 &&
+                      L.kblock_ksteps[kb] <= 4, "srf_nerf_mlp_fwd", "bad K-block descriptor");
+      SRF_REQUIRE(!((used >> L.kblock_region[kb]) & 1), "srf_nerf_mlp_fwd", "a region may appear once per layer");
+      used |= 1 << L.kblock_region[kb];
+    }
+    used_any |= used;
+    // barrier generations: whatever an epilogue writes must be consumed in full by the following layer
+    if (l == 0) SRF_REQUIRE(used & 1, "srf_nerf_mlp_fwd", "layer 0 must read the point encoding (region 0)");
+    if (l > 0 && prog.layers[l - 1].write_h)
+      SRF_REQUIRE((used & 0x1E) == 0x1E, "srf_nerf_mlp_fwd", "a layer after write_h must read H0..H3");
+    if (l > 0 && !prog.layers[l - 1].write_h)
+      SRF_REQUIRE((used & 0x1E) == 0, "srf_nerf_mlp_fwd", "H is stale after a layer without write_h");
+    SRF_REQUIRE(!(L.write_h && l == prog.num_layers - 1), "srf_nerf_mlp_fwd", "last layer cannot write H");
+  }
+  SRF_REQUIRE((prog.views_degree >= 0) == (((used_any >> 5) & 1) != 0), "srf_nerf_mlp_fwd",
+              "view encoding (region 5) must be used iff views_degree >= 0");
+  MlpArgs a;
+  a.weights = reinterpret_cast<const uint8_t*>(weights);
+  a.side = side; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.view_dirs = view_dirs; a.noise = noise;
+  a.sigma = sigma; a.rgb = rgb;
+  a.total = (long long)num_rays * num_samples;
+  a.S = num_samples;
+  a.num_tiles = (int)((a.total + 127) / 128);
+  const size_t smem = sizeof(MlpSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("srf_nerf_mlp_fwd", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+  nerf_mlp_fwd_kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, a);
+  return check_launch("srf_nerf_mlp_fwd");
+}
+
+SRF_API int srf_nerf_mlp_program_bytes(void) { return (int)sizeof(MlpProgram); }

@@ -317,10 +317,10 @@ SRF_API int srf_raygen(const int32_t* pixel_id, int64_t num_rays, const float* k
                        const float* focal, int num_views, int height, int width, float near, float two_near,
                        int half_pixel, int flip_x, int ndc, int viewdirs_from_ndc, float* rays_o, float* rays_d,
                        float* rays_o_ndc, float* rays_d_ndc, float* view_dirs, void* stream) {
+  if (num_rays == 0) return 0;
   SRF_REQUIRE(pixel_id && k_inv && c2w && focal && rays_o && rays_d && view_dirs, "srf_raygen", "null pointer");
   SRF_REQUIRE(!ndc || (rays_o_ndc && rays_d_ndc), "srf_raygen", "ndc outputs required when ndc != 0");
   SRF_REQUIRE(num_views > 0 && num_rays >= 0, "srf_raygen", "bad sizes");
-  if (num_rays == 0) return 0;
   RaygenParams p{pixel_id, k_inv, c2w, focal, rays_o, rays_d, rays_o_ndc, rays_d_ndc, view_dirs, num_rays, num_views,
                  (float)height, (float)width, near, two_near, half_pixel, flip_x, ndc, viewdirs_from_ndc};
   const unsigned blocks = (unsigned)((num_rays + RAYGEN_THREADS - 1) / RAYGEN_THREADS);
@@ -330,10 +330,10 @@ SRF_API int srf_raygen(const int32_t* pixel_id, int64_t num_rays, const float* k
 
 SRF_API int srf_stratified_z(const float* ladder, int num_samples, int64_t num_rays, const float* jitter,
                              int use_philox, uint64_t seed, float* z, void* stream) {
+  if (num_rays == 0) return 0;
   SRF_REQUIRE(ladder && z, "srf_stratified_z", "null pointer");
   SRF_REQUIRE(num_samples > 0 && num_rays >= 0, "srf_stratified_z", "bad sizes");
   const long long total = (long long)num_rays * num_samples;
-  if (total == 0) return 0;
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)sm_count() * 16;
@@ -346,9 +346,9 @@ SRF_API int srf_stratified_z(const float* ladder, int num_samples, int64_t num_r
 SRF_API int srf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int64_t u_row_stride,
                                  uint64_t seed, int64_t num_rays, int num_coarse, int num_fine, float* z_fine,
                                  float* samples, int64_t* below, int64_t* above, void* stream) {
+  if (num_rays == 0) return 0;
   SRF_REQUIRE(z_coarse && weights && z_fine, "srf_sample_pdf_merge", "null pointer");
   SRF_REQUIRE(num_coarse >= 3 && num_fine >= 1 && num_rays >= 0, "srf_sample_pdf_merge", "need S >= 3, N >= 1");
-  if (num_rays == 0) return 0;
   int npad = 2;
   while (npad < num_coarse + num_fine) npad <<= 1;
   const size_t smem = (size_t)PDF_WARPS * (3 * num_coarse + npad) * sizeof(float);

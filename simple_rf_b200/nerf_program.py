@@ -1,0 +1,216 @@
+"""Host side of the fused NeRF MLP kernel: layer program + packed-weight cache for one MLP variant.
+
+The reference MLP (models/SimpleNeRF17.py:616-785) is described to the kernel as a list of layers whose
+A operand is a concatenation of 64-column shared-memory K-blocks:
+    region 0 = E  point encoding (63 columns + zero pad)      regions 1..4 = H0..H3 (256 hidden units)
+    region 5 = V  view-direction encoding (27 columns + zero pad)
+`nn.Linear` weights stay the fp32 `nn.Parameter`s the optimiser and checkpoints see; the bf16,
+128-byte-swizzled K-block images the tensor cores read are a derived cache, rebuilt by one gather
+whenever the parameters change (PackedMLP.refresh).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MAX_LAYERS = 12
+MAX_KBLOCKS = 6
+
+
+class MlpLayer(ctypes.Structure):
+    _fields_ = [('num_kblocks', ctypes.c_int32), ('kblock_region', ctypes.c_int32 * MAX_KBLOCKS),
+                ('kblock_ksteps', ctypes.c_int32 * MAX_KBLOCKS), ('n', ctypes.c_int32), ('relu', ctypes.c_int32),
+                ('write_h', ctypes.c_int32), ('head', ctypes.c_int32), ('bias_offset', ctypes.c_int32),
+                ('head_offset', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
+
+
+class MlpProgram(ctypes.Structure):
+    _fields_ = [('num_layers', ctypes.c_int32), ('points_degree', ctypes.c_int32), ('views_degree', ctypes.c_int32),
+                ('side_count', ctypes.c_int32), ('layers', MlpLayer * MAX_LAYERS)]
+
+
+def _enc_width(degree):
+    return 3 * (2 * degree + 1)
+
+
+class PackedMLP:
+    """Program + gather indices for one reference MLP (any of the three shipped variants).
+
+    `param_names` is the flat parameter order the gather indices refer to; `refresh(params)` takes the
+    live fp32 tensors (dict name -> tensor on the device) and rebuilds the packed blob + side table."""
+
+    def __init__(self, mlp_configs, width=256, views_width=128, depth=8, skips=(4,)):
+        cfg = mlp_configs
+        assert width == 256 and cfg['points_net_width'] == 256, 'kernel is specialised for 256-wide trunks'
+        assert cfg['points_net_depth'] == depth
+        self.cfg = cfg
+        self.pdeg = cfg['points_positional_encoding_degree']
+        full = _enc_width(self.pdeg)
+        assert full <= 63
+        self.use_views = bool(cfg['use_view_dirs'])
+        self.view_dep = bool(cfg['view_dependent_rgb'])
+        assert self.use_views == self.view_dep, 'view dirs are only consumed by the view-dependent head'
+        self.vdeg = cfg['views_positional_encoding_degree'] if self.use_views else -1
+        if self.use_views:
+            assert _enc_width(self.vdeg) <= 32 and cfg['views_net_depth'] == 1 and cfg['views_net_width'] == views_width
+        pts_in = full
+        if 'points_sigma_positional_encoding_degree' in cfg:
+            pts_in = _enc_width(cfg['points_sigma_positional_encoding_degree'])
+        extra = full - pts_in                      # encoding columns routed to the view branch instead
+
+        # ---- flat parameter order
+        names = []
+        for i in range(depth):
+            names += [f'pts_linears.{i}.weight', f'pts_linears.{i}.bias']
+        names += ['pts_output_linear.weight', 'pts_output_linear.bias']
+        if self.view_dep:
+            names += ['feature_linear.weight', 'feature_linear.bias', 'views_linears.0.weight', 'views_linears.0.bias',
+                      'views_output_linear.weight', 'views_output_linear.bias']
+        self.param_names = names
+        shapes = {}
+        for i in range(depth):
+            k = pts_in if i == 0 else (width + pts_in if (i - 1) in skips else width)
+            shapes[f'pts_linears.{i}.weight'] = (width, k)
+            shapes[f'pts_linears.{i}.bias'] = (width,)
+        shapes['pts_output_linear.weight'] = (1 if self.view_dep else 4, width)
+        shapes['pts_output_linear.bias'] = (1 if self.view_dep else 4,)
+        if self.view_dep:
+            shapes['feature_linear.weight'] = (width, width)
+            shapes['feature_linear.bias'] = (width,)
+            vin = width + extra + _enc_width(self.vdeg)
+            shapes['views_linears.0.weight'] = (views_width, vin)
+            shapes['views_linears.0.bias'] = (views_width,)
+            shapes['views_output_linear.weight'] = (3, views_width)
+            shapes['views_output_linear.bias'] = (3,)
+        self.shapes = shapes
+        offs, o = {}, 0
+        for n in names:
+            offs[n] = o
+            o += int(np.prod(shapes[n]))
+        self.flat_size = o
+        zero = o                                   # index of the appended zero element
+
+        def widx(name, row, col):
+            return offs[name] + row * shapes[name][1] + col
+
+        # column maps: for a layer, a list of K-blocks; each K-block = (region, 64 source columns or -1)
+        def enc_block(ncols, src0=0, first=0):
+            """E block exposing encoding columns [first, first+ncols) as weight columns src0.."""
+            cols = [-1] * 64
+            for j in range(ncols):
+                cols[first + j] = src0 + j
+            return (0, cols)
+
+        def h_blocks(src0):
+            return [(1 + b, [src0 + b * 64 + j for j in range(64)]) for b in range(4)]
+
+        layers = []                                # (weight name, n, kblocks, relu, write_h, head)
+        for i in range(depth):
+            name = f'pts_linears.{i}.weight'
+            if i == 0:
+                kbs = [enc_block(pts_in)]
+            elif (i - 1) in skips:
+                kbs = [enc_block(pts_in)] + h_blocks(pts_in)       # cat([input_pts, h]) (:732-733)
+            else:
+                kbs = h_blocks(0)
+            last = i == depth - 1
+            head = 0
+            if last:
+                head = 1 if self.view_dep else 2
+            layers.append((name, width, kbs, 1, 0 if (last and not self.view_dep) else 1, head))
+        if self.view_dep:
+            layers.append(('feature_linear.weight', width, h_blocks(0), 0, 1, 0))
+            kbs = h_blocks(0)
+            if extra > 0:                                           # [feature | enc[pts_in:] | enc_view] (:703, :765)
+                kbs.append(enc_block(extra, src0=width, first=pts_in))
+            vcols = [-1] * 64
+            for j in range(_enc_width(self.vdeg)):
+                vcols[j] = width + extra + j
+            kbs.append((5, vcols))
+            layers.append(('views_linears.0.weight', views_width, kbs, 1, 0, 3))
+        assert len(layers) <= MAX_LAYERS
+
+        prog = MlpProgram()
+        prog.num_layers = len(layers)
+        prog.points_degree = self.pdeg
+        prog.views_degree = self.vdeg
+        gather = []
+        side = []
+        woff = 0
+        rows_sw = {}
+        for li, (name, n, kbs, relu, write_h, head) in enumerate(layers):
+            Lr = prog.layers[li]
+            Lr.num_kblocks = len(kbs)
+            Lr.n, Lr.relu, Lr.write_h, Lr.head = n, relu, write_h, head
+            Lr.weight_offset = woff * 2
+            for bi, (region, cols) in enumerate(kbs):
+                Lr.kblock_region[bi] = region
+                used = max(j for j, c in enumerate(cols) if c >= 0) + 1
+                Lr.kblock_ksteps[bi] = (used + 15) // 16
+                cols = np.asarray(cols)
+                if n not in rows_sw:
+                    e = np.arange(n * 64)
+                    r = e // 64
+                    unit = (e % 64) // 8
+                    rows_sw[n] = (r, ((unit ^ (r & 7)) * 8) + e % 8)
+                r, c = rows_sw[n]
+                src = cols[c]
+                idx = np.where(src >= 0, offs[name] + r * shapes[name][1] + np.maximum(src, 0), zero)
+                gather.append(idx)
+                woff += n * 64
+            bname = name.replace('.weight', '.bias')
+            Lr.bias_offset = len(side)
+            side += [offs[bname] + j for j in range(n)]
+            if head:
+                hname = 'views_output_linear' if head == 3 else 'pts_output_linear'
+                rows = shapes[f'{hname}.weight'][0]
+                Lr.head_offset = len(side)
+                side += [widx(f'{hname}.weight', r_, c_) for r_ in range(rows) for c_ in range(n)]
+                side += [offs[f'{hname}.bias'] + r_ for r_ in range(rows)]
+        prog.side_count = len(side)
+        self.program = prog
+        self.blob_elems = woff
+        self._gather_np = np.concatenate(gather).astype(np.int64)
+        self._side_np = np.asarray(side, dtype=np.int64)
+        self._dev = None
+        self.blob = None
+        self.side = None
+        macs = 0
+        for name, n, kbs, *_ in layers:
+            macs += shapes[name][0] * shapes[name][1]
+        macs += shapes['pts_output_linear.weight'][0] * width + (3 * views_width if self.view_dep else 0)
+        self.macs_per_sample = macs          # unpadded, as SURVEY.md §8d counts them
+
+    def refresh(self, params):
+        """params: dict name -> fp32 CUDA tensor (the live nn.Parameters).  Rebuilds blob + side table."""
+        dev = params[self.param_names[0]].device
+        L.require_cuda(params[self.param_names[0]])
+        if self._dev != dev:
+            self._gather = torch.from_numpy(self._gather_np).to(dev)
+            self._side_idx = torch.from_numpy(self._side_np).to(dev)
+            self._dev = dev
+        flat = torch.cat([params[n].detach().reshape(-1).float() for n in self.param_names] +
+                         [torch.zeros(1, dtype=torch.float32, device=dev)])
+        assert flat.numel() == self.flat_size + 1, 'parameter shapes do not match the MLP config'
+        self.blob = flat[self._gather].to(torch.bfloat16).contiguous()
+        self.side = flat[self._side_idx].contiguous()
+        return self
+
+    def forward(self, rays_o, rays_d, z, view_dirs=None, noise=None):
+        """rays_o/rays_d [R,3] (the origin/direction the sample points are built from), z [R,S].
+        Returns sigma [R,S,1], rgb [R,S,3] (post-activation, as MLP.forward returns them)."""
+        assert self.blob is not None, 'call refresh(params) first'
+        L.require_cuda(rays_o, rays_d, z, view_dirs, noise)
+        rays_o, rays_d, z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
+        view_dirs, noise = L.f32c(view_dirs), L.f32c(noise)
+        R, S = z.shape
+        sigma = torch.empty((R, S, 1), dtype=torch.float32, device=z.device)
+        rgb = torch.empty((R, S, 3), dtype=torch.float32, device=z.device)
+        if self.use_views and view_dirs is None:
+            raise L.SimpleRFNativeError('this MLP variant needs view_dirs')
+        L.call('srf_nerf_mlp_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
+               L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
+               L.ptr(sigma), L.ptr(rgb), L.stream_handle())
+        return sigma, rgb

@@ -1,0 +1,84 @@
+"""GPU parity: fused tcgen05 NeRF MLP (points -> encoding -> trunk -> heads) against the fp32 oracle.
+
+The tensor-core path rounds operands (activations, weights) to bf16 and accumulates in fp32, so this is the
+"stated looser tolerance for the bf16 MLP" of the parity ledger; the bounds asserted here are what was
+measured on default-initialised weights (+2 sigma bias), with head-room, and are tightened as measured."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import fixtures as FX
+from oracle import nerf_mlp as M
+from oracle import rays as RY
+from oracle import sampling as SP
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+SIGMA_TOL = 5e-3      # abs on raw sigma of O(1..5) at init (bf16 operands, fp32 accumulate)
+RGB_TOL = 3e-3        # abs on sigmoid outputs
+
+
+def _variants(golden_configs):
+    configs, mc = golden_configs('nerf')
+    m = configs['model']
+    return configs, mc, {'main': m['coarse_model'], 'points_augmentation': m['augmentations'][0]['coarse_model'],
+                         'views_augmentation': m['augmentations'][1]['coarse_model']}
+
+
+def test_program_struct_matches_c_abi():
+    from simple_rf_b200 import _lib, nerf_program
+    assert _lib.load().srf_nerf_mlp_program_bytes() == ctypes.sizeof(nerf_program.MlpProgram)
+
+
+@pytest.mark.parametrize('variant', ['main', 'points_augmentation', 'views_augmentation'])
+@pytest.mark.parametrize('R,S', [(37, 64), (300, 192), (1, 1)])
+def test_mlp_forward_vs_oracle(golden_configs, variant, R, S):
+    from simple_rf_b200 import nerf_program
+    configs, mc, variants = _variants(golden_configs)
+    cfg = variants[variant]
+    g = torch.Generator().manual_seed(hash(variant) % 1000 + R)
+    params = M.init_mlp_params(cfg, g)
+    params['pts_output_linear.bias'][0] += 2.0
+    K = torch.tensor(mc['intrinsics']); E = torch.tensor(mc['extrinsics'])
+    h, w = mc['resolution']
+    pid = FX.random_pixels(R, K.shape[0], h, w, seed=R)
+    ro, rd = RY.camera_rays(pid, K, E, half_pixel=False, flip_x=False)
+    img = pid[:, 0].long()
+    on, dn = RY.ndc_rays(ro, rd, h, w, K[img, 0, 0], K[img, 1, 1], mc['near'])
+    vd = RY.view_dirs(rd)
+    z = SP.stratified_depths(SP.coarse_depths(S, 0., 1.), R, torch.rand(R, S, generator=g))
+    noise = torch.randn(R * S, 1, generator=g)
+    pts = (on[:, None, :] + dn[:, None, :] * z[..., None]).reshape(-1, 3)
+    vflat = vd[:, None].expand(R, S, 3).reshape(-1, 3)
+    ref = M.mlp_forward(params, cfg, pts, vflat if cfg['use_view_dirs'] else None, noise)
+
+    packed = nerf_program.PackedMLP(cfg).refresh({k: v.to(DEV) for k, v in params.items()})
+    sigma, rgb = packed.forward(on.to(DEV), dn.to(DEV), z.to(DEV), vd.to(DEV), noise.to(DEV))
+    torch.cuda.synchronize()
+    es = (sigma.cpu().reshape(-1, 1) - ref['sigma']).abs().max().item()
+    er = (rgb.cpu().reshape(-1, 3) - ref['rgb']).abs().max().item()
+    print(f'{variant} R={R} S={S}: max|d sigma|={es:.2e} max|d rgb|={er:.2e} (sigma max {ref["sigma"].max():.2f})')
+    assert es <= SIGMA_TOL * max(1.0, ref['sigma'].abs().max().item()), es
+    assert er <= RGB_TOL, er
+
+
+def test_mlp_is_row_independent_at_scale(golden_configs):
+    """Size-independent property at frame scale: a sample's output does not depend on which tile / CTA
+    processed it (permuting rays permutes outputs bit-exactly)."""
+    from simple_rf_b200 import nerf_program
+    configs, mc, variants = _variants(golden_configs)
+    cfg = variants['main']
+    g = torch.Generator().manual_seed(5)
+    params = {k: v.to(DEV) for k, v in M.init_mlp_params(cfg, g).items()}
+    packed = nerf_program.PackedMLP(cfg).refresh(params)
+    R, S = 20000, 64
+    o = torch.rand(R, 3, generator=g).to(DEV) - 0.5
+    d = torch.rand(R, 3, generator=g).to(DEV) - 0.5
+    vd = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).to(DEV)
+    z = torch.rand(R, S, generator=g).to(DEV)
+    perm = torch.randperm(R, generator=g).to(DEV)
+    s1, c1 = packed.forward(o, d, z, vd)
+    s2, c2 = packed.forward(o[perm], d[perm], z[perm], vd[perm])
+    assert torch.equal(s1[perm], s2) and torch.equal(c1[perm], c2)
+    assert torch.isfinite(s1).all() and torch.isfinite(c1).all()
