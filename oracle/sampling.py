@@ -67,6 +67,7 @@ def fine_depths(z_coarse, weights_coarse, u):
     Returns (z_fine [R,S+N], samples, below, above)."""
     mids = .5 * (z_coarse[..., 1:] + z_coarse[..., :-1])
     samples, below, above, _ = inverse_cdf(mids, weights_coarse[..., 1:-1], u)
+    samples = samples.detach()                                   # SimpleNeRF17.py:368
     z_fine, _ = torch.sort(torch.cat([z_coarse, samples], -1), -1)
     return z_fine, samples, below, above
 

@@ -1,0 +1,18 @@
+"""Make the drop-in classes discoverable by the reference's UNMODIFIED factory.
+
+src/models/ModelFactory02.py:10-22 imports `models.<name>` and instantiates the class called `<name>` minus
+its two-digit suffix.  `install()` appends a directory of one-line shim modules (`SimpleNeRF91.py`,
+`SimpleTensoRF91.py`) to the `__path__` of the reference's already-importable `models` package, so a config
+with `"model": {"name": "SimpleNeRF91", ...}` resolves to simple_rf_b200's class.  The alternative with no
+Python call at all is to copy / symlink the two shim files into `<reference>/src/models/`.
+"""
+from pathlib import Path
+
+SHIM_DIR = Path(__file__).resolve().parent / 'models_shims'
+
+
+def install():
+    import models  # the reference's package: <reference>/src must already be on sys.path
+    if str(SHIM_DIR) not in list(models.__path__):
+        models.__path__.append(str(SHIM_DIR))
+    return SHIM_DIR
