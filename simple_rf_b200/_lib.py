@@ -67,11 +67,23 @@ def stream_handle():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+LAUNCHES = {}          # entry point -> number of successful launches (bench.py reports the total)
+TIMING = None          # when a list: (name, start_event, end_event, work) tuples appended per timed launch
+
+
+def call(name, *args, work=None):
     lib = load()
+    timing = TIMING is not None and work is not None
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise SimpleRFNativeError(lib.srf_last_error().decode())
+    if timing:
+        e1.record()
+        TIMING.append((name, e0, e1, work))
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
 
 
 def require_cuda(*tensors):

@@ -405,7 +405,19 @@ class ExtrinsicsLearner(torch.nn.Module):
     def view_matrices(self):
         return self.forward(torch.arange(self.num_frames, device=self.initial_extrinsics.device)).detach()
 
+    def _is_identity_correction(self):
+        if self.learn_rotation or self.learn_translation:
+            return False
+        key = (self.r._version, self.t._version, self.r.data_ptr())
+        if getattr(self, '_ident_key', None) != key:
+            self._ident_key = key
+            self._ident = not bool(self.r.any() or self.t.any())
+        return self._ident
+
     def forward(self, cam_id):
+        if self._is_identity_correction():
+            # r = t = 0: inv([Exp(0)|0]) is exactly I, and M @ I == M, so skip the per-ray 4x4 inverse (:831-842)
+            return self.initial_extrinsics[cam_id]
         r, t = self.r[cam_id], self.t[cam_id]
         return self.initial_extrinsics[cam_id] @ self.make_extrinsics(r, t)
 

@@ -212,5 +212,5 @@ class PackedMLP:
             raise L.SimpleRFNativeError('this MLP variant needs view_dirs')
         L.call('srf_nerf_mlp_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
                L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
-               L.ptr(sigma), L.ptr(rgb), L.stream_handle())
+               L.ptr(sigma), L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)
         return sigma, rgb
