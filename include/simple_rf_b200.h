@@ -83,11 +83,12 @@ int srf_composite_bwd(const float* sigma, const float* rgb, const float* z, cons
  * The MLP variant is described by a layer program (HOST pointer, copied at launch).  The A operand of a
  * layer is a concatenation of 64-column shared-memory K-blocks ("regions"): 0 = point encoding E
  * (3*(2*points_degree+1) columns, zero padded), 1..4 = the four 64-column blocks of the 256 hidden
- * units, 5 = view-direction encoding V.  Weights: for every layer, for every K-block in program order,
- * an image of n rows x 64 bf16 (row = output unit, column = input column of that block) in which the
- * 16-byte unit u of row r is stored at unit position (u ^ (r & 7)) — the UMMA 128-byte swizzle — so one
- * bulk copy lands it in shared memory ready for the tensor cores.  `side` is an fp32 table holding, per
- * layer, the bias [n] and, for head layers, head weights [rows][n] followed by head biases [rows]. */
+ * units, 5 = view-direction encoding V.  Weights: for every layer, for every 128-row half of its n output
+ * units, for every K-block in program order, an image of 128 rows x 64 bf16 (row = output unit, column =
+ * input column of that block) in which the 16-byte unit u of row r is stored at unit position
+ * (u ^ (r & 7)) — the UMMA 128-byte swizzle — so one 16 KB bulk copy lands it in shared memory ready for
+ * the tensor cores.  `side` is an fp32 table holding, per layer, the bias [n] and, for head layers, head
+ * weights [rows][n] followed by head biases [rows]; bias_offset / head_offset are multiples of 4. */
 typedef struct {
   int32_t num_kblocks;
   int32_t kblock_region[6];

@@ -10,7 +10,10 @@ from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / 'libsimple_rf_b200.so'
+import os
+
+# SIMPLE_RF_B200_LIB selects an alternative build of the same ABI (kernel-tuning variants); default: the in-tree library
+LIB_PATH = Path(os.environ.get('SIMPLE_RF_B200_LIB') or (Path(__file__).resolve().parent / 'libsimple_rf_b200.so'))
 _P = c_void_p
 
 _SIGNATURES = {

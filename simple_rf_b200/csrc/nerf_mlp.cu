@@ -59,11 +59,27 @@ struct MlpArgs {
   int num_tiles;
 };
 
-constexpr int MLP_THREADS = 384;          // warp 0 producer, warp 1 MMA, warps 2-3 idle, warps 4-11 epilogue
-constexpr int EPI_WARP0 = 4;
+// Schedule switches (tools/mlp_variants.sh builds and times all four combinations):
+//   SRF_MLP_NSPLIT   1: a 256-wide layer is issued as two N=128 passes so the epilogue of the first half overlaps
+//                       the MMAs of the second;  0: one N=256 pass, epilogue after the whole layer
+//   SRF_MLP_PREFETCH 1: the TMEM load of slice k+1 is issued before the math of slice k
+#ifndef SRF_MLP_NSPLIT
+#define SRF_MLP_NSPLIT 0
+#endif
+#ifndef SRF_MLP_PREFETCH
+#define SRF_MLP_PREFETCH 0
+#endif
+constexpr int MLP_THREADS = 320;          // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int EPI_WARP0 = 2;
 constexpr int KBLOCK_BYTES = 128 * 128;   // 128 rows x 64 bf16
-constexpr int STAGE_BYTES = 256 * 128;    // weight K-block for N = 256
+constexpr int IMAGE_BYTES = 128 * 128;    // packed weight image: 128 output units x one 64-wide K block
+#if SRF_MLP_NSPLIT
+constexpr int STAGE_BYTES = IMAGE_BYTES;  // one image per ring stage
+constexpr int NUM_STAGES = 6;
+#else
+constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;  // both 128-row halves of a K block per ring stage
 constexpr int NUM_STAGES = 3;
+#endif
 constexpr int MAX_SIDE = 4608;            // floats
 
 struct alignas(1024) MlpSmem {
@@ -73,7 +89,7 @@ struct alignas(1024) MlpSmem {
   float part[2][128][4];                  // head partial sums handed from column-half 1 to column-half 0
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
   uint64_t a_ready[6];                    // per A region: written and visible to the async proxy
-  uint64_t d_full[2];                     // accumulator buffer complete
+  uint64_t d_full[4];                     // accumulator [buffer][128-column half] complete
   uint32_t tmem_base;
 };
 
@@ -99,16 +115,16 @@ __device__ __forceinline__ void store_bf16(uint8_t* block, int row, int col, flo
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __grid_constant__ MlpProgram prog,
                                                                       const MlpArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  MlpSmem& sm = *reinterpret_cast<MlpSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  MlpSmem& sm = *reinterpret_cast<MlpSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
 
   for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
     for (int r = 0; r < 6; ++r) ptx::mbar_init(&sm.a_ready[r], 8);
-    ptx::mbar_init(&sm.d_full[0], 1);
-    ptx::mbar_init(&sm.d_full[1], 1);
+    for (int b = 0; b < 4; ++b) ptx::mbar_init(&sm.d_full[b], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
@@ -125,13 +141,26 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 0; l < prog.num_layers; ++l) {
           const MlpLayer& L = prog.layers[l];
-          const uint32_t bytes = (uint32_t)L.n * 128u;
+#if SRF_MLP_NSPLIT
+          const int nstages = (L.n >> 7) * L.num_kblocks;       // [n half][K block] images of 128 x 64
+          for (int s = 0; s < nstages; ++s, ++it) {
+            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
+            ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
+            ptx::mbar_arrive_expect_tx(&sm.w_full[st], IMAGE_BYTES);
+            ptx::bulk_g2s(sm.w[st], args.weights + L.weight_offset + (size_t)s * IMAGE_BYTES, IMAGE_BYTES, &sm.w_full[st]);
+          }
+#else
+          const int halves = L.n >> 7;
           for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
             const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
             ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
-            ptx::mbar_arrive_expect_tx(&sm.w_full[st], bytes);
-            ptx::bulk_g2s(sm.w[st], args.weights + L.weight_offset + (size_t)kb * bytes, bytes, &sm.w_full[st]);
+            ptx::mbar_arrive_expect_tx(&sm.w_full[st], halves * IMAGE_BYTES);
+            for (int nh = 0; nh < halves; ++nh)
+              ptx::bulk_g2s(sm.w[st] + nh * IMAGE_BYTES,
+                            args.weights + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * IMAGE_BYTES, IMAGE_BYTES,
+                            &sm.w_full[st]);
           }
+#endif
         }
       }
     }
@@ -144,29 +173,38 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
           const MlpLayer& L = prog.layers[l];
-          const uint32_t d_addr = tmem + (layer_count & 1) * 256;
+          const uint32_t buf = layer_count & 1;
+#if SRF_MLP_NSPLIT
+          const int passes = L.n >> 7;
+          const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+#else
+          const int passes = 1;
           const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
-          bool first = true;
-          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
-            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
-            const int reg = L.kblock_region[kb];
-            if (!((a_seen >> reg) & 1)) {
-              ptx::mbar_wait(&sm.a_ready[reg], (a_phase >> reg) & 1);
-              a_phase ^= 1u << reg;
-              a_seen |= 1u << reg;
+#endif
+          for (int nh = 0; nh < passes; ++nh) {
+            const uint32_t d_addr = tmem + buf * 256 + nh * 128;
+            bool first = true;
+            for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
+              const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
+              const int reg = L.kblock_region[kb];
+              if (!((a_seen >> reg) & 1)) {
+                ptx::mbar_wait(&sm.a_ready[reg], (a_phase >> reg) & 1);
+                a_phase ^= 1u << reg;
+                a_seen |= 1u << reg;
+              }
+              ptx::mbar_wait(&sm.w_full[st], ph);
+              ptx::tc_fence_after();
+              const uint32_t a_base = ptx::smem_u32(sm.a[reg]);
+              const uint32_t b_base = ptx::smem_u32(sm.w[st]);
+              for (int k = 0; k < L.kblock_ksteps[kb]; ++k) {
+                ptx::umma_bf16(d_addr, ptx::make_sw128_desc(a_base + k * 32), ptx::make_sw128_desc(b_base + k * 32), idesc,
+                               first ? 0u : 1u);
+                first = false;
+              }
+              ptx::umma_commit(&sm.w_empty[st]);
             }
-            ptx::mbar_wait(&sm.w_full[st], ph);
-            ptx::tc_fence_after();
-            const uint32_t a_base = ptx::smem_u32(sm.a[reg]);
-            const uint32_t b_base = ptx::smem_u32(sm.w[st]);
-            for (int k = 0; k < L.kblock_ksteps[kb]; ++k) {
-              ptx::umma_bf16(d_addr, ptx::make_sw128_desc(a_base + k * 32), ptx::make_sw128_desc(b_base + k * 32), idesc,
-                             first ? 0u : 1u);
-              first = false;
-            }
-            ptx::umma_commit(&sm.w_empty[st]);
+            ptx::umma_commit(&sm.d_full[buf * 2 + nh]);
           }
-          ptx::umma_commit(&sm.d_full[layer_count & 1]);
           // the epilogue of this layer rewrites H (write_h) - its blocks must be re-acquired
           if (L.write_h) a_seen &= ~0x1Eu;
         }
@@ -176,7 +214,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ encoding + epilogue warps
     const int ew = warp - EPI_WARP0;
-    const int quarter = ew & 3;          // TMEM lane quarter this warp may read
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may read: fixed by hardware to warp_id % 4
     const int half = ew >> 2;            // column half of every 64-wide block this warp owns
     const int row = quarter * 32 + lane;
     uint32_t layer_count = 0;
@@ -245,71 +283,135 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
         const MlpLayer& L = prog.layers[l];
         const uint32_t buf = layer_count & 1;
-        ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
-        d_phase ^= 1u << buf;
-        ptx::tc_fence_after();
+        const int n = L.n, relu = L.relu, write_h = L.write_h, head = L.head;
         const float* bias = sm.side + L.bias_offset;
-        const int head_rows = L.head == 1 ? 1 : (L.head == 2 ? 4 : (L.head == 3 ? 3 : 0));
+        const int head_rows = head == 1 ? 1 : (head == 2 ? 4 : (head == 3 ? 3 : 0));
         const float* hw = sm.side + L.head_offset;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-        const int nblocks = L.n >> 6;
-        for (int kb = 0; kb < nblocks; ++kb) {
+        const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + half * 32;
+
+        // bias + activation (+ head partial dot products) on one 32-column slice, packed to bf16 pairs
+        auto compute = [&](uint32_t (&v)[32], uint32_t (&pk)[16], int kb) {
           const int col0 = kb * 64 + half * 32;
-          uint32_t v[32];
-          ptx::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + col0, v);
-          ptx::tmem_ld_wait();
-          float f[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + bias[col0 + j];
-            f[j] = L.relu ? fmaxf(x, 0.f) : x;
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = b4[q];
+            float x0 = __uint_as_float(v[4 * q + 0]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
+            float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
+            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+            v[4 * q + 0] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+            v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
           }
-          if (head_rows > 0) {
-            for (int hr = 0; hr < head_rows; ++hr) {
-              const float* wr = hw + hr * L.n + col0;
-              float a = hacc[hr];
+          for (int hr = 0; hr < head_rows; ++hr) {
+            const float4* w4 = reinterpret_cast<const float4*>(hw + hr * n + col0);
+            float a = hacc[hr];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) a = fmaf(f[j], wr[j], a);
-              hacc[hr] = a;
+            for (int q = 0; q < 8; ++q) {
+              const float4 w = w4[q];
+              a = fmaf(__uint_as_float(v[4 * q + 0]), w.x, a); a = fmaf(__uint_as_float(v[4 * q + 1]), w.y, a);
+              a = fmaf(__uint_as_float(v[4 * q + 2]), w.z, a); a = fmaf(__uint_as_float(v[4 * q + 3]), w.w, a);
             }
+            hacc[hr] = a;
           }
-          if (L.write_h) {
-            uint8_t* H = sm.a[1 + kb];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 q;
-              q.x = ptx::pack_bf16(f[u * 8 + 0], f[u * 8 + 1]);
-              q.y = ptx::pack_bf16(f[u * 8 + 2], f[u * 8 + 3]);
-              q.z = ptx::pack_bf16(f[u * 8 + 4], f[u * 8 + 5]);
-              q.w = ptx::pack_bf16(f[u * 8 + 6], f[u * 8 + 7]);
-              *reinterpret_cast<uint4*>(H + ptx::sw128_offset(row, half * 4 + u)) = q;
-            }
-            ptx::fence_proxy_async_smem();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
-          }
+          for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        };
+        // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H)
+        auto store = [&](const uint32_t (&pk)[16], int kb) {
+          if (!write_h) return;
+          uint8_t* H = sm.a[1 + kb];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(H + ptx::sw128_offset(row, half * 4 + u)) =
+                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
+        };
+        auto wait_half = [&](int nh) {
+          const uint32_t b = buf * 2 + nh;
+          ptx::mbar_wait(&sm.d_full[b], (d_phase >> b) & 1);
+          d_phase ^= 1u << b;
+          ptx::tc_fence_after();
+        };
+
+        // The MMAs of the second accumulator half still read the old H while the first half is already
+        // complete: slices 0 and 1 are computed into registers meanwhile and stored once every MMA of the
+        // layer has retired; TMEM loads run one slice ahead of the math.
+        // Slices 0 and 1 (first accumulator half) are computed into registers and stored only after every
+        // MMA of the layer has retired (with SRF_MLP_NSPLIT the second half's MMAs still read the old H).
+        const bool two_halves = n > 128;
+#if SRF_MLP_PREFETCH
+        uint32_t va[32], vb[32], pa[16], pb[16];
+        wait_half(0);
+        ptx::tmem_ld32(t_row, va);
+        ptx::tmem_ld_wait(va);
+        ptx::tmem_ld32(t_row + 64, vb);
+        compute(va, pa, 0);
+        ptx::tmem_ld_wait(vb);
+        if (two_halves) {
+          if (SRF_MLP_NSPLIT) wait_half(1);
+          ptx::tmem_ld32(t_row + 128, va);
         }
+        compute(vb, pb, 1);
+        store(pa, 0);
+        store(pb, 1);
+        if (two_halves) {
+          ptx::tmem_ld_wait(va);
+          ptx::tmem_ld32(t_row + 192, vb);
+          compute(va, pa, 2);
+          store(pa, 2);
+          ptx::tmem_ld_wait(vb);
+          compute(vb, pb, 3);
+          store(pb, 3);
+        }
+#else
+        uint32_t va[32], pa[16], pb[16];
+        wait_half(0);
+        ptx::tmem_ld32(t_row, va);
+        ptx::tmem_ld_wait(va);
+        compute(va, pa, 0);
+        if (!SRF_MLP_NSPLIT) store(pa, 0);
+        ptx::tmem_ld32(t_row + 64, va);
+        ptx::tmem_ld_wait(va);
+        compute(va, pb, 1);
+        if (SRF_MLP_NSPLIT) {
+          if (two_halves) wait_half(1);
+          store(pa, 0);
+        }
+        store(pb, 1);
+        if (two_halves) {
+          ptx::tmem_ld32(t_row + 128, va);
+          ptx::tmem_ld_wait(va);
+          compute(va, pa, 2);
+          store(pa, 2);
+          ptx::tmem_ld32(t_row + 192, va);
+          ptx::tmem_ld_wait(va);
+          compute(va, pb, 3);
+          store(pb, 3);
+        }
+#endif
         ptx::tc_fence_before();
         if (head_rows > 0) {
-          const int slot = L.head == 3 ? 1 : 0;
+          const int slot = head == 3 ? 1 : 0;
           if (half == 1) {
 #pragma unroll
             for (int hr = 0; hr < 4; ++hr) sm.part[slot][row][hr] = hacc[hr];
           }
           epi_bar_sync();
           if (half == 0 && valid) {
-            const float* hb = hw + head_rows * L.n;
+            const float* hb = hw + head_rows * n;
             float o[4];
 #pragma unroll
             for (int hr = 0; hr < 4; ++hr) o[hr] = hacc[hr] + sm.part[slot][row][hr] + (hr < head_rows ? hb[hr] : 0.f);
-            if (L.head == 1 || L.head == 2) {
-              float s = o[0];
-              if (args.noise != nullptr) s += args.noise[m];
-              args.sigma[m] = fmaxf(s, 0.f);
+            if (head == 1 || head == 2) {
+              float sg = o[0];
+              if (args.noise != nullptr) sg += args.noise[m];
+              args.sigma[m] = fmaxf(sg, 0.f);
             }
-            if (L.head == 2 || L.head == 3) {
-              const int b = L.head == 2 ? 1 : 0;
+            if (head == 2 || head == 3) {
+              const int b = head == 2 ? 1 : 0;
 #pragma unroll
               for (int c = 0; c < 3; ++c) args.rgb[m * 3 + c] = 1.f / (1.f + expf(-o[b + c]));
             }

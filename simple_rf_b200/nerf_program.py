@@ -139,7 +139,6 @@ class PackedMLP:
         gather = []
         side = []
         woff = 0
-        rows_sw = {}
         for li, (name, n, kbs, relu, write_h, head) in enumerate(layers):
             Lr = prog.layers[li]
             Lr.num_kblocks = len(kbs)
@@ -149,23 +148,25 @@ class PackedMLP:
                 Lr.kblock_region[bi] = region
                 used = max(j for j, c in enumerate(cols) if c >= 0) + 1
                 Lr.kblock_ksteps[bi] = (used + 15) // 16
-                cols = np.asarray(cols)
-                if n not in rows_sw:
-                    e = np.arange(n * 64)
-                    r = e // 64
-                    unit = (e % 64) // 8
-                    rows_sw[n] = (r, ((unit ^ (r & 7)) * 8) + e % 8)
-                r, c = rows_sw[n]
-                src = cols[c]
-                idx = np.where(src >= 0, offs[name] + r * shapes[name][1] + np.maximum(src, 0), zero)
-                gather.append(idx)
-                woff += n * 64
+            # weight images in streaming order: [128-row half of n][K block] -> 128 x 64 bf16, 128B swizzle
+            e = np.arange(128 * 64)
+            r = e // 64
+            unit = (e % 64) // 8
+            c = ((unit ^ (r & 7)) * 8) + e % 8
+            for nh in range(n // 128):
+                for bi, (region, cols) in enumerate(kbs):
+                    src = np.asarray(cols)[c]
+                    idx = np.where(src >= 0, offs[name] + (nh * 128 + r) * shapes[name][1] + np.maximum(src, 0), zero)
+                    gather.append(idx)
+                    woff += 128 * 64
             bname = name.replace('.weight', '.bias')
+            side += [zero] * (-len(side) % 4)                      # float4 loads in the epilogue
             Lr.bias_offset = len(side)
             side += [offs[bname] + j for j in range(n)]
             if head:
                 hname = 'views_output_linear' if head == 3 else 'pts_output_linear'
                 rows = shapes[f'{hname}.weight'][0]
+                side += [zero] * (-len(side) % 4)
                 Lr.head_offset = len(side)
                 side += [widx(f'{hname}.weight', r_, c_) for r_ in range(rows) for c_ in range(n)]
                 side += [offs[f'{hname}.bias'] + r_ for r_ in range(rows)]
