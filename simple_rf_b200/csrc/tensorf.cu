@@ -1,0 +1,653 @@
+// Simple-TensoRF vector-matrix (VM) tensor: occupancy test, sample compaction, density / appearance gathers.
+//
+// Replaces (reference file:line, relative to the upstream checkout):
+//   srf_pack_alpha_bits        derived cache of AlphaGridMask.alpha_volume (src/models/SimpleTensoRF09.py:1323-1345)
+//   srf_tensorf_mask           :263 (pts = o + d z), :705 (box test), :707-710 + :1342-1349 (alphaMask test)
+//   srf_threshold_mask         :726 (weights > ray_marching_weight_threshold)
+//   srf_compact                the boolean-mask indexing of :1221 / :1248 (stable row-major order) without the host sync
+//   srf_vm_density_fwd / _bwd  :763-765 (normalise), :1214-1239 (get_volume_density) and its autograd
+//   srf_vm_color_features_fwd / _bwd   :1241-1263 (plane x line products, basis_matrix_color) and its autograd
+//
+// Planes and lines are read from channels-last derived caches ([H][W][C] / [L][C]) so that one texel is one or
+// a few 16-byte vectors; the fp32 `nn.Parameter`s keep the reference's [1,C,H,W] layout.  The occupancy volume
+// is 1 bit per voxel (x fastest), i.e. L2/shared-memory sized, and the test reproduces ATen's grid_sampler_3d
+// coordinate arithmetic exactly, so mask and compaction order are bit-identical to the reference.
+#include "common.cuh"
+
+namespace srf {
+
+constexpr int CMP_BLOCK = 1024;     // elements per compaction block (256 threads x 4)
+
+// ------------------------------------------------------------------------------------------ occupancy bits
+__global__ void pack_alpha_kernel(const float* __restrict__ vol, long long n, uint32_t* __restrict__ bits) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long base = w * 32;
+  if (base >= n) return;
+  uint32_t word = 0;
+  for (int b = 0; b < 32; ++b) {
+    const long long i = base + b;
+    if (i < n && vol[i] > 0.f) word |= 1u << b;
+  }
+  bits[w] = word;
+}
+
+struct MaskParams {
+  const float* rays_o; const float* rays_d; const float* z;
+  const uint32_t* alpha_bits;          // nullptr: no alphaMask
+  uint8_t* mask; int* block_counts;
+  long long total; int S;
+  float bb0[3], bb1[3];                // tensor bounding box
+  float ab0[3], asize[3];              // alpha-volume box: min corner and size (fp32, as the reference stores them)
+  int ax, ay, az;                      // alpha-volume resolution
+};
+
+__device__ __forceinline__ bool alpha_hit(const MaskParams& p, const float (&pt)[3]) {
+  const int dims[3] = {p.ax, p.ay, p.az};
+  float ix[3], f0[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    // normalise ((p - b0) / size) * 2 - 1  (:1347-1349), unnormalise ((c + 1) / 2) * (dim - 1) (ATen GridSampler.h)
+    const float c = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(pt[a], -p.ab0[a]), p.asize[a]), 2.f), -1.f);
+    ix[a] = __fmul_rn(__fdiv_rn(__fadd_rn(c, 1.f), 2.f), (float)(dims[a] - 1));
+    f0[a] = floorf(ix[a]);
+  }
+  bool hit = false;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+    const int xi = (int)f0[0] + dx, yi = (int)f0[1] + dy, zi = (int)f0[2] + dz;
+    if (xi < 0 || yi < 0 || zi < 0 || xi >= p.ax || yi >= p.ay || zi >= p.az) continue;
+    const float wx = dx ? __fadd_rn(ix[0], -f0[0]) : __fadd_rn(__fadd_rn(f0[0], 1.f), -ix[0]);
+    const float wy = dy ? __fadd_rn(ix[1], -f0[1]) : __fadd_rn(__fadd_rn(f0[1], 1.f), -ix[1]);
+    const float wz = dz ? __fadd_rn(ix[2], -f0[2]) : __fadd_rn(__fadd_rn(f0[2], 1.f), -ix[2]);
+    const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+    if (w > 0.f) {
+      const long long v = ((long long)zi * p.ay + yi) * p.ax + xi;
+      hit |= (p.alpha_bits[v >> 5] >> (v & 31)) & 1u;
+    }
+  }
+  return hit;
+}
+
+__global__ void __launch_bounds__(256) tensorf_mask_kernel(MaskParams p) {
+  const long long base = (long long)blockIdx.x * CMP_BLOCK;
+  int local = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    bool ok = false;
+    if (i < p.total) {
+      const long long r = i / p.S;
+      const float zz = p.z[i];
+      float pt[3];
+      ok = true;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        pt[a] = __fadd_rn(p.rays_o[r * 3 + a], __fmul_rn(p.rays_d[r * 3 + a], zz));
+        ok = ok && (p.bb0[a] <= pt[a]) && (pt[a] <= p.bb1[a]);
+      }
+      if (ok && p.alpha_bits != nullptr) ok = alpha_hit(p, pt);
+      p.mask[i] = ok ? 1 : 0;
+    }
+    local += ok ? 1 : 0;
+  }
+  __shared__ int s_cnt[8];
+  int w = local;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(FULL, w, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; ++k) t += s_cnt[k];
+    p.block_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) threshold_mask_kernel(const float* __restrict__ v, float thr, long long total,
+                                                             uint8_t* __restrict__ mask, int* __restrict__ block_counts) {
+  const long long base = (long long)blockIdx.x * CMP_BLOCK;
+  int local = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    bool ok = false;
+    if (i < total) { ok = v[i] > thr; mask[i] = ok ? 1 : 0; }
+    local += ok ? 1 : 0;
+  }
+  __shared__ int s_cnt[8];
+  int w = local;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(FULL, w, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; ++k) t += s_cnt[k];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the per-block counts (one CTA; nb is a few thousand at most), total -> count[0]
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict__ counts, int nb, int* __restrict__ offsets,
+                                                           int* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? counts[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = s_warp[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, w, o);
+        if (threadIdx.x >= o) w += t;
+      }
+      s_warp[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) == 0 ? 0 : s_warp[(threadIdx.x >> 5) - 1];
+    const int carry = s_carry;
+    if (i < nb) offsets[i] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count[0] = s_carry;
+}
+
+// stable scatter: element order inside a block is k-major over the 4 strips of 256, matching the mask kernels
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const uint8_t* __restrict__ mask, long long total,
+                                                              const int* __restrict__ offsets, int* __restrict__ idx) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const long long base = (long long)blockIdx.x * CMP_BLOCK;
+  if (threadIdx.x == 0) s_base = offsets[blockIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    const bool ok = i < total && mask[i] != 0;
+    const unsigned bal = __ballot_sync(FULL, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, strip = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; if (w < warp) before += c; strip += c; }
+    if (ok) idx[s_base + before + __popc(bal & ((1u << lane) - 1))] = (int)i;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += strip;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ VM gathers
+struct VmGrid {
+  const float* plane[3];   // channels-last [H][W][C]
+  const float* line[3];    // [L][C]
+  int C[3];                // channels per plane/line pair (multiples of 4)
+  int res[3];              // tensor resolution (X, Y, Z)
+};
+
+struct VmGeom {
+  const float* rays_o; const float* rays_d; const float* z;
+  const int* idx; const int* count;
+  int S;
+  float bb0[3], bsize[3];
+};
+
+// matrix_axes = [[0,1],[0,2],[1,2]], vector_axes = [2,1,0]  (:1131-1132); grid x -> W = res[a0], y -> H = res[a1]
+__device__ __constant__ int c_a0[3] = {0, 0, 1};
+__device__ __constant__ int c_a1[3] = {1, 2, 2};
+__device__ __constant__ int c_av[3] = {2, 1, 0};
+
+struct Bilerp {
+  int x0, y0, W, H;
+  float wx0, wx1, wy0, wy1;
+};
+
+__device__ __forceinline__ void normalized_point(const VmGeom& g, int flat, float (&pn)[3]) {
+  const int r = flat / g.S;
+  const float zz = g.z[flat];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pt = __fadd_rn(g.rays_o[r * 3 + a], __fmul_rn(g.rays_d[r * 3 + a], zz));
+    pn[a] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(pt, -g.bb0[a]), g.bsize[a]), 2.f), -1.f);
+  }
+}
+
+__device__ __forceinline__ float unnorm(float c, int size) { return __fmul_rn(__fdiv_rn(__fadd_rn(c, 1.f), 2.f), (float)(size - 1)); }
+
+__device__ __forceinline__ Bilerp plane_coords(const float (&pn)[3], const int (&res)[3], int i) {
+  Bilerp b;
+  b.W = res[c_a0[i]]; b.H = res[c_a1[i]];
+  const float ix = unnorm(pn[c_a0[i]], b.W), iy = unnorm(pn[c_a1[i]], b.H);
+  const float fx = floorf(ix), fy = floorf(iy);
+  b.x0 = (int)fx; b.y0 = (int)fy;
+  b.wx1 = ix - fx; b.wx0 = (fx + 1.f) - ix;
+  b.wy1 = iy - fy; b.wy0 = (fy + 1.f) - iy;
+  return b;
+}
+
+// value of channel group [c, c+4) of a plane at the bilinear position (zeros outside, as grid_sample pads)
+__device__ __forceinline__ float4 plane_fetch4(const float* plane, const Bilerp& b, int C, int c) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
+    if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
+    const float w = ((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(plane + ((size_t)y * b.W + x) * C + c));
+    acc.x += t.x * w; acc.y += t.y * w; acc.z += t.z * w; acc.w += t.w * w;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void line_coords(const float (&pn)[3], const int (&res)[3], int i, int& l0, int& L, float& w0, float& w1) {
+  L = res[c_av[i]];
+  const float iy = unnorm(pn[c_av[i]], L);
+  const float fy = floorf(iy);
+  l0 = (int)fy;
+  w1 = iy - fy; w0 = (fy + 1.f) - iy;
+}
+
+__device__ __forceinline__ float4 line_fetch4(const float* line, int l0, int L, float w0, float w1, int C, int c) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (l0 >= 0 && l0 < L) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(line + (size_t)l0 * C + c));
+    acc.x += t.x * w0; acc.y += t.y * w0; acc.z += t.z * w0; acc.w += t.w * w0;
+  }
+  if (l0 + 1 >= 0 && l0 + 1 < L) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(line + (size_t)(l0 + 1) * C + c));
+    acc.x += t.x * w1; acc.y += t.y * w1; acc.z += t.z * w1; acc.w += t.w * w1;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// density: sigma = act(sum_i sum_c plane_i,c * line_i,c); one thread per compacted sample
+__global__ void __launch_bounds__(256) vm_density_fwd_kernel(VmGeom g, VmGrid t, int softplus, float offset,
+                                                             float* __restrict__ sigma, float* __restrict__ feat_out) {
+  const int n = g.count[0];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int flat = g.idx[j];
+    float pn[3];
+    normalized_point(g, flat, pn);
+    float feat = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const Bilerp b = plane_coords(pn, t.res, i);
+      int l0, L; float w0, w1;
+      line_coords(pn, t.res, i, l0, L, w0, w1);
+      float part = 0.f;
+      for (int c = 0; c < t.C[i]; c += 4) {
+        const float4 pv = plane_fetch4(t.plane[i], b, t.C[i], c);
+        const float4 lv = line_fetch4(t.line[i], l0, L, w0, w1, t.C[i], c);
+        part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+      }
+      feat += part;
+    }
+    if (feat_out) feat_out[j] = feat;
+    float s;
+    if (softplus) { const float x = feat + offset; s = x > 20.f ? x : log1pf(expf(x)); }
+    else s = fmaxf(feat, 0.f);
+    sigma[flat] = s;
+  }
+}
+
+// backward: d feat -> bilinear/linear scatter-add into the channels-last gradient buffers
+__global__ void __launch_bounds__(256) vm_density_bwd_kernel(VmGeom g, VmGrid t, int softplus, float offset,
+                                                             const float* __restrict__ g_sigma, const float* __restrict__ feat_in,
+                                                             float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
+  const int n = g.count[0];
+  float* gplane[3] = {gp0, gp1, gp2};
+  float* gline[3] = {gl0, gl1, gl2};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int flat = g.idx[j];
+    const float feat = feat_in[j];
+    float gf = g_sigma[flat];
+    if (softplus) { const float x = feat + offset; gf *= 1.f / (1.f + expf(-x)); }
+    else gf = feat > 0.f ? gf : 0.f;
+    if (gf == 0.f) continue;
+    float pn[3];
+    normalized_point(g, flat, pn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const Bilerp b = plane_coords(pn, t.res, i);
+      int l0, L; float w0, w1;
+      line_coords(pn, t.res, i, l0, L, w0, w1);
+      const int C = t.C[i];
+      for (int c = 0; c < C; c += 4) {
+        const float4 pv = plane_fetch4(t.plane[i], b, C, c);
+        const float4 lv = line_fetch4(t.line[i], l0, L, w0, w1, C, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
+          if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
+          const float w = gf * ((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0);
+          red_add4(gplane[i] + ((size_t)y * b.W + x) * C + c, w * lv.x, w * lv.y, w * lv.z, w * lv.w);
+        }
+        if (l0 >= 0 && l0 < L) red_add4(gline[i] + (size_t)l0 * C + c, gf * w0 * pv.x, gf * w0 * pv.y, gf * w0 * pv.z, gf * w0 * pv.w);
+        if (l0 + 1 >= 0 && l0 + 1 < L)
+          red_add4(gline[i] + (size_t)(l0 + 1) * C + c, gf * w1 * pv.x, gf * w1 * pv.y, gf * w1 * pv.z, gf * w1 * pv.w);
+      }
+    }
+  }
+}
+
+// appearance: products (plane x line) over all channels -> basis matrix [F,CT] (F <= 32 outputs) -> rows of
+// [features | view_dirs | zero pad] (row width 32) that the tensor-core colour MLP consumes.
+// One warp per sample: lane l owns product channels l, l+32, l+64 (CT <= 96) and output feature l.
+constexpr int COLOR_ROW = 32;
+
+__device__ __forceinline__ float color_product(const VmGrid& t, const float (&pn)[3], int ch, int& plane_i, int& local_c) {
+  int i = 0, c = ch;
+  while (i < 2 && c >= t.C[i]) { c -= t.C[i]; ++i; }
+  plane_i = i; local_c = c;
+  const Bilerp b = plane_coords(pn, t.res, i);
+  int l0, L; float w0, w1;
+  line_coords(pn, t.res, i, l0, L, w0, w1);
+  float pv = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
+    if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
+    pv += __ldg(t.plane[i] + ((size_t)y * b.W + x) * t.C[i] + c) * (((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0));
+  }
+  float lv = 0.f;
+  if (l0 >= 0 && l0 < L) lv += __ldg(t.line[i] + (size_t)l0 * t.C[i] + c) * w0;
+  if (l0 + 1 >= 0 && l0 + 1 < L) lv += __ldg(t.line[i] + (size_t)(l0 + 1) * t.C[i] + c) * w1;
+  return pv * lv;
+}
+
+__global__ void __launch_bounds__(256) vm_color_features_fwd_kernel(VmGeom g, VmGrid t, const float* __restrict__ basis, int F, int CT,
+                                                                    const float* __restrict__ view_dirs, float* __restrict__ rows) {
+  extern __shared__ float s_basis[];                 // [F][CT]
+  for (int i = threadIdx.x; i < F * CT; i += blockDim.x) s_basis[i] = basis[i];
+  __syncthreads();
+  const int n = g.count[0];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+    const int flat = g.idx[j];
+    float pn[3];
+    normalized_point(g, flat, pn);
+    float prod[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int ch = lane + 32 * k;
+      int pi, lc;
+      if (ch < CT) prod[k] = color_product(t, pn, ch, pi, lc);
+    }
+    float out = 0.f;
+    for (int ch = 0; ch < CT; ++ch) {
+      const float v = __shfl_sync(FULL, prod[ch >> 5], ch & 31);
+      if (lane < F) out = fmaf(v, s_basis[lane * CT + ch], out);
+    }
+    const int r = flat / g.S;
+    float val = 0.f;
+    if (lane < F) val = out;
+    else if (lane < F + 3) val = view_dirs[r * 3 + (lane - F)];
+    rows[(size_t)j * COLOR_ROW + lane] = val;
+  }
+}
+
+// backward of the above: g_rows[:, :F] -> g_basis (block-reduced, then atomics) and scatter into planes / lines
+__global__ void __launch_bounds__(256) vm_color_features_bwd_kernel(VmGeom g, VmGrid t, const float* __restrict__ basis, int F, int CT,
+                                                                    const float* __restrict__ g_rows, float* __restrict__ g_basis,
+                                                                    float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
+  extern __shared__ float s_mem[];                   // basis [F][CT] | g_basis accumulator [F][CT]
+  float* s_basis = s_mem;
+  float* s_gb = s_mem + F * CT;
+  for (int i = threadIdx.x; i < F * CT; i += blockDim.x) { s_basis[i] = basis[i]; s_gb[i] = 0.f; }
+  __syncthreads();
+  float* gplane[3] = {gp0, gp1, gp2};
+  float* gline[3] = {gl0, gl1, gl2};
+  const int n = g.count[0];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+    const int flat = g.idx[j];
+    float pn[3];
+    normalized_point(g, flat, pn);
+    const float gout = lane < F ? g_rows[(size_t)j * COLOR_ROW + lane] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int ch = lane + 32 * k;
+      const bool live = ch < CT;
+      // recompute the product's two factors for this channel
+      int i = 0, c = live ? ch : 0;
+      while (i < 2 && c >= t.C[i]) { c -= t.C[i]; ++i; }
+      const Bilerp b = plane_coords(pn, t.res, i);
+      int l0, L; float w0, w1;
+      line_coords(pn, t.res, i, l0, L, w0, w1);
+      float pv = 0.f, lv = 0.f;
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int x = b.x0 + (q & 1), y = b.y0 + (q >> 1);
+          if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
+          pv += __ldg(t.plane[i] + ((size_t)y * b.W + x) * t.C[i] + c) * (((q & 1) ? b.wx1 : b.wx0) * ((q >> 1) ? b.wy1 : b.wy0));
+        }
+        if (l0 >= 0 && l0 < L) lv += __ldg(t.line[i] + (size_t)l0 * t.C[i] + c) * w0;
+        if (l0 + 1 >= 0 && l0 + 1 < L) lv += __ldg(t.line[i] + (size_t)(l0 + 1) * t.C[i] + c) * w1;
+      }
+      const float prod = pv * lv;
+      // g_prod[ch] = sum_f g_out[f] * basis[f][ch];  g_basis[f][ch] += g_out[f] * prod[ch]
+      float gprod = 0.f;
+      for (int f = 0; f < F; ++f) {
+        const float gf = __shfl_sync(FULL, gout, f);
+        if (live) {
+          gprod = fmaf(gf, s_basis[f * CT + ch], gprod);
+          atomicAdd(&s_gb[f * CT + ch], gf * prod);
+        }
+      }
+      if (live && gprod != 0.f) {
+        const float gpv = gprod * lv, glv = gprod * pv;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int x = b.x0 + (q & 1), y = b.y0 + (q >> 1);
+          if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
+          atomicAdd(gplane[i] + ((size_t)y * b.W + x) * t.C[i] + c, gpv * (((q & 1) ? b.wx1 : b.wx0) * ((q >> 1) ? b.wy1 : b.wy0)));
+        }
+        if (l0 >= 0 && l0 < L) atomicAdd(gline[i] + (size_t)l0 * t.C[i] + c, glv * w0);
+        if (l0 + 1 >= 0 && l0 + 1 < L) atomicAdd(gline[i] + (size_t)(l0 + 1) * t.C[i] + c, glv * w1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * CT; i += blockDim.x) {
+    const float v = s_gb[i];
+    if (v != 0.f) atomicAdd(g_basis + i, v);
+  }
+}
+
+// scatter compacted rows [n, width] back to the dense [total, width] tensor (the reference's rgb[mask] = ..., :1271)
+__global__ void scatter_rows_kernel(const int* __restrict__ idx, const int* __restrict__ count, const float* __restrict__ src,
+                                    int width, float* __restrict__ dst) {
+  const int n = count[0];
+  const long long total = (long long)n * width;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e / width), c = (int)(e % width);
+    dst[(size_t)idx[j] * width + c] = src[e];
+  }
+}
+// gather dense rows -> compacted rows (backward of the scatter)
+__global__ void gather_rows_kernel(const int* __restrict__ idx, const int* __restrict__ count, const float* __restrict__ src,
+                                   int width, float* __restrict__ dst) {
+  const int n = count[0];
+  const long long total = (long long)n * width;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e / width), c = (int)(e % width);
+    dst[e] = src[(size_t)idx[j] * width + c];
+  }
+}
+
+inline int blocks_for(long long n, int per_block, int cap_mult = 32) {
+  long long b = (n + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count() * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace srf
+
+using namespace srf;
+
+SRF_API int srf_pack_alpha_bits(const float* volume, int64_t num_voxels, uint32_t* bits, void* stream) {
+  if (num_voxels == 0) return 0;
+  SRF_REQUIRE(volume && bits, "srf_pack_alpha_bits", "null pointer");
+  const long long words = (num_voxels + 31) / 32;
+  pack_alpha_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, num_voxels, bits);
+  return check_launch("srf_pack_alpha_bits");
+}
+
+SRF_API int srf_compaction_blocks(int64_t total) { return (int)((total + CMP_BLOCK - 1) / CMP_BLOCK); }
+
+SRF_API int srf_tensorf_mask(const float* rays_o, const float* rays_d, const float* z, int64_t num_rays, int num_samples,
+                             const float* bbox, const uint32_t* alpha_bits, const int* alpha_res, const float* alpha_box_min,
+                             const float* alpha_box_size, uint8_t* mask, int* block_counts, void* stream) {
+  if (num_rays == 0) return 0;
+  SRF_REQUIRE(rays_o && rays_d && z && bbox && mask && block_counts, "srf_tensorf_mask", "null pointer");
+  SRF_REQUIRE(alpha_bits == nullptr || (alpha_res && alpha_box_min && alpha_box_size), "srf_tensorf_mask", "alpha box missing");
+  MaskParams p{};
+  p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.alpha_bits = alpha_bits; p.mask = mask; p.block_counts = block_counts;
+  p.total = (long long)num_rays * num_samples; p.S = num_samples;
+  for (int a = 0; a < 3; ++a) { p.bb0[a] = bbox[a]; p.bb1[a] = bbox[3 + a]; }     // HOST pointers: 6 floats
+  if (alpha_bits) {
+    for (int a = 0; a < 3; ++a) { p.ab0[a] = alpha_box_min[a]; p.asize[a] = alpha_box_size[a]; }
+    p.ax = alpha_res[0]; p.ay = alpha_res[1]; p.az = alpha_res[2];
+  }
+  tensorf_mask_kernel<<<srf_compaction_blocks(p.total), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("srf_tensorf_mask");
+}
+
+SRF_API int srf_threshold_mask(const float* values, float threshold, int64_t total, uint8_t* mask, int* block_counts, void* stream) {
+  if (total == 0) return 0;
+  SRF_REQUIRE(values && mask && block_counts, "srf_threshold_mask", "null pointer");
+  threshold_mask_kernel<<<srf_compaction_blocks(total), 256, 0, (cudaStream_t)stream>>>(values, threshold, total, mask, block_counts);
+  return check_launch("srf_threshold_mask");
+}
+
+SRF_API int srf_compact(const uint8_t* mask, int64_t total, int* block_counts, int* block_offsets, int* indices, int* count,
+                        void* stream) {
+  SRF_REQUIRE(count, "srf_compact", "null pointer");
+  if (total == 0) return cudaMemsetAsync(count, 0, sizeof(int), (cudaStream_t)stream) == cudaSuccess ? 0 : fail("srf_compact", "memset");
+  SRF_REQUIRE(mask && block_counts && block_offsets && indices, "srf_compact", "null pointer");
+  SRF_REQUIRE(total < (1ll << 31), "srf_compact", "more than 2^31 samples in one call");
+  const int nb = srf_compaction_blocks(total);
+  scan_blocks_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(block_counts, nb, block_offsets, count);
+  compact_scatter_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(mask, total, block_offsets, indices);
+  return check_launch("srf_compact");
+}
+
+namespace {
+int fill_geom(VmGeom& g, const float* rays_o, const float* rays_d, const float* z, const int* idx, const int* count, int S,
+              const float* box_min, const float* box_size) {
+  g.rays_o = rays_o; g.rays_d = rays_d; g.z = z; g.idx = idx; g.count = count; g.S = S;
+  for (int a = 0; a < 3; ++a) { g.bb0[a] = box_min[a]; g.bsize[a] = box_size[a]; }
+  return 0;
+}
+int fill_grid(VmGrid& t, const float* const* planes, const float* const* lines, const int* channels, const int* res, const char* where) {
+  for (int i = 0; i < 3; ++i) {
+    t.plane[i] = planes[i]; t.line[i] = lines[i]; t.C[i] = channels[i]; t.res[i] = res[i];
+    if (!planes[i] || !lines[i]) return fail(where, "null plane/line pointer");
+    if (channels[i] <= 0 || (channels[i] & 3)) return fail(where, "channel counts must be positive multiples of 4");
+  }
+  return 0;
+}
+}  // namespace
+
+SRF_API int srf_vm_density_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                               const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                               int softplus, float density_offset, float* sigma, float* features, void* stream) {
+  if (max_count == 0) return 0;
+  SRF_REQUIRE(rays_o && rays_d && z && indices && count && box_min && box_size && sigma, "srf_vm_density_fwd", "null pointer");
+  VmGeom g; VmGrid t;
+  fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
+  if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_density_fwd")) return 1;
+  vm_density_fwd_kernel<<<blocks_for(max_count, 256), 256, 0, (cudaStream_t)stream>>>(g, t, softplus, density_offset, sigma, features);
+  return check_launch("srf_vm_density_fwd");
+}
+
+SRF_API int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                               const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                               int softplus, float density_offset, const float* g_sigma, const float* features,
+                               float* const* g_planes, float* const* g_lines, void* stream) {
+  if (max_count == 0) return 0;
+  SRF_REQUIRE(rays_o && rays_d && z && indices && count && g_sigma && features && g_planes && g_lines, "srf_vm_density_bwd", "null pointer");
+  VmGeom g; VmGrid t;
+  fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
+  if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_density_bwd")) return 1;
+  vm_density_bwd_kernel<<<blocks_for(max_count, 256), 256, 0, (cudaStream_t)stream>>>(
+      g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  return check_launch("srf_vm_density_bwd");
+}
+
+SRF_API int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                                      const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                                      const float* const* planes, const float* const* lines, const int* channels,
+                                      const int* resolution, const float* basis, int num_features, const float* view_dirs,
+                                      float* rows, void* stream) {
+  if (max_count == 0) return 0;
+  SRF_REQUIRE(rays_o && rays_d && z && indices && count && basis && view_dirs && rows, "srf_vm_color_features_fwd", "null pointer");
+  VmGeom g; VmGrid t;
+  fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
+  if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_fwd")) return 1;
+  const int CT = channels[0] + channels[1] + channels[2];
+  SRF_REQUIRE(CT <= 96 && num_features + 3 <= COLOR_ROW, "srf_vm_color_features_fwd", "need sum(C) <= 96 and features + 3 <= 32");
+  const size_t smem = (size_t)num_features * CT * sizeof(float);
+  vm_color_features_fwd_kernel<<<blocks_for(max_count, 8), 256, smem, (cudaStream_t)stream>>>(g, t, basis, num_features, CT, view_dirs, rows);
+  return check_launch("srf_vm_color_features_fwd");
+}
+
+SRF_API int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                                      const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                                      const float* const* planes, const float* const* lines, const int* channels,
+                                      const int* resolution, const float* basis, int num_features, const float* g_rows,
+                                      float* g_basis, float* const* g_planes, float* const* g_lines, void* stream) {
+  if (max_count == 0) return 0;
+  SRF_REQUIRE(rays_o && rays_d && z && indices && count && basis && g_rows && g_basis && g_planes && g_lines,
+              "srf_vm_color_features_bwd", "null pointer");
+  VmGeom g; VmGrid t;
+  fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
+  if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_bwd")) return 1;
+  const int CT = channels[0] + channels[1] + channels[2];
+  SRF_REQUIRE(CT <= 96 && num_features + 3 <= COLOR_ROW, "srf_vm_color_features_bwd", "need sum(C) <= 96 and features + 3 <= 32");
+  const size_t smem = 2 * (size_t)num_features * CT * sizeof(float);
+  vm_color_features_bwd_kernel<<<blocks_for(max_count, 8, 8), 256, smem, (cudaStream_t)stream>>>(
+      g, t, basis, num_features, CT, g_rows, g_basis, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  return check_launch("srf_vm_color_features_bwd");
+}
+
+SRF_API int srf_scatter_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
+                             void* stream) {
+  if (max_count == 0) return 0;
+  SRF_REQUIRE(indices && count && src && dst && width > 0, "srf_scatter_rows", "null pointer");
+  scatter_rows_kernel<<<blocks_for(max_count * width, 256), 256, 0, (cudaStream_t)stream>>>(indices, count, src, width, dst);
+  return check_launch("srf_scatter_rows");
+}
+
+SRF_API int srf_gather_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
+                            void* stream) {
+  if (max_count == 0) return 0;
+  SRF_REQUIRE(indices && count && src && dst && width > 0, "srf_gather_rows", "null pointer");
+  gather_rows_kernel<<<blocks_for(max_count * width, 256), 256, 0, (cudaStream_t)stream>>>(indices, count, src, width, dst);
+  return check_launch("srf_gather_rows");
+}
