@@ -119,6 +119,69 @@ int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side
                      int64_t num_rays, int num_samples, float* sigma, float* rgb, void* stream);
 int srf_nerf_mlp_program_bytes(void);   /* sizeof(srf_mlp_program) as compiled, for binding self-checks */
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Simple-TensoRF vector-matrix tensor.  Small parameter blocks marked HOST are host pointers read at launch.
+ * Planes / lines are channels-last derived caches: plane i is [res[a1]][res[a0]][C_i] with
+ * (a0,a1) = (0,1),(0,2),(1,2) and line i is [res[v_i]][C_i] with v = (2,1,0) (SimpleTensoRF09.py:1131-1132,
+ * :1159); C_i must be multiples of 4.  Compacted sample lists are int32 flat indices r*S+s in ascending
+ * (row-major, stable) order with the element count kept on the DEVICE (no host synchronisation). */
+
+/* 1 bit per voxel (x fastest, 32 voxels per word) from the fp32 {0,1} volume [Z,Y,X] (SimpleTensoRF09.py:1333). */
+int srf_pack_alpha_bits(const float* volume, int64_t num_voxels, uint32_t* bits, void* stream);
+int srf_compaction_blocks(int64_t total);   /* length of the block_counts / block_offsets scratch arrays */
+
+/* pts = o + d z (SimpleTensoRF09.py:263), inside-box test (:705) and alphaMask test (:707-710, :1342-1349;
+ * bit-exact w.r.t. F.grid_sample(...) > 0).  bbox HOST [2,3]; alpha_bits nullable; alpha_res HOST (X,Y,Z);
+ * alpha_box_min / alpha_box_size HOST [3].  mask uint8 [R,S]; block_counts int32 [srf_compaction_blocks]. */
+int srf_tensorf_mask(const float* rays_o, const float* rays_d, const float* z, int64_t num_rays, int num_samples,
+                     const float* bbox, const uint32_t* alpha_bits, const int* alpha_res, const float* alpha_box_min,
+                     const float* alpha_box_size, uint8_t* mask, int* block_counts, void* stream);
+/* mask = values > threshold (SimpleTensoRF09.py:726). */
+int srf_threshold_mask(const float* values, float threshold, int64_t total, uint8_t* mask, int* block_counts, void* stream);
+/* Stable stream compaction of a mask produced by the two calls above (replaces pts[mask], :1221, :1248). */
+int srf_compact(const uint8_t* mask, int64_t total, int* block_counts, int* block_offsets, int* indices, int* count,
+                void* stream);
+
+/* VM density (SimpleTensoRF09.py:763-765, :1214-1239): sigma[idx] = act(sum_i sum_c plane_i,c * line_i,c), act =
+ * ReLU or softplus(x + density_offset); sigma [R*S] must be zero-filled by the caller; features [max_count]
+ * (pre-activation, compacted order) is kept for the backward.  planes / lines: HOST arrays of 3 device pointers;
+ * channels, resolution (X,Y,Z), box_min, box_size: HOST. */
+int srf_vm_density_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                       const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                       const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                       int softplus, float density_offset, float* sigma, float* features, void* stream);
+/* its autograd: g_sigma [R*S] -> scatter-add into zero-initialised channels-last gradient buffers. */
+int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                       const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                       const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                       int softplus, float density_offset, const float* g_sigma, const float* features,
+                       float* const* g_planes, float* const* g_lines, void* stream);
+
+/* VM appearance features (SimpleTensoRF09.py:1241-1263): (plane x line) products over sum(C) <= 96 channels ->
+ * basis_matrix_color [F, sum(C)] -> rows [max_count, 32] = [F features | 3 view_dirs | zero pad], the input of the
+ * colour MLP (:1411-1421 with identity encodings). */
+int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                              const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                              const float* const* planes, const float* const* lines, const int* channels,
+                              const int* resolution, const float* basis, int num_features, const float* view_dirs,
+                              float* rows, void* stream);
+int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                              const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                              const float* const* planes, const float* const* lines, const int* channels,
+                              const int* resolution, const float* basis, int num_features, const float* g_rows,
+                              float* g_basis, float* const* g_planes, float* const* g_lines, void* stream);
+
+/* dst[indices[j], :] = src[j, :] (the scatter-back of :1238 / :1271) and its transpose. */
+int srf_scatter_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
+                     void* stream);
+int srf_gather_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
+                    void* stream);
+
+/* Colour MLP on the tensor cores: same kernel and program format as srf_nerf_mlp_fwd, but region 0 is filled from
+ * precomputed rows [max_rows, 32] (fp32) instead of a positional encoding; the row count is read from the device. */
+int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const float* rows, const int* count,
+                     int64_t max_rows, float* rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

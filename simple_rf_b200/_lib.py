@@ -27,6 +27,18 @@ _SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_nerf_mlp_fwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
     'srf_nerf_mlp_program_bytes': (c_int, []),
+    'srf_pack_alpha_bits': (c_int, [_P, c_int64, _P, _P]),
+    'srf_compaction_blocks': (c_int, [c_int64]),
+    'srf_tensorf_mask': (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'srf_threshold_mask': (c_int, [_P, c_float, c_int64, _P, _P, _P]),
+    'srf_compact': (c_int, [_P, c_int64, _P, _P, _P, _P, _P]),
+    'srf_vm_density_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P]),
+    'srf_vm_density_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P]),
+    'srf_vm_color_features_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    'srf_vm_color_features_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    'srf_scatter_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
+    'srf_gather_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
+    'srf_mlp_rows_fwd': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P]),
     'srf_composite_bwd': (c_int, [_P] * 17 + [c_int64, c_int, c_int, c_int, c_float, _P, _P, _P]),
 }
 

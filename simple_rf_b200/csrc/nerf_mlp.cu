@@ -52,48 +52,46 @@ struct MlpArgs {
   const float* z;               // [R,S]
   const float* view_dirs;       // [R,3] or nullptr
   const float* noise;           // [R*S] or nullptr: added to raw sigma before the ReLU
+  const float* rows;            // rows mode: [total, 32] fp32 inputs copied into region 0 instead of an encoding
+  const int* count;             // rows mode: device-side row count (<= total), or nullptr
   float* sigma;                 // [R*S]
   float* rgb;                   // [R*S,3]
-  long long total;              // R*S
+  long long total;              // R*S (rows mode: capacity of `rows`)
   int S;
-  int num_tiles;
 };
 
-// Schedule switches (tools/mlp_variants.sh builds and times all four combinations):
-//   SRF_MLP_NSPLIT   1: a 256-wide layer is issued as two N=128 passes so the epilogue of the first half overlaps
-//                       the MMAs of the second;  0: one N=256 pass, epilogue after the whole layer
+// Tuning switches (tools/mlp_variants.sh builds and times the combinations):
+//   SRF_MLP_GROUPS   column groups per 64-wide block = epilogue warps per TMEM lane quarter (2 or 4)
 //   SRF_MLP_PREFETCH 1: the TMEM load of slice k+1 is issued before the math of slice k
-#ifndef SRF_MLP_NSPLIT
-#define SRF_MLP_NSPLIT 0
+#ifndef SRF_MLP_GROUPS
+#define SRF_MLP_GROUPS 2
 #endif
 #ifndef SRF_MLP_PREFETCH
 #define SRF_MLP_PREFETCH 0
 #endif
-constexpr int MLP_THREADS = 320;          // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int GROUPS = SRF_MLP_GROUPS;
+constexpr int COLS = 64 / GROUPS;                 // columns of a 64-wide block owned by one epilogue warp
+constexpr int EPI_THREADS = 128 * GROUPS;
+constexpr int MLP_THREADS = 64 + EPI_THREADS;     // warp 0 producer, warp 1 MMA, then the epilogue warps
 constexpr int EPI_WARP0 = 2;
-constexpr int KBLOCK_BYTES = 128 * 128;   // 128 rows x 64 bf16
-constexpr int IMAGE_BYTES = 128 * 128;    // packed weight image: 128 output units x one 64-wide K block
-#if SRF_MLP_NSPLIT
-constexpr int STAGE_BYTES = IMAGE_BYTES;  // one image per ring stage
-constexpr int NUM_STAGES = 6;
-#else
-constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;  // both 128-row halves of a K block per ring stage
+constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
+constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
+constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
 constexpr int NUM_STAGES = 3;
-#endif
-constexpr int MAX_SIDE = 4608;            // floats
+constexpr int MAX_SIDE = 4608;                    // floats
 
 struct alignas(1024) MlpSmem {
   uint8_t a[6][KBLOCK_BYTES];             // E, H0..H3, V
   uint8_t w[NUM_STAGES][STAGE_BYTES];
   float side[MAX_SIDE];
-  float part[2][128][4];                  // head partial sums handed from column-half 1 to column-half 0
+  float part[2][GROUPS][128][4];          // head partial sums of each column group
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
   uint64_t a_ready[6];                    // per A region: written and visible to the async proxy
-  uint64_t d_full[4];                     // accumulator [buffer][128-column half] complete
+  uint64_t d_full[2];                     // accumulator buffer complete
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // sin/cos of 2^k x for k = k0 .. k0+count-1 by angle doubling from one accurate sincosf
 template <typename F>
@@ -113,6 +111,13 @@ __device__ __forceinline__ void store_bf16(uint8_t* block, int row, int col, flo
   *reinterpret_cast<__nv_bfloat16*>(block + off) = __float2bfloat16_rn(v);
 }
 
+template <int N>
+__device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_load<32>(uint32_t taddr, uint32_t (&v)[32]) { ptx::tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_load<16>(uint32_t taddr, uint32_t (&v)[16]) { ptx::tmem_ld16(taddr, v); }
+
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __grid_constant__ MlpProgram prog,
                                                                       const MlpArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -123,8 +128,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
-    for (int r = 0; r < 6; ++r) ptx::mbar_init(&sm.a_ready[r], 8);
-    for (int b = 0; b < 4; ++b) ptx::mbar_init(&sm.d_full[b], 1);
+    for (int r = 0; r < 6; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * GROUPS);
+    ptx::mbar_init(&sm.d_full[0], 1);
+    ptx::mbar_init(&sm.d_full[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
@@ -132,7 +138,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  const int my_tiles = (args.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  long long total = args.total;
+  if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
+  const int num_tiles = (int)((total + 127) / 128);
+  const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer
@@ -141,15 +150,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       for (int t = 0; t < my_tiles; ++t) {
         for (int l = 0; l < prog.num_layers; ++l) {
           const MlpLayer& L = prog.layers[l];
-#if SRF_MLP_NSPLIT
-          const int nstages = (L.n >> 7) * L.num_kblocks;       // [n half][K block] images of 128 x 64
-          for (int s = 0; s < nstages; ++s, ++it) {
-            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
-            ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
-            ptx::mbar_arrive_expect_tx(&sm.w_full[st], IMAGE_BYTES);
-            ptx::bulk_g2s(sm.w[st], args.weights + L.weight_offset + (size_t)s * IMAGE_BYTES, IMAGE_BYTES, &sm.w_full[st]);
-          }
-#else
           const int halves = L.n >> 7;
           for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
             const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
@@ -160,7 +160,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
                             args.weights + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * IMAGE_BYTES, IMAGE_BYTES,
                             &sm.w_full[st]);
           }
-#endif
         }
       }
     }
@@ -174,57 +173,61 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
           const MlpLayer& L = prog.layers[l];
           const uint32_t buf = layer_count & 1;
-#if SRF_MLP_NSPLIT
-          const int passes = L.n >> 7;
-          const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
-#else
-          const int passes = 1;
           const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
-#endif
-          for (int nh = 0; nh < passes; ++nh) {
-            const uint32_t d_addr = tmem + buf * 256 + nh * 128;
-            bool first = true;
-            for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
-              const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
-              const int reg = L.kblock_region[kb];
-              if (!((a_seen >> reg) & 1)) {
-                ptx::mbar_wait(&sm.a_ready[reg], (a_phase >> reg) & 1);
-                a_phase ^= 1u << reg;
-                a_seen |= 1u << reg;
-              }
-              ptx::mbar_wait(&sm.w_full[st], ph);
-              ptx::tc_fence_after();
-              const uint32_t a_base = ptx::smem_u32(sm.a[reg]);
-              const uint32_t b_base = ptx::smem_u32(sm.w[st]);
-              for (int k = 0; k < L.kblock_ksteps[kb]; ++k) {
-                ptx::umma_bf16(d_addr, ptx::make_sw128_desc(a_base + k * 32), ptx::make_sw128_desc(b_base + k * 32), idesc,
-                               first ? 0u : 1u);
-                first = false;
-              }
-              ptx::umma_commit(&sm.w_empty[st]);
+          const uint32_t d_addr = tmem + buf * 256;
+          bool first = true;
+          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
+            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
+            const int reg = L.kblock_region[kb];
+            if (!((a_seen >> reg) & 1)) {
+              ptx::mbar_wait(&sm.a_ready[reg], (a_phase >> reg) & 1);
+              a_phase ^= 1u << reg;
+              a_seen |= 1u << reg;
             }
-            ptx::umma_commit(&sm.d_full[buf * 2 + nh]);
+            ptx::mbar_wait(&sm.w_full[st], ph);
+            ptx::tc_fence_after();
+            const uint32_t a_base = ptx::smem_u32(sm.a[reg]);
+            const uint32_t b_base = ptx::smem_u32(sm.w[st]);
+            for (int k = 0; k < L.kblock_ksteps[kb]; ++k) {
+              ptx::umma_bf16(d_addr, ptx::make_sw128_desc(a_base + k * 32), ptx::make_sw128_desc(b_base + k * 32), idesc,
+                             first ? 0u : 1u);
+              first = false;
+            }
+            ptx::umma_commit(&sm.w_empty[st]);
           }
+          ptx::umma_commit(&sm.d_full[buf]);
           // the epilogue of this layer rewrites H (write_h) - its blocks must be re-acquired
           if (L.write_h) a_seen &= ~0x1Eu;
         }
         a_seen = 0;                      // next tile: E and V are rewritten as well
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else {
     // ------------------------------------------------------------ encoding + epilogue warps
-    const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;        // TMEM lane quarter this warp may read: fixed by hardware to warp_id % 4
-    const int half = ew >> 2;            // column half of every 64-wide block this warp owns
+    const int grp = (warp - EPI_WARP0) >> 2;   // column group of every 64-wide block this warp owns
     const int row = quarter * 32 + lane;
     uint32_t layer_count = 0;
     uint32_t d_phase = 0;                // bit b: parity to wait for on d_full[b]
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long m = tile * 128 + row;
-      const bool valid = m < args.total;
-      // ---- sample point and encodings (split between the two column halves by octave)
-      {
+      const bool valid = m < total;
+      // ---- region 0 (and 5): precomputed rows, or sample point + encodings (split between groups 0 and 1 by octave)
+      if (args.rows != nullptr) {
+        if (grp < 2) {
+          uint8_t* E = sm.a[0];
+          float4 x[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            x[q] = valid ? __ldg(reinterpret_cast<const float4*>(args.rows + m * 32 + grp * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            *reinterpret_cast<uint4*>(E + ptx::sw128_offset(row, grp * 2 + u)) =
+                make_uint4(ptx::pack_bf16(x[2 * u].x, x[2 * u].y), ptx::pack_bf16(x[2 * u].z, x[2 * u].w),
+                           ptx::pack_bf16(x[2 * u + 1].x, x[2 * u + 1].y), ptx::pack_bf16(x[2 * u + 1].z, x[2 * u + 1].w));
+        }
+      } else if (grp < 2) {
         float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
         if (valid) {
           const long long r = m / args.S;
@@ -238,15 +241,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         }
         uint8_t* E = sm.a[0];
         const int deg = prog.points_degree;
-        const int split = (deg + 1) / 2;                 // octaves [0, split) by half 0, the rest by half 1
-        if (half == 0) {
+        const int split = (deg + 1) / 2;                 // octaves [0, split) by group 0, the rest by group 1
+        if (grp == 0) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) store_bf16(E, row, c, p[c]);
         } else {
           for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
         }
-        const int k0 = half == 0 ? 0 : split;
-        const int cnt = half == 0 ? split : deg - split;
+        const int k0 = grp == 0 ? 0 : split;
+        const int cnt = grp == 0 ? split : deg - split;
         if (cnt > 0) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         if (prog.views_degree >= 0) {
           uint8_t* V = sm.a[5];
           const int vdeg = prog.views_degree;
-          if (half == 0) {
+          if (grp == 0) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               store_bf16(V, row, c, vd[c]);
@@ -272,12 +275,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             for (int c = 3 + 6 * vdeg; c < 64; ++c) store_bf16(V, row, c, 0.f);
           }
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(&sm.a_ready[0]);
-          if (prog.views_degree >= 0) ptx::mbar_arrive(&sm.a_ready[5]);
-        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&sm.a_ready[0]);
+        if (prog.views_degree >= 0) ptx::mbar_arrive(&sm.a_ready[5]);
       }
       // ---- layer epilogues
       for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
@@ -288,14 +291,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         const int head_rows = head == 1 ? 1 : (head == 2 ? 4 : (head == 3 ? 3 : 0));
         const float* hw = sm.side + L.head_offset;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + half * 32;
+        const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + grp * COLS;
 
-        // bias + activation (+ head partial dot products) on one 32-column slice, packed to bf16 pairs
-        auto compute = [&](uint32_t (&v)[32], uint32_t (&pk)[16], int kb) {
-          const int col0 = kb * 64 + half * 32;
+        // bias + activation (+ head partial dot products) on one COLS-column slice, packed to bf16 pairs
+        auto compute = [&](uint32_t (&v)[COLS], uint32_t (&pk)[COLS / 2], int kb) {
+          const int col0 = kb * 64 + grp * COLS;
           const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < COLS / 4; ++q) {
             const float4 b = b4[q];
             float x0 = __uint_as_float(v[4 * q + 0]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
             float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             const float4* w4 = reinterpret_cast<const float4*>(hw + hr * n + col0);
             float a = hacc[hr];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < COLS / 4; ++q) {
               const float4 w = w4[q];
               a = fmaf(__uint_as_float(v[4 * q + 0]), w.x, a); a = fmaf(__uint_as_float(v[4 * q + 1]), w.y, a);
               a = fmaf(__uint_as_float(v[4 * q + 2]), w.z, a); a = fmaf(__uint_as_float(v[4 * q + 3]), w.w, a);
@@ -315,96 +318,68 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             hacc[hr] = a;
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         };
-        // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H)
-        auto store = [&](const uint32_t (&pk)[16], int kb) {
+        // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H:
+        // every MMA of this layer has retired once d_full fired)
+        auto store = [&](const uint32_t (&pk)[COLS / 2], int kb) {
           if (!write_h) return;
           uint8_t* H = sm.a[1 + kb];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(H + ptx::sw128_offset(row, half * 4 + u)) =
+          for (int u = 0; u < COLS / 8; ++u)
+            *reinterpret_cast<uint4*>(H + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
                 make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
         };
-        auto wait_half = [&](int nh) {
-          const uint32_t b = buf * 2 + nh;
-          ptx::mbar_wait(&sm.d_full[b], (d_phase >> b) & 1);
-          d_phase ^= 1u << b;
-          ptx::tc_fence_after();
-        };
 
-        // The MMAs of the second accumulator half still read the old H while the first half is already
-        // complete: slices 0 and 1 are computed into registers meanwhile and stored once every MMA of the
-        // layer has retired; TMEM loads run one slice ahead of the math.
-        // Slices 0 and 1 (first accumulator half) are computed into registers and stored only after every
-        // MMA of the layer has retired (with SRF_MLP_NSPLIT the second half's MMAs still read the old H).
-        const bool two_halves = n > 128;
+        ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
+        d_phase ^= 1u << buf;
+        ptx::tc_fence_after();
+        const int nblocks = n >> 6;
 #if SRF_MLP_PREFETCH
-        uint32_t va[32], vb[32], pa[16], pb[16];
-        wait_half(0);
-        ptx::tmem_ld32(t_row, va);
-        ptx::tmem_ld_wait(va);
-        ptx::tmem_ld32(t_row + 64, vb);
-        compute(va, pa, 0);
-        ptx::tmem_ld_wait(vb);
-        if (two_halves) {
-          if (SRF_MLP_NSPLIT) wait_half(1);
-          ptx::tmem_ld32(t_row + 128, va);
-        }
-        compute(vb, pb, 1);
-        store(pa, 0);
-        store(pb, 1);
-        if (two_halves) {
+        uint32_t va[COLS], vb[COLS], pk[COLS / 2];
+        tmem_load<COLS>(t_row, va);
+        for (int kb = 0; kb < nblocks; kb += 2) {
           ptx::tmem_ld_wait(va);
-          ptx::tmem_ld32(t_row + 192, vb);
-          compute(va, pa, 2);
-          store(pa, 2);
-          ptx::tmem_ld_wait(vb);
-          compute(vb, pb, 3);
-          store(pb, 3);
+          if (kb + 1 < nblocks) tmem_load<COLS>(t_row + (kb + 1) * 64, vb);
+          compute(va, pk, kb);
+          store(pk, kb);
+          if (kb + 1 < nblocks) {
+            ptx::tmem_ld_wait(vb);
+            if (kb + 2 < nblocks) tmem_load<COLS>(t_row + (kb + 2) * 64, va);
+            compute(vb, pk, kb + 1);
+            store(pk, kb + 1);
+          }
         }
 #else
-        uint32_t va[32], pa[16], pb[16];
-        wait_half(0);
-        ptx::tmem_ld32(t_row, va);
-        ptx::tmem_ld_wait(va);
-        compute(va, pa, 0);
-        if (!SRF_MLP_NSPLIT) store(pa, 0);
-        ptx::tmem_ld32(t_row + 64, va);
-        ptx::tmem_ld_wait(va);
-        compute(va, pb, 1);
-        if (SRF_MLP_NSPLIT) {
-          if (two_halves) wait_half(1);
-          store(pa, 0);
-        }
-        store(pb, 1);
-        if (two_halves) {
-          ptx::tmem_ld32(t_row + 128, va);
+        uint32_t va[COLS], pk[COLS / 2];
+        for (int kb = 0; kb < nblocks; ++kb) {
+          tmem_load<COLS>(t_row + kb * 64, va);
           ptx::tmem_ld_wait(va);
-          compute(va, pa, 2);
-          store(pa, 2);
-          ptx::tmem_ld32(t_row + 192, va);
-          ptx::tmem_ld_wait(va);
-          compute(va, pb, 3);
-          store(pb, 3);
+          compute(va, pk, kb);
+          store(pk, kb);
         }
 #endif
         ptx::tc_fence_before();
         if (head_rows > 0) {
           const int slot = head == 3 ? 1 : 0;
-          if (half == 1) {
+          if (grp != 0) {
 #pragma unroll
-            for (int hr = 0; hr < 4; ++hr) sm.part[slot][row][hr] = hacc[hr];
+            for (int hr = 0; hr < 4; ++hr) sm.part[slot][grp][row][hr] = hacc[hr];
           }
           epi_bar_sync();
-          if (half == 0 && valid) {
+          if (grp == 0 && valid) {
             const float* hb = hw + head_rows * n;
             float o[4];
 #pragma unroll
-            for (int hr = 0; hr < 4; ++hr) o[hr] = hacc[hr] + sm.part[slot][row][hr] + (hr < head_rows ? hb[hr] : 0.f);
+            for (int hr = 0; hr < 4; ++hr) {
+              float a = hacc[hr];
+#pragma unroll
+              for (int g = 1; g < GROUPS; ++g) a += sm.part[slot][g][row][hr];
+              o[hr] = a + (hr < head_rows ? hb[hr] : 0.f);
+            }
             if (head == 1 || head == 2) {
               float sg = o[0];
               if (args.noise != nullptr) sg += args.noise[m];
@@ -432,58 +407,87 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 
 using namespace srf;
 
+namespace {
+int validate_program(const MlpProgram& prog, const char* where, bool rows_mode) {
+  SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= MLP_MAX_LAYERS, where, "bad layer count");
+  SRF_REQUIRE(prog.points_degree >= 0 && prog.points_degree <= 10 && prog.views_degree <= 4, where,
+              "encoding degree out of range (points <= 10, views <= 4)");
+  SRF_REQUIRE(prog.side_count <= MAX_SIDE, where, "side table too large");
+  int used_any = 0;
+  for (int l = 0; l < prog.num_layers; ++l) {
+    const MlpLayer& L = prog.layers[l];
+    SRF_REQUIRE(L.n == 256 || L.n == 128, where, "layer width must be 128 or 256");
+    SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= MLP_MAX_KBLOCKS, where, "bad K-block count");
+    SRF_REQUIRE((L.bias_offset & 3) == 0 && (L.head_offset & 3) == 0, where, "side-table offsets must be multiples of 4");
+    int used = 0;
+    for (int kb = 0; kb < L.num_kblocks; ++kb) {
+      SRF_REQUIRE(L.kblock_region[kb] >= 0 && L.kblock_region[kb] <= 5 && L.kblock_ksteps[kb] >= 1 && L.kblock_ksteps[kb] <= 4,
+                  where, "bad K-block descriptor");
+      SRF_REQUIRE(!((used >> L.kblock_region[kb]) & 1), where, "a region may appear once per layer");
+      used |= 1 << L.kblock_region[kb];
+    }
+    used_any |= used;
+    // barrier generations: whatever an epilogue writes must be consumed in full by the following layer
+    if (l == 0) SRF_REQUIRE(used & 1, where, "layer 0 must read region 0");
+    if (l > 0) {
+      const MlpLayer& P = prog.layers[l - 1];
+      const int written = P.write_h ? (((1 << (P.n >> 6)) - 1) << 1) : 0;
+      SRF_REQUIRE((used & 0x1E) == written, where, "a layer must read exactly the H blocks the previous epilogue wrote");
+    }
+    SRF_REQUIRE(!(L.write_h && l == prog.num_layers - 1), where, "last layer cannot write H");
+  }
+  SRF_REQUIRE(rows_mode ? prog.views_degree < 0 : true, where, "rows mode has no view encoding");
+  SRF_REQUIRE((prog.views_degree >= 0) == (((used_any >> 5) & 1) != 0), where,
+              "view encoding (region 5) must be used iff views_degree >= 0");
+  return 0;
+}
+
+int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, void* stream, const char* where) {
+  const size_t smem = sizeof(MlpSmem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(where, cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long tiles = (max_total + 127) / 128;
+  const int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  nerf_mlp_fwd_kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, a);
+  return check_launch(where);
+}
+}  // namespace
+
 SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
                              const float* rays_d, const float* z, const float* view_dirs, const float* noise,
                              int64_t num_rays, int num_samples, float* sigma, float* rgb, void* stream) {
   if (num_rays == 0) return 0;
   SRF_REQUIRE(program && weights && side && rays_o && rays_d && z && sigma && rgb, "srf_nerf_mlp_fwd", "null pointer");
   MlpProgram prog = *reinterpret_cast<const MlpProgram*>(program);
-  SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= MLP_MAX_LAYERS, "srf_nerf_mlp_fwd", "bad layer count");
-  SRF_REQUIRE(prog.points_degree >= 0 && prog.points_degree <= 10 && prog.views_degree <= 4, "srf_nerf_mlp_fwd",
-              "encoding degree out of range (points <= 10, views <= 4)");
-  SRF_REQUIRE(prog.side_count <= MAX_SIDE, "srf_nerf_mlp_fwd", "side table too large");
+  if (validate_program(prog, "srf_nerf_mlp_fwd", false)) return 1;
   SRF_REQUIRE(prog.views_degree < 0 || view_dirs != nullptr, "srf_nerf_mlp_fwd", "view_dirs required by the program");
-  int used_any = 0;
-  for (int l = 0; l < prog.num_layers; ++l) {
-    const MlpLayer& L = prog.layers[l];
-    SRF_REQUIRE(L.n == 256 || L.n == 128, "srf_nerf_mlp_fwd", "layer width must be 128 or 256");
-    SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= MLP_MAX_KBLOCKS, "srf_nerf_mlp_fwd", "bad K-block count");
-    SRF_REQUIRE(!L.write_h || L.n == 256, "srf_nerf_mlp_fwd", "hidden activations are 256 wide");
-    int used = 0;
-    for (int kb = 0; kb < L.num_kblocks; ++kb) {
-      SRF_REQUIRE(L.kblock_region[kb] >= 0 && L.kblock_region[kb] <= 5 && L.kblock_ksteps[kb] >= 1 &&
-                      L.kblock_ksteps[kb] <= 4, "srf_nerf_mlp_fwd", "bad K-block descriptor");
-      SRF_REQUIRE(!((used >> L.kblock_region[kb]) & 1), "srf_nerf_mlp_fwd", "a region may appear once per layer");
-      used |= 1 << L.kblock_region[kb];
-    }
-    used_any |= used;
-    // barrier generations: whatever an epilogue writes must be consumed in full by the following layer
-    if (l == 0) SRF_REQUIRE(used & 1, "srf_nerf_mlp_fwd", "layer 0 must read the point encoding (region 0)");
-    if (l > 0 && prog.layers[l - 1].write_h)
-      SRF_REQUIRE((used & 0x1E) == 0x1E, "srf_nerf_mlp_fwd", "a layer after write_h must read H0..H3");
-    if (l > 0 && !prog.layers[l - 1].write_h)
-      SRF_REQUIRE((used & 0x1E) == 0, "srf_nerf_mlp_fwd", "H is stale after a layer without write_h");
-    SRF_REQUIRE(!(L.write_h && l == prog.num_layers - 1), "srf_nerf_mlp_fwd", "last layer cannot write H");
-  }
-  SRF_REQUIRE((prog.views_degree >= 0) == (((used_any >> 5) & 1) != 0), "srf_nerf_mlp_fwd",
-              "view encoding (region 5) must be used iff views_degree >= 0");
-  MlpArgs a;
+  MlpArgs a{};
   a.weights = reinterpret_cast<const uint8_t*>(weights);
   a.side = side; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.view_dirs = view_dirs; a.noise = noise;
   a.sigma = sigma; a.rgb = rgb;
   a.total = (long long)num_rays * num_samples;
   a.S = num_samples;
-  a.num_tiles = (int)((a.total + 127) / 128);
-  const size_t smem = sizeof(MlpSmem) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail("srf_nerf_mlp_fwd", cudaGetErrorString(e));
-    configured = true;
-  }
-  const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
-  nerf_mlp_fwd_kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, a);
-  return check_launch("srf_nerf_mlp_fwd");
+  return launch_mlp(prog, a, a.total, stream, "srf_nerf_mlp_fwd");
+}
+
+SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const float* rows, const int* count,
+                             int64_t max_rows, float* rgb, void* stream) {
+  if (max_rows == 0) return 0;
+  SRF_REQUIRE(program && weights && side && rows && rgb, "srf_mlp_rows_fwd", "null pointer");
+  MlpProgram prog = *reinterpret_cast<const MlpProgram*>(program);
+  if (validate_program(prog, "srf_mlp_rows_fwd", true)) return 1;
+  for (int l = 0; l < prog.num_layers; ++l)
+    SRF_REQUIRE(prog.layers[l].head == 0 || prog.layers[l].head == 3, "srf_mlp_rows_fwd", "only the rgb head is supported in rows mode");
+  MlpArgs a{};
+  a.weights = reinterpret_cast<const uint8_t*>(weights);
+  a.side = side; a.rows = rows; a.count = count; a.rgb = rgb;
+  a.total = max_rows;
+  a.S = 1;
+  return launch_mlp(prog, a, max_rows, stream, "srf_mlp_rows_fwd");
 }
 
 SRF_API int srf_nerf_mlp_program_bytes(void) { return (int)sizeof(MlpProgram); }

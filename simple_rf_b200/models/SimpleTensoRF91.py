@@ -1,0 +1,510 @@
+"""Drop-in Simple-TensoRF model class backed by the sm_100a kernels.
+
+Resolvable by the reference's unmodified factory (src/models/ModelFactory02.py:10-22): module
+`SimpleTensoRF91` -> class `SimpleTensoRF`.  Mirrors the public surface of src/models/SimpleTensoRF09.py:
+`forward` dict contract (:133-162, :194-351), `get_trainable_parameters` with the `*_tensor_params` /
+`*_network_params` groups (:1167-1194), `optimizers` hand-off (:98-113), in-forward model surgery
+(alphaMask rebuild, shrink, upsampling, optimiser reconfiguration, :821-944), `augmented_models`, and
+state-dict compatible names (`coarse_model.matrices_density.0`, `coarse_model.alpha_mask.alpha_volume`, ...).
+
+Per-ray arithmetic (ray generation, stratified depths, occupancy test, compaction, VM density / appearance
+gathers, colour MLP, compositing) runs in hand-written CUDA kernels; planes stay `nn.Parameter`s of logical
+shape [1,C,H,W] (TotalVariationLoss04.py:85-95 differentiates them directly), channels-last and bit-packed
+copies are derived per call.  Grid surgery (5 iterations out of 25 000) uses the same kernels for the dense
+density evaluation and plain tensor ops for the pooling / resampling.
+"""
+import numpy
+import torch
+import torch.nn.functional as F
+from torch.nn import ModuleDict, ModuleList
+
+from .. import _lib as L
+from .. import ops
+from .. import tensorf_ops as T
+from ..nerf_program import PackedRowsMLP
+from .SimpleNeRF91 import ExtrinsicsLearner, IntrinsicsLearner, _coarse_ladder
+
+
+class SimpleTensoRF(torch.nn.Module):
+    def __init__(self, configs: dict, model_configs: dict):
+        super().__init__()
+        self.configs = configs
+        self.model_configs = model_configs
+        self.ndc = self.configs['data_loader']['ndc']
+        if not self.ndc:
+            raise NotImplementedError('only the NDC path (every shipped config) is implemented')
+        mc = self.configs['model']
+        self.coarse_model_needed = 'coarse_model' in mc
+        self.fine_model_needed = 'fine_model' in mc
+        if self.fine_model_needed:
+            raise NotImplementedError('shipped Simple-TensoRF configs have no fine model')
+        if self.coarse_model_needed and mc['coarse_model']['predict_visibility']:
+            raise NotImplementedError('predict_visibility raises upstream as well (SimpleTensoRF09.py:1274-1275)')
+        self.rng_mode = mc.get('rng_mode', 'reference')
+        self.eval_chunk = int(mc.get('eval_chunk', 1 << 14))
+        self.coarse_model = None
+        self.fine_model = None
+        self.augmentations_needed = 'augmentations' in mc
+        if self.augmentations_needed:
+            self.augmented_models = []
+            self.augmented_models_nn = []
+        self._camera_tables = None
+        self.build_nerf()
+        self.optimizers = None
+        self.train_data_preprocessor = None
+
+    def build_nerf(self):
+        mc = self.configs['model']
+        if self.coarse_model_needed:
+            self.coarse_model = VmDecomposedTensor('coarse_model', self.configs, mc['coarse_model'], self.model_configs)
+        self.intrinsics_learner = IntrinsicsLearner(numpy.array(self.model_configs['intrinsics']),
+                                                    learn_focal=mc['learn_camera_focal_length'])
+        self.extrinsics_learner = ExtrinsicsLearner(numpy.array(self.model_configs['extrinsics']),
+                                                    learn_rotation=mc['learn_camera_rotation'],
+                                                    learn_translation=mc['learn_camera_translation'])
+        if self.augmentations_needed:
+            for aug in mc['augmentations']:
+                nn_dict = ModuleDict()
+                entry = {'name': aug['name'], 'coarse_model': None, 'fine_model': None}
+                if 'coarse_model' in aug:
+                    entry['coarse_model'] = VmDecomposedTensor(f"{aug['name']}_coarse_model", self.configs, aug['coarse_model'],
+                                                               self.model_configs)
+                    nn_dict['coarse_model'] = entry['coarse_model']
+                if 'fine_model' in aug:
+                    raise NotImplementedError
+                self.augmented_models.append(entry)
+                self.augmented_models_nn.append(nn_dict)
+            self.augmented_models_nn = ModuleList(self.augmented_models_nn)
+
+    def _tensors(self):
+        out = [self.coarse_model] if self.coarse_model is not None else []
+        if self.augmentations_needed:
+            out += [a['coarse_model'] for a in self.augmented_models if a['coarse_model'] is not None]
+        return out
+
+    def get_trainable_parameters(self, optimizer_configs):
+        groups = []
+        for t in self._tensors():
+            groups.extend(t.get_trainable_parameters(optimizer_configs))
+        return groups
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name == 'optimizers' and value is not None:           # SimpleTensoRF09.py:98-113
+            for t in self._tensors():
+                t.optimizers = value
+
+    def rebuild_camera_params_learners(self, *, intrinsics: numpy.ndarray = None, extrinsics=None, device):
+        mc = self.configs['model']
+        if intrinsics is not None:
+            self.intrinsics_learner = IntrinsicsLearner(intrinsics, learn_focal=mc['learn_camera_focal_length']).to(device)
+        if extrinsics is not None:
+            self.extrinsics_learner = ExtrinsicsLearner(extrinsics, learn_rotation=mc['learn_camera_rotation'],
+                                                        learn_translation=mc['learn_camera_translation']).to(device)
+        self._camera_tables = None
+
+    def forward(self, input_batch: dict, *, retraw: bool = False, sec_views_vis: bool = False, mode: str = None):
+        pixel_id = input_batch['pixel_id']
+        L.require_cuda(pixel_id)
+        if self.training and mode != 'test_camera_params_optimization' and input_batch['sub_batch_index'] == 0:
+            self.run_model_modifications(input_batch['iter_num'])          # SimpleTensoRF09.py:141-145
+        image_id = pixel_id[:, 0].long()
+        intrinsics = self.intrinsics_learner(image_id)
+        # the reference flips x of the per-ray extrinsics in place through a view (SimpleTensoRF09.py:206, App. C5)
+        extrinsics = self.extrinsics_learner(image_id).clone()
+        extrinsics[:, 0, 3] *= -1
+        all_extrinsics = self.extrinsics_learner(torch.arange(input_batch['num_frames'], device=pixel_id.device))
+        if mode == 'camera_params_only':
+            out = {}
+        else:
+            out = self.render(input_batch, retraw=retraw or self.training, mode=mode)
+        out['intrinsics'] = intrinsics
+        out['extrinsics'] = extrinsics
+        out['extrinsics_all'] = all_extrinsics
+        return out
+
+    def run_model_modifications(self, iter_num):
+        for t in self._tensors():
+            t.run_model_modifications(iter_num)
+
+    def _tables(self, device, intrinsics=None, extrinsics=None):
+        if self.extrinsics_learner.learn_rotation or self.extrinsics_learner.learn_translation:
+            raise NotImplementedError('learnable cameras are not supported by the fused ray generation')
+        if intrinsics is not None:
+            return ops.camera_tables(intrinsics, extrinsics, device)
+        if self._camera_tables is None or self._camera_tables[0].device != device:
+            self._camera_tables = ops.camera_tables(self.intrinsics_learner.initial_intrinsics,
+                                                    self.extrinsics_learner.view_matrices(), device)
+        return self._camera_tables
+
+    def render(self, input_dict: dict, *, retraw: bool, mode: str):
+        pixel_id = input_dict['pixel_id']
+        chunk = self.configs['model']['chunk'] if self.training else max(self.eval_chunk, self.configs['model']['chunk'])
+        parts = [self.render_rays(pixel_id[i:i + chunk], input_dict, retraw=retraw, mode=mode)
+                 for i in range(0, pixel_id.shape[0], chunk)]
+        if len(parts) == 1:
+            return parts[0]
+        return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+
+    def render_rays(self, pixel_id, input_dict, *, retraw, mode):
+        mc = self.configs['model']
+        dev = pixel_id.device
+        R = pixel_id.shape[0]
+        h, w = self.model_configs['resolution']
+        rays_o, rays_d, o_ndc, d_ndc, view_dirs = ops.raygen(
+            pixel_id, self._tables(dev), h, w, self.model_configs['near'], half_pixel=True, flip_x=True, ndc=True,
+            viewdirs_from_ndc=True)
+        if mode == 'static_camera':                                          # SimpleTensoRF09.py:222-233
+            cd = input_dict['common_data']
+            pose = cd['processed_view_pose']
+            pose = pose[0] if pose.dim() == 3 else pose
+            k_view = cd.get('view_intrinsic')
+            if k_view is not None and k_view.dim() == 3:
+                k_view = k_view[0]
+            nviews = self.intrinsics_learner.initial_intrinsics.shape[0]
+            ks = self.intrinsics_learner.initial_intrinsics.detach() if k_view is None else k_view[None].expand(nviews, 3, 3)
+            tabs = self._tables(dev, ks, pose[None].expand(nviews, 4, 4))
+            view_dirs = ops.raygen(pixel_id, tabs, h, w, self.model_configs['near'], half_pixel=False, flip_x=False, ndc=True,
+                                   viewdirs_from_ndc=True)[4]
+        out = {'rays_o': rays_o, 'rays_d': rays_d, 'rays_o_ndc': o_ndc, 'rays_d_ndc': d_ndc, 'view_dirs': view_dirs}
+        main = self.coarse_model
+        S = int(main.num_samples)
+        ladder = _coarse_ladder(S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp']).to(dev)
+        perturb = self.training and mc['perturb']
+        if perturb and self.rng_mode == 'reference':
+            z = ops.stratified_z(ladder, R, jitter=torch.rand([R, S]).to(dev))                     # SimpleTensoRF09.py:379
+        elif perturb:
+            z = ops.stratified_z(ladder, R, philox_seed=int(torch.randint(0, 2 ** 31, (1,)).item()))
+        else:
+            z = ops.stratified_z(ladder, R)
+        out['z_vals_coarse'] = z
+        rays = dict(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=o_ndc, rays_d_ndc=d_ndc, view_dirs=view_dirs, z=z)
+        for k, v in main(rays, retraw, white_bkgd=mc['white_bkgd']).items():
+            out[f'{k}_coarse'] = v
+        if self.augmentations_needed and self.training and mode != 'test_camera_params_optimization':
+            for aug in self.augmented_models:
+                if aug['coarse_model'] is not None:                        # same z_vals as the main tensor (:283-296)
+                    for k, v in aug['coarse_model'](rays, retraw, white_bkgd=mc['white_bkgd']).items():
+                        out[f"{aug['name']}_{k}_coarse"] = v
+        if not retraw:
+            for k in [k for k in out if k.startswith('z_vals_') or '_alpha_' in f'_{k}' or '_visibility_' in f'_{k}'
+                      or '_weights_' in f'_{k}']:
+                del out[k]
+        return out
+
+
+class AlphaGridMask(torch.nn.Module):
+    """SimpleTensoRF09.py:1323-1367: binary occupancy volume [1,1,Z,Y,X] (fp32 in memory, bool in checkpoints)."""
+
+    def __init__(self, alpha_volume, bounding_box):
+        super().__init__()
+        self.register_buffer('alpha_volume', torch.tensor(0, dtype=bool))
+        self.register_buffer('bounding_box', torch.zeros(size=(2, 3)))
+        self.register_buffer('bounding_box_size', torch.zeros(size=(3,)))
+        self.register_buffer('resolution', torch.zeros(size=(3,), dtype=torch.long))
+        self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+        self.bounding_box = bounding_box
+        self.bounding_box_size = self.bounding_box[1] - self.bounding_box[0]
+        self.resolution = torch.LongTensor([alpha_volume.shape[-1], alpha_volume.shape[-2], alpha_volume.shape[-3]]).to(alpha_volume.device)
+        self._register_state_dict_hook(self._save_hook)
+        self._register_load_state_dict_pre_hook(self._load_hook)
+        self._bits = None
+
+    def _save_hook(self, obj, state, prefix, *args, **kwargs):
+        state[f'{prefix}alpha_volume'] = state[f'{prefix}alpha_volume'].bool()
+
+    def _load_hook(self, state, prefix, *args, **kwargs):
+        state[f'{prefix}alpha_volume'] = state[f'{prefix}alpha_volume'].float()
+
+    def packed(self):
+        """1 bit / voxel derived cache + host-side box description for the mask kernel."""
+        key = (self.alpha_volume.data_ptr(), self.alpha_volume._version)
+        if self._bits is None or self._bits[0] != key:
+            self._bits = (key, {'bits': T.pack_alpha_bits(self.alpha_volume.float()), 'res': self.resolution.tolist(),
+                                'box_min': self.bounding_box[0].tolist(), 'box_size': self.bounding_box_size.tolist()})
+        return self._bits[1]
+
+
+class MlpFeaturesColorPredictor(torch.nn.Module):
+    """SimpleTensoRF09.py:1370-1421 with both encoding degrees 0 (the shipped setting): parameter container with
+    the reference's `mlp.{0,2,4}` names; evaluated by the tensor-core rows MLP."""
+
+    def __init__(self, tensor_configs, features_dim, num_units):
+        super().__init__()
+        if tensor_configs['features_positional_encoding_degree'] != 0 or tensor_configs['views_positional_encoding_degree'] != 0:
+            raise NotImplementedError('colour predictor encodings other than degree 0 are not shipped')
+        self.input_dim = features_dim + (3 if tensor_configs['use_view_dirs'] else 0)
+        Lin = torch.nn.Linear
+        self.mlp = torch.nn.Sequential(Lin(self.input_dim, num_units), torch.nn.ReLU(inplace=True), Lin(num_units, num_units),
+                                       torch.nn.ReLU(inplace=True), Lin(num_units, 3), torch.nn.Sigmoid())
+        torch.nn.init.constant_(self.mlp[-2].bias, 0)
+        self._packed = PackedRowsMLP(self.input_dim, prefix='mlp', units=num_units)
+        self._version = None
+
+    def packed(self):
+        params = dict(self.named_parameters())
+        version = tuple((p.data_ptr(), p._version) for p in params.values())
+        if version != self._version:
+            self._packed.refresh(params)
+            self._version = version
+        return self._packed
+
+
+class _RowsMLP(torch.autograd.Function):
+    """Forward: tensor-core rows MLP.  Backward (round-1 interim): library GEMMs through torch on the
+    `count` live rows."""
+
+    @staticmethod
+    def forward(ctx, predictor, comp, rows, *params):
+        rgb = predictor.packed().forward(rows, comp.count, rows.shape[0])
+        ctx.predictor, ctx.comp = predictor, comp
+        ctx.save_for_backward(rows, *params)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        rows, *params = ctx.saved_tensors
+        n = int(ctx.comp.count.item())
+        g_rows = torch.zeros_like(rows)
+        grads = [None] * len(params)
+        if n > 0:
+            with torch.enable_grad():
+                x = rows[:n, :ctx.predictor.input_dim].detach().requires_grad_()
+                ps = [p.detach().requires_grad_() for p in params]
+                hcur = F.relu(F.linear(x, ps[0], ps[1]))
+                hcur = F.relu(F.linear(hcur, ps[2], ps[3]))
+                y = torch.sigmoid(F.linear(hcur, ps[4], ps[5]))
+                gx, *grads = torch.autograd.grad(y, [x] + ps, g_rgb[:n])
+            g_rows[:n, :ctx.predictor.input_dim] = gx
+        return (None, None, g_rows, *grads)
+
+
+class VmDecomposedTensor(torch.nn.Module):
+    """SimpleTensoRF09.py:582-961 (LowRankTensor) + :1126-1320 (VmDecomposedTensor)."""
+
+    def __init__(self, name, configs, tensor_configs, model_configs):
+        super().__init__()
+        self.name = name
+        self.configs = configs
+        self.tensor_configs = tensor_configs
+        self.model_configs = model_configs
+        self.ndc = configs['data_loader']['ndc']
+        self.predict_visibility = tensor_configs['predict_visibility']
+        if tensor_configs['decomposition_type'] != 'VectorMatrix':
+            raise NotImplementedError('CandecompParafac is never selected by a shipped config (SURVEY.md App. C9)')
+        for buf, val in (('bounding_box', torch.zeros(2, 3)), ('resolution', torch.zeros(3)), ('num_samples', torch.tensor(0)),
+                         ('bounding_box_size', torch.zeros(3)), ('voxel_length', torch.zeros(3)), ('step_size', torch.tensor(0))):
+            self.register_buffer(buf, val)
+        bbox = torch.tensor(tensor_configs.get('bounding_box', model_configs['bounding_box']))
+        self.matrix_axes = T.MATRIX_AXES
+        self.vector_axes = T.VECTOR_AXES
+        self.alpha_mask = None
+        self.optimizers = None
+        self.update_tensor_params(self.compute_resolution_in_voxels(tensor_configs['num_voxels_initial'], bbox), bbox)
+        tc = tensor_configs
+        self.matrices_density, self.vectors_density = self.create_decomposed_tensor(tc['num_components_density'], self.resolution, 0.1)
+        self.matrices_color, self.vectors_color = self.create_decomposed_tensor(tc['num_components_color'], self.resolution, 0.1)
+        self.basis_matrix_color = torch.nn.Linear(sum(tc['num_components_color']), tc['features_dimension_color'], bias=False)
+        if tc['density_predictor'] not in ('ReLU', 'SoftPlus'):
+            raise NotImplementedError
+        self.density_predictor = tc['density_predictor']
+        if tc['color_predictor'] != 'MLP_Features':
+            raise NotImplementedError
+        self.color_predictor = MlpFeaturesColorPredictor(tc, tc['features_dimension_color'], tc['num_units_color_predictor'])
+        self._register_load_state_dict_pre_hook(self._load_hook)
+
+    # ---------------------------------------------------------------- geometry bookkeeping (:625-665)
+    @staticmethod
+    def compute_resolution_in_voxels(num_voxels, bounding_box):
+        lo, hi = bounding_box
+        voxel = ((hi - lo).prod() / num_voxels).pow(1 / 3)
+        return ((hi - lo) / voxel).long()
+
+    def compute_num_samples(self, resolution, voxels_per_sample):
+        n = (torch.linalg.norm(resolution.float()) / voxels_per_sample).round().long()
+        return min(self.tensor_configs['num_samples_max'], n)
+
+    def update_tensor_params(self, new_resolution, new_bounding_box):
+        self.bounding_box = new_bounding_box.float()
+        self.bounding_box_size = self.bounding_box[1] - self.bounding_box[0]
+        self.resolution = new_resolution.long()
+        self.voxel_length = self.bounding_box_size / (self.resolution - 1)
+        self.step_size = torch.mean(self.voxel_length) * self.tensor_configs['num_voxels_per_sample']
+        self.num_samples = self.compute_num_samples(self.resolution, self.tensor_configs['num_voxels_per_sample'])
+
+    def create_decomposed_tensor(self, comps, resolution, scale):
+        mats, vecs = [], []
+        for i in range(3):
+            a0, a1 = self.matrix_axes[i]
+            mats.append(torch.nn.Parameter(scale * torch.randn((1, comps[i], resolution[a1], resolution[a0]))))
+            vecs.append(torch.nn.Parameter(scale * torch.randn((1, comps[i], resolution[self.vector_axes[i]], 1))))
+        return torch.nn.ParameterList(mats), torch.nn.ParameterList(vecs)
+
+    def get_trainable_parameters(self, optimizer_configs):
+        tensor_params, network_params = torch.nn.ParameterList(), torch.nn.ParameterList()
+        tensor_params.extend(self.vectors_density)
+        tensor_params.extend(self.matrices_density)
+        tensor_params.extend(self.vectors_color)
+        tensor_params.extend(self.matrices_color)
+        network_params.extend(self.basis_matrix_color.parameters())
+        network_params.extend(self.color_predictor.parameters())
+        return [{'name': f'{self.name}_tensor_params', 'params': tensor_params, 'lr': optimizer_configs['lr_initial_tensor']},
+                {'name': f'{self.name}_network_params', 'params': network_params, 'lr': optimizer_configs['lr_initial_network']}]
+
+    def _load_hook(self, state, prefix, *args, **kwargs):
+        """:946-961 + :1196-1212: rebuild the alpha mask and resize planes/lines before loading."""
+        if f'{prefix}alpha_mask.alpha_volume' in state:
+            self.alpha_mask = AlphaGridMask(state[f'{prefix}alpha_mask.alpha_volume'].float(), state[f'{prefix}alpha_mask.bounding_box'])
+        new_res = state[f'{prefix}resolution']
+        self.matrices_density, self.vectors_density = self.upsample_vectors_and_matrices(self.matrices_density, self.vectors_density, new_res)
+        self.matrices_color, self.vectors_color = self.upsample_vectors_and_matrices(self.matrices_color, self.vectors_color, new_res)
+
+    # ---------------------------------------------------------------- forward (:701-761)
+    def _geometry(self, rays_o_s, rays_d_s, z):
+        return T.VmGeometry(rays_o_s, rays_d_s, z, self.bounding_box[0], self.bounding_box_size, self.resolution)
+
+    def forward(self, rays: dict, retraw: bool, white_bkgd=False):
+        tc = self.tensor_configs
+        z = rays['z']
+        R, S = z.shape
+        so, sd = rays['rays_o_ndc'], rays['rays_d_ndc']
+        alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
+        valid = T.validity_compact(so, sd, z, self.bounding_box, alpha)
+        geom = self._geometry(so, sd, z)
+        sigma = T.vm_density(geom, valid, list(self.matrices_density), list(self.vectors_density),
+                             softplus=self.density_predictor == 'SoftPlus', offset=tc['density_offset'])
+        with torch.no_grad():                                               # weights only decide where colour is read (:726)
+            w0 = ops.composite(sigma.detach()[..., 0], None, z, rays['rays_o'], rays['rays_d'], sd, ndc=True,
+                               distance_scale=tc['distance_scale'], per_sample=False)['weights']
+        surface = T.threshold_compact(w0, tc['ray_marching_weight_threshold'])
+        rows = T.vm_color_rows(geom, surface, rays['view_dirs'], self.basis_matrix_color.weight, list(self.matrices_color),
+                               list(self.vectors_color))
+        cp = self.color_predictor
+        if torch.is_grad_enabled() and any(p.requires_grad for p in cp.parameters()):
+            rgb_rows = _RowsMLP.apply(cp, surface, rows, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)])
+        else:
+            rgb_rows = cp.packed().forward(rows, surface.count, rows.shape[0])
+        rgb = T._ScatterRows.apply(surface, rgb_rows, R * S).view(R, S, 3)
+        white = white_bkgd or bool(self.training and (torch.rand((1,)) < 0.5))      # :746
+        vr = ops.composite(sigma[..., 0], rgb, z, rays['rays_o'], rays['rays_d'], sd, ndc=True, white_bkgd=white,
+                           distance_scale=tc['distance_scale'], per_sample=True)
+        out = {k: vr[k] for k in ('acc', 'alpha', 'visibility', 'weights', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'rgb')}
+        if retraw:
+            out['raw_sigma'] = sigma
+            out['raw_rgb'] = rgb
+        return out
+
+    # ---------------------------------------------------------------- dense density for surgery (:878-897)
+    @torch.no_grad()
+    def compute_alpha(self, xyz, length=1):
+        """alpha = 1 - exp(-sigma * length) at world points xyz [N,3]: each point is a zero-direction 'ray'."""
+        n = xyz.shape[0]
+        out = torch.empty((n,), dtype=torch.float32, device=xyz.device)
+        step = 1 << 22
+        zero_d = torch.zeros((min(step, n), 3), dtype=torch.float32, device=xyz.device)
+        zero_z = torch.zeros((min(step, n), 1), dtype=torch.float32, device=xyz.device)
+        alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
+        for i in range(0, n, step):
+            p = xyz[i:i + step].contiguous()
+            m = p.shape[0]
+            # the reference tests only the alpha mask here, not the box (:879-883)
+            comp = T.validity_compact(p, zero_d[:m], zero_z[:m], [[-3e38] * 3, [3e38] * 3], alpha)
+            geom = self._geometry(p, zero_d[:m], zero_z[:m])
+            sigma = T.vm_density(geom, comp, list(self.matrices_density), list(self.vectors_density),
+                                 softplus=self.density_predictor == 'SoftPlus', offset=self.tensor_configs['density_offset'])
+            out[i:i + m] = 1 - torch.exp(-sigma.view(-1) * length)
+        return out
+
+    # ---------------------------------------------------------------- model surgery (:821-944, :1277-1320)
+    def run_model_modifications(self, iter_num):
+        tc = self.tensor_configs
+        if self.training and iter_num in tc['alpha_mask_update_iters']:
+            new_box = self.update_alpha_mask(iter_num)
+            if iter_num == tc['alpha_mask_update_iters'][0]:
+                self.shrink_tensor(new_box)
+        if self.training and iter_num in tc['tensor_upsampling_iters']:
+            self.upsample_model_resolution(iter_num)
+            self.reconfigure_optimizer()
+
+    def get_new_num_voxels(self, iter_num):
+        iters = self.tensor_configs['tensor_upsampling_iters']
+        if iter_num not in iters:
+            raise RuntimeError('get_new_num_voxels() called at invalid iteration number')
+        k = iters.index(iter_num) + 1
+        lo, hi = numpy.log(self.tensor_configs['num_voxels_initial']), numpy.log(self.tensor_configs['num_voxels_final'])
+        return int(numpy.round(numpy.exp(lo + (hi - lo) * k / len(iters))))
+
+    @torch.no_grad()
+    def update_alpha_mask(self, iter_num):
+        dev = self.bounding_box.device
+        gs = tuple(int(v) for v in self.resolution.tolist())
+        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gs[0]), torch.linspace(0, 1, gs[1]), torch.linspace(0, 1, gs[2]),
+                                             indexing='ij'), -1).to(dev)
+        dense_xyz = self.bounding_box[0] * (1 - samples) + self.bounding_box[1] * samples
+        alpha = self.compute_alpha(dense_xyz.view(-1, 3), self.step_size).view(gs)
+        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gs[::-1])
+        thr = self.tensor_configs['alpha_mask_threshold']
+        alpha = (alpha >= thr).float()
+        self.alpha_mask = AlphaGridMask(alpha, self.bounding_box)
+        valid_xyz = dense_xyz[alpha > 0.5]
+        return torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
+
+    @torch.no_grad()
+    def shrink_tensor(self, new_box):
+        lo, hi = new_box
+        t_l, b_r = (lo - self.bounding_box[0]) / self.voxel_length, (hi - self.bounding_box[0]) / self.voxel_length
+        t_l, b_r = torch.round(torch.round(t_l)).long(), torch.round(b_r).long() + 1
+        b_r = torch.stack([b_r, self.resolution]).amin(0)
+        if not torch.equal(self.alpha_mask.resolution, self.resolution):
+            t_l_r, b_r_r = t_l / (self.resolution - 1), (b_r - 1) / (self.resolution - 1)
+            box = torch.zeros_like(new_box)
+            box[0] = (1 - t_l_r) * self.bounding_box[0] + t_l_r * self.bounding_box[1]
+            box[1] = (1 - b_r_r) * self.bounding_box[0] + b_r_r * self.bounding_box[1]
+            new_box = box
+        self.update_tensor_params(b_r - t_l, new_box)
+        for i in range(3):
+            v = self.vector_axes[i]
+            a0, a1 = self.matrix_axes[i]
+            for vecs, mats in ((self.vectors_density, self.matrices_density), (self.vectors_color, self.matrices_color)):
+                vecs[i] = torch.nn.Parameter(vecs[i].data[..., t_l[v]:b_r[v], :])
+                mats[i] = torch.nn.Parameter(mats[i].data[..., t_l[a1]:b_r[a1], t_l[a0]:b_r[a0]])
+
+    def upsample_model_resolution(self, iter_num):
+        res = self.compute_resolution_in_voxels(self.get_new_num_voxels(iter_num), self.bounding_box)
+        self.update_tensor_params(res, self.bounding_box)
+        self.matrices_density, self.vectors_density = self.upsample_vectors_and_matrices(self.matrices_density, self.vectors_density, self.resolution)
+        self.matrices_color, self.vectors_color = self.upsample_vectors_and_matrices(self.matrices_color, self.vectors_color, self.resolution)
+
+    def upsample_vectors_and_matrices(self, matrices, vectors, new_res):
+        mats, vecs = [], []
+        for i in range(3):
+            a0, a1 = self.matrix_axes[i]
+            v = self.vector_axes[i]
+            mats.append(torch.nn.Parameter(F.interpolate(matrices[i].data, size=(int(new_res[a1]), int(new_res[a0])), mode='bilinear',
+                                                         align_corners=True)))
+            vecs.append(torch.nn.Parameter(F.interpolate(vectors[i].data, size=(int(new_res[v]), 1), mode='bilinear', align_corners=True)))
+        return torch.nn.ParameterList(mats), torch.nn.ParameterList(vecs)
+
+    def reconfigure_optimizer(self):
+        """:916-944, quirks included: groups are re-added with the INITIAL learning rates."""
+        optimizer = self.optimizers['optimizer_nerf']
+        opt_cfg = next(filter(lambda c: c['name'] == 'optimizer_main', self.configs['optimizers']))
+        groups = self.get_trainable_parameters(opt_cfg)
+        for group in groups:
+            index = 0
+            for i, existing in enumerate(optimizer.param_groups):
+                count = len(existing['params'])
+                if existing['name'] == group['name']:
+                    del optimizer.param_groups[i]
+                    for _ in range(count):
+                        keys = list(optimizer.state.keys())
+                        if index < len(keys):
+                            del optimizer.state[keys[index]]
+                        else:
+                            print(f'Unable to delete item at {index} since list has only {len(keys)} elements')
+                else:
+                    index += count
+        for group in groups:
+            optimizer.add_param_group(group)

@@ -132,49 +132,9 @@ class PackedMLP:
             layers.append(('views_linears.0.weight', views_width, kbs, 1, 0, 3))
         assert len(layers) <= MAX_LAYERS
 
-        prog = MlpProgram()
-        prog.num_layers = len(layers)
-        prog.points_degree = self.pdeg
-        prog.views_degree = self.vdeg
-        gather = []
-        side = []
-        woff = 0
-        for li, (name, n, kbs, relu, write_h, head) in enumerate(layers):
-            Lr = prog.layers[li]
-            Lr.num_kblocks = len(kbs)
-            Lr.n, Lr.relu, Lr.write_h, Lr.head = n, relu, write_h, head
-            Lr.weight_offset = woff * 2
-            for bi, (region, cols) in enumerate(kbs):
-                Lr.kblock_region[bi] = region
-                used = max(j for j, c in enumerate(cols) if c >= 0) + 1
-                Lr.kblock_ksteps[bi] = (used + 15) // 16
-            # weight images in streaming order: [128-row half of n][K block] -> 128 x 64 bf16, 128B swizzle
-            e = np.arange(128 * 64)
-            r = e // 64
-            unit = (e % 64) // 8
-            c = ((unit ^ (r & 7)) * 8) + e % 8
-            for nh in range(n // 128):
-                for bi, (region, cols) in enumerate(kbs):
-                    src = np.asarray(cols)[c]
-                    idx = np.where(src >= 0, offs[name] + (nh * 128 + r) * shapes[name][1] + np.maximum(src, 0), zero)
-                    gather.append(idx)
-                    woff += 128 * 64
-            bname = name.replace('.weight', '.bias')
-            side += [zero] * (-len(side) % 4)                      # float4 loads in the epilogue
-            Lr.bias_offset = len(side)
-            side += [offs[bname] + j for j in range(n)]
-            if head:
-                hname = 'views_output_linear' if head == 3 else 'pts_output_linear'
-                rows = shapes[f'{hname}.weight'][0]
-                side += [zero] * (-len(side) % 4)
-                Lr.head_offset = len(side)
-                side += [widx(f'{hname}.weight', r_, c_) for r_ in range(rows) for c_ in range(n)]
-                side += [offs[f'{hname}.bias'] + r_ for r_ in range(rows)]
-        prog.side_count = len(side)
-        self.program = prog
-        self.blob_elems = woff
-        self._gather_np = np.concatenate(gather).astype(np.int64)
-        self._side_np = np.asarray(side, dtype=np.int64)
+        self.program, self.blob_elems, self._gather_np, self._side_np = build_program(
+            layers, shapes, offs, zero, self.pdeg, self.vdeg,
+            head_names={1: 'pts_output_linear', 2: 'pts_output_linear', 3: 'views_output_linear'})
         self._dev = None
         self.blob = None
         self.side = None
@@ -215,3 +175,92 @@ class PackedMLP:
                L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
                L.ptr(sigma), L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)
         return sigma, rgb
+
+
+def build_program(layers, shapes, offs, zero, points_degree, views_degree, head_names):
+    """layers: [(weight name, n, [(region, 64 source columns or -1)], relu, write_h, head)].
+    Returns (MlpProgram, number of bf16 blob elements, blob gather indices, side-table gather indices);
+    indices address the flat parameter vector described by `offs` / `shapes`, `zero` = index of a 0 element."""
+    assert len(layers) <= MAX_LAYERS
+    prog = MlpProgram()
+    prog.num_layers = len(layers)
+    prog.points_degree = points_degree
+    prog.views_degree = views_degree
+    gather, side, woff = [], [], 0
+    e = np.arange(128 * 64)
+    r = e // 64
+    unit = (e % 64) // 8
+    c = ((unit ^ (r & 7)) * 8) + e % 8
+    for li, (name, n, kbs, relu, write_h, head) in enumerate(layers):
+        Lr = prog.layers[li]
+        Lr.num_kblocks = len(kbs)
+        Lr.n, Lr.relu, Lr.write_h, Lr.head = n, relu, write_h, head
+        Lr.weight_offset = woff * 2
+        for bi, (region, cols) in enumerate(kbs):
+            Lr.kblock_region[bi] = region
+            used = max(j for j, cc in enumerate(cols) if cc >= 0) + 1
+            Lr.kblock_ksteps[bi] = (used + 15) // 16
+        # weight images in streaming order: [128-row half of n][K block] -> 128 x 64 bf16, 128B swizzle
+        for nh in range(n // 128):
+            for bi, (region, cols) in enumerate(kbs):
+                src = np.asarray(cols)[c]
+                gather.append(np.where(src >= 0, offs[name] + (nh * 128 + r) * shapes[name][1] + np.maximum(src, 0), zero))
+                woff += 128 * 64
+        bname = name.replace('.weight', '.bias')
+        side += [zero] * (-len(side) % 4)                      # float4 loads in the epilogue
+        Lr.bias_offset = len(side)
+        side += [offs[bname] + j for j in range(n)]
+        if head:
+            hname = head_names[head]
+            rows = shapes[f'{hname}.weight'][0]
+            side += [zero] * (-len(side) % 4)
+            Lr.head_offset = len(side)
+            side += [offs[f'{hname}.weight'] + r_ * shapes[f'{hname}.weight'][1] + c_ for r_ in range(rows) for c_ in range(n)]
+            side += [offs[f'{hname}.bias'] + r_ for r_ in range(rows)]
+    prog.side_count = len(side)
+    return prog, woff, np.concatenate(gather).astype(np.int64), np.asarray(side, dtype=np.int64)
+
+
+class PackedRowsMLP:
+    """Two-hidden-layer MLP over precomputed 32-wide rows (the TensoRF colour predictor, reference
+    models/SimpleTensoRF09.py:1389-1393: Linear(in<=32,128) ReLU Linear(128,128) ReLU Linear(128,3) Sigmoid)."""
+
+    def __init__(self, in_features, prefix='color_predictor.mlp', units=128):
+        assert in_features <= 32 and units == 128
+        self.names = [f'{prefix}.0.weight', f'{prefix}.0.bias', f'{prefix}.2.weight', f'{prefix}.2.bias',
+                      f'{prefix}.4.weight', f'{prefix}.4.bias']
+        shapes = {self.names[0]: (units, in_features), self.names[1]: (units,), self.names[2]: (units, units),
+                  self.names[3]: (units,), self.names[4]: (3, units), self.names[5]: (3,)}
+        offs, o = {}, 0
+        for n in self.names:
+            offs[n] = o
+            o += int(np.prod(shapes[n]))
+        self.flat_size = o
+        cols0 = [j if j < in_features else -1 for j in range(64)]
+        layers = [(self.names[0], units, [(0, cols0)], 1, 1, 0),
+                  (self.names[2], units, [(1, list(range(64))), (2, list(range(64, 128)))], 1, 0, 3)]
+        self.program, self.blob_elems, self._gather_np, self._side_np = build_program(
+            layers, shapes, offs, o, 0, -1, head_names={3: f'{prefix}.4'})
+        self._dev = None
+        self.blob = self.side = None
+        self.macs_per_row = units * in_features + units * units + 3 * units
+
+    def refresh(self, params):
+        dev = params[self.names[0]].device
+        if self._dev != dev:
+            self._gather = torch.from_numpy(self._gather_np).to(dev)
+            self._side_idx = torch.from_numpy(self._side_np).to(dev)
+            self._dev = dev
+        flat = torch.cat([params[n].detach().reshape(-1).float() for n in self.names] +
+                         [torch.zeros(1, dtype=torch.float32, device=dev)])
+        assert flat.numel() == self.flat_size + 1
+        self.blob = flat[self._gather].to(torch.bfloat16).contiguous()
+        self.side = flat[self._side_idx].contiguous()
+        return self
+
+    def forward(self, rows, count, max_rows):
+        """rows [max_rows, 32] fp32, count int32[1] on the device -> rgb [max_rows, 3] (rows >= count undefined)."""
+        rgb = torch.empty((max_rows, 3), dtype=torch.float32, device=rows.device)
+        L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
+               L.ptr(count), max_rows, L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
+        return rgb

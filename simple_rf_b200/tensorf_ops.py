@@ -1,0 +1,200 @@
+"""Tensor-level wrappers + autograd glue for the Simple-TensoRF kernels (csrc/tensorf.cu).
+
+Reference: models/SimpleTensoRF09.py:701-761 (LowRankTensor.forward), :1214-1272 (VM density / colour),
+:1342-1349 (AlphaGridMask).  No CPU / eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+MATRIX_AXES = [[0, 1], [0, 2], [1, 2]]      # SimpleTensoRF09.py:1131
+VECTOR_AXES = [2, 1, 0]                     # SimpleTensoRF09.py:1132
+
+
+def _f3(t):
+    v = [float(x) for x in torch.as_tensor(t).reshape(-1).tolist()]
+    return (ctypes.c_float * len(v))(*v)
+
+
+def _i3(t):
+    v = [int(x) for x in torch.as_tensor(t).reshape(-1).tolist()]
+    return (ctypes.c_int * len(v))(*v)
+
+
+def _ptrs(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def pack_alpha_bits(alpha_volume):
+    """fp32 {0,1} volume [..., Z, Y, X] (AlphaGridMask.alpha_volume) -> uint32 words, 1 bit per voxel."""
+    L.require_cuda(alpha_volume)
+    vol = L.f32c(alpha_volume).reshape(-1)
+    n = vol.numel()
+    bits = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=vol.device)
+    L.call('srf_pack_alpha_bits', L.ptr(vol), n, L.ptr(bits), L.stream_handle())
+    return bits
+
+
+class Compacted:
+    """A compacted sample list: int32 indices (first `count` valid) with the count kept on the device."""
+    __slots__ = ('mask', 'idx', 'count', 'total')
+
+    def __init__(self, mask, idx, count, total):
+        self.mask, self.idx, self.count, self.total = mask, idx, count, total
+
+
+def _compact(mask_u8, counts, total):
+    dev = mask_u8.device
+    offsets = torch.empty_like(counts)
+    idx = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    L.call('srf_compact', L.ptr(mask_u8), total, L.ptr(counts), L.ptr(offsets), L.ptr(idx), L.ptr(count), L.stream_handle())
+    return idx, count
+
+
+def validity_compact(rays_o, rays_d, z, bbox, alpha=None):
+    """bbox test AND alphaMask test on pts = o + d z, then stable compaction (SimpleTensoRF09.py:705-710, :1221).
+    alpha: None or dict(bits=int32 words, res=(X,Y,Z), box_min=[3], box_size=[3])."""
+    L.require_cuda(rays_o, rays_d, z)
+    rays_o, rays_d, z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
+    R, S = z.shape
+    total = R * S
+    mask = torch.empty((R, S), dtype=torch.uint8, device=z.device)
+    nb = L.load().srf_compaction_blocks(total)
+    counts = torch.empty((max(nb, 1),), dtype=torch.int32, device=z.device)
+    if alpha is None:
+        a_bits = a_res = a_min = a_size = None
+    else:
+        a_bits, a_res, a_min, a_size = L.ptr(alpha['bits']), _i3(alpha['res']), _f3(alpha['box_min']), _f3(alpha['box_size'])
+    L.call('srf_tensorf_mask', L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), R, S, _f3(bbox), a_bits, a_res, a_min, a_size,
+           L.ptr(mask), L.ptr(counts), L.stream_handle())
+    idx, count = _compact(mask, counts, total)
+    return Compacted(mask.view(torch.bool), idx, count, total)
+
+
+def threshold_compact(values, threshold):
+    """mask = values > threshold, then stable compaction (SimpleTensoRF09.py:726, :1248)."""
+    L.require_cuda(values)
+    values = L.f32c(values.detach())
+    total = values.numel()
+    mask = torch.empty(values.shape, dtype=torch.uint8, device=values.device)
+    nb = L.load().srf_compaction_blocks(total)
+    counts = torch.empty((max(nb, 1),), dtype=torch.int32, device=values.device)
+    L.call('srf_threshold_mask', L.ptr(values), float(threshold), total, L.ptr(mask), L.ptr(counts), L.stream_handle())
+    idx, count = _compact(mask, counts, total)
+    return Compacted(mask.view(torch.bool), idx, count, total)
+
+
+def to_channels_last(planes, lines):
+    """[1,C,H,W] -> [H,W,C] and [1,C,L,1] -> [L,C] contiguous copies (the derived caches the kernels read)."""
+    return ([p.detach()[0].permute(1, 2, 0).contiguous() for p in planes],
+            [l.detach()[0, :, :, 0].permute(1, 0).contiguous() for l in lines])
+
+
+class VmGeometry:
+    """Everything the gather kernels need besides the parameter tables."""
+
+    def __init__(self, rays_o, rays_d, z, box_min, box_size, resolution):
+        self.rays_o, self.rays_d, self.z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
+        self.S = z.shape[1]
+        self.box_min, self.box_size = _f3(box_min), _f3(box_size)
+        self.res = _i3(resolution)
+
+    def args(self, comp):
+        return (L.ptr(self.rays_o), L.ptr(self.rays_d), L.ptr(self.z), self.S, L.ptr(comp.idx), L.ptr(comp.count), comp.total,
+                self.box_min, self.box_size)
+
+
+class _VmDensity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geom, comp, softplus, offset, n_planes, *params):
+        planes, lines = params[:n_planes], params[n_planes:]
+        planes_cl, lines_cl = to_channels_last(planes, lines)
+        chans = _i3([p.shape[1] for p in planes])
+        R = geom.z.shape[0]
+        sigma = torch.zeros((R, geom.S, 1), dtype=torch.float32, device=geom.z.device)
+        feat = torch.empty((max(comp.total, 1),), dtype=torch.float32, device=geom.z.device)
+        L.call('srf_vm_density_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, int(softplus),
+               float(offset), L.ptr(sigma), L.ptr(feat), L.stream_handle())
+        ctx.geom, ctx.comp, ctx.cfg = geom, comp, (int(softplus), float(offset), n_planes)
+        ctx.tables = (planes_cl, lines_cl, chans)
+        ctx.save_for_backward(feat)
+        return sigma
+
+    @staticmethod
+    def backward(ctx, g_sigma):
+        (feat,) = ctx.saved_tensors
+        geom, comp = ctx.geom, ctx.comp
+        softplus, offset, n_planes = ctx.cfg
+        planes_cl, lines_cl, chans = ctx.tables
+        gp = [torch.zeros_like(p) for p in planes_cl]
+        gl = [torch.zeros_like(l) for l in lines_cl]
+        L.call('srf_vm_density_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, softplus, offset,
+               L.ptr(L.f32c(g_sigma)), L.ptr(feat), _ptrs(gp), _ptrs(gl), L.stream_handle())
+        grads = [g.permute(2, 0, 1)[None].contiguous() for g in gp] + [g.permute(1, 0)[None, :, :, None].contiguous() for g in gl]
+        return (None, None, None, None, None, *grads)
+
+
+def vm_density(geom, comp, planes, lines, softplus=False, offset=0.0):
+    """sigma [R,S,1] (zeros where the mask is false), differentiable w.r.t. planes / lines ([1,C,H,W] / [1,C,L,1])."""
+    return _VmDensity.apply(geom, comp, softplus, offset, len(planes), *planes, *lines)
+
+
+class _VmColorRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geom, comp, view_dirs, n_planes, basis, *params):
+        planes, lines = params[:n_planes], params[n_planes:]
+        planes_cl, lines_cl = to_channels_last(planes, lines)
+        chans = _i3([p.shape[1] for p in planes])
+        basis_c = L.f32c(basis.detach())
+        F = basis_c.shape[0]
+        rows = torch.empty((max(comp.total, 1), 32), dtype=torch.float32, device=geom.z.device)
+        L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, L.ptr(basis_c), F,
+               L.ptr(L.f32c(view_dirs)), L.ptr(rows), L.stream_handle())
+        ctx.geom, ctx.comp, ctx.n_planes = geom, comp, n_planes
+        ctx.tables = (planes_cl, lines_cl, chans, basis_c)
+        return rows
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        geom, comp = ctx.geom, ctx.comp
+        planes_cl, lines_cl, chans, basis_c = ctx.tables
+        gp = [torch.zeros_like(p) for p in planes_cl]
+        gl = [torch.zeros_like(l) for l in lines_cl]
+        gb = torch.zeros_like(basis_c)
+        L.call('srf_vm_color_features_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, L.ptr(basis_c),
+               basis_c.shape[0], L.ptr(L.f32c(g_rows)), L.ptr(gb), _ptrs(gp), _ptrs(gl), L.stream_handle())
+        grads = [g.permute(2, 0, 1)[None].contiguous() for g in gp] + [g.permute(1, 0)[None, :, :, None].contiguous() for g in gl]
+        return (None, None, None, None, gb, *grads)
+
+
+def vm_color_rows(geom, comp, view_dirs, basis, planes, lines):
+    """rows [total, 32] = [basis(plane x line) (F) | view_dirs (3) | 0], first comp.count rows valid."""
+    return _VmColorRows.apply(geom, comp, view_dirs, len(planes), basis, *planes, *lines)
+
+
+def scatter_rows(comp, src, width, total):
+    dst = torch.zeros((total, width), dtype=torch.float32, device=src.device)
+    L.call('srf_scatter_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(L.f32c(src)), width, L.ptr(dst), L.stream_handle())
+    return dst
+
+
+def gather_rows(comp, src, width):
+    dst = torch.zeros((max(comp.total, 1), width), dtype=torch.float32, device=src.device)
+    L.call('srf_gather_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(L.f32c(src)), width, L.ptr(dst), L.stream_handle())
+    return dst
+
+
+class _ScatterRows(torch.autograd.Function):
+    """dense[idx[j]] = rows[j] for j < count (the reference's rgb[mask] = surface_rgb, SimpleTensoRF09.py:1271)."""
+
+    @staticmethod
+    def forward(ctx, comp, rows, total):
+        ctx.comp, ctx.width = comp, rows.shape[1]
+        return scatter_rows(comp, rows, rows.shape[1], total)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, gather_rows(ctx.comp, g, ctx.width)[:ctx.comp.total], None

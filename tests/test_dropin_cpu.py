@@ -46,3 +46,31 @@ def test_nerf_dropin_refuses_cpu(golden_configs):
     pid = torch.zeros(4, 3, dtype=torch.int32)
     with pytest.raises(SimpleRFNativeError):
         model({'pixel_id': pid, 'num_frames': 3})
+
+
+@pytest.mark.needs_reference
+def test_tensorf_dropin_resolves_and_matches_state_dict():
+    from oracle import reference_harness as H
+    from simple_rf_b200 import dropin
+    get_model, _ = H.import_reference()
+    dropin.install()
+    configs, model_configs = H.load_configs(212, '00000')
+    configs['model']['coarse_model']['num_voxels_initial'] = 30 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 16 ** 3
+    models = []
+    for name in ('SimpleTensoRF09', 'SimpleTensoRF91'):
+        configs['model']['name'] = name
+        torch.manual_seed(0)
+        models.append(get_model(copy.deepcopy(configs), model_configs=model_configs))
+    ref, mine = models
+    assert type(mine).__module__.startswith('simple_rf_b200.models')
+    sd_ref, sd_mine = ref.state_dict(), mine.state_dict()
+    assert list(sd_ref.keys()) == list(sd_mine.keys())
+    for k in sd_ref:
+        assert sd_ref[k].shape == sd_mine[k].shape, k
+        assert torch.equal(sd_ref[k], sd_mine[k]), k
+    opt_cfg = configs['optimizers'][0]
+    g_ref, g_mine = ref.get_trainable_parameters(opt_cfg), mine.get_trainable_parameters(opt_cfg)
+    assert [g['name'] for g in g_ref] == [g['name'] for g in g_mine]
+    assert [[tuple(p.shape) for p in g['params']] for g in g_ref] == [[tuple(p.shape) for p in g['params']] for g in g_mine]
+    assert int(mine.coarse_model.num_samples) == int(ref.coarse_model.num_samples)

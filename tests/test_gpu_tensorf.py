@@ -1,0 +1,235 @@
+"""GPU parity: Simple-TensoRF kernels (occupancy mask, compaction, VM density / appearance, colour MLP) and the
+drop-in model end to end, against the CPU oracle and the committed outputs of the unmodified reference."""
+import pytest
+import torch
+
+from oracle import fixtures as FX
+from oracle import pipeline as P
+from oracle import rays as RY
+from oracle import sampling as SP
+from oracle import tensorf as TF
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 1e-3        # fp32 paths: rgb / depth / weights within 1e-3 (north_star)
+MLP_TOL = 3e-3    # colour MLP runs bf16 operands on the tensor cores (stated looser tolerance)
+
+
+def _scene(golden_configs, R, seed, with_alpha, S=None):
+    configs, mc = golden_configs('tensorf')
+    sets = FX.tensorf_sets(configs, seed=21, with_alpha=with_alpha)
+    K = torch.tensor(mc['intrinsics']); E = torch.tensor(mc['extrinsics'])
+    h, w = mc['resolution']
+    pid = FX.random_pixels(R, K.shape[0], h, w, seed=seed)
+    ro, rd = RY.camera_rays(pid, K, E, half_pixel=True, flip_x=True)
+    img = pid[:, 0].long()
+    on, dn = RY.ndc_rays(ro, rd, h, w, K[img, 0, 0], K[img, 1, 1], mc['near'])
+    vd = RY.view_dirs(dn)
+    t = sets['coarse_model']
+    S = S or t['num_samples']
+    g = torch.Generator().manual_seed(seed)
+    z = SP.stratified_depths(SP.coarse_depths(S, 0., 1.), R, torch.rand(R, S, generator=g))
+    return configs, mc, t, dict(ro=ro, rd=rd, on=on, dn=dn, vd=vd, z=z)
+
+
+def _alpha_dict(t):
+    from simple_rf_b200 import tensorf_ops as T
+    vol = t['alpha_volume'].to(DEV)
+    Z, Y, X = vol.shape[-3:]
+    size = t['alpha_bbox'][1] - t['alpha_bbox'][0]
+    return {'bits': T.pack_alpha_bits(vol), 'res': [X, Y, Z], 'box_min': t['alpha_bbox'][0].tolist(), 'box_size': size.tolist()}
+
+
+@pytest.mark.parametrize('with_alpha', [False, True])
+@pytest.mark.parametrize('R', [1, 257, 3000])
+def test_mask_and_compaction_bit_exact(golden_configs, with_alpha, R):
+    from simple_rf_b200 import tensorf_ops as T
+    configs, mc, t, a = _scene(golden_configs, R, seed=R, with_alpha=with_alpha)
+    # stretch some rays so a good share of the samples leaves the box
+    a['dn'][::3] *= 2.5
+    pts = a['on'][:, None, :] + a['dn'][:, None, :] * a['z'][..., None]
+    ref = TF.validity_mask(pts, t['bbox'], t.get('alpha_volume'), t.get('alpha_bbox'))
+    comp = T.validity_compact(a['on'].to(DEV), a['dn'].to(DEV), a['z'].to(DEV), t['bbox'], _alpha_dict(t) if with_alpha else None)
+    assert torch.equal(comp.mask.cpu(), ref)                              # bit-exact occupancy / box mask
+    n = int(comp.count.item())
+    assert n == int(ref.sum())
+    assert torch.equal(comp.idx[:n].cpu().long(), torch.nonzero(ref.reshape(-1))[:, 0])      # stable row-major order
+    assert 0 < n < ref.numel() or R == 1
+
+
+def test_mask_on_voxel_planes_and_box_faces(golden_configs):
+    """Points exactly on voxel planes / box faces (the cases SURVEY.md §7 singles out) through zero-direction rays."""
+    from simple_rf_b200 import tensorf_ops as T
+    configs, mc, t, _ = _scene(golden_configs, 4, seed=1, with_alpha=True)
+    X, Y, Z = [int(v) for v in t['resolution']]
+    g = torch.Generator().manual_seed(0)
+    b0, b1 = t['bbox']
+    lat = torch.stack([torch.linspace(b0[0], b1[0], X)[torch.randint(0, X, (4000,), generator=g)],
+                       torch.linspace(b0[1], b1[1], Y)[torch.randint(0, Y, (4000,), generator=g)],
+                       torch.linspace(b0[2], b1[2], Z)[torch.randint(0, Z, (4000,), generator=g)]], 1)
+    rnd = (torch.rand(4000, 3, generator=g) * 1.2 - 0.1) * (b1 - b0) + b0
+    pts = torch.cat([lat, rnd, b0[None], b1[None]])
+    ref = TF.validity_mask(pts[:, None, :], t['bbox'], t['alpha_volume'], t['alpha_bbox'])
+    zero = torch.zeros_like(pts)
+    comp = T.validity_compact(pts.to(DEV), zero.to(DEV), zero[:, :1].contiguous().to(DEV), t['bbox'], _alpha_dict(t))
+    assert torch.equal(comp.mask.cpu(), ref)
+
+
+def test_threshold_compaction_matches_nonzero():
+    from simple_rf_b200 import tensorf_ops as T
+    g = torch.Generator().manual_seed(3)
+    w = torch.rand(777, 462, generator=g) ** 8
+    comp = T.threshold_compact(w.to(DEV), 1e-4)
+    ref = w > 1e-4
+    n = int(comp.count.item())
+    assert torch.equal(comp.mask.cpu(), ref) and n == int(ref.sum())
+    assert torch.equal(comp.idx[:n].cpu().long(), torch.nonzero(ref.reshape(-1))[:, 0])
+    empty = T.threshold_compact(torch.zeros(5, 7, device=DEV), 1e-4)
+    assert int(empty.count.item()) == 0
+
+
+@pytest.mark.parametrize('with_alpha', [False, True])
+def test_vm_density_forward_backward(golden_configs, with_alpha):
+    from simple_rf_b200 import tensorf_ops as T
+    configs, mc, t, a = _scene(golden_configs, 200, seed=5, with_alpha=with_alpha)
+    a['dn'][::4] *= 2.0
+    params = {k: v.clone().requires_grad_() for k, v in t['params'].items() if 'density' in k}
+    pts = a['on'][:, None, :] + a['dn'][:, None, :] * a['z'][..., None]
+    mask = TF.validity_mask(pts, t['bbox'], t.get('alpha_volume'), t.get('alpha_bbox'))
+    ref = TF.vm_density(params, TF.normalize(pts, t['bbox']), mask)
+    up = torch.rand(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * up).sum().backward()
+
+    dev_params = {k: v.detach().to(DEV).requires_grad_() for k, v in params.items()}
+    comp = T.validity_compact(a['on'].to(DEV), a['dn'].to(DEV), a['z'].to(DEV), t['bbox'], _alpha_dict(t) if with_alpha else None)
+    geom = T.VmGeometry(a['on'].to(DEV), a['dn'].to(DEV), a['z'].to(DEV), t['bbox'][0], t['bbox'][1] - t['bbox'][0], t['resolution'])
+    planes = [dev_params[f'matrices_density.{i}'] for i in range(3)]
+    lines = [dev_params[f'vectors_density.{i}'] for i in range(3)]
+    sigma = T.vm_density(geom, comp, planes, lines)
+    assert (sigma.cpu() - ref.detach()).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    (sigma * up.to(DEV)).sum().backward()
+    for k in params:
+        gref = params[k].grad
+        err = (dev_params[k].grad.cpu() - gref).abs().max().item() / max(gref.abs().max().item(), 1e-12)
+        assert err <= 1e-4, (k, err)          # fp32 gather/scatter: atomics only reorder the sums
+
+
+def test_vm_color_rows_and_mlp(golden_configs):
+    from simple_rf_b200 import tensorf_ops as T
+    from simple_rf_b200.nerf_program import PackedRowsMLP
+    configs, mc, t, a = _scene(golden_configs, 150, seed=8, with_alpha=False)
+    params = {k: v.clone().requires_grad_() for k, v in t['params'].items()}
+    pts = a['on'][:, None, :] + a['dn'][:, None, :] * a['z'][..., None]
+    pn = TF.normalize(pts, t['bbox'])
+    g = torch.Generator().manual_seed(2)
+    wts = torch.rand(a['z'].shape, generator=g) ** 6
+    surf = wts > 1e-4
+    feats = TF.vm_color_features(params, pn[surf])
+    vd = a['vd'][:, None].expand(pts.shape)[surf]
+    rgb_ref = TF.color_mlp(params, feats, vd)
+    up = torch.rand(feats.shape, generator=g)
+    (feats * up).sum().backward()
+
+    dp = {k: v.detach().to(DEV).requires_grad_() for k, v in params.items()}
+    comp = T.threshold_compact(wts.to(DEV), 1e-4)
+    n = int(comp.count.item())
+    assert n == int(surf.sum())
+    geom = T.VmGeometry(a['on'].to(DEV), a['dn'].to(DEV), a['z'].to(DEV), t['bbox'][0], t['bbox'][1] - t['bbox'][0], t['resolution'])
+    rows = T.vm_color_rows(geom, comp, a['vd'].to(DEV), dp['basis_matrix_color.weight'],
+                           [dp[f'matrices_color.{i}'] for i in range(3)], [dp[f'vectors_color.{i}'] for i in range(3)])
+    F_ = feats.shape[1]
+    assert (rows[:n, :F_].cpu() - feats.detach()).abs().max().item() <= 1e-5 * max(1.0, feats.abs().max().item())
+    assert (rows[:n, F_:F_ + 3].cpu() - vd).abs().max().item() == 0
+    assert (rows[:n, F_ + 3:] == 0).all()
+    g_rows = torch.zeros_like(rows)
+    g_rows[:n, :F_] = up.to(DEV)
+    rows.backward(g_rows)
+    for k in ('basis_matrix_color.weight', 'matrices_color.0', 'matrices_color.2', 'vectors_color.0', 'vectors_color.1'):
+        gref = params[k].grad
+        err = (dp[k].grad.cpu() - gref).abs().max().item() / max(gref.abs().max().item(), 1e-12)
+        assert err <= 1e-4, (k, err)
+    mlp = PackedRowsMLP(F_ + 3, prefix='color_predictor.mlp').refresh({k: v.detach() for k, v in dp.items() if k.startswith('color_predictor')})
+    rgb = mlp.forward(rows.detach(), comp.count, rows.shape[0])
+    err = (rgb[:n].cpu() - rgb_ref.detach()).abs().max().item()
+    print('colour MLP max abs err', err)
+    assert err <= MLP_TOL
+
+
+def _model(golden_configs, g):
+    from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask, SimpleTensoRF
+    configs, mc = golden_configs('tensorf')
+    sets = FX.tensorf_sets(configs, seed=int(g['param_seed']), with_alpha=bool(g['with_alpha']))
+    model = SimpleTensoRF(configs, mc)
+
+    def put(module, t):
+        sd = dict(module.named_parameters())
+        assert set(sd.keys()) == set(t['params'].keys())
+        for k, v in t['params'].items():
+            sd[k].data.copy_(v)
+        module.alpha_mask = AlphaGridMask(t['alpha_volume'][0, 0], t['alpha_bbox']) if 'alpha_volume' in t else None
+    put(model.coarse_model, sets['coarse_model'])
+    for aug, (_, _, t) in zip(model.augmented_models, sets['augmentations']):
+        put(aug['coarse_model'], t)
+    return model.to(DEV), configs, mc, sets
+
+
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_dropin_forward_vs_reference_golden(golden, golden_configs, mode):
+    g = golden(f'tensorf_{mode}')
+    model, configs, mc, sets = _model(golden_configs, g)
+    model.train(mode == 'train')
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+    for k in ('rays_o', 'rays_d', 'rays_o_ndc', 'rays_d_ndc', 'view_dirs'):
+        assert (out[k].cpu() - g[k]).abs().max().item() <= 1e-6 * max(1.0, g[k].abs().max().item()), k
+    assert torch.equal(out['z_vals_coarse'].cpu(), g['z_vals_coarse'])
+    worst = {}
+    for k, ref in g.items():
+        if k not in out or ref.dtype != torch.float32 or k in ('z_vals_coarse', 'view_dirs') or k.startswith('rays'):
+            continue
+        got = out[k].cpu()
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        err = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        worst[k] = err
+        tol = MLP_TOL if 'rgb' in k else TOL
+        assert err <= tol, (k, err)
+    # sigma > 0 exactly where the reference's (bit-exact) validity mask says so
+    assert torch.equal((out['raw_sigma_coarse'][..., 0] > 0).cpu() | ~g['validity_mask_coarse'], (g['raw_sigma_coarse'][..., 0] > 0) | ~g['validity_mask_coarse'])
+    print(mode, 'worst:', sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+
+
+def test_dropin_training_gradients(golden, golden_configs):
+    """Gradients of every trainable tensor after one forward/backward against autograd through the fp32 oracle.
+    Stated tolerance: 2e-2 of the per-tensor max |g| (colour MLP forward runs bf16 operands)."""
+    g = golden('tensorf_train')
+    model, configs, mc, sets = _model(golden_configs, g)
+    model.train()
+    pid = g['pixel_id']
+    torch.manual_seed(int(g['rng_seed']))
+    out = model({'pixel_id': pid.to(DEV), 'num_frames': 3, 'iter_num': 1, 'sub_batch_index': 1})
+    keys = ['rgb_coarse', 'depth_coarse', 'points_augmentation_rgb_coarse', 'points_augmentation_depth_coarse', 'depth_ndc_coarse']
+    loss = sum(out[k].square().mean() for k in keys) + out['points_augmentation_weights_coarse'].square().sum() * 1e-2
+    loss.backward()
+    tensors = [sets['coarse_model']] + [s[2] for s in sets['augmentations']]
+    for t in tensors:
+        for k in t['params']:
+            t['params'][k] = t['params'][k].clone().requires_grad_()
+    torch.manual_seed(int(g['rng_seed']))
+    ref = P.tensorf_render_chunk(sets, configs, mc, pid, training=True)
+    ref_loss = sum(ref[k].square().mean() for k in keys) + ref['points_augmentation_weights_coarse'].square().sum() * 1e-2
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 3e-3 * abs(ref_loss.item())
+    mods = [model.coarse_model] + [a['coarse_model'] for a in model.augmented_models]
+    worst = 0.0
+    for mod, t in zip(mods, tensors):
+        for k, p in mod.named_parameters():
+            gr = t['params'][k].grad
+            if gr is None or gr.abs().max() == 0:
+                assert p.grad is None or p.grad.abs().max().item() <= 1e-8, k
+                continue
+            assert p.grad is not None, k
+            rel = (p.grad.cpu() - gr).abs().max().item() / gr.abs().max().item()
+            worst = max(worst, rel)
+            assert rel <= 2e-2, (mod.name, k, rel)
+    print('worst relative gradient error', worst)
