@@ -69,26 +69,54 @@ struct MlpArgs {
 #ifndef SRF_MLP_PREFETCH
 #define SRF_MLP_PREFETCH 0
 #endif
+// SRF_MLP_TRACE: CTA 0 records clock64() at pipeline events of its 3rd tile into a global buffer (tools/mlp_trace.py)
+#ifndef SRF_MLP_TRACE
+#define SRF_MLP_TRACE 0
+#endif
+#if SRF_MLP_TRACE
+__device__ long long g_mlp_trace[4096];
+#define TRACE(slot) do { if (blockIdx.x == 0 && t == 2) g_mlp_trace[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 constexpr int GROUPS = SRF_MLP_GROUPS;
 constexpr int COLS = 64 / GROUPS;                 // columns of a 64-wide block owned by one epilogue warp
 constexpr int EPI_THREADS = 128 * GROUPS;
-constexpr int MLP_THREADS = 64 + EPI_THREADS;     // warp 0 producer, warp 1 MMA, then the epilogue warps
-constexpr int EPI_WARP0 = 2;
+constexpr int EPI_WARP0 = 2;                      // warp 0 weight producer, warp 1 MMA issuer
+constexpr int ENC_WARP0 = EPI_WARP0 + 4 * GROUPS; // 4 encoding warps (one row per thread) run one tile ahead
+constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 4);
 constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
 constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
 constexpr int NUM_STAGES = 3;
 constexpr int MAX_SIDE = 4608;                    // floats
+constexpr int MAX_STEPS = MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
+
+// One K-block step of the MMA issuer, flattened from the layer program at kernel start so that the issuing
+// thread's loop is a single shared-memory load away from the next tcgen05.mma.
+struct alignas(16) MmaStep {
+  uint32_t a_desc_lo;     // low word of the A-operand descriptor (region base >> 4)
+  uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
+  uint16_t layer;         // layer index inside the tile (selects the accumulator buffer)
+  uint8_t ksteps;         // 16-wide K steps to issue
+  int8_t wait_region;     // region whose a_ready barrier must be acquired first, or -1
+  uint8_t first;          // first step of the layer: overwrite the accumulator
+  uint8_t last;           // last step of the layer: commit d_full
+  uint8_t free_e, free_v; // last reader of region 0 / 5 in the tile: commit e_free / v_free
+};
 
 struct alignas(1024) MlpSmem {
   uint8_t a[6][KBLOCK_BYTES];             // E, H0..H3, V
   uint8_t w[NUM_STAGES][STAGE_BYTES];
   float side[MAX_SIDE];
   float part[2][GROUPS][128][4];          // head partial sums of each column group
+  MmaStep steps[MAX_STEPS];
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
   uint64_t a_ready[6];                    // per A region: written and visible to the async proxy
   uint64_t d_full[2];                     // accumulator buffer complete
+  uint64_t e_free, v_free;                // every MMA reading region 0 / 5 of the current tile has retired
   uint32_t tmem_base;
+  int num_steps;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
@@ -128,10 +156,40 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
-    for (int r = 0; r < 6; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * GROUPS);
+    ptx::mbar_init(&sm.a_ready[0], 4);
+    ptx::mbar_init(&sm.a_ready[5], 4);
+    for (int r = 1; r < 5; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * GROUPS);
     ptx::mbar_init(&sm.d_full[0], 1);
     ptx::mbar_init(&sm.d_full[1], 1);
+    ptx::mbar_init(&sm.e_free, 1);
+    ptx::mbar_init(&sm.v_free, 1);
     ptx::fence_barrier_init();
+    // flatten the layer program into MMA steps
+    int ns = 0, last_e = -1, last_v = -1;
+    uint32_t seen = 0;
+    for (int l = 0; l < prog.num_layers; ++l) {
+      const MlpLayer& L = prog.layers[l];
+      for (int kb = 0; kb < L.num_kblocks; ++kb, ++ns) {
+        MmaStep st;
+        const int reg = L.kblock_region[kb];
+        st.a_desc_lo = (ptx::smem_u32(sm.a[reg]) >> 4) & 0x3FFF;
+        st.idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
+        st.layer = (uint16_t)l;
+        st.ksteps = (uint8_t)L.kblock_ksteps[kb];
+        st.wait_region = ((seen >> reg) & 1) ? -1 : (int8_t)reg;
+        seen |= 1u << reg;
+        st.first = kb == 0;
+        st.last = kb == L.num_kblocks - 1;
+        st.free_e = st.free_v = 0;
+        if (reg == 0) last_e = ns;
+        if (reg == 5) last_v = ns;
+        sm.steps[ns] = st;
+      }
+      if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
+    }
+    if (last_e >= 0) sm.steps[last_e].free_e = 1;
+    if (last_v >= 0) sm.steps[last_v].free_v = 1;
+    sm.num_steps = ns;
   }
   if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
   ptx::tc_fence_before();
@@ -142,6 +200,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
   const int num_tiles = (int)((total + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const bool has_views = prog.views_degree >= 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer
@@ -166,44 +225,110 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      uint32_t it = 0, layer_count = 0;
+      const int num_steps = sm.num_steps;
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+      const uint32_t w_desc_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
+      uint32_t it = 0, layer_base = 0;
       uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
-      uint32_t a_seen = 0;               // bit r: region r already acquired for its current contents
       for (int t = 0; t < my_tiles; ++t) {
-        for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
-          const MlpLayer& L = prog.layers[l];
-          const uint32_t buf = layer_count & 1;
-          const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
-          const uint32_t d_addr = tmem + buf * 256;
-          bool first = true;
-          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
-            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
-            const int reg = L.kblock_region[kb];
-            if (!((a_seen >> reg) & 1)) {
-              ptx::mbar_wait(&sm.a_ready[reg], (a_phase >> reg) & 1);
-              a_phase ^= 1u << reg;
-              a_seen |= 1u << reg;
-            }
-            ptx::mbar_wait(&sm.w_full[st], ph);
-            ptx::tc_fence_after();
-            const uint32_t a_base = ptx::smem_u32(sm.a[reg]);
-            const uint32_t b_base = ptx::smem_u32(sm.w[st]);
-            for (int k = 0; k < L.kblock_ksteps[kb]; ++k) {
-              ptx::umma_bf16(d_addr, ptx::make_sw128_desc(a_base + k * 32), ptx::make_sw128_desc(b_base + k * 32), idesc,
-                             first ? 0u : 1u);
-              first = false;
-            }
-            ptx::umma_commit(&sm.w_empty[st]);
+        for (int s = 0; s < num_steps; ++s, ++it) {
+          const MmaStep st = sm.steps[s];
+          const uint32_t stage = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
+          if (st.wait_region >= 0) {
+            ptx::mbar_wait(&sm.a_ready[st.wait_region], (a_phase >> st.wait_region) & 1);
+            a_phase ^= 1u << st.wait_region;
           }
-          ptx::umma_commit(&sm.d_full[buf]);
-          // the epilogue of this layer rewrites H (write_h) - its blocks must be re-acquired
-          if (L.write_h) a_seen &= ~0x1Eu;
+          TRACE(16 + s * 4 + 0);
+          ptx::mbar_wait(&sm.w_full[stage], ph);
+          TRACE(16 + s * 4 + 1);
+          ptx::tc_fence_after();
+          const uint32_t buf = (layer_base + st.layer) & 1;
+          const uint32_t d_addr = tmem + buf * 256;
+          const uint64_t a_desc = ((uint64_t)desc_hi << 32) | st.a_desc_lo;
+          const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (w_desc_lo + stage * (STAGE_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < st.ksteps) ptx::umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, st.idesc, (st.first && k == 0) ? 0u : 1u);
+          ptx::umma_commit(&sm.w_empty[stage]);
+          if (st.last) ptx::umma_commit(&sm.d_full[buf]);
+          if (st.free_e) ptx::umma_commit(&sm.e_free);
+          if (st.free_v) ptx::umma_commit(&sm.v_free);
+          TRACE(16 + s * 4 + 2);
         }
-        a_seen = 0;                      // next tile: E and V are rewritten as well
+        layer_base += prog.num_layers;
+      }
+    }
+  } else if (warp >= ENC_WARP0) {
+    // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
+    const int row = (warp - ENC_WARP0) * 32 + lane;
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long m = tile * 128 + row;
+      const bool valid = m < total;
+      float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
+      float4 x[8];
+      if (args.rows != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          x[q] = valid ? __ldg(reinterpret_cast<const float4*>(args.rows + m * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (valid) {
+        const long long r = m / args.S;
+        const float zz = args.z[m];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(args.rays_o[r * 3 + c], __fmul_rn(args.rays_d[r * 3 + c], zz));
+        if (args.view_dirs != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) vd[c] = args.view_dirs[r * 3 + c];
+        }
+      }
+      // region 0 of the previous tile must have been read by its last MMA
+      ptx::mbar_wait(&sm.e_free, (t & 1) ^ 1);
+      if (warp == ENC_WARP0 && lane == 0) TRACE(0);
+      uint8_t* E = sm.a[0];
+      if (args.rows != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(E + ptx::sw128_offset(row, u)) =
+              make_uint4(ptx::pack_bf16(x[2 * u].x, x[2 * u].y), ptx::pack_bf16(x[2 * u].z, x[2 * u].w),
+                         ptx::pack_bf16(x[2 * u + 1].x, x[2 * u + 1].y), ptx::pack_bf16(x[2 * u + 1].z, x[2 * u + 1].w));
+      } else {
+        const int deg = prog.points_degree;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          store_bf16(E, row, c, p[c]);
+          if (deg > 0)
+            encode_octaves(p[c], 0, deg, [&](int k, float s, float co) {
+              store_bf16(E, row, 3 + 6 * k + c, s);
+              store_bf16(E, row, 6 + 6 * k + c, co);
+            });
+        }
+        for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.a_ready[0]);
+      if (warp == ENC_WARP0 && lane == 0) TRACE(1);
+      if (has_views) {
+        ptx::mbar_wait(&sm.v_free, (t & 1) ^ 1);
+        uint8_t* V = sm.a[5];
+        const int vdeg = prog.views_degree;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          store_bf16(V, row, c, vd[c]);
+          if (vdeg > 0)
+            encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
+              store_bf16(V, row, 3 + 6 * k + c, s);
+              store_bf16(V, row, 6 + 6 * k + c, co);
+            });
+        }
+        for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16(V, row, c, 0.f);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm.a_ready[5]);
       }
     }
   } else {
-    // ------------------------------------------------------------ encoding + epilogue warps
+    // ------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;        // TMEM lane quarter this warp may read: fixed by hardware to warp_id % 4
     const int grp = (warp - EPI_WARP0) >> 2;   // column group of every 64-wide block this warp owns
     const int row = quarter * 32 + lane;
@@ -213,76 +338,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long m = tile * 128 + row;
       const bool valid = m < total;
-      // ---- region 0 (and 5): precomputed rows, or sample point + encodings (split between groups 0 and 1 by octave)
-      if (args.rows != nullptr) {
-        if (grp < 2) {
-          uint8_t* E = sm.a[0];
-          float4 x[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            x[q] = valid ? __ldg(reinterpret_cast<const float4*>(args.rows + m * 32 + grp * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-            *reinterpret_cast<uint4*>(E + ptx::sw128_offset(row, grp * 2 + u)) =
-                make_uint4(ptx::pack_bf16(x[2 * u].x, x[2 * u].y), ptx::pack_bf16(x[2 * u].z, x[2 * u].w),
-                           ptx::pack_bf16(x[2 * u + 1].x, x[2 * u + 1].y), ptx::pack_bf16(x[2 * u + 1].z, x[2 * u + 1].w));
-        }
-      } else if (grp < 2) {
-        float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
-        if (valid) {
-          const long long r = m / args.S;
-          const float zz = args.z[m];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(args.rays_o[r * 3 + c], __fmul_rn(args.rays_d[r * 3 + c], zz));
-          if (args.view_dirs != nullptr) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) vd[c] = args.view_dirs[r * 3 + c];
-          }
-        }
-        uint8_t* E = sm.a[0];
-        const int deg = prog.points_degree;
-        const int split = (deg + 1) / 2;                 // octaves [0, split) by group 0, the rest by group 1
-        if (grp == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) store_bf16(E, row, c, p[c]);
-        } else {
-          for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
-        }
-        const int k0 = grp == 0 ? 0 : split;
-        const int cnt = grp == 0 ? split : deg - split;
-        if (cnt > 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            encode_octaves(p[c], k0, cnt, [&](int k, float s, float co) {
-              store_bf16(E, row, 3 + 6 * k + c, s);
-              store_bf16(E, row, 6 + 6 * k + c, co);
-            });
-        }
-        if (prog.views_degree >= 0) {
-          uint8_t* V = sm.a[5];
-          const int vdeg = prog.views_degree;
-          if (grp == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              store_bf16(V, row, c, vd[c]);
-              if (vdeg > 0)
-                encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
-                  store_bf16(V, row, 3 + 6 * k + c, s);
-                  store_bf16(V, row, 6 + 6 * k + c, co);
-                });
-            }
-          } else {
-            for (int c = 3 + 6 * vdeg; c < 64; ++c) store_bf16(V, row, c, 0.f);
-          }
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(&sm.a_ready[0]);
-        if (prog.views_degree >= 0) ptx::mbar_arrive(&sm.a_ready[5]);
-      }
-      // ---- layer epilogues
       for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
         const MlpLayer& L = prog.layers[l];
         const uint32_t buf = layer_count & 1;
@@ -337,6 +392,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
         d_phase ^= 1u << buf;
         ptx::tc_fence_after();
+        if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16);
         const int nblocks = n >> 6;
 #if SRF_MLP_PREFETCH
         uint32_t va[COLS], vb[COLS], pk[COLS / 2];
@@ -358,8 +414,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         for (int kb = 0; kb < nblocks; ++kb) {
           tmem_load<COLS>(t_row + kb * 64, va);
           ptx::tmem_ld_wait(va);
+          if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 1 + 2 * kb);
           compute(va, pk, kb);
           store(pk, kb);
+          if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * kb);
         }
 #endif
         ptx::tc_fence_before();
@@ -491,3 +549,10 @@ SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const flo
 }
 
 SRF_API int srf_nerf_mlp_program_bytes(void) { return (int)sizeof(MlpProgram); }
+
+#if SRF_MLP_TRACE
+extern "C" __attribute__((visibility("default"))) int srf_debug_mlp_trace(long long* host_out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_mlp_trace, sizeof(long long) * 4096) == cudaSuccess ? 0 : 1;
+}
+#endif
