@@ -89,7 +89,7 @@ constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
 constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
 constexpr int NUM_STAGES = 3;
-constexpr int MAX_SIDE = 4608;                    // floats
+constexpr int MAX_SIDE = 4096;                    // floats
 constexpr int MAX_STEPS = MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
 
 // One K-block step of the MMA issuer, flattened from the layer program at kernel start so that the issuing
