@@ -46,6 +46,14 @@ class SimpleNeRF(torch.nn.Module):
             self.augmented_models_nn = []
         self._camera_tables = None
         self.build_nerf()
+        self.optimizers = None          # Trainer10.py:61-62 hands the optimiser dict over through this attribute
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name == 'optimizers' and value is not None:
+            # multi-GPU: one flat-bucket NCCL all-reduce of the gradients before every optimizer.step()
+            from .. import parallel
+            super().__setattr__('_grad_allreduce', parallel.attach_gradient_allreduce(value))
 
     # ------------------------------------------------------------------ construction (SimpleNeRF17.py:36-75)
     def build_nerf(self):

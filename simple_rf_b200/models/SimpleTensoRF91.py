@@ -93,6 +93,9 @@ class SimpleTensoRF(torch.nn.Module):
         if name == 'optimizers' and value is not None:           # SimpleTensoRF09.py:98-113
             for t in self._tensors():
                 t.optimizers = value
+            # multi-GPU: one flat-bucket NCCL all-reduce of the gradients before every optimizer.step()
+            from .. import parallel
+            super().__setattr__('_grad_allreduce', parallel.attach_gradient_allreduce(value))
 
     def rebuild_camera_params_learners(self, *, intrinsics: numpy.ndarray = None, extrinsics=None, device):
         mc = self.configs['model']
