@@ -158,6 +158,109 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(Composite
   }
 }
 
+// Rays of at most 32*K samples (the Simple-NeRF shapes: 64 coarse, 192 fine): every load of the ray is issued
+// before any arithmetic (K*(2+3) independent loads in flight per lane), weights and depths stay in registers for
+// the variance pass, and the successor depth comes from a shuffle instead of a second load.
+template <int K>
+__global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_small_kernel(CompositeFwd p) {
+  __shared__ float s_rgb[CMP_WARPS][K * 96];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
+  if (r >= p.R) return;
+  const int S = p.S;
+  const float* sig = p.sigma + r * S;
+  const float* zz = p.z + r * S;
+  const float far_z = p.ndc ? 1.f : 1e10f;
+  float sg[K], zi[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int i = (k << 5) + lane;
+    sg[k] = i < S ? ldg_stream(sig + i) : 0.f;
+    zi[k] = i < S ? ldg_stream(zz + i) : far_z;
+  }
+  if (p.rgb != nullptr) {
+    const float* src = p.rgb + r * S * 3;
+#pragma unroll
+    for (int k = 0; k < 3 * K; ++k) {
+      const int e = (k << 5) + lane;
+      if (e < S * 3) s_rgb[warp][e] = ldg_stream(src + e);
+    }
+  }
+  const float* dsrc = p.ndc ? p.rays_d_ndc : p.rays_d;
+  const float dx = dsrc[r * 3 + 0], dy = dsrc[r * 3 + 1], dz = dsrc[r * 3 + 2];
+  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+  float A = 0.f, tn = 0.f;
+  if (p.ndc) {
+    const float oz = p.rays_o[r * 3 + 2], wz = p.rays_d[r * 3 + 2];
+    tn = __fdiv_rn(-__fadd_rn(1.f, oz), wz);
+    A = __fdiv_rn(__fadd_rn(oz, __fmul_rn(tn, wz)), wz);
+  }
+  __syncwarp();
+  float carry = 1.f, acc = 0.f, nz = 0.f, nzw = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  float w[K], zw[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int i = (k << 5) + lane;
+    const bool ok = i < S;
+    float zn = __shfl_down_sync(FULL, zi[k], 1);
+    const float head_next = (k + 1 < K) ? __shfl_sync(FULL, zi[(k + 1 < K) ? k + 1 : k], 0) : far_z;
+    if (lane == 31) zn = head_next;
+    if (i >= S - 1) zn = far_z;
+    const float delta = (zn - zi[k]) * nrm;
+    const float al = ok ? 1.f - expf(-sg[k] * delta * p.distance_scale) : 0.f;
+    const float q = ok ? (1.f - al + 1e-10f) : 1.f;
+    const float incl = warp_incl_prod(q, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.f;
+    const float T = carry * excl;
+    carry *= __shfl_sync(FULL, incl, 31);
+    w[k] = ok ? al * T : 0.f;
+    zw[k] = p.ndc ? ndc_to_world(zi[k], A, tn) : zi[k];
+    if (ok) {
+      stg_stream(p.weights + r * S + i, w[k]);
+      if (p.alpha) stg_stream(p.alpha + r * S + i, al);
+      if (p.visibility) stg_stream(p.visibility + r * S + i, T);
+      acc += w[k];
+      nz += w[k] * zi[k];
+      nzw += w[k] * zw[k];
+      if (p.rgb != nullptr) {
+        c0 += w[k] * s_rgb[warp][i * 3 + 0];
+        c1 += w[k] * s_rgb[warp][i * 3 + 1];
+        c2 += w[k] * s_rgb[warp][i * 3 + 2];
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  nz = warp_sum(nz);
+  const float inv = 1.f / (acc + 1e-6f);
+  const float d_main = nz * inv;
+  float d_world = d_main;
+  if (p.ndc) d_world = warp_sum(nzw) * inv;
+  float v_main = 0.f, v_world = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float a = zi[k] - d_main;
+    v_main += w[k] * a * a;
+    const float b = zw[k] - d_world;
+    v_world += w[k] * b * b;
+  }
+  v_main = warp_sum(v_main);
+  if (p.ndc) v_world = warp_sum(v_world);
+  if (p.rgb_map != nullptr) {
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+    if (p.white_bkgd) { const float bg = 1.f - acc; c0 += bg; c1 += bg; c2 += bg; }
+  }
+  if (lane == 0) {
+    p.acc[r] = acc;
+    if (p.ndc) {
+      p.depth_ndc[r] = d_main; p.depth_var_ndc[r] = v_main; p.depth[r] = d_world; p.depth_var[r] = v_world;
+    } else {
+      p.depth[r] = d_main; p.depth_var[r] = v_main;
+    }
+    if (p.rgb_map != nullptr) { p.rgb_map[r * 3 + 0] = c0; p.rgb_map[r * 3 + 1] = c1; p.rgb_map[r * 3 + 2] = c2; }
+  }
+}
+
 struct CompositeBwd {
   const float* sigma; const float* rgb; const float* z; const float* visibility;
   const float* rays_o; const float* rays_d; const float* rays_d_ndc;
@@ -303,7 +406,9 @@ SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float*
   CompositeFwd p{sigma, rgb, z, rays_o, rays_d, rays_d_ndc, alpha, visibility, weights, rgb_map, acc, depth,
                  depth_var, depth_ndc, depth_var_ndc, num_rays, num_samples, ndc, white_bkgd, distance_scale};
   const unsigned blocks = (unsigned)((num_rays + CMP_WARPS - 1) / CMP_WARPS);
-  composite_fwd_kernel<<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  if (num_samples <= 64) composite_fwd_small_kernel<2><<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  else if (num_samples <= 192) composite_fwd_small_kernel<6><<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  else composite_fwd_kernel<<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   return check_launch("srf_composite_fwd");
 }
 

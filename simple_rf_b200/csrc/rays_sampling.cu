@@ -288,12 +288,14 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) sample_pdf_merge_kernel(PdfPar
     if (p.above) p.above[r * N + j] = a;
   }
   __syncwarp();
-  // bitonic sort of npad values (coarse depths + new samples + inf padding), ascending
-  for (int k = 2; k <= npad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  // bitonic sort of npad values (coarse depths + new samples + inf padding), ascending; j, k are powers of
+  // two, so pair indices are built with shifts (no integer division on the hot loop)
+  for (int k = 2, lk = 1; k <= npad; k <<= 1, ++lk) {
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
       for (int q = lane; q < (npad >> 1); q += 32) {
-        const int i = ((q / j) * (j << 1)) + (q % j);
-        const int l = i + j;
+        const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
+        const int l = i | j;
         const float a = sbuf[i], b = sbuf[l];
         const bool up = (i & k) == 0;
         if ((a > b) == up) { sbuf[i] = b; sbuf[l] = a; }

@@ -375,8 +375,11 @@ __device__ __forceinline__ float color_product(const VmGrid& t, const float (&pn
 
 __global__ void __launch_bounds__(256) vm_color_features_fwd_kernel(VmGeom g, VmGrid t, const float* __restrict__ basis, int F, int CT,
                                                                     const float* __restrict__ view_dirs, float* __restrict__ rows) {
-  extern __shared__ float s_basis[];                 // [F][CT]
-  for (int i = threadIdx.x; i < F * CT; i += blockDim.x) s_basis[i] = basis[i];
+  extern __shared__ float s_basis[];                 // transposed [CT][32]: lane f reads s_basis[ch*32 + f], conflict-free
+  for (int i = threadIdx.x; i < CT * 32; i += blockDim.x) {
+    const int ch = i >> 5, f = i & 31;
+    s_basis[i] = f < F ? basis[f * CT + ch] : 0.f;
+  }
   __syncthreads();
   const int n = g.count[0];
   const int lane = threadIdx.x & 31;
@@ -393,9 +396,10 @@ __global__ void __launch_bounds__(256) vm_color_features_fwd_kernel(VmGeom g, Vm
       if (ch < CT) prod[k] = color_product(t, pn, ch, pi, lc);
     }
     float out = 0.f;
-    for (int ch = 0; ch < CT; ++ch) {
-      const float v = __shfl_sync(FULL, prod[ch >> 5], ch & 31);
-      if (lane < F) out = fmaf(v, s_basis[lane * CT + ch], out);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int lim = min(32, CT - 32 * k);
+      for (int c = 0; c < lim; ++c) out = fmaf(__shfl_sync(FULL, prod[k], c), s_basis[(32 * k + c) * 32 + lane], out);
     }
     const int r = flat / g.S;
     float val = 0.f;
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(256) vm_color_features_fwd_kernel(VmGeom g, Vm
 __global__ void __launch_bounds__(256) vm_color_features_bwd_kernel(VmGeom g, VmGrid t, const float* __restrict__ basis, int F, int CT,
                                                                     const float* __restrict__ g_rows, float* __restrict__ g_basis,
                                                                     float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
-  extern __shared__ float s_mem[];                   // basis [F][CT] | g_basis accumulator [F][CT]
+  extern __shared__ float s_mem[];                   // basis [F][CT] | g_basis accumulator [F][CT] (lane = channel: stride-1)
   float* s_basis = s_mem;
   float* s_gb = s_mem + F * CT;
   for (int i = threadIdx.x; i < F * CT; i += blockDim.x) { s_basis[i] = basis[i]; s_gb[i] = 0.f; }
@@ -612,7 +616,7 @@ SRF_API int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, 
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_fwd")) return 1;
   const int CT = channels[0] + channels[1] + channels[2];
   SRF_REQUIRE(CT <= 96 && num_features + 3 <= COLOR_ROW, "srf_vm_color_features_fwd", "need sum(C) <= 96 and features + 3 <= 32");
-  const size_t smem = (size_t)num_features * CT * sizeof(float);
+  const size_t smem = (size_t)32 * CT * sizeof(float);
   vm_color_features_fwd_kernel<<<blocks_for(max_count, 8), 256, smem, (cudaStream_t)stream>>>(g, t, basis, num_features, CT, view_dirs, rows);
   return check_launch("srf_vm_color_features_fwd");
 }
