@@ -186,10 +186,86 @@ def run_ours(args, rank, world, device):
                      'kernel_share_of_step': mlp_ms / ms_dev, 'launches': len(mlp)},
         'clocks': clocks.summary(),
     }
+    if world == 1 and not args.no_extras:
+        line['extras'] = extras(device)
     if rank == 0:
         if world == 1:
             line['cpu_baseline'] = cpu_baseline(budget_s=12.0)
         print(json.dumps(line), flush=True)
+
+
+def _time_steps(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extras(device):
+    """Secondary, informational measurements of the other BASELINE.json configs (single GPU, device-timed):
+    Simple-TensoRF frame render (configs[3] shape) and one Simple-NeRF training iteration (configs[1] shape;
+    its MLP backward is still the library-GEMM interim of DESIGN.md §6, so it is NOT a headline number)."""
+    from simple_rf_b200 import synthetic
+    from simple_rf_b200.models.SimpleNeRF91 import SimpleNeRF
+    from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask, SimpleTensoRF
+    out = {}
+    # ---- Simple-TensoRF: 576x1024 frame, 300^3-class grid (331x368x220 -> 1083 samples/ray), 5 % occupancy mask
+    try:
+        cfg = synthetic.tensorf_configs(num_voxels=300 ** 3, augmentations=False)
+        mc = synthetic.scene_model_configs('re10k', num_views=3)
+        torch.manual_seed(0)
+        model = SimpleTensoRF(cfg, mc).to(device).eval()
+        t = model.coarse_model
+        for p_ in t.matrices_density:
+            p_.data.mul_(6.0)
+        g = torch.Generator().manual_seed(1)
+        vol = (torch.rand(190, 190, 190, generator=g) < 0.05).float()
+        t.alpha_mask = AlphaGridMask(vol, t.bounding_box.cpu()).to(device)
+        h, w = mc['resolution']
+        pid = torch.from_numpy(synthetic.frame_pixel_ids(h, w, view=0)).to(device)
+
+        def render():
+            with torch.no_grad():
+                model({'pixel_id': pid, 'num_frames': 3})
+        ms = _time_steps(render, steps=2, warmup=1)
+        out['simple_tensorf_frame_render'] = {'rays_per_sec': pid.shape[0] / (ms * 1e-3), 'ms_per_frame': ms, 'frame': [h, w],
+                                              'grid': [int(v) for v in t.resolution.tolist()], 'samples_per_ray': int(t.num_samples),
+                                              'alpha_mask_occupancy': 0.05}
+        del model, pid
+    except Exception as e:                                    # informational: never take the contract line down
+        out['simple_tensorf_frame_render'] = {'error': repr(e)[:200]}
+    # ---- Simple-NeRF training iteration: 4096 rays, main coarse+fine + both augmentations, Adam step
+    try:
+        cfg = synthetic.nerf_configs(rng_mode='device')
+        mc = synthetic.scene_model_configs('llff', num_views=3)
+        torch.manual_seed(0)
+        model = SimpleNeRF(cfg, mc).to(device).train()
+        opt = torch.optim.Adam(model.get_trainable_parameters(cfg['optimizers'][0]), betas=(0.9, 0.999))
+        g = torch.Generator().manual_seed(2)
+        pid = torch.stack([torch.randint(0, 3, (4096,), generator=g), torch.randint(0, FRAME_W, (4096,), generator=g),
+                           torch.randint(0, FRAME_H, (4096,), generator=g)], 1).int().to(device)
+        target = torch.rand(4096, 3, device=device)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            o = model({'pixel_id': pid, 'num_frames': 3, 'iter_num': 0, 'sub_batch_index': 0})
+            loss = sum(((o[k] - target) ** 2).mean() for k in ('rgb_coarse', 'rgb_fine', 'points_augmentation_rgb_coarse',
+                                                                 'views_augmentation_rgb_coarse'))
+            loss = loss + 0.1 * (o['depth_coarse'] - o['points_augmentation_depth_coarse'].detach()).square().mean()
+            loss.backward()
+            opt.step()
+        ms = _time_steps(step, steps=3, warmup=2)
+        out['simple_nerf_train_iteration'] = {'iters_per_sec': 1e3 / ms, 'ms_per_iter': ms, 'rays_per_iter': 4096,
+                                              'note': 'forward on tcgen05 kernels; MLP backward = interim library GEMMs (DESIGN.md §6)'}
+    except Exception as e:
+        out['simple_nerf_train_iteration'] = {'error': repr(e)[:200]}
+    return out
 
 
 def cpu_render_sample(num_rays, configs, model_configs, sets):
@@ -258,6 +334,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-extras', action='store_true', help='skip the informational secondary measurements')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
