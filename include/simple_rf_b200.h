@@ -99,6 +99,7 @@ typedef struct {
   int32_t head;               /* 0 none; 1 sigma = relu(w.h + b [+ noise]); 2 sigma + sigmoid rgb (4 rows); 3 sigmoid rgb (3 rows) */
   int32_t bias_offset;        /* float offsets into `side` */
   int32_t head_offset;
+  int32_t save_slot;          /* training: first image slot of this layer's output in the saved tile, or -1 */
   int64_t weight_offset;      /* byte offset into `weights` */
 } srf_mlp_layer;
 
@@ -113,10 +114,14 @@ typedef struct {
 /*   rays_o, rays_d [R,3]: origin / direction the sample points are built from (the NDC pair when ndc);
  *   z [R,S];  view_dirs [R,3] (NULL iff views_degree < 0);  noise [R*S] nullable: the reference's
  *   randn * raw_noise_std (SimpleNeRF17.py:739-741), added before the sigma ReLU;
- *   sigma [R*S], rgb [R*S,3]: post-activation outputs. */
+ *   sigma [R*S], rgb [R*S,3]: post-activation outputs.
+ *   Training (save_acts != NULL): every A-operand tile is also written to HBM as [tile][act_slots][128 x 64 bf16
+ *   swizzled image] (encodings at e_slot / v_slot, layer outputs at layers[l].save_slot) together with ReLU bit masks
+ *   save_masks [tile][num_layers][128][8 words]; these feed srf_nerf_mlp_dgrad / srf_nerf_mlp_wgrad. */
 int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
                      const float* rays_d, const float* z, const float* view_dirs, const float* noise,
-                     int64_t num_rays, int num_samples, float* sigma, float* rgb, void* stream);
+                     int64_t num_rays, int num_samples, float* sigma, float* rgb, void* save_acts,
+                     uint32_t* save_masks, int act_slots, int e_slot, int v_slot, void* stream);
 int srf_nerf_mlp_program_bytes(void);   /* sizeof(srf_mlp_program) as compiled, for binding self-checks */
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ class MlpLayer(ctypes.Structure):
     _fields_ = [('num_kblocks', ctypes.c_int32), ('kblock_region', ctypes.c_int32 * MAX_KBLOCKS),
                 ('kblock_ksteps', ctypes.c_int32 * MAX_KBLOCKS), ('n', ctypes.c_int32), ('relu', ctypes.c_int32),
                 ('write_h', ctypes.c_int32), ('head', ctypes.c_int32), ('bias_offset', ctypes.c_int32),
-                ('head_offset', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
+                ('head_offset', ctypes.c_int32), ('save_slot', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
 
 
 class MlpProgram(ctypes.Structure):
@@ -159,9 +159,10 @@ class PackedMLP:
         self.side = flat[self._side_idx].contiguous()
         return self
 
-    def forward(self, rays_o, rays_d, z, view_dirs=None, noise=None):
+    def forward(self, rays_o, rays_d, z, view_dirs=None, noise=None, save=False):
         """rays_o/rays_d [R,3] (the origin/direction the sample points are built from), z [R,S].
-        Returns sigma [R,S,1], rgb [R,S,3] (post-activation, as MLP.forward returns them)."""
+        Returns sigma [R,S,1], rgb [R,S,3] (post-activation, as MLP.forward returns them); with save=True also
+        (acts uint8 [tiles, act_slots, 16384], masks int32 [tiles, layers, 128, 8]) for the backward kernels."""
         assert self.blob is not None, 'call refresh(params) first'
         L.require_cuda(rays_o, rays_d, z, view_dirs, noise)
         rays_o, rays_d, z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
@@ -171,9 +172,18 @@ class PackedMLP:
         rgb = torch.empty((R, S, 3), dtype=torch.float32, device=z.device)
         if self.use_views and view_dirs is None:
             raise L.SimpleRFNativeError('this MLP variant needs view_dirs')
-        L.call('srf_nerf_mlp_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
+        acts = masks = None
+        prog = self.program
+        if save:
+            tiles = (R * S + 127) // 128
+            acts = torch.empty((tiles, prog.act_slots, 16384), dtype=torch.uint8, device=z.device)
+            masks = torch.empty((tiles, prog.num_layers, 128, 8), dtype=torch.int32, device=z.device)
+        L.call('srf_nerf_mlp_fwd', ctypes.addressof(prog), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
                L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
-               L.ptr(sigma), L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)
+               L.ptr(sigma), L.ptr(rgb), L.ptr(acts), L.ptr(masks), prog.act_slots if save else 0, 0, max(prog.v_slot, 0),
+               L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)
+        if save:
+            return sigma, rgb, acts, masks
         return sigma, rgb
 
 
@@ -187,6 +197,7 @@ def build_program(layers, shapes, offs, zero, points_degree, views_degree, head_
     prog.points_degree = points_degree
     prog.views_degree = views_degree
     gather, side, woff = [], [], 0
+    slot = 1                                                   # saved-tile image slots: 0 = E, layer outputs, then V
     e = np.arange(128 * 64)
     r = e // 64
     unit = (e % 64) // 8
@@ -196,6 +207,8 @@ def build_program(layers, shapes, offs, zero, points_degree, views_degree, head_
         Lr.num_kblocks = len(kbs)
         Lr.n, Lr.relu, Lr.write_h, Lr.head = n, relu, write_h, head
         Lr.weight_offset = woff * 2
+        Lr.save_slot = slot
+        slot += n // 64
         for bi, (region, cols) in enumerate(kbs):
             Lr.kblock_region[bi] = region
             used = max(j for j, cc in enumerate(cols) if cc >= 0) + 1
@@ -218,6 +231,8 @@ def build_program(layers, shapes, offs, zero, points_degree, views_degree, head_
             side += [offs[f'{hname}.weight'] + r_ * shapes[f'{hname}.weight'][1] + c_ for r_ in range(rows) for c_ in range(n)]
             side += [offs[f'{hname}.bias'] + r_ for r_ in range(rows)]
     prog.side_count = len(side)
+    prog.v_slot = slot if views_degree >= 0 else -1             # python-side attributes (not part of the C struct)
+    prog.act_slots = slot + (1 if views_degree >= 0 else 0)
     return prog, woff, np.concatenate(gather).astype(np.int64), np.asarray(side, dtype=np.int64)
 
 
