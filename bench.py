@@ -209,8 +209,8 @@ def _time_steps(fn, steps, warmup):
 
 def extras(device):
     """Secondary, informational measurements of the other BASELINE.json configs (single GPU, device-timed):
-    Simple-TensoRF frame render (configs[3] shape) and one Simple-NeRF training iteration (configs[1] shape;
-    its MLP backward is still the library-GEMM interim of DESIGN.md §6, so it is NOT a headline number)."""
+    Simple-TensoRF frame render (configs[3] shape) and one Simple-NeRF training iteration (configs[1] shape:
+    4096 rays, main coarse + fine + both augmented MLPs, forward + hand-written tcgen05 backward + Adam step)."""
     from simple_rf_b200 import synthetic
     from simple_rf_b200.models.SimpleNeRF91 import SimpleNeRF
     from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask, SimpleTensoRF
@@ -262,7 +262,7 @@ def extras(device):
             opt.step()
         ms = _time_steps(step, steps=3, warmup=2)
         out['simple_nerf_train_iteration'] = {'iters_per_sec': 1e3 / ms, 'ms_per_iter': ms, 'rays_per_iter': 4096,
-                                              'note': 'forward on tcgen05 kernels; MLP backward = interim library GEMMs (DESIGN.md §6)'}
+                                              'note': 'forward + dgrad + wgrad on tcgen05 kernels, compositing backward hand-written; synthetic MSE + depth-consistency loss'}
     except Exception as e:
         out['simple_nerf_train_iteration'] = {'error': repr(e)[:200]}
     return out

@@ -187,6 +187,40 @@ int srf_gather_rows(const int* indices, const int* count, int64_t max_count, con
 int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const float* rows, const int* count,
                      int64_t max_rows, float* rgb, void* stream);
 
+/* Weight gradients of the fused MLP (what autograd derives for the nn.Linear layers of
+ * src/models/SimpleNeRF17.py:644-666): dW = dZ^T X and db = colsum(dZ) on tcgen05, K = samples.  `acts` are the
+ * activation tile images saved by srf_nerf_mlp_fwd, `dz` the pre-activation gradient images written by
+ * srf_nerf_mlp_dgrad (same 128 x 64 bf16 swizzled format, [tile][slots][16 KB]).  Each work item (HOST array)
+ * multiplies dz images [dz_slot, dz_slot + dz_images) (64 output channels each; 2 or 4 images) with act images
+ * [x_slot, x_slot + x_images) and ADDS rows [0, out_rows) x image columns [in_col0, in_col0 + in_cols) into
+ * grads[dw_offset + row * w_stride + w_col0 + (col - in_col0)] (+ column sums into grads[db_offset + row] if bias). */
+typedef struct {
+  int32_t dz_slot, dz_images, x_slot, x_images;
+  int32_t out_rows, in_col0, in_cols, w_col0, w_stride, bias;
+  int64_t dw_offset, db_offset;
+} srf_wgrad_item;
+int srf_nerf_mlp_wgrad(const void* items, int num_items, const void* acts, int act_slots, const void* dz, int dz_slots,
+                       int64_t num_tiles, float* grads, void* stream);
+int srf_wgrad_item_bytes(void);
+
+/* Data-gradient chain of the fused MLP (what autograd derives for src/models/SimpleNeRF17.py:726-785): from
+ * g_sigma [M], g_rgb [M,3] (nullable) through the heads and every hidden layer down to layer 1, on tcgen05 with the
+ * transposed weights streamed as swizzled images ([layer][128-row half of the 256 inputs][K block of outputs]).
+ * Reads the ReLU bit masks and the sigma / rgb outputs of srf_nerf_mlp_fwd; writes every layer's pre-activation
+ * gradient as tile images into dz [tile][dz_slots][16 KB] for srf_nerf_mlp_wgrad. */
+typedef struct {
+  int32_t num_kblocks, mask_layer, rank1_offset, dz_slot;
+  int64_t weight_offset;
+} srf_dgrad_layer;
+typedef struct {
+  int32_t num_layers, num_fwd_layers, top_width, top_mask_layer, top_slot, head_slot, head_kind, head_w_offset, side_count, pad_;
+  srf_dgrad_layer layers[12];
+} srf_dgrad_program;
+int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const uint32_t* masks,
+                       const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
+                       void* dz, int dz_slots, void* stream);
+int srf_dgrad_program_bytes(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,319 @@
+// Data-gradient chain of the fused NeRF MLP on tcgen05 tensor cores: from (d loss / d sigma, d loss / d rgb)
+// back through the heads, the view branch, the feature layer and the 8x256 trunk, one persistent CTA per SM,
+// 128 samples per tile — the mirror image of nerf_mlp.cu.
+//
+// Replaces what autograd derives for src/models/SimpleNeRF17.py:726-785 (MLP trunk / heads).  Per tile:
+//   init warps : d_o = g_rgb * rgb * (1 - rgb), d_sigma_raw = g_sigma * [sigma > 0]; the gradient entering the top
+//                hidden layer, dZ_top = (sum_c d_o[c] W_head[c,:]) * relu-mask, as bf16 A-operand K blocks; the head
+//                gradient images [d_o | d_sigma_raw] for the weight-gradient kernel
+//   MMA thread : dX = dZ * W  as  tcgen05.mma with the TRANSPOSED weights streamed as pre-swizzled images
+//   epilogue   : tcgen05.ld -> (+ d_sigma_raw * w_sigma for the layer under the sigma head) -> * ReLU bit mask saved
+//                by the forward -> bf16 -> next layer's A operand (in place) AND the dZ tile image in HBM that
+//                srf_nerf_mlp_wgrad multiplies with the saved activations.
+// Sample points and encodings carry no gradient (z_samples.detach(), frozen cameras), so the chain stops at layer 1.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace srf {
+
+constexpr int DG_MAX_LAYERS = 12;
+
+struct DgradLayer {           // mirrors srf_dgrad_layer in include/simple_rf_b200.h
+  int32_t num_kblocks;        // 64-wide K blocks of the incoming gradient (output width of the forward layer / 64)
+  int32_t mask_layer;         // forward layer whose ReLU mask gates this layer's output, or -1
+  int32_t rank1_offset;       // >= 0: side offset of w_sigma[256]; adds d_sigma_raw[row] * w_sigma[col] before the mask
+  int32_t dz_slot;            // first dz image slot of the 256-wide output
+  int64_t weight_offset;      // byte offset into the transposed-weight blob
+};
+
+struct DgradProgram {
+  int32_t num_layers, num_fwd_layers;
+  int32_t top_width;          // 128 or 256
+  int32_t top_mask_layer;     // forward layer whose mask gates dZ_top
+  int32_t top_slot;           // dz slot of dZ_top (top_width / 64 images)
+  int32_t head_slot;          // dz slots [head_slot, head_slot + 2): head-gradient images
+  int32_t head_kind;          // 1: 3-row rgb head (d_o in image 0, d_sigma_raw in image 1 col 0); 2: 4-row head [sigma, r, g, b]
+  int32_t head_w_offset;      // side offset of the head weights [rows][top_width]
+  int32_t side_count;
+  int32_t pad_;
+  DgradLayer layers[DG_MAX_LAYERS];
+};
+
+struct DgradArgs {
+  const uint8_t* weights_t;   // transposed-weight images
+  const float* side;
+  const uint32_t* masks;      // [tile][num_fwd_layers][128][8]
+  const float* sigma; const float* rgb;       // forward outputs [M], [M,3]
+  const float* g_sigma; const float* g_rgb;   // upstream gradients [M], [M,3] (nullable)
+  uint8_t* dz;                // [tile][dz_slots][16 KB]
+  int dz_slots;
+  long long total;
+};
+
+constexpr int DG_GROUPS = 2;
+constexpr int DG_COLS = 32;
+constexpr int DG_EPI_WARP0 = 2;
+constexpr int DG_INIT_WARP0 = DG_EPI_WARP0 + 4 * DG_GROUPS;
+constexpr int DG_THREADS = 32 * (DG_INIT_WARP0 + 4);
+constexpr int DG_KBLOCK = 128 * 128;
+constexpr int DG_STAGE = 2 * DG_KBLOCK;
+constexpr int DG_STAGES = 3;
+constexpr int DG_MAX_SIDE = 2048;
+
+struct alignas(1024) DgradSmem {
+  uint8_t h[4][DG_KBLOCK];
+  uint8_t w[DG_STAGES][DG_STAGE];
+  float side[DG_MAX_SIDE];
+  float dsig[128];
+  uint64_t w_full[DG_STAGES], w_empty[DG_STAGES];
+  uint64_t a_ready[4];        // H block rewritten by the epilogue of the previous backward layer
+  uint64_t top_ready;         // H blocks written by the init warps
+  uint64_t h_free;            // every MMA of the tile's last layer has retired
+  uint64_t d_full[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __grid_constant__ DgradProgram prog,
+                                                                       const DgradArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  DgradSmem& sm = *reinterpret_cast<DgradSmem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
+  for (int i = threadIdx.x; i < prog.side_count; i += DG_THREADS) sm.side[i] = args.side[i];
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < DG_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
+    for (int r = 0; r < 4; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * DG_GROUPS);
+    ptx::mbar_init(&sm.top_ready, 4);
+    ptx::mbar_init(&sm.h_free, 1);
+    ptx::mbar_init(&sm.d_full[0], 1);
+    ptx::mbar_init(&sm.d_full[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const int num_tiles = (int)((args.total + 127) / 128);
+  const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int NL = prog.num_layers;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ transposed-weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = 0; t < my_tiles; ++t)
+        for (int l = 0; l < NL; ++l) {
+          const DgradLayer& L = prog.layers[l];
+          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
+            const uint32_t st = it % DG_STAGES, ph = (it / DG_STAGES) & 1;
+            ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
+            ptx::mbar_arrive_expect_tx(&sm.w_full[st], DG_STAGE);
+            for (int nh = 0; nh < 2; ++nh)
+              ptx::bulk_g2s(sm.w[st] + nh * DG_KBLOCK, args.weights_t + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * DG_KBLOCK,
+                            DG_KBLOCK, &sm.w_full[st]);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 256);
+      uint32_t it = 0, layer_count = 0, a_phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        ptx::mbar_wait(&sm.top_ready, t & 1);
+        for (int l = 0; l < NL; ++l, ++layer_count) {
+          const DgradLayer& L = prog.layers[l];
+          const uint32_t buf = layer_count & 1;
+          const uint32_t d_addr = tmem + buf * 256;
+          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
+            const uint32_t st = it % DG_STAGES, ph = (it / DG_STAGES) & 1;
+            if (l > 0) {
+              ptx::mbar_wait(&sm.a_ready[kb], (a_phase >> kb) & 1);
+              a_phase ^= 1u << kb;
+            }
+            ptx::mbar_wait(&sm.w_full[st], ph);
+            ptx::tc_fence_after();
+            const uint64_t a_desc = ((uint64_t)desc_hi << 32) | ((ptx::smem_u32(sm.h[kb]) >> 4) & 0x3FFF);
+            const uint64_t b_desc = ((uint64_t)desc_hi << 32) | ((ptx::smem_u32(sm.w[st]) >> 4) & 0x3FFF);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+            ptx::umma_commit(&sm.w_empty[st]);
+          }
+          ptx::umma_commit(&sm.d_full[buf]);
+          if (l == NL - 1) ptx::umma_commit(&sm.h_free);
+        }
+      }
+    }
+  } else if (warp >= DG_INIT_WARP0) {
+    // ------------------------------------------------------------ init warps: heads -> dZ_top, head-gradient images
+    const int row = (warp - DG_INIT_WARP0) * 32 + lane;
+    const int tw = prog.top_width;
+    const float* hw = sm.side + prog.head_w_offset;
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long m = tile * 128 + row;
+      const bool valid = m < args.total;
+      float d_o[4] = {0.f, 0.f, 0.f, 0.f};            // head_kind 1: [r, g, b, -]; head_kind 2: [sigma, r, g, b]
+      float dsig = 0.f;
+      if (valid) {
+        if (args.g_sigma != nullptr && args.sigma[m] > 0.f) dsig = args.g_sigma[m];
+        if (args.g_rgb != nullptr) {
+          const int b = prog.head_kind == 2 ? 1 : 0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { const float y = args.rgb[m * 3 + c]; d_o[b + c] = args.g_rgb[m * 3 + c] * y * (1.f - y); }
+        }
+        if (prog.head_kind == 2) d_o[0] = dsig;
+      }
+      const int head_rows = prog.head_kind == 2 ? 4 : 3;
+      // head-gradient images (image 0: d_o in the first columns; image 1: d_sigma_raw in column 0), rest zero
+      {
+        uint8_t* img = args.dz + ((size_t)tile * args.dz_slots + prog.head_slot) * DG_KBLOCK;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 1; u < 8; ++u) {
+          *reinterpret_cast<uint4*>(img + ptx::sw128_offset(row, u)) = zero;
+          *reinterpret_cast<uint4*>(img + DG_KBLOCK + ptx::sw128_offset(row, u)) = zero;
+        }
+        *reinterpret_cast<uint4*>(img + ptx::sw128_offset(row, 0)) = make_uint4(ptx::pack_bf16(d_o[0], d_o[1]), ptx::pack_bf16(d_o[2], d_o[3]), 0u, 0u);
+        *reinterpret_cast<uint4*>(img + DG_KBLOCK + ptx::sw128_offset(row, 0)) = make_uint4(ptx::pack_bf16(dsig, 0.f), 0u, 0u, 0u);
+      }
+      const uint32_t* mrow = args.masks + (((size_t)tile * prog.num_fwd_layers + prog.top_mask_layer) * 128 + row) * 8;
+      uint32_t mbits[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mbits[q] = (q * 32 < tw) ? mrow[q] : 0u;
+      // H of the previous tile is still being read until its last layer's MMAs retire
+      ptx::mbar_wait(&sm.h_free, (t & 1) ^ 1);
+      sm.dsig[row] = dsig;
+      uint8_t* top = args.dz + ((size_t)tile * args.dz_slots + prog.top_slot) * DG_KBLOCK;
+      for (int u = 0; u < tw / 8; ++u) {               // 8 columns (one 16-byte unit) at a time
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = u * 8 + j;
+          float a = 0.f;
+          for (int c = 0; c < head_rows; ++c) a = fmaf(d_o[c], hw[c * tw + col], a);
+          v[j] = ((mbits[col >> 5] >> (col & 31)) & 1u) ? a : 0.f;
+        }
+        const uint4 q = make_uint4(ptx::pack_bf16(v[0], v[1]), ptx::pack_bf16(v[2], v[3]), ptx::pack_bf16(v[4], v[5]), ptx::pack_bf16(v[6], v[7]));
+        const uint32_t off = ptx::sw128_offset(row, u & 7);
+        *reinterpret_cast<uint4*>(sm.h[u >> 3] + off) = q;
+        *reinterpret_cast<uint4*>(top + (size_t)(u >> 3) * DG_KBLOCK + off) = q;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.top_ready);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;
+    const int grp = (warp - DG_EPI_WARP0) >> 2;
+    const int row = quarter * 32 + lane;
+    uint32_t layer_count = 0, d_phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      for (int l = 0; l < NL; ++l, ++layer_count) {
+        const DgradLayer& L = prog.layers[l];
+        const uint32_t buf = layer_count & 1;
+        const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + grp * DG_COLS;
+        const bool last = l == NL - 1;
+        const float* wsig = L.rank1_offset >= 0 ? sm.side + L.rank1_offset : nullptr;
+        const uint32_t* mrow = L.mask_layer >= 0 ? args.masks + (((size_t)tile * prog.num_fwd_layers + L.mask_layer) * 128 + row) * 8 : nullptr;
+        uint8_t* out = args.dz + ((size_t)tile * args.dz_slots + L.dz_slot) * DG_KBLOCK;
+        uint32_t mw[4];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) mw[kb] = mrow != nullptr ? mrow[kb * 2 + grp] : 0xffffffffu;
+        ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
+        d_phase ^= 1u << buf;
+        ptx::tc_fence_after();
+        const float ds = wsig != nullptr ? sm.dsig[row] : 0.f;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          uint32_t v[32], pk[16];
+          ptx::tmem_ld32(t_row + kb * 64, v);
+          ptx::tmem_ld_wait(v);
+          const int col0 = kb * 64 + grp * DG_COLS;
+          if (wsig != nullptr) {
+            const float4* w4 = reinterpret_cast<const float4*>(wsig + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w = w4[q];
+              v[4 * q + 0] = __float_as_uint(fmaf(ds, w.x, __uint_as_float(v[4 * q + 0])));
+              v[4 * q + 1] = __float_as_uint(fmaf(ds, w.y, __uint_as_float(v[4 * q + 1])));
+              v[4 * q + 2] = __float_as_uint(fmaf(ds, w.z, __uint_as_float(v[4 * q + 2])));
+              v[4 * q + 3] = __float_as_uint(fmaf(ds, w.w, __uint_as_float(v[4 * q + 3])));
+            }
+          }
+          const uint32_t bits = mw[kb];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = ((bits >> (2 * j)) & 1u) ? __uint_as_float(v[2 * j]) : 0.f;
+            const float b = ((bits >> (2 * j + 1)) & 1u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
+            pk[j] = ptx::pack_bf16(a, b);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 q = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            const uint32_t off = ptx::sw128_offset(row, grp * 4 + u);
+            *reinterpret_cast<uint4*>(out + (size_t)kb * DG_KBLOCK + off) = q;
+            if (!last) *reinterpret_cast<uint4*>(sm.h[kb] + off) = q;
+          }
+          if (!last) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&sm.a_ready[kb]);
+          }
+        }
+        ptx::tc_fence_before();
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace srf
+
+using namespace srf;
+
+SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const uint32_t* masks,
+                               const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
+                               void* dz, int dz_slots, void* stream) {
+  if (num_rows == 0) return 0;
+  SRF_REQUIRE(program && weights_t && side && masks && sigma && rgb && dz, "srf_nerf_mlp_dgrad", "null pointer");
+  DgradProgram prog = *reinterpret_cast<const DgradProgram*>(program);
+  SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= DG_MAX_LAYERS, "srf_nerf_mlp_dgrad", "bad layer count");
+  SRF_REQUIRE(prog.top_width == 128 || prog.top_width == 256, "srf_nerf_mlp_dgrad", "top width must be 128 or 256");
+  SRF_REQUIRE(prog.head_kind == 1 || prog.head_kind == 2, "srf_nerf_mlp_dgrad", "bad head kind");
+  SRF_REQUIRE(prog.side_count <= DG_MAX_SIDE, "srf_nerf_mlp_dgrad", "side table too large");
+  SRF_REQUIRE(prog.layers[0].num_kblocks * 64 == prog.top_width, "srf_nerf_mlp_dgrad", "first layer must consume dZ_top");
+  for (int l = 0; l < prog.num_layers; ++l) {
+    const DgradLayer& L = prog.layers[l];
+    SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= 4 && (l == 0 || L.num_kblocks == 4), "srf_nerf_mlp_dgrad", "bad K-block count");
+    SRF_REQUIRE(L.dz_slot >= 0 && L.dz_slot + 4 <= dz_slots && L.mask_layer < prog.num_fwd_layers, "srf_nerf_mlp_dgrad", "bad slot / mask index");
+    SRF_REQUIRE(L.rank1_offset < 0 || (L.rank1_offset & 3) == 0, "srf_nerf_mlp_dgrad", "rank-1 offset must be a multiple of 4");
+  }
+  SRF_REQUIRE(prog.head_slot >= 0 && prog.head_slot + 2 <= dz_slots && prog.top_slot >= 0 && prog.top_slot + prog.top_width / 64 <= dz_slots,
+              "srf_nerf_mlp_dgrad", "bad head / top slot");
+  DgradArgs a{};
+  a.weights_t = reinterpret_cast<const uint8_t*>(weights_t); a.side = side; a.masks = masks; a.sigma = sigma; a.rgb = rgb;
+  a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dz = reinterpret_cast<uint8_t*>(dz); a.dz_slots = dz_slots; a.total = num_rows;
+  const size_t smem = sizeof(DgradSmem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("srf_nerf_mlp_dgrad", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long tiles = (num_rows + 127) / 128;
+  const int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  nerf_mlp_dgrad_kernel<<<grid, DG_THREADS, smem, (cudaStream_t)stream>>>(prog, a);
+  return check_launch("srf_nerf_mlp_dgrad");
+}
+
+SRF_API int srf_dgrad_program_bytes(void) { return (int)sizeof(DgradProgram); }

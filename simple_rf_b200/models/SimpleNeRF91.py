@@ -317,62 +317,32 @@ class MLP(torch.nn.Module):
 
 
 class _FusedMLP(torch.autograd.Function):
-    """Forward: the fused tcgen05 kernel.  Backward (round-1 interim): activations are
-    recomputed and differentiated with library GEMMs (cuBLAS through torch) in fp32; the hand-written
-    dgrad/wgrad tensor-core kernels replace this in the next round."""
+    """Forward: the fused tcgen05 kernel, also saving activation tiles + ReLU masks.  Backward: the hand-written
+    dgrad chain (srf_nerf_mlp_dgrad) and weight-gradient GEMMs (srf_nerf_mlp_wgrad) on the tensor cores."""
 
     @staticmethod
     def forward(ctx, module, rays_o, rays_d, z, view_dirs, noise, *params):
         packed = module.packed()
-        sigma, rgb = packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise)
-        ctx.module = module
-        ctx.save_for_backward(rays_o, rays_d, z, view_dirs, noise, sigma, *params)
+        sigma, rgb, acts, masks = packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise, save=True)
+        ctx.packed = packed
+        ctx.flat = packed.flat
+        ctx.shapes = [p.shape for p in params]
+        ctx.save_for_backward(acts, masks, sigma, rgb)
         return sigma, rgb
 
     @staticmethod
     def backward(ctx, g_sigma, g_rgb):
-        rays_o, rays_d, z, view_dirs, noise, sigma, *params = ctx.saved_tensors
-        module = ctx.module
-        names = module._packed.param_names
-        with torch.enable_grad():
-            ps = [p.detach().requires_grad_() for p in params]
-            s, c = _torch_mlp(module, dict(zip(names, ps)), rays_o, rays_d, z, view_dirs, noise)
-            grads = torch.autograd.grad([s, c], ps, [g_sigma, g_rgb], allow_unused=True)
+        from ..nerf_program import mlp_backward
+        acts, masks, sigma, rgb = ctx.saved_tensors
+        flat_grad, _ = mlp_backward(ctx.packed, ctx.flat, acts, masks, sigma, rgb, g_sigma, g_rgb)
+        grads, o = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            grads.append(flat_grad[o:o + n].view(shp))
+            o += n
         return (None, None, None, None, None, None, *grads)
-
-
-def _torch_mlp(module, p, rays_o, rays_d, z, view_dirs, noise):
-    """fp32 restatement of MLP.forward used only by the interim backward above."""
-    import torch.nn.functional as F
-    cfg = module.mlp_configs
-    R, S = z.shape
-    pts = (rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]).reshape(-1, 3)
-
-    def enc(x, deg):
-        parts = [x]
-        for k in range(deg):
-            parts += [torch.sin(x * 2. ** k), torch.cos(x * 2. ** k)]
-        return torch.cat(parts, -1)
-    e = enc(pts, cfg['points_positional_encoding_degree'])
-    x_in = e[:, :module.pts_input_dim]
-    hcur = x_in
-    for i in range(module.Dp):
-        hcur = F.relu(F.linear(hcur, p[f'pts_linears.{i}.weight'], p[f'pts_linears.{i}.bias']))
-        if i in module.skips:
-            hcur = torch.cat([x_in, hcur], -1)
-    head = F.linear(hcur, p['pts_output_linear.weight'], p['pts_output_linear.bias'])
-    raw = head[:, 0:1]
-    if noise is not None:
-        raw = raw + noise.reshape(-1, 1)
-    sigma = F.relu(raw).reshape(R, S, 1)
-    if not module.view_dep_rgb:
-        return sigma, torch.sigmoid(head[:, 1:4]).reshape(R, S, 3)
-    feat = F.linear(hcur, p['feature_linear.weight'], p['feature_linear.bias'])
-    ev = enc(view_dirs[:, None, :].expand(R, S, 3).reshape(-1, 3), cfg['views_positional_encoding_degree'])
-    hv = F.relu(F.linear(torch.cat([feat, e[:, module.pts_input_dim:], ev], -1), p['views_linears.0.weight'],
-                         p['views_linears.0.bias']))
-    rgb = torch.sigmoid(F.linear(hv, p['views_output_linear.weight'], p['views_output_linear.bias']))
-    return sigma, rgb.reshape(R, S, 3)
 
 
 class IntrinsicsLearner(torch.nn.Module):

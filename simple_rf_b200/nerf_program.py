@@ -138,6 +138,8 @@ class PackedMLP:
         self._dev = None
         self.blob = None
         self.side = None
+        self.offs = offs
+        self.backward_plan = build_backward_plan(layers, shapes, offs, zero, self.program)
         macs = 0
         for name, n, kbs, *_ in layers:
             macs += shapes[name][0] * shapes[name][1]
@@ -155,6 +157,7 @@ class PackedMLP:
         flat = torch.cat([params[n].detach().reshape(-1).float() for n in self.param_names] +
                          [torch.zeros(1, dtype=torch.float32, device=dev)])
         assert flat.numel() == self.flat_size + 1, 'parameter shapes do not match the MLP config'
+        self.flat = flat
         self.blob = flat[self._gather].to(torch.bfloat16).contiguous()
         self.side = flat[self._side_idx].contiguous()
         return self
@@ -279,3 +282,149 @@ class PackedRowsMLP:
         L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
                L.ptr(count), max_rows, L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
         return rgb
+
+
+class WgradItem(ctypes.Structure):
+    _fields_ = [('dz_slot', ctypes.c_int32), ('dz_images', ctypes.c_int32), ('x_slot', ctypes.c_int32), ('x_images', ctypes.c_int32),
+                ('out_rows', ctypes.c_int32), ('in_col0', ctypes.c_int32), ('in_cols', ctypes.c_int32), ('w_col0', ctypes.c_int32),
+                ('w_stride', ctypes.c_int32), ('bias', ctypes.c_int32), ('dw_offset', ctypes.c_int64), ('db_offset', ctypes.c_int64)]
+
+
+def run_wgrad(items, acts, dz, grads):
+    """items: list of WgradItem; acts / dz uint8 [tiles, slots, 16384]; grads flat fp32 (accumulated into)."""
+    arr = (WgradItem * len(items))(*items)
+    tiles = acts.shape[0]
+    flops = sum(2.0 * 64 * it.dz_images * 64 * it.x_images * 128 * tiles for it in items)
+    L.call('srf_nerf_mlp_wgrad', ctypes.addressof(arr), len(items), L.ptr(acts), acts.shape[1], L.ptr(dz), dz.shape[1], tiles,
+           L.ptr(grads), L.stream_handle(), work=flops)
+
+
+class DgradLayer(ctypes.Structure):
+    _fields_ = [('num_kblocks', ctypes.c_int32), ('mask_layer', ctypes.c_int32), ('rank1_offset', ctypes.c_int32),
+                ('dz_slot', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
+
+
+class DgradProgram(ctypes.Structure):
+    _fields_ = [('num_layers', ctypes.c_int32), ('num_fwd_layers', ctypes.c_int32), ('top_width', ctypes.c_int32),
+                ('top_mask_layer', ctypes.c_int32), ('top_slot', ctypes.c_int32), ('head_slot', ctypes.c_int32),
+                ('head_kind', ctypes.c_int32), ('head_w_offset', ctypes.c_int32), ('side_count', ctypes.c_int32),
+                ('pad_', ctypes.c_int32), ('layers', DgradLayer * MAX_LAYERS)]
+
+
+class BackwardPlan:
+    """Everything the dgrad / wgrad kernels need for one MLP variant (built once from the forward layer list)."""
+    __slots__ = ('program', 'dz_slots', 'items', 'gather_t', 'side_idx', '_dev', '_gather', '_side')
+
+
+def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
+    nl = len(layers)
+    top = nl - 1
+    name_t, n_t, kbs_t, relu_t, _, head_t = layers[top]
+    plan = BackwardPlan()
+    prog = DgradProgram()
+    prog.num_fwd_layers = nl
+    prog.head_slot = 0
+    prog.top_slot = 2
+    prog.top_width = n_t
+    prog.top_mask_layer = top
+    assert relu_t and head_t in (2, 3)
+    prog.head_kind = 1 if head_t == 3 else 2
+    hname = 'views_output_linear' if head_t == 3 else 'pts_output_linear'
+    rows = shapes[f'{hname}.weight'][0]
+    side = [offs[f'{hname}.weight'] + r * n_t + c for r in range(rows) for c in range(n_t)]
+    prog.head_w_offset = 0
+    # dz slots: 0,1 head images; top; then the output of every backward layer (dZ of forward layer f-1)
+    dz_of = {top: 2}
+    slot = 2 + n_t // 64
+    e = np.arange(128 * 64)
+    r = e // 64
+    unit = (e % 64) // 8
+    c = ((unit ^ (r & 7)) * 8) + e % 8
+    gather, woff, bl = [], 0, 0
+    sigma_layer = next((i for i, L_ in enumerate(layers) if L_[5] == 1), None)      # forward layer carrying the sigma head
+    for f in range(top, 0, -1):
+        name, n, kbs, relu, write_h, head = layers[f]
+        hb = [(reg, cols) for reg, cols in kbs if 1 <= reg <= 4]
+        assert len(hb) == 4 and [reg for reg, _ in hb] == [1, 2, 3, 4], 'hidden input of every layer above 0 is 256 wide'
+        src0 = hb[0][1][0]
+        in_total = shapes[name][1]
+        Lr = prog.layers[bl]
+        Lr.num_kblocks = n // 64
+        below = layers[f - 1]
+        Lr.mask_layer = f - 1 if below[3] else -1
+        Lr.rank1_offset = -1
+        if sigma_layer is not None and sigma_layer == f - 1:
+            side += [zero] * (-len(side) % 4)
+            Lr.rank1_offset = len(side)
+            side += [offs['pts_output_linear.weight'] + j for j in range(256)]
+        dz_of[f - 1] = slot
+        Lr.dz_slot = slot
+        slot += 4
+        Lr.weight_offset = woff * 2
+        for nh in range(2):
+            for kb in range(n // 64):
+                gather.append(offs[name] + (kb * 64 + c) * in_total + src0 + nh * 128 + r)
+                woff += 128 * 64
+        bl += 1
+    prog.num_layers = bl
+    prog.side_count = len(side)
+    plan.program = prog
+    plan.dz_slots = slot
+    plan.gather_t = np.concatenate(gather).astype(np.int64)
+    plan.side_idx = np.asarray(side, dtype=np.int64)
+    # ---- weight-gradient work items
+    items = []
+    for f in range(nl):
+        name, n, kbs, relu, write_h, head = layers[f]
+        in_total = shapes[name][1]
+        bname = name.replace('.weight', '.bias')
+        first = True
+        groups = []                                   # (x_slot, x_images, in_col0, in_cols, w_col0)
+        hb = [(reg, cols) for reg, cols in kbs if 1 <= reg <= 4]
+        if hb:
+            prev_slot = fwd_prog.layers[f - 1].save_slot
+            groups.append((prev_slot, len(hb), 0, 64 * len(hb), hb[0][1][0]))
+        for reg, cols in kbs:
+            if reg in (0, 5):
+                valid = [i for i, cc in enumerate(cols) if cc >= 0]
+                assert valid == list(range(valid[0], valid[-1] + 1)) and [cols[i] for i in valid] == list(range(cols[valid[0]], cols[valid[0]] + len(valid)))
+                groups.append((0 if reg == 0 else fwd_prog.v_slot, 1, valid[0], len(valid), cols[valid[0]]))
+        for x_slot, x_images, in_col0, in_cols, w_col0 in groups:
+            items.append(WgradItem(dz_of[f], n // 64, x_slot, x_images, n, in_col0, in_cols, w_col0, in_total, 1 if first else 0,
+                                   offs[name], offs[bname]))
+            first = False
+    if prog.head_kind == 1:
+        items.append(WgradItem(1, 2, fwd_prog.layers[sigma_layer].save_slot, 4, 1, 0, 256, 0, 256, 1,
+                               offs['pts_output_linear.weight'], offs['pts_output_linear.bias']))
+        items.append(WgradItem(0, 2, fwd_prog.layers[top].save_slot, n_t // 64, 3, 0, n_t, 0, n_t, 1,
+                               offs['views_output_linear.weight'], offs['views_output_linear.bias']))
+    else:
+        items.append(WgradItem(0, 2, fwd_prog.layers[top].save_slot, 4, 4, 0, 256, 0, 256, 1,
+                               offs['pts_output_linear.weight'], offs['pts_output_linear.bias']))
+    plan.items = items
+    plan._dev = None
+    return plan
+
+
+def mlp_backward(packed, params_flat, acts, masks, sigma, rgb, g_sigma, g_rgb):
+    """Hand-written backward of one fused-MLP evaluation: dgrad chain then weight gradients.
+    params_flat: the flat fp32 parameter vector (+ trailing zero) used for the forward's refresh.
+    Returns the flat fp32 gradient (same layout as the parameters)."""
+    plan = packed.backward_plan
+    dev = acts.device
+    if plan._dev != dev:
+        plan._gather = torch.from_numpy(plan.gather_t).to(dev)
+        plan._side = torch.from_numpy(plan.side_idx).to(dev)
+        plan._dev = dev
+    wt = params_flat[plan._gather].to(torch.bfloat16).contiguous()
+    side = params_flat[plan._side].contiguous()
+    tiles = acts.shape[0]
+    rows = sigma.numel()
+    dz = torch.empty((tiles, plan.dz_slots, 16384), dtype=torch.uint8, device=dev)
+    gs = None if g_sigma is None else L.f32c(g_sigma).reshape(-1)
+    gc = None if g_rgb is None else L.f32c(g_rgb).reshape(-1, 3)
+    L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(masks), L.ptr(sigma), L.ptr(rgb),
+           L.ptr(gs), L.ptr(gc), rows, L.ptr(dz), plan.dz_slots, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
+    grads = torch.zeros(packed.flat_size, dtype=torch.float32, device=dev)
+    run_wgrad(plan.items, acts, dz, grads)
+    return grads, dz
