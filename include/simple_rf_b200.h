@@ -116,12 +116,12 @@ typedef struct {
  *   randn * raw_noise_std (SimpleNeRF17.py:739-741), added before the sigma ReLU;
  *   sigma [R*S], rgb [R*S,3]: post-activation outputs.
  *   Training (save_acts != NULL): every A-operand tile is also written to HBM as [tile][act_slots][128 x 64 bf16
- *   swizzled image] (encodings at e_slot / v_slot, layer outputs at layers[l].save_slot) together with ReLU bit masks
- *   save_masks [tile][num_layers][128][8 words]; these feed srf_nerf_mlp_dgrad / srf_nerf_mlp_wgrad. */
+ *   swizzled image] (encodings at e_slot / v_slot, layer outputs at layers[l].save_slot); these feed
+ *   srf_nerf_mlp_dgrad (as ReLU masks) and srf_nerf_mlp_wgrad (as GEMM operands). */
 int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
                      const float* rays_d, const float* z, const float* view_dirs, const float* noise,
                      int64_t num_rays, int num_samples, float* sigma, float* rgb, void* save_acts,
-                     uint32_t* save_masks, int act_slots, int e_slot, int v_slot, void* stream);
+                     int act_slots, int e_slot, int v_slot, void* stream);
 int srf_nerf_mlp_program_bytes(void);   /* sizeof(srf_mlp_program) as compiled, for binding self-checks */
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -206,17 +206,18 @@ int srf_wgrad_item_bytes(void);
 /* Data-gradient chain of the fused MLP (what autograd derives for src/models/SimpleNeRF17.py:726-785): from
  * g_sigma [M], g_rgb [M,3] (nullable) through the heads and every hidden layer down to layer 1, on tcgen05 with the
  * transposed weights streamed as swizzled images ([layer][128-row half of the 256 inputs][K block of outputs]).
- * Reads the ReLU bit masks and the sigma / rgb outputs of srf_nerf_mlp_fwd; writes every layer's pre-activation
+ * Reads the saved activation tiles (their non-zero pattern is the ReLU mask) and the sigma / rgb outputs of
+ * srf_nerf_mlp_fwd; writes every layer's pre-activation
  * gradient as tile images into dz [tile][dz_slots][16 KB] for srf_nerf_mlp_wgrad. */
 typedef struct {
-  int32_t num_kblocks, mask_layer, rank1_offset, dz_slot;
+  int32_t num_kblocks, mask_slot, rank1_offset, dz_slot;
   int64_t weight_offset;
 } srf_dgrad_layer;
 typedef struct {
-  int32_t num_layers, num_fwd_layers, top_width, top_mask_layer, top_slot, head_slot, head_kind, head_w_offset, side_count, pad_;
+  int32_t num_layers, num_fwd_layers, top_width, top_mask_slot, top_slot, head_slot, head_kind, head_w_offset, side_count, pad_;
   srf_dgrad_layer layers[12];
 } srf_dgrad_program;
-int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const uint32_t* masks,
+int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const void* acts, int act_slots,
                        const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
                        void* dz, int dz_slots, void* stream);
 int srf_dgrad_program_bytes(void);

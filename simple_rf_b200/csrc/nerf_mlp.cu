@@ -58,9 +58,9 @@ struct MlpArgs {
   float* sigma;                 // [R*S]
   float* rgb;                   // [R*S,3]
   // training: every A-operand tile (encodings, post-activation layer outputs) is also written to HBM as the same
-  // 128x64 bf16 swizzled images the tensor cores read ([tile][slot][16 KB]), plus 1 bit / activation ReLU masks
+  // 128x64 bf16 swizzled images the tensor cores read ([tile][slot][16 KB]); the backward kernels read them both as
+  // GEMM operands and as ReLU masks (post-activation value != 0)
   uint8_t* save_acts;           // or nullptr
-  uint32_t* save_masks;         // [tile][layer][128 rows][8 words] or nullptr
   int act_slots, e_slot, v_slot;
   long long total;              // R*S (rows mode: capacity of `rows`)
   int S;
@@ -371,8 +371,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + grp * COLS;
         const int save_slot = args.save_acts != nullptr ? L.save_slot : -1;
         uint8_t* save_base = save_slot >= 0 ? args.save_acts + ((size_t)tile * args.act_slots + save_slot) * KBLOCK_BYTES : nullptr;
-        uint32_t* mask_row = (save_slot >= 0 && args.save_masks != nullptr)
-                                 ? args.save_masks + (((size_t)tile * prog.num_layers + l) * 128 + row) * 8 : nullptr;
 
         // bias + activation (+ head partial dot products) on one COLS-column slice, packed to bf16 pairs
         auto compute = [&](uint32_t (&v)[COLS], uint32_t (&pk)[COLS / 2], int kb) {
@@ -400,13 +398,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           }
 #pragma unroll
           for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          if (mask_row != nullptr) {                      // 1 bit per activation: (post-activation value > 0)
-            uint32_t bits = 0;
-#pragma unroll
-            for (int j = 0; j < COLS; ++j) bits |= (__uint_as_float(v[j]) > 0.f ? 1u : 0u) << j;
-            if (COLS == 32) mask_row[kb * 2 + grp] = bits;
-            else reinterpret_cast<uint16_t*>(mask_row)[(kb * 64 + grp * COLS) >> 4] = (uint16_t)bits;
-          }
         };
         // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H:
         // every MMA of this layer has retired once d_full fired)
@@ -557,10 +548,10 @@ int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, vo
 SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
                              const float* rays_d, const float* z, const float* view_dirs, const float* noise,
                              int64_t num_rays, int num_samples, float* sigma, float* rgb, void* save_acts,
-                             uint32_t* save_masks, int act_slots, int e_slot, int v_slot, void* stream) {
+                             int act_slots, int e_slot, int v_slot, void* stream) {
   if (num_rays == 0) return 0;
   SRF_REQUIRE(program && weights && side && rays_o && rays_d && z && sigma && rgb, "srf_nerf_mlp_fwd", "null pointer");
-  SRF_REQUIRE(save_acts == nullptr || (save_masks != nullptr && act_slots > 0 && e_slot >= 0 && e_slot < act_slots && v_slot < act_slots),
+  SRF_REQUIRE(save_acts == nullptr || (act_slots > 0 && e_slot >= 0 && e_slot < act_slots && v_slot < act_slots),
               "srf_nerf_mlp_fwd", "bad activation-save description");
   MlpProgram prog = *reinterpret_cast<const MlpProgram*>(program);
   if (validate_program(prog, "srf_nerf_mlp_fwd", false)) return 1;
@@ -569,7 +560,7 @@ SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const flo
   a.weights = reinterpret_cast<const uint8_t*>(weights);
   a.side = side; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.view_dirs = view_dirs; a.noise = noise;
   a.sigma = sigma; a.rgb = rgb;
-  a.save_acts = reinterpret_cast<uint8_t*>(save_acts); a.save_masks = save_masks;
+  a.save_acts = reinterpret_cast<uint8_t*>(save_acts);
   a.act_slots = act_slots; a.e_slot = e_slot; a.v_slot = v_slot;
   a.total = (long long)num_rays * num_samples;
   a.S = num_samples;

@@ -7,9 +7,10 @@
 //                hidden layer, dZ_top = (sum_c d_o[c] W_head[c,:]) * relu-mask, as bf16 A-operand K blocks; the head
 //                gradient images [d_o | d_sigma_raw] for the weight-gradient kernel
 //   MMA thread : dX = dZ * W  as  tcgen05.mma with the TRANSPOSED weights streamed as pre-swizzled images
-//   epilogue   : tcgen05.ld -> (+ d_sigma_raw * w_sigma for the layer under the sigma head) -> * ReLU bit mask saved
-//                by the forward -> bf16 -> next layer's A operand (in place) AND the dZ tile image in HBM that
-//                srf_nerf_mlp_wgrad multiplies with the saved activations.
+//   epilogue   : tcgen05.ld -> (+ d_sigma_raw * w_sigma for the layer under the sigma head) -> bf16 -> AND with the
+//                ReLU mask (non-zero pattern of the activation tile the forward saved, two values per 32-bit lane) ->
+//                next layer's A operand (in place) AND the dZ tile image in HBM that srf_nerf_mlp_wgrad multiplies
+//                with the saved activations.
 // Sample points and encodings carry no gradient (z_samples.detach(), frozen cameras), so the chain stops at layer 1.
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -20,7 +21,7 @@ constexpr int DG_MAX_LAYERS = 12;
 
 struct DgradLayer {           // mirrors srf_dgrad_layer in include/simple_rf_b200.h
   int32_t num_kblocks;        // 64-wide K blocks of the incoming gradient (output width of the forward layer / 64)
-  int32_t mask_layer;         // forward layer whose ReLU mask gates this layer's output, or -1
+  int32_t mask_slot;          // saved-activation slot (4 images) whose non-zero pattern is the ReLU mask of this layer's output, or -1
   int32_t rank1_offset;       // >= 0: side offset of w_sigma[256]; adds d_sigma_raw[row] * w_sigma[col] before the mask
   int32_t dz_slot;            // first dz image slot of the 256-wide output
   int64_t weight_offset;      // byte offset into the transposed-weight blob
@@ -29,7 +30,7 @@ struct DgradLayer {           // mirrors srf_dgrad_layer in include/simple_rf_b2
 struct DgradProgram {
   int32_t num_layers, num_fwd_layers;
   int32_t top_width;          // 128 or 256
-  int32_t top_mask_layer;     // forward layer whose mask gates dZ_top
+  int32_t top_mask_slot;      // saved-activation slot of the top hidden layer (its non-zero pattern gates dZ_top)
   int32_t top_slot;           // dz slot of dZ_top (top_width / 64 images)
   int32_t head_slot;          // dz slots [head_slot, head_slot + 2): head-gradient images
   int32_t head_kind;          // 1: 3-row rgb head (d_o in image 0, d_sigma_raw in image 1 col 0); 2: 4-row head [sigma, r, g, b]
@@ -42,7 +43,8 @@ struct DgradProgram {
 struct DgradArgs {
   const uint8_t* weights_t;   // transposed-weight images
   const float* side;
-  const uint32_t* masks;      // [tile][num_fwd_layers][128][8]
+  const uint8_t* acts;        // saved activation tiles of the forward [tile][act_slots][16 KB]
+  int act_slots;
   const float* sigma; const float* rgb;       // forward outputs [M], [M,3]
   const float* g_sigma; const float* g_rgb;   // upstream gradients [M], [M,3] (nullable)
   uint8_t* dz;                // [tile][dz_slots][16 KB]
@@ -179,10 +181,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
         *reinterpret_cast<uint4*>(img + ptx::sw128_offset(row, 0)) = make_uint4(ptx::pack_bf16(d_o[0], d_o[1]), ptx::pack_bf16(d_o[2], d_o[3]), 0u, 0u);
         *reinterpret_cast<uint4*>(img + DG_KBLOCK + ptx::sw128_offset(row, 0)) = make_uint4(ptx::pack_bf16(dsig, 0.f), 0u, 0u, 0u);
       }
-      const uint32_t* mrow = args.masks + (((size_t)tile * prog.num_fwd_layers + prog.top_mask_layer) * 128 + row) * 8;
-      uint32_t mbits[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) mbits[q] = (q * 32 < tw) ? mrow[q] : 0u;
+      const uint8_t* mtile = args.acts + ((size_t)tile * args.act_slots + prog.top_mask_slot) * DG_KBLOCK;
       // H of the previous tile is still being read until its last layer's MMAs retire
       ptx::mbar_wait(&sm.h_free, (t & 1) ^ 1);
       sm.dsig[row] = dsig;
@@ -194,10 +193,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
           const int col = u * 8 + j;
           float a = 0.f;
           for (int c = 0; c < head_rows; ++c) a = fmaf(d_o[c], hw[c * tw + col], a);
-          v[j] = ((mbits[col >> 5] >> (col & 31)) & 1u) ? a : 0.f;
+          v[j] = a;
         }
-        const uint4 q = make_uint4(ptx::pack_bf16(v[0], v[1]), ptx::pack_bf16(v[2], v[3]), ptx::pack_bf16(v[4], v[5]), ptx::pack_bf16(v[6], v[7]));
         const uint32_t off = ptx::sw128_offset(row, u & 7);
+        const uint4 x = *reinterpret_cast<const uint4*>(mtile + (size_t)(u >> 3) * DG_KBLOCK + off);
+        const uint4 q = make_uint4(ptx::pack_bf16(v[0], v[1]) & __vcmpne2(x.x, 0u), ptx::pack_bf16(v[2], v[3]) & __vcmpne2(x.y, 0u),
+                                   ptx::pack_bf16(v[4], v[5]) & __vcmpne2(x.z, 0u), ptx::pack_bf16(v[6], v[7]) & __vcmpne2(x.w, 0u));
         *reinterpret_cast<uint4*>(sm.h[u >> 3] + off) = q;
         *reinterpret_cast<uint4*>(top + (size_t)(u >> 3) * DG_KBLOCK + off) = q;
       }
@@ -219,11 +220,16 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
         const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + grp * DG_COLS;
         const bool last = l == NL - 1;
         const float* wsig = L.rank1_offset >= 0 ? sm.side + L.rank1_offset : nullptr;
-        const uint32_t* mrow = L.mask_layer >= 0 ? args.masks + (((size_t)tile * prog.num_fwd_layers + L.mask_layer) * 128 + row) * 8 : nullptr;
+        const uint8_t* mtile = L.mask_slot >= 0 ? args.acts + ((size_t)tile * args.act_slots + L.mask_slot) * DG_KBLOCK : nullptr;
         uint8_t* out = args.dz + ((size_t)tile * args.dz_slots + L.dz_slot) * DG_KBLOCK;
-        uint32_t mw[4];
+        // the activation units this thread masks with: issued before the accumulator is ready (independent of the MMAs)
+        uint4 mx[4][4];
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) mw[kb] = mrow != nullptr ? mrow[kb * 2 + grp] : 0xffffffffu;
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            mx[kb][u] = mtile != nullptr ? __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)kb * DG_KBLOCK + ptx::sw128_offset(row, grp * 4 + u)))
+                                         : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
         d_phase ^= 1u << buf;
         ptx::tc_fence_after();
@@ -245,16 +251,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
               v[4 * q + 3] = __float_as_uint(fmaf(ds, w.w, __uint_as_float(v[4 * q + 3])));
             }
           }
-          const uint32_t bits = mw[kb];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = ((bits >> (2 * j)) & 1u) ? __uint_as_float(v[2 * j]) : 0.f;
-            const float b = ((bits >> (2 * j + 1)) & 1u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
-            pk[j] = ptx::pack_bf16(a, b);
-          }
+          for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint4 q = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            const uint4 x = mx[kb][u];
+            const uint4 q = make_uint4(pk[4 * u] & __vcmpne2(x.x, 0u), pk[4 * u + 1] & __vcmpne2(x.y, 0u),
+                                       pk[4 * u + 2] & __vcmpne2(x.z, 0u), pk[4 * u + 3] & __vcmpne2(x.w, 0u));
             const uint32_t off = ptx::sw128_offset(row, grp * 4 + u);
             *reinterpret_cast<uint4*>(out + (size_t)kb * DG_KBLOCK + off) = q;
             if (!last) *reinterpret_cast<uint4*>(sm.h[kb] + off) = q;
@@ -281,11 +284,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
 
 using namespace srf;
 
-SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const uint32_t* masks,
+SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const void* acts, int act_slots,
                                const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
                                void* dz, int dz_slots, void* stream) {
   if (num_rows == 0) return 0;
-  SRF_REQUIRE(program && weights_t && side && masks && sigma && rgb && dz, "srf_nerf_mlp_dgrad", "null pointer");
+  SRF_REQUIRE(program && weights_t && side && acts && sigma && rgb && dz, "srf_nerf_mlp_dgrad", "null pointer");
   DgradProgram prog = *reinterpret_cast<const DgradProgram*>(program);
   SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= DG_MAX_LAYERS, "srf_nerf_mlp_dgrad", "bad layer count");
   SRF_REQUIRE(prog.top_width == 128 || prog.top_width == 256, "srf_nerf_mlp_dgrad", "top width must be 128 or 256");
@@ -295,13 +298,15 @@ SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const
   for (int l = 0; l < prog.num_layers; ++l) {
     const DgradLayer& L = prog.layers[l];
     SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= 4 && (l == 0 || L.num_kblocks == 4), "srf_nerf_mlp_dgrad", "bad K-block count");
-    SRF_REQUIRE(L.dz_slot >= 0 && L.dz_slot + 4 <= dz_slots && L.mask_layer < prog.num_fwd_layers, "srf_nerf_mlp_dgrad", "bad slot / mask index");
+    SRF_REQUIRE(L.dz_slot >= 0 && L.dz_slot + 4 <= dz_slots && L.mask_slot + 4 <= act_slots, "srf_nerf_mlp_dgrad", "bad slot / mask index");
     SRF_REQUIRE(L.rank1_offset < 0 || (L.rank1_offset & 3) == 0, "srf_nerf_mlp_dgrad", "rank-1 offset must be a multiple of 4");
   }
+  SRF_REQUIRE(prog.top_mask_slot >= 0 && prog.top_mask_slot + prog.top_width / 64 <= act_slots, "srf_nerf_mlp_dgrad", "bad top mask slot");
   SRF_REQUIRE(prog.head_slot >= 0 && prog.head_slot + 2 <= dz_slots && prog.top_slot >= 0 && prog.top_slot + prog.top_width / 64 <= dz_slots,
               "srf_nerf_mlp_dgrad", "bad head / top slot");
   DgradArgs a{};
-  a.weights_t = reinterpret_cast<const uint8_t*>(weights_t); a.side = side; a.masks = masks; a.sigma = sigma; a.rgb = rgb;
+  a.weights_t = reinterpret_cast<const uint8_t*>(weights_t); a.side = side; a.acts = reinterpret_cast<const uint8_t*>(acts);
+  a.act_slots = act_slots; a.sigma = sigma; a.rgb = rgb;
   a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dz = reinterpret_cast<uint8_t*>(dz); a.dz_slots = dz_slots; a.total = num_rows;
   const size_t smem = sizeof(DgradSmem);
   static bool configured = false;

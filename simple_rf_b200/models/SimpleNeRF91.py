@@ -317,24 +317,24 @@ class MLP(torch.nn.Module):
 
 
 class _FusedMLP(torch.autograd.Function):
-    """Forward: the fused tcgen05 kernel, also saving activation tiles + ReLU masks.  Backward: the hand-written
+    """Forward: the fused tcgen05 kernel, also saving the activation tiles.  Backward: the hand-written
     dgrad chain (srf_nerf_mlp_dgrad) and weight-gradient GEMMs (srf_nerf_mlp_wgrad) on the tensor cores."""
 
     @staticmethod
     def forward(ctx, module, rays_o, rays_d, z, view_dirs, noise, *params):
         packed = module.packed()
-        sigma, rgb, acts, masks = packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise, save=True)
+        sigma, rgb, acts = packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise, save=True)
         ctx.packed = packed
         ctx.flat = packed.flat
         ctx.shapes = [p.shape for p in params]
-        ctx.save_for_backward(acts, masks, sigma, rgb)
+        ctx.save_for_backward(acts, sigma, rgb)
         return sigma, rgb
 
     @staticmethod
     def backward(ctx, g_sigma, g_rgb):
         from ..nerf_program import mlp_backward
-        acts, masks, sigma, rgb = ctx.saved_tensors
-        flat_grad, _ = mlp_backward(ctx.packed, ctx.flat, acts, masks, sigma, rgb, g_sigma, g_rgb)
+        acts, sigma, rgb = ctx.saved_tensors
+        flat_grad, _ = mlp_backward(ctx.packed, ctx.flat, acts, sigma, rgb, g_sigma, g_rgb)
         grads, o = [], 0
         for shp in ctx.shapes:
             n = 1

@@ -165,7 +165,7 @@ class PackedMLP:
     def forward(self, rays_o, rays_d, z, view_dirs=None, noise=None, save=False):
         """rays_o/rays_d [R,3] (the origin/direction the sample points are built from), z [R,S].
         Returns sigma [R,S,1], rgb [R,S,3] (post-activation, as MLP.forward returns them); with save=True also
-        (acts uint8 [tiles, act_slots, 16384], masks int32 [tiles, layers, 128, 8]) for the backward kernels."""
+        acts uint8 [tiles, act_slots, 16384] (the saved activation tile images) for the backward kernels."""
         assert self.blob is not None, 'call refresh(params) first'
         L.require_cuda(rays_o, rays_d, z, view_dirs, noise)
         rays_o, rays_d, z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
@@ -175,18 +175,17 @@ class PackedMLP:
         rgb = torch.empty((R, S, 3), dtype=torch.float32, device=z.device)
         if self.use_views and view_dirs is None:
             raise L.SimpleRFNativeError('this MLP variant needs view_dirs')
-        acts = masks = None
+        acts = None
         prog = self.program
         if save:
             tiles = (R * S + 127) // 128
             acts = torch.empty((tiles, prog.act_slots, 16384), dtype=torch.uint8, device=z.device)
-            masks = torch.empty((tiles, prog.num_layers, 128, 8), dtype=torch.int32, device=z.device)
         L.call('srf_nerf_mlp_fwd', ctypes.addressof(prog), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
                L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
-               L.ptr(sigma), L.ptr(rgb), L.ptr(acts), L.ptr(masks), prog.act_slots if save else 0, 0, max(prog.v_slot, 0),
+               L.ptr(sigma), L.ptr(rgb), L.ptr(acts), prog.act_slots if save else 0, 0, max(prog.v_slot, 0),
                L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)
         if save:
-            return sigma, rgb, acts, masks
+            return sigma, rgb, acts
         return sigma, rgb
 
 
@@ -300,13 +299,13 @@ def run_wgrad(items, acts, dz, grads):
 
 
 class DgradLayer(ctypes.Structure):
-    _fields_ = [('num_kblocks', ctypes.c_int32), ('mask_layer', ctypes.c_int32), ('rank1_offset', ctypes.c_int32),
+    _fields_ = [('num_kblocks', ctypes.c_int32), ('mask_slot', ctypes.c_int32), ('rank1_offset', ctypes.c_int32),
                 ('dz_slot', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
 
 
 class DgradProgram(ctypes.Structure):
     _fields_ = [('num_layers', ctypes.c_int32), ('num_fwd_layers', ctypes.c_int32), ('top_width', ctypes.c_int32),
-                ('top_mask_layer', ctypes.c_int32), ('top_slot', ctypes.c_int32), ('head_slot', ctypes.c_int32),
+                ('top_mask_slot', ctypes.c_int32), ('top_slot', ctypes.c_int32), ('head_slot', ctypes.c_int32),
                 ('head_kind', ctypes.c_int32), ('head_w_offset', ctypes.c_int32), ('side_count', ctypes.c_int32),
                 ('pad_', ctypes.c_int32), ('layers', DgradLayer * MAX_LAYERS)]
 
@@ -326,7 +325,7 @@ def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
     prog.head_slot = 0
     prog.top_slot = 2
     prog.top_width = n_t
-    prog.top_mask_layer = top
+    prog.top_mask_slot = fwd_prog.layers[top].save_slot
     assert relu_t and head_t in (2, 3)
     prog.head_kind = 1 if head_t == 3 else 2
     hname = 'views_output_linear' if head_t == 3 else 'pts_output_linear'
@@ -351,7 +350,7 @@ def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
         Lr = prog.layers[bl]
         Lr.num_kblocks = n // 64
         below = layers[f - 1]
-        Lr.mask_layer = f - 1 if below[3] else -1
+        Lr.mask_slot = fwd_prog.layers[f - 1].save_slot if below[3] else -1
         Lr.rank1_offset = -1
         if sigma_layer is not None and sigma_layer == f - 1:
             side += [zero] * (-len(side) % 4)
@@ -406,7 +405,7 @@ def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
     return plan
 
 
-def mlp_backward(packed, params_flat, acts, masks, sigma, rgb, g_sigma, g_rgb):
+def mlp_backward(packed, params_flat, acts, sigma, rgb, g_sigma, g_rgb):
     """Hand-written backward of one fused-MLP evaluation: dgrad chain then weight gradients.
     params_flat: the flat fp32 parameter vector (+ trailing zero) used for the forward's refresh.
     Returns the flat fp32 gradient (same layout as the parameters)."""
@@ -423,7 +422,7 @@ def mlp_backward(packed, params_flat, acts, masks, sigma, rgb, g_sigma, g_rgb):
     dz = torch.empty((tiles, plan.dz_slots, 16384), dtype=torch.uint8, device=dev)
     gs = None if g_sigma is None else L.f32c(g_sigma).reshape(-1)
     gc = None if g_rgb is None else L.f32c(g_rgb).reshape(-1, 3)
-    L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(masks), L.ptr(sigma), L.ptr(rgb),
+    L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), acts.shape[1], L.ptr(sigma), L.ptr(rgb),
            L.ptr(gs), L.ptr(gc), rows, L.ptr(dz), plan.dz_slots, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
     grads = torch.zeros(packed.flat_size, dtype=torch.float32, device=dev)
     run_wgrad(plan.items, acts, dz, grads)

@@ -47,11 +47,11 @@ def _hidden(params, cfg, pts, vdirs):
 
 
 @pytest.mark.parametrize('variant', ['main', 'views_augmentation'])
-def test_forward_saves_activation_tiles_and_masks(golden_configs, variant):
+def test_forward_saves_activation_tiles(golden_configs, variant):
     from simple_rf_b200 import tile_images as TI
     R, S = 50, 64                                     # 3200 rows = 25 tiles
     cfg, params, packed, o, d, vd, z = _setup(golden_configs, variant, R, S)
-    sigma, rgb, acts, masks = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV), save=True)
+    sigma, rgb, acts = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV), save=True)
     s2, c2 = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV))
     assert torch.equal(sigma, s2) and torch.equal(rgb, c2)
     pts = (o[:, None] + d[:, None] * z[..., None]).reshape(-1, 3)
@@ -66,9 +66,7 @@ def test_forward_saves_activation_tiles_and_masks(golden_configs, variant):
         h = TI.decode(acts, prog.layers[l].save_slot, 4)[:n].cpu()
         tol = 2e-2 * max(1.0, ref['h'][l].abs().max().item())
         assert (h - ref['h'][l]).abs().max().item() <= tol, l
-        bits = masks[:, l].reshape(-1, 8)[:n].cpu()
-        got = torch.stack([(bits[:, w] >> b) & 1 for w in range(8) for b in range(32)], 1).bool()
-        assert torch.equal(got, TI.decode(acts, prog.layers[l].save_slot, 4)[:n].cpu() > 0), l
+        assert torch.equal(h > 0, ref['h'][l] > 0) or ((h > 0) != (ref['h'][l] > 0)).float().mean() < 1e-3, l   # ReLU pattern
     if cfg['view_dependent_rgb']:
         feat = TI.decode(acts, prog.layers[8].save_slot, 4)[:n].cpu()
         assert (feat - ref['feat']).abs().max().item() <= 2e-2 * max(1.0, ref['feat'].abs().max().item())
@@ -179,8 +177,8 @@ def test_mlp_backward_vs_autograd(golden_configs, variant, R, S):
     sb, cb = _bf16_model_forward(leaves_b, cfg, pts, vflat)
     ((sb * g_sigma.reshape(-1, 1)).sum() + (cb * g_rgb.reshape(-1, 3)).sum()).backward()
 
-    sigma, rgb, acts, masks = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV), save=True)
-    flat_grad, dz = NP.mlp_backward(packed, packed.flat, acts, masks, sigma, rgb, g_sigma.to(DEV), g_rgb.to(DEV))
+    sigma, rgb, acts = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV), save=True)
+    flat_grad, dz = NP.mlp_backward(packed, packed.flat, acts, sigma, rgb, g_sigma.to(DEV), g_rgb.to(DEV))
     torch.cuda.synchronize()
     err_model, err_fp32 = {}, {}
     off = 0
