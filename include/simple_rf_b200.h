@@ -162,19 +162,20 @@ int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const float* z,
                        int softplus, float density_offset, const float* g_sigma, const float* features,
                        float* const* g_planes, float* const* g_lines, void* stream);
 
-/* VM appearance features (SimpleTensoRF09.py:1241-1263): (plane x line) products over sum(C) <= 96 channels ->
- * basis_matrix_color [F, sum(C)] -> rows [max_count, 32] = [F features | 3 view_dirs | zero pad], the input of the
- * colour MLP (:1411-1421 with identity encodings). */
+/* VM appearance features (SimpleTensoRF09.py:1241-1263): (plane x line) products over sum(C) <= 96 channels written as
+ * bf16 rows [max_count, 128] = [products | 3 view_dirs | zero pad] — the two 64-column A-operand blocks of the colour
+ * MLP.  basis_matrix_color (:1151, :1263) is linear and is folded into the MLP's first layer by the host
+ * (W0' = [W0[:, :F] B | W0[:, F:]]), so this kernel is a pure gather.  The backward scatters g_rows[:, :sum(C)]
+ * (fp32, row pitch g_row_pitch floats) into zero-initialised channels-last plane / line gradients. */
 int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
                               const float* const* planes, const float* const* lines, const int* channels,
-                              const int* resolution, const float* basis, int num_features, const float* view_dirs,
-                              float* rows, void* stream);
+                              const int* resolution, const float* view_dirs, void* rows, void* stream);
 int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
                               const float* const* planes, const float* const* lines, const int* channels,
-                              const int* resolution, const float* basis, int num_features, const float* g_rows,
-                              float* g_basis, float* const* g_planes, float* const* g_lines, void* stream);
+                              const int* resolution, const float* g_rows, int g_row_pitch, float* const* g_planes,
+                              float* const* g_lines, void* stream);
 
 /* dst[indices[j], :] = src[j, :] (the scatter-back of :1238 / :1271) and its transpose. */
 int srf_scatter_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
@@ -182,9 +183,10 @@ int srf_scatter_rows(const int* indices, const int* count, int64_t max_count, co
 int srf_gather_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
                     void* stream);
 
-/* Colour MLP on the tensor cores: same kernel and program format as srf_nerf_mlp_fwd, but region 0 is filled from
- * precomputed rows [max_rows, 32] (fp32) instead of a positional encoding; the row count is read from the device. */
-int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const float* rows, const int* count,
+/* Colour MLP on the tensor cores: same kernel and program format as srf_nerf_mlp_fwd, but regions 0 and 5 are filled from
+ * precomputed bf16 rows [max_rows, 128] (columns 0..63 / 64..127) instead of encodings (views_degree = -2 in the
+ * program; -1 when only region 0 is used); the row count is read from the device. */
+int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, const int* count,
                      int64_t max_rows, float* rgb, void* stream);
 
 /* Weight gradients of the fused MLP (what autograd derives for the nn.Linear layers of

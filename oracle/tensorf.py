@@ -69,15 +69,19 @@ def vm_density(params, pts_norm, mask, density_predictor='ReLU', density_offset=
     return sigma
 
 
-def vm_color_features(params, p):
-    """SimpleTensoRF09.py:1252-1263: (plane*line)^T [N, sum(C)] -> basis matrix -> [N, 27]."""
+def vm_color_products(params, p):
+    """SimpleTensoRF09.py:1252-1262: (plane*line)^T [N, sum(C)], the input of basis_matrix_color."""
     cp, cl = _plane_line_coords(p)
     pcs, lcs = [], []
     for i in range(3):
         pcs.append(F.grid_sample(params[f'matrices_color.{i}'], cp[[i]], align_corners=True).view(-1, p.shape[0]))
         lcs.append(F.grid_sample(params[f'vectors_color.{i}'], cl[[i]], align_corners=True).view(-1, p.shape[0]))
-    prod = (torch.cat(pcs) * torch.cat(lcs)).T
-    return F.linear(prod, params['basis_matrix_color.weight'])
+    return (torch.cat(pcs) * torch.cat(lcs)).T
+
+
+def vm_color_features(params, p):
+    """SimpleTensoRF09.py:1252-1263: products -> basis matrix -> [N, 27]."""
+    return F.linear(vm_color_products(params, p), params['basis_matrix_color.weight'])
 
 
 def color_mlp(params, features, view_dirs):

@@ -53,7 +53,7 @@ struct MlpArgs {
   const float* z;               // [R,S]
   const float* view_dirs;       // [R,3] or nullptr
   const float* noise;           // [R*S] or nullptr: added to raw sigma before the ReLU
-  const float* rows;            // rows mode: [total, 32] fp32 inputs copied into region 0 instead of an encoding
+  const uint4* rows;            // rows mode: [total, 128] bf16 inputs: columns 0..63 fill region 0, 64..127 region 5
   const int* count;             // rows mode: device-side row count (<= total), or nullptr
   float* sigma;                 // [R*S]
   float* rgb;                   // [R*S,3]
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
   const int num_tiles = (int)((total + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const bool has_views = prog.views_degree >= 0;
+  const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer
@@ -272,11 +272,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       const long long m = tile * 128 + row;
       const bool valid = m < total;
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
-      float4 x[8];
+      uint4 x[16];
       if (args.rows != nullptr) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          x[q] = valid ? __ldg(reinterpret_cast<const float4*>(args.rows + m * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 16; ++q)
+          x[q] = (valid && (q < 8 || has_views)) ? __ldg(args.rows + m * 16 + q) : make_uint4(0u, 0u, 0u, 0u);
       } else if (valid) {
         const long long r = m / args.S;
         const float zz = args.z[m];
@@ -293,10 +293,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       uint8_t* E = sm.a[0];
       if (args.rows != nullptr) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(E + ptx::sw128_offset(row, u)) =
-              make_uint4(ptx::pack_bf16(x[2 * u].x, x[2 * u].y), ptx::pack_bf16(x[2 * u].z, x[2 * u].w),
-                         ptx::pack_bf16(x[2 * u + 1].x, x[2 * u + 1].y), ptx::pack_bf16(x[2 * u + 1].z, x[2 * u + 1].w));
+        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(E + ptx::sw128_offset(row, u)) = x[u];
       } else {
         const int deg = prog.points_degree;
 #pragma unroll
@@ -326,16 +323,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         ptx::mbar_wait(&sm.v_free, (t & 1) ^ 1);
         uint8_t* V = sm.a[5];
         const int vdeg = prog.views_degree;
+        if (args.rows != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          store_bf16(V, row, c, vd[c]);
-          if (vdeg > 0)
-            encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
-              store_bf16(V, row, 3 + 6 * k + c, s);
-              store_bf16(V, row, 6 + 6 * k + c, co);
-            });
+          for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(V + ptx::sw128_offset(row, u)) = x[8 + u];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            store_bf16(V, row, c, vd[c]);
+            if (vdeg > 0)
+              encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
+                store_bf16(V, row, 3 + 6 * k + c, s);
+                store_bf16(V, row, 6 + 6 * k + c, co);
+              });
+          }
+          for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16(V, row, c, 0.f);
         }
-        for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16(V, row, c, 0.f);
         if (args.save_acts != nullptr) {
           uint8_t* dst = args.save_acts + ((size_t)tile * args.act_slots + args.v_slot) * KBLOCK_BYTES;
 #pragma unroll
@@ -524,9 +526,9 @@ int validate_program(const MlpProgram& prog, const char* where, bool rows_mode) 
     }
     SRF_REQUIRE(!(L.write_h && l == prog.num_layers - 1), where, "last layer cannot write H");
   }
-  SRF_REQUIRE(rows_mode ? prog.views_degree < 0 : true, where, "rows mode has no view encoding");
-  SRF_REQUIRE((prog.views_degree >= 0) == (((used_any >> 5) & 1) != 0), where,
-              "view encoding (region 5) must be used iff views_degree >= 0");
+  SRF_REQUIRE(rows_mode ? prog.views_degree < 0 : true, where, "rows mode has no view encoding (views_degree -1: one block, -2: two blocks)");
+  SRF_REQUIRE((prog.views_degree >= 0 || (rows_mode && prog.views_degree == -2)) == (((used_any >> 5) & 1) != 0), where,
+              "region 5 must be used iff views_degree >= 0 (or -2 in rows mode)");
   return 0;
 }
 
@@ -567,7 +569,7 @@ SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const flo
   return launch_mlp(prog, a, a.total, stream, "srf_nerf_mlp_fwd");
 }
 
-SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const float* rows, const int* count,
+SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, const int* count,
                              int64_t max_rows, float* rgb, void* stream) {
   if (max_rows == 0) return 0;
   SRF_REQUIRE(program && weights && side && rows && rgb, "srf_mlp_rows_fwd", "null pointer");
@@ -577,7 +579,7 @@ SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const flo
     SRF_REQUIRE(prog.layers[l].head == 0 || prog.layers[l].head == 3, "srf_mlp_rows_fwd", "only the rgb head is supported in rows mode");
   MlpArgs a{};
   a.weights = reinterpret_cast<const uint8_t*>(weights);
-  a.side = side; a.rows = rows; a.count = count; a.rgb = rgb;
+  a.side = side; a.rows = reinterpret_cast<const uint4*>(rows); a.count = count; a.rgb = rgb;
   a.total = max_rows;
   a.S = 1;
   return launch_mlp(prog, a, max_rows, stream, "srf_mlp_rows_fwd");

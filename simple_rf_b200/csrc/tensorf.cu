@@ -12,6 +12,8 @@
 // a few 16-byte vectors; the fp32 `nn.Parameter`s keep the reference's [1,C,H,W] layout.  The occupancy volume
 // is 1 bit per voxel (x fastest), i.e. L2/shared-memory sized, and the test reproduces ATen's grid_sampler_3d
 // coordinate arithmetic exactly, so mask and compaction order are bit-identical to the reference.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace srf {
@@ -348,134 +350,145 @@ __global__ void __launch_bounds__(256) vm_density_bwd_kernel(VmGeom g, VmGrid t,
   }
 }
 
-// appearance: products (plane x line) over all channels -> basis matrix [F,CT] (F <= 32 outputs) -> rows of
-// [features | view_dirs | zero pad] (row width 32) that the tensor-core colour MLP consumes.
-// One warp per sample: lane l owns product channels l, l+32, l+64 (CT <= 96) and output feature l.
-constexpr int COLOR_ROW = 32;
+// appearance: products (plane x line) over all channels -> rows of [products (CT <= 96) | view_dirs (3) | zero pad],
+// 128 bf16 per row, the two 64-column A-operand blocks of the tensor-core colour MLP (whose first layer absorbs
+// basis_matrix_color: W0' = [W0[:, :F] B | W0[:, F:]], so no matrix-vector product is left in this kernel).
+// A warp takes 32 samples: lane-per-sample coordinate / weight arithmetic into shared memory, then lane-per-channel
+// gathers (channels-last texels: consecutive lanes read consecutive floats) for one sample at a time.
+constexpr int COLOR_ROW = 128;          // bf16 elements per row
+constexpr int CF_WARPS = 8;
 
-__device__ __forceinline__ float color_product(const VmGrid& t, const float (&pn)[3], int ch, int& plane_i, int& local_c) {
+struct SampleCoords {                   // per sample: 3 planes (x0, y0, 4 corner weights) + 3 lines (l0, 2 weights)
+  int px0[3], py0[3];
+  float pw[3][4];
+  int l0[3];
+  float lw[3][2];
+  int ray;
+};
+
+__device__ __forceinline__ void compute_coords(const VmGeom& g, const VmGrid& t, int flat, SampleCoords& c) {
+  float pn[3];
+  normalized_point(g, flat, pn);
+  c.ray = flat / g.S;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const Bilerp b = plane_coords(pn, t.res, i);
+    c.px0[i] = b.x0; c.py0[i] = b.y0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
+      const bool in = x >= 0 && y >= 0 && x < b.W && y < b.H;
+      c.pw[i][k] = in ? ((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0) : 0.f;   // zero weight = zero padding
+    }
+    int l0, L; float w0, w1;
+    line_coords(pn, t.res, i, l0, L, w0, w1);
+    c.l0[i] = l0;
+    c.lw[i][0] = (l0 >= 0 && l0 < L) ? w0 : 0.f;
+    c.lw[i][1] = (l0 + 1 >= 0 && l0 + 1 < L) ? w1 : 0.f;
+  }
+}
+
+// clamped texel address helpers: out-of-range corners carry zero weight, so any in-range address may be read
+__device__ __forceinline__ int clampi(int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); }
+
+struct ChannelSlot { int plane, c, C, W, H, L; };
+
+__device__ __forceinline__ ChannelSlot channel_slot(const VmGrid& t, int ch, int CT) {
+  ChannelSlot s{0, 0, 0, 0, 0, 0};
+  if (ch >= CT) { s.plane = -1; return s; }
   int i = 0, c = ch;
   while (i < 2 && c >= t.C[i]) { c -= t.C[i]; ++i; }
-  plane_i = i; local_c = c;
-  const Bilerp b = plane_coords(pn, t.res, i);
-  int l0, L; float w0, w1;
-  line_coords(pn, t.res, i, l0, L, w0, w1);
-  float pv = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
-    if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
-    pv += __ldg(t.plane[i] + ((size_t)y * b.W + x) * t.C[i] + c) * (((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0));
-  }
-  float lv = 0.f;
-  if (l0 >= 0 && l0 < L) lv += __ldg(t.line[i] + (size_t)l0 * t.C[i] + c) * w0;
-  if (l0 + 1 >= 0 && l0 + 1 < L) lv += __ldg(t.line[i] + (size_t)(l0 + 1) * t.C[i] + c) * w1;
-  return pv * lv;
+  s.plane = i; s.c = c; s.C = t.C[i];
+  s.W = t.res[c_a0[i]]; s.H = t.res[c_a1[i]]; s.L = t.res[c_av[i]];
+  return s;
 }
 
-__global__ void __launch_bounds__(256) vm_color_features_fwd_kernel(VmGeom g, VmGrid t, const float* __restrict__ basis, int F, int CT,
-                                                                    const float* __restrict__ view_dirs, float* __restrict__ rows) {
-  extern __shared__ float s_basis[];                 // transposed [CT][32]: lane f reads s_basis[ch*32 + f], conflict-free
-  for (int i = threadIdx.x; i < CT * 32; i += blockDim.x) {
-    const int ch = i >> 5, f = i & 31;
-    s_basis[i] = f < F ? basis[f * CT + ch] : 0.f;
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_fwd_kernel(VmGeom g, VmGrid t, int CT, const float* __restrict__ view_dirs,
+                                                                              __nv_bfloat16* __restrict__ rows) {
+  __shared__ SampleCoords s_c[CF_WARPS][32];
+  __shared__ __align__(16) __nv_bfloat16 s_row[CF_WARPS][COLOR_ROW];
   const int n = g.count[0];
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
-    const int flat = g.idx[j];
-    float pn[3];
-    normalized_point(g, flat, pn);
-    float prod[3] = {0.f, 0.f, 0.f};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CF_WARPS + warp, nw = gridDim.x * CF_WARPS;
+  ChannelSlot slot[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int ch = lane + 32 * k;
-      int pi, lc;
-      if (ch < CT) prod[k] = color_product(t, pn, ch, pi, lc);
-    }
-    float out = 0.f;
+  for (int k = 0; k < 3; ++k) slot[k] = channel_slot(t, lane + 32 * k, CT);
+  for (int base = gw * 32; base < n; base += nw * 32) {
+    const int cnt = min(32, n - base);
+    if (lane < cnt) compute_coords(g, t, g.idx[base + lane], s_c[warp][lane]);
+    __syncwarp();
+    for (int sidx = 0; sidx < cnt; ++sidx) {
+      const SampleCoords& c = s_c[warp][sidx];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int lim = min(32, CT - 32 * k);
-      for (int c = 0; c < lim; ++c) out = fmaf(__shfl_sync(FULL, prod[k], c), s_basis[(32 * k + c) * 32 + lane], out);
+      for (int k = 0; k < 3; ++k) {
+        float prod = 0.f;
+        const ChannelSlot& sl = slot[k];
+        if (sl.plane >= 0) {
+          const int i = sl.plane;
+          const float* pl = t.plane[i];
+          const int x0 = c.px0[i], y0 = c.py0[i];
+          const int xa = clampi(x0, sl.W), xb = clampi(x0 + 1, sl.W), ya = clampi(y0, sl.H), yb = clampi(y0 + 1, sl.H);
+          const float pv = __ldg(pl + ((size_t)ya * sl.W + xa) * sl.C + sl.c) * c.pw[i][0] + __ldg(pl + ((size_t)ya * sl.W + xb) * sl.C + sl.c) * c.pw[i][1] +
+                           __ldg(pl + ((size_t)yb * sl.W + xa) * sl.C + sl.c) * c.pw[i][2] + __ldg(pl + ((size_t)yb * sl.W + xb) * sl.C + sl.c) * c.pw[i][3];
+          const int la = clampi(c.l0[i], sl.L), lb = clampi(c.l0[i] + 1, sl.L);
+          const float lv = __ldg(t.line[i] + (size_t)la * sl.C + sl.c) * c.lw[i][0] + __ldg(t.line[i] + (size_t)lb * sl.C + sl.c) * c.lw[i][1];
+          prod = pv * lv;
+        }
+        s_row[warp][lane + 32 * k] = __float2bfloat16_rn(prod);
+      }
+      s_row[warp][96 + lane] = __float2bfloat16_rn(0.f);
+      __syncwarp();
+      if (lane < 3) s_row[warp][CT + lane] = __float2bfloat16_rn(view_dirs[c.ray * 3 + lane]);
+      __syncwarp();
+      // 256-byte row, 8 bytes per lane
+      reinterpret_cast<uint2*>(rows + (size_t)(base + sidx) * COLOR_ROW)[lane] = reinterpret_cast<const uint2*>(s_row[warp])[lane];
+      __syncwarp();
     }
-    const int r = flat / g.S;
-    float val = 0.f;
-    if (lane < F) val = out;
-    else if (lane < F + 3) val = view_dirs[r * 3 + (lane - F)];
-    rows[(size_t)j * COLOR_ROW + lane] = val;
   }
 }
 
-// backward of the above: g_rows[:, :F] -> g_basis (block-reduced, then atomics) and scatter into planes / lines
-__global__ void __launch_bounds__(256) vm_color_features_bwd_kernel(VmGeom g, VmGrid t, const float* __restrict__ basis, int F, int CT,
-                                                                    const float* __restrict__ g_rows, float* __restrict__ g_basis,
-                                                                    float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
-  extern __shared__ float s_mem[];                   // basis [F][CT] | g_basis accumulator [F][CT] (lane = channel: stride-1)
-  float* s_basis = s_mem;
-  float* s_gb = s_mem + F * CT;
-  for (int i = threadIdx.x; i < F * CT; i += blockDim.x) { s_basis[i] = basis[i]; s_gb[i] = 0.f; }
-  __syncthreads();
+// backward: g_rows[:, :CT] (fp32, row pitch `pitch`) scattered into the channels-last plane / line gradients
+__global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_bwd_kernel(VmGeom g, VmGrid t, int CT, const float* __restrict__ g_rows, int pitch,
+                                                                              float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
+  __shared__ SampleCoords s_c[CF_WARPS][32];
   float* gplane[3] = {gp0, gp1, gp2};
   float* gline[3] = {gl0, gl1, gl2};
   const int n = g.count[0];
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
-    const int flat = g.idx[j];
-    float pn[3];
-    normalized_point(g, flat, pn);
-    const float gout = lane < F ? g_rows[(size_t)j * COLOR_ROW + lane] : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CF_WARPS + warp, nw = gridDim.x * CF_WARPS;
+  ChannelSlot slot[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int ch = lane + 32 * k;
-      const bool live = ch < CT;
-      // recompute the product's two factors for this channel
-      int i = 0, c = live ? ch : 0;
-      while (i < 2 && c >= t.C[i]) { c -= t.C[i]; ++i; }
-      const Bilerp b = plane_coords(pn, t.res, i);
-      int l0, L; float w0, w1;
-      line_coords(pn, t.res, i, l0, L, w0, w1);
-      float pv = 0.f, lv = 0.f;
-      if (live) {
+  for (int k = 0; k < 3; ++k) slot[k] = channel_slot(t, lane + 32 * k, CT);
+  for (int base = gw * 32; base < n; base += nw * 32) {
+    const int cnt = min(32, n - base);
+    if (lane < cnt) compute_coords(g, t, g.idx[base + lane], s_c[warp][lane]);
+    __syncwarp();
+    for (int sidx = 0; sidx < cnt; ++sidx) {
+      const SampleCoords& c = s_c[warp][sidx];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int x = b.x0 + (q & 1), y = b.y0 + (q >> 1);
-          if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
-          pv += __ldg(t.plane[i] + ((size_t)y * b.W + x) * t.C[i] + c) * (((q & 1) ? b.wx1 : b.wx0) * ((q >> 1) ? b.wy1 : b.wy0));
-        }
-        if (l0 >= 0 && l0 < L) lv += __ldg(t.line[i] + (size_t)l0 * t.C[i] + c) * w0;
-        if (l0 + 1 >= 0 && l0 + 1 < L) lv += __ldg(t.line[i] + (size_t)(l0 + 1) * t.C[i] + c) * w1;
-      }
-      const float prod = pv * lv;
-      // g_prod[ch] = sum_f g_out[f] * basis[f][ch];  g_basis[f][ch] += g_out[f] * prod[ch]
-      float gprod = 0.f;
-      for (int f = 0; f < F; ++f) {
-        const float gf = __shfl_sync(FULL, gout, f);
-        if (live) {
-          gprod = fmaf(gf, s_basis[f * CT + ch], gprod);
-          atomicAdd(&s_gb[f * CT + ch], gf * prod);
-        }
-      }
-      if (live && gprod != 0.f) {
+      for (int k = 0; k < 3; ++k) {
+        const ChannelSlot& sl = slot[k];
+        if (sl.plane < 0) continue;
+        const float gprod = g_rows[(size_t)(base + sidx) * pitch + lane + 32 * k];
+        if (gprod == 0.f) continue;
+        const int i = sl.plane;
+        const float* pl = t.plane[i];
+        const int x0 = c.px0[i], y0 = c.py0[i];
+        const int xs[2] = {clampi(x0, sl.W), clampi(x0 + 1, sl.W)}, ys[2] = {clampi(y0, sl.H), clampi(y0 + 1, sl.H)};
+        const int la = clampi(c.l0[i], sl.L), lb = clampi(c.l0[i] + 1, sl.L);
+        float pv = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pv += __ldg(pl + ((size_t)ys[q >> 1] * sl.W + xs[q & 1]) * sl.C + sl.c) * c.pw[i][q];
+        const float lv = __ldg(t.line[i] + (size_t)la * sl.C + sl.c) * c.lw[i][0] + __ldg(t.line[i] + (size_t)lb * sl.C + sl.c) * c.lw[i][1];
         const float gpv = gprod * lv, glv = gprod * pv;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int x = b.x0 + (q & 1), y = b.y0 + (q >> 1);
-          if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
-          atomicAdd(gplane[i] + ((size_t)y * b.W + x) * t.C[i] + c, gpv * (((q & 1) ? b.wx1 : b.wx0) * ((q >> 1) ? b.wy1 : b.wy0)));
-        }
-        if (l0 >= 0 && l0 < L) atomicAdd(gline[i] + (size_t)l0 * t.C[i] + c, glv * w0);
-        if (l0 + 1 >= 0 && l0 + 1 < L) atomicAdd(gline[i] + (size_t)(l0 + 1) * t.C[i] + c, glv * w1);
+        for (int q = 0; q < 4; ++q)
+          if (c.pw[i][q] != 0.f) atomicAdd(gplane[i] + ((size_t)ys[q >> 1] * sl.W + xs[q & 1]) * sl.C + sl.c, gpv * c.pw[i][q]);
+        if (c.lw[i][0] != 0.f) atomicAdd(gline[i] + (size_t)la * sl.C + sl.c, glv * c.lw[i][0]);
+        if (c.lw[i][1] != 0.f) atomicAdd(gline[i] + (size_t)lb * sl.C + sl.c, glv * c.lw[i][1]);
       }
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < F * CT; i += blockDim.x) {
-    const float v = s_gb[i];
-    if (v != 0.f) atomicAdd(g_basis + i, v);
+    __syncwarp();
   }
 }
 
@@ -607,36 +620,33 @@ SRF_API int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const f
 SRF_API int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                                       const int* count, int64_t max_count, const float* box_min, const float* box_size,
                                       const float* const* planes, const float* const* lines, const int* channels,
-                                      const int* resolution, const float* basis, int num_features, const float* view_dirs,
-                                      float* rows, void* stream) {
+                                      const int* resolution, const float* view_dirs, void* rows, void* stream) {
   if (max_count == 0) return 0;
-  SRF_REQUIRE(rays_o && rays_d && z && indices && count && basis && view_dirs && rows, "srf_vm_color_features_fwd", "null pointer");
+  SRF_REQUIRE(rays_o && rays_d && z && indices && count && view_dirs && rows, "srf_vm_color_features_fwd", "null pointer");
   VmGeom g; VmGrid t;
   fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_fwd")) return 1;
   const int CT = channels[0] + channels[1] + channels[2];
-  SRF_REQUIRE(CT <= 96 && num_features + 3 <= COLOR_ROW, "srf_vm_color_features_fwd", "need sum(C) <= 96 and features + 3 <= 32");
-  const size_t smem = (size_t)32 * CT * sizeof(float);
-  vm_color_features_fwd_kernel<<<blocks_for(max_count, 8), 256, smem, (cudaStream_t)stream>>>(g, t, basis, num_features, CT, view_dirs, rows);
+  SRF_REQUIRE(CT + 3 <= COLOR_ROW && CT <= 96, "srf_vm_color_features_fwd", "need sum(C) <= 96");
+  vm_color_features_fwd_kernel<<<blocks_for(max_count, CF_WARPS * 32, 16), CF_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      g, t, CT, view_dirs, reinterpret_cast<__nv_bfloat16*>(rows));
   return check_launch("srf_vm_color_features_fwd");
 }
 
 SRF_API int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                                       const int* count, int64_t max_count, const float* box_min, const float* box_size,
                                       const float* const* planes, const float* const* lines, const int* channels,
-                                      const int* resolution, const float* basis, int num_features, const float* g_rows,
-                                      float* g_basis, float* const* g_planes, float* const* g_lines, void* stream) {
+                                      const int* resolution, const float* g_rows, int g_row_pitch, float* const* g_planes,
+                                      float* const* g_lines, void* stream) {
   if (max_count == 0) return 0;
-  SRF_REQUIRE(rays_o && rays_d && z && indices && count && basis && g_rows && g_basis && g_planes && g_lines,
-              "srf_vm_color_features_bwd", "null pointer");
+  SRF_REQUIRE(rays_o && rays_d && z && indices && count && g_rows && g_planes && g_lines, "srf_vm_color_features_bwd", "null pointer");
   VmGeom g; VmGrid t;
   fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_bwd")) return 1;
   const int CT = channels[0] + channels[1] + channels[2];
-  SRF_REQUIRE(CT <= 96 && num_features + 3 <= COLOR_ROW, "srf_vm_color_features_bwd", "need sum(C) <= 96 and features + 3 <= 32");
-  const size_t smem = 2 * (size_t)num_features * CT * sizeof(float);
-  vm_color_features_bwd_kernel<<<blocks_for(max_count, 8, 8), 256, smem, (cudaStream_t)stream>>>(
-      g, t, basis, num_features, CT, g_rows, g_basis, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  SRF_REQUIRE(CT <= 96 && g_row_pitch >= CT, "srf_vm_color_features_bwd", "need sum(C) <= 96 and pitch >= sum(C)");
+  vm_color_features_bwd_kernel<<<blocks_for(max_count, CF_WARPS * 32, 16), CF_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      g, t, CT, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
   return check_launch("srf_vm_color_features_bwd");
 }
 

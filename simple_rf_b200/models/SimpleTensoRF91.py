@@ -241,45 +241,56 @@ class MlpFeaturesColorPredictor(torch.nn.Module):
         self.mlp = torch.nn.Sequential(Lin(self.input_dim, num_units), torch.nn.ReLU(inplace=True), Lin(num_units, num_units),
                                        torch.nn.ReLU(inplace=True), Lin(num_units, 3), torch.nn.Sigmoid())
         torch.nn.init.constant_(self.mlp[-2].bias, 0)
-        self._packed = PackedRowsMLP(self.input_dim, prefix='mlp', units=num_units)
+        self._packed = PackedRowsMLP(sum(tensor_configs['num_components_color']), features_dim,
+                                     3 if tensor_configs['use_view_dirs'] else 0, prefix='mlp', units=num_units)
         self._version = None
 
-    def packed(self):
+    def packed(self, basis):
+        """basis: basis_matrix_color.weight [F, sum(C)] (:1151), folded into the first tensor-core layer."""
         params = dict(self.named_parameters())
-        version = tuple((p.data_ptr(), p._version) for p in params.values())
+        version = tuple((p.data_ptr(), p._version) for p in [*params.values(), basis])
         if version != self._version:
-            self._packed.refresh(params)
+            self._packed.refresh(params, basis)
             self._version = version
         return self._packed
 
 
-class _RowsMLP(torch.autograd.Function):
-    """Forward: tensor-core rows MLP.  Backward (round-1 interim): library GEMMs through torch on the
-    `count` live rows."""
+class _VmColor(torch.autograd.Function):
+    """The appearance branch on the compacted surface samples: VM gather -> (basis o colour MLP) on the tensor cores.
+    Backward (round-1 interim for the MLP part): library GEMMs through torch on the `count` live rows,
+    then the hand-written scatter kernel for the planes / lines."""
 
     @staticmethod
-    def forward(ctx, predictor, comp, rows, *params):
-        rgb = predictor.packed().forward(rows, comp.count, rows.shape[0])
-        ctx.predictor, ctx.comp = predictor, comp
-        ctx.save_for_backward(rows, *params)
+    def forward(ctx, predictor, geom, comp, view_dirs, n_planes, basis, *params):
+        planes, lines, mlp = params[:n_planes], params[n_planes:2 * n_planes], params[2 * n_planes:]
+        rows, tables = T.vm_color_rows(geom, comp, view_dirs, list(planes), list(lines))
+        rgb = predictor.packed(basis).forward(rows, comp.count, rows.shape[0])
+        ctx.predictor, ctx.geom, ctx.comp, ctx.tables, ctx.n_planes = predictor, geom, comp, tables, n_planes
+        ctx.save_for_backward(rows, view_dirs, basis, *mlp)
         return rgb
 
     @staticmethod
     def backward(ctx, g_rgb):
-        rows, *params = ctx.saved_tensors
+        rows, view_dirs, basis, *mlp = ctx.saved_tensors
+        packed = ctx.predictor._packed
         n = int(ctx.comp.count.item())
-        g_rows = torch.zeros_like(rows)
-        grads = [None] * len(params)
+        ct = packed.num_products
+        g_rows = torch.zeros((rows.shape[0], ct), dtype=torch.float32, device=rows.device)
+        grads = [None] * (1 + len(mlp))
         if n > 0:
             with torch.enable_grad():
-                x = rows[:n, :ctx.predictor.input_dim].detach().requires_grad_()
-                ps = [p.detach().requires_grad_() for p in params]
-                hcur = F.relu(F.linear(x, ps[0], ps[1]))
-                hcur = F.relu(F.linear(hcur, ps[2], ps[3]))
-                y = torch.sigmoid(F.linear(hcur, ps[4], ps[5]))
+                x = rows[:n, :packed.in_cols].float()
+                if packed.num_view:             # fp32 view directions instead of their bf16 image (1 % on the table gradients)
+                    x[:, ct:] = view_dirs[(ctx.comp.idx[:n] // ctx.geom.S).long()]
+                x.requires_grad_()
+                ps = [p.detach().requires_grad_() for p in [basis] + mlp]
+                hcur = F.relu(F.linear(x, packed.composed_first_layer(ps[1], ps[0]), ps[2]))
+                hcur = F.relu(F.linear(hcur, ps[3], ps[4]))
+                y = torch.sigmoid(F.linear(hcur, ps[5], ps[6]))
                 gx, *grads = torch.autograd.grad(y, [x] + ps, g_rgb[:n])
-            g_rows[:n, :ctx.predictor.input_dim] = gx
-        return (None, None, g_rows, *grads)
+            g_rows[:n] = gx[:, :ct]
+        gp, gl = T.vm_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
+        return (None, None, None, None, None, grads[0], *gp, *gl, *grads[1:])
 
 
 class VmDecomposedTensor(torch.nn.Module):
@@ -380,13 +391,14 @@ class VmDecomposedTensor(torch.nn.Module):
             w0 = ops.composite(sigma.detach()[..., 0], None, z, rays['rays_o'], rays['rays_d'], sd, ndc=True,
                                distance_scale=tc['distance_scale'], per_sample=False)['weights']
         surface = T.threshold_compact(w0, tc['ray_marching_weight_threshold'])
-        rows = T.vm_color_rows(geom, surface, rays['view_dirs'], self.basis_matrix_color.weight, list(self.matrices_color),
-                               list(self.vectors_color))
         cp = self.color_predictor
-        if torch.is_grad_enabled() and any(p.requires_grad for p in cp.parameters()):
-            rgb_rows = _RowsMLP.apply(cp, surface, rows, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)])
+        basis = self.basis_matrix_color.weight
+        color_params = [*self.matrices_color, *self.vectors_color, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)]]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in [basis] + color_params):
+            rgb_rows = _VmColor.apply(cp, geom, surface, rays['view_dirs'], len(self.matrices_color), basis, *color_params)
         else:
-            rgb_rows = cp.packed().forward(rows, surface.count, rows.shape[0])
+            rows, _ = T.vm_color_rows(geom, surface, rays['view_dirs'], list(self.matrices_color), list(self.vectors_color))
+            rgb_rows = cp.packed(basis).forward(rows, surface.count, rows.shape[0])
         rgb = T._ScatterRows.apply(surface, rgb_rows, R * S).view(R, S, 3)
         white = white_bkgd or bool(self.training and (torch.rand((1,)) < 0.5))      # :746
         vr = ops.composite(sigma[..., 0], rgb, z, rays['rays_o'], rays['rays_d'], sd, ndc=True, white_bkgd=white,

@@ -239,36 +239,49 @@ def build_program(layers, shapes, offs, zero, points_degree, views_degree, head_
 
 
 class PackedRowsMLP:
-    """Two-hidden-layer MLP over precomputed 32-wide rows (the TensoRF colour predictor, reference
-    models/SimpleTensoRF09.py:1389-1393: Linear(in<=32,128) ReLU Linear(128,128) ReLU Linear(128,3) Sigmoid)."""
+    """The TensoRF colour predictor (reference models/SimpleTensoRF09.py:1389-1393: Linear(F [+3], 128) ReLU
+    Linear(128,128) ReLU Linear(128,3) Sigmoid) composed with basis_matrix_color (:1151, :1263, Linear(sum(C), F) without
+    bias): the first tensor-core layer uses W0' = [W0[:, :F] @ B | W0[:, F:]] over the 128-wide bf16 rows
+    [products (sum(C)) | view_dirs (3) | 0] that srf_vm_color_features_fwd writes."""
 
-    def __init__(self, in_features, prefix='color_predictor.mlp', units=128):
-        assert in_features <= 32 and units == 128
+    def __init__(self, num_products, features_dim, num_view=3, prefix='color_predictor.mlp', units=128):
+        assert num_products + num_view <= 128 and units == 128
+        self.num_products, self.features_dim, self.num_view = num_products, features_dim, num_view
+        self.in_cols = num_products + num_view
         self.names = [f'{prefix}.0.weight', f'{prefix}.0.bias', f'{prefix}.2.weight', f'{prefix}.2.bias',
                       f'{prefix}.4.weight', f'{prefix}.4.bias']
-        shapes = {self.names[0]: (units, in_features), self.names[1]: (units,), self.names[2]: (units, units),
+        shapes = {self.names[0]: (units, self.in_cols), self.names[1]: (units,), self.names[2]: (units, units),
                   self.names[3]: (units,), self.names[4]: (3, units), self.names[5]: (3,)}
         offs, o = {}, 0
         for n in self.names:
             offs[n] = o
             o += int(np.prod(shapes[n]))
         self.flat_size = o
-        cols0 = [j if j < in_features else -1 for j in range(64)]
-        layers = [(self.names[0], units, [(0, cols0)], 1, 1, 0),
+        two = self.in_cols > 64
+        kbs0 = [(0, [j if j < self.in_cols else -1 for j in range(64)])]
+        if two:
+            kbs0.append((5, [j if j < self.in_cols else -1 for j in range(64, 128)]))
+        layers = [(self.names[0], units, kbs0, 1, 1, 0),
                   (self.names[2], units, [(1, list(range(64))), (2, list(range(64, 128)))], 1, 0, 3)]
         self.program, self.blob_elems, self._gather_np, self._side_np = build_program(
-            layers, shapes, offs, o, 0, -1, head_names={3: f'{prefix}.4'})
+            layers, shapes, offs, o, 0, -2 if two else -1, head_names={3: f'{prefix}.4'})
         self._dev = None
         self.blob = self.side = None
-        self.macs_per_row = units * in_features + units * units + 3 * units
+        self.macs_per_row = units * self.in_cols + units * units + 3 * units
 
-    def refresh(self, params):
+    def composed_first_layer(self, w0, basis):
+        """W0' [units, sum(C) + num_view] (differentiable in torch: the interim backward and the tests use it too)."""
+        f = self.features_dim
+        return torch.cat([w0[:, :f] @ basis, w0[:, f:f + self.num_view]], dim=1)
+
+    def refresh(self, params, basis):
         dev = params[self.names[0]].device
         if self._dev != dev:
             self._gather = torch.from_numpy(self._gather_np).to(dev)
             self._side_idx = torch.from_numpy(self._side_np).to(dev)
             self._dev = dev
-        flat = torch.cat([params[n].detach().reshape(-1).float() for n in self.names] +
+        w0c = self.composed_first_layer(params[self.names[0]].detach().float(), basis.detach().float())
+        flat = torch.cat([w0c.reshape(-1)] + [params[n].detach().reshape(-1).float() for n in self.names[1:]] +
                          [torch.zeros(1, dtype=torch.float32, device=dev)])
         assert flat.numel() == self.flat_size + 1
         self.blob = flat[self._gather].to(torch.bfloat16).contiguous()
@@ -276,7 +289,8 @@ class PackedRowsMLP:
         return self
 
     def forward(self, rows, count, max_rows):
-        """rows [max_rows, 32] fp32, count int32[1] on the device -> rgb [max_rows, 3] (rows >= count undefined)."""
+        """rows [max_rows, 128] bf16, count int32[1] on the device -> rgb [max_rows, 3] (rows >= count undefined)."""
+        assert rows.dtype == torch.bfloat16 and rows.shape[1] == 128 and rows.is_contiguous()
         rgb = torch.empty((max_rows, 3), dtype=torch.float32, device=rows.device)
         L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
                L.ptr(count), max_rows, L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)

@@ -142,37 +142,30 @@ def vm_density(geom, comp, planes, lines, softplus=False, offset=0.0):
     return _VmDensity.apply(geom, comp, softplus, offset, len(planes), *planes, *lines)
 
 
-class _VmColorRows(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, geom, comp, view_dirs, n_planes, basis, *params):
-        planes, lines = params[:n_planes], params[n_planes:]
-        planes_cl, lines_cl = to_channels_last(planes, lines)
-        chans = _i3([p.shape[1] for p in planes])
-        basis_c = L.f32c(basis.detach())
-        F = basis_c.shape[0]
-        rows = torch.empty((max(comp.total, 1), 32), dtype=torch.float32, device=geom.z.device)
-        L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, L.ptr(basis_c), F,
-               L.ptr(L.f32c(view_dirs)), L.ptr(rows), L.stream_handle())
-        ctx.geom, ctx.comp, ctx.n_planes = geom, comp, n_planes
-        ctx.tables = (planes_cl, lines_cl, chans, basis_c)
-        return rows
-
-    @staticmethod
-    def backward(ctx, g_rows):
-        geom, comp = ctx.geom, ctx.comp
-        planes_cl, lines_cl, chans, basis_c = ctx.tables
-        gp = [torch.zeros_like(p) for p in planes_cl]
-        gl = [torch.zeros_like(l) for l in lines_cl]
-        gb = torch.zeros_like(basis_c)
-        L.call('srf_vm_color_features_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, L.ptr(basis_c),
-               basis_c.shape[0], L.ptr(L.f32c(g_rows)), L.ptr(gb), _ptrs(gp), _ptrs(gl), L.stream_handle())
-        grads = [g.permute(2, 0, 1)[None].contiguous() for g in gp] + [g.permute(1, 0)[None, :, :, None].contiguous() for g in gl]
-        return (None, None, None, None, gb, *grads)
+COLOR_ROW = 128
 
 
-def vm_color_rows(geom, comp, view_dirs, basis, planes, lines):
-    """rows [total, 32] = [basis(plane x line) (F) | view_dirs (3) | 0], first comp.count rows valid."""
-    return _VmColorRows.apply(geom, comp, view_dirs, len(planes), basis, *planes, *lines)
+def vm_color_rows(geom, comp, view_dirs, planes, lines):
+    """rows [total, 128] bf16 = [plane x line products (sum C) | view_dirs (3) | 0], first comp.count rows valid; also
+    returns the channels-last tables for vm_color_rows_backward.  Not an autograd node by itself: the colour branch
+    (gather -> MLP) is one autograd.Function in models/SimpleTensoRF91.py so the bf16 rows never carry a gradient."""
+    planes_cl, lines_cl = to_channels_last(planes, lines)
+    chans = _i3([p.shape[1] for p in planes])
+    rows = torch.empty((max(comp.total, 1), COLOR_ROW), dtype=torch.bfloat16, device=geom.z.device)
+    L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
+           L.ptr(L.f32c(view_dirs)), L.ptr(rows), L.stream_handle())
+    return rows, (planes_cl, lines_cl, chans)
+
+
+def vm_color_rows_backward(geom, comp, tables, g_rows):
+    """g_rows [>= count, >= sum C] fp32 -> gradients of planes ([1,C,H,W]) and lines ([1,C,L,1])."""
+    planes_cl, lines_cl, chans = tables
+    gp = [torch.zeros_like(p) for p in planes_cl]
+    gl = [torch.zeros_like(l) for l in lines_cl]
+    g = L.f32c(g_rows)
+    L.call('srf_vm_color_features_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
+           L.ptr(g), g.shape[1], _ptrs(gp), _ptrs(gl), L.stream_handle())
+    return ([x.permute(2, 0, 1)[None].contiguous() for x in gp], [x.permute(1, 0)[None, :, :, None].contiguous() for x in gl])
 
 
 def scatter_rows(comp, src, width, total):

@@ -115,8 +115,10 @@ def test_vm_density_forward_backward(golden_configs, with_alpha):
 
 
 def test_vm_color_rows_and_mlp(golden_configs):
+    """The appearance branch: gathered (plane x line) product rows (bf16), their scatter backward, and the colour MLP
+    with basis_matrix_color folded into its first layer, against the fp32 oracle."""
     from simple_rf_b200 import tensorf_ops as T
-    from simple_rf_b200.nerf_program import PackedRowsMLP
+    from simple_rf_b200.models.SimpleTensoRF91 import MlpFeaturesColorPredictor, _VmColor
     configs, mc, t, a = _scene(golden_configs, 150, seed=8, with_alpha=False)
     params = {k: v.clone().requires_grad_() for k, v in t['params'].items()}
     pts = a['on'][:, None, :] + a['dn'][:, None, :] * a['z'][..., None]
@@ -124,35 +126,64 @@ def test_vm_color_rows_and_mlp(golden_configs):
     g = torch.Generator().manual_seed(2)
     wts = torch.rand(a['z'].shape, generator=g) ** 6
     surf = wts > 1e-4
-    feats = TF.vm_color_features(params, pn[surf])
+    prods = TF.vm_color_products(params, pn[surf])
     vd = a['vd'][:, None].expand(pts.shape)[surf]
-    rgb_ref = TF.color_mlp(params, feats, vd)
-    up = torch.rand(feats.shape, generator=g)
-    (feats * up).sum().backward()
+    up = torch.rand(prods.shape, generator=g)
+    (prods * up).sum().backward()
+    gref_tables = {k: params[k].grad.clone() for k in params if k.startswith(('matrices_color', 'vectors_color'))}
+    for p_ in params.values():
+        p_.grad = None
 
     dp = {k: v.detach().to(DEV).requires_grad_() for k, v in params.items()}
     comp = T.threshold_compact(wts.to(DEV), 1e-4)
     n = int(comp.count.item())
     assert n == int(surf.sum())
     geom = T.VmGeometry(a['on'].to(DEV), a['dn'].to(DEV), a['z'].to(DEV), t['bbox'][0], t['bbox'][1] - t['bbox'][0], t['resolution'])
-    rows = T.vm_color_rows(geom, comp, a['vd'].to(DEV), dp['basis_matrix_color.weight'],
-                           [dp[f'matrices_color.{i}'] for i in range(3)], [dp[f'vectors_color.{i}'] for i in range(3)])
-    F_ = feats.shape[1]
-    assert (rows[:n, :F_].cpu() - feats.detach()).abs().max().item() <= 1e-5 * max(1.0, feats.abs().max().item())
-    assert (rows[:n, F_:F_ + 3].cpu() - vd).abs().max().item() == 0
-    assert (rows[:n, F_ + 3:] == 0).all()
-    g_rows = torch.zeros_like(rows)
-    g_rows[:n, :F_] = up.to(DEV)
-    rows.backward(g_rows)
-    for k in ('basis_matrix_color.weight', 'matrices_color.0', 'matrices_color.2', 'vectors_color.0', 'vectors_color.1'):
-        gref = params[k].grad
-        err = (dp[k].grad.cpu() - gref).abs().max().item() / max(gref.abs().max().item(), 1e-12)
-        assert err <= 1e-4, (k, err)
-    mlp = PackedRowsMLP(F_ + 3, prefix='color_predictor.mlp').refresh({k: v.detach() for k, v in dp.items() if k.startswith('color_predictor')})
-    rgb = mlp.forward(rows.detach(), comp.count, rows.shape[0])
+    planes, lines = [dp[f'matrices_color.{i}'] for i in range(3)], [dp[f'vectors_color.{i}'] for i in range(3)]
+    rows, tables = T.vm_color_rows(geom, comp, a['vd'].to(DEV), planes, lines)
+    CT = prods.shape[1]
+    assert rows.dtype == torch.bfloat16 and rows.shape[1] == 128
+    # products are computed in fp32 and rounded once to bf16 (2^-9 relative), view directions likewise
+    ref_b = prods.detach()
+    assert ((rows[:n, :CT].float().cpu() - ref_b).abs() <= 2.0 ** -8 * ref_b.abs() + 1e-6).all()
+    assert torch.equal(rows[:n, CT:CT + 3].cpu(), vd.to(torch.bfloat16))
+    assert (rows[:n, CT + 3:] == 0).all()
+    g_rows = torch.zeros((rows.shape[0], CT), device=DEV)
+    g_rows[:n] = up.to(DEV)
+    gp, gl = T.vm_color_rows_backward(geom, comp, tables, g_rows)
+    for i in range(3):
+        for k, got in ((f'matrices_color.{i}', gp[i]), (f'vectors_color.{i}', gl[i])):
+            gref = gref_tables[k]
+            err = (got.cpu() - gref).abs().max().item() / max(gref.abs().max().item(), 1e-12)
+            assert err <= 1e-4, (k, err)          # fp32 scatter: atomics only reorder the sums
+
+    # whole branch (gather -> basis o MLP) through the autograd node the model uses
+    rgb_ref = TF.color_mlp(params, TF.vm_color_features(params, pn[surf]), vd)
+    up3 = torch.rand(rgb_ref.shape, generator=g)
+    (rgb_ref * up3).sum().backward()
+    tc = configs['model']['coarse_model']
+    cp = MlpFeaturesColorPredictor(tc, dp['basis_matrix_color.weight'].shape[0], 128).to(DEV)
+    names = [f'mlp.{i}.{w}' for i in (0, 2, 4) for w in ('weight', 'bias')]
+    cp.load_state_dict({nm: dp[f'color_predictor.{nm}'].detach() for nm in names})
+    mlp_params = [dict(cp.named_parameters())[nm] for nm in names]
+    for nm, p_ in zip(names, mlp_params):
+        dp[f'color_predictor.{nm}'] = p_
+    rgb = _VmColor.apply(cp, geom, comp, a['vd'].to(DEV), 3, dp['basis_matrix_color.weight'], *planes, *lines, *mlp_params)
     err = (rgb[:n].cpu() - rgb_ref.detach()).abs().max().item()
-    print('colour MLP max abs err', err)
+    print('colour branch max abs err', err)
     assert err <= MLP_TOL
+    g_rgb = torch.zeros_like(rgb)
+    g_rgb[:n] = up3.to(DEV)
+    rgb.backward(g_rgb)
+    for k in params:
+        if not k.startswith(('matrices_color', 'vectors_color', 'basis_matrix_color', 'color_predictor')):
+            continue
+        gref = params[k].grad
+        got = dp[k].grad.cpu()
+        err = (got - gref).abs().max().item() / max(gref.abs().max().item(), 1e-12)
+        l2 = ((got - gref).norm() / gref.norm().clamp_min(1e-12)).item()
+        # stated tolerance: the saved product rows are bf16 (2^-9 relative), everything else in this backward is fp32
+        assert err <= 2e-2 and l2 <= 5e-3, (k, err, l2)
 
 
 def _model(golden_configs, g):
@@ -201,7 +232,8 @@ def test_dropin_forward_vs_reference_golden(golden, golden_configs, mode):
 
 def test_dropin_training_gradients(golden, golden_configs):
     """Gradients of every trainable tensor after one forward/backward against autograd through the fp32 oracle.
-    Stated tolerance: 2e-2 of the per-tensor max |g| (colour MLP forward runs bf16 operands)."""
+    Stated tolerance: max-abs <= 1e-2 of the per-tensor max |g| and rel-L2 <= 5e-3 (the colour branch's product rows are
+    bf16; measured worst 3.7e-3 / 1e-3)."""
     g = golden('tensorf_train')
     model, configs, mc, sets = _model(golden_configs, g)
     model.train()
@@ -221,7 +253,7 @@ def test_dropin_training_gradients(golden, golden_configs):
     ref_loss.backward()
     assert abs(loss.item() - ref_loss.item()) <= 3e-3 * abs(ref_loss.item())
     mods = [model.coarse_model] + [a['coarse_model'] for a in model.augmented_models]
-    worst = 0.0
+    worst, report = 0.0, []
     for mod, t in zip(mods, tensors):
         for k, p in mod.named_parameters():
             gr = t['params'][k].grad
@@ -230,6 +262,10 @@ def test_dropin_training_gradients(golden, golden_configs):
                 continue
             assert p.grad is not None, k
             rel = (p.grad.cpu() - gr).abs().max().item() / gr.abs().max().item()
+            l2 = ((p.grad.cpu() - gr).norm() / gr.norm()).item()
             worst = max(worst, rel)
-            assert rel <= 2e-2, (mod.name, k, rel)
+            report.append((mod.name, k, round(rel, 5), round(l2, 5)))
     print('worst relative gradient error', worst)
+    print('\n'.join(map(str, report)))
+    for name, k, rel, l2 in report:
+        assert rel <= 1e-2 and l2 <= 5e-3, (name, k, rel, l2)

@@ -112,5 +112,5 @@ ns = int(surf.count.item())
 cplanes = [params[f'matrices_color.{i}'] for i in range(3)]; clines = [params[f'vectors_color.{i}'] for i in range(3)]
 vd = torch.nn.functional.normalize(torch.randn(R, 3, device=dev), dim=-1)
 with torch.no_grad():
-    ms = timed(lambda: T.vm_color_rows(geom, surf, vd, params['basis_matrix_color.weight'], cplanes, clines))
+    ms = timed(lambda: T.vm_color_rows(geom, surf, vd, cplanes, clines))
 report(f'vm_color_rows n={ns} ({ns / (R * S):.3f} of samples)', ms, ns * 1728, unit_note='requested texel bytes; includes channels-last cache rebuild')
