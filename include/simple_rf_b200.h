@@ -163,14 +163,14 @@ int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const float* z,
                        float* const* g_planes, float* const* g_lines, void* stream);
 
 /* VM appearance features (SimpleTensoRF09.py:1241-1263): (plane x line) products over sum(C) <= 96 channels written as
- * bf16 rows [max_count, 128] = [products | 3 view_dirs | zero pad] — the two 64-column A-operand blocks of the colour
- * MLP.  basis_matrix_color (:1151, :1263) is linear and is folded into the MLP's first layer by the host
+ * bf16 rows [max_count, row_pitch] = [products | 3 view_dirs | zero pad] (row_pitch a multiple of 8 that holds
+ * sum(C) + 3 elements, <= 128; every C a multiple of 4) — the A operand of the colour MLP.  basis_matrix_color (:1151, :1263) is linear and is folded into the MLP's first layer by the host
  * (W0' = [W0[:, :F] B | W0[:, F:]]), so this kernel is a pure gather.  The backward scatters g_rows[:, :sum(C)]
  * (fp32, row pitch g_row_pitch floats) into zero-initialised channels-last plane / line gradients. */
 int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
                               const float* const* planes, const float* const* lines, const int* channels,
-                              const int* resolution, const float* view_dirs, void* rows, void* stream);
+                              const int* resolution, const float* view_dirs, void* rows, int row_pitch, void* stream);
 int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
                               const float* const* planes, const float* const* lines, const int* channels,
@@ -184,9 +184,9 @@ int srf_gather_rows(const int* indices, const int* count, int64_t max_count, con
                     void* stream);
 
 /* Colour MLP on the tensor cores: same kernel and program format as srf_nerf_mlp_fwd, but regions 0 and 5 are filled from
- * precomputed bf16 rows [max_rows, 128] (columns 0..63 / 64..127) instead of encodings (views_degree = -2 in the
+ * precomputed bf16 rows [max_rows, row_pitch] (columns 0..63 / 64..row_pitch-1, zero beyond) instead of encodings (views_degree = -2 in the
  * program; -1 when only region 0 is used); the row count is read from the device. */
-int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, const int* count,
+int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, int row_pitch, const int* count,
                      int64_t max_rows, float* rgb, void* stream);
 
 /* Weight gradients of the fused MLP (what autograd derives for the nn.Linear layers of

@@ -55,6 +55,7 @@ struct MlpArgs {
   const float* noise;           // [R*S] or nullptr: added to raw sigma before the ReLU
   const uint4* rows;            // rows mode: [total, 128] bf16 inputs: columns 0..63 fill region 0, 64..127 region 5
   const int* count;             // rows mode: device-side row count (<= total), or nullptr
+  int row_units;                // rows mode: 16-byte units per row (units 0..7 -> region 0, 8..15 -> region 5)
   float* sigma;                 // [R*S]
   float* rgb;                   // [R*S,3]
   // training: every A-operand tile (encodings, post-activation layer outputs) is also written to HBM as the same
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       if (args.rows != nullptr) {
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          x[q] = (valid && (q < 8 || has_views)) ? __ldg(args.rows + m * 16 + q) : make_uint4(0u, 0u, 0u, 0u);
+          x[q] = (valid && q < args.row_units) ? __ldg(args.rows + m * args.row_units + q) : make_uint4(0u, 0u, 0u, 0u);
       } else if (valid) {
         const long long r = m / args.S;
         const float zz = args.z[m];
@@ -569,8 +570,8 @@ SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const flo
   return launch_mlp(prog, a, a.total, stream, "srf_nerf_mlp_fwd");
 }
 
-SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, const int* count,
-                             int64_t max_rows, float* rgb, void* stream) {
+SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, int row_pitch,
+                             const int* count, int64_t max_rows, float* rgb, void* stream) {
   if (max_rows == 0) return 0;
   SRF_REQUIRE(program && weights && side && rows && rgb, "srf_mlp_rows_fwd", "null pointer");
   MlpProgram prog = *reinterpret_cast<const MlpProgram*>(program);
@@ -580,6 +581,9 @@ SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const flo
   MlpArgs a{};
   a.weights = reinterpret_cast<const uint8_t*>(weights);
   a.side = side; a.rows = reinterpret_cast<const uint4*>(rows); a.count = count; a.rgb = rgb;
+  SRF_REQUIRE(row_pitch % 8 == 0 && row_pitch >= 8 && row_pitch <= 128 && (prog.views_degree == -2 || row_pitch <= 64), "srf_mlp_rows_fwd",
+              "row_pitch must be a multiple of 8 in 8..128 (<= 64 for a one-block program)");
+  a.row_units = row_pitch / 8;
   a.total = max_rows;
   a.S = 1;
   return launch_mlp(prog, a, max_rows, stream, "srf_mlp_rows_fwd");

@@ -209,9 +209,10 @@ struct VmGeom {
 };
 
 // matrix_axes = [[0,1],[0,2],[1,2]], vector_axes = [2,1,0]  (:1131-1132); grid x -> W = res[a0], y -> H = res[a1]
-__device__ __constant__ int c_a0[3] = {0, 0, 1};
-__device__ __constant__ int c_a1[3] = {1, 2, 2};
-__device__ __constant__ int c_av[3] = {2, 1, 0};
+// (functions, not __constant__ tables: after unrolling the axis is a compile-time constant and nothing is indexed dynamically)
+__host__ __device__ __forceinline__ constexpr int axis0(int i) { return i == 2 ? 1 : 0; }
+__host__ __device__ __forceinline__ constexpr int axis1(int i) { return i == 0 ? 1 : 2; }
+__host__ __device__ __forceinline__ constexpr int axisv(int i) { return 2 - i; }
 
 struct Bilerp {
   int x0, y0, W, H;
@@ -232,8 +233,8 @@ __device__ __forceinline__ float unnorm(float c, int size) { return __fmul_rn(__
 
 __device__ __forceinline__ Bilerp plane_coords(const float (&pn)[3], const int (&res)[3], int i) {
   Bilerp b;
-  b.W = res[c_a0[i]]; b.H = res[c_a1[i]];
-  const float ix = unnorm(pn[c_a0[i]], b.W), iy = unnorm(pn[c_a1[i]], b.H);
+  b.W = res[axis0(i)]; b.H = res[axis1(i)];
+  const float ix = unnorm(pn[axis0(i)], b.W), iy = unnorm(pn[axis1(i)], b.H);
   const float fx = floorf(ix), fy = floorf(iy);
   b.x0 = (int)fx; b.y0 = (int)fy;
   b.wx1 = ix - fx; b.wx0 = (fx + 1.f) - ix;
@@ -256,8 +257,8 @@ __device__ __forceinline__ float4 plane_fetch4(const float* plane, const Bilerp&
 }
 
 __device__ __forceinline__ void line_coords(const float (&pn)[3], const int (&res)[3], int i, int& l0, int& L, float& w0, float& w1) {
-  L = res[c_av[i]];
-  const float iy = unnorm(pn[c_av[i]], L);
+  L = res[axisv(i)];
+  const float iy = unnorm(pn[axisv(i)], L);
   const float fy = floorf(iy);
   l0 = (int)fy;
   w1 = iy - fy; w0 = (fy + 1.f) - iy;
@@ -350,143 +351,142 @@ __global__ void __launch_bounds__(256) vm_density_bwd_kernel(VmGeom g, VmGrid t,
   }
 }
 
-// appearance: products (plane x line) over all channels -> rows of [products (CT <= 96) | view_dirs (3) | zero pad],
-// 128 bf16 per row, the two 64-column A-operand blocks of the tensor-core colour MLP (whose first layer absorbs
-// basis_matrix_color: W0' = [W0[:, :F] B | W0[:, F:]], so no matrix-vector product is left in this kernel).
-// A warp takes 32 samples: lane-per-sample coordinate / weight arithmetic into shared memory, then lane-per-channel
-// gathers (channels-last texels: consecutive lanes read consecutive floats) for one sample at a time.
-constexpr int COLOR_ROW = 128;          // bf16 elements per row
+// appearance: products (plane x line) over all channels -> bf16 rows of `pitch` elements
+// [products (CT = sum C) | view_dirs (3) | zero pad]: the A operand of the tensor-core colour MLP, whose first layer
+// absorbs basis_matrix_color (W0' = [W0[:, :F] B | W0[:, F:]]), so no matrix-vector product is left in this kernel.
+// A warp takes 32 samples.  Phase 1, lane per sample: coordinates -> per plane 4 clamped corner offsets + weights
+// (zero weight = grid_sample's zero padding) and per line 2 offsets + weights, into shared memory.  Phase 2, lane per
+// (sample, 4-channel group): 6 float4 texel loads, 28 FMAs, one 8-byte store; consecutive lanes write consecutive
+// 8-byte pieces of the row-major output, so stores are fully coalesced and no lane idles on a short channel list.
 constexpr int CF_WARPS = 8;
 
-struct SampleCoords {                   // per sample: 3 planes (x0, y0, 4 corner weights) + 3 lines (l0, 2 weights)
-  int px0[3], py0[3];
+struct alignas(16) SampleRec {
+  int poff[3][4];          // element offsets of the bilinear corners in the channels-last plane
   float pw[3][4];
-  int l0[3];
-  float lw[3][2];
-  int ray;
+  int line[3][4];          // {offset 0, offset 1, weight 0 bits, weight 1 bits}
 };
 
-__device__ __forceinline__ void compute_coords(const VmGeom& g, const VmGrid& t, int flat, SampleCoords& c) {
+__device__ __forceinline__ int clampi(int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); }
+
+__device__ __forceinline__ void compute_record(const VmGeom& g, const VmGrid& t, int flat, SampleRec& r) {
   float pn[3];
   normalized_point(g, flat, pn);
-  c.ray = flat / g.S;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const Bilerp b = plane_coords(pn, t.res, i);
-    c.px0[i] = b.x0; c.py0[i] = b.y0;
+    const int C = t.C[i];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
       const bool in = x >= 0 && y >= 0 && x < b.W && y < b.H;
-      c.pw[i][k] = in ? ((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0) : 0.f;   // zero weight = zero padding
+      r.pw[i][k] = in ? ((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0) : 0.f;
+      r.poff[i][k] = (clampi(y, b.H) * b.W + clampi(x, b.W)) * C;
     }
     int l0, L; float w0, w1;
     line_coords(pn, t.res, i, l0, L, w0, w1);
-    c.l0[i] = l0;
-    c.lw[i][0] = (l0 >= 0 && l0 < L) ? w0 : 0.f;
-    c.lw[i][1] = (l0 + 1 >= 0 && l0 + 1 < L) ? w1 : 0.f;
+    r.line[i][0] = clampi(l0, L) * C;
+    r.line[i][1] = clampi(l0 + 1, L) * C;
+    r.line[i][2] = __float_as_int((l0 >= 0 && l0 < L) ? w0 : 0.f);
+    r.line[i][3] = __float_as_int((l0 + 1 >= 0 && l0 + 1 < L) ? w1 : 0.f);
   }
 }
 
-// clamped texel address helpers: out-of-range corners carry zero weight, so any in-range address may be read
-__device__ __forceinline__ int clampi(int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); }
+struct GroupMap { int g0, g1, G, GP; unsigned inv; };     // float4 groups: [0,g0) plane 0, [g0,g1) plane 1, [g1,G) plane 2
 
-struct ChannelSlot { int plane, c, C, W, H, L; };
-
-__device__ __forceinline__ ChannelSlot channel_slot(const VmGrid& t, int ch, int CT) {
-  ChannelSlot s{0, 0, 0, 0, 0, 0};
-  if (ch >= CT) { s.plane = -1; return s; }
-  int i = 0, c = ch;
-  while (i < 2 && c >= t.C[i]) { c -= t.C[i]; ++i; }
-  s.plane = i; s.c = c; s.C = t.C[i];
-  s.W = t.res[c_a0[i]]; s.H = t.res[c_a1[i]]; s.L = t.res[c_av[i]];
-  return s;
+__device__ __forceinline__ uint32_t ptx_pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
-__global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_fwd_kernel(VmGeom g, VmGrid t, int CT, const float* __restrict__ view_dirs,
-                                                                              __nv_bfloat16* __restrict__ rows) {
-  __shared__ SampleCoords s_c[CF_WARPS][32];
-  __shared__ __align__(16) __nv_bfloat16 s_row[CF_WARPS][COLOR_ROW];
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// plane and line values of one 4-channel group at one sample
+__device__ __forceinline__ void fetch_group(const VmGrid& t, const SampleRec& r, int i, int c, float4& pv, float4& lv, int4& po, float4& pw,
+                                            int4& lr) {
+  po = *reinterpret_cast<const int4*>(r.poff[i]);
+  pw = *reinterpret_cast<const float4*>(r.pw[i]);
+  lr = *reinterpret_cast<const int4*>(r.line[i]);
+  const float* pl = (i == 0 ? t.plane[0] : (i == 1 ? t.plane[1] : t.plane[2])) + c;      // selects: no local copy of the params
+  const float* ln = (i == 0 ? t.line[0] : (i == 1 ? t.line[1] : t.line[2])) + c;
+  const float4 a0 = ldg4(pl + po.x), a1 = ldg4(pl + po.y), a2 = ldg4(pl + po.z), a3 = ldg4(pl + po.w);
+  const float4 b0 = ldg4(ln + lr.x), b1 = ldg4(ln + lr.y);
+  const float w0 = __int_as_float(lr.z), w1 = __int_as_float(lr.w);
+  pv.x = a0.x * pw.x + a1.x * pw.y + a2.x * pw.z + a3.x * pw.w;
+  pv.y = a0.y * pw.x + a1.y * pw.y + a2.y * pw.z + a3.y * pw.w;
+  pv.z = a0.z * pw.x + a1.z * pw.y + a2.z * pw.z + a3.z * pw.w;
+  pv.w = a0.w * pw.x + a1.w * pw.y + a2.w * pw.z + a3.w * pw.w;
+  lv.x = b0.x * w0 + b1.x * w1; lv.y = b0.y * w0 + b1.y * w1; lv.z = b0.z * w0 + b1.z * w1; lv.w = b0.w * w0 + b1.w * w1;
+}
+
+__global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_fwd_kernel(VmGeom g, VmGrid t, GroupMap m, const float* __restrict__ view_dirs,
+                                                                              uint2* __restrict__ rows) {
+  __shared__ SampleRec s_rec[CF_WARPS][32];
+  __shared__ uint2 s_vd[CF_WARPS][32];
   const int n = g.count[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CF_WARPS + warp, nw = gridDim.x * CF_WARPS;
-  ChannelSlot slot[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) slot[k] = channel_slot(t, lane + 32 * k, CT);
   for (int base = gw * 32; base < n; base += nw * 32) {
     const int cnt = min(32, n - base);
-    if (lane < cnt) compute_coords(g, t, g.idx[base + lane], s_c[warp][lane]);
-    __syncwarp();
-    for (int sidx = 0; sidx < cnt; ++sidx) {
-      const SampleCoords& c = s_c[warp][sidx];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float prod = 0.f;
-        const ChannelSlot& sl = slot[k];
-        if (sl.plane >= 0) {
-          const int i = sl.plane;
-          const float* pl = t.plane[i];
-          const int x0 = c.px0[i], y0 = c.py0[i];
-          const int xa = clampi(x0, sl.W), xb = clampi(x0 + 1, sl.W), ya = clampi(y0, sl.H), yb = clampi(y0 + 1, sl.H);
-          const float pv = __ldg(pl + ((size_t)ya * sl.W + xa) * sl.C + sl.c) * c.pw[i][0] + __ldg(pl + ((size_t)ya * sl.W + xb) * sl.C + sl.c) * c.pw[i][1] +
-                           __ldg(pl + ((size_t)yb * sl.W + xa) * sl.C + sl.c) * c.pw[i][2] + __ldg(pl + ((size_t)yb * sl.W + xb) * sl.C + sl.c) * c.pw[i][3];
-          const int la = clampi(c.l0[i], sl.L), lb = clampi(c.l0[i] + 1, sl.L);
-          const float lv = __ldg(t.line[i] + (size_t)la * sl.C + sl.c) * c.lw[i][0] + __ldg(t.line[i] + (size_t)lb * sl.C + sl.c) * c.lw[i][1];
-          prod = pv * lv;
-        }
-        s_row[warp][lane + 32 * k] = __float2bfloat16_rn(prod);
-      }
-      s_row[warp][96 + lane] = __float2bfloat16_rn(0.f);
-      __syncwarp();
-      if (lane < 3) s_row[warp][CT + lane] = __float2bfloat16_rn(view_dirs[c.ray * 3 + lane]);
-      __syncwarp();
-      // 256-byte row, 8 bytes per lane
-      reinterpret_cast<uint2*>(rows + (size_t)(base + sidx) * COLOR_ROW)[lane] = reinterpret_cast<const uint2*>(s_row[warp])[lane];
-      __syncwarp();
+    if (lane < cnt) {
+      const int flat = g.idx[base + lane];
+      compute_record(g, t, flat, s_rec[warp][lane]);
+      const float* vd = view_dirs + (size_t)(flat / g.S) * 3;
+      s_vd[warp][lane] = make_uint2(ptx_pack_bf16(vd[0], vd[1]), ptx_pack_bf16(vd[2], 0.f));
     }
+    __syncwarp();
+    uint2* out = rows + (size_t)base * m.GP;
+    for (int item = lane; item < cnt * m.GP; item += 32) {
+      const int sidx = (int)(((unsigned)item * m.inv) >> 16);
+      const int gq = item - sidx * m.GP;
+      uint2 v = make_uint2(0u, 0u);
+      if (gq < m.G) {
+        const int i = (gq >= m.g0) + (gq >= m.g1);
+        const int c = (gq - (i == 0 ? 0 : (i == 1 ? m.g0 : m.g1))) << 2;
+        float4 pv, lv, pw; int4 po, lr;
+        fetch_group(t, s_rec[warp][sidx], i, c, pv, lv, po, pw, lr);
+        v = make_uint2(ptx_pack_bf16(pv.x * lv.x, pv.y * lv.y), ptx_pack_bf16(pv.z * lv.z, pv.w * lv.w));
+      } else if (gq == m.G) {
+        v = s_vd[warp][sidx];
+      }
+      out[item] = v;
+    }
+    __syncwarp();
   }
 }
 
-// backward: g_rows[:, :CT] (fp32, row pitch `pitch`) scattered into the channels-last plane / line gradients
-__global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_bwd_kernel(VmGeom g, VmGrid t, int CT, const float* __restrict__ g_rows, int pitch,
+// backward: g_rows[:, :CT] (fp32, row pitch `pitch` floats, a multiple of 4) scattered into the zero-initialised
+// channels-last plane / line gradients with 16-byte vector reductions; same (sample, group) work split as the forward
+__global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_bwd_kernel(VmGeom g, VmGrid t, GroupMap m, const float* __restrict__ g_rows, int pitch,
                                                                               float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
-  __shared__ SampleCoords s_c[CF_WARPS][32];
-  float* gplane[3] = {gp0, gp1, gp2};
-  float* gline[3] = {gl0, gl1, gl2};
+  __shared__ SampleRec s_rec[CF_WARPS][32];
   const int n = g.count[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CF_WARPS + warp, nw = gridDim.x * CF_WARPS;
-  ChannelSlot slot[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) slot[k] = channel_slot(t, lane + 32 * k, CT);
   for (int base = gw * 32; base < n; base += nw * 32) {
     const int cnt = min(32, n - base);
-    if (lane < cnt) compute_coords(g, t, g.idx[base + lane], s_c[warp][lane]);
+    if (lane < cnt) compute_record(g, t, g.idx[base + lane], s_rec[warp][lane]);
     __syncwarp();
-    for (int sidx = 0; sidx < cnt; ++sidx) {
-      const SampleCoords& c = s_c[warp][sidx];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const ChannelSlot& sl = slot[k];
-        if (sl.plane < 0) continue;
-        const float gprod = g_rows[(size_t)(base + sidx) * pitch + lane + 32 * k];
-        if (gprod == 0.f) continue;
-        const int i = sl.plane;
-        const float* pl = t.plane[i];
-        const int x0 = c.px0[i], y0 = c.py0[i];
-        const int xs[2] = {clampi(x0, sl.W), clampi(x0 + 1, sl.W)}, ys[2] = {clampi(y0, sl.H), clampi(y0 + 1, sl.H)};
-        const int la = clampi(c.l0[i], sl.L), lb = clampi(c.l0[i] + 1, sl.L);
-        float pv = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pv += __ldg(pl + ((size_t)ys[q >> 1] * sl.W + xs[q & 1]) * sl.C + sl.c) * c.pw[i][q];
-        const float lv = __ldg(t.line[i] + (size_t)la * sl.C + sl.c) * c.lw[i][0] + __ldg(t.line[i] + (size_t)lb * sl.C + sl.c) * c.lw[i][1];
-        const float gpv = gprod * lv, glv = gprod * pv;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (c.pw[i][q] != 0.f) atomicAdd(gplane[i] + ((size_t)ys[q >> 1] * sl.W + xs[q & 1]) * sl.C + sl.c, gpv * c.pw[i][q]);
-        if (c.lw[i][0] != 0.f) atomicAdd(gline[i] + (size_t)la * sl.C + sl.c, glv * c.lw[i][0]);
-        if (c.lw[i][1] != 0.f) atomicAdd(gline[i] + (size_t)lb * sl.C + sl.c, glv * c.lw[i][1]);
-      }
+    for (int item = lane; item < cnt * m.G; item += 32) {
+      const int sidx = (int)(((unsigned)item * m.inv) >> 16);        // m.inv / m.GP describe G groups per sample here
+      const int gq = item - sidx * m.G;
+      const float4 go = ldg4(g_rows + (size_t)(base + sidx) * pitch + gq * 4);
+      if (go.x == 0.f && go.y == 0.f && go.z == 0.f && go.w == 0.f) continue;
+      const int i = (gq >= m.g0) + (gq >= m.g1);
+      const int c = (gq - (i == 0 ? 0 : (i == 1 ? m.g0 : m.g1))) << 2;
+      float4 pv, lv, pw; int4 po, lr;
+      fetch_group(t, s_rec[warp][sidx], i, c, pv, lv, po, pw, lr);
+      float* gpl = (i == 0 ? gp0 : (i == 1 ? gp1 : gp2)) + c;
+      float* gln = (i == 0 ? gl0 : (i == 1 ? gl1 : gl2)) + c;
+      const float4 gpv = make_float4(go.x * lv.x, go.y * lv.y, go.z * lv.z, go.w * lv.w);
+      const float4 glv = make_float4(go.x * pv.x, go.y * pv.y, go.z * pv.z, go.w * pv.w);
+      if (pw.x != 0.f) red_add4(gpl + po.x, gpv.x * pw.x, gpv.y * pw.x, gpv.z * pw.x, gpv.w * pw.x);
+      if (pw.y != 0.f) red_add4(gpl + po.y, gpv.x * pw.y, gpv.y * pw.y, gpv.z * pw.y, gpv.w * pw.y);
+      if (pw.z != 0.f) red_add4(gpl + po.z, gpv.x * pw.z, gpv.y * pw.z, gpv.z * pw.z, gpv.w * pw.z);
+      if (pw.w != 0.f) red_add4(gpl + po.w, gpv.x * pw.w, gpv.y * pw.w, gpv.z * pw.w, gpv.w * pw.w);
+      const float w0 = __int_as_float(lr.z), w1 = __int_as_float(lr.w);
+      if (w0 != 0.f) red_add4(gln + lr.x, glv.x * w0, glv.y * w0, glv.z * w0, glv.w * w0);
+      if (w1 != 0.f) red_add4(gln + lr.y, glv.x * w1, glv.y * w1, glv.z * w1, glv.w * w1);
     }
     __syncwarp();
   }
@@ -617,19 +617,29 @@ SRF_API int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const f
   return check_launch("srf_vm_density_bwd");
 }
 
+static int fill_groups(GroupMap& m, const int* channels, int groups_per_row, const char* where) {
+  SRF_REQUIRE(channels[0] % 4 == 0 && channels[1] % 4 == 0 && channels[2] % 4 == 0, where, "component counts must be multiples of 4");
+  m.g0 = channels[0] / 4; m.g1 = m.g0 + channels[1] / 4; m.G = m.g1 + channels[2] / 4;
+  m.GP = groups_per_row;
+  SRF_REQUIRE(m.GP >= 1 && m.GP <= 32, where, "row width must be 4..128 elements");
+  m.inv = (65536u + (unsigned)m.GP - 1u) / (unsigned)m.GP;      // item / GP == (item * inv) >> 16 for item < 1024
+  return 0;
+}
+
 SRF_API int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                                       const int* count, int64_t max_count, const float* box_min, const float* box_size,
                                       const float* const* planes, const float* const* lines, const int* channels,
-                                      const int* resolution, const float* view_dirs, void* rows, void* stream) {
+                                      const int* resolution, const float* view_dirs, void* rows, int row_pitch, void* stream) {
   if (max_count == 0) return 0;
   SRF_REQUIRE(rays_o && rays_d && z && indices && count && view_dirs && rows, "srf_vm_color_features_fwd", "null pointer");
-  VmGeom g; VmGrid t;
+  VmGeom g; VmGrid t; GroupMap m;
   fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_fwd")) return 1;
-  const int CT = channels[0] + channels[1] + channels[2];
-  SRF_REQUIRE(CT + 3 <= COLOR_ROW && CT <= 96, "srf_vm_color_features_fwd", "need sum(C) <= 96");
+  SRF_REQUIRE(row_pitch % 8 == 0 && row_pitch <= 128, "srf_vm_color_features_fwd", "row_pitch must be a multiple of 8, <= 128");
+  if (fill_groups(m, channels, row_pitch / 4, "srf_vm_color_features_fwd")) return 1;
+  SRF_REQUIRE(m.G + 1 <= m.GP, "srf_vm_color_features_fwd", "row_pitch must hold sum(C) + 3 elements");
   vm_color_features_fwd_kernel<<<blocks_for(max_count, CF_WARPS * 32, 16), CF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      g, t, CT, view_dirs, reinterpret_cast<__nv_bfloat16*>(rows));
+      g, t, m, view_dirs, reinterpret_cast<uint2*>(rows));
   return check_launch("srf_vm_color_features_fwd");
 }
 
@@ -640,13 +650,15 @@ SRF_API int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, 
                                       float* const* g_lines, void* stream) {
   if (max_count == 0) return 0;
   SRF_REQUIRE(rays_o && rays_d && z && indices && count && g_rows && g_planes && g_lines, "srf_vm_color_features_bwd", "null pointer");
-  VmGeom g; VmGrid t;
+  VmGeom g; VmGrid t; GroupMap m;
   fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_bwd")) return 1;
   const int CT = channels[0] + channels[1] + channels[2];
-  SRF_REQUIRE(CT <= 96 && g_row_pitch >= CT, "srf_vm_color_features_bwd", "need sum(C) <= 96 and pitch >= sum(C)");
+  SRF_REQUIRE(CT <= 128 && g_row_pitch >= CT && g_row_pitch % 4 == 0, "srf_vm_color_features_bwd",
+              "need sum(C) <= 128 and a pitch >= sum(C) that is a multiple of 4");
+  if (fill_groups(m, channels, CT / 4, "srf_vm_color_features_bwd")) return 1;
   vm_color_features_bwd_kernel<<<blocks_for(max_count, CF_WARPS * 32, 16), CF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      g, t, CT, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+      g, t, m, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
   return check_launch("srf_vm_color_features_bwd");
 }
 

@@ -241,8 +241,8 @@ def build_program(layers, shapes, offs, zero, points_degree, views_degree, head_
 class PackedRowsMLP:
     """The TensoRF colour predictor (reference models/SimpleTensoRF09.py:1389-1393: Linear(F [+3], 128) ReLU
     Linear(128,128) ReLU Linear(128,3) Sigmoid) composed with basis_matrix_color (:1151, :1263, Linear(sum(C), F) without
-    bias): the first tensor-core layer uses W0' = [W0[:, :F] @ B | W0[:, F:]] over the 128-wide bf16 rows
-    [products (sum(C)) | view_dirs (3) | 0] that srf_vm_color_features_fwd writes."""
+    bias): the first tensor-core layer uses W0' = [W0[:, :F] @ B | W0[:, F:]] over the bf16 rows
+    [products (sum(C)) | view_dirs (3) | 0] (8..128 wide) that srf_vm_color_features_fwd writes."""
 
     def __init__(self, num_products, features_dim, num_view=3, prefix='color_predictor.mlp', units=128):
         assert num_products + num_view <= 128 and units == 128
@@ -289,11 +289,11 @@ class PackedRowsMLP:
         return self
 
     def forward(self, rows, count, max_rows):
-        """rows [max_rows, 128] bf16, count int32[1] on the device -> rgb [max_rows, 3] (rows >= count undefined)."""
-        assert rows.dtype == torch.bfloat16 and rows.shape[1] == 128 and rows.is_contiguous()
+        """rows [max_rows, pitch] bf16, count int32[1] on the device -> rgb [max_rows, 3] (rows >= count undefined)."""
+        assert rows.dtype == torch.bfloat16 and rows.shape[1] >= self.in_cols and rows.is_contiguous()
         rgb = torch.empty((max_rows, 3), dtype=torch.float32, device=rows.device)
         L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
-               L.ptr(count), max_rows, L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
+               rows.shape[1], L.ptr(count), max_rows, L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
         return rgb
 
 

@@ -142,18 +142,21 @@ def vm_density(geom, comp, planes, lines, softplus=False, offset=0.0):
     return _VmDensity.apply(geom, comp, softplus, offset, len(planes), *planes, *lines)
 
 
-COLOR_ROW = 128
+def color_row_pitch(num_products):
+    """bf16 elements per colour row: products + 3 view directions, rounded up to one 16-wide MMA K step."""
+    return -(-(num_products + 3) // 16) * 16
 
 
 def vm_color_rows(geom, comp, view_dirs, planes, lines):
-    """rows [total, 128] bf16 = [plane x line products (sum C) | view_dirs (3) | 0], first comp.count rows valid; also
+    """rows [total, pitch] bf16 = [plane x line products (sum C) | view_dirs (3) | 0], first comp.count rows valid; also
     returns the channels-last tables for vm_color_rows_backward.  Not an autograd node by itself: the colour branch
     (gather -> MLP) is one autograd.Function in models/SimpleTensoRF91.py so the bf16 rows never carry a gradient."""
     planes_cl, lines_cl = to_channels_last(planes, lines)
     chans = _i3([p.shape[1] for p in planes])
-    rows = torch.empty((max(comp.total, 1), COLOR_ROW), dtype=torch.bfloat16, device=geom.z.device)
+    pitch = color_row_pitch(sum(p.shape[1] for p in planes))
+    rows = torch.empty((max(comp.total, 1), pitch), dtype=torch.bfloat16, device=geom.z.device)
     L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
-           L.ptr(L.f32c(view_dirs)), L.ptr(rows), L.stream_handle())
+           L.ptr(L.f32c(view_dirs)), L.ptr(rows), pitch, L.stream_handle())
     return rows, (planes_cl, lines_cl, chans)
 
 
