@@ -43,55 +43,87 @@ struct MaskParams {
   int ax, ay, az;                      // alpha-volume resolution
 };
 
+// trilinear grid_sample(align_corners=True, zero padding) of the {0,1} volume is > 0 iff some in-range corner with a
+// positive fp32 weight product holds a 1 (ATen's evaluation order for coordinates and weights is reproduced exactly)
 __device__ __forceinline__ bool alpha_hit(const MaskParams& p, const float (&pt)[3]) {
   const int dims[3] = {p.ax, p.ay, p.az};
-  float ix[3], f0[3];
+  int i0[3];
+  float w[3][2];
+  bool cand[3][2];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    // normalise ((p - b0) / size) * 2 - 1  (:1347-1349), unnormalise ((c + 1) / 2) * (dim - 1) (ATen GridSampler.h)
+    // normalise ((p - b0) / size) * 2 - 1  (:1347-1349), unnormalise ((c + 1) / 2) * (dim - 1) (ATen GridSampler.h);
+    // the division by 2 is an exact scaling, so a multiplication by 0.5 gives the same bits
     const float c = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(pt[a], -p.ab0[a]), p.asize[a]), 2.f), -1.f);
-    ix[a] = __fmul_rn(__fdiv_rn(__fadd_rn(c, 1.f), 2.f), (float)(dims[a] - 1));
-    f0[a] = floorf(ix[a]);
+    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(c, 1.f), 0.5f), (float)(dims[a] - 1));
+    const float f0 = floorf(ix);
+    i0[a] = (int)f0;
+    w[a][0] = __fadd_rn(__fadd_rn(f0, 1.f), -ix);
+    w[a][1] = __fadd_rn(ix, -f0);
+    cand[a][0] = i0[a] >= 0 && i0[a] < dims[a] && w[a][0] > 0.f;
+    cand[a][1] = i0[a] + 1 >= 0 && i0[a] + 1 < dims[a] && w[a][1] > 0.f;
   }
+  const int v0 = (i0[2] * p.ay + i0[1]) * p.ax + i0[0];        // < 2^31 voxels (checked by the host)
+  const int sy = p.ax, sz = p.ax * p.ay;
   bool hit = false;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
-    const int xi = (int)f0[0] + dx, yi = (int)f0[1] + dy, zi = (int)f0[2] + dz;
-    if (xi < 0 || yi < 0 || zi < 0 || xi >= p.ax || yi >= p.ay || zi >= p.az) continue;
-    const float wx = dx ? __fadd_rn(ix[0], -f0[0]) : __fadd_rn(__fadd_rn(f0[0], 1.f), -ix[0]);
-    const float wy = dy ? __fadd_rn(ix[1], -f0[1]) : __fadd_rn(__fadd_rn(f0[1], 1.f), -ix[1]);
-    const float wz = dz ? __fadd_rn(ix[2], -f0[2]) : __fadd_rn(__fadd_rn(f0[2], 1.f), -ix[2]);
-    const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
-    if (w > 0.f) {
-      const long long v = ((long long)zi * p.ay + yi) * p.ax + xi;
-      hit |= (p.alpha_bits[v >> 5] >> (v & 31)) & 1u;
-    }
+    if (!(cand[0][dx] && cand[1][dy] && cand[2][dz])) continue;
+    if (!(__fmul_rn(__fmul_rn(w[0][dx], w[1][dy]), w[2][dz]) > 0.f)) continue;      // the product itself may underflow to 0
+    const int v = v0 + dx + dy * sy + dz * sz;
+    hit |= (__ldg(p.alpha_bits + (v >> 5)) >> (v & 31)) & 1u;
   }
   return hit;
 }
 
+// thread = 4 consecutive samples (normally of one ray): one 16-byte depth load, one 4-byte mask store, ray origin and
+// direction fetched once; the only 64-bit division is one per thread
 __global__ void __launch_bounds__(256) tensorf_mask_kernel(MaskParams p) {
-  const long long base = (long long)blockIdx.x * CMP_BLOCK;
+  const long long i0 = (long long)blockIdx.x * CMP_BLOCK + threadIdx.x * 4;
   int local = 0;
+  if (i0 < p.total) {
+    const int nvalid = (int)min(4LL, p.total - i0);
+    float zz[4];
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(p.z + i0) & 15) == 0) {
+      const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.z + i0));
+      zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+    } else {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long i = base + k * 256 + threadIdx.x;
-    bool ok = false;
-    if (i < p.total) {
-      const long long r = i / p.S;
-      const float zz = p.z[i];
-      float pt[3];
-      ok = true;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        pt[a] = __fadd_rn(p.rays_o[r * 3 + a], __fmul_rn(p.rays_d[r * 3 + a], zz));
-        ok = ok && (p.bb0[a] <= pt[a]) && (pt[a] <= p.bb1[a]);
-      }
-      if (ok && p.alpha_bits != nullptr) ok = alpha_hit(p, pt);
-      p.mask[i] = ok ? 1 : 0;
+      for (int k = 0; k < 4; ++k) zz[k] = k < nvalid ? p.z[i0 + k] : 0.f;
     }
-    local += ok ? 1 : 0;
+    long long r = i0 / p.S;
+    int rem = (int)(i0 - r * p.S);
+    long long loaded = -1;
+    float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nvalid) {
+        while (rem >= p.S) { rem -= p.S; ++r; }
+        if (r != loaded) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { o[a] = __ldg(p.rays_o + r * 3 + a); d[a] = __ldg(p.rays_d + r * 3 + a); }
+          loaded = r;
+        }
+        float pt[3];
+        bool ok = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          pt[a] = __fadd_rn(o[a], __fmul_rn(d[a], zz[k]));
+          ok = ok && (p.bb0[a] <= pt[a]) && (pt[a] <= p.bb1[a]);
+        }
+        if (ok && p.alpha_bits != nullptr) ok = alpha_hit(p, pt);
+        packed |= (ok ? 1u : 0u) << (8 * k);
+        local += ok ? 1 : 0;
+        ++rem;
+      }
+    }
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(p.mask + i0) & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(p.mask + i0) = packed;
+    } else {
+      for (int k = 0; k < nvalid; ++k) p.mask[i0 + k] = (uint8_t)((packed >> (8 * k)) & 1u);
+    }
   }
   __shared__ int s_cnt[8];
   int w = local;
@@ -548,6 +580,8 @@ SRF_API int srf_tensorf_mask(const float* rays_o, const float* rays_d, const flo
   if (alpha_bits) {
     for (int a = 0; a < 3; ++a) { p.ab0[a] = alpha_box_min[a]; p.asize[a] = alpha_box_size[a]; }
     p.ax = alpha_res[0]; p.ay = alpha_res[1]; p.az = alpha_res[2];
+    SRF_REQUIRE(p.ax > 0 && p.ay > 0 && p.az > 0 && (long long)p.ax * p.ay * p.az < (1ll << 31), "srf_tensorf_mask",
+                "alpha volume must hold fewer than 2^31 voxels");
   }
   tensorf_mask_kernel<<<srf_compaction_blocks(p.total), 256, 0, (cudaStream_t)stream>>>(p);
   return check_launch("srf_tensorf_mask");

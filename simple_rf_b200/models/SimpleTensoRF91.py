@@ -171,7 +171,7 @@ class SimpleTensoRF(torch.nn.Module):
                                    viewdirs_from_ndc=True)[4]
         out = {'rays_o': rays_o, 'rays_d': rays_d, 'rays_o_ndc': o_ndc, 'rays_d_ndc': d_ndc, 'view_dirs': view_dirs}
         main = self.coarse_model
-        S = int(main.num_samples)
+        S = main.host_geometry()['num_samples']
         ladder = _coarse_ladder(S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp']).to(dev)
         perturb = self.training and mc['perturb']
         if perturb and self.rng_mode == 'reference':
@@ -374,8 +374,22 @@ class VmDecomposedTensor(torch.nn.Module):
         self.matrices_color, self.vectors_color = self.upsample_vectors_and_matrices(self.matrices_color, self.vectors_color, new_res)
 
     # ---------------------------------------------------------------- forward (:701-761)
+    def host_geometry(self):
+        """Host copies of the box / resolution / sample-count buffers (read once per change, not once per chunk: a
+        `.tolist()` on a device buffer is a stream synchronisation)."""
+        bufs = (self.bounding_box, self.bounding_box_size, self.resolution, self.num_samples)
+        key = tuple((b.data_ptr(), b._version) for b in bufs)
+        cached = getattr(self, '_host_geom', None)
+        if cached is None or cached[0] != key:
+            box = self.bounding_box.tolist()
+            cached = (key, {'box': box, 'box_min': box[0], 'box_size': self.bounding_box_size.tolist(),
+                            'res': [int(v) for v in self.resolution.tolist()], 'num_samples': int(self.num_samples)})
+            self._host_geom = cached
+        return cached[1]
+
     def _geometry(self, rays_o_s, rays_d_s, z):
-        return T.VmGeometry(rays_o_s, rays_d_s, z, self.bounding_box[0], self.bounding_box_size, self.resolution)
+        hg = self.host_geometry()
+        return T.VmGeometry(rays_o_s, rays_d_s, z, hg['box_min'], hg['box_size'], hg['res'])
 
     def forward(self, rays: dict, retraw: bool, white_bkgd=False):
         tc = self.tensor_configs
@@ -383,7 +397,7 @@ class VmDecomposedTensor(torch.nn.Module):
         R, S = z.shape
         so, sd = rays['rays_o_ndc'], rays['rays_d_ndc']
         alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
-        valid = T.validity_compact(so, sd, z, self.bounding_box, alpha)
+        valid = T.validity_compact(so, sd, z, self.host_geometry()['box'], alpha)
         geom = self._geometry(so, sd, z)
         sigma = T.vm_density(geom, valid, list(self.matrices_density), list(self.vectors_density),
                              softplus=self.density_predictor == 'SoftPlus', offset=tc['density_offset'])
@@ -402,8 +416,8 @@ class VmDecomposedTensor(torch.nn.Module):
         rgb = T._ScatterRows.apply(surface, rgb_rows, R * S).view(R, S, 3)
         white = white_bkgd or bool(self.training and (torch.rand((1,)) < 0.5))      # :746
         vr = ops.composite(sigma[..., 0], rgb, z, rays['rays_o'], rays['rays_d'], sd, ndc=True, white_bkgd=white,
-                           distance_scale=tc['distance_scale'], per_sample=True)
-        out = {k: vr[k] for k in ('acc', 'alpha', 'visibility', 'weights', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'rgb')}
+                           distance_scale=tc['distance_scale'], per_sample=retraw)      # alpha / visibility are dropped unless retraw
+        out = {k: vr[k] for k in ('acc', 'alpha', 'visibility', 'weights', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'rgb') if k in vr}
         if retraw:
             out['raw_sigma'] = sigma
             out['raw_rgb'] = rgb

@@ -87,10 +87,23 @@ def threshold_compact(values, threshold):
     return Compacted(mask.view(torch.bool), idx, count, total)
 
 
+_CL_CACHE = {}
+
+
 def to_channels_last(planes, lines):
-    """[1,C,H,W] -> [H,W,C] and [1,C,L,1] -> [L,C] contiguous copies (the derived caches the kernels read)."""
-    return ([p.detach()[0].permute(1, 2, 0).contiguous() for p in planes],
-            [l.detach()[0, :, :, 0].permute(1, 0).contiguous() for l in lines])
+    """[1,C,H,W] -> [H,W,C] and [1,C,L,1] -> [L,C] contiguous copies (the derived caches the kernels read).  Rebuilt only
+    when a parameter's storage or version changes, so the chunks of one frame (and all frames of a test run) share them."""
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (*planes, *lines))
+    slot = (len(planes), planes[0].device, planes[0].shape[1], lines[0].shape[1] if lines else 0, id(planes[0]))
+    hit = _CL_CACHE.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = ([p.detach()[0].permute(1, 2, 0).contiguous() for p in planes],
+           [l.detach()[0, :, :, 0].permute(1, 0).contiguous() for l in lines])
+    if len(_CL_CACHE) > 64:
+        _CL_CACHE.clear()
+    _CL_CACHE[slot] = (key, val)
+    return val
 
 
 class VmGeometry:
