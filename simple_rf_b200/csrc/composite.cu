@@ -24,7 +24,7 @@ struct CompositeFwd {
   const float* rays_d_ndc; // [R,3] (ndc only)
   float* alpha;            // [R,S] or nullptr
   float* visibility;       // [R,S] or nullptr
-  float* weights;          // [R,S] (required: second pass re-reads it)
+  float* weights;          // [R,S]
   float* rgb_map;          // [R,3] or nullptr
   float* acc;              // [R]
   float* depth;            // [R]
@@ -35,12 +35,25 @@ struct CompositeFwd {
   int S;
   int ndc, white_bkgd;
   float distance_scale;
+  int vec;                 // every per-sample pointer is 16-byte aligned: 128-bit loads / stores
 };
 
-// world depth of an NDC depth (CommonUtils04.py:217-223): A * (1/(1 - z + [z==1]*1e-3) - 1) + tn
+// world depth of an NDC depth (CommonUtils04.py:217-223): A * (1/(1 - z + [z==1]*1e-3) - 1) + tn.  The per-ray constants
+// keep IEEE divisions; the per-sample reciprocal is the 1-ulp MUFU approximation (the kernels are issue-bound on exactly
+// this per-sample arithmetic, and the tolerance of this fp32 path is 1e-3).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float ndc_to_world(float zn, float A, float tn) {
   const float eps = zn == 1.f ? 1e-3f : 0.f;
-  return __fadd_rn(__fmul_rn(A, __fadd_rn(__fdiv_rn(1.f, __fadd_rn(__fadd_rn(1.f, -zn), eps)), -1.f)), tn);
+  return fmaf(A, rcp_approx(__fadd_rn(__fadd_rn(1.f, -zn), eps)) - 1.f, tn);
 }
 
 __device__ __forceinline__ float warp_incl_prod(float v, int lane) {
@@ -52,204 +65,238 @@ __device__ __forceinline__ float warp_incl_prod(float v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(CompositeFwd p) {
-  __shared__ float s_rgb[CMP_WARPS][96];
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
-  if (r >= p.R) return;
-  const int S = p.S;
-  const float* sig = p.sigma + r * S;
-  const float* zz = p.z + r * S;
-  float* wout = p.weights + r * S;
+__device__ __forceinline__ void stg_stream4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void stg_stream2(float* p, float a, float b) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 
-  const float* dsrc = p.ndc ? p.rays_d_ndc : p.rays_d;
-  const float dx = dsrc[r * 3 + 0], dy = dsrc[r * 3 + 1], dz = dsrc[r * 3 + 2];
-  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-  const float far_z = p.ndc ? 1.f : 1e10f;
-  float A = 0.f, tn = 0.f;
-  if (p.ndc) {
-    const float oz = p.rays_o[r * 3 + 2], wz = p.rays_d[r * 3 + 2];
-    tn = __fdiv_rn(-__fadd_rn(1.f, oz), wz);
-    A = __fdiv_rn(__fadd_rn(oz, __fmul_rn(tn, wz)), wz);
-  }
-
-  float carry = 1.f;
-  float acc = 0.f, nz = 0.f, nzw = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-  const int chunks = (S + 31) >> 5;
-  for (int c = 0; c < chunks; ++c) {
-    const int i = (c << 5) + lane;
-    const bool ok = i < S;
-    float zi = 0.f, zn = 0.f, sg = 0.f;
-    if (ok) {
-      zi = ldg_stream(zz + i);
-      zn = (i + 1 < S) ? __ldg(zz + i + 1) : far_z;
-      sg = ldg_stream(sig + i);
-    }
-    if (p.rgb != nullptr) {
-      const long long base = (r * S + (c << 5)) * 3;
-      const int lim = min(96, (S - (c << 5)) * 3);
+// N consecutive floats at `src` (N = L or 3 L).  `fast`: the whole run belongs to the ray and the address is aligned
+// to the vector piece (128-bit pieces when N % 4 == 0, else 64-bit; L1-allocating loads, because a lane's pieces of
+// the 3 L-wide rgb run share sectors with its neighbours').  Otherwise element k is read iff its local index
+// i0 + k / PER lies in [0, S).
+template <int N, int PER>
+__device__ __forceinline__ void load_run(const float* src, bool fast, int i0, int S, float (&v)[N]) {
+  if (fast) {
+    if (N % 4 == 0) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int e = k * 32 + lane;
-        if (e < lim) s_rgb[warp][e] = ldg_stream(p.rgb + base + e);
+      for (int k = 0; k < N / 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src) + k);
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
       }
-    }
-    const float delta = (zn - zi) * nrm;
-    const float al = ok ? 1.f - expf(-sg * delta * p.distance_scale) : 0.f;
-    const float q = ok ? (1.f - al + 1e-10f) : 1.f;
-    const float incl = warp_incl_prod(q, lane);
-    float excl = __shfl_up_sync(FULL, incl, 1);
-    if (lane == 0) excl = 1.f;
-    const float T = carry * excl;
-    carry *= __shfl_sync(FULL, incl, 31);
-    const float w = al * T;
-    __syncwarp();
-    if (ok) {
-      stg_stream(wout + i, w);
-      if (p.alpha) stg_stream(p.alpha + r * S + i, al);
-      if (p.visibility) stg_stream(p.visibility + r * S + i, T);
-      acc += w;
-      nz += w * zi;
-      if (p.ndc) nzw += w * ndc_to_world(zi, A, tn);
-      if (p.rgb != nullptr) {
-        c0 += w * s_rgb[warp][lane * 3 + 0];
-        c1 += w * s_rgb[warp][lane * 3 + 1];
-        c2 += w * s_rgb[warp][lane * 3 + 2];
-      }
-    }
-    __syncwarp();
-  }
-  acc = warp_sum(acc);
-  nz = warp_sum(nz);
-  const float inv = 1.f / (acc + 1e-6f);
-  const float d_main = nz * inv;          // NDC depth when ndc, world depth otherwise
-  float d_world = d_main;
-  if (p.ndc) d_world = warp_sum(nzw) * inv;
-  // second pass: variances (each lane re-reads exactly the weights it wrote)
-  float v_main = 0.f, v_world = 0.f;
-  for (int i = lane; i < S; i += 32) {
-    const float w = wout[i];
-    const float zi = __ldg(zz + i);
-    const float a = zi - d_main;
-    v_main += w * a * a;
-    if (p.ndc) {
-      const float b = ndc_to_world(zi, A, tn) - d_world;
-      v_world += w * b * b;
-    }
-  }
-  v_main = warp_sum(v_main);
-  if (p.ndc) v_world = warp_sum(v_world);
-  if (p.rgb_map != nullptr) {
-    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
-    if (p.white_bkgd) { const float bg = 1.f - acc; c0 += bg; c1 += bg; c2 += bg; }
-  }
-  if (lane == 0) {
-    p.acc[r] = acc;
-    if (p.ndc) {
-      p.depth_ndc[r] = d_main;
-      p.depth_var_ndc[r] = v_main;
-      p.depth[r] = d_world;
-      p.depth_var[r] = v_world;
     } else {
-      p.depth[r] = d_main;
-      p.depth_var[r] = v_main;
+#pragma unroll
+      for (int k = 0; k < N / 2; ++k) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(src) + k);
+        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+      }
     }
-    if (p.rgb_map != nullptr) { p.rgb_map[r * 3 + 0] = c0; p.rgb_map[r * 3 + 1] = c1; p.rgb_map[r * 3 + 2] = c2; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = (unsigned)(i0 + k / PER) < (unsigned)S ? __ldg(src + k) : 0.f;
   }
 }
 
-// Rays of at most 32*K samples (the Simple-NeRF shapes: 64 coarse, 192 fine): every load of the ray is issued
-// before any arithmetic (K*(2+3) independent loads in flight per lane), weights and depths stay in registers for
-// the variance pass, and the successor depth comes from a shuffle instead of a second load.
-template <int K>
-__global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_small_kernel(CompositeFwd p) {
-  __shared__ float s_rgb[CMP_WARPS][K * 96];
+template <int N, int PER>
+__device__ __forceinline__ void store_run(float* dst, bool fast, int i0, int S, const float (&v)[N]) {
+  if (fast) {
+    if (N % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < N / 4; ++k) stg_stream4(dst + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < N / 2; ++k) stg_stream2(dst + 2 * k, v[2 * k], v[2 * k + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if ((unsigned)(i0 + k / PER) < (unsigned)S) stg_stream(dst + k, v[k]);
+  }
+}
+
+// Sums of 8 per-lane values over the warp in 4 + 2 + 1 + 2 = 9 shuffles (instead of 8 x 5): each exchange step halves
+// the number of values a lane carries.  On return lane 4k (k = 0..7) holds the total of value k.
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  float a[4], b[2], c;
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = u16 ? v[k] : v[k + 4];
+    const float keep = u16 ? v[k + 4] : v[k];
+    a[k] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = u8 ? a[k] : a[k + 2];
+    const float keep = u8 ? a[k + 2] : a[k];
+    b[k] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+  {
+    const float send = u4 ? b[0] : b[1];
+    const float keep = u4 ? b[1] : b[0];
+    c = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  c += __shfl_xor_sync(FULL, c, 2);
+  c += __shfl_xor_sync(FULL, c, 1);
+  return c;
+}
+// two values in 1 + 4 shuffles: lanes 0..15 end with the total of x, lanes 16..31 with the total of y
+__device__ __forceinline__ float warp_reduce2(float x, float y, int lane) {
+  const bool u16 = lane & 16;
+  float c = (u16 ? y : x) + __shfl_xor_sync(FULL, u16 ? x : y, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  return c;
+}
+
+struct RayConsts { float nrm, far_z, A, tn; };
+
+template <typename P>
+__device__ __forceinline__ RayConsts ray_consts(const P& p, long long r) {
+  RayConsts k;
+  const float* dsrc = p.ndc ? p.rays_d_ndc : p.rays_d;
+  const float dx = dsrc[r * 3 + 0], dy = dsrc[r * 3 + 1], dz = dsrc[r * 3 + 2];
+  k.nrm = sqrt_approx(dx * dx + dy * dy + dz * dz);
+  k.far_z = p.ndc ? 1.f : 1e10f;
+  k.A = 0.f; k.tn = 0.f;
+  if (p.ndc) {
+    const float oz = p.rays_o[r * 3 + 2], wz = p.rays_d[r * 3 + 2];
+    const float iw = rcp_approx(wz);
+    k.tn = -(1.f + oz) * iw;
+    k.A = (oz + k.tn * wz) * iw;
+  }
+  return k;
+}
+
+// Forward.  One warp per ray; a lane owns RUNS of L consecutive samples (32 L samples per warp step): vector loads per
+// input array and run ([R,S,3] rgb needs no shared-memory transpose this way), the transmittance product is sequential
+// inside the run with ONE 5-step shuffle scan per step across lanes, and the per-ray sums are reduced once at the end
+// with the multi-value butterfly above.  Runs are aligned in the FLAT [R*S] arrays, so any S (e.g. TensoRF's 1083)
+// vectorises: elements of the neighbouring rays that fall into a ray's first / last run are loaded but masked.
+// L is chosen by the host so that the steps cover S with few idle lanes (64 -> 2, 128 -> 4, 192 -> 6, 256 -> 8).
+// NC > 0: at most NC steps, weights and depths stay in registers for the variance pass; NC == 0: any length, the
+// variance pass re-reads what the lane wrote.
+template <int L, int NC>
+__global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(CompositeFwd p) {
+  constexpr int G = L % 4 == 0 ? 4 : 2;          // alignment granule of a run (floats)
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
   if (r >= p.R) return;
   const int S = p.S;
-  const float* sig = p.sigma + r * S;
-  const float* zz = p.z + r * S;
-  const float far_z = p.ndc ? 1.f : 1e10f;
-  float sg[K], zi[K];
+  const long long first = r * S;
+  const int lead = (int)(first & (G - 1));       // elements of the previous ray in this ray's first run
+  const int nchunks = (lead + S + 32 * L - 1) / (32 * L);
+  const RayConsts k = ray_consts(p, r);
+  const bool vec = p.vec != 0;
+  const bool has_rgb = p.rgb != nullptr;
+  const float ns = k.nrm * p.distance_scale;
+
+  float carry = 1.f;
+  float red[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // acc, sum w z, sum w z_world, r, g, b
+  constexpr int KEEP = NC > 0 ? NC : 1;
+  float wk[KEEP][L], zk[KEEP][L], zwk[KEEP][L];
+
+  auto step = [&](int c, float (&w)[L], float (&zi)[L], float (&zw)[L]) {
+    const int i0 = c * 32 * L + lane * L - lead;              // local index of the run's first element
+    const long long e0 = first + i0;
+    const bool fast = vec && i0 >= 0 && i0 + L <= S;
+    float sg[L], col[3 * L];
+    load_run<L, 1>(p.sigma + e0, fast, i0, S, sg);
+    load_run<L, 1>(p.z + e0, fast, i0, S, zi);
+    if (has_rgb) load_run<3 * L, 3>(p.rgb + e0 * 3, fast, i0, S, col);
+    float znext = __shfl_down_sync(FULL, zi[0], 1);
+    if (lane == 31) znext = (i0 + L < S) ? __ldg(p.z + e0 + L) : k.far_z;
+    float q[L], al[L];
+    float P = 1.f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int i = (k << 5) + lane;
-    sg[k] = i < S ? ldg_stream(sig + i) : 0.f;
-    zi[k] = i < S ? ldg_stream(zz + i) : far_z;
-  }
-  if (p.rgb != nullptr) {
-    const float* src = p.rgb + r * S * 3;
-#pragma unroll
-    for (int k = 0; k < 3 * K; ++k) {
-      const int e = (k << 5) + lane;
-      if (e < S * 3) s_rgb[warp][e] = ldg_stream(src + e);
+    for (int j = 0; j < L; ++j) {
+      const int i = i0 + j;
+      const bool ok = (unsigned)i < (unsigned)S;
+      float zn = j < L - 1 ? zi[j < L - 1 ? j + 1 : j] : znext;
+      if (i + 1 >= S) zn = k.far_z;
+      const float ex = __expf(-sg[j] * ((zn - zi[j]) * ns));
+      al[j] = ok ? 1.f - ex : 0.f;
+      q[j] = ok ? (1.f - al[j] + 1e-10f) : 1.f;
+      P *= q[j];
     }
-  }
-  const float* dsrc = p.ndc ? p.rays_d_ndc : p.rays_d;
-  const float dx = dsrc[r * 3 + 0], dy = dsrc[r * 3 + 1], dz = dsrc[r * 3 + 2];
-  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-  float A = 0.f, tn = 0.f;
-  if (p.ndc) {
-    const float oz = p.rays_o[r * 3 + 2], wz = p.rays_d[r * 3 + 2];
-    tn = __fdiv_rn(-__fadd_rn(1.f, oz), wz);
-    A = __fdiv_rn(__fadd_rn(oz, __fmul_rn(tn, wz)), wz);
-  }
-  __syncwarp();
-  float carry = 1.f, acc = 0.f, nz = 0.f, nzw = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-  float w[K], zw[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int i = (k << 5) + lane;
-    const bool ok = i < S;
-    float zn = __shfl_down_sync(FULL, zi[k], 1);
-    const float head_next = (k + 1 < K) ? __shfl_sync(FULL, zi[(k + 1 < K) ? k + 1 : k], 0) : far_z;
-    if (lane == 31) zn = head_next;
-    if (i >= S - 1) zn = far_z;
-    const float delta = (zn - zi[k]) * nrm;
-    const float al = ok ? 1.f - expf(-sg[k] * delta * p.distance_scale) : 0.f;
-    const float q = ok ? (1.f - al + 1e-10f) : 1.f;
-    const float incl = warp_incl_prod(q, lane);
+    const float incl = warp_incl_prod(P, lane);
     float excl = __shfl_up_sync(FULL, incl, 1);
     if (lane == 0) excl = 1.f;
-    const float T = carry * excl;
+    float T = carry * excl;
     carry *= __shfl_sync(FULL, incl, 31);
-    w[k] = ok ? al * T : 0.f;
-    zw[k] = p.ndc ? ndc_to_world(zi[k], A, tn) : zi[k];
-    if (ok) {
-      stg_stream(p.weights + r * S + i, w[k]);
-      if (p.alpha) stg_stream(p.alpha + r * S + i, al);
-      if (p.visibility) stg_stream(p.visibility + r * S + i, T);
-      acc += w[k];
-      nz += w[k] * zi[k];
-      nzw += w[k] * zw[k];
-      if (p.rgb != nullptr) {
-        c0 += w[k] * s_rgb[warp][i * 3 + 0];
-        c1 += w[k] * s_rgb[warp][i * 3 + 1];
-        c2 += w[k] * s_rgb[warp][i * 3 + 2];
+    float vis[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      vis[j] = T;
+      w[j] = al[j] * T;                 // 0 for masked elements (al = 0)
+      T *= q[j];
+      red[0] += w[j];
+      red[1] += w[j] * zi[j];
+      zw[j] = 0.f;
+      if (p.ndc) {
+        zw[j] = ndc_to_world(zi[j], k.A, k.tn);
+        red[2] += w[j] * zw[j];
+      }
+      if (has_rgb) {
+        red[3] += w[j] * col[3 * j + 0];
+        red[4] += w[j] * col[3 * j + 1];
+        red[5] += w[j] * col[3 * j + 2];
+      }
+    }
+    store_run<L, 1>(p.weights + e0, fast, i0, S, w);
+    if (p.alpha) store_run<L, 1>(p.alpha + e0, fast, i0, S, al);
+    if (p.visibility) store_run<L, 1>(p.visibility + e0, fast, i0, S, vis);
+  };
+
+  if (NC > 0) {               // unconditional: a step beyond the ray is fully masked (no loads, no stores)
+#pragma unroll
+    for (int c = 0; c < KEEP; ++c) step(c, wk[c], zk[c], zwk[c]);
+  } else {
+    for (int c = 0; c < nchunks; ++c) step(c, wk[0], zk[0], zwk[0]);
+  }
+
+  const float mine = warp_reduce8(red, lane);
+  const float acc = __shfl_sync(FULL, mine, 0), nz = __shfl_sync(FULL, mine, 4), nzw = __shfl_sync(FULL, mine, 8);
+  float c0 = __shfl_sync(FULL, mine, 12), c1 = __shfl_sync(FULL, mine, 16), c2 = __shfl_sync(FULL, mine, 20);
+  const float inv = rcp_approx(acc + 1e-6f);
+  const float d_main = nz * inv;          // NDC depth when ndc, world depth otherwise
+  const float d_world = p.ndc ? nzw * inv : d_main;
+  // variances around the means (each lane handles exactly the runs it produced)
+  float v_main = 0.f, v_world = 0.f;
+  if (NC > 0) {
+#pragma unroll
+    for (int c = 0; c < KEEP; ++c)
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const float a = zk[c][j] - d_main;
+        v_main += wk[c][j] * a * a;
+        if (p.ndc) {
+          const float b = zwk[c][j] - d_world;
+          v_world += wk[c][j] * b * b;
+        }
+      }
+  } else {
+    for (int c = 0; c < nchunks; ++c) {
+      const int i0 = c * 32 * L + lane * L - lead;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {            // plain loads: the weights were written by this thread in this kernel
+        const int i = i0 + j;
+        const bool ok = (unsigned)i < (unsigned)S;
+        const float w = ok ? p.weights[first + i] : 0.f;
+        const float zi = ok ? __ldg(p.z + first + i) : 0.f;
+        const float a = zi - d_main;
+        v_main += w * a * a;
+        if (p.ndc) {
+          const float b = ndc_to_world(zi, k.A, k.tn) - d_world;
+          v_world += w * b * b;
+        }
       }
     }
   }
-  acc = warp_sum(acc);
-  nz = warp_sum(nz);
-  const float inv = 1.f / (acc + 1e-6f);
-  const float d_main = nz * inv;
-  float d_world = d_main;
-  if (p.ndc) d_world = warp_sum(nzw) * inv;
-  float v_main = 0.f, v_world = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const float a = zi[k] - d_main;
-    v_main += w[k] * a * a;
-    const float b = zw[k] - d_world;
-    v_world += w[k] * b * b;
-  }
-  v_main = warp_sum(v_main);
-  if (p.ndc) v_world = warp_sum(v_world);
-  if (p.rgb_map != nullptr) {
-    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
-    if (p.white_bkgd) { const float bg = 1.f - acc; c0 += bg; c1 += bg; c2 += bg; }
-  }
+  const float vv = warp_reduce2(v_main, v_world, lane);
+  v_main = __shfl_sync(FULL, vv, 0);
+  v_world = __shfl_sync(FULL, vv, 16);
   if (lane == 0) {
     p.acc[r] = acc;
     if (p.ndc) {
@@ -257,7 +304,10 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_small_kernel(Com
     } else {
       p.depth[r] = d_main; p.depth_var[r] = v_main;
     }
-    if (p.rgb_map != nullptr) { p.rgb_map[r * 3 + 0] = c0; p.rgb_map[r * 3 + 1] = c1; p.rgb_map[r * 3 + 2] = c2; }
+    if (p.rgb_map != nullptr) {
+      if (p.white_bkgd) { const float bg = 1.f - acc; c0 += bg; c1 += bg; c2 += bg; }
+      p.rgb_map[r * 3 + 0] = c0; p.rgb_map[r * 3 + 1] = c1; p.rgb_map[r * 3 + 2] = c2;
+    }
   }
 }
 
@@ -278,30 +328,27 @@ struct CompositeBwd {
   int S;
   int ndc, white_bkgd;
   float distance_scale;
+  int vec;
 };
 
+// Backward: one reverse pass with the same run layout; sum_{k>i} g_w[k] w_k is a sequential suffix sum inside the run
+// plus one shuffle suffix scan per step (closed form in oracle/composite.py).
+template <int L>
 __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(CompositeBwd p) {
-  __shared__ float s_rgb[CMP_WARPS][96];
+  constexpr int G = L % 4 == 0 ? 4 : 2;
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
   if (r >= p.R) return;
   const int S = p.S;
-  const float* sig = p.sigma + r * S;
-  const float* zz = p.z + r * S;
-  const float* vis = p.visibility + r * S;
+  const long long first = r * S;
+  const int lead = (int)(first & (G - 1));
+  const int nchunks = (lead + S + 32 * L - 1) / (32 * L);
+  const RayConsts k = ray_consts(p, r);
+  const bool vec = p.vec != 0;
+  const float ns = k.nrm * p.distance_scale;
 
-  const float* dsrc = p.ndc ? p.rays_d_ndc : p.rays_d;
-  const float dx = dsrc[r * 3 + 0], dy = dsrc[r * 3 + 1], dz = dsrc[r * 3 + 2];
-  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-  const float far_z = p.ndc ? 1.f : 1e10f;
-  float A = 0.f, tn = 0.f;
-  if (p.ndc) {
-    const float oz = p.rays_o[r * 3 + 2], wz = p.rays_d[r * 3 + 2];
-    tn = __fdiv_rn(-__fadd_rn(1.f, oz), wz);
-    A = __fdiv_rn(__fadd_rn(oz, __fmul_rn(tn, wz)), wz);
-  }
   const float acc = p.acc[r];
-  const float invA = 1.f / (acc + 1e-6f);
+  const float invA = rcp_approx(acc + 1e-6f);
   const float d_world = p.depth[r];
   const float d_ndc = p.ndc ? p.depth_ndc[r] : 0.f;
   float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
@@ -316,81 +363,105 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(Composite
   // N - depth*acc = depth*(acc+1e-6) - depth*acc = depth*1e-6 (exactly the forward's N)
   const float kv_world = 2.f * (d_world * 1e-6f) * invA;
   const float kv_ndc = 2.f * (d_ndc * 1e-6f) * invA;
-
-  float carry = 0.f;    // sum_{k > current chunk} g_w[k] w_k
-  const int chunks = (S + 31) >> 5;
   const bool has_rgb = p.rgb != nullptr && p.g_rgb != nullptr;
-  for (int c = chunks - 1; c >= 0; --c) {
-    const int i = (c << 5) + lane;
-    const bool ok = i < S;
-    float zi = 0.f, zn = 0.f, sg = 0.f, T = 0.f;
-    if (ok) {
-      zi = ldg_stream(zz + i);
-      zn = (i + 1 < S) ? __ldg(zz + i + 1) : far_z;
-      sg = ldg_stream(sig + i);
-      T = ldg_stream(vis + i);
-    }
-    const long long base = (r * S + (c << 5)) * 3;
-    const int lim = min(96, (S - (c << 5)) * 3);
-    if (has_rgb) {
+  const bool depth_main = gd_ndc != 0.f || gv_ndc != 0.f;                 // warp-uniform: skip unused depth terms
+  const bool depth_world = gd_world != 0.f || gv_world != 0.f;
+
+  float carry = 0.f;    // sum over the samples of later steps of g_w[k] w_k
+  for (int c = nchunks - 1; c >= 0; --c) {
+    const int i0 = c * 32 * L + lane * L - lead;
+    const long long e0 = first + i0;
+    const bool fast = vec && i0 >= 0 && i0 + L <= S;
+    float sg[L], zi[L], T[L], col[3 * L], gwt[L];
+    load_run<L, 1>(p.sigma + e0, fast, i0, S, sg);
+    load_run<L, 1>(p.z + e0, fast, i0, S, zi);
+    load_run<L, 1>(p.visibility + e0, fast, i0, S, T);
+    if (has_rgb) load_run<3 * L, 3>(p.rgb + e0 * 3, fast, i0, S, col);
+    if (p.g_weights) load_run<L, 1>(p.g_weights + e0, fast, i0, S, gwt);
+    float znext = __shfl_down_sync(FULL, zi[0], 1);
+    if (lane == 31) znext = (i0 + L < S) ? __ldg(p.z + e0 + L) : k.far_z;
+    float gw[L], gww[L], w[L], q[L], de[L];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int e = k * 32 + lane;
-        if (e < lim) s_rgb[warp][e] = ldg_stream(p.rgb + base + e);
+    for (int j = 0; j < L; ++j) {
+      const int i = i0 + j;
+      const bool ok = (unsigned)i < (unsigned)S;
+      float zn = j < L - 1 ? zi[j < L - 1 ? j + 1 : j] : znext;
+      if (i + 1 >= S) zn = k.far_z;
+      const float dscale = (zn - zi[j]) * ns;
+      const float ex = ok ? __expf(-sg[j] * dscale) : 1.f;
+      const float al = 1.f - ex;
+      q[j] = al == 1.f ? 1e-10f : (1.f - al + 1e-10f);
+      w[j] = ok ? al * T[j] : 0.f;
+      de[j] = dscale * ex;
+      float g = g_acc;
+      if (p.g_weights) g += gwt[j];
+      if (has_rgb) g += gr0 * col[3 * j + 0] + gr1 * col[3 * j + 1] + gr2 * col[3 * j + 2];
+      if (p.ndc) {
+        if (depth_main) {
+          const float a = zi[j] - d_ndc;
+          g += gd_ndc * a * invA + gv_ndc * (a * a - kv_ndc * a);
+        }
+        if (depth_world) {
+          const float b = ndc_to_world(zi[j], k.A, k.tn) - d_world;
+          g += gd_world * b * invA + gv_world * (b * b - kv_world * b);
+        }
+      } else if (depth_world) {
+        const float b = zi[j] - d_world;
+        g += gd_world * b * invA + gv_world * (b * b - kv_world * b);
       }
+      gw[j] = g;
+      gww[j] = ok ? g * w[j] : 0.f;
     }
-    __syncwarp();
-    const float dscale = (zn - zi) * nrm * p.distance_scale;
-    const float e = ok ? expf(-sg * dscale) : 1.f;
-    const float al = 1.f - e;
-    const float q = al == 1.f ? 1e-10f : (1.f - al + 1e-10f);
-    const float w = al * T;
-    float gw = g_acc;
-    if (p.g_weights && ok) gw += ldg_stream(p.g_weights + r * S + i);
-    if (has_rgb && ok)
-      gw += gr0 * s_rgb[warp][lane * 3 + 0] + gr1 * s_rgb[warp][lane * 3 + 1] + gr2 * s_rgb[warp][lane * 3 + 2];
-    if (p.ndc) {
-      const float a = zi - d_ndc;
-      gw += gd_ndc * a * invA + gv_ndc * (a * a - kv_ndc * a);
-      const float b = ndc_to_world(zi, A, tn) - d_world;
-      gw += gd_world * b * invA + gv_world * (b * b - kv_world * b);
-    } else {
-      const float b = zi - d_world;
-      gw += gd_world * b * invA + gv_world * (b * b - kv_world * b);
-    }
-    const float gww = ok ? gw * w : 0.f;
-    // inclusive suffix sum within the chunk (towards higher lanes)
-    float suf = gww;
+    // suffix sums: after[j] = sum of gww over the later elements of this run
+    float after[L];
+    after[L - 1] = 0.f;
+#pragma unroll
+    for (int j = L - 2; j >= 0; --j) after[j] = after[j + 1] + gww[j + 1];
+    const float tot = after[0] + gww[0];
+    float suf = tot;      // inclusive suffix sum over lanes (towards higher lanes)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const float t = __shfl_down_sync(FULL, suf, o);
       if (lane + o < 32) suf += t;
     }
-    const float later = carry + (suf - gww);     // sum over k > i
+    const float base_later = carry + (suf - tot);
     carry += __shfl_sync(FULL, suf, 0);
-    const float g_alpha = gw * T - later / q;
-    __syncwarp();
-    if (ok) stg_stream(p.g_sigma + r * S + i, g_alpha * (dscale * e));
-    if (p.g_rgb_s != nullptr) {
-      if (ok) {
-        s_rgb[warp][lane * 3 + 0] = w * gr0;
-        s_rgb[warp][lane * 3 + 1] = w * gr1;
-        s_rgb[warp][lane * 3 + 2] = w * gr2;
-      }
-      __syncwarp();
+    float gs[L];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int e2 = k * 32 + lane;
-        if (e2 < lim) stg_stream(p.g_rgb_s + base + e2, s_rgb[warp][e2]);
-      }
+    for (int j = 0; j < L; ++j) {
+      const float later = base_later + after[j];
+      const float g_alpha = gw[j] * T[j] - __fdividef(later, q[j]);
+      gs[j] = g_alpha * de[j];
     }
-    __syncwarp();
+    store_run<L, 1>(p.g_sigma + e0, fast, i0, S, gs);
+    if (p.g_rgb_s != nullptr) {
+      float gc[3 * L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) { gc[3 * j] = w[j] * gr0; gc[3 * j + 1] = w[j] * gr1; gc[3 * j + 2] = w[j] * gr2; }
+      store_run<3 * L, 3>(p.g_rgb_s + e0 * 3, fast, i0, S, gc);
+    }
   }
 }
 
 }  // namespace srf
 
 using namespace srf;
+
+// samples per lane and step: 2 (64 per warp step, 64-bit pieces) or 4 (128 per step, 128-bit pieces) - whichever
+// covers the ray with fewer idle lane slots; longer runs win unless they idle more than 15 % extra (fewer scans).
+// Every piece a lane loads or stores is contiguous with its neighbours', so all accesses are fully coalesced.
+static int run_length(int S) {
+  const long long s2 = (long long)((S + (S % 2) + 63) / 64) * 64;
+  const long long s4 = (long long)((S + (S % 4 ? 3 : 0) + 127) / 128) * 128;
+  return s4 * 100 <= s2 * 115 ? 4 : 2;
+}
+
+template <typename... Ts>
+static int aligned16(const Ts*... ptrs) {
+  uintptr_t bits = 0;
+  for (const void* q : {static_cast<const void*>(ptrs)...}) bits |= reinterpret_cast<uintptr_t>(q);     // nullptr contributes nothing
+  return (bits & 15) == 0 ? 1 : 0;
+}
 
 SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float* z, const float* rays_o,
                               const float* rays_d, const float* rays_d_ndc, int64_t num_rays, int num_samples,
@@ -403,12 +474,27 @@ SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float*
               "ndc needs rays_o, rays_d_ndc, depth_ndc, depth_var_ndc");
   SRF_REQUIRE((rgb == nullptr) == (rgb_map == nullptr), "srf_composite_fwd", "rgb and rgb_map go together");
   SRF_REQUIRE(num_samples > 0 && num_rays >= 0, "srf_composite_fwd", "bad sizes");
+  const int vec = aligned16(sigma, rgb, z, alpha, visibility, weights);
   CompositeFwd p{sigma, rgb, z, rays_o, rays_d, rays_d_ndc, alpha, visibility, weights, rgb_map, acc, depth,
-                 depth_var, depth_ndc, depth_var_ndc, num_rays, num_samples, ndc, white_bkgd, distance_scale};
+                 depth_var, depth_ndc, depth_var_ndc, num_rays, num_samples, ndc, white_bkgd, distance_scale, vec};
   const unsigned blocks = (unsigned)((num_rays + CMP_WARPS - 1) / CMP_WARPS);
-  if (num_samples <= 64) composite_fwd_small_kernel<2><<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
-  else if (num_samples <= 192) composite_fwd_small_kernel<6><<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
-  else composite_fwd_kernel<<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  const dim3 blk(CMP_WARPS * 32);
+  const cudaStream_t st = (cudaStream_t)stream;
+  const int L = run_length(num_samples);
+  const int G = L == 4 ? 4 : 2;
+  const int span = num_samples + (num_samples % G != 0 ? G - 1 : 0);       // worst case with the leading partial run
+  const int steps = (span + 32 * L - 1) / (32 * L);
+  if (L == 2) {
+    if (steps <= 1) composite_fwd_kernel<2, 1><<<blocks, blk, 0, st>>>(p);
+    else if (steps <= 2) composite_fwd_kernel<2, 2><<<blocks, blk, 0, st>>>(p);
+    else if (steps <= 3) composite_fwd_kernel<2, 3><<<blocks, blk, 0, st>>>(p);
+    else composite_fwd_kernel<2, 0><<<blocks, blk, 0, st>>>(p);
+  } else {
+    if (steps <= 1) composite_fwd_kernel<4, 1><<<blocks, blk, 0, st>>>(p);
+    else if (steps <= 2) composite_fwd_kernel<4, 2><<<blocks, blk, 0, st>>>(p);
+    else if (steps <= 4) composite_fwd_kernel<4, 4><<<blocks, blk, 0, st>>>(p);
+    else composite_fwd_kernel<4, 0><<<blocks, blk, 0, st>>>(p);
+  }
   return check_launch("srf_composite_fwd");
 }
 
@@ -426,8 +512,9 @@ SRF_API int srf_composite_bwd(const float* sigma, const float* rgb, const float*
   SRF_REQUIRE(num_samples > 0 && num_rays >= 0, "srf_composite_bwd", "bad sizes");
   CompositeBwd p{sigma, rgb, z, visibility, rays_o, rays_d, rays_d_ndc, acc, depth, depth_ndc, g_rgb, g_acc, g_depth,
                  g_depth_ndc, g_depth_var, g_depth_var_ndc, g_weights, g_sigma, g_rgb_samples, num_rays, num_samples,
-                 ndc, white_bkgd, distance_scale};
+                 ndc, white_bkgd, distance_scale, aligned16(sigma, rgb, z, visibility, g_weights, g_sigma, g_rgb_samples)};
   const unsigned blocks = (unsigned)((num_rays + CMP_WARPS - 1) / CMP_WARPS);
-  composite_bwd_kernel<<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  if (run_length(num_samples) == 2) composite_bwd_kernel<2><<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  else composite_bwd_kernel<4><<<blocks, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   return check_launch("srf_composite_bwd");
 }
