@@ -187,7 +187,7 @@ int srf_gather_rows(const int* indices, const int* count, int64_t max_count, con
  * precomputed bf16 rows [max_rows, row_pitch] (columns 0..63 / 64..row_pitch-1, zero beyond) instead of encodings (views_degree = -2 in the
  * program; -1 when only region 0 is used); the row count is read from the device. */
 int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, int row_pitch, const int* count,
-                     int64_t max_rows, float* rgb, void* stream);
+                     int64_t max_rows, float* rgb, void* save_acts, int act_slots, int e_slot, int v_slot, void* stream);
 
 /* Weight gradients of the fused MLP (what autograd derives for the nn.Linear layers of
  * src/models/SimpleNeRF17.py:644-666): dW = dZ^T X and db = colsum(dZ) on tcgen05, K = samples.  `acts` are the
@@ -210,9 +210,13 @@ int srf_wgrad_item_bytes(void);
  * transposed weights streamed as swizzled images ([layer][128-row half of the 256 inputs][K block of outputs]).
  * Reads the saved activation tiles (their non-zero pattern is the ReLU mask) and the sigma / rgb outputs of
  * srf_nerf_mlp_fwd; writes every layer's pre-activation
- * gradient as tile images into dz [tile][dz_slots][16 KB] for srf_nerf_mlp_wgrad. */
+ * gradient as tile images into dz [tile][dz_slots][16 KB] for srf_nerf_mlp_wgrad.
+ * Every backward layer has its own output width n_out (128 or 256).  The TensoRF colour MLP
+ * (src/models/SimpleTensoRF09.py:1389-1393, srf_mlp_rows_fwd) uses the same chain with 128-wide layers; its last layer
+ * sets dz_slot = -1 and rows_cols = sum(C): the gradient of the product rows is written as fp32 g_rows [M, g_row_pitch]
+ * for srf_vm_color_features_bwd. */
 typedef struct {
-  int32_t num_kblocks, mask_slot, rank1_offset, dz_slot;
+  int32_t num_kblocks, mask_slot, rank1_offset, dz_slot, n_out, rows_cols;
   int64_t weight_offset;
 } srf_dgrad_layer;
 typedef struct {
@@ -221,7 +225,7 @@ typedef struct {
 } srf_dgrad_program;
 int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const void* acts, int act_slots,
                        const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
-                       void* dz, int dz_slots, void* stream);
+                       void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream);
 int srf_dgrad_program_bytes(void);
 
 #ifdef __cplusplus

@@ -571,7 +571,8 @@ SRF_API int srf_nerf_mlp_fwd(const void* program, const void* weights, const flo
 }
 
 SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side, const void* rows, int row_pitch,
-                             const int* count, int64_t max_rows, float* rgb, void* stream) {
+                             const int* count, int64_t max_rows, float* rgb, void* save_acts, int act_slots, int e_slot, int v_slot,
+                             void* stream) {
   if (max_rows == 0) return 0;
   SRF_REQUIRE(program && weights && side && rows && rgb, "srf_mlp_rows_fwd", "null pointer");
   MlpProgram prog = *reinterpret_cast<const MlpProgram*>(program);
@@ -583,6 +584,10 @@ SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const flo
   a.side = side; a.rows = reinterpret_cast<const uint4*>(rows); a.count = count; a.rgb = rgb;
   SRF_REQUIRE(row_pitch % 8 == 0 && row_pitch >= 8 && row_pitch <= 128 && (prog.views_degree == -2 || row_pitch <= 64), "srf_mlp_rows_fwd",
               "row_pitch must be a multiple of 8 in 8..128 (<= 64 for a one-block program)");
+  SRF_REQUIRE(save_acts == nullptr || (act_slots > 0 && e_slot >= 0 && e_slot < act_slots && v_slot < act_slots), "srf_mlp_rows_fwd",
+              "bad saved-tile slots");
+  a.save_acts = reinterpret_cast<uint8_t*>(save_acts);
+  a.act_slots = act_slots; a.e_slot = e_slot; a.v_slot = v_slot;
   a.row_units = row_pitch / 8;
   a.total = max_rows;
   a.S = 1;

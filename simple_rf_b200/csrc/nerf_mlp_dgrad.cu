@@ -23,7 +23,9 @@ struct DgradLayer {           // mirrors srf_dgrad_layer in include/simple_rf_b2
   int32_t num_kblocks;        // 64-wide K blocks of the incoming gradient (output width of the forward layer / 64)
   int32_t mask_slot;          // saved-activation slot (4 images) whose non-zero pattern is the ReLU mask of this layer's output, or -1
   int32_t rank1_offset;       // >= 0: side offset of w_sigma[256]; adds d_sigma_raw[row] * w_sigma[col] before the mask
-  int32_t dz_slot;            // first dz image slot of the 256-wide output
+  int32_t dz_slot;            // first dz image slot of the output (n_out / 64 images), or -1: not written
+  int32_t n_out;              // output width of this backward layer: 128 or 256 (input width of the forward layer, padded)
+  int32_t rows_cols;          // > 0 (last layer only): the first rows_cols output columns are ALSO written as fp32 rows (input gradient)
   int64_t weight_offset;      // byte offset into the transposed-weight blob
 };
 
@@ -49,6 +51,8 @@ struct DgradArgs {
   const float* g_sigma; const float* g_rgb;   // upstream gradients [M], [M,3] (nullable)
   uint8_t* dz;                // [tile][dz_slots][16 KB]
   int dz_slots;
+  float* g_rows;              // [M, g_row_pitch] fp32 input gradient of the chain's last layer, or nullptr
+  int g_row_pitch;
   long long total;
 };
 
@@ -109,9 +113,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
           const DgradLayer& L = prog.layers[l];
           for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
             const uint32_t st = it % DG_STAGES, ph = (it / DG_STAGES) & 1;
+            const int halves = L.n_out >> 7;
             ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
-            ptx::mbar_arrive_expect_tx(&sm.w_full[st], DG_STAGE);
-            for (int nh = 0; nh < 2; ++nh)
+            ptx::mbar_arrive_expect_tx(&sm.w_full[st], halves * DG_KBLOCK);
+            for (int nh = 0; nh < halves; ++nh)
               ptx::bulk_g2s(sm.w[st] + nh * DG_KBLOCK, args.weights_t + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * DG_KBLOCK,
                             DG_KBLOCK, &sm.w_full[st]);
           }
@@ -121,7 +126,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t idesc = ptx::make_idesc_bf16(128, 256);
       uint32_t it = 0, layer_count = 0, a_phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
         ptx::mbar_wait(&sm.top_ready, t & 1);
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
           const DgradLayer& L = prog.layers[l];
           const uint32_t buf = layer_count & 1;
           const uint32_t d_addr = tmem + buf * 256;
+          const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n_out);
           for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
             const uint32_t st = it % DG_STAGES, ph = (it / DG_STAGES) & 1;
             if (l > 0) {
@@ -223,23 +228,35 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
         const uint8_t* mtile = L.mask_slot >= 0 ? args.acts + ((size_t)tile * args.act_slots + L.mask_slot) * DG_KBLOCK : nullptr;
         uint8_t* out = args.dz + ((size_t)tile * args.dz_slots + L.dz_slot) * DG_KBLOCK;
         // the activation units this thread masks with: issued before the accumulator is ready (independent of the MMAs)
+        const int out_blocks = L.n_out >> 6;
         uint4 mx[4][4];
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            mx[kb][u] = mtile != nullptr ? __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)kb * DG_KBLOCK + ptx::sw128_offset(row, grp * 4 + u)))
-                                         : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+            mx[kb][u] = (mtile != nullptr && kb < out_blocks)
+                            ? __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)kb * DG_KBLOCK + ptx::sw128_offset(row, grp * 4 + u)))
+                            : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        const long long m_row = tile * 128 + row;
+        float* grow = (L.rows_cols > 0 && args.g_rows != nullptr && m_row < args.total) ? args.g_rows + (size_t)m_row * args.g_row_pitch : nullptr;
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
         d_phase ^= 1u << buf;
         ptx::tc_fence_after();
         const float ds = wsig != nullptr ? sm.dsig[row] : 0.f;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
+          if (kb >= out_blocks) break;
           uint32_t v[32], pk[16];
           ptx::tmem_ld32(t_row + kb * 64, v);
           ptx::tmem_ld_wait(v);
           const int col0 = kb * 64 + grp * DG_COLS;
+          if (grow != nullptr) {                      // fp32 input gradient: 32 consecutive columns of this thread's row
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (col0 + 4 * q + 4 <= L.rows_cols)
+                *reinterpret_cast<float4*>(grow + col0 + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                             __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          }
           if (wsig != nullptr) {
             const float4* w4 = reinterpret_cast<const float4*>(wsig + col0);
 #pragma unroll
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
             const uint4 q = make_uint4(pk[4 * u] & __vcmpne2(x.x, 0u), pk[4 * u + 1] & __vcmpne2(x.y, 0u),
                                        pk[4 * u + 2] & __vcmpne2(x.z, 0u), pk[4 * u + 3] & __vcmpne2(x.w, 0u));
             const uint32_t off = ptx::sw128_offset(row, grp * 4 + u);
-            *reinterpret_cast<uint4*>(out + (size_t)kb * DG_KBLOCK + off) = q;
+            if (L.dz_slot >= 0) *reinterpret_cast<uint4*>(out + (size_t)kb * DG_KBLOCK + off) = q;
             if (!last) *reinterpret_cast<uint4*>(sm.h[kb] + off) = q;
           }
           if (!last) {
@@ -286,9 +303,9 @@ using namespace srf;
 
 SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const void* acts, int act_slots,
                                const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
-                               void* dz, int dz_slots, void* stream) {
+                               void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream) {
   if (num_rows == 0) return 0;
-  SRF_REQUIRE(program && weights_t && side && acts && sigma && rgb && dz, "srf_nerf_mlp_dgrad", "null pointer");
+  SRF_REQUIRE(program && weights_t && side && acts && rgb && dz && (sigma || !g_sigma), "srf_nerf_mlp_dgrad", "null pointer");
   DgradProgram prog = *reinterpret_cast<const DgradProgram*>(program);
   SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= DG_MAX_LAYERS, "srf_nerf_mlp_dgrad", "bad layer count");
   SRF_REQUIRE(prog.top_width == 128 || prog.top_width == 256, "srf_nerf_mlp_dgrad", "top width must be 128 or 256");
@@ -297,9 +314,14 @@ SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const
   SRF_REQUIRE(prog.layers[0].num_kblocks * 64 == prog.top_width, "srf_nerf_mlp_dgrad", "first layer must consume dZ_top");
   for (int l = 0; l < prog.num_layers; ++l) {
     const DgradLayer& L = prog.layers[l];
-    SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= 4 && (l == 0 || L.num_kblocks == 4), "srf_nerf_mlp_dgrad", "bad K-block count");
-    SRF_REQUIRE(L.dz_slot >= 0 && L.dz_slot + 4 <= dz_slots && L.mask_slot + 4 <= act_slots, "srf_nerf_mlp_dgrad", "bad slot / mask index");
-    SRF_REQUIRE(L.rank1_offset < 0 || (L.rank1_offset & 3) == 0, "srf_nerf_mlp_dgrad", "rank-1 offset must be a multiple of 4");
+    SRF_REQUIRE(L.n_out == 128 || L.n_out == 256, "srf_nerf_mlp_dgrad", "layer output width must be 128 or 256");
+    SRF_REQUIRE(L.num_kblocks >= 1 && L.num_kblocks <= 4 && (l == 0 || L.num_kblocks * 64 == prog.layers[l - 1].n_out), "srf_nerf_mlp_dgrad",
+                "K blocks must cover the previous layer's output");
+    SRF_REQUIRE(L.dz_slot + L.n_out / 64 <= dz_slots && L.mask_slot + L.n_out / 64 <= act_slots, "srf_nerf_mlp_dgrad", "bad slot / mask index");
+    SRF_REQUIRE(L.dz_slot >= 0 || l == prog.num_layers - 1, "srf_nerf_mlp_dgrad", "only the last layer may skip its dZ images");
+    SRF_REQUIRE(L.rank1_offset < 0 || ((L.rank1_offset & 3) == 0 && L.n_out == 256), "srf_nerf_mlp_dgrad", "rank-1 offset must be a multiple of 4 (256-wide layers)");
+    SRF_REQUIRE(L.rows_cols == 0 || (l == prog.num_layers - 1 && g_rows != nullptr && L.rows_cols % 4 == 0 && L.rows_cols <= L.n_out &&
+                                     L.rows_cols <= g_row_pitch && g_row_pitch % 4 == 0), "srf_nerf_mlp_dgrad", "bad fp32 row output");
   }
   SRF_REQUIRE(prog.top_mask_slot >= 0 && prog.top_mask_slot + prog.top_width / 64 <= act_slots, "srf_nerf_mlp_dgrad", "bad top mask slot");
   SRF_REQUIRE(prog.head_slot >= 0 && prog.head_slot + 2 <= dz_slots && prog.top_slot >= 0 && prog.top_slot + prog.top_width / 64 <= dz_slots,
@@ -308,6 +330,7 @@ SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const
   a.weights_t = reinterpret_cast<const uint8_t*>(weights_t); a.side = side; a.acts = reinterpret_cast<const uint8_t*>(acts);
   a.act_slots = act_slots; a.sigma = sigma; a.rgb = rgb;
   a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dz = reinterpret_cast<uint8_t*>(dz); a.dz_slots = dz_slots; a.total = num_rows;
+  a.g_rows = g_rows; a.g_row_pitch = g_row_pitch;
   const size_t smem = sizeof(DgradSmem);
   static bool configured = false;
   if (!configured) {

@@ -256,41 +256,40 @@ class MlpFeaturesColorPredictor(torch.nn.Module):
 
 
 class _VmColor(torch.autograd.Function):
-    """The appearance branch on the compacted surface samples: VM gather -> (basis o colour MLP) on the tensor cores.
-    Backward (round-1 interim for the MLP part): library GEMMs through torch on the `count` live rows,
-    then the hand-written scatter kernel for the planes / lines."""
+    """The appearance branch on the compacted surface samples, forward and backward hand-written:
+    VM gather (srf_vm_color_features_fwd) -> basis o colour MLP on the tensor cores (srf_mlp_rows_fwd, activations saved
+    as tile images) | data-gradient chain + weight gradients on the tensor cores (srf_nerf_mlp_dgrad / _wgrad) -> scatter
+    of d loss / d products into the planes / lines (srf_vm_color_features_bwd).  What autograd derives for
+    SimpleTensoRF09.py:1241-1272 + :1411-1421.  The surface count is read back once (4 bytes) so that every buffer of
+    the training step is sized exactly."""
 
     @staticmethod
     def forward(ctx, predictor, geom, comp, view_dirs, n_planes, basis, *params):
         planes, lines, mlp = params[:n_planes], params[n_planes:2 * n_planes], params[2 * n_planes:]
-        rows, tables = T.vm_color_rows(geom, comp, view_dirs, list(planes), list(lines))
-        rgb = predictor.packed(basis).forward(rows, comp.count, rows.shape[0])
-        ctx.predictor, ctx.geom, ctx.comp, ctx.tables, ctx.n_planes = predictor, geom, comp, tables, n_planes
-        ctx.save_for_backward(rows, view_dirs, basis, *mlp)
+        n = int(comp.count.item())
+        ctx.n = n
+        if n == 0:
+            return torch.zeros((1, 3), dtype=torch.float32, device=geom.z.device)
+        tight = T.Compacted(comp.mask, comp.idx, comp.count, n)
+        rows, tables = T.vm_color_rows(geom, tight, view_dirs, list(planes), list(lines))
+        packed = predictor.packed(basis)
+        rgb, acts = packed.forward(rows, None, n, save=True)
+        ctx.packed, ctx.flat, ctx.geom, ctx.comp, ctx.tables = packed, packed.flat, geom, tight, tables
+        ctx.save_for_backward(rgb, acts, basis, mlp[0])
         return rgb
 
     @staticmethod
     def backward(ctx, g_rgb):
-        rows, view_dirs, basis, *mlp = ctx.saved_tensors
-        packed = ctx.predictor._packed
-        n = int(ctx.comp.count.item())
-        ct = packed.num_products
-        g_rows = torch.zeros((rows.shape[0], ct), dtype=torch.float32, device=rows.device)
-        grads = [None] * (1 + len(mlp))
-        if n > 0:
-            with torch.enable_grad():
-                x = rows[:n, :packed.in_cols].float()
-                if packed.num_view:             # fp32 view directions instead of their bf16 image (1 % on the table gradients)
-                    x[:, ct:] = view_dirs[(ctx.comp.idx[:n] // ctx.geom.S).long()]
-                x.requires_grad_()
-                ps = [p.detach().requires_grad_() for p in [basis] + mlp]
-                hcur = F.relu(F.linear(x, packed.composed_first_layer(ps[1], ps[0]), ps[2]))
-                hcur = F.relu(F.linear(hcur, ps[3], ps[4]))
-                y = torch.sigmoid(F.linear(hcur, ps[5], ps[6]))
-                gx, *grads = torch.autograd.grad(y, [x] + ps, g_rgb[:n])
-            g_rows[:n] = gx[:, :ct]
+        n_in = len(ctx.needs_input_grad)
+        if ctx.n == 0:
+            return (None,) * n_in
+        rgb, acts, basis, w0 = ctx.saved_tensors
+        packed = ctx.packed
+        g_flat, g_rows = packed.backward(acts, rgb, g_rgb[:ctx.n], ctx.n, flat=ctx.flat)
         gp, gl = T.vm_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
-        return (None, None, None, None, None, grads[0], *gp, *gl, *grads[1:])
+        g_w0, g_basis = packed.split_first_layer_grad(g_flat, w0.detach().float(), basis.detach().float())
+        g_mlp = [g_w0] + [packed.grad_of(g_flat, nm) for nm in packed.names[1:]]
+        return (None, None, None, None, None, g_basis, *gp, *gl, *g_mlp)
 
 
 class VmDecomposedTensor(torch.nn.Module):

@@ -268,6 +268,56 @@ class PackedRowsMLP:
         self._dev = None
         self.blob = self.side = None
         self.macs_per_row = units * self.in_cols + units * units + 3 * units
+        self.units = units
+        self.offs, self.shapes = offs, shapes
+        self.e_slot, self.v_slot, self.act_slots = 0, (5 if two else -1), (6 if two else 5)     # E | L0 out (1,2) | L1 out (3,4) | V
+        assert self.program.layers[0].save_slot == 1 and self.program.layers[1].save_slot == 3
+        self.backward_plan = self._build_backward_plan(o, two)
+
+    def _build_backward_plan(self, zero, two):
+        """dgrad chain dZ1 -> dZ0 -> d(rows) and the weight-gradient work items, in the formats of nerf_mlp_dgrad.cu /
+        nerf_mlp_wgrad.cu (transposed-weight images [K block of outputs] of 128 inputs x 64 outputs)."""
+        n, offs, names = self.units, self.offs, self.names
+        plan = BackwardPlan()
+        prog = DgradProgram()
+        prog.num_fwd_layers, prog.num_layers = 2, 2
+        prog.head_slot, prog.top_slot, prog.top_width = 0, 2, n
+        prog.top_mask_slot = 3
+        prog.head_kind = 1
+        prog.head_w_offset = 0
+        side = [offs[names[4]] + r * n + c for r in range(3) for c in range(n)]
+        e = np.arange(128 * 64)
+        r = e // 64
+        unit = (e % 64) // 8
+        c = ((unit ^ (r & 7)) * 8) + e % 8
+        gather, woff = [], 0
+        # backward layer 0: dH0 = dZ1 W1, masked by the L0 activations -> dZ0 (dz slots 4, 5)
+        L0 = prog.layers[0]
+        L0.num_kblocks, L0.mask_slot, L0.rank1_offset, L0.dz_slot, L0.n_out, L0.rows_cols = n // 64, 1, -1, 4, n, 0
+        L0.weight_offset = 0
+        for kb in range(n // 64):
+            gather.append(offs[names[2]] + (kb * 64 + c) * n + r)
+            woff += 128 * 64
+        # backward layer 1: d(rows) = dZ0 W0' (no mask; only the product columns are written, as fp32 rows)
+        L1 = prog.layers[1]
+        L1.num_kblocks, L1.mask_slot, L1.rank1_offset, L1.dz_slot, L1.n_out, L1.rows_cols = n // 64, -1, -1, -1, 128, self.num_products
+        L1.weight_offset = woff * 2
+        for kb in range(n // 64):
+            gather.append(np.where(r < self.in_cols, offs[names[0]] + (kb * 64 + c) * self.in_cols + np.minimum(r, self.in_cols - 1), zero))
+            woff += 128 * 64
+        prog.side_count = len(side)
+        plan.program, plan.dz_slots = prog, 6
+        plan.gather_t = np.concatenate(gather).astype(np.int64)
+        plan.side_idx = np.asarray(side, dtype=np.int64)
+        e_cols = min(64, self.in_cols)
+        items = [WgradItem(2, 2, 1, 2, n, 0, n, 0, n, 1, offs[names[2]], offs[names[3]]),
+                 WgradItem(4, 2, 0, 1, n, 0, e_cols, 0, self.in_cols, 1, offs[names[0]], offs[names[1]])]
+        if two:
+            items.append(WgradItem(4, 2, 5, 1, n, 0, self.in_cols - 64, 64, self.in_cols, 0, offs[names[0]], offs[names[1]]))
+        items.append(WgradItem(0, 2, 3, 2, 3, 0, n, 0, n, 1, offs[names[4]], offs[names[5]]))
+        plan.items = items
+        plan._dev = None
+        return plan
 
     def composed_first_layer(self, w0, basis):
         """W0' [units, sum(C) + num_view] (differentiable in torch: the interim backward and the tests use it too)."""
@@ -284,17 +334,58 @@ class PackedRowsMLP:
         flat = torch.cat([w0c.reshape(-1)] + [params[n].detach().reshape(-1).float() for n in self.names[1:]] +
                          [torch.zeros(1, dtype=torch.float32, device=dev)])
         assert flat.numel() == self.flat_size + 1
+        self.flat = flat
         self.blob = flat[self._gather].to(torch.bfloat16).contiguous()
         self.side = flat[self._side_idx].contiguous()
         return self
 
-    def forward(self, rows, count, max_rows):
-        """rows [max_rows, pitch] bf16, count int32[1] on the device -> rgb [max_rows, 3] (rows >= count undefined)."""
+    def forward(self, rows, count, max_rows, save=False):
+        """rows [max_rows, pitch] bf16, count int32[1] on the device (or None: all rows) -> rgb [max_rows, 3] (rows >=
+        count undefined).  save=True also returns the saved activation tile images for `backward`."""
         assert rows.dtype == torch.bfloat16 and rows.shape[1] >= self.in_cols and rows.is_contiguous()
         rgb = torch.empty((max_rows, 3), dtype=torch.float32, device=rows.device)
+        acts = torch.empty(((max_rows + 127) // 128, self.act_slots, 16384), dtype=torch.uint8, device=rows.device) if save else None
         L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
-               rows.shape[1], L.ptr(count), max_rows, L.ptr(rgb), L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
-        return rgb
+               rows.shape[1], L.ptr(count), max_rows, L.ptr(rgb), L.ptr(acts), self.act_slots, self.e_slot, self.v_slot,
+               L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
+        return (rgb, acts) if save else rgb
+
+    def backward(self, acts, rgb, g_rgb, num_rows, flat=None):
+        """Hand-written backward on the tensor cores (nerf_mlp_dgrad.cu / nerf_mlp_wgrad.cu) of a forward(save=True) over
+        exactly num_rows rows: returns (flat gradient in the layout [W0' | b0 | W1 | b1 | W2 | b2], g_rows fp32
+        [num_rows, pitch4] whose first num_products columns are d loss / d product rows)."""
+        plan = self.backward_plan
+        dev = acts.device
+        if plan._dev != dev:
+            plan._gather = torch.from_numpy(plan.gather_t).to(dev)
+            plan._side = torch.from_numpy(plan.side_idx).to(dev)
+            plan._dev = dev
+        flat = self.flat if flat is None else flat
+        wt = flat[plan._gather].to(torch.bfloat16).contiguous()
+        side = flat[plan._side].contiguous()
+        tiles = acts.shape[0]
+        dz = torch.empty((tiles, plan.dz_slots, 16384), dtype=torch.uint8, device=dev)
+        pitch = -(-self.num_products // 4) * 4
+        g_rows = torch.empty((max(num_rows, 1), pitch), dtype=torch.float32, device=dev)
+        L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), acts.shape[1], None, L.ptr(rgb),
+               None, L.ptr(L.f32c(g_rgb)), num_rows, L.ptr(dz), plan.dz_slots, L.ptr(g_rows), pitch, L.stream_handle(),
+               work=2.0 * (2 * self.units * self.units) * num_rows)
+        grads = torch.zeros(self.flat_size, dtype=torch.float32, device=dev)
+        run_wgrad(plan.items, acts, dz, grads)
+        return grads, g_rows
+
+    def split_first_layer_grad(self, g_flat, w0, basis):
+        """(dW0, dB) from dW0' = d loss / d [W0[:, :F] B | W0[:, F:]] (chain rule through composed_first_layer)."""
+        f, ct = self.features_dim, self.num_products
+        gw = g_flat[self.offs[self.names[0]]:self.offs[self.names[0]] + self.units * self.in_cols].view(self.units, self.in_cols)
+        g_w0 = torch.cat([gw[:, :ct] @ basis.t(), gw[:, ct:ct + self.num_view]], dim=1)
+        g_basis = w0[:, :f].t() @ gw[:, :ct]
+        return g_w0, g_basis
+
+    def grad_of(self, g_flat, name):
+        o = self.offs[name]
+        shape = self.shapes[name]
+        return g_flat[o:o + int(np.prod(shape))].view(shape)
 
 
 class WgradItem(ctypes.Structure):
@@ -314,7 +405,7 @@ def run_wgrad(items, acts, dz, grads):
 
 class DgradLayer(ctypes.Structure):
     _fields_ = [('num_kblocks', ctypes.c_int32), ('mask_slot', ctypes.c_int32), ('rank1_offset', ctypes.c_int32),
-                ('dz_slot', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
+                ('dz_slot', ctypes.c_int32), ('n_out', ctypes.c_int32), ('rows_cols', ctypes.c_int32), ('weight_offset', ctypes.c_int64)]
 
 
 class DgradProgram(ctypes.Structure):
@@ -372,6 +463,8 @@ def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
             side += [offs['pts_output_linear.weight'] + j for j in range(256)]
         dz_of[f - 1] = slot
         Lr.dz_slot = slot
+        Lr.n_out = 256
+        Lr.rows_cols = 0
         slot += 4
         Lr.weight_offset = woff * 2
         for nh in range(2):
@@ -437,7 +530,7 @@ def mlp_backward(packed, params_flat, acts, sigma, rgb, g_sigma, g_rgb):
     gs = None if g_sigma is None else L.f32c(g_sigma).reshape(-1)
     gc = None if g_rgb is None else L.f32c(g_rgb).reshape(-1, 3)
     L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), acts.shape[1], L.ptr(sigma), L.ptr(rgb),
-           L.ptr(gs), L.ptr(gc), rows, L.ptr(dz), plan.dz_slots, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
+           L.ptr(gs), L.ptr(gc), rows, L.ptr(dz), plan.dz_slots, None, 0, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
     grads = torch.zeros(packed.flat_size, dtype=torch.float32, device=dev)
     run_wgrad(plan.items, acts, dz, grads)
     return grads, dz

@@ -190,8 +190,9 @@ def scatter_rows(comp, src, width, total):
     return dst
 
 
-def gather_rows(comp, src, width):
-    dst = torch.zeros((max(comp.total, 1), width), dtype=torch.float32, device=src.device)
+def gather_rows(comp, src, width, nrows=None):
+    """nrows: rows of the result when the caller knows count <= nrows (default: the worst case comp.total)."""
+    dst = torch.zeros((max(comp.total if nrows is None else nrows, 1), width), dtype=torch.float32, device=src.device)
     L.call('srf_gather_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(L.f32c(src)), width, L.ptr(dst), L.stream_handle())
     return dst
 
@@ -201,9 +202,9 @@ class _ScatterRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, comp, rows, total):
-        ctx.comp, ctx.width = comp, rows.shape[1]
+        ctx.comp, ctx.width, ctx.nrows = comp, rows.shape[1], rows.shape[0]
         return scatter_rows(comp, rows, rows.shape[1], total)
 
     @staticmethod
     def backward(ctx, g):
-        return None, gather_rows(ctx.comp, g, ctx.width)[:ctx.comp.total], None
+        return None, gather_rows(ctx.comp, g, ctx.width, ctx.nrows)[:ctx.nrows], None
