@@ -76,13 +76,13 @@ struct MlpArgs {
 #ifndef SRF_MLP_PREFETCH
 #define SRF_MLP_PREFETCH 0
 #endif
-// SRF_MLP_TRACE: CTA 0 records clock64() at pipeline events of its 3rd tile into a global buffer (tools/mlp_trace.py)
+// SRF_MLP_TRACE: CTA 0 records clock64() at pipeline events of its 3rd and 4th tile into a global buffer (tools/mlp_trace.py)
 #ifndef SRF_MLP_TRACE
 #define SRF_MLP_TRACE 0
 #endif
 #if SRF_MLP_TRACE
 __device__ long long g_mlp_trace[4096];
-#define TRACE(slot) do { if (blockIdx.x == 0 && t == 2) g_mlp_trace[(slot)] = clock64(); } while (0)
+#define TRACE(slot) do { if (blockIdx.x == 0 && (t == 2 || t == 3)) g_mlp_trace[(slot) + (t - 2) * 2048] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
@@ -379,28 +379,42 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         auto compute = [&](uint32_t (&v)[COLS], uint32_t (&pk)[COLS / 2], int kb) {
           const int col0 = kb * 64 + grp * COLS;
           const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+          float x[COLS];
 #pragma unroll
-          for (int q = 0; q < COLS / 4; ++q) {
+          for (int q = 0; q < COLS / 4; ++q) {                     // + bias as packed fp32 pairs (FADD2)
             const float4 b = b4[q];
-            float x0 = __uint_as_float(v[4 * q + 0]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
-            float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
-            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-            v[4 * q + 0] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
-            v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+            x[4 * q + 0] = __uint_as_float(v[4 * q + 0]); x[4 * q + 1] = __uint_as_float(v[4 * q + 1]);
+            x[4 * q + 2] = __uint_as_float(v[4 * q + 2]); x[4 * q + 3] = __uint_as_float(v[4 * q + 3]);
+            ptx::fadd2(x[4 * q + 0], x[4 * q + 1], b.x, b.y);
+            ptx::fadd2(x[4 * q + 2], x[4 * q + 3], b.z, b.w);
           }
-          for (int hr = 0; hr < head_rows; ++hr) {
+          if (head_rows == 0) {                                    // plain hidden layer: ReLU rides on the bf16 conversion (F2FP.RELU)
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16_relu(x[2 * j], x[2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(x[2 * j], x[2 * j + 1]);
+            }
+            return;
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < COLS; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          for (int hr = 0; hr < head_rows; ++hr) {                 // head partial dot products on the fp32 activations (FFMA2)
             const float4* w4 = reinterpret_cast<const float4*>(hw + hr * n + col0);
-            float a = hacc[hr];
+            float a0 = hacc[hr], a1 = 0.f;
 #pragma unroll
             for (int q = 0; q < COLS / 4; ++q) {
               const float4 w = w4[q];
-              a = fmaf(__uint_as_float(v[4 * q + 0]), w.x, a); a = fmaf(__uint_as_float(v[4 * q + 1]), w.y, a);
-              a = fmaf(__uint_as_float(v[4 * q + 2]), w.z, a); a = fmaf(__uint_as_float(v[4 * q + 3]), w.w, a);
+              ptx::ffma2(a0, a1, x[4 * q + 0], x[4 * q + 1], w.x, w.y);
+              ptx::ffma2(a0, a1, x[4 * q + 2], x[4 * q + 3], w.z, w.w);
             }
-            hacc[hr] = a;
+            hacc[hr] = a0 + a1;
           }
 #pragma unroll
-          for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(x[2 * j], x[2 * j + 1]);
         };
         // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H:
         // every MMA of this layer has retired once d_full fired)
@@ -479,9 +493,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             if (head == 2 || head == 3) {
               const int b = head == 2 ? 1 : 0;
 #pragma unroll
-              for (int c = 0; c < 3; ++c) args.rgb[m * 3 + c] = 1.f / (1.f + expf(-o[b + c]));
+              for (int c = 0; c < 3; ++c) args.rgb[m * 3 + c] = __fdividef(1.f, 1.f + __expf(-o[b + c]));
             }
           }
+          if (warp == EPI_WARP0 && lane == 0) TRACE(2000 + l);
         }
       }
     }

@@ -144,6 +144,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// max(x, 0) fused into the fp32 -> bf16x2 conversion (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// packed fp32 pair arithmetic (FADD2 / FFMA2 on sm_100): (x0, x1) += (b0, b1);  (a0, a1) += (x0, x1) * (w0, w1)
+__device__ __forceinline__ void fadd2(float& x0, float& x1, float b0, float b1) {
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(x0), "+f"(x1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float x0, float x1, float w0, float w1) {
+  asm("{\n\t.reg .b64 a, x, w;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 x, {%2, %3};\n\tmov.b64 w, {%4, %5};\n\tfma.rn.f32x2 a, x, w, a;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(x0), "f"(x1), "f"(w0), "f"(w1));
+}
+
 // byte offset of 16-byte unit `unit` (0..7) of row `row` inside a SW128 K-block
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t unit) {
   return row * 128u + ((unit ^ (row & 7u)) << 4);

@@ -50,7 +50,9 @@ def test_composite_vs_reference_golden(golden, tag, ndc, white):
 @pytest.mark.parametrize('R,S,ndc,scale,white', [(1000, 64, True, 1.0, False), (257, 192, True, 1.0, True),
                                                  (64, 462, True, 25.0, False), (33, 1083, True, 25.0, False),
                                                  (100, 45, False, 1.0, False), (5, 1, True, 1.0, False),
-                                                 (3, 31, False, 25.0, True), (0, 64, True, 1.0, False)])
+                                                 (3, 31, False, 25.0, True), (0, 64, True, 1.0, False),
+                                                 (7, 2, True, 1.0, False), (9, 3, False, 1.0, False), (130, 130, True, 1.0, False),
+                                                 (41, 515, True, 25.0, True), (19, 128, False, 1.0, False), (17, 256, True, 1.0, False)])
 def test_composite_forward_backward_vs_oracle(R, S, ndc, scale, white):
     from simple_rf_b200 import ops
     sigma, rgb, z, ro, rd, dn = _inputs(R, S, ndc, seed=R + S)
@@ -77,6 +79,31 @@ def test_composite_forward_backward_vs_oracle(R, S, ndc, scale, white):
                                   g_depth_var_ndc=dd(ups['depth_var_ndc']) if ndc else None, g_weights=dd(ups['weights']))
     assert _rel(sg.grad.cpu(), gs) <= 1e-3, 'g_sigma'      # relative to max |g| per tensor
     assert _rel(cg.grad.cpu(), gc) <= 1e-5, 'g_rgb'
+
+
+@pytest.mark.parametrize('S', [64, 77, 192])
+def test_composite_unaligned_views(S):
+    """Per-sample tensors that do not start on a 16-byte boundary take the scalar load / store path: same results."""
+    from simple_rf_b200 import ops
+    R = 50
+    sigma, rgb, z, ro, rd, dn = _inputs(R, S, True, seed=S)
+
+    def shifted(t, k):
+        buf = torch.zeros(t.numel() + k, device=DEV)
+        buf[k:] = t.reshape(-1).to(DEV)
+        v = buf[k:].view(t.shape)
+        assert v.data_ptr() % 16 == (4 * k) % 16
+        return v
+    a = ops.composite(sigma.to(DEV).requires_grad_(), rgb.to(DEV).requires_grad_(), z.to(DEV), ro.to(DEV), rd.to(DEV), dn.to(DEV), ndc=True)
+    sg, cg = shifted(sigma, 1).requires_grad_(), shifted(rgb, 3).requires_grad_()
+    b = ops.composite(sg, cg, shifted(z, 2), ro.to(DEV), rd.to(DEV), dn.to(DEV), ndc=True)
+    for k in ('rgb', 'acc', 'depth', 'depth_ndc', 'depth_var', 'weights', 'alpha', 'visibility'):
+        assert torch.equal(a[k], b[k]), k
+    ups = torch.rand(R, 3, device=DEV)
+    (b['rgb'] * ups).sum().backward()
+    ref = C.composite(sigma.requires_grad_(), rgb.requires_grad_(), z, ro, rd, dn, ndc=True)
+    (ref['rgb'] * ups.cpu()).sum().backward()
+    assert _rel(sg.grad.cpu(), sigma.grad) <= 1e-3 and _rel(cg.grad.cpu(), rgb.grad) <= 1e-5
 
 
 def test_composite_without_rgb_and_inference_mode():
