@@ -99,17 +99,21 @@ constexpr int NUM_STAGES = 3;
 constexpr int MAX_SIDE = 4096;                    // floats
 constexpr int MAX_STEPS = MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
 
-// One K-block step of the MMA issuer, flattened from the layer program at kernel start so that the issuing
-// thread's loop is a single shared-memory load away from the next tcgen05.mma.
+// One K-block step of the MMA issuer.  The host flattens the layer program into this schedule and passes it as a kernel
+// parameter: the issuing warp reads it with uniform constant-bank loads, so step data never leaves uniform registers.
 struct alignas(16) MmaStep {
-  uint32_t a_desc_lo;     // low word of the A-operand descriptor (region base >> 4)
+  uint32_t a_off;         // (byte offset of the A region inside MlpSmem::a) >> 4
   uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
-  uint16_t layer;         // layer index inside the tile (selects the accumulator buffer)
-  uint8_t ksteps;         // 16-wide K steps to issue
+  int32_t layer;          // layer index inside the tile (selects the accumulator buffer)
+  int8_t ksteps;          // 16-wide K steps to issue
   int8_t wait_region;     // region whose a_ready barrier must be acquired first, or -1
   uint8_t first;          // first step of the layer: overwrite the accumulator
-  uint8_t last;           // last step of the layer: commit d_full
-  uint8_t free_e, free_v; // last reader of region 0 / 5 in the tile: commit e_free / v_free
+  uint8_t flags;          // 1: last step of the layer (commit d_full); 2 / 4: last reader of region 0 / 5 (commit e_free / v_free)
+};
+struct MmaSchedule {
+  int32_t num_steps;
+  int32_t pad_[3];
+  MmaStep steps[MAX_STEPS];
 };
 
 struct alignas(1024) MlpSmem {
@@ -117,13 +121,11 @@ struct alignas(1024) MlpSmem {
   uint8_t w[NUM_STAGES][STAGE_BYTES];
   float side[MAX_SIDE];
   float part[2][GROUPS][128][4];          // head partial sums of each column group
-  MmaStep steps[MAX_STEPS];
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
   uint64_t a_ready[6];                    // per A region: written and visible to the async proxy
   uint64_t d_full[2];                     // accumulator buffer complete
   uint64_t e_free, v_free;                // every MMA reading region 0 / 5 of the current tile has retired
   uint32_t tmem_base;
-  int num_steps;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
@@ -154,7 +156,7 @@ template <>
 __device__ __forceinline__ void tmem_load<16>(uint32_t taddr, uint32_t (&v)[16]) { ptx::tmem_ld16(taddr, v); }
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __grid_constant__ MlpProgram prog,
-                                                                      const MlpArgs args) {
+                                                                      const __grid_constant__ MmaSchedule sched, const MlpArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   MlpSmem& sm = *reinterpret_cast<MlpSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,32 +173,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     ptx::mbar_init(&sm.e_free, 1);
     ptx::mbar_init(&sm.v_free, 1);
     ptx::fence_barrier_init();
-    // flatten the layer program into MMA steps
-    int ns = 0, last_e = -1, last_v = -1;
-    uint32_t seen = 0;
-    for (int l = 0; l < prog.num_layers; ++l) {
-      const MlpLayer& L = prog.layers[l];
-      for (int kb = 0; kb < L.num_kblocks; ++kb, ++ns) {
-        MmaStep st;
-        const int reg = L.kblock_region[kb];
-        st.a_desc_lo = (ptx::smem_u32(sm.a[reg]) >> 4) & 0x3FFF;
-        st.idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
-        st.layer = (uint16_t)l;
-        st.ksteps = (uint8_t)L.kblock_ksteps[kb];
-        st.wait_region = ((seen >> reg) & 1) ? -1 : (int8_t)reg;
-        seen |= 1u << reg;
-        st.first = kb == 0;
-        st.last = kb == L.num_kblocks - 1;
-        st.free_e = st.free_v = 0;
-        if (reg == 0) last_e = ns;
-        if (reg == 5) last_v = ns;
-        sm.steps[ns] = st;
-      }
-      if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
-    }
-    if (last_e >= 0) sm.steps[last_e].free_e = 1;
-    if (last_v >= 0) sm.steps[last_v].free_v = 1;
-    sm.num_steps = ns;
   }
   if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
   ptx::tc_fence_before();
@@ -230,40 +206,49 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      const int num_steps = sm.num_steps;
-      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
-      const uint32_t w_desc_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
-      uint32_t it = 0, layer_base = 0;
-      uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
-      for (int t = 0; t < my_tiles; ++t) {
-        for (int s = 0; s < num_steps; ++s, ++it) {
-          const MmaStep st = sm.steps[s];
-          const uint32_t stage = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
-          if (st.wait_region >= 0) {
-            ptx::mbar_wait(&sm.a_ready[st.wait_region], (a_phase >> st.wait_region) & 1);
-            a_phase ^= 1u << st.wait_region;
-          }
-          TRACE(16 + s * 4 + 0);
-          ptx::mbar_wait(&sm.w_full[stage], ph);
-          TRACE(16 + s * 4 + 1);
-          ptx::tc_fence_after();
-          const uint32_t buf = (layer_base + st.layer) & 1;
-          const uint32_t d_addr = tmem + buf * 256;
-          const uint64_t a_desc = ((uint64_t)desc_hi << 32) | st.a_desc_lo;
-          const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (w_desc_lo + stage * (STAGE_BYTES >> 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < st.ksteps) ptx::umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, st.idesc, (st.first && k == 0) ? 0u : 1u);
-          ptx::umma_commit(&sm.w_empty[stage]);
-          if (st.last) ptx::umma_commit(&sm.d_full[buf]);
-          if (st.free_e) ptx::umma_commit(&sm.e_free);
-          if (st.free_v) ptx::umma_commit(&sm.v_free);
-          TRACE(16 + s * 4 + 2);
+    // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (uniform control
+    // flow), one elected lane issues tcgen05.mma / tcgen05.commit
+    const int num_steps = sched.num_steps;
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+    const uint32_t w_desc_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
+    const uint32_t a_desc_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
+    uint32_t stage = 0, ph = 0, layer_base = 0;
+    uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
+    for (int t = 0; t < my_tiles; ++t) {
+      for (int s = 0; s < num_steps; ++s) {
+        const MmaStep st = sched.steps[s];
+        if (st.wait_region >= 0) {
+          ptx::mbar_wait(&sm.a_ready[st.wait_region], (a_phase >> st.wait_region) & 1);
+          a_phase ^= 1u << st.wait_region;
         }
-        layer_base += prog.num_layers;
+        if (lane == 0) TRACE(16 + s * 4 + 0);
+        ptx::mbar_wait(&sm.w_full[stage], ph);
+        if (lane == 0) TRACE(16 + s * 4 + 1);
+        ptx::tc_fence_after();
+        const uint32_t buf = (layer_base + (uint32_t)st.layer) & 1;
+        const uint32_t d_addr = tmem + buf * 256;
+        const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (a_desc_lo + st.a_off);
+        const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (w_desc_lo + stage * (STAGE_BYTES >> 4));
+        const uint32_t issue = ptx::elect_one();
+        if (st.ksteps == 4) {
+          ptx::umma_bf16_if(issue, d_addr, a_desc, b_desc, st.idesc, st.first ? 0u : 1u);
+          ptx::umma_bf16_if(issue, d_addr, a_desc + 2, b_desc + 2, st.idesc, 1u);
+          ptx::umma_bf16_if(issue, d_addr, a_desc + 4, b_desc + 4, st.idesc, 1u);
+          ptx::umma_bf16_if(issue, d_addr, a_desc + 6, b_desc + 6, st.idesc, 1u);
+        } else {
+          for (int k = 0; k < st.ksteps; ++k)
+            ptx::umma_bf16_if(issue, d_addr, a_desc + 2 * k, b_desc + 2 * k, st.idesc, (st.first && k == 0) ? 0u : 1u);
+        }
+        ptx::umma_commit_if(issue, &sm.w_empty[stage]);
+        if (st.flags) {
+          if (st.flags & 1) ptx::umma_commit_if(issue, &sm.d_full[buf]);
+          if (st.flags & 2) ptx::umma_commit_if(issue, &sm.e_free);
+          if (st.flags & 4) ptx::umma_commit_if(issue, &sm.v_free);
+        }
+        if (lane == 0) TRACE(16 + s * 4 + 2);
+        if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
       }
+      layer_base += (uint32_t)prog.num_layers;
     }
   } else if (warp >= ENC_WARP0) {
     // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
@@ -548,8 +533,38 @@ int validate_program(const MlpProgram& prog, const char* where, bool rows_mode) 
   return 0;
 }
 
+// flatten the layer program into the MMA issuer's K-block steps
+MmaSchedule make_schedule(const MlpProgram& prog) {
+  MmaSchedule sc{};
+  int ns = 0, last_e = -1, last_v = -1;
+  uint32_t seen = 0;
+  for (int l = 0; l < prog.num_layers; ++l) {
+    const MlpLayer& L = prog.layers[l];
+    for (int kb = 0; kb < L.num_kblocks; ++kb, ++ns) {
+      MmaStep& st = sc.steps[ns];
+      const int reg = L.kblock_region[kb];
+      st.a_off = (uint32_t)(reg * KBLOCK_BYTES) >> 4;
+      st.idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
+      st.layer = l;
+      st.ksteps = (int8_t)L.kblock_ksteps[kb];
+      st.wait_region = ((seen >> reg) & 1) ? (int8_t)-1 : (int8_t)reg;
+      seen |= 1u << reg;
+      st.first = kb == 0;
+      st.flags = kb == L.num_kblocks - 1 ? 1 : 0;
+      if (reg == 0) last_e = ns;
+      if (reg == 5) last_v = ns;
+    }
+    if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
+  }
+  if (last_e >= 0) sc.steps[last_e].flags |= 2;
+  if (last_v >= 0) sc.steps[last_v].flags |= 4;
+  sc.num_steps = ns;
+  return sc;
+}
+
 int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, void* stream, const char* where) {
   const size_t smem = sizeof(MlpSmem);
+  const MmaSchedule sched = make_schedule(prog);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -558,7 +573,7 @@ int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, vo
   }
   const long long tiles = (max_total + 127) / 128;
   const int grid = tiles < sm_count() ? (int)tiles : sm_count();
-  nerf_mlp_fwd_kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, a);
+  nerf_mlp_fwd_kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, sched, a);
   return check_launch(where);
 }
 }  // namespace

@@ -5,9 +5,9 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 out = ROOT / 'gpurun_out' / 'lib_trace.so'
 out.parent.mkdir(exist_ok=True)
-src = [str(ROOT / 'simple_rf_b200/csrc' / f) for f in ('rays_sampling.cu', 'composite.cu', 'nerf_mlp.cu', 'tensorf.cu')]
-subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
-                '-DSRF_MLP_TRACE=1', '-shared', '-o', str(out)] + src, check=True)
+from simple_rf_b200 import build as B
+src = [str(B.CSRC / f) for f in B.SOURCES]
+subprocess.run([B.nvcc_path(), *B.FLAGS, '-DSRF_MLP_TRACE=1', '-shared', '-o', str(out)] + src, check=True)
 os.environ['SIMPLE_RF_B200_LIB'] = str(out)
 import torch
 from simple_rf_b200 import _lib, nerf_program
