@@ -123,33 +123,40 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
         }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      uint32_t it = 0, layer_count = 0, a_phase = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        ptx::mbar_wait(&sm.top_ready, t & 1);
-        for (int l = 0; l < NL; ++l, ++layer_count) {
-          const DgradLayer& L = prog.layers[l];
-          const uint32_t buf = layer_count & 1;
-          const uint32_t d_addr = tmem + buf * 256;
-          const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n_out);
-          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
-            const uint32_t st = it % DG_STAGES, ph = (it / DG_STAGES) & 1;
-            if (l > 0) {
-              ptx::mbar_wait(&sm.a_ready[kb], (a_phase >> kb) & 1);
-              a_phase ^= 1u << kb;
-            }
-            ptx::mbar_wait(&sm.w_full[st], ph);
-            ptx::tc_fence_after();
-            const uint64_t a_desc = ((uint64_t)desc_hi << 32) | ((ptx::smem_u32(sm.h[kb]) >> 4) & 0x3FFF);
-            const uint64_t b_desc = ((uint64_t)desc_hi << 32) | ((ptx::smem_u32(sm.w[st]) >> 4) & 0x3FFF);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-            ptx::umma_commit(&sm.w_empty[st]);
+    // ------------------------------------------------------------ MMA issuer: converged warp, one elected lane issues
+    // (uniform control flow keeps the descriptors in uniform registers, see nerf_mlp.cu)
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t h_lo = (ptx::smem_u32(sm.h[0]) >> 4) & 0x3FFF;
+    const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
+    uint32_t st = 0, ph = 0, layer_count = 0, a_phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      ptx::mbar_wait(&sm.top_ready, t & 1);
+      for (int l = 0; l < NL; ++l, ++layer_count) {
+        const DgradLayer& L = prog.layers[l];
+        const uint32_t buf = layer_count & 1;
+        const uint32_t d_addr = tmem + buf * 256;
+        const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n_out);
+        const int nkb = L.num_kblocks;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (l > 0) {
+            ptx::mbar_wait(&sm.a_ready[kb], (a_phase >> kb) & 1);
+            a_phase ^= 1u << kb;
           }
-          ptx::umma_commit(&sm.d_full[buf]);
-          if (l == NL - 1) ptx::umma_commit(&sm.h_free);
+          ptx::mbar_wait(&sm.w_full[st], ph);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (h_lo + (uint32_t)kb * (DG_KBLOCK >> 4));
+          const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (w_lo + st * (DG_STAGE >> 4));
+          const uint32_t issue = ptx::elect_one();
+          ptx::umma_bf16_if(issue, d_addr, a_desc, b_desc, idesc, kb == 0 ? 0u : 1u);
+          ptx::umma_bf16_if(issue, d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
+          ptx::umma_bf16_if(issue, d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+          ptx::umma_bf16_if(issue, d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          ptx::umma_commit_if(issue, &sm.w_empty[st]);
+          if (kb == nkb - 1) {
+            ptx::umma_commit_if(issue, &sm.d_full[buf]);
+            if (l == NL - 1) ptx::umma_commit_if(issue, &sm.h_free);
+          }
+          if (++st == DG_STAGES) { st = 0; ph ^= 1; }
         }
       }
     }

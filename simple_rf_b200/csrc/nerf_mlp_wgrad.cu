@@ -106,24 +106,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_mlp_wgrad_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // A and B both MN-major (bits 15, 16), fp32 accumulate, bf16 operands
-      const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)N) | (1u << 15) | (1u << 16);
-      for (int i = 0; i < num_stages_total; ++i) {
-        const int s = i % WG_STAGES, ph = (i / WG_STAGES) & 1;
-        ptx::mbar_wait(&sm.full[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t base = ptx::smem_u32(sm.stage[s]);
+    // MMA issuer: converged warp, one elected lane issues.  A and B both MN-major (bits 15, 16), fp32 accumulate, bf16 operands
+    const uint32_t idesc = ptx::make_idesc_bf16(128, (uint32_t)N) | (1u << 15) | (1u << 16);
+    uint32_t s = 0, ph = 0;
+    for (int i = 0; i < num_stages_total; ++i) {
+      ptx::mbar_wait(&sm.full[s], ph);
+      ptx::tc_fence_after();
+      const uint32_t base = ptx::smem_u32(sm.stage[s]);
+      const uint32_t issue = ptx::elect_one();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                 // 16 samples per MMA
-          for (int h = 0; h < halves; ++h)
-            ptx::umma_bf16(tmem + h * 256, make_mn_desc(base + (2 * h) * HALF_IMAGE + k * 2048, HALF_IMAGE),
-                           make_mn_desc(base + 4 * HALF_IMAGE + k * 2048, HALF_IMAGE), idesc, (i == 0 && k == 0) ? 0u : 1u);
-        }
-        ptx::umma_commit(&sm.empty[s]);
+      for (int k = 0; k < 4; ++k) {                 // 16 samples per MMA
+        const uint64_t b_desc = make_mn_desc(base + 4 * HALF_IMAGE + k * 2048, HALF_IMAGE);
+        ptx::umma_bf16_if(issue, tmem, make_mn_desc(base + k * 2048, HALF_IMAGE), b_desc, idesc, (i == 0 && k == 0) ? 0u : 1u);
+        if (halves > 1)
+          ptx::umma_bf16_if(issue, tmem + 256, make_mn_desc(base + 2 * HALF_IMAGE + k * 2048, HALF_IMAGE), b_desc, idesc,
+                            (i == 0 && k == 0) ? 0u : 1u);
       }
-      ptx::umma_commit(&sm.done);
+      ptx::umma_commit_if(issue, &sm.empty[s]);
+      if (++s == WG_STAGES) { s = 0; ph ^= 1; }
     }
+    ptx::umma_commit_if(ptx::elect_one(), &sm.done);
   } else {
     // ------------------------------------------------------------ bias column sums, then the TMEM -> global epilogue
     const int t = threadIdx.x - 64;                  // 0..127
