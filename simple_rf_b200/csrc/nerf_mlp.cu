@@ -387,7 +387,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < COLS; ++j) x[j] = fmaxf(x[j], 0.f);
           }
-          for (int hr = 0; hr < head_rows; ++hr) {                 // head partial dot products on the fp32 activations (FFMA2)
+#pragma unroll
+          for (int hr = 0; hr < 4; ++hr) {                         // head partial dot products on the fp32 activations (FFMA2);
+            if (hr >= head_rows) break;                            // unrolled: hacc[] must stay in registers
             const float4* w4 = reinterpret_cast<const float4*>(hw + hr * n + col0);
             float a0 = hacc[hr], a1 = 0.f;
 #pragma unroll
@@ -454,12 +456,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 #endif
         ptx::tc_fence_before();
         if (head_rows > 0) {
+          if (warp == EPI_WARP0 && lane == 0) TRACE(2010 + l);
           const int slot = head == 3 ? 1 : 0;
           if (grp != 0) {
 #pragma unroll
             for (int hr = 0; hr < 4; ++hr) sm.part[slot][grp][row][hr] = hacc[hr];
           }
           epi_bar_sync();
+          if (warp == EPI_WARP0 && lane == 0) TRACE(2020 + l);
           if (grp == 0 && valid) {
             const float* hb = hw + head_rows * n;
             float o[4];
@@ -475,10 +479,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
               if (args.noise != nullptr) sg += args.noise[m];
               args.sigma[m] = fmaxf(sg, 0.f);
             }
-            if (head == 2 || head == 3) {
-              const int b = head == 2 ? 1 : 0;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) args.rgb[m * 3 + c] = __fdividef(1.f, 1.f + __expf(-o[b + c]));
+            if (head == 2 || head == 3) {            // selects, not o[b + c]: a runtime index would put o[] in local memory
+              const float c0 = head == 2 ? o[1] : o[0], c1 = head == 2 ? o[2] : o[1], c2 = head == 2 ? o[3] : o[2];
+              float* dst = args.rgb + m * 3;
+              dst[0] = __fdividef(1.f, 1.f + __expf(-c0));
+              dst[1] = __fdividef(1.f, 1.f + __expf(-c1));
+              dst[2] = __fdividef(1.f, 1.f + __expf(-c2));
             }
           }
           if (warp == EPI_WARP0 && lane == 0) TRACE(2000 + l);

@@ -52,4 +52,4 @@ for k in (0, 1):
         e = [t[o + 1024 + l * 16 + q] - t0 for q in range(1 + 2 * (L.n // 64))]
         print(f'  layer {l}: MMA ' + ' | '.join(mma))
         print(f'           EPI d_full@{e[0]} ' + ' '.join(f'[ld@{e[1 + 2 * q]} st@{e[2 + 2 * q]}]' for q in range(L.n // 64)),
-              f' head done @{t[o + 2000 + l] - t0}' if L.head else '')
+              f' head: enter @{t[o + 2010 + l] - t0} after bar @{t[o + 2020 + l] - t0} done @{t[o + 2000 + l] - t0}' if L.head else '')
