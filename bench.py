@@ -209,8 +209,9 @@ def _time_steps(fn, steps, warmup):
 
 def extras(device):
     """Secondary, informational measurements of the other BASELINE.json configs (single GPU, device-timed):
-    Simple-TensoRF frame render (configs[3] shape) and one Simple-NeRF training iteration (configs[1] shape:
-    4096 rays, main coarse + fine + both augmented MLPs, forward + hand-written tcgen05 backward + Adam step)."""
+    Simple-TensoRF frame render (configs[3] shape), one Simple-NeRF training iteration (configs[1] shape: 4096 rays,
+    main coarse + fine + both augmented MLPs, forward + hand-written tcgen05 backward + Adam step) and one Simple-TensoRF
+    training iteration (configs[2] shape)."""
     from simple_rf_b200 import synthetic
     from simple_rf_b200.models.SimpleNeRF91 import SimpleNeRF
     from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask, SimpleTensoRF
@@ -265,6 +266,39 @@ def extras(device):
                                               'note': 'forward + dgrad + wgrad on tcgen05 kernels, compositing backward hand-written; synthetic MSE + depth-consistency loss'}
     except Exception as e:
         out['simple_nerf_train_iteration'] = {'error': repr(e)[:200]}
+    # ---- Simple-TensoRF training iteration (configs[2] shape): 4096 rays, 300^3-class main tensor + points-augmentation
+    # tensor, alpha mask set, Adam step; every kernel of forward and backward is hand-written
+    try:
+        cfg = synthetic.tensorf_configs(num_voxels=300 ** 3, augmentations=True, rng_mode='device')
+        mc = synthetic.scene_model_configs('re10k', num_views=3)
+        torch.manual_seed(0)
+        model = SimpleTensoRF(cfg, mc).to(device).train()
+        t = model.coarse_model
+        with torch.no_grad():
+            for p_ in t.matrices_density:
+                p_.mul_(6.0)
+        vol = (torch.rand(190, 190, 190, generator=torch.Generator().manual_seed(1)) < 0.05).float()
+        t.alpha_mask = AlphaGridMask(vol, t.bounding_box.cpu()).to(device)
+        opt = torch.optim.Adam(model.get_trainable_parameters(cfg['optimizers'][0]), betas=(0.9, 0.99))
+        h, w = mc['resolution']
+        g = torch.Generator().manual_seed(2)
+        pid = torch.stack([torch.randint(0, 3, (4096,), generator=g), torch.randint(0, w, (4096,), generator=g),
+                           torch.randint(0, h, (4096,), generator=g)], 1).int().to(device)
+        target = torch.rand(4096, 3, device=device)
+
+        def tstep():
+            opt.zero_grad(set_to_none=True)
+            o = model({'pixel_id': pid, 'num_frames': 3, 'iter_num': 0, 'sub_batch_index': 0})
+            loss = sum(((o[k] - target) ** 2).mean() for k in ('rgb_coarse', 'points_augmentation_rgb_coarse'))
+            loss = loss + 0.1 * (o['depth_coarse'] - o['points_augmentation_depth_coarse'].detach()).square().mean()
+            loss.backward()
+            opt.step()
+        ms = _time_steps(tstep, steps=3, warmup=2)
+        out['simple_tensorf_train_iteration'] = {'iters_per_sec': 1e3 / ms, 'ms_per_iter': ms, 'rays_per_iter': 4096,
+                                                 'samples_per_ray': int(t.num_samples),
+                                                 'note': 'VM gathers / scatters, colour MLP forward + dgrad + wgrad on tcgen05, compositing fwd/bwd; synthetic MSE + depth-consistency loss'}
+    except Exception as e:
+        out['simple_tensorf_train_iteration'] = {'error': repr(e)[:200]}
     return out
 
 

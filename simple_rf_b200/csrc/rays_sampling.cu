@@ -225,6 +225,24 @@ struct PdfParams {
   int S, N, npad;
 };
 
+// ascending bitonic sort of n (a power of two) floats in shared memory by one warp; j, k are powers of two, so pair
+// indices are built with shifts (no integer division on the hot loop)
+__device__ __forceinline__ void bitonic_sort_smem(float* v, int n, int lane) {
+  for (int k = 2, lk = 1; k <= n; k <<= 1, ++lk) {
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
+      for (int q = lane; q < (n >> 1); q += 32) {
+        const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
+        const int l = i | j;
+        const float a = v[i], b = v[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { v[i] = b; v[l] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(PDF_WARPS * 32) sample_pdf_merge_kernel(PdfParams p) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -249,10 +267,47 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) sample_pdf_merge_kernel(PdfPar
   const float total = aten_row_sum(cdf, n);
   __syncwarp();
   for (int i = lane; i < nb; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zc[i + 1], zc[i]));
-  // pdf, then the sequential fp64 prefix sum of ATen's cumsum, shifted by one for the leading 0
-  for (int i = lane; i < n; i += 32) cdf[i] = __fdiv_rn(cdf[i], total);
+  // pdf, then ATen's cumsum (sequential fp64 accumulation, each prefix rounded to fp32), shifted by one for the leading 0.
+  // The pdf values are fp32 numbers that sum to ~1: when the smallest one is >= 2^-28 every fp64 partial sum is EXACT
+  // (48 significant bits at most), so the additions may be re-associated without changing a single bit and the prefix
+  // sum runs as a warp scan.  Otherwise (weights far outside [0, 1]) one lane reproduces the sequential order.
+  float pmin = __int_as_float(0x7f800000);
+  for (int i = lane; i < n; i += 32) {
+    const float pv = __fdiv_rn(cdf[i], total);
+    cdf[i] = pv;
+    pmin = fminf(pmin, pv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pmin = fminf(pmin, __shfl_xor_sync(FULL, pmin, o));
   __syncwarp();
-  if (lane == 0) {
+  constexpr int MAXC = 8;
+  const int per = (n + 31) >> 5;
+  if (per <= MAXC && pmin >= 3.7252903e-09f) {
+    float pv[MAXC];
+    const int i0 = lane * per;
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      pv[q] = (q < per && i0 + q < n) ? cdf[i0 + q] : 0.f;
+      tot += (double)pv[q];
+    }
+    double incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    double acc = incl - tot;
+    __syncwarp();                            // every lane holds its pdf values in registers before cdf is overwritten
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      if (q < per && i0 + q < n) {
+        acc += (double)pv[q];
+        cdf[i0 + q + 1] = (float)acc;
+      }
+    }
+    if (lane == 0) cdf[0] = 0.f;
+  } else if (lane == 0) {
     double acc = 0.0;
     float prev = 0.f;                     // cdf[0]
     for (int i = 0; i < n; ++i) {
@@ -288,20 +343,58 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) sample_pdf_merge_kernel(PdfPar
     if (p.above) p.above[r * N + j] = a;
   }
   __syncwarp();
-  // bitonic sort of npad values (coarse depths + new samples + inf padding), ascending; j, k are powers of
-  // two, so pair indices are built with shifts (no integer division on the hot loop)
-  for (int k = 2, lk = 1; k <= npad; k <<= 1, ++lk) {
-    for (int lj = lk - 1; lj >= 0; --lj) {
-      const int j = 1 << lj;
-      for (int q = lane; q < (npad >> 1); q += 32) {
-        const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
-        const int l = i | j;
-        const float a = sbuf[i], b = sbuf[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { sbuf[i] = b; sbuf[l] = a; }
+  // merge.  Both runs are normally sorted already (coarse depths by construction, the new samples whenever u is sorted:
+  // the inverse CDF is monotone), so each element's final position is its own index plus its rank in the other run
+  // (binary searches; ties: coarse depths first - equal values make the order immaterial for the sorted VALUES the
+  // reference's torch.sort returns).  Unsorted input (random u in training) takes the bitonic network below.
+  constexpr int MAXQ = 8;
+  const bool small = (S + 31) / 32 <= MAXQ && (N + 31) / 32 <= MAXQ;
+  bool z_sorted = true, s_sorted = true;
+  for (int i = lane; i < S - 1; i += 32) z_sorted = z_sorted && (sbuf[i] <= sbuf[i + 1]);
+  for (int j = lane; j < N - 1; j += 32) s_sorted = s_sorted && (sbuf[S + j] <= sbuf[S + j + 1]);
+  z_sorted = __all_sync(FULL, z_sorted);
+  s_sorted = __all_sync(FULL, s_sorted);
+  int np2 = 2;
+  while (np2 < N) np2 <<= 1;
+  if (small && z_sorted && !s_sorted && S + np2 <= npad) {
+    bitonic_sort_smem(sbuf + S, np2, lane);           // random u (training): sort the new samples only (+inf padded)
+    s_sorted = true;
+  }
+  if (small && z_sorted && s_sorted) {
+    float vz[MAXQ], vs[MAXQ];
+    int pz[MAXQ], ps[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      const int i = lane + 32 * q;
+      pz[q] = -1; ps[q] = -1; vz[q] = 0.f; vs[q] = 0.f;
+      if (i < S) {                                    // coarse depth i: rank = number of samples strictly below it
+        const float v = sbuf[i];
+        int lo = 0, hi = N;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sbuf[S + mid] < v) lo = mid + 1; else hi = mid;
+        }
+        vz[q] = v; pz[q] = i + lo;
       }
-      __syncwarp();
+      if (i < N) {                                    // sample i: rank = number of coarse depths <= it
+        const float v = sbuf[S + i];
+        int lo = 0, hi = S;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sbuf[mid] <= v) lo = mid + 1; else hi = mid;
+        }
+        vs[q] = v; ps[q] = i + lo;
+      }
     }
+    __syncwarp();                                     // all reads done before the scatter overwrites sbuf
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      if (pz[q] >= 0) sbuf[pz[q]] = vz[q];
+      if (ps[q] >= 0) sbuf[ps[q]] = vs[q];
+    }
+    __syncwarp();
+  } else {
+    bitonic_sort_smem(sbuf, npad, lane);              // coarse depths + new samples + inf padding
   }
   const int M = S + N;
   for (int i = lane; i < M; i += 32) p.z_fine[r * M + i] = sbuf[i];

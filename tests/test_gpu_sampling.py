@@ -109,6 +109,27 @@ def test_sample_pdf_bit_exact_vs_oracle(S, N, R, det):
     assert bool((z_f[:, 1:] >= z_f[:, :-1]).all())
 
 
+@pytest.mark.parametrize('det', [True, False])
+def test_sample_pdf_extreme_weights_and_ties(det):
+    """Weights far outside [0, 1] (fp64 prefix sums no longer exact: the sequential order must be reproduced), repeated
+    coarse depths and zero-weight stretches (ties in the merge): still bit-identical to the ATen CPU path."""
+    from simple_rf_b200 import ops
+    R, S, N = 4000, 64, 128
+    g = torch.Generator().manual_seed(5)
+    z = torch.sort(torch.rand(R, S, generator=g), -1)[0]
+    z[::5, 10:14] = z[::5, 10:11]                      # repeated depths
+    w = torch.rand(R, S, generator=g)
+    w[::2, 7] = 3e5                                     # one dominant bin: the smallest pdf value drops below 2^-28
+    w[1::4, 20:40] = 0
+    w[2::9] = 0                                         # all-zero rows: uniform pdf from the 1e-5 floor
+    u = (torch.linspace(0., 1., steps=N).expand(R, N) if det else torch.rand(R, N, generator=g)).contiguous()
+    z_ref, s_ref, b_ref, a_ref = SP.fine_depths(z, w, u)
+    z_f, s_, b, a = ops.sample_pdf_merge(z.to(DEV), w.to(DEV), N, u=u.to(DEV), return_indices=True)
+    assert torch.equal(b.cpu(), b_ref) and torch.equal(a.cpu(), a_ref)
+    assert torch.equal(s_.cpu(), s_ref)
+    assert torch.equal(z_f.cpu(), z_ref)
+
+
 def test_sample_pdf_philox_mode_is_sorted_superset():
     from simple_rf_b200 import ops
     R, S, N = 513, 64, 128

@@ -64,6 +64,9 @@ for R, S in sizes:
         u = torch.rand(R, 128, device=dev, generator=g)
         ms = timed(lambda: ops.sample_pdf_merge(z, w, 128, u=u))
         report(f'sample_pdf_merge R={R} 64->+128 (u given)', ms, R * (4 * 62 + 4 * 64 + 4 * 128 + 4 * 192))
+        u_det = torch.linspace(0., 1., steps=128, device=dev)
+        ms = timed(lambda: ops.sample_pdf_merge(z, w, 128, u=u_det))
+        report(f'sample_pdf_merge R={R} 64->+128 (deterministic u, test-time path)', ms, R * (4 * 62 + 4 * 64 + 4 * 192))
         ms = timed(lambda: ops.sample_pdf_merge(z, w, 128, philox_seed=1))
         report(f'sample_pdf_merge R={R} 64->+128 (philox)', ms, R * (4 * 62 + 4 * 64 + 4 * 192))
     del sigma, rgb, z
