@@ -200,29 +200,41 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict
   if (threadIdx.x == 0) count[0] = s_carry;
 }
 
-// stable scatter: element order inside a block is k-major over the 4 strips of 256, matching the mask kernels
+// stable scatter: thread t of a block owns the 4 consecutive elements base + 4t .. 4t + 3 (one 32-bit mask load), the
+// block-wide exclusive scan of the per-thread counts is one shuffle scan per warp plus an 8-entry exchange; blocks whose
+// count is zero (most of them behind a sparse alpha mask) exit after one load
 __global__ void __launch_bounds__(256) compact_scatter_kernel(const uint8_t* __restrict__ mask, long long total,
-                                                              const int* __restrict__ offsets, int* __restrict__ idx) {
+                                                              const int* __restrict__ counts, const int* __restrict__ offsets,
+                                                              int* __restrict__ idx) {
+  if (counts[blockIdx.x] == 0) return;
   __shared__ int s_warp[8];
-  __shared__ int s_base;
-  const long long base = (long long)blockIdx.x * CMP_BLOCK;
-  if (threadIdx.x == 0) s_base = offsets[blockIdx.x];
-  __syncthreads();
+  const long long i0 = (long long)blockIdx.x * CMP_BLOCK + threadIdx.x * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = 0; k < 4; ++k) {
-    const long long i = base + k * 256 + threadIdx.x;
-    const bool ok = i < total && mask[i] != 0;
-    const unsigned bal = __ballot_sync(FULL, ok);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, strip = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; if (w < warp) before += c; strip += c; }
-    if (ok) idx[s_base + before + __popc(bal & ((1u << lane) - 1))] = (int)i;
-    __syncthreads();
-    if (threadIdx.x == 0) s_base += strip;
-    __syncthreads();
+  uint32_t m = 0;
+  if (i0 + 4 <= total && (reinterpret_cast<uintptr_t>(mask + i0) & 3) == 0) {
+    m = *reinterpret_cast<const uint32_t*>(mask + i0);
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k < total) m |= (uint32_t)mask[i0 + k] << (8 * k);
   }
+  const int f0 = (m & 0xffu) != 0, f1 = (m & 0xff00u) != 0, f2 = (m & 0xff0000u) != 0, f3 = (m & 0xff000000u) != 0;
+  const int mine = f0 + f1 + f2 + f3;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int before = offsets[blockIdx.x] + incl - mine;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (w < warp) before += s_warp[w];
+  if (f0) idx[before++] = (int)i0;
+  if (f1) idx[before++] = (int)(i0 + 1);
+  if (f2) idx[before++] = (int)(i0 + 2);
+  if (f3) idx[before] = (int)(i0 + 3);
 }
 
 // ------------------------------------------------------------------------------------------ VM gathers
@@ -602,7 +614,7 @@ SRF_API int srf_compact(const uint8_t* mask, int64_t total, int* block_counts, i
   SRF_REQUIRE(total < (1ll << 31), "srf_compact", "more than 2^31 samples in one call");
   const int nb = srf_compaction_blocks(total);
   scan_blocks_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(block_counts, nb, block_offsets, count);
-  compact_scatter_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(mask, total, block_offsets, indices);
+  compact_scatter_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(mask, total, block_counts, block_offsets, indices);
   return check_launch("srf_compact");
 }
 
