@@ -175,8 +175,9 @@ __device__ __forceinline__ RayConsts ray_consts(const P& p, long long r) {
 // with the multi-value butterfly above.  Runs are aligned in the FLAT [R*S] arrays, so any S (e.g. TensoRF's 1083)
 // vectorises: elements of the neighbouring rays that fall into a ray's first / last run are loaded but masked.
 // L is chosen by the host so that the steps cover S with few idle lanes (64 -> 2, 128 -> 4, 192 -> 6, 256 -> 8).
-// NC > 0: at most NC steps, weights and depths stay in registers for the variance pass; NC == 0: any length, the
-// variance pass re-reads what the lane wrote.
+// NC == 1: a single step, weights and depths stay in registers for the variance pass; NC == 0: any length, the variance
+// pass re-reads what the lane wrote (L2 hits).  Keeping 2-4 steps in registers was measured slower (512 samples: 47 % ->
+// 60 % of HBM peak without it): the registers cost more occupancy than the re-read costs bandwidth.
 template <int L, int NC>
 __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(CompositeFwd p) {
   constexpr int G = L % 4 == 0 ? 4 : 2;          // alignment granule of a run (floats)
@@ -486,13 +487,9 @@ SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float*
   const int steps = (span + 32 * L - 1) / (32 * L);
   if (L == 2) {
     if (steps <= 1) composite_fwd_kernel<2, 1><<<blocks, blk, 0, st>>>(p);
-    else if (steps <= 2) composite_fwd_kernel<2, 2><<<blocks, blk, 0, st>>>(p);
-    else if (steps <= 3) composite_fwd_kernel<2, 3><<<blocks, blk, 0, st>>>(p);
     else composite_fwd_kernel<2, 0><<<blocks, blk, 0, st>>>(p);
   } else {
     if (steps <= 1) composite_fwd_kernel<4, 1><<<blocks, blk, 0, st>>>(p);
-    else if (steps <= 2) composite_fwd_kernel<4, 2><<<blocks, blk, 0, st>>>(p);
-    else if (steps <= 4) composite_fwd_kernel<4, 4><<<blocks, blk, 0, st>>>(p);
     else composite_fwd_kernel<4, 0><<<blocks, blk, 0, st>>>(p);
   }
   return check_launch("srf_composite_fwd");
