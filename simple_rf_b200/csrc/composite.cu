@@ -335,7 +335,7 @@ struct CompositeBwd {
 // Backward: one reverse pass with the same run layout; sum_{k>i} g_w[k] w_k is a sequential suffix sum inside the run
 // plus one shuffle suffix scan per step (closed form in oracle/composite.py).
 template <int L>
-__global__ void __launch_bounds__(CMP_WARPS * 32, 4) composite_bwd_kernel(CompositeBwd p) {
+__global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? 5 : 4) composite_bwd_kernel(CompositeBwd p) {
   constexpr int G = L % 4 == 0 ? 4 : 2;
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
