@@ -228,6 +228,21 @@ int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* 
                        void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream);
 int srf_dgrad_program_bytes(void);
 
+/* ---- "next" row f1: masks of the patch-reprojection depth losses
+ * (src/loss_functions/AugmentationsDepthLoss11.py:105-182, src/loss_functions/CoarseFineConsistencyLoss34.py:89-164,
+ * src/utils/CommonUtils04.py:227-253).  For each of num_rays image rays: the two candidate depths are reprojected into
+ * the closest other training view (closest_view [V], poses [V,4,4] camera-to-world, intrinsics_first = device pointer to the 3x3
+ * intrinsics of the first ray, which the reference hard-codes), patch_x x patch_y rgb patches of images [V,H,W,3] around
+ * pixel_id [N,3] = (view, x, y) and the two reprojections are compared (RMSE, zeros outside the frame) and mask1 / mask2
+ * [N] (0/1) mark the rays where model 1 / model 2 is the more accurate one.  both_invalid_rule = 1 adds
+ * AugmentationsDepthLoss11.py:178-182 (prefer the larger depth when both reprojections leave the frame).  rmse1 / rmse2 are
+ * optional [N] outputs. */
+int srf_patch_reprojection_masks(const float* rays_o, const float* rays_d, const float* depth1, const float* depth2,
+                                 const int32_t* pixel_id, int64_t num_rays, const int32_t* closest_view, const float* poses,
+                                 const float* intrinsics_first, const float* images, int num_views, int height, int width,
+                                 int patch_x, int patch_y, float rmse_threshold, int both_invalid_rule, uint8_t* mask1,
+                                 uint8_t* mask2, float* rmse1, float* rmse2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

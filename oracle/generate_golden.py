@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import composite as C
+from . import losses as OL
 from . import fixtures as FX
 from . import nerf_mlp as M
 from . import pipeline as P
@@ -230,6 +231,70 @@ def golden_tensorf():
         print(f'tensorf_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f})')
 
 
+def patch_loss_inputs(num_rays=6000, h=96, w=128, seed=0):
+    """Seeded scene for the patch-reprojection losses: smooth random images, three LLFF-like cameras, rays through random
+    pixels, two noisy depth candidates, and a half-random image-ray mask (shared with tests/)."""
+    from simple_rf_b200 import synthetic
+    mc = synthetic.scene_model_configs('llff', num_views=3)
+    g = torch.Generator().manual_seed(seed)
+    v = 3
+    images = torch.rand(v, h, w, 3, generator=g)
+    images = torch.nn.functional.avg_pool2d(images.permute(0, 3, 1, 2), 9, 1, 4).permute(0, 2, 3, 1).contiguous()
+    poses = torch.tensor(np.array(mc['extrinsics']), dtype=torch.float32)
+    k = torch.tensor(np.array(mc['intrinsics']), dtype=torch.float32)[0].clone()
+    k[0, 2], k[1, 2], k[0, 0], k[1, 1] = w / 2, h / 2, 100.0, 100.0
+    pid = torch.stack([torch.randint(0, v, (num_rays,), generator=g), torch.randint(0, w, (num_rays,), generator=g),
+                       torch.randint(0, h, (num_rays,), generator=g)], 1)
+    dirs = torch.stack([(pid[:, 1] - k[0, 2]) / k[0, 0], -(pid[:, 2] - k[1, 2]) / k[1, 1], -torch.ones(num_rays)], -1)
+    c2w = poses[pid[:, 0]]
+    rays_d = (c2w[:, :3, :3] @ dirs[..., None]).squeeze(-1)
+    rays_o = c2w[:, :3, 3].contiguous()
+    d1 = 2 + 6 * torch.rand(num_rays, generator=g)
+    d2 = d1 * (1 + 0.2 * torch.randn(num_rays, generator=g))
+    d2[::17] = -d2[::17]                                        # points behind the other camera
+    d1[5::29] = 1e-3                                            # reprojections far outside the frame
+    mask_nerf = torch.ones(num_rays, dtype=torch.bool)
+    mask_nerf[num_rays // 2:] = torch.rand(num_rays - num_rays // 2, generator=g) < 0.5
+    return dict(images=images, poses=poses, k=k, pixel_id=pid.int(), rays_o=rays_o, rays_d=rays_d, depth1=d1, depth2=d2,
+                mask_nerf=mask_nerf, h=h, w=w)
+
+
+def golden_patch_loss():
+    """both reference loss classes' `compute_loss_nerf` on the seeded scene; the oracle must match
+    loss, loss maps and gradients bit-exactly."""
+    H.import_reference()
+    from loss_functions.AugmentationsDepthLoss11 import AugmentationsDepthLoss
+    from loss_functions.CoarseFineConsistencyLoss34 import CoarseFineConsistencyLoss
+    a = patch_loss_inputs()
+    fixture = {k_: v_ for k_, v_ in a.items()}
+    n = a['depth1'].shape[0]
+    intr = a['k'][None].expand(n, 3, 3)
+    for tag, cls, rule in (('aug', AugmentationsDepthLoss, True), ('cf', CoarseFineConsistencyLoss, False)):
+        d1 = a['depth1'].clone().requires_grad_()
+        d2 = a['depth2'].clone().requires_grad_()
+        obj = cls({'model': {'coarse_model': {}, 'fine_model': {}}, 'data_loader': {}}, {'patch_size': [5, 5], 'rmse_threshold': 0.1})
+        loss, map1, map2 = obj.compute_loss_nerf(d1, d2, a['mask_nerf'], a['rays_o'], a['rays_d'], a['poses'], a['images'],
+                                                 a['pixel_id'].long(), intr, (a['h'], a['w']))
+        g1, g2 = torch.autograd.grad(loss, [d1, d2], allow_unused=True)
+        g1 = torch.zeros(n) if g1 is None else g1
+        g2 = torch.zeros(n) if g2 is None else g2
+        m = a['mask_nerf']
+        e1 = a['depth1'].clone().requires_grad_()
+        e2 = a['depth2'].clone().requires_grad_()
+        m1, m2, r1, r2 = OL.patch_reprojection_masks(a['rays_o'][m], a['rays_d'][m], e1[m], e2[m], a['pixel_id'][m], a['poses'], a['k'],
+                                                     a['images'], (5, 5), 0.1, rule)
+        oloss, omap1, omap2 = OL.masked_depth_loss(e1[m], e2[m], m1, m2)
+        h1, h2 = torch.autograd.grad(oloss, [e1, e2], allow_unused=True)
+        h1 = torch.zeros(n) if h1 is None else h1
+        h2 = torch.zeros(n) if h2 is None else h2
+        for name, ref, mine in (('loss', loss, oloss), ('map1', map1, omap1), ('map2', map2, omap2), ('g1', g1, h1), ('g2', g2, h2)):
+            _check(f'patch_loss.{tag}.{name}', ref.detach(), mine.detach())
+        fixture.update({f'{tag}_loss': loss, f'{tag}_map1': map1, f'{tag}_map2': map2, f'{tag}_g1': g1, f'{tag}_g2': g2,
+                        f'{tag}_mask1': m1, f'{tag}_mask2': m2, f'{tag}_rmse1': r1, f'{tag}_rmse2': r2})
+        print(f'patch_loss {tag}: oracle == reference (mask1 {m1.float().mean():.3f}, mask2 {m2.float().mean():.3f}, loss {loss.item():.5f})')
+    np.savez_compressed(OUT / 'patch_loss.npz', **_np(fixture))
+
+
 def main():
     if not H.available():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
@@ -239,6 +304,7 @@ def main():
     golden_sample_pdf()
     golden_composite(copy.deepcopy(configs), model_configs)
     golden_tensorf()
+    golden_patch_loss()
 
 
 if __name__ == '__main__':

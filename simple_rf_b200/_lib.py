@@ -31,6 +31,8 @@ _SIGNATURES = {
     'srf_compaction_blocks': (c_int, [c_int64]),
     'srf_tensorf_mask': (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_threshold_mask': (c_int, [_P, c_float, c_int64, _P, _P, _P]),
+    'srf_patch_reprojection_masks': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                             _P, _P, _P, _P, _P]),
     'srf_compact': (c_int, [_P, c_int64, _P, _P, _P, _P, _P]),
     'srf_vm_density_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P]),
     'srf_vm_density_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P]),

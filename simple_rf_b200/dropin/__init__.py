@@ -9,10 +9,19 @@ Python call at all is to copy / symlink the two shim files into `<reference>/src
 from pathlib import Path
 
 SHIM_DIR = Path(__file__).resolve().parent / 'models_shims'
+LOSS_SHIM_DIR = Path(__file__).resolve().parent / 'loss_shims'
 
 
 def install():
+    """Models (`SimpleNeRF91`, `SimpleTensoRF91`) and the fused patch-reprojection losses (`AugmentationsDepthLoss91`,
+    `CoarseFineConsistencyLoss91`, resolved by src/loss_functions/LossComputer03.py:21-32 the same way)."""
     import models  # the reference's package: <reference>/src must already be on sys.path
     if str(SHIM_DIR) not in list(models.__path__):
         models.__path__.append(str(SHIM_DIR))
+    try:
+        import loss_functions
+        if str(LOSS_SHIM_DIR) not in list(loss_functions.__path__):
+            loss_functions.__path__.append(str(LOSS_SHIM_DIR))
+    except ImportError:
+        pass
     return SHIM_DIR
