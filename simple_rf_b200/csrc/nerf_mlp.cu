@@ -76,6 +76,22 @@ struct MlpArgs {
 #ifndef SRF_MLP_PREFETCH
 #define SRF_MLP_PREFETCH 0
 #endif
+//   SRF_MLP_ISSUER   2: lean MMA issue path (packed schedule entries, one statement per K block); 1: the previous one
+#ifndef SRF_MLP_ISSUER
+#define SRF_MLP_ISSUER 2
+#endif
+//   SRF_MLP_TS       1: hidden activations never leave tensor memory: the epilogue packs them to bf16 and writes them back
+//                       with tcgen05.st over the accumulator columns it just drained, and the next layer's MMAs take A
+//                       from TMEM (".ts" form).  Shared memory then carries only the weights (and the E / V encodings):
+//                       the SS form spends 96 B/clk of the 128 B/clk shared-memory bandwidth on operand reads and the
+//                       epilogue another 32 B/clk on the activation stores, which is what bounded the kernel.
+#ifndef SRF_MLP_TS
+#define SRF_MLP_TS 1
+#endif
+//   SRF_MLP_PIPE     1: the TMEM load of the next 64-column block is issued before the stores / fence / arrive of the current one
+#ifndef SRF_MLP_PIPE
+#define SRF_MLP_PIPE 0
+#endif
 // SRF_MLP_TRACE: CTA 0 records clock64() at pipeline events of its 3rd and 4th tile into a global buffer (tools/mlp_trace.py)
 #ifndef SRF_MLP_TRACE
 #define SRF_MLP_TRACE 0
@@ -95,12 +111,31 @@ constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 4);
 constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
 constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
+#if SRF_MLP_TS
+static_assert(SRF_MLP_GROUPS == 2 && SRF_MLP_ISSUER == 2, "the TMEM-resident activation layout assumes two 32-column groups per block");
+constexpr int NUM_STAGES = 5;
+constexpr int A_REGIONS = 2;                      // E and V only; H lives in tensor memory
+#else
 constexpr int NUM_STAGES = 3;
+constexpr int A_REGIONS = 6;
+#endif
+constexpr int V_REGION = A_REGIONS - 1;
 constexpr int MAX_SIDE = 4096;                    // floats
 constexpr int MAX_STEPS = MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
 
 // One K-block step of the MMA issuer.  The host flattens the layer program into this schedule and passes it as a kernel
 // parameter: the issuing warp reads it with uniform constant-bank loads, so step data never leaves uniform registers.
+#if SRF_MLP_ISSUER == 2
+struct alignas(16) MmaStep {
+  uint32_t a_off;         // (byte offset of the A region inside MlpSmem::a) >> 4
+  uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
+  // bits 0-2: 16-wide K steps to issue; 3: first step of the layer (overwrite the accumulator); 4: last step of the layer
+  // (commit d_full); 5 / 6: last reader of region 0 / 5 (commit e_free / v_free); 8-11: 1 + region whose a_ready barrier
+  // must be acquired first (0: none); 12: layer index & 1 (selects the accumulator buffer); 13: A operand in tensor memory
+  uint32_t meta;
+  uint32_t pad_;
+};
+#else
 struct alignas(16) MmaStep {
   uint32_t a_off;         // (byte offset of the A region inside MlpSmem::a) >> 4
   uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
@@ -110,6 +145,7 @@ struct alignas(16) MmaStep {
   uint8_t first;          // first step of the layer: overwrite the accumulator
   uint8_t flags;          // 1: last step of the layer (commit d_full); 2 / 4: last reader of region 0 / 5 (commit e_free / v_free)
 };
+#endif
 struct MmaSchedule {
   int32_t num_steps;
   int32_t pad_[3];
@@ -117,7 +153,7 @@ struct MmaSchedule {
 };
 
 struct alignas(1024) MlpSmem {
-  uint8_t a[6][KBLOCK_BYTES];             // E, H0..H3, V
+  uint8_t a[A_REGIONS][KBLOCK_BYTES];     // E, H0..H3, V  (TS: E, V)
   uint8_t w[NUM_STAGES][STAGE_BYTES];
   float side[MAX_SIDE];
   float part[2][GROUPS][128][4];          // head partial sums of each column group
@@ -208,6 +244,56 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (uniform control
     // flow), one elected lane issues tcgen05.mma / tcgen05.commit
+#if SRF_MLP_ISSUER == 2
+    // lean issue path: one 16-byte schedule entry per step (prefetched one step ahead), 32-bit descriptor words,
+    // barrier addresses as plain shared-memory offsets, one statement for the four MMAs of a K block
+    const int num_steps = sched.num_steps;
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+    const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
+    const uint32_t a_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
+    const uint32_t bar_full = ptx::smem_u32(&sm.w_full[0]), bar_empty = ptx::smem_u32(&sm.w_empty[0]);
+    const uint32_t bar_a = ptx::smem_u32(&sm.a_ready[0]), bar_d = ptx::smem_u32(&sm.d_full[0]);
+    const uint32_t bar_e = ptx::smem_u32(&sm.e_free), bar_v = ptx::smem_u32(&sm.v_free);
+    const uint4* steps = reinterpret_cast<const uint4*>(sched.steps);
+    uint32_t stage = 0, ph = 0, parity = 0;
+    uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
+    for (int t = 0; t < my_tiles; ++t) {
+      uint4 nxt = steps[0];
+      for (int s = 0; s < num_steps; ++s) {
+        const uint4 st = nxt;           // x: A offset >> 4, y: instruction descriptor, z: packed step data
+        nxt = steps[s + 1 < num_steps ? s + 1 : 0];
+        const uint32_t meta = st.z;
+        const uint32_t wr = (meta >> 8) & 15u;
+        if (wr) {
+          ptx::mbar_wait_addr(bar_a + (wr - 1) * 8, (a_phase >> (wr - 1)) & 1);
+          a_phase ^= 1u << (wr - 1);
+        }
+        if (lane == 0) TRACE(16 + s * 4 + 0);
+        ptx::mbar_wait_addr(bar_full + stage * 8, ph);
+        if (lane == 0) TRACE(16 + s * 4 + 1);
+        ptx::tc_fence_after();
+        const uint32_t buf = ((meta >> 12) ^ parity) & 1;
+        const uint32_t issue = ptx::elect_one();
+#if SRF_MLP_TS
+        if (meta & 0x2000u)            // A = H block of the previous layer, in the other accumulator buffer's columns
+          ptx::umma4_bf16_ts_if(issue, tmem + buf * 256, tmem + (buf ^ 1u) * 256 + st.x, 32u, w_lo + stage * (STAGE_BYTES >> 4),
+                                desc_hi, st.y, (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
+        else
+#endif
+        ptx::umma4_bf16_if(issue, tmem + buf * 256, a_lo + st.x, w_lo + stage * (STAGE_BYTES >> 4), desc_hi, st.y,
+                           (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
+        ptx::umma_commit_addr_if(issue, bar_empty + stage * 8);
+        if (meta & 0x70u) {
+          if (meta & 0x10u) ptx::umma_commit_addr_if(issue, bar_d + buf * 8);
+          if (meta & 0x20u) ptx::umma_commit_addr_if(issue, bar_e);
+          if (meta & 0x40u) ptx::umma_commit_addr_if(issue, bar_v);
+        }
+        if (lane == 0) TRACE(16 + s * 4 + 2);
+        if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
+      }
+      parity ^= (uint32_t)prog.num_layers & 1u;
+    }
+#else
     const int num_steps = sched.num_steps;
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
     const uint32_t w_desc_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
@@ -250,6 +336,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       }
       layer_base += (uint32_t)prog.num_layers;
     }
+#endif
   } else if (warp >= ENC_WARP0) {
     // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
     const int row = (warp - ENC_WARP0) * 32 + lane;
@@ -307,7 +394,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       if (warp == ENC_WARP0 && lane == 0) TRACE(1);
       if (has_views) {
         ptx::mbar_wait(&sm.v_free, (t & 1) ^ 1);
-        uint8_t* V = sm.a[5];
+        uint8_t* V = sm.a[V_REGION];
         const int vdeg = prog.views_degree;
         if (args.rows != nullptr) {
 #pragma unroll
@@ -413,6 +500,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
                   make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
           if (!write_h) return;
+#if SRF_MLP_TS
+          // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained
+          ptx::tmem_st16(t_row + kb * 64, pk);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
+          return;
+#else
           uint8_t* H = sm.a[1 + kb];
 #pragma unroll
           for (int u = 0; u < COLS / 8; ++u)
@@ -421,6 +517,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
+#endif
         };
 
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
@@ -443,6 +540,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             store(pk, kb + 1);
           }
         }
+#elif SRF_MLP_PIPE
+        uint32_t va[COLS], pk[COLS / 2];
+        tmem_load<COLS>(t_row, va);
+        for (int kb = 0; kb < nblocks; ++kb) {
+          ptx::tmem_ld_wait(va);
+          compute(va, pk, kb);                                            // va is dead after this: reload it for the next
+          if (kb + 1 < nblocks) tmem_load<COLS>(t_row + (kb + 1) * 64, va);   // block while this one is stored and published
+          store(pk, kb);
+        }
+        ptx::tmem_ld_wait();
 #else
         uint32_t va[COLS], pk[COLS / 2];
         for (int kb = 0; kb < nblocks; ++kb) {
@@ -549,21 +656,39 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
     for (int kb = 0; kb < L.num_kblocks; ++kb, ++ns) {
       MmaStep& st = sc.steps[ns];
       const int reg = L.kblock_region[kb];
+#if SRF_MLP_TS
+      st.a_off = reg == 0 ? 0u : (reg == 5 ? (uint32_t)(V_REGION * KBLOCK_BYTES) >> 4 : (uint32_t)(reg - 1) * 64u);   // smem / TMEM column
+#else
       st.a_off = (uint32_t)(reg * KBLOCK_BYTES) >> 4;
+#endif
       st.idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
+      const bool wait = !((seen >> reg) & 1);
+      seen |= 1u << reg;
+#if SRF_MLP_ISSUER == 2
+      st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 ? 8u : 0u) | (kb == L.num_kblocks - 1 ? 0x10u : 0u) |
+                (wait ? (uint32_t)(reg + 1) << 8 : 0u) | ((uint32_t)(l & 1) << 12);
+#if SRF_MLP_TS
+      if (reg >= 1 && reg <= 4) st.meta |= 0x2000u;
+#endif
+#else
       st.layer = l;
       st.ksteps = (int8_t)L.kblock_ksteps[kb];
-      st.wait_region = ((seen >> reg) & 1) ? (int8_t)-1 : (int8_t)reg;
-      seen |= 1u << reg;
+      st.wait_region = wait ? (int8_t)reg : (int8_t)-1;
       st.first = kb == 0;
       st.flags = kb == L.num_kblocks - 1 ? 1 : 0;
+#endif
       if (reg == 0) last_e = ns;
       if (reg == 5) last_v = ns;
     }
     if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
   }
+#if SRF_MLP_ISSUER == 2
+  if (last_e >= 0) sc.steps[last_e].meta |= 0x20u;
+  if (last_v >= 0) sc.steps[last_v].meta |= 0x40u;
+#else
   if (last_e >= 0) sc.steps[last_e].flags |= 2;
   if (last_v >= 0) sc.steps[last_v].flags |= 4;
+#endif
   sc.num_steps = ns;
   return sc;
 }

@@ -91,6 +91,110 @@ __device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t d_tmem, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
+// One 64-wide K block = up to four K=16 MMAs in ONE statement: the descriptors are passed as their 32-bit low words
+// (start address >> 4; the constant high word is attached inside), so the per-MMA 64-bit carry chains and the repeated
+// register -> uniform-register moves of four separate statements disappear from the issuing warp's critical path.
+// `ksteps` (1..4) MMAs are issued; the first one overwrites the accumulator when accumulate == 0.
+__device__ __forceinline__ void umma4_bf16_if(uint32_t issue, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t ksteps) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, ptrue, q0, q1, q2, q3;\n\t"
+      ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+      ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.b32 ptrue, 0, 0;\n\t"
+      "setp.ne.b32 q0, %6, 0;\n\t"
+      "setp.gt.and.u32 q1, %7, 1, q0;\n\t"
+      "setp.gt.and.u32 q2, %7, 2, q0;\n\t"
+      "setp.gt.and.u32 q3, %7, 3, q0;\n\t"
+      "add.u32 a1, %1, 2;\n\t"
+      "add.u32 a2, %1, 4;\n\t"
+      "add.u32 a3, %1, 6;\n\t"
+      "add.u32 b1, %2, 2;\n\t"
+      "add.u32 b2, %2, 4;\n\t"
+      "add.u32 b3, %2, 6;\n\t"
+      "mov.b64 da0, {%1, %3};\n\t"
+      "mov.b64 da1, {a1, %3};\n\t"
+      "mov.b64 da2, {a2, %3};\n\t"
+      "mov.b64 da3, {a3, %3};\n\t"
+      "mov.b64 db0, {%2, %3};\n\t"
+      "mov.b64 db1, {b1, %3};\n\t"
+      "mov.b64 db2, {b2, %3};\n\t"
+      "mov.b64 db3, {b3, %3};\n\t"
+      "@q0 tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %4, pacc;\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da1, db1, %4, ptrue;\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da2, db2, %4, ptrue;\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da3, db3, %4, ptrue;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps)
+      : "memory");
+}
+// Same, A operand in tensor memory (".ts" form): a_tmem is the TMEM address of the 128-lane x 8-column block holding the
+// K = 16 slice of A as packed bf16 pairs (row m in lane m, elements 2c / 2c+1 in the low / high half of column c);
+// the four slices of a 64-wide K block sit at a_tmem + {0, 8, off2, off2 + 8}.
+__device__ __forceinline__ void umma4_bf16_ts_if(uint32_t issue, uint32_t d_tmem, uint32_t a_tmem, uint32_t off2, uint32_t b_lo,
+                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate, uint32_t ksteps) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, ptrue, q0, q1, q2, q3;\n\t"
+      ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+      ".reg .b64 db0, db1, db2, db3;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.b32 ptrue, 0, 0;\n\t"
+      "setp.ne.b32 q0, %6, 0;\n\t"
+      "setp.gt.and.u32 q1, %7, 1, q0;\n\t"
+      "setp.gt.and.u32 q2, %7, 2, q0;\n\t"
+      "setp.gt.and.u32 q3, %7, 3, q0;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.u32 a2, %1, %8;\n\t"
+      "add.u32 a3, a2, 8;\n\t"
+      "add.u32 b1, %2, 2;\n\t"
+      "add.u32 b2, %2, 4;\n\t"
+      "add.u32 b3, %2, 6;\n\t"
+      "mov.b64 db0, {%2, %3};\n\t"
+      "mov.b64 db1, {b1, %3};\n\t"
+      "mov.b64 db2, {b2, %3};\n\t"
+      "mov.b64 db3, {b3, %3};\n\t"
+      "@q0 tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db0, %4, pacc;\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], db1, %4, ptrue;\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], db2, %4, ptrue;\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], db3, %4, ptrue;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps), "r"(off2)
+      : "memory");
+}
+// thread i of the warp writes 16 consecutive 32-bit columns of lane (lane base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit_addr_if(uint32_t issue, uint32_t bar_smem_addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar_smem_addr), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_smem_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar_smem_addr), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_if(uint32_t issue, uint64_t* bar) {
   asm volatile(
       "{\n\t"
