@@ -76,9 +76,12 @@ struct MlpArgs {
 #ifndef SRF_MLP_PREFETCH
 #define SRF_MLP_PREFETCH 0
 #endif
-//   SRF_MLP_ISSUER   2: lean MMA issue path (packed schedule entries, one statement per K block); 1: the previous one
+//   SRF_MLP_ISSUER   2: lean MMA issue path (packed schedule entries, one statement per K block); 1: the previous one;
+//                    3: two issuing warps take alternate K-block steps (each prepares its next step - schedule entry,
+//                       barrier acquisition, descriptors - while the other one issues; a named-barrier token keeps the
+//                       MMAs in schedule order)
 #ifndef SRF_MLP_ISSUER
-#define SRF_MLP_ISSUER 2
+#define SRF_MLP_ISSUER 3
 #endif
 //   SRF_MLP_TS       1: hidden activations never leave tensor memory: the epilogue packs them to bf16 and writes them back
 //                       with tcgen05.st over the accumulator columns it just drained, and the next layer's MMAs take A
@@ -107,12 +110,18 @@ constexpr int COLS = 64 / GROUPS;                 // columns of a 64-wide block 
 constexpr int EPI_THREADS = 128 * GROUPS;
 constexpr int EPI_WARP0 = 2;                      // warp 0 weight producer, warp 1 MMA issuer
 constexpr int ENC_WARP0 = EPI_WARP0 + 4 * GROUPS; // 4 encoding warps (one row per thread) run one tile ahead
+#if SRF_MLP_ISSUER == 3
+constexpr int ISSUER2_WARP = ENC_WARP0 + 4;
+constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 5);
+#else
+constexpr int ISSUER2_WARP = -1;
 constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 4);
+#endif
 constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
 constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
 #if SRF_MLP_TS
-static_assert(SRF_MLP_GROUPS == 2 && SRF_MLP_ISSUER == 2, "the TMEM-resident activation layout assumes two 32-column groups per block");
+static_assert(SRF_MLP_GROUPS == 2 && SRF_MLP_ISSUER >= 2, "the TMEM-resident activation layout assumes two 32-column groups per block");
 constexpr int NUM_STAGES = 5;
 constexpr int A_REGIONS = 2;                      // E and V only; H lives in tensor memory
 #else
@@ -125,13 +134,14 @@ constexpr int MAX_STEPS = MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
 
 // One K-block step of the MMA issuer.  The host flattens the layer program into this schedule and passes it as a kernel
 // parameter: the issuing warp reads it with uniform constant-bank loads, so step data never leaves uniform registers.
-#if SRF_MLP_ISSUER == 2
+#if SRF_MLP_ISSUER >= 2
 struct alignas(16) MmaStep {
   uint32_t a_off;         // (byte offset of the A region inside MlpSmem::a) >> 4
   uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
   // bits 0-2: 16-wide K steps to issue; 3: first step of the layer (overwrite the accumulator); 4: last step of the layer
   // (commit d_full); 5 / 6: last reader of region 0 / 5 (commit e_free / v_free); 8-11: 1 + region whose a_ready barrier
-  // must be acquired first (0: none); 12: layer index & 1 (selects the accumulator buffer); 13: A operand in tensor memory
+  // must be acquired first (0: none); 12: layer index & 1 (selects the accumulator buffer); 13: A operand in tensor memory;
+  // 14: index (& 1) of this acquisition among the tile's acquisitions of that region; 15: their count per tile (& 1)
   uint32_t meta;
   uint32_t pad_;
 };
@@ -241,10 +251,62 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == ISSUER2_WARP) {
     // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (uniform control
     // flow), one elected lane issues tcgen05.mma / tcgen05.commit
-#if SRF_MLP_ISSUER == 2
+#if SRF_MLP_ISSUER == 3
+    const int num_steps = sched.num_steps;
+    const uint32_t me = warp == 1 ? 0u : 1u;
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+    const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
+    const uint32_t a_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
+    const uint32_t bar_full = ptx::smem_u32(&sm.w_full[0]), bar_empty = ptx::smem_u32(&sm.w_empty[0]);
+    const uint32_t bar_a = ptx::smem_u32(&sm.a_ready[0]), bar_d = ptx::smem_u32(&sm.d_full[0]);
+    const uint32_t bar_e = ptx::smem_u32(&sm.e_free), bar_v = ptx::smem_u32(&sm.v_free);
+    const uint4* steps = reinterpret_cast<const uint4*>(sched.steps);
+    const uint32_t odd_layers = (uint32_t)prog.num_layers & 1u;
+    // global step g = t * num_steps + s; this warp owns g = me, me + 2, ...; ring stage g % NUM_STAGES, phase (g / NUM_STAGES) & 1
+    uint32_t stage = me % NUM_STAGES, ph = (me / NUM_STAGES) & 1;
+    int s = (int)me, t = 0;
+    while (s >= num_steps) { s -= num_steps; ++t; }
+    if (me == 1) asm volatile("bar.arrive 2, 64;" ::: "memory");       // warp A may issue step 0
+    while (t < my_tiles) {
+      const uint4 st = steps[s];           // x: A offset, y: instruction descriptor, z: packed step data
+      const uint32_t meta = st.z;
+      const uint32_t wr = (meta >> 8) & 15u;
+      const uint32_t tp = (uint32_t)t & 1u;
+      if (wr) ptx::mbar_wait_addr(bar_a + (wr - 1) * 8, ((meta >> 14) ^ ((meta >> 15) & tp)) & 1u);
+      if (lane == 0) TRACE(16 + s * 4 + 0);
+      ptx::mbar_wait_addr(bar_full + stage * 8, ph);
+      if (lane == 0) TRACE(16 + s * 4 + 1);
+      const uint32_t buf = ((meta >> 12) ^ (tp & odd_layers)) & 1;
+      // token: every MMA of the previous step has been issued by the other warp
+      if (me == 0) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 3, 64;" ::: "memory");
+      ptx::tc_fence_after();
+      const uint32_t issue = ptx::elect_one();
+#if SRF_MLP_TS
+      if (meta & 0x2000u)            // A = H block of the previous layer, in the other accumulator buffer's columns
+        ptx::umma4_bf16_ts_if(issue, tmem + buf * 256, tmem + (buf ^ 1u) * 256 + st.x, 32u, w_lo + stage * (STAGE_BYTES >> 4),
+                              desc_hi, st.y, (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
+      else
+#endif
+      ptx::umma4_bf16_if(issue, tmem + buf * 256, a_lo + st.x, w_lo + stage * (STAGE_BYTES >> 4), desc_hi, st.y,
+                         (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
+      ptx::umma_commit_addr_if(issue, bar_empty + stage * 8);
+      if (meta & 0x70u) {
+        if (meta & 0x10u) ptx::umma_commit_addr_if(issue, bar_d + buf * 8);
+        if (meta & 0x20u) ptx::umma_commit_addr_if(issue, bar_e);
+        if (meta & 0x40u) ptx::umma_commit_addr_if(issue, bar_v);
+      }
+      ptx::tc_fence_before();
+      if (me == 0) asm volatile("bar.arrive 3, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
+      if (lane == 0) TRACE(16 + s * 4 + 2);
+      stage += 2;
+      if (stage >= NUM_STAGES) { stage -= NUM_STAGES; ph ^= 1; }
+      s += 2;
+      while (s >= num_steps) { s -= num_steps; ++t; }
+    }
+#elif SRF_MLP_ISSUER == 2
     // lean issue path: one 16-byte schedule entry per step (prefetched one step ahead), 32-bit descriptor words,
     // barrier addresses as plain shared-memory offsets, one statement for the four MMAs of a K block
     const int num_steps = sched.num_steps;
@@ -664,7 +726,7 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
       st.idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
       const bool wait = !((seen >> reg) & 1);
       seen |= 1u << reg;
-#if SRF_MLP_ISSUER == 2
+#if SRF_MLP_ISSUER >= 2
       st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 ? 8u : 0u) | (kb == L.num_kblocks - 1 ? 0x10u : 0u) |
                 (wait ? (uint32_t)(reg + 1) << 8 : 0u) | ((uint32_t)(l & 1) << 12);
 #if SRF_MLP_TS
@@ -682,9 +744,18 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
     }
     if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
   }
-#if SRF_MLP_ISSUER == 2
+#if SRF_MLP_ISSUER >= 2
   if (last_e >= 0) sc.steps[last_e].meta |= 0x20u;
   if (last_v >= 0) sc.steps[last_v].meta |= 0x40u;
+  int waits[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < ns; ++i) {
+    const uint32_t wr = (sc.steps[i].meta >> 8) & 15u;
+    if (wr) sc.steps[i].meta |= (uint32_t)(waits[wr - 1]++ & 1) << 14;
+  }
+  for (int i = 0; i < ns; ++i) {
+    const uint32_t wr = (sc.steps[i].meta >> 8) & 15u;
+    if (wr) sc.steps[i].meta |= (uint32_t)(waits[wr - 1] & 1) << 15;
+  }
 #else
   if (last_e >= 0) sc.steps[last_e].flags |= 2;
   if (last_v >= 0) sc.steps[last_v].flags |= 4;
