@@ -67,34 +67,6 @@ struct MlpArgs {
   int S;
 };
 
-// Tuning switches (tools/mlp_variants.sh builds and times the combinations):
-//   SRF_MLP_GROUPS   column groups per 64-wide block = epilogue warps per TMEM lane quarter (2 or 4)
-//   SRF_MLP_PREFETCH 1: the TMEM load of slice k+1 is issued before the math of slice k
-#ifndef SRF_MLP_GROUPS
-#define SRF_MLP_GROUPS 2
-#endif
-#ifndef SRF_MLP_PREFETCH
-#define SRF_MLP_PREFETCH 0
-#endif
-//   SRF_MLP_ISSUER   2: lean MMA issue path (packed schedule entries, one statement per K block); 1: the previous one;
-//                    3: two issuing warps take alternate K-block steps (each prepares its next step - schedule entry,
-//                       barrier acquisition, descriptors - while the other one issues; a named-barrier token keeps the
-//                       MMAs in schedule order)
-#ifndef SRF_MLP_ISSUER
-#define SRF_MLP_ISSUER 3
-#endif
-//   SRF_MLP_TS       1: hidden activations never leave tensor memory: the epilogue packs them to bf16 and writes them back
-//                       with tcgen05.st over the accumulator columns it just drained, and the next layer's MMAs take A
-//                       from TMEM (".ts" form).  Shared memory then carries only the weights (and the E / V encodings):
-//                       the SS form spends 96 B/clk of the 128 B/clk shared-memory bandwidth on operand reads and the
-//                       epilogue another 32 B/clk on the activation stores, which is what bounded the kernel.
-#ifndef SRF_MLP_TS
-#define SRF_MLP_TS 1
-#endif
-//   SRF_MLP_PIPE     1: the TMEM load of the next 64-column block is issued before the stores / fence / arrive of the current one
-#ifndef SRF_MLP_PIPE
-#define SRF_MLP_PIPE 0
-#endif
 // SRF_MLP_TRACE: CTA 0 records clock64() at pipeline events of its 3rd and 4th tile into a global buffer (tools/mlp_trace.py)
 #ifndef SRF_MLP_TRACE
 #define SRF_MLP_TRACE 0
@@ -105,57 +77,49 @@ __device__ long long g_mlp_trace[4096];
 #else
 #define TRACE(slot) do { } while (0)
 #endif
-constexpr int GROUPS = SRF_MLP_GROUPS;
+// SRF_MLP_SPLIT 1: a 256-wide layer is issued as two 128-column halves (all K blocks of half 0, then of half 1), so the
+// epilogue of half 0 - and the hand-off of the next layer's first two K blocks - runs under the MMAs of half 1
+#ifndef SRF_MLP_SPLIT
+#define SRF_MLP_SPLIT 1
+#endif
+#ifndef SRF_MLP_CHUNK
+#define SRF_MLP_CHUNK 2
+#endif
+constexpr int GROUPS = 2;                         // column groups per 64-wide block = epilogue warps per TMEM lane quarter
 constexpr int COLS = 64 / GROUPS;                 // columns of a 64-wide block owned by one epilogue warp
 constexpr int EPI_THREADS = 128 * GROUPS;
-constexpr int EPI_WARP0 = 2;                      // warp 0 weight producer, warp 1 MMA issuer
+constexpr int EPI_WARP0 = 2;                      // warp 0 weight producer, warp 1 first MMA issuer
 constexpr int ENC_WARP0 = EPI_WARP0 + 4 * GROUPS; // 4 encoding warps (one row per thread) run one tile ahead
-#if SRF_MLP_ISSUER == 3
-constexpr int ISSUER2_WARP = ENC_WARP0 + 4;
+constexpr int ISSUER2_WARP = ENC_WARP0 + 4;       // second MMA issuer
 constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 5);
-#else
-constexpr int ISSUER2_WARP = -1;
-constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 4);
-#endif
 constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
+#if SRF_MLP_SPLIT
+constexpr int STAGE_BYTES = IMAGE_BYTES;          // one 128-row half of a K block per ring stage
+constexpr int NUM_STAGES = 10;
+#else
 constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
-#if SRF_MLP_TS
-static_assert(SRF_MLP_GROUPS == 2 && SRF_MLP_ISSUER >= 2, "the TMEM-resident activation layout assumes two 32-column groups per block");
 constexpr int NUM_STAGES = 5;
-constexpr int A_REGIONS = 2;                      // E and V only; H lives in tensor memory
-#else
-constexpr int NUM_STAGES = 3;
-constexpr int A_REGIONS = 6;
 #endif
-constexpr int V_REGION = A_REGIONS - 1;
+constexpr int A_REGIONS = 2;                      // E and V only; the hidden activations live in tensor memory
+constexpr int V_REGION = 1;
 constexpr int MAX_SIDE = 4096;                    // floats
-constexpr int MAX_STEPS = MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
+constexpr int MAX_STEPS = 2 * MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
 
-// One K-block step of the MMA issuer.  The host flattens the layer program into this schedule and passes it as a kernel
-// parameter: the issuing warp reads it with uniform constant-bank loads, so step data never leaves uniform registers.
-#if SRF_MLP_ISSUER >= 2
+// One step of the MMA issuers = the (up to) four K=16 MMAs of one 64-wide K block [of one 128-column half].  The host
+// flattens the layer program into this schedule and passes it as a kernel parameter (constant bank); the producer streams
+// the weight images in the same order.
 struct alignas(16) MmaStep {
-  uint32_t a_off;         // (byte offset of the A region inside MlpSmem::a) >> 4
-  uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
-  // bits 0-2: 16-wide K steps to issue; 3: first step of the layer (overwrite the accumulator); 4: last step of the layer
-  // (commit d_full); 5 / 6: last reader of region 0 / 5 (commit e_free / v_free); 8-11: 1 + region whose a_ready barrier
-  // must be acquired first (0: none); 12: layer index & 1 (selects the accumulator buffer); 13: A operand in tensor memory;
-  // 14: index (& 1) of this acquisition among the tile's acquisitions of that region; 15: their count per tile (& 1)
+  uint32_t a_off;         // region 0 / 5: (byte offset of the A region inside MlpSmem::a) >> 4;  H block r: TMEM column 64 (r - 1)
+  uint32_t idesc;         // instruction descriptor (M = 128, N = columns of this step)
+  // bits 0-2: 16-wide K steps to issue; 3: first step of the accumulator half (overwrite); 4: last step of the half
+  // (commit d_full); 5 / 6: last reader of region 0 / 5 (commit e_free / v_free); 7: column half (0 / 1);
+  // 8-11: 1 + region whose a_ready barrier must be acquired first (0: none); 12: layer index & 1 (selects the accumulator
+  // buffer); 13: A operand in tensor memory; 14: index (& 1) of this acquisition among the tile's acquisitions of that
+  // region; 15: their count per tile (& 1); 16-17: weight images of this step (1 or 2); 18-20: K blocks of the layer
   uint32_t meta;
-  uint32_t pad_;
+  uint32_t w_off;         // (byte offset of the step's first weight image in the blob) >> 4
 };
-#else
-struct alignas(16) MmaStep {
-  uint32_t a_off;         // (byte offset of the A region inside MlpSmem::a) >> 4
-  uint32_t idesc;         // instruction descriptor of the layer (M = 128, N = n)
-  int32_t layer;          // layer index inside the tile (selects the accumulator buffer)
-  int8_t ksteps;          // 16-wide K steps to issue
-  int8_t wait_region;     // region whose a_ready barrier must be acquired first, or -1
-  uint8_t first;          // first step of the layer: overwrite the accumulator
-  uint8_t flags;          // 1: last step of the layer (commit d_full); 2 / 4: last reader of region 0 / 5 (commit e_free / v_free)
-};
-#endif
 struct MmaSchedule {
   int32_t num_steps;
   int32_t pad_[3];
@@ -163,13 +127,13 @@ struct MmaSchedule {
 };
 
 struct alignas(1024) MlpSmem {
-  uint8_t a[A_REGIONS][KBLOCK_BYTES];     // E, H0..H3, V  (TS: E, V)
+  uint8_t a[A_REGIONS][KBLOCK_BYTES];     // E, V
   uint8_t w[NUM_STAGES][STAGE_BYTES];
   float side[MAX_SIDE];
   float part[2][GROUPS][128][4];          // head partial sums of each column group
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
-  uint64_t a_ready[6];                    // per A region: written and visible to the async proxy
-  uint64_t d_full[2];                     // accumulator buffer complete
+  uint64_t a_ready[6];                    // per A region (0 E, 1..4 H blocks, 5 V): written and visible to the tensor core
+  uint64_t d_full[4];                     // [accumulator buffer][column half] complete
   uint64_t e_free, v_free;                // every MMA reading region 0 / 5 of the current tile has retired
   uint32_t tmem_base;
 };
@@ -205,7 +169,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
                                                                       const __grid_constant__ MmaSchedule sched, const MlpArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   MlpSmem& sm = *reinterpret_cast<MlpSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a lane-0 shuffle: tells the compiler it is warp-uniform (role dispatch and the issuers' step
+  // data can then live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
 
   for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
@@ -214,8 +180,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     ptx::mbar_init(&sm.a_ready[0], 4);
     ptx::mbar_init(&sm.a_ready[5], 4);
     for (int r = 1; r < 5; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * GROUPS);
-    ptx::mbar_init(&sm.d_full[0], 1);
-    ptx::mbar_init(&sm.d_full[1], 1);
+    for (int b = 0; b < 4; ++b) ptx::mbar_init(&sm.d_full[b], 1);
     ptx::mbar_init(&sm.e_free, 1);
     ptx::mbar_init(&sm.v_free, 1);
     ptx::fence_barrier_init();
@@ -232,29 +197,29 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
   if (warp == 0) {
-    // ------------------------------------------------------------ weight producer
+    // ------------------------------------------------------------ weight producer: one ring stage per schedule step
     if (lane == 0) {
-      uint32_t it = 0;
+      const int num_steps = sched.num_steps;
+      uint32_t stage = 0, ph = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        for (int l = 0; l < prog.num_layers; ++l) {
-          const MlpLayer& L = prog.layers[l];
-          const int halves = L.n >> 7;
-          for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
-            const uint32_t st = it % NUM_STAGES, ph = (it / NUM_STAGES) & 1;
-            ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
-            ptx::mbar_arrive_expect_tx(&sm.w_full[st], halves * IMAGE_BYTES);
-            for (int nh = 0; nh < halves; ++nh)
-              ptx::bulk_g2s(sm.w[st] + nh * IMAGE_BYTES,
-                            args.weights + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * IMAGE_BYTES, IMAGE_BYTES,
-                            &sm.w_full[st]);
-          }
+        for (int s = 0; s < num_steps; ++s) {
+          const MmaStep st = sched.steps[s];
+          const uint32_t images = (st.meta >> 16) & 3u;
+          ptx::mbar_wait(&sm.w_empty[stage], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&sm.w_full[stage], images * IMAGE_BYTES);
+          const uint32_t half_stride = ((st.meta >> 18) & 7u) * IMAGE_BYTES;     // blob order: [layer][128-row half][K block]
+          for (uint32_t i = 0; i < images; ++i)
+            ptx::bulk_g2s(sm.w[stage] + i * IMAGE_BYTES, args.weights + ((size_t)st.w_off << 4) + (size_t)i * half_stride, IMAGE_BYTES,
+                          &sm.w_full[stage]);
+          if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1 || warp == ISSUER2_WARP) {
-    // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (uniform control
-    // flow), one elected lane issues tcgen05.mma / tcgen05.commit
-#if SRF_MLP_ISSUER == 3
+    // ------------------------------------------------------------ MMA issuers: two warps take alternate steps; each prepares
+    // its next step (schedule entry, barrier acquisition, descriptors) while the other one issues, and a named-barrier token
+    // keeps the MMAs in schedule order.  The whole warp runs the loop (uniform control flow: descriptors stay in uniform
+    // registers), one elected lane issues tcgen05.mma / tcgen05.commit.
     const int num_steps = sched.num_steps;
     const uint32_t me = warp == 1 ? 0u : 1u;
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
@@ -269,7 +234,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     uint32_t stage = me % NUM_STAGES, ph = (me / NUM_STAGES) & 1;
     int s = (int)me, t = 0;
     while (s >= num_steps) { s -= num_steps; ++t; }
-    if (me == 1) asm volatile("bar.arrive 2, 64;" ::: "memory");       // warp A may issue step 0
+    if (me == 1) asm volatile("bar.arrive 2, 64;" ::: "memory");       // the first warp may issue step 0
     while (t < my_tiles) {
       const uint4 st = steps[s];           // x: A offset, y: instruction descriptor, z: packed step data
       const uint32_t meta = st.z;
@@ -280,125 +245,27 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       ptx::mbar_wait_addr(bar_full + stage * 8, ph);
       if (lane == 0) TRACE(16 + s * 4 + 1);
       const uint32_t buf = ((meta >> 12) ^ (tp & odd_layers)) & 1;
-      // token: every MMA of the previous step has been issued by the other warp
-      if (me == 0) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 3, 64;" ::: "memory");
-      ptx::tc_fence_after();
+      const uint32_t half = (meta >> 7) & 1u;
       const uint32_t issue = ptx::elect_one();
-#if SRF_MLP_TS
-      if (meta & 0x2000u)            // A = H block of the previous layer, in the other accumulator buffer's columns
-        ptx::umma4_bf16_ts_if(issue, tmem + buf * 256, tmem + (buf ^ 1u) * 256 + st.x, 32u, w_lo + stage * (STAGE_BYTES >> 4),
-                              desc_hi, st.y, (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
-      else
-#endif
-      ptx::umma4_bf16_if(issue, tmem + buf * 256, a_lo + st.x, w_lo + stage * (STAGE_BYTES >> 4), desc_hi, st.y,
-                         (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
-      ptx::umma_commit_addr_if(issue, bar_empty + stage * 8);
-      if (meta & 0x70u) {
-        if (meta & 0x10u) ptx::umma_commit_addr_if(issue, bar_d + buf * 8);
-        if (meta & 0x20u) ptx::umma_commit_addr_if(issue, bar_e);
-        if (meta & 0x40u) ptx::umma_commit_addr_if(issue, bar_v);
+      const uint32_t d_addr = tmem + buf * 256 + half * 128;
+      const uint32_t b_lo = w_lo + stage * (STAGE_BYTES >> 4);
+      const uint32_t acc = (meta >> 3) & 1 ? 0u : 1u, ksteps = meta & 7u;
+      const uint32_t bx = meta & 0x10u ? bar_d + (buf * 2 + half) * 8 : 0u, by = meta & 0x20u ? bar_e : 0u, bz = meta & 0x40u ? bar_v : 0u;
+      // token (inside the statement): every MMA of the previous step has been issued by the other warp
+      if (meta & 0x2000u) {          // A = H block of the previous layer, packed in the other accumulator buffer's columns
+        const uint32_t a_t = tmem + (buf ^ 1u) * 256 + st.x;
+        if (me == 0) ptx::umma4_step<2, 3, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        else ptx::umma4_step<3, 2, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+      } else {
+        if (me == 0) ptx::umma4_step<2, 3, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        else ptx::umma4_step<3, 2, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
       }
-      ptx::tc_fence_before();
-      if (me == 0) asm volatile("bar.arrive 3, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
       if (lane == 0) TRACE(16 + s * 4 + 2);
       stage += 2;
       if (stage >= NUM_STAGES) { stage -= NUM_STAGES; ph ^= 1; }
       s += 2;
       while (s >= num_steps) { s -= num_steps; ++t; }
     }
-#elif SRF_MLP_ISSUER == 2
-    // lean issue path: one 16-byte schedule entry per step (prefetched one step ahead), 32-bit descriptor words,
-    // barrier addresses as plain shared-memory offsets, one statement for the four MMAs of a K block
-    const int num_steps = sched.num_steps;
-    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
-    const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
-    const uint32_t a_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
-    const uint32_t bar_full = ptx::smem_u32(&sm.w_full[0]), bar_empty = ptx::smem_u32(&sm.w_empty[0]);
-    const uint32_t bar_a = ptx::smem_u32(&sm.a_ready[0]), bar_d = ptx::smem_u32(&sm.d_full[0]);
-    const uint32_t bar_e = ptx::smem_u32(&sm.e_free), bar_v = ptx::smem_u32(&sm.v_free);
-    const uint4* steps = reinterpret_cast<const uint4*>(sched.steps);
-    uint32_t stage = 0, ph = 0, parity = 0;
-    uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
-    for (int t = 0; t < my_tiles; ++t) {
-      uint4 nxt = steps[0];
-      for (int s = 0; s < num_steps; ++s) {
-        const uint4 st = nxt;           // x: A offset >> 4, y: instruction descriptor, z: packed step data
-        nxt = steps[s + 1 < num_steps ? s + 1 : 0];
-        const uint32_t meta = st.z;
-        const uint32_t wr = (meta >> 8) & 15u;
-        if (wr) {
-          ptx::mbar_wait_addr(bar_a + (wr - 1) * 8, (a_phase >> (wr - 1)) & 1);
-          a_phase ^= 1u << (wr - 1);
-        }
-        if (lane == 0) TRACE(16 + s * 4 + 0);
-        ptx::mbar_wait_addr(bar_full + stage * 8, ph);
-        if (lane == 0) TRACE(16 + s * 4 + 1);
-        ptx::tc_fence_after();
-        const uint32_t buf = ((meta >> 12) ^ parity) & 1;
-        const uint32_t issue = ptx::elect_one();
-#if SRF_MLP_TS
-        if (meta & 0x2000u)            // A = H block of the previous layer, in the other accumulator buffer's columns
-          ptx::umma4_bf16_ts_if(issue, tmem + buf * 256, tmem + (buf ^ 1u) * 256 + st.x, 32u, w_lo + stage * (STAGE_BYTES >> 4),
-                                desc_hi, st.y, (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
-        else
-#endif
-        ptx::umma4_bf16_if(issue, tmem + buf * 256, a_lo + st.x, w_lo + stage * (STAGE_BYTES >> 4), desc_hi, st.y,
-                           (meta >> 3) & 1 ? 0u : 1u, meta & 7u);
-        ptx::umma_commit_addr_if(issue, bar_empty + stage * 8);
-        if (meta & 0x70u) {
-          if (meta & 0x10u) ptx::umma_commit_addr_if(issue, bar_d + buf * 8);
-          if (meta & 0x20u) ptx::umma_commit_addr_if(issue, bar_e);
-          if (meta & 0x40u) ptx::umma_commit_addr_if(issue, bar_v);
-        }
-        if (lane == 0) TRACE(16 + s * 4 + 2);
-        if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
-      }
-      parity ^= (uint32_t)prog.num_layers & 1u;
-    }
-#else
-    const int num_steps = sched.num_steps;
-    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
-    const uint32_t w_desc_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
-    const uint32_t a_desc_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
-    uint32_t stage = 0, ph = 0, layer_base = 0;
-    uint32_t a_phase = 0;              // bit r: parity to wait for on a_ready[r]
-    for (int t = 0; t < my_tiles; ++t) {
-      for (int s = 0; s < num_steps; ++s) {
-        const MmaStep st = sched.steps[s];
-        if (st.wait_region >= 0) {
-          ptx::mbar_wait(&sm.a_ready[st.wait_region], (a_phase >> st.wait_region) & 1);
-          a_phase ^= 1u << st.wait_region;
-        }
-        if (lane == 0) TRACE(16 + s * 4 + 0);
-        ptx::mbar_wait(&sm.w_full[stage], ph);
-        if (lane == 0) TRACE(16 + s * 4 + 1);
-        ptx::tc_fence_after();
-        const uint32_t buf = (layer_base + (uint32_t)st.layer) & 1;
-        const uint32_t d_addr = tmem + buf * 256;
-        const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (a_desc_lo + st.a_off);
-        const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (w_desc_lo + stage * (STAGE_BYTES >> 4));
-        const uint32_t issue = ptx::elect_one();
-        if (st.ksteps == 4) {
-          ptx::umma_bf16_if(issue, d_addr, a_desc, b_desc, st.idesc, st.first ? 0u : 1u);
-          ptx::umma_bf16_if(issue, d_addr, a_desc + 2, b_desc + 2, st.idesc, 1u);
-          ptx::umma_bf16_if(issue, d_addr, a_desc + 4, b_desc + 4, st.idesc, 1u);
-          ptx::umma_bf16_if(issue, d_addr, a_desc + 6, b_desc + 6, st.idesc, 1u);
-        } else {
-          for (int k = 0; k < st.ksteps; ++k)
-            ptx::umma_bf16_if(issue, d_addr, a_desc + 2 * k, b_desc + 2 * k, st.idesc, (st.first && k == 0) ? 0u : 1u);
-        }
-        ptx::umma_commit_if(issue, &sm.w_empty[stage]);
-        if (st.flags) {
-          if (st.flags & 1) ptx::umma_commit_if(issue, &sm.d_full[buf]);
-          if (st.flags & 2) ptx::umma_commit_if(issue, &sm.e_free);
-          if (st.flags & 4) ptx::umma_commit_if(issue, &sm.v_free);
-        }
-        if (lane == 0) TRACE(16 + s * 4 + 2);
-        if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
-      }
-      layer_base += (uint32_t)prog.num_layers;
-    }
-#endif
   } else if (warp >= ENC_WARP0) {
     // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
     const int row = (warp - ENC_WARP0) * 32 + lane;
@@ -562,59 +429,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
                   make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
           if (!write_h) return;
-#if SRF_MLP_TS
-          // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained
+          // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained: K block kb of the
+          // next layer's A operand never leaves tensor memory
           ptx::tmem_st16(t_row + kb * 64, pk);
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
-          return;
-#else
-          uint8_t* H = sm.a[1 + kb];
-#pragma unroll
-          for (int u = 0; u < COLS / 8; ++u)
-            *reinterpret_cast<uint4*>(H + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
-                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
-#endif
         };
 
-        ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
-        d_phase ^= 1u << buf;
-        ptx::tc_fence_after();
-        if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16);
         const int nblocks = n >> 6;
-#if SRF_MLP_PREFETCH
-        uint32_t va[COLS], vb[COLS], pk[COLS / 2];
-        tmem_load<COLS>(t_row, va);
-        for (int kb = 0; kb < nblocks; kb += 2) {
-          ptx::tmem_ld_wait(va);
-          if (kb + 1 < nblocks) tmem_load<COLS>(t_row + (kb + 1) * 64, vb);
-          compute(va, pk, kb);
-          store(pk, kb);
-          if (kb + 1 < nblocks) {
-            ptx::tmem_ld_wait(vb);
-            if (kb + 2 < nblocks) tmem_load<COLS>(t_row + (kb + 2) * 64, va);
-            compute(vb, pk, kb + 1);
-            store(pk, kb + 1);
+        uint32_t va[COLS], pk[COLS / 2];
+        for (int kb = 0; kb < nblocks; ++kb) {
+          if (kb == 0 || (SRF_MLP_SPLIT && kb == 2)) {            // blocks 2, 3 belong to the second column half
+            const uint32_t b = buf * 2 + (SRF_MLP_SPLIT ? (uint32_t)(kb >> 1) : 0u);
+            ptx::mbar_wait(&sm.d_full[b], (d_phase >> b) & 1);
+            d_phase ^= 1u << b;
+            ptx::tc_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + (kb ? 9 : 0));
           }
-        }
-#elif SRF_MLP_PIPE
-        uint32_t va[COLS], pk[COLS / 2];
-        tmem_load<COLS>(t_row, va);
-        for (int kb = 0; kb < nblocks; ++kb) {
-          ptx::tmem_ld_wait(va);
-          compute(va, pk, kb);                                            // va is dead after this: reload it for the next
-          if (kb + 1 < nblocks) tmem_load<COLS>(t_row + (kb + 1) * 64, va);   // block while this one is stored and published
-          store(pk, kb);
-        }
-        ptx::tmem_ld_wait();
-#else
-        uint32_t va[COLS], pk[COLS / 2];
-        for (int kb = 0; kb < nblocks; ++kb) {
           tmem_load<COLS>(t_row + kb * 64, va);
           ptx::tmem_ld_wait(va);
           if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 1 + 2 * kb);
@@ -622,7 +455,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           store(pk, kb);
           if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * kb);
         }
-#endif
         ptx::tc_fence_before();
         if (head_rows > 0) {
           if (warp == EPI_WARP0 && lane == 0) TRACE(2010 + l);
@@ -715,36 +547,31 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
   uint32_t seen = 0;
   for (int l = 0; l < prog.num_layers; ++l) {
     const MlpLayer& L = prog.layers[l];
-    for (int kb = 0; kb < L.num_kblocks; ++kb, ++ns) {
-      MmaStep& st = sc.steps[ns];
-      const int reg = L.kblock_region[kb];
-#if SRF_MLP_TS
-      st.a_off = reg == 0 ? 0u : (reg == 5 ? (uint32_t)(V_REGION * KBLOCK_BYTES) >> 4 : (uint32_t)(reg - 1) * 64u);   // smem / TMEM column
-#else
-      st.a_off = (uint32_t)(reg * KBLOCK_BYTES) >> 4;
-#endif
-      st.idesc = ptx::make_idesc_bf16(128, (uint32_t)L.n);
-      const bool wait = !((seen >> reg) & 1);
-      seen |= 1u << reg;
-#if SRF_MLP_ISSUER >= 2
-      st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 ? 8u : 0u) | (kb == L.num_kblocks - 1 ? 0x10u : 0u) |
-                (wait ? (uint32_t)(reg + 1) << 8 : 0u) | ((uint32_t)(l & 1) << 12);
-#if SRF_MLP_TS
-      if (reg >= 1 && reg <= 4) st.meta |= 0x2000u;
-#endif
-#else
-      st.layer = l;
-      st.ksteps = (int8_t)L.kblock_ksteps[kb];
-      st.wait_region = wait ? (int8_t)reg : (int8_t)-1;
-      st.first = kb == 0;
-      st.flags = kb == L.num_kblocks - 1 ? 1 : 0;
-#endif
-      if (reg == 0) last_e = ns;
-      if (reg == 5) last_v = ns;
+    const int halves = SRF_MLP_SPLIT ? L.n >> 7 : 1;
+    const int images = SRF_MLP_SPLIT ? 1 : L.n >> 7;      // 128-row weight images per step
+    // issue order inside a layer: chunks of SRF_MLP_CHUNK K blocks, both column halves per chunk - the first half completes
+    // (and its epilogue starts) while the last chunk of the second half is still on the tensor core, and the early steps
+    // only need the first K blocks of the previous layer's output
+    for (int c0 = 0; c0 < L.num_kblocks; c0 += SRF_MLP_CHUNK)
+    for (int h = 0; h < halves; ++h) {
+      for (int kb = c0; kb < L.num_kblocks && kb < c0 + SRF_MLP_CHUNK; ++kb, ++ns) {
+        MmaStep& st = sc.steps[ns];
+        const int reg = L.kblock_region[kb];
+        st.a_off = reg == 0 ? 0u : (reg == 5 ? (uint32_t)(V_REGION * KBLOCK_BYTES) >> 4 : (uint32_t)(reg - 1) * 64u);
+        st.idesc = ptx::make_idesc_bf16(128, (uint32_t)(128 * images));
+        const bool wait = !((seen >> reg) & 1);
+        seen |= 1u << reg;
+        st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 ? 8u : 0u) | (kb == L.num_kblocks - 1 ? 0x10u : 0u) | ((uint32_t)h << 7) |
+                  (wait ? (uint32_t)(reg + 1) << 8 : 0u) | ((uint32_t)(l & 1) << 12) | (reg >= 1 && reg <= 4 ? 0x2000u : 0u) |
+                  ((uint32_t)images << 16) | ((uint32_t)L.num_kblocks << 18);
+        // blob order: [layer][128-row half][K block]
+        st.w_off = (uint32_t)((L.weight_offset + (int64_t)(h * L.num_kblocks + kb) * IMAGE_BYTES) >> 4);
+        if (reg == 0) last_e = ns;
+        if (reg == 5) last_v = ns;
+      }
     }
     if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
   }
-#if SRF_MLP_ISSUER >= 2
   if (last_e >= 0) sc.steps[last_e].meta |= 0x20u;
   if (last_v >= 0) sc.steps[last_v].meta |= 0x40u;
   int waits[6] = {0, 0, 0, 0, 0, 0};
@@ -756,10 +583,6 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
     const uint32_t wr = (sc.steps[i].meta >> 8) & 15u;
     if (wr) sc.steps[i].meta |= (uint32_t)(waits[wr - 1] & 1) << 15;
   }
-#else
-  if (last_e >= 0) sc.steps[last_e].flags |= 2;
-  if (last_v >= 0) sc.steps[last_v].flags |= 4;
-#endif
   sc.num_steps = ns;
   return sc;
 }

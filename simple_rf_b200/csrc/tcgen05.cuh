@@ -164,6 +164,104 @@ __device__ __forceinline__ void umma4_bf16_ts_if(uint32_t issue, uint32_t d_tmem
       "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps), "r"(off2)
       : "memory");
 }
+// One whole issuer step in ONE statement, for two issuing warps that alternate steps: descriptor / predicate set-up,
+// then the named-barrier token (SYNC_ID: the other warp has issued the previous step), the MMAs, the commits
+// (bar_empty always; bar_x / bar_y / bar_z when non-zero), and the token for the other warp (ARRIVE_ID).  Keeping the
+// set-up inside the statement lets ptxas place it ahead of the barrier, so only the UTCHMMA / UTCBAR issue sits between
+// the two tokens.  TS: A operand from tensor memory (slices at a + {0, 8, 32, 40}); otherwise from shared memory
+// (descriptor low word a, slices at a + {0, 2, 4, 6}).
+template <int SYNC_ID, int ARRIVE_ID, bool TS>
+__device__ __forceinline__ void umma4_step(uint32_t issue, uint32_t d_tmem, uint32_t a, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t accumulate, uint32_t ksteps, uint32_t bar_empty,
+                                           uint32_t bar_x, uint32_t bar_y, uint32_t bar_z) {
+  if constexpr (TS) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, ptrue, q0, q1, q2, q3, cx, cy, cz;\n\t"
+        ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 db0, db1, db2, db3;\n\t"
+        "setp.ne.b32 pacc, %5, 0;\n\t"
+        "setp.eq.b32 ptrue, 0, 0;\n\t"
+        "setp.ne.b32 q0, %6, 0;\n\t"
+        "setp.gt.and.u32 q1, %7, 1, q0;\n\t"
+        "setp.gt.and.u32 q2, %7, 2, q0;\n\t"
+        "setp.gt.and.u32 q3, %7, 3, q0;\n\t"
+        "setp.ne.and.b32 cx, %9, 0, q0;\n\t"
+        "setp.ne.and.b32 cy, %10, 0, q0;\n\t"
+        "setp.ne.and.b32 cz, %11, 0, q0;\n\t"
+        "add.u32 a1, %1, 8;\n\t"
+        "add.u32 a2, %1, 32;\n\t"
+        "add.u32 a3, %1, 40;\n\t"
+        "add.u32 b1, %2, 2;\n\t"
+        "add.u32 b2, %2, 4;\n\t"
+        "add.u32 b3, %2, 6;\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "bar.sync %12, 64;\n\t"
+        "tcgen05.fence::after_thread_sync;\n\t"
+        "@q0 tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db0, %4, pacc;\n\t"
+        "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], db1, %4, ptrue;\n\t"
+        "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], db2, %4, ptrue;\n\t"
+        "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], db3, %4, ptrue;\n\t"
+        "@q0 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "@cx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "@cy tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+        "@cz tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "tcgen05.fence::before_thread_sync;\n\t"
+        "bar.arrive %13, 64;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps), "r"(bar_empty), "r"(bar_x),
+        "r"(bar_y), "r"(bar_z), "n"(SYNC_ID), "n"(ARRIVE_ID)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, ptrue, q0, q1, q2, q3, cx, cy, cz;\n\t"
+        ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "setp.ne.b32 pacc, %5, 0;\n\t"
+        "setp.eq.b32 ptrue, 0, 0;\n\t"
+        "setp.ne.b32 q0, %6, 0;\n\t"
+        "setp.gt.and.u32 q1, %7, 1, q0;\n\t"
+        "setp.gt.and.u32 q2, %7, 2, q0;\n\t"
+        "setp.gt.and.u32 q3, %7, 3, q0;\n\t"
+        "setp.ne.and.b32 cx, %9, 0, q0;\n\t"
+        "setp.ne.and.b32 cy, %10, 0, q0;\n\t"
+        "setp.ne.and.b32 cz, %11, 0, q0;\n\t"
+        "add.u32 a1, %1, 2;\n\t"
+        "add.u32 a2, %1, 4;\n\t"
+        "add.u32 a3, %1, 6;\n\t"
+        "add.u32 b1, %2, 2;\n\t"
+        "add.u32 b2, %2, 4;\n\t"
+        "add.u32 b3, %2, 6;\n\t"
+        "mov.b64 da0, {%1, %3};\n\t"
+        "mov.b64 da1, {a1, %3};\n\t"
+        "mov.b64 da2, {a2, %3};\n\t"
+        "mov.b64 da3, {a3, %3};\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "bar.sync %12, 64;\n\t"
+        "tcgen05.fence::after_thread_sync;\n\t"
+        "@q0 tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %4, pacc;\n\t"
+        "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da1, db1, %4, ptrue;\n\t"
+        "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da2, db2, %4, ptrue;\n\t"
+        "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da3, db3, %4, ptrue;\n\t"
+        "@q0 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "@cx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "@cy tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+        "@cz tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "tcgen05.fence::before_thread_sync;\n\t"
+        "bar.arrive %13, 64;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps), "r"(bar_empty), "r"(bar_x),
+        "r"(bar_y), "r"(bar_z), "n"(SYNC_ID), "n"(ARRIVE_ID)
+        : "memory");
+  }
+}
 // thread i of the warp writes 16 consecutive 32-bit columns of lane (lane base + i)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(

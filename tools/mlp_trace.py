@@ -29,13 +29,16 @@ prog = packed.program
 t0 = t[1024]                      # epilogue sees layer 0 complete
 print('encoding warps (run ahead): E published', t[1] - t[0], 'cycles after region 0 was free; relative to t0:', t[0] - t0, t[1] - t0)
 s = 0
+SPLIT = int(os.environ.get('SRF_MLP_SPLIT', '1'))
 for l in range(prog.num_layers):
     L = prog.layers[l]
     mma = []
-    for kb in range(L.num_kblocks):
-        a, w, i = (t[16 + s * 4 + k] - t0 for k in range(3))
-        mma.append(f'kb{kb}: A@{a} W@{w} issued@{i}')
-        s += 1
-    e = [t[1024 + l * 16 + k] - t0 for k in range(1 + 2 * (L.n // 64))]
+    halves = (L.n // 128) if SPLIT else 1
+    for h in range(halves):
+        for kb in range(L.num_kblocks):
+            a, w, i = (t[16 + s * 4 + k] - t0 for k in range(3))
+            mma.append(f'h{h}kb{kb}: A@{a} W@{w} issued@{i}')
+            s += 1
+    e = [t[1024 + l * 16 + k] - t0 for k in range(10)]
     print(f'layer {l}: MMA ' + ' | '.join(mma))
-    print(f'         EPI d_full@{e[0]} ' + ' '.join(f'[ld@{e[1 + 2 * k]} st@{e[2 + 2 * k]}]' for k in range(L.n // 64)))
+    print(f'         EPI d_full@{e[0]} ' + ' '.join(f'[ld@{e[1 + 2 * k]} st@{e[2 + 2 * k]}]' for k in range(L.n // 64)) + f' d_full(h1)@{e[9]}')
