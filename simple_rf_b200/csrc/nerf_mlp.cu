@@ -6,15 +6,17 @@
 // variants (main, points_augmentation with the degree-3 sigma input, views_augmentation with the 4-wide
 // head); the variant is a small "layer program" passed by the host (srf_mlp_layer in the header).
 //
-// Data flow per tile (nothing between the ray data and sigma/rgb touches HBM):
-//   epilogue warps: points + encoding -> bf16 A-operand K-blocks E (points) / V (views) in shared memory
-//   producer warp : streams pre-packed bf16 weight K-blocks (128B-swizzled images) through a ring with
-//                   cp.async.bulk + mbarrier complete_tx (TMA bulk engine)
-//   MMA thread    : tcgen05.mma M=128, N=256|128, K=16 from shared memory, fp32 accumulators in TMEM
-//                   (two 256-column buffers, alternating per layer)
-//   epilogue warps: tcgen05.ld -> +bias, ReLU -> bf16 -> swizzled st.shared as the next layer's A operand,
-//                   signalled per 64-column K-block so the next layer's MMAs start while the rest of the
-//                   epilogue is still running; the 1/3/4-wide heads are thread-local dot products.
+// Data flow per tile (nothing between the ray data and sigma/rgb touches HBM, and the hidden activations never
+// leave tensor memory):
+//   encoding warps: points + encoding -> bf16 A-operand K-blocks E (points) / V (views) in shared memory, one tile ahead
+//   producer warp : streams pre-packed bf16 weight images (128 output units x 64-wide K block, 128B-swizzled) through a
+//                   ring with cp.async.bulk + mbarrier complete_tx (TMA bulk engine), in schedule order
+//   2 MMA issuers : alternate steps of a host-flattened schedule; a step = four tcgen05.mma M=128, N=128, K=16 of one
+//                   K block of one 128-column half; B from shared memory, A from shared memory (E, V) or from tensor
+//                   memory (hidden activations); fp32 accumulators in TMEM (two 256-column buffers, alternating per layer)
+//   epilogue warps: tcgen05.ld -> +bias, ReLU -> bf16 pairs -> tcgen05.st over the accumulator columns just drained = the
+//                   next layer's A operand, signalled per 64-column K-block so the next layer's MMAs start while the rest
+//                   of the epilogue is still running; the 1/3/4-wide heads are thread-local dot products.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
