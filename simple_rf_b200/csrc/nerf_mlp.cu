@@ -103,6 +103,10 @@ constexpr int NUM_STAGES = 10;
 constexpr int STAGE_BYTES = 2 * IMAGE_BYTES;      // both 128-row halves of a K block per ring stage
 constexpr int NUM_STAGES = 5;
 #endif
+// training (activation tiles are saved): the ring shrinks to SAVE_RING_BYTES and the rest of `w` holds SAVE_BUFS
+// 16 KB staging images, written by the epilogue warps and drained to HBM by bulk async copies
+constexpr int SAVE_BUFS = 4;
+constexpr int SAVE_STAGES = NUM_STAGES - SAVE_BUFS * IMAGE_BYTES / STAGE_BYTES;
 constexpr int A_REGIONS = 2;                      // E and V only; the hidden activations live in tensor memory
 constexpr int V_REGION = 1;
 constexpr int MAX_SIDE = 4096;                    // floats
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
   const int num_tiles = (int)((total + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : NUM_STAGES;
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
   if (warp == 0) {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           for (uint32_t i = 0; i < images; ++i)
             ptx::bulk_g2s(sm.w[stage] + i * IMAGE_BYTES, args.weights + ((size_t)st.w_off << 4) + (size_t)i * half_stride, IMAGE_BYTES,
                           &sm.w_full[stage]);
-          if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
+          if (++stage == num_stages) { stage = 0; ph ^= 1; }
         }
       }
     }
@@ -232,8 +237,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     const uint32_t bar_e = ptx::smem_u32(&sm.e_free), bar_v = ptx::smem_u32(&sm.v_free);
     const uint4* steps = reinterpret_cast<const uint4*>(sched.steps);
     const uint32_t odd_layers = (uint32_t)prog.num_layers & 1u;
-    // global step g = t * num_steps + s; this warp owns g = me, me + 2, ...; ring stage g % NUM_STAGES, phase (g / NUM_STAGES) & 1
-    uint32_t stage = me % NUM_STAGES, ph = (me / NUM_STAGES) & 1;
+    // global step g = t * num_steps + s; this warp owns g = me, me + 2, ...; ring stage g % num_stages, phase (g / num_stages) & 1
+    uint32_t stage = me % num_stages, ph = (me / num_stages) & 1;
     int s = (int)me, t = 0;
     while (s >= num_steps) { s -= num_steps; ++t; }
     if (me == 1) asm volatile("bar.arrive 2, 64;" ::: "memory");       // the first warp may issue step 0
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       }
       if (lane == 0) TRACE(16 + s * 4 + 2);
       stage += 2;
-      if (stage >= NUM_STAGES) { stage -= NUM_STAGES; ph ^= 1; }
+      if (stage >= num_stages) { stage -= num_stages; ph ^= 1; }
       s += 2;
       while (s >= num_steps) { s -= num_steps; ++t; }
     }
@@ -362,6 +367,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     const int row = quarter * 32 + lane;
     uint32_t layer_count = 0;
     uint32_t d_phase = 0;                // bit b: parity to wait for on d_full[b]
+    uint32_t save_count = 0;             // staged activation images so far (selects the staging buffer)
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long m = tile * 128 + row;
@@ -424,20 +430,34 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H:
         // every MMA of this layer has retired once d_full fired)
         auto store = [&](const uint32_t (&pk)[COLS / 2], int kb) {
+          if (write_h) {
+            // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained: K block kb of the
+            // next layer's A operand never leaves tensor memory
+            ptx::tmem_st16(t_row + kb * 64, pk);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
+          }
           if (save_base != nullptr) {
+            // staged through shared memory: a thread owns 64 bytes of a 128-byte image row, so direct global stores touch 32
+            // lines per instruction; the swizzled staging image leaves as one 16 KB bulk copy instead
+            uint8_t* stg = sm.w[0] + (size_t)SAVE_STAGES * STAGE_BYTES + (size_t)(save_count & (SAVE_BUFS - 1)) * IMAGE_BYTES;
 #pragma unroll
             for (int u = 0; u < COLS / 8; ++u)
-              *reinterpret_cast<uint4*>(save_base + (size_t)kb * KBLOCK_BYTES + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
+              *reinterpret_cast<uint4*>(stg + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
                   make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            ptx::fence_proxy_async_smem();
+            // the buffer the NEXT block will use was handed to the copy engine SAVE_BUFS - 1 blocks ago: at most
+            // SAVE_BUFS - 2 newer groups may still be reading when everybody passes the barrier below
+            if (threadIdx.x == EPI_WARP0 * 32) ptx::bulk_wait_read<SAVE_BUFS - 2>();
+            epi_bar_sync();
+            if (threadIdx.x == EPI_WARP0 * 32) {
+              ptx::bulk_s2g(save_base + (size_t)kb * KBLOCK_BYTES, stg, IMAGE_BYTES);
+              ptx::bulk_commit();
+            }
+            ++save_count;
           }
-          if (!write_h) return;
-          // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained: K block kb of the
-          // next layer's A operand never leaves tensor memory
-          ptx::tmem_st16(t_row + kb * 64, pk);
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
         };
 
         const int nblocks = n >> 6;
@@ -495,6 +515,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       }
     }
   }
+  if (threadIdx.x == EPI_WARP0 * 32 && args.save_acts != nullptr) ptx::bulk_wait_all();   // staged images have left shared memory
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
