@@ -45,6 +45,14 @@ __device__ __forceinline__ void stg_stream(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// Saved activation tiles of the fused MLP: [tile][act_slots data images + mask images][16 KB].  The mask images follow the
+// data images; the 1 KB record of data image s (one 32-bit word per (column group, row): bit i = pre-activation value of
+// column 32 * group + i is positive, i.e. the ReLU output is non-zero) sits in mask image s / 16 at byte (s % 16) * 1024 + group * 512 + row * 4.
+__host__ __device__ inline int act_tile_images(int act_slots) { return act_slots + (act_slots + 15) / 16; }
+__host__ __device__ inline size_t act_mask_offset(int act_slots, int slot) {
+  return (size_t)(act_slots + slot / 16) * 16384 + (size_t)(slot % 16) * 1024;
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
       }
       if (args.save_acts != nullptr) {                 // each thread re-reads the row it just wrote
-        uint8_t* dst = args.save_acts + ((size_t)tile * args.act_slots + args.e_slot) * KBLOCK_BYTES;
+        uint8_t* dst = args.save_acts + ((size_t)tile * act_tile_images(args.act_slots) + args.e_slot) * KBLOCK_BYTES;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const uint32_t off = ptx::sw128_offset(row, u);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16(V, row, c, 0.f);
         }
         if (args.save_acts != nullptr) {
-          uint8_t* dst = args.save_acts + ((size_t)tile * args.act_slots + args.v_slot) * KBLOCK_BYTES;
+          uint8_t* dst = args.save_acts + ((size_t)tile * act_tile_images(args.act_slots) + args.v_slot) * KBLOCK_BYTES;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const uint32_t off = ptx::sw128_offset(row, u);
@@ -382,9 +382,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + grp * COLS;
         const int save_slot = args.save_acts != nullptr ? L.save_slot : -1;
-        uint8_t* save_base = save_slot >= 0 ? args.save_acts + ((size_t)tile * args.act_slots + save_slot) * KBLOCK_BYTES : nullptr;
+        uint8_t* tile_base = args.save_acts != nullptr ? args.save_acts + (size_t)tile * act_tile_images(args.act_slots) * KBLOCK_BYTES : nullptr;
+        uint8_t* save_base = save_slot >= 0 ? tile_base + (size_t)save_slot * KBLOCK_BYTES : nullptr;
 
         // bias + activation (+ head partial dot products) on one COLS-column slice, packed to bf16 pairs
+        uint32_t mask_bits = 0;
         auto compute = [&](uint32_t (&v)[COLS], uint32_t (&pk)[COLS / 2], int kb) {
           const int col0 = kb * 64 + grp * COLS;
           const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
@@ -396,6 +398,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             x[4 * q + 2] = __uint_as_float(v[4 * q + 2]); x[4 * q + 3] = __uint_as_float(v[4 * q + 3]);
             ptx::fadd2(x[4 * q + 0], x[4 * q + 1], b.x, b.y);
             ptx::fadd2(x[4 * q + 2], x[4 * q + 3], b.z, b.w);
+          }
+          if (save_base != nullptr) {
+            // sign pattern of the pre-activation values = the ReLU mask the data-gradient chain applies (bit i: x[i] > 0):
+            // top bit of -x (as integers) shifted in, last element first
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = COLS - 1; i >= 0; --i) bits = __funnelshift_l(0u - __float_as_uint(x[i]), bits, 1);
+            mask_bits = bits;
           }
           if (head_rows == 0) {                                    // plain hidden layer: ReLU rides on the bf16 conversion (F2FP.RELU)
             if (relu) {
@@ -447,6 +457,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             for (int u = 0; u < COLS / 8; ++u)
               *reinterpret_cast<uint4*>(stg + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
                   make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            // one mask word per thread, 128 bytes per warp (the dgrad chain reads these instead of the 64-byte activation row)
+            *reinterpret_cast<uint32_t*>(tile_base + act_mask_offset(args.act_slots, save_slot + kb) + grp * 512 + row * 4) = mask_bits;
             ptx::fence_proxy_async_smem();
             // the buffer the NEXT block will use was handed to the copy engine SAVE_BUFS - 1 blocks ago: at most
             // SAVE_BUFS - 2 newer groups may still be reading when everybody passes the barrier below

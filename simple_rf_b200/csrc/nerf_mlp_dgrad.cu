@@ -8,9 +8,10 @@
 //                gradient images [d_o | d_sigma_raw] for the weight-gradient kernel
 //   MMA thread : dX = dZ * W  as  tcgen05.mma with the TRANSPOSED weights streamed as pre-swizzled images
 //   epilogue   : tcgen05.ld -> (+ d_sigma_raw * w_sigma for the layer under the sigma head) -> bf16 -> AND with the
-//                ReLU mask (non-zero pattern of the activation tile the forward saved, two values per 32-bit lane) ->
-//                next layer's A operand (in place) AND the dZ tile image in HBM that srf_nerf_mlp_wgrad multiplies
-//                with the saved activations.
+//                ReLU mask (one bit per value, written by the forward next to the activation tiles) -> next layer's A
+//                operand, written back into TENSOR MEMORY over the accumulator columns just drained (tcgen05.st; the
+//                next layer's MMAs take A from TMEM), AND the dZ tile image for srf_nerf_mlp_wgrad, staged in shared
+//                memory and written to HBM by 16 KB bulk async copies.
 // Sample points and encodings carry no gradient (z_samples.detach(), frozen cameras), so the chain stops at layer 1.
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -45,7 +46,7 @@ struct DgradProgram {
 struct DgradArgs {
   const uint8_t* weights_t;   // transposed-weight images
   const float* side;
-  const uint8_t* acts;        // saved activation tiles of the forward [tile][act_slots][16 KB]
+  const uint8_t* acts;        // saved activation tiles of the forward [tile][act_slots + mask images][16 KB]; only the masks are read
   int act_slots;
   const float* sigma; const float* rgb;       // forward outputs [M], [M,3]
   const float* g_sigma; const float* g_rgb;   // upstream gradients [M], [M,3] (nullable)
@@ -59,31 +60,43 @@ struct DgradArgs {
 constexpr int DG_GROUPS = 2;
 constexpr int DG_COLS = 32;
 constexpr int DG_EPI_WARP0 = 2;
+constexpr int DG_EPI_THREADS = 128 * DG_GROUPS;
 constexpr int DG_INIT_WARP0 = DG_EPI_WARP0 + 4 * DG_GROUPS;
 constexpr int DG_THREADS = 32 * (DG_INIT_WARP0 + 4);
 constexpr int DG_KBLOCK = 128 * 128;
 constexpr int DG_STAGE = 2 * DG_KBLOCK;
 constexpr int DG_STAGES = 3;
+constexpr int DG_OUT_BUFS = 3;             // staging images of the dZ tiles on their way to HBM
 constexpr int DG_MAX_SIDE = 2048;
 
 struct alignas(1024) DgradSmem {
-  uint8_t h[4][DG_KBLOCK];
+  uint8_t h[4][DG_KBLOCK];                 // dZ_top (A operand of the first backward layer; also the source of its HBM copy)
   uint8_t w[DG_STAGES][DG_STAGE];
+  uint8_t out[DG_OUT_BUFS][DG_KBLOCK];
   float side[DG_MAX_SIDE];
-  float dsig[128];
+  float dsig[2][128];                      // d_sigma_raw per row, double-buffered over tiles (the init warps run a tile ahead)
   uint64_t w_full[DG_STAGES], w_empty[DG_STAGES];
-  uint64_t a_ready[4];        // H block rewritten by the epilogue of the previous backward layer
+  uint64_t a_ready[4];        // K block of the next layer's A operand written to tensor memory by the epilogue
   uint64_t top_ready;         // H blocks written by the init warps
-  uint64_t h_free;            // every MMA of the tile's last layer has retired
+  uint64_t h_free;            // every MMA of the tile's FIRST layer (the only reader of `h`) has retired
   uint64_t d_full[2];
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ void dg_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DG_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void dg_init_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// 2 mask bits -> 0xFFFF per set bit (low / high bf16 of a packed pair)
+__device__ __forceinline__ uint32_t pair_mask(uint32_t bits, int j) {
+  const uint32_t b = bits >> (2 * j);
+  return ((b & 1u) ? 0x0000FFFFu : 0u) | ((b & 2u) ? 0xFFFF0000u : 0u);
+}
 
 __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __grid_constant__ DgradProgram prog,
                                                                        const DgradArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   DgradSmem& sm = *reinterpret_cast<DgradSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   for (int i = threadIdx.x; i < prog.side_count; i += DG_THREADS) sm.side[i] = args.side[i];
   if (warp == 0 && lane == 0) {
@@ -103,6 +116,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
   const int num_tiles = (int)((args.total + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int NL = prog.num_layers;
+  const size_t act_stride = (size_t)act_tile_images(args.act_slots) * DG_KBLOCK;
 
   if (warp == 0) {
     // ------------------------------------------------------------ transposed-weight producer
@@ -124,7 +138,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: converged warp, one elected lane issues
-    // (uniform control flow keeps the descriptors in uniform registers, see nerf_mlp.cu)
+    // (uniform control flow keeps the descriptors in uniform registers, see nerf_mlp.cu).  The first layer reads dZ_top from
+    // shared memory; every later layer reads the gradient the epilogue packed back into tensor memory.
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     const uint32_t h_lo = (ptx::smem_u32(sm.h[0]) >> 4) & 0x3FFF;
     const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
@@ -144,17 +159,17 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
           }
           ptx::mbar_wait(&sm.w_full[st], ph);
           ptx::tc_fence_after();
-          const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (h_lo + (uint32_t)kb * (DG_KBLOCK >> 4));
-          const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (w_lo + st * (DG_STAGE >> 4));
           const uint32_t issue = ptx::elect_one();
-          ptx::umma_bf16_if(issue, d_addr, a_desc, b_desc, idesc, kb == 0 ? 0u : 1u);
-          ptx::umma_bf16_if(issue, d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
-          ptx::umma_bf16_if(issue, d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
-          ptx::umma_bf16_if(issue, d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          if (l > 0)
+            ptx::umma4_bf16_ts_if(issue, d_addr, tmem + (buf ^ 1u) * 256 + (uint32_t)kb * 64, 32u, w_lo + st * (DG_STAGE >> 4), desc_hi,
+                                  idesc, kb == 0 ? 0u : 1u, 4u);
+          else
+            ptx::umma4_bf16_if(issue, d_addr, h_lo + (uint32_t)kb * (DG_KBLOCK >> 4), w_lo + st * (DG_STAGE >> 4), desc_hi, idesc,
+                               kb == 0 ? 0u : 1u, 4u);
           ptx::umma_commit_if(issue, &sm.w_empty[st]);
           if (kb == nkb - 1) {
             ptx::umma_commit_if(issue, &sm.d_full[buf]);
-            if (l == NL - 1) ptx::umma_commit_if(issue, &sm.h_free);
+            if (l == 0) ptx::umma_commit_if(issue, &sm.h_free);
           }
           if (++st == DG_STAGES) { st = 0; ph ^= 1; }
         }
@@ -163,6 +178,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
   } else if (warp >= DG_INIT_WARP0) {
     // ------------------------------------------------------------ init warps: heads -> dZ_top, head-gradient images
     const int row = (warp - DG_INIT_WARP0) * 32 + lane;
+    const bool leader = threadIdx.x == DG_INIT_WARP0 * 32;
     const int tw = prog.top_width;
     const float* hw = sm.side + prog.head_w_offset;
     for (int t = 0; t < my_tiles; ++t) {
@@ -193,63 +209,83 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
         *reinterpret_cast<uint4*>(img + ptx::sw128_offset(row, 0)) = make_uint4(ptx::pack_bf16(d_o[0], d_o[1]), ptx::pack_bf16(d_o[2], d_o[3]), 0u, 0u);
         *reinterpret_cast<uint4*>(img + DG_KBLOCK + ptx::sw128_offset(row, 0)) = make_uint4(ptx::pack_bf16(dsig, 0.f), 0u, 0u, 0u);
       }
-      const uint8_t* mtile = args.acts + ((size_t)tile * args.act_slots + prog.top_mask_slot) * DG_KBLOCK;
-      // H of the previous tile is still being read until its last layer's MMAs retire
-      ptx::mbar_wait(&sm.h_free, (t & 1) ^ 1);
-      sm.dsig[row] = dsig;
-      uint8_t* top = args.dz + ((size_t)tile * args.dz_slots + prog.top_slot) * DG_KBLOCK;
-      for (int u = 0; u < tw / 8; ++u) {               // 8 columns (one 16-byte unit) at a time
-        float v[8];
+      // ReLU mask of the top hidden layer: one word per 32 columns
+      const uint8_t* mrec = args.acts + (size_t)tile * act_stride;
+      uint32_t mbits[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = u * 8 + j;
-          float a = 0.f;
-          for (int c = 0; c < head_rows; ++c) a = fmaf(d_o[c], hw[c * tw + col], a);
-          v[j] = a;
+      for (int q = 0; q < 8; ++q)
+        mbits[q] = q < tw / 32 ? __ldg(reinterpret_cast<const uint32_t*>(mrec + act_mask_offset(args.act_slots, prog.top_mask_slot + (q >> 1)) +
+                                                                          (q & 1) * 512 + row * 4))
+                               : 0u;
+      // `h` of the previous tile: read by its first layer's MMAs and by the bulk copies of its dZ_top images
+      if (leader) ptx::bulk_wait_read<0>();
+      dg_init_bar();
+      ptx::mbar_wait(&sm.h_free, (t & 1) ^ 1);
+      sm.dsig[t & 1][row] = dsig;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                    // 32 columns = four 16-byte units at a time
+        if (q >= tw / 32) break;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int u = q * 4 + uu;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = u * 8 + j;
+            float a = 0.f;
+            for (int c = 0; c < head_rows; ++c) a = fmaf(d_o[c], hw[c * tw + col], a);
+            v[j] = a;
+          }
+          const uint32_t off = ptx::sw128_offset(row, u & 7);
+          const uint32_t bq = mbits[q] >> (8 * uu);
+          *reinterpret_cast<uint4*>(sm.h[u >> 3] + off) =
+              make_uint4(ptx::pack_bf16(v[0], v[1]) & pair_mask(bq, 0), ptx::pack_bf16(v[2], v[3]) & pair_mask(bq, 1),
+                         ptx::pack_bf16(v[4], v[5]) & pair_mask(bq, 2), ptx::pack_bf16(v[6], v[7]) & pair_mask(bq, 3));
         }
-        const uint32_t off = ptx::sw128_offset(row, u & 7);
-        const uint4 x = *reinterpret_cast<const uint4*>(mtile + (size_t)(u >> 3) * DG_KBLOCK + off);
-        const uint4 q = make_uint4(ptx::pack_bf16(v[0], v[1]) & __vcmpne2(x.x, 0u), ptx::pack_bf16(v[2], v[3]) & __vcmpne2(x.y, 0u),
-                                   ptx::pack_bf16(v[4], v[5]) & __vcmpne2(x.z, 0u), ptx::pack_bf16(v[6], v[7]) & __vcmpne2(x.w, 0u));
-        *reinterpret_cast<uint4*>(sm.h[u >> 3] + off) = q;
-        *reinterpret_cast<uint4*>(top + (size_t)(u >> 3) * DG_KBLOCK + off) = q;
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sm.top_ready);
+      // the same images go to HBM (operands of the weight-gradient kernel) as bulk copies
+      dg_init_bar();
+      if (leader) {
+        uint8_t* top = args.dz + ((size_t)tile * args.dz_slots + prog.top_slot) * DG_KBLOCK;
+        ptx::bulk_s2g(top, sm.h[0], (uint32_t)(tw / 64) * DG_KBLOCK);
+        ptx::bulk_commit();
+      }
     }
+    if (leader) ptx::bulk_wait_all();
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;
     const int grp = (warp - DG_EPI_WARP0) >> 2;
     const int row = quarter * 32 + lane;
-    uint32_t layer_count = 0, d_phase = 0;
+    const bool leader = threadIdx.x == DG_EPI_WARP0 * 32;
+    uint32_t layer_count = 0, d_phase = 0, out_count = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const uint8_t* mrec = args.acts + (size_t)tile * act_stride;
       for (int l = 0; l < NL; ++l, ++layer_count) {
         const DgradLayer& L = prog.layers[l];
         const uint32_t buf = layer_count & 1;
         const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + grp * DG_COLS;
         const bool last = l == NL - 1;
         const float* wsig = L.rank1_offset >= 0 ? sm.side + L.rank1_offset : nullptr;
-        const uint8_t* mtile = L.mask_slot >= 0 ? args.acts + ((size_t)tile * args.act_slots + L.mask_slot) * DG_KBLOCK : nullptr;
         uint8_t* out = args.dz + ((size_t)tile * args.dz_slots + L.dz_slot) * DG_KBLOCK;
-        // the activation units this thread masks with: issued before the accumulator is ready (independent of the MMAs)
+        // the mask words this thread applies: issued before the accumulator is ready (independent of the MMAs)
         const int out_blocks = L.n_out >> 6;
-        uint4 mx[4][4];
+        uint32_t mb[4];
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            mx[kb][u] = (mtile != nullptr && kb < out_blocks)
-                            ? __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)kb * DG_KBLOCK + ptx::sw128_offset(row, grp * 4 + u)))
-                            : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+          mb[kb] = (L.mask_slot >= 0 && kb < out_blocks)
+                       ? __ldg(reinterpret_cast<const uint32_t*>(mrec + act_mask_offset(args.act_slots, L.mask_slot + kb) + grp * 512 + row * 4))
+                       : 0xFFFFFFFFu;
         const long long m_row = tile * 128 + row;
         float* grow = (L.rows_cols > 0 && args.g_rows != nullptr && m_row < args.total) ? args.g_rows + (size_t)m_row * args.g_row_pitch : nullptr;
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
         d_phase ^= 1u << buf;
         ptx::tc_fence_after();
-        const float ds = wsig != nullptr ? sm.dsig[row] : 0.f;
+        const float ds = wsig != nullptr ? sm.dsig[t & 1][row] : 0.f;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           if (kb >= out_blocks) break;
@@ -276,25 +312,35 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
             }
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 x = mx[kb][u];
-            const uint4 q = make_uint4(pk[4 * u] & __vcmpne2(x.x, 0u), pk[4 * u + 1] & __vcmpne2(x.y, 0u),
-                                       pk[4 * u + 2] & __vcmpne2(x.z, 0u), pk[4 * u + 3] & __vcmpne2(x.w, 0u));
-            const uint32_t off = ptx::sw128_offset(row, grp * 4 + u);
-            if (L.dz_slot >= 0) *reinterpret_cast<uint4*>(out + (size_t)kb * DG_KBLOCK + off) = q;
-            if (!last) *reinterpret_cast<uint4*>(sm.h[kb] + off) = q;
-          }
+          for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & pair_mask(mb[kb], j);
           if (!last) {
-            ptx::fence_proxy_async_smem();
+            // K block kb of the next backward layer's A operand: packed pairs over the accumulator columns just drained
+            ptx::tmem_st16(t_row + kb * 64, pk);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&sm.a_ready[kb]);
+          }
+          if (L.dz_slot >= 0) {
+            // dZ tile image for the weight-gradient kernel: staged in shared memory, written by one 16 KB bulk copy
+            uint8_t* stg = sm.out[out_count % DG_OUT_BUFS];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(stg + ptx::sw128_offset(row, grp * 4 + u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            ptx::fence_proxy_async_smem();
+            if (leader) ptx::bulk_wait_read<DG_OUT_BUFS - 2>();     // the next block's buffer is free once everybody passes the barrier
+            dg_epi_bar();
+            if (leader) {
+              ptx::bulk_s2g(out + (size_t)kb * DG_KBLOCK, stg, DG_KBLOCK);
+              ptx::bulk_commit();
+            }
+            ++out_count;
           }
         }
         ptx::tc_fence_before();
       }
     }
+    if (leader) ptx::bulk_wait_all();
   }
   ptx::tc_fence_before();
   __syncthreads();

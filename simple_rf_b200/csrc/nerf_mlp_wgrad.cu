@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_mlp_wgrad_kernel(const __g
                         p.dz + ((size_t)tile * p.dz_slots + it.dz_slot + a) * (2 * HALF_IMAGE) + half * HALF_IMAGE, HALF_IMAGE, &sm.full[s]);
         for (int b = 0; b < it.x_images; ++b)
           ptx::bulk_g2s(sm.stage[s] + (4 + b) * HALF_IMAGE,
-                        p.acts + ((size_t)tile * p.act_slots + it.x_slot + b) * (2 * HALF_IMAGE) + half * HALF_IMAGE, HALF_IMAGE, &sm.full[s]);
+                        p.acts + ((size_t)tile * act_tile_images(p.act_slots) + it.x_slot + b) * (2 * HALF_IMAGE) + half * HALF_IMAGE, HALF_IMAGE, &sm.full[s]);
       }
     }
   } else if (warp == 1) {

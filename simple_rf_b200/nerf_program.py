@@ -179,7 +179,7 @@ class PackedMLP:
         prog = self.program
         if save:
             tiles = (R * S + 127) // 128
-            acts = torch.empty((tiles, prog.act_slots, 16384), dtype=torch.uint8, device=z.device)
+            acts = torch.empty((tiles, act_tile_images(prog.act_slots), 16384), dtype=torch.uint8, device=z.device)
         L.call('srf_nerf_mlp_fwd', ctypes.addressof(prog), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
                L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
                L.ptr(sigma), L.ptr(rgb), L.ptr(acts), prog.act_slots if save else 0, 0, max(prog.v_slot, 0),
@@ -344,7 +344,8 @@ class PackedRowsMLP:
         count undefined).  save=True also returns the saved activation tile images for `backward`."""
         assert rows.dtype == torch.bfloat16 and rows.shape[1] >= self.in_cols and rows.is_contiguous()
         rgb = torch.empty((max_rows, 3), dtype=torch.float32, device=rows.device)
-        acts = torch.empty(((max_rows + 127) // 128, self.act_slots, 16384), dtype=torch.uint8, device=rows.device) if save else None
+        acts = torch.empty(((max_rows + 127) // 128, act_tile_images(self.act_slots), 16384), dtype=torch.uint8,
+                           device=rows.device) if save else None
         L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
                rows.shape[1], L.ptr(count), max_rows, L.ptr(rgb), L.ptr(acts), self.act_slots, self.e_slot, self.v_slot,
                L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
@@ -367,7 +368,7 @@ class PackedRowsMLP:
         dz = torch.empty((tiles, plan.dz_slots, 16384), dtype=torch.uint8, device=dev)
         pitch = -(-self.num_products // 4) * 4
         g_rows = torch.empty((max(num_rows, 1), pitch), dtype=torch.float32, device=dev)
-        L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), acts.shape[1], None, L.ptr(rgb),
+        L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), act_data_slots(acts.shape[1]), None, L.ptr(rgb),
                None, L.ptr(L.f32c(g_rgb)), num_rows, L.ptr(dz), plan.dz_slots, L.ptr(g_rows), pitch, L.stream_handle(),
                work=2.0 * (2 * self.units * self.units) * num_rows)
         grads = torch.zeros(self.flat_size, dtype=torch.float32, device=dev)
@@ -388,6 +389,21 @@ class PackedRowsMLP:
         return g_flat[o:o + int(np.prod(shape))].view(shape)
 
 
+def act_tile_images(act_slots):
+    """Images per tile of a saved-activation buffer: the data images plus one mask image per 16 of them (the forward writes,
+    for every saved image, one 32-bit non-zero mask per (row, 32-column group): csrc/common.cuh act_mask_offset)."""
+    return act_slots + (act_slots + 15) // 16
+
+
+def act_data_slots(tile_images):
+    """Inverse of act_tile_images."""
+    d = tile_images
+    while act_tile_images(d) > tile_images:
+        d -= 1
+    assert act_tile_images(d) == tile_images, 'not a saved-activation buffer'
+    return d
+
+
 class WgradItem(ctypes.Structure):
     _fields_ = [('dz_slot', ctypes.c_int32), ('dz_images', ctypes.c_int32), ('x_slot', ctypes.c_int32), ('x_images', ctypes.c_int32),
                 ('out_rows', ctypes.c_int32), ('in_col0', ctypes.c_int32), ('in_cols', ctypes.c_int32), ('w_col0', ctypes.c_int32),
@@ -399,7 +415,7 @@ def run_wgrad(items, acts, dz, grads):
     arr = (WgradItem * len(items))(*items)
     tiles = acts.shape[0]
     flops = sum(2.0 * 64 * it.dz_images * 64 * it.x_images * 128 * tiles for it in items)
-    L.call('srf_nerf_mlp_wgrad', ctypes.addressof(arr), len(items), L.ptr(acts), acts.shape[1], L.ptr(dz), dz.shape[1], tiles,
+    L.call('srf_nerf_mlp_wgrad', ctypes.addressof(arr), len(items), L.ptr(acts), act_data_slots(acts.shape[1]), L.ptr(dz), dz.shape[1], tiles,
            L.ptr(grads), L.stream_handle(), work=flops)
 
 
@@ -529,7 +545,7 @@ def mlp_backward(packed, params_flat, acts, sigma, rgb, g_sigma, g_rgb):
     dz = torch.empty((tiles, plan.dz_slots, 16384), dtype=torch.uint8, device=dev)
     gs = None if g_sigma is None else L.f32c(g_sigma).reshape(-1)
     gc = None if g_rgb is None else L.f32c(g_rgb).reshape(-1, 3)
-    L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), acts.shape[1], L.ptr(sigma), L.ptr(rgb),
+    L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), act_data_slots(acts.shape[1]), L.ptr(sigma), L.ptr(rgb),
            L.ptr(gs), L.ptr(gc), rows, L.ptr(dz), plan.dz_slots, None, 0, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
     grads = torch.zeros(packed.flat_size, dtype=torch.float32, device=dev)
     run_wgrad(plan.items, acts, dz, grads)

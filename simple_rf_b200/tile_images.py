@@ -29,3 +29,22 @@ def encode(x, tiles):
     img = torch.empty_like(xb)
     img[:, :, perm] = xb
     return img.view(torch.uint8).view(tiles, nb, 16384)
+
+
+def add_masks(acts):
+    """Append the mask images the forward kernel writes after the data images (csrc/common.cuh act_mask_offset): one 32-bit
+    word per (image, 32-column group, row), bit i = value of column 32*group + i is non-zero."""
+    from .nerf_program import act_tile_images
+    tiles, slots, _ = acts.shape
+    out = torch.zeros((tiles, act_tile_images(slots), 16384), dtype=torch.uint8, device=acts.device)
+    out[:, :slots] = acts
+    words = out[:, slots:].reshape(tiles, -1).view(torch.int32)                    # [tiles, mask images * 4096]
+    weights = (1 << torch.arange(32, device=acts.device, dtype=torch.int64))
+    for s in range(slots):
+        nz = decode(acts, s, 1).view(tiles, 128, 2, 32) != 0                         # [tile, row, group, bit]
+        w = (nz.to(torch.int64) * weights).sum(-1)                                   # [tile, row, group]
+        w = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+        base = (s // 16) * 4096 + (s % 16) * 256
+        for g in range(2):
+            words[:, base + g * 128: base + g * 128 + 128] = w[:, :, g]
+    return out

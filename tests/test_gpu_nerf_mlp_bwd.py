@@ -59,6 +59,17 @@ def test_forward_saves_activation_tiles(golden_configs, variant):
     ref = _hidden(params, cfg, pts, vflat)
     prog = packed.program
     n = R * S
+    # the non-zero mask words written next to the tiles (what the dgrad chain reads as ReLU masks): bit-exact against the host
+    # restatement, for every image an epilogue saved (the encoding images E / V carry no mask)
+    from simple_rf_b200.nerf_program import act_tile_images
+    assert acts.shape[1] == act_tile_images(prog.act_slots)
+    host = TI.add_masks(acts[:, :prog.act_slots].contiguous())
+    words, hwords = (x[:, prog.act_slots:].reshape(acts.shape[0], -1).view(torch.int32) for x in (acts, host))
+    for l in range(prog.num_layers):
+        s0 = prog.layers[l].save_slot if prog.layers[l].relu else -1      # the words are ReLU masks: x > 0
+        for s_ in range(s0, s0 + prog.layers[l].n // 64 if s0 >= 0 else s0):
+            base = (s_ // 16) * 4096 + (s_ % 16) * 256
+            assert torch.equal(words[:, base:base + 256], hwords[:, base:base + 256]), (l, s_)
     enc = TI.decode(acts, 0, 1)[:n].cpu()
     assert (enc[:, :63] - ref['enc']).abs().max().item() <= 1e-2          # bf16 rounding of values up to ~1
     assert (enc[:, 63] == 0).all()
@@ -93,7 +104,7 @@ def test_wgrad_kernel_vs_matmul():
     X = torch.randn(M_, 6 * 64, device=DEV, generator=g).to(torch.bfloat16).float()          # slots 0..5
     dZ = (torch.randn(M_, 6 * 64, device=DEV, generator=g) * 0.1).to(torch.bfloat16).float()  # slots 0..5
     dZ[-40:] = 0                                                                              # padded rows carry no gradient
-    acts, dz = TI.encode(X, tiles), TI.encode(dZ, tiles)
+    acts, dz = TI.add_masks(TI.encode(X, tiles)), TI.encode(dZ, tiles)
     # item 0: a 256x256 hidden layer (dz 0..3, x 1..4) with bias; item 1: its 63-wide encoding block (x slot 0, columns 0..62
     # -> weight columns 0..62 of a [256, 319] matrix); item 2: a 3-row head over 128 inputs (dz 4..5, x 4..5)
     grads = torch.zeros(256 * 256 + 256 + 256 * 319 + 3 * 128 + 3, device=DEV)
