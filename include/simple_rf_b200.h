@@ -115,9 +115,13 @@ typedef struct {
  *   z [R,S];  view_dirs [R,3] (NULL iff views_degree < 0);  noise [R*S] nullable: the reference's
  *   randn * raw_noise_std (SimpleNeRF17.py:739-741), added before the sigma ReLU;
  *   sigma [R*S], rgb [R*S,3]: post-activation outputs.
- *   Training (save_acts != NULL): every A-operand tile is also written to HBM as [tile][act_slots][128 x 64 bf16
- *   swizzled image] (encodings at e_slot / v_slot, layer outputs at layers[l].save_slot); these feed
- *   srf_nerf_mlp_dgrad (as ReLU masks) and srf_nerf_mlp_wgrad (as GEMM operands). */
+ *   Training (save_acts != NULL): every A-operand tile is also written to HBM as [tile][act_slots + M][128 x 64 bf16
+ *   swizzled image] (encodings at e_slot / v_slot, layer outputs at layers[l].save_slot); the images feed
+ *   srf_nerf_mlp_wgrad as GEMM operands.  The M = ceil(act_slots / 16) trailing "mask images" hold, for every saved layer
+ *   output image s, one 32-bit word per (32-column group g, row r) at byte (act_slots + s / 16) * 16384 + (s % 16) * 1024 +
+ *   g * 512 + r * 4 of the tile: bit i = pre-activation value of column 32 g + i is positive.  srf_nerf_mlp_dgrad reads
+ *   these words as ReLU masks (128 bytes per warp instead of the activation rows).  `act_slots` counts the data images
+ *   only, in all three entry points. */
 int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side, const float* rays_o,
                      const float* rays_d, const float* z, const float* view_dirs, const float* noise,
                      int64_t num_rays, int num_samples, float* sigma, float* rgb, void* save_acts,
@@ -208,7 +212,7 @@ int srf_wgrad_item_bytes(void);
 /* Data-gradient chain of the fused MLP (what autograd derives for src/models/SimpleNeRF17.py:726-785): from
  * g_sigma [M], g_rgb [M,3] (nullable) through the heads and every hidden layer down to layer 1, on tcgen05 with the
  * transposed weights streamed as swizzled images ([layer][128-row half of the 256 inputs][K block of outputs]).
- * Reads the saved activation tiles (their non-zero pattern is the ReLU mask) and the sigma / rgb outputs of
+ * Reads the mask words saved next to the activation tiles (see srf_nerf_mlp_fwd) and the sigma / rgb outputs of
  * srf_nerf_mlp_fwd; writes every layer's pre-activation
  * gradient as tile images into dz [tile][dz_slots][16 KB] for srf_nerf_mlp_wgrad.
  * Every backward layer has its own output width n_out (128 or 256).  The TensoRF colour MLP
