@@ -248,6 +248,7 @@ def extras(device):
         torch.manual_seed(0)
         model = SimpleNeRF(cfg, mc).to(device).train()
         opt = torch.optim.Adam(model.get_trainable_parameters(cfg['optimizers'][0]), betas=(0.9, 0.999))
+        model.optimizers = {'optimizer_nerf': opt}        # what Trainer10.py:59-62 does: the drop-in attaches its fused Adam step
         g = torch.Generator().manual_seed(2)
         pid = torch.stack([torch.randint(0, 3, (4096,), generator=g), torch.randint(0, FRAME_W, (4096,), generator=g),
                            torch.randint(0, FRAME_H, (4096,), generator=g)], 1).int().to(device)
@@ -280,6 +281,7 @@ def extras(device):
         vol = (torch.rand(190, 190, 190, generator=torch.Generator().manual_seed(1)) < 0.05).float()
         t.alpha_mask = AlphaGridMask(vol, t.bounding_box.cpu()).to(device)
         opt = torch.optim.Adam(model.get_trainable_parameters(cfg['optimizers'][0]), betas=(0.9, 0.99))
+        model.optimizers = {'optimizer_nerf': opt}        # what Trainer10.py:59-62 does: the drop-in attaches its fused Adam step
         h, w = mc['resolution']
         g = torch.Generator().manual_seed(2)
         pid = torch.stack([torch.randint(0, 3, (4096,), generator=g), torch.randint(0, w, (4096,), generator=g),

@@ -247,6 +247,13 @@ int srf_patch_reprojection_masks(const float* rays_o, const float* rays_d, const
                                  int patch_x, int patch_y, float rmse_threshold, int both_invalid_rule, uint8_t* mask1,
                                  uint8_t* mask2, float* rmse1, float* rmse2, void* stream);
 
+/* ---- "next" row f4: optimiser tail.  One fused Adam step over flat fp32 arrays (device pointers, 16-byte
+ * aligned), replacing torch.optim.Adam.step as created by src/optimizers/OptimizerFactory02.py:9-22 and called at
+ * src/Trainer10.py:109-110; arithmetic of torch/optim/adam.py::_single_tensor_adam (amsgrad / maximize off), `step` counts
+ * from 1, weight_decay is the L2 form (0 in every shipped config). */
+int srf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

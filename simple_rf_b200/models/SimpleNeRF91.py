@@ -51,8 +51,10 @@ class SimpleNeRF(torch.nn.Module):
     def __setattr__(self, name, value):
         super().__setattr__(name, value)
         if name == 'optimizers' and value is not None:
-            # multi-GPU: one flat-bucket NCCL all-reduce of the gradients before every optimizer.step()
-            from .. import parallel
+            # optimiser tail: Adam optimisers step through one fused kernel over flat buffers, with ONE
+            # all-reduce of the flat gradient bucket on several ranks; other optimisers get the generic all-reduce hook
+            from .. import optim, parallel
+            super().__setattr__('_fused_adam', optim.attach(value) if optim.enabled() else [])
             super().__setattr__('_grad_allreduce', parallel.attach_gradient_allreduce(value))
 
     # ------------------------------------------------------------------ construction (SimpleNeRF17.py:36-75)

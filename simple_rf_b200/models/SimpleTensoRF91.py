@@ -93,8 +93,10 @@ class SimpleTensoRF(torch.nn.Module):
         if name == 'optimizers' and value is not None:           # SimpleTensoRF09.py:98-113
             for t in self._tensors():
                 t.optimizers = value
-            # multi-GPU: one flat-bucket NCCL all-reduce of the gradients before every optimizer.step()
-            from .. import parallel
+            # optimiser tail: Adam optimisers step through one fused kernel over flat buffers, with ONE
+            # all-reduce of the flat gradient bucket on several ranks; other optimisers get the generic all-reduce hook
+            from .. import optim, parallel
+            super().__setattr__('_fused_adam', optim.attach(value) if optim.enabled() else [])
             super().__setattr__('_grad_allreduce', parallel.attach_gradient_allreduce(value))
 
     def rebuild_camera_params_learners(self, *, intrinsics: numpy.ndarray = None, extrinsics=None, device):

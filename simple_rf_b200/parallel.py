@@ -109,7 +109,8 @@ def attach_gradient_allreduce(optimizers):
     """optimizers: the trainer's dict name -> torch optimiser.  Returns the hooks (kept alive by the caller)."""
     if not is_distributed():
         return []
-    return [FlatGradAllReduce(opt) for opt in optimizers.values() if opt is not None]
+    # optimisers stepping through optim.FusedFlatAdam reduce their own flat gradient bucket
+    return [FlatGradAllReduce(opt) for opt in optimizers.values() if opt is not None and getattr(opt, '_srf_fused', None) is None]
 
 
 def render_sharded(model, input_batch, gather_keys=None, **forward_kwargs):

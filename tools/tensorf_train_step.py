@@ -23,6 +23,7 @@ vol = (torch.rand(190, 190, 190, generator=torch.Generator().manual_seed(1)) < 0
 t.alpha_mask = AlphaGridMask(vol, t.bounding_box.cpu()).to(dev)
 groups = model.get_trainable_parameters(cfg['optimizers'][0]) if hasattr(model, 'get_trainable_parameters') else None
 opt = torch.optim.Adam(groups, betas=(0.9, 0.99))
+model.optimizers = {'optimizer_nerf': opt}        # what Trainer10.py:59-62 does: the drop-in attaches its fused Adam step
 h, w = mc['resolution']
 g = torch.Generator().manual_seed(2)
 pid = torch.stack([torch.randint(0, 3, (4096,), generator=g), torch.randint(0, w, (4096,), generator=g),

@@ -14,6 +14,7 @@ mc = synthetic.scene_model_configs('llff', num_views=3)
 torch.manual_seed(0)
 model = SimpleNeRF(cfg, mc).to(dev).train()
 opt = torch.optim.Adam(model.get_trainable_parameters(cfg['optimizers'][0]), betas=(0.9, 0.999))
+model.optimizers = {'optimizer_nerf': opt}        # what Trainer10.py:59-62 does: the drop-in attaches its fused Adam step
 g = torch.Generator().manual_seed(2)
 pid = torch.stack([torch.randint(0, 3, (4096,), generator=g), torch.randint(0, 1008, (4096,), generator=g),
                    torch.randint(0, 756, (4096,), generator=g)], 1).int().to(dev)
