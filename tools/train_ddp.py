@@ -59,7 +59,10 @@ else:
     same = torch.ones(1)
 if rank == 0:
     hooks = getattr(model, '_grad_allreduce', [])
+    fused = getattr(model, '_fused_adam', [])
+    nbytes = fused[0].bytes_reduced_last if fused else (hooks[0].bytes_last if hooks else 0)
     print(f'world {world}: {ms.item():.3f} ms / iteration ({1e3 / ms.item():.1f} it/s over a 4096-ray global batch), '
-          f'ranks in lock-step: {bool(same.item())}, all-reduce bytes/step: {hooks[0].bytes_last if hooks else 0}')
+          f'ranks in lock-step: {bool(same.item())}, all-reduce bytes/step: {nbytes} '
+          f"({'fused flat Adam' if fused else 'torch Adam + hook'})")
 if world > 1:
     dist.destroy_process_group()
