@@ -295,6 +295,45 @@ def golden_patch_loss():
     np.savez_compressed(OUT / 'patch_loss.npz', **_np(fixture))
 
 
+def golden_nerf_training_curve(iters=8, R=96):
+    """Loss scalars per iteration (SURVEY.md §8c parity ledger): the UNMODIFIED reference model trained for a few iterations
+    with the reference's optimiser (torch.optim.Adam over get_trainable_parameters, as OptimizerFactory02 builds it) on fixed
+    random batches; the drop-in (forward + hand-written backward + fused Adam) must follow the same curve."""
+    configs, model_configs = H.load_configs(1142, 'fern')
+    model_configs = H.shrink(model_configs, 4)
+    configs['model']['netchunk'] = 2048
+    model = H.build_model(configs, model_configs)
+    sets = FX.nerf_param_sets(configs, seed=11)
+    load_nerf_params(model, sets)
+    model.train()
+    opt_cfg = next(c for c in configs['optimizers'] if c['name'] == 'optimizer_main')
+    opt = torch.optim.Adam(model.get_trainable_parameters(opt_cfg), lr=opt_cfg['lr_initial'], betas=(opt_cfg['beta1'], opt_cfg['beta2']))
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    g = torch.Generator().manual_seed(77)
+    pids, targets, losses = [], [], []
+    torch.manual_seed(4242)
+    rgb_keys = ('rgb_coarse', 'rgb_fine', 'points_augmentation_rgb_coarse', 'views_augmentation_rgb_coarse')
+    for it in range(iters):
+        if it % 4 == 0:                                # a new batch every 4 iterations: the loss falls within a batch
+            pid = FX.random_pixels(R, nviews, h, w, 500 + it)
+            target = torch.rand(R, 3, generator=g)
+        opt.zero_grad(set_to_none=True)
+        out = model({'pixel_id': pid, 'num_frames': nviews, 'iter_num': it, 'sub_batch_index': 0})
+        loss = sum(((out[k] - target) ** 2).mean() for k in rgb_keys)
+        loss = loss + 0.1 * (out['depth_coarse'] - out['points_augmentation_depth_coarse'].detach()).square().mean()
+        loss.backward()
+        opt.step()
+        pids.append(pid); targets.append(target); losses.append(loss.detach())
+        print(f'  reference training iteration {it}: loss {loss.item():.6f}')
+    norms = torch.stack([p.detach().norm() for p in model.coarse_model.parameters()])
+    fixture = {'pixel_id': torch.stack(pids), 'target': torch.stack(targets), 'loss': torch.stack(losses), 'param_seed': 11,
+               'rng_seed': 4242, 'lr': opt_cfg['lr_initial'], 'beta1': opt_cfg['beta1'], 'beta2': opt_cfg['beta2'],
+               'coarse_param_norms': norms}
+    np.savez_compressed(OUT / 'nerf_train_curve.npz', **_np(fixture))
+    print(f'nerf_train_curve: {iters} iterations of the reference model')
+
+
 def main():
     if not H.available():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
@@ -305,6 +344,7 @@ def main():
     golden_composite(copy.deepcopy(configs), model_configs)
     golden_tensorf()
     golden_patch_loss()
+    golden_nerf_training_curve()
 
 
 if __name__ == '__main__':
