@@ -334,6 +334,60 @@ def golden_nerf_training_curve(iters=8, R=96):
     print(f'nerf_train_curve: {iters} iterations of the reference model')
 
 
+def tensorf_curve_configs():
+    """Shipped TensoRF training config, shrunk for the CPU, with a resolution upsampling at iteration 4 and an alpha-mask
+    rebuild (+ bounding-box shrink) at iteration 6 so that the curve crosses the in-forward model surgery and the
+    optimiser re-grouping (src/models/SimpleTensoRF09.py:821-944)."""
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    for cm, (v0, v1) in ((configs['model']['coarse_model'], (36, 52)), (configs['model']['augmentations'][0]['coarse_model'], (20, 28))):
+        cm['num_voxels_initial'] = v0 ** 3
+        cm['num_voxels_final'] = v1 ** 3
+        cm['tensor_upsampling_iters'] = [4]
+        cm['alpha_mask_update_iters'] = [6]
+    return configs, model_configs
+
+
+def golden_tensorf_training_curve(iters=8, R=96):
+    """TensoRF counterpart of golden_nerf_training_curve: the unmodified reference model, its own parameter groups
+    (lr_initial_tensor / lr_initial_network), torch.optim.Adam handed over through `model.optimizers` as Trainer10 does."""
+    configs, model_configs = tensorf_curve_configs()
+    (OUT / 'tensorf_curve_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    sets = FX.tensorf_sets(configs, seed=21, with_alpha=False)
+    load_tensorf_params(model, sets)
+    model.train()
+    opt_cfg = next(c for c in configs['optimizers'] if c['name'] == 'optimizer_main')
+    opt = torch.optim.Adam(model.get_trainable_parameters(opt_cfg), betas=(opt_cfg['beta1'], opt_cfg['beta2']))
+    model.optimizers = {'optimizer_nerf': opt}
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    g = torch.Generator().manual_seed(78)
+    pids, targets, losses, grids = [], [], [], []
+    torch.manual_seed(4343)
+    for it in range(iters):
+        if it % 4 == 0:
+            pid = FX.random_pixels(R, nviews, h, w, 600 + it)
+            target = torch.rand(R, 3, generator=g)
+        opt.zero_grad(set_to_none=True)
+        out = model({'pixel_id': pid, 'num_frames': nviews, 'iter_num': it + 1, 'sub_batch_index': 0})
+        loss = ((out['rgb_coarse'] - target) ** 2).mean() + ((out['points_augmentation_rgb_coarse'] - target) ** 2).mean()
+        loss = loss + 0.1 * (out['depth_coarse'] - out['points_augmentation_depth_coarse'].detach()).square().mean()
+        loss = loss + 1e-3 * out['weights_coarse'].square().sum(dim=1).mean()
+        loss.backward()
+        opt.step()
+        pids.append(pid); targets.append(target); losses.append(loss.detach())
+        grids.append(torch.as_tensor([int(v) for v in model.coarse_model.resolution]))
+        print(f'  reference TensoRF iteration {it + 1}: loss {loss.item():.6f}, grid {grids[-1].tolist()}, '
+              f'samples/ray {int(model.coarse_model.num_samples)}, alpha mask {model.coarse_model.alpha_mask is not None}')
+    norms = torch.stack([p.detach().norm() for p in model.coarse_model.parameters()])
+    fixture = {'pixel_id': torch.stack(pids), 'target': torch.stack(targets), 'loss': torch.stack(losses), 'param_seed': 21,
+               'rng_seed': 4343, 'grid': torch.stack(grids), 'coarse_param_norms': norms,
+               'bounding_box': model.coarse_model.bounding_box.detach().clone()}
+    np.savez_compressed(OUT / 'tensorf_train_curve.npz', **_np(fixture))
+    print(f'tensorf_train_curve: {iters} iterations of the reference model')
+
+
 def main():
     if not H.available():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
@@ -345,6 +399,7 @@ def main():
     golden_tensorf()
     golden_patch_loss()
     golden_nerf_training_curve()
+    golden_tensorf_training_curve()
 
 
 if __name__ == '__main__':

@@ -275,3 +275,50 @@ def test_dropin_training_gradients(golden, golden_configs):
             assert rel <= 1e-4 and l2 <= 1e-4, (name, k, rel, l2)
         else:
             assert rel <= 1.5e-1 and l2 <= 8e-2, (name, k, rel, l2)
+
+
+@pytest.mark.parametrize('fused_adam', [True, False])
+def test_training_curve_follows_reference_through_model_surgery(golden, golden_configs, fused_adam, monkeypatch):
+    """Loss scalars per iteration (parity ledger) for Simple-TensoRF: 8 training iterations on the batches of
+    tests/golden/tensorf_train_curve.npz against the curve of the UNMODIFIED reference model (torch autograd, torch.optim.Adam,
+    CPU; oracle/generate_golden.py::golden_tensorf_training_curve).  The schedule crosses a resolution upsampling with
+    optimiser re-grouping (iteration 4) and an alpha-mask rebuild with bounding-box shrink (iteration 6), all inside
+    forward() as in src/models/SimpleTensoRF09.py:141-145, 821-944.  Stated tolerance: 0.1 % of the loss per iteration (the
+    colour branch runs bf16 operands on the tensor cores in both directions; measured 8e-6), same grid / samples per ray / bounding box."""
+    from simple_rf_b200.models.SimpleTensoRF91 import SimpleTensoRF
+    monkeypatch.setenv('SIMPLE_RF_B200_FUSED_ADAM', '1' if fused_adam else '0')
+    g = golden('tensorf_train_curve')
+    configs, mc = golden_configs('tensorf_curve')
+    sets = FX.tensorf_sets(configs, seed=int(g['param_seed']), with_alpha=False)
+    model = SimpleTensoRF(configs, mc)
+    mods = [(model.coarse_model, sets['coarse_model'])] + [(a['coarse_model'], s[2]) for a, s in zip(model.augmented_models, sets['augmentations'])]
+    for mod, t in mods:
+        sd = dict(mod.named_parameters())
+        assert set(sd.keys()) == set(t['params'].keys())
+        for k, v in t['params'].items():
+            sd[k].data.copy_(v)
+        mod.alpha_mask = None
+    model = model.to(DEV).train()
+    opt_cfg = next(c for c in configs['optimizers'] if c['name'] == 'optimizer_main')
+    opt = torch.optim.Adam(model.get_trainable_parameters(opt_cfg), betas=(opt_cfg['beta1'], opt_cfg['beta2']))
+    model.optimizers = {'optimizer_nerf': opt}           # Trainer10.py:59-62
+    torch.manual_seed(int(g['rng_seed']))
+    worst = 0.0
+    for it in range(g['loss'].shape[0]):
+        pid, target = g['pixel_id'][it].to(DEV), g['target'][it].to(DEV)
+        opt.zero_grad(set_to_none=True)
+        out = model({'pixel_id': pid, 'num_frames': 3, 'iter_num': it + 1, 'sub_batch_index': 0})
+        loss = ((out['rgb_coarse'] - target) ** 2).mean() + ((out['points_augmentation_rgb_coarse'] - target) ** 2).mean()
+        loss = loss + 0.1 * (out['depth_coarse'] - out['points_augmentation_depth_coarse'].detach()).square().mean()
+        loss = loss + 1e-3 * out['weights_coarse'].square().sum(dim=1).mean()
+        loss.backward()
+        opt.step()
+        assert [int(v) for v in model.coarse_model.resolution] == g['grid'][it].tolist(), it
+        ref = g['loss'][it].item()
+        rel = abs(loss.item() - ref) / ref
+        worst = max(worst, rel)
+        print(f'iteration {it + 1}: loss {loss.item():.6f} (reference {ref:.6f})')
+        assert rel <= 1e-3, (it, loss.item(), ref)
+    assert (model.coarse_model.bounding_box.cpu() - g['bounding_box']).abs().max().item() <= 1e-5
+    assert model.coarse_model.alpha_mask is not None
+    print(f'worst relative loss deviation {worst:.2e}')
