@@ -247,6 +247,17 @@ int srf_patch_reprojection_masks(const float* rays_o, const float* rays_d, const
                                  int patch_x, int patch_y, float rmse_threshold, int both_invalid_rule, uint8_t* mask1,
                                  uint8_t* mask2, float* rmse1, float* rmse2, void* stream);
 
+/* ---- "next" row f2: device-side batch assembly.  Replaces load_nerf_cached_batch /
+ * load_sparse_depth_cached_batch (src/data_preprocessors/DataPreprocessor10.py:530-549, 568-595): row b takes the cached
+ * per-pixel tables at flat index indices[b] (all tables [num_pixels, C], device); image rays (is_sparse_depth[b] == 0, or
+ * is_sparse_depth NULL) get pixel_id + target_rgb, sparse-depth rays get pixel_id + depth / reprojection error / 3-D point;
+ * fields a ray kind does not carry are -1, as the reference initialises them.  sd_* outputs (and their tables) are nullable.
+ * Indices must lie in [0, num_pixels) (they are the reference's own shuffled index arrays). */
+int srf_assemble_batch(const int64_t* indices, const uint8_t* is_sparse_depth, int64_t batch, int64_t num_pixels,
+                       const int* pixel_table, const float* rgb_table, const float* depth_table, const float* error_table,
+                       const float* points_table, int* pixel_id, float* target_rgb, float* sd_depth, float* sd_error,
+                       float* sd_points, void* stream);
+
 /* ---- "next" row f4: optimiser tail.  One fused Adam step over flat fp32 arrays (device pointers, 16-byte
  * aligned), replacing torch.optim.Adam.step as created by src/optimizers/OptimizerFactory02.py:9-22 and called at
  * src/Trainer10.py:109-110; arithmetic of torch/optim/adam.py::_single_tensor_adam (amsgrad / maximize off), `step` counts

@@ -388,6 +388,30 @@ def golden_tensorf_training_curve(iters=8, R=96):
     print(f'tensorf_train_curve: {iters} iterations of the reference model')
 
 
+def golden_batch_assembly():
+    """f2: the reference's own load_nerf_cached_batch / load_sparse_depth_cached_batch (unbound, on a stand-in object holding the
+    cached tables) against oracle/batch.py, bit-exact; inputs + reference outputs -> tests/golden/batch_assembly.npz."""
+    import types
+    H.import_reference()
+    from data_preprocessors.DataPreprocessor10 import DataPreprocessor
+    from oracle import batch as OB
+    t = OB.synthetic_tables()
+    indices, m_nerf, m_sd = OB.synthetic_indices(t['pixel'].shape[0], 300, 212, seed=3)
+    this = types.SimpleNamespace(device='cpu', preprocessed_data_dict={
+        'frame_nums': np.arange(3), 'nerf_data': {'pixel_id': t['pixel'], 'target_rgb': t['rgb']},
+        'sparse_depth_data': {'depths': t['depth'], 'reprojection_errors': t['error'], 'points_3d': t['points']}})
+    idx = {'indices': indices, 'indices_mask_nerf': m_nerf, 'indices_mask_sparse_depth': m_sd}
+    ref = DataPreprocessor.load_nerf_cached_batch(this, 7, idx)
+    ref.update(DataPreprocessor.load_sparse_depth_cached_batch(this, idx, ref))
+    mine = OB.assemble_batch(indices, m_nerf, m_sd, t['pixel'], t['rgb'], t['depth'], t['error'], t['points'])
+    fixture = {'indices': indices, 'mask_nerf': m_nerf, 'mask_sd': m_sd}
+    for k in ('pixel_id', 'target_rgb', 'sparse_depth_values', 'sparse_depth_errors', 'sparse_depth_points3d'):
+        _check(f'batch/{k}', ref[k], mine[k])
+        fixture[k] = ref[k]
+    np.savez_compressed(OUT / 'batch_assembly.npz', **_np(fixture))
+    print('batch_assembly: oracle == reference')
+
+
 def main():
     if not H.available():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
@@ -400,6 +424,7 @@ def main():
     golden_patch_loss()
     golden_nerf_training_curve()
     golden_tensorf_training_curve()
+    golden_batch_assembly()
 
 
 if __name__ == '__main__':

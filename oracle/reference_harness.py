@@ -31,6 +31,16 @@ def _install_stubs():
                 sys.modules[name] = types.ModuleType(name)
     if not hasattr(sys.modules['matplotlib'], 'pyplot'):
         sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    # the data preprocessors import skimage for image I/O only (src/data_preprocessors/DataPreprocessor10.py:10-11)
+    for name in ('skimage', 'skimage.io', 'skimage.transform'):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    for sub in ('io', 'transform'):
+        if not hasattr(sys.modules['skimage'], sub):
+            setattr(sys.modules['skimage'], sub, sys.modules[f'skimage.{sub}'])
 
 
 def import_reference():

@@ -10,6 +10,7 @@ from pathlib import Path
 
 SHIM_DIR = Path(__file__).resolve().parent / 'models_shims'
 LOSS_SHIM_DIR = Path(__file__).resolve().parent / 'loss_shims'
+PREPROC_SHIM_DIR = Path(__file__).resolve().parent / 'preproc_shims'
 
 
 def install():
@@ -22,6 +23,12 @@ def install():
         import loss_functions
         if str(LOSS_SHIM_DIR) not in list(loss_functions.__path__):
             loss_functions.__path__.append(str(LOSS_SHIM_DIR))
+    except ImportError:
+        pass
+    try:                                   # `DataPreprocessor91` (fused batch assembly), src/data_preprocessors/DataPreprocessorFactory01.py:15-22
+        import data_preprocessors
+        if str(PREPROC_SHIM_DIR) not in list(data_preprocessors.__path__):
+            data_preprocessors.__path__.append(str(PREPROC_SHIM_DIR))
     except ImportError:
         pass
     return SHIM_DIR
