@@ -199,7 +199,7 @@ class SimpleNeRF(torch.nn.Module):
         z_coarse = weights_coarse = None
         if self.coarse_model_needed:
             S = mc['coarse_model']['num_samples']
-            ladder = _coarse_ladder(S, near, far, mc['lindisp']).to(dev)
+            ladder = coarse_ladder_on(dev, S, near, far, mc['lindisp'])
             if perturb and self.rng_mode == 'reference':
                 z_coarse = ops.stratified_z(ladder, R, jitter=torch.rand([R, S]).to(dev))       # SimpleNeRF17.py:355
             elif perturb:
@@ -220,7 +220,7 @@ class SimpleNeRF(torch.nn.Module):
             elif perturb:
                 z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, philox_seed=int(torch.randint(0, 2 ** 31, (1,)).item()))
             else:
-                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=torch.linspace(0., 1., steps=N).to(dev))
+                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=_on_device('linspace', int(N), dev, lambda: torch.linspace(0., 1., steps=N)))
             out['z_vals_fine'] = z_fine
             run(self.fine_model, z_fine, 'fine')
             if aug_active:
@@ -240,6 +240,25 @@ def _coarse_ladder(num_samples, near, far, lindisp):
     if not lindisp:
         return near * (1. - t) + far * t
     return 1. / (1. / near * (1. - t) + 1. / far * t)
+
+
+_DEVICE_CONSTANTS = {}
+
+
+def _on_device(kind, key, device, make):
+    """Small per-call constants (depth ladders, the deterministic u of sample_pdf) are built once on the host with the
+    reference's CPU ops and cached per device: a pageable host->device copy in every forward() synchronises the stream and
+    drains the launch queue."""
+    k = (kind, key, str(device))
+    t = _DEVICE_CONSTANTS.get(k)
+    if t is None:
+        t = _DEVICE_CONSTANTS[k] = make().to(device)
+    return t
+
+
+def coarse_ladder_on(device, num_samples, near, far, lindisp):
+    return _on_device('ladder', (int(num_samples), float(near), float(far), bool(lindisp)), device,
+                      lambda: _coarse_ladder(num_samples, near, far, lindisp))
 
 
 class MLP(torch.nn.Module):

@@ -22,7 +22,7 @@ from .. import _lib as L
 from .. import ops
 from .. import tensorf_ops as T
 from ..nerf_program import PackedRowsMLP
-from .SimpleNeRF91 import ExtrinsicsLearner, IntrinsicsLearner, _coarse_ladder
+from .SimpleNeRF91 import ExtrinsicsLearner, IntrinsicsLearner, coarse_ladder_on
 
 
 class SimpleTensoRF(torch.nn.Module):
@@ -174,7 +174,7 @@ class SimpleTensoRF(torch.nn.Module):
         out = {'rays_o': rays_o, 'rays_d': rays_d, 'rays_o_ndc': o_ndc, 'rays_d_ndc': d_ndc, 'view_dirs': view_dirs}
         main = self.coarse_model
         S = main.host_geometry()['num_samples']
-        ladder = _coarse_ladder(S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp']).to(dev)
+        ladder = coarse_ladder_on(dev, S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp'])
         perturb = self.training and mc['perturb']
         if perturb and self.rng_mode == 'reference':
             z = ops.stratified_z(ladder, R, jitter=torch.rand([R, S]).to(dev))                     # SimpleTensoRF09.py:379
