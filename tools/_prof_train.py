@@ -1,9 +1,9 @@
 import sys, torch
 sys.path.insert(0, '.')
-sys.argv = ['train_step.py', '3']
+sys.argv = ["tensorf_train_step.py"]
 import runpy
 from torch.profiler import profile, ProfilerActivity
-ns = runpy.run_path('tools/train_step.py')
+ns = runpy.run_path('tools/tensorf_train_step.py')
 step = ns['step']
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
