@@ -70,19 +70,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {   
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Forms for a CONVERGED warp (uniform control flow keeps descriptors in uniform registers and avoids the per-instruction
+// D[tmem] (+)= A * B^T, bf16 x bf16 -> fp32.  Forms for a CONVERGED warp (uniform control flow keeps descriptors in uniform registers and avoids the per-instruction
 // election loops the compiler wraps around tcgen05 ops inside a divergent `if (lane == 0)`): every lane executes the
 // statement, `issue` (from elect_one) is non-zero in exactly one lane.
 __device__ __forceinline__ uint32_t elect_one() {
@@ -283,15 +271,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit_addr_if(uint32_t issue, uint32_t bar_smem_addr) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}" ::"r"(bar_smem_addr), "r"(issue)
-      : "memory");
-}
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_smem_addr, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -313,12 +292,6 @@ __device__ __forceinline__ void umma_commit_if(uint32_t issue, uint64_t* bar) {
       "}" ::"r"(smem_u32(bar)), "r"(issue)
       : "memory");
 }
-// arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
 // 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane base + i), columns [c, c+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -366,16 +339,10 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row atoms of 1024 B (SBO), the
 // 16-byte unit index inside a row XOR-ed with (row & 7).  Tile base must be 1024-byte aligned; a K
-// step of 16 elements advances the start address by 32 bytes inside the atom.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
-  d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset  [32,46)
-  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                            // layout: SWIZZLE_128B
-  return d;
-}
+// step of 16 elements advances the start address by 32 bytes inside the atom.  The 64-bit shared-memory descriptor is
+// (start address >> 4) | SBO (1024 >> 4) << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61; the kernels pass its low word
+// and attach the constant high word inside the issue statements above.
+//
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
