@@ -199,14 +199,16 @@ int srf_mlp_rows_fwd(const void* program, const void* weights, const float* side
  * srf_nerf_mlp_dgrad (same 128 x 64 bf16 swizzled format, [tile][slots][16 KB]).  Each work item (HOST array)
  * multiplies dz images [dz_slot, dz_slot + dz_images) (64 output channels each; 2 or 4 images) with act images
  * [x_slot, x_slot + x_images) and ADDS rows [0, out_rows) x image columns [in_col0, in_col0 + in_cols) into
- * grads[dw_offset + row * w_stride + w_col0 + (col - in_col0)] (+ column sums into grads[db_offset + row] if bias). */
+ * grads[dw_offset + row * w_stride + w_col0 + (col - in_col0)] (+ column sums into grads[db_offset + row] if bias).
+ * `count` (device, nullable; also in srf_nerf_mlp_dgrad): the number of valid rows when the buffers are sized for a worst case
+ * (TensoRF surface samples: the count stays on the device, no read-back synchronisation in the training step). */
 typedef struct {
   int32_t dz_slot, dz_images, x_slot, x_images;
   int32_t out_rows, in_col0, in_cols, w_col0, w_stride, bias;
   int64_t dw_offset, db_offset;
 } srf_wgrad_item;
 int srf_nerf_mlp_wgrad(const void* items, int num_items, const void* acts, int act_slots, const void* dz, int dz_slots,
-                       int64_t num_tiles, float* grads, void* stream);
+                       int64_t num_tiles, const int* count, float* grads, void* stream);
 int srf_wgrad_item_bytes(void);
 
 /* Data-gradient chain of the fused MLP (what autograd derives for src/models/SimpleNeRF17.py:726-785): from
@@ -229,7 +231,7 @@ typedef struct {
 } srf_dgrad_program;
 int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const void* acts, int act_slots,
                        const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
-                       void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream);
+                       const int* count, void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream);
 int srf_dgrad_program_bytes(void);
 
 /* ---- "next" row f1: masks of the patch-reprojection depth losses

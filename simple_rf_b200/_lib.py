@@ -41,9 +41,9 @@ _SIGNATURES = {
     'srf_scatter_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     'srf_gather_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     'srf_mlp_rows_fwd': (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, _P, _P, c_int, c_int, c_int, _P]),
-    'srf_nerf_mlp_wgrad': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int64, _P, _P]),
+    'srf_nerf_mlp_wgrad': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int64, _P, _P, _P]),
     'srf_wgrad_item_bytes': (c_int, []),
-    'srf_nerf_mlp_dgrad': (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int, _P, c_int, _P]),
+    'srf_nerf_mlp_dgrad': (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_int, _P, c_int, _P]),
     'srf_dgrad_program_bytes': (c_int, []),
     'srf_assemble_batch': (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_adam_step': (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),

@@ -55,6 +55,7 @@ struct DgradArgs {
   float* g_rows;              // [M, g_row_pitch] fp32 input gradient of the chain's last layer, or nullptr
   int g_row_pitch;
   long long total;
+  const int* count;           // device-side row count (<= total), or nullptr: the chain stops there (rows beyond carry no gradient)
 };
 
 constexpr int DG_GROUPS = 2;
@@ -113,7 +114,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  const int num_tiles = (int)((args.total + 127) / 128);
+  long long total_rows = args.total;
+  if (args.count != nullptr) { const long long c = *args.count; total_rows = c < total_rows ? c : total_rows; }
+  const int num_tiles = (int)((total_rows + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int NL = prog.num_layers;
   const size_t act_stride = (size_t)act_tile_images(args.act_slots) * DG_KBLOCK;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long m = tile * 128 + row;
-      const bool valid = m < args.total;
+      const bool valid = m < total_rows;
       float d_o[4] = {0.f, 0.f, 0.f, 0.f};            // head_kind 1: [r, g, b, -]; head_kind 2: [sigma, r, g, b]
       float dsig = 0.f;
       if (valid) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
                        ? __ldg(reinterpret_cast<const uint32_t*>(mrec + act_mask_offset(args.act_slots, L.mask_slot + kb) + grp * 512 + row * 4))
                        : 0xFFFFFFFFu;
         const long long m_row = tile * 128 + row;
-        float* grow = (L.rows_cols > 0 && args.g_rows != nullptr && m_row < args.total) ? args.g_rows + (size_t)m_row * args.g_row_pitch : nullptr;
+        float* grow = (L.rows_cols > 0 && args.g_rows != nullptr && m_row < total_rows) ? args.g_rows + (size_t)m_row * args.g_row_pitch : nullptr;
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
         d_phase ^= 1u << buf;
         ptx::tc_fence_after();
@@ -356,7 +359,7 @@ using namespace srf;
 
 SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* side, const void* acts, int act_slots,
                                const float* sigma, const float* rgb, const float* g_sigma, const float* g_rgb, int64_t num_rows,
-                               void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream) {
+                               const int* count, void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream) {
   if (num_rows == 0) return 0;
   SRF_REQUIRE(program && weights_t && side && acts && rgb && dz && (sigma || !g_sigma), "srf_nerf_mlp_dgrad", "null pointer");
   DgradProgram prog = *reinterpret_cast<const DgradProgram*>(program);
@@ -382,7 +385,7 @@ SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const
   DgradArgs a{};
   a.weights_t = reinterpret_cast<const uint8_t*>(weights_t); a.side = side; a.acts = reinterpret_cast<const uint8_t*>(acts);
   a.act_slots = act_slots; a.sigma = sigma; a.rgb = rgb;
-  a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dz = reinterpret_cast<uint8_t*>(dz); a.dz_slots = dz_slots; a.total = num_rows;
+  a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dz = reinterpret_cast<uint8_t*>(dz); a.dz_slots = dz_slots; a.total = num_rows; a.count = count;
   a.g_rows = g_rows; a.g_row_pitch = g_row_pitch;
   const size_t smem = sizeof(DgradSmem);
   static bool configured = false;

@@ -38,6 +38,7 @@ struct WgradParams {
   float* grads;
   int act_slots, dz_slots;
   int num_tiles, splits;
+  const int* count;           // device-side row count, or nullptr: only tiles below ceil(count / 128) are accumulated
   int num_items;
   WgradItem items[WG_MAX_ITEMS];
 };
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_mlp_wgrad_kernel(const __g
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   const WgradItem& it = p.items[blockIdx.x / p.splits];
   const int split = blockIdx.x % p.splits;
-  const int t0 = (int)((long long)p.num_tiles * split / p.splits), t1 = (int)((long long)p.num_tiles * (split + 1) / p.splits);
+  int num_tiles = p.num_tiles;
+  if (p.count != nullptr) { const int c = (*p.count + 127) / 128; num_tiles = c < num_tiles ? c : num_tiles; }
+  const int t0 = (int)((long long)num_tiles * split / p.splits), t1 = (int)((long long)num_tiles * (split + 1) / p.splits);
+  if (t1 == t0) return;                              // nothing to accumulate for this CTA (uniform exit, before any barrier)
   const int halves = it.dz_images >> 1;            // accumulators (M = 128 each)
   const int N = it.x_images * 64;
   const int bias_arrivals = it.bias ? 4 : 0;
@@ -190,13 +194,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_mlp_wgrad_kernel(const __g
 using namespace srf;
 
 SRF_API int srf_nerf_mlp_wgrad(const void* items, int num_items, const void* acts, int act_slots, const void* dz, int dz_slots,
-                               int64_t num_tiles, float* grads, void* stream) {
+                               int64_t num_tiles, const int* count, float* grads, void* stream) {
   if (num_tiles == 0 || num_items == 0) return 0;
   SRF_REQUIRE(items && acts && dz && grads, "srf_nerf_mlp_wgrad", "null pointer");
   SRF_REQUIRE(num_items <= WG_MAX_ITEMS, "srf_nerf_mlp_wgrad", "too many work items");
   WgradParams p{};
   p.acts = reinterpret_cast<const uint8_t*>(acts); p.dz = reinterpret_cast<const uint8_t*>(dz); p.grads = grads;
-  p.act_slots = act_slots; p.dz_slots = dz_slots; p.num_tiles = (int)num_tiles; p.num_items = num_items;
+  p.act_slots = act_slots; p.dz_slots = dz_slots; p.num_tiles = (int)num_tiles; p.num_items = num_items; p.count = count;
   const WgradItem* src = reinterpret_cast<const WgradItem*>(items);
   for (int i = 0; i < num_items; ++i) {
     const WgradItem& it = src[i];

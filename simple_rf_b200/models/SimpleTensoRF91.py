@@ -262,32 +262,25 @@ class _VmColor(torch.autograd.Function):
     VM gather (srf_vm_color_features_fwd) -> basis o colour MLP on the tensor cores (srf_mlp_rows_fwd, activations saved
     as tile images) | data-gradient chain + weight gradients on the tensor cores (srf_nerf_mlp_dgrad / _wgrad) -> scatter
     of d loss / d products into the planes / lines (srf_vm_color_features_bwd).  What autograd derives for
-    SimpleTensoRF09.py:1241-1272 + :1411-1421.  The surface count is read back once (4 bytes) so that every buffer of
-    the training step is sized exactly."""
+    SimpleTensoRF09.py:1241-1272 + :1411-1421."""
 
     @staticmethod
     def forward(ctx, predictor, geom, comp, view_dirs, n_planes, basis, *params):
         planes, lines, mlp = params[:n_planes], params[n_planes:2 * n_planes], params[2 * n_planes:]
-        n = int(comp.count.item())
-        ctx.n = n
-        if n == 0:
-            return torch.zeros((1, 3), dtype=torch.float32, device=geom.z.device)
-        tight = T.Compacted(comp.mask, comp.idx, comp.count, n)
-        rows, tables = T.vm_color_rows(geom, tight, view_dirs, list(planes), list(lines))
+        # the surface count stays on the device (no read-back: a synchronisation here drains the launch queue twice per
+        # iteration); every buffer is sized for the worst case comp.total and every kernel stops at the device-side count
+        rows, tables = T.vm_color_rows(geom, comp, view_dirs, list(planes), list(lines))
         packed = predictor.packed(basis)
-        rgb, acts = packed.forward(rows, None, n, save=True)
-        ctx.packed, ctx.flat, ctx.geom, ctx.comp, ctx.tables = packed, packed.flat, geom, tight, tables
+        rgb, acts = packed.forward(rows, comp.count, rows.shape[0], save=True)
+        ctx.packed, ctx.flat, ctx.geom, ctx.comp, ctx.tables = packed, packed.flat, geom, comp, tables
         ctx.save_for_backward(rgb, acts, basis, mlp[0])
         return rgb
 
     @staticmethod
     def backward(ctx, g_rgb):
-        n_in = len(ctx.needs_input_grad)
-        if ctx.n == 0:
-            return (None,) * n_in
         rgb, acts, basis, w0 = ctx.saved_tensors
         packed = ctx.packed
-        g_flat, g_rows = packed.backward(acts, rgb, g_rgb[:ctx.n], ctx.n, flat=ctx.flat)
+        g_flat, g_rows = packed.backward(acts, rgb, g_rgb, rgb.shape[0], flat=ctx.flat, count=ctx.comp.count)
         gp, gl = T.vm_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
         g_w0, g_basis = packed.split_first_layer_grad(g_flat, w0.detach().float(), basis.detach().float())
         g_mlp = [g_w0] + [packed.grad_of(g_flat, nm) for nm in packed.names[1:]]

@@ -351,9 +351,9 @@ class PackedRowsMLP:
                L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
         return (rgb, acts) if save else rgb
 
-    def backward(self, acts, rgb, g_rgb, num_rows, flat=None):
+    def backward(self, acts, rgb, g_rgb, num_rows, flat=None, count=None):
         """Hand-written backward on the tensor cores (nerf_mlp_dgrad.cu / nerf_mlp_wgrad.cu) of a forward(save=True) over
-        exactly num_rows rows: returns (flat gradient in the layout [W0' | b0 | W1 | b1 | W2 | b2], g_rows fp32
+        num_rows rows (count: device int32[1] with the number of valid rows when num_rows is a worst-case capacity): returns (flat gradient in the layout [W0' | b0 | W1 | b1 | W2 | b2], g_rows fp32
         [num_rows, pitch4] whose first num_products columns are d loss / d product rows)."""
         plan = self.backward_plan
         dev = acts.device
@@ -369,10 +369,10 @@ class PackedRowsMLP:
         pitch = -(-self.num_products // 4) * 4
         g_rows = torch.empty((max(num_rows, 1), pitch), dtype=torch.float32, device=dev)
         L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), act_data_slots(acts.shape[1]), None, L.ptr(rgb),
-               None, L.ptr(L.f32c(g_rgb)), num_rows, L.ptr(dz), plan.dz_slots, L.ptr(g_rows), pitch, L.stream_handle(),
+               None, L.ptr(L.f32c(g_rgb)), num_rows, L.ptr(count), L.ptr(dz), plan.dz_slots, L.ptr(g_rows), pitch, L.stream_handle(),
                work=2.0 * (2 * self.units * self.units) * num_rows)
         grads = torch.zeros(self.flat_size, dtype=torch.float32, device=dev)
-        run_wgrad(plan.items, acts, dz, grads)
+        run_wgrad(plan.items, acts, dz, grads, count=count)
         return grads, g_rows
 
     def split_first_layer_grad(self, g_flat, w0, basis):
@@ -410,13 +410,13 @@ class WgradItem(ctypes.Structure):
                 ('w_stride', ctypes.c_int32), ('bias', ctypes.c_int32), ('dw_offset', ctypes.c_int64), ('db_offset', ctypes.c_int64)]
 
 
-def run_wgrad(items, acts, dz, grads):
+def run_wgrad(items, acts, dz, grads, count=None):
     """items: list of WgradItem; acts / dz uint8 [tiles, slots, 16384]; grads flat fp32 (accumulated into)."""
     arr = (WgradItem * len(items))(*items)
     tiles = acts.shape[0]
     flops = sum(2.0 * 64 * it.dz_images * 64 * it.x_images * 128 * tiles for it in items)
     L.call('srf_nerf_mlp_wgrad', ctypes.addressof(arr), len(items), L.ptr(acts), act_data_slots(acts.shape[1]), L.ptr(dz), dz.shape[1], tiles,
-           L.ptr(grads), L.stream_handle(), work=flops)
+           L.ptr(count), L.ptr(grads), L.stream_handle(), work=flops)
 
 
 class DgradLayer(ctypes.Structure):
@@ -546,7 +546,7 @@ def mlp_backward(packed, params_flat, acts, sigma, rgb, g_sigma, g_rgb):
     gs = None if g_sigma is None else L.f32c(g_sigma).reshape(-1)
     gc = None if g_rgb is None else L.f32c(g_rgb).reshape(-1, 3)
     L.call('srf_nerf_mlp_dgrad', ctypes.addressof(plan.program), L.ptr(wt), L.ptr(side), L.ptr(acts), act_data_slots(acts.shape[1]), L.ptr(sigma), L.ptr(rgb),
-           L.ptr(gs), L.ptr(gc), rows, L.ptr(dz), plan.dz_slots, None, 0, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
+           L.ptr(gs), L.ptr(gc), rows, None, L.ptr(dz), plan.dz_slots, None, 0, L.stream_handle(), work=2.0 * packed.macs_per_sample * rows)
     grads = torch.zeros(packed.flat_size, dtype=torch.float32, device=dev)
     run_wgrad(plan.items, acts, dz, grads)
     return grads, dz
