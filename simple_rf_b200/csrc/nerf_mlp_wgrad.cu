@@ -7,7 +7,8 @@
 // SWIZZLE_128B UMMA operand (rows = K, 64 contiguous channels = one MN atom), so the images are bulk-copied from HBM
 // into shared memory and fed to tcgen05.mma unchanged — no transposes.
 //
-// One CTA per (work item, split): the item names the dZ images (M = 128 or 256 output channels) and the X images
+// One CTA per (work item, split) - the SMs are dealt out to the items in proportion to the bytes they stream per tile, so
+// the launch is one balanced wave: the item names the dZ images (M = 128 or 256 output channels) and the X images
 // (N <= 256 input channels); the split is a contiguous range of sample tiles.  fp32 accumulators live in TMEM
 // (2 x 256 columns) across the whole range and are added to the global gradient with red.global at the end.
 // HBM-bound by design: 128 FLOP per byte streamed.
@@ -37,7 +38,9 @@ struct WgradParams {
   const uint8_t* acts; const uint8_t* dz;
   float* grads;
   int act_slots, dz_slots;
-  int num_tiles, splits;
+  int num_tiles;
+  int cta_first[WG_MAX_ITEMS + 1];   // CTAs [cta_first[i], cta_first[i + 1]) share item i: the SMs are dealt out in proportion to the
+                                     // bytes an item streams per tile (dz + x images), one wave, no tail
   const int* count;           // device-side row count, or nullptr: only tiles below ceil(count / 128) are accumulated
   int num_items;
   WgradItem items[WG_MAX_ITEMS];
@@ -71,11 +74,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_mlp_wgrad_kernel(const __g
   WgradSmem& sm = *reinterpret_cast<WgradSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const WgradItem& it = p.items[blockIdx.x / p.splits];
-  const int split = blockIdx.x % p.splits;
+  int item = 0;
+  while (item + 1 < p.num_items && (int)blockIdx.x >= p.cta_first[item + 1]) ++item;
+  const WgradItem& it = p.items[item];
+  const int split = (int)blockIdx.x - p.cta_first[item], splits = p.cta_first[item + 1] - p.cta_first[item];
   int num_tiles = p.num_tiles;
   if (p.count != nullptr) { const int c = (*p.count + 127) / 128; num_tiles = c < num_tiles ? c : num_tiles; }
-  const int t0 = (int)((long long)num_tiles * split / p.splits), t1 = (int)((long long)num_tiles * (split + 1) / p.splits);
+  const int t0 = (int)((long long)num_tiles * split / splits), t1 = (int)((long long)num_tiles * (split + 1) / splits);
   if (t1 == t0) return;                              // nothing to accumulate for this CTA (uniform exit, before any barrier)
   const int halves = it.dz_images >> 1;            // accumulators (M = 128 each)
   const int N = it.x_images * 64;
@@ -211,10 +216,33 @@ SRF_API int srf_nerf_mlp_wgrad(const void* items, int num_items, const void* act
                     it.in_col0 + it.in_cols <= 64 * it.x_images, "srf_nerf_mlp_wgrad", "bad row / column mapping");
     p.items[i] = it;
   }
-  int splits = (sm_count() + num_items - 1) / num_items;           // about one CTA per SM
-  if (splits < 1) splits = 1;
-  if (splits > num_tiles) splits = (int)num_tiles;
-  p.splits = splits;
+  // deal the SMs out in proportion to the bytes per tile of every item (largest-remainder rounding, at least one CTA each)
+  int ctas = sm_count();
+  if ((long long)ctas > (long long)num_items * num_tiles) ctas = (int)((long long)num_items * num_tiles);
+  if (ctas < num_items) ctas = num_items;
+  int weight[WG_MAX_ITEMS], share[WG_MAX_ITEMS], total_w = 0, used = 0;
+  for (int i = 0; i < num_items; ++i) { weight[i] = p.items[i].dz_images + p.items[i].x_images; total_w += weight[i]; }
+  for (int i = 0; i < num_items; ++i) {
+    share[i] = (int)((long long)ctas * weight[i] / total_w);
+    if (share[i] < 1) share[i] = 1;
+    if (share[i] > num_tiles) share[i] = (int)num_tiles;
+    used += share[i];
+  }
+  for (int guard = 0; used != ctas && guard < 4 * ctas; ++guard) {      // hand the remainder to / take the excess from the
+    int best = -1;                                                      // items with the most / least work per CTA
+    for (int i = 0; i < num_items; ++i) {
+      if (used < ctas ? share[i] >= num_tiles : share[i] <= 1) continue;
+      if (best < 0 || (used < ctas ? (long long)weight[i] * share[best] > (long long)weight[best] * share[i]
+                                   : (long long)weight[i] * share[best] < (long long)weight[best] * share[i]))
+        best = i;
+    }
+    if (best < 0) break;
+    share[best] += used < ctas ? 1 : -1;
+    used += used < ctas ? 1 : -1;
+  }
+  p.cta_first[0] = 0;
+  for (int i = 0; i < num_items; ++i) p.cta_first[i + 1] = p.cta_first[i] + share[i];
+  const int grid = p.cta_first[num_items];
   const size_t smem = sizeof(WgradSmem);
   static bool configured = false;
   if (!configured) {
@@ -222,7 +250,7 @@ SRF_API int srf_nerf_mlp_wgrad(const void* items, int num_items, const void* act
     if (e != cudaSuccess) return fail("srf_nerf_mlp_wgrad", cudaGetErrorString(e));
     configured = true;
   }
-  nerf_mlp_wgrad_kernel<<<num_items * splits, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
+  nerf_mlp_wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("srf_nerf_mlp_wgrad");
 }
 
