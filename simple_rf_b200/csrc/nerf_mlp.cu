@@ -17,6 +17,7 @@
 //   epilogue warps: tcgen05.ld -> +bias, ReLU -> bf16 pairs -> tcgen05.st over the accumulator columns just drained = the
 //                   next layer's A operand, signalled per 64-column K-block so the next layer's MMAs start while the rest
 //                   of the epilogue is still running; the 1/3/4-wide heads are thread-local dot products.
+#include <type_traits>
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -90,10 +91,16 @@ __device__ long long g_mlp_trace[4096];
 constexpr int GROUPS = 2;                         // column groups per 64-wide block = epilogue warps per TMEM lane quarter
 constexpr int COLS = 64 / GROUPS;                 // columns of a 64-wide block owned by one epilogue warp
 constexpr int EPI_THREADS = 128 * GROUPS;
-constexpr int EPI_WARP0 = 2;                      // warp 0 weight producer, warp 1 first MMA issuer
+// Warp roles: 0 weight producer (one lane), 1 first MMA issuer, 2..9 epilogue, 10..13 encoding, 14 second MMA issuer.
+// Every SM sub-partition (warp id % 4) hosts two epilogue warps and one encoding warp; TMEM lane quarters follow
+// warp id % 4, which any 8 consecutive warps cover twice.  Two other numberings were measured on hardware and lost 10 %
+// (encoding warps below the epilogue warps; both issuers first): keep this one.
+constexpr int PRODUCER_WARP = 0;
+constexpr int ISSUER1_WARP = 1;
+constexpr int EPI_WARP0 = 2;                      // 4 * GROUPS epilogue warps
 constexpr int ENC_WARP0 = EPI_WARP0 + 4 * GROUPS; // 4 encoding warps (one row per thread) run one tile ahead
-constexpr int ISSUER2_WARP = ENC_WARP0 + 4;       // second MMA issuer
-constexpr int MLP_THREADS = 32 * (ENC_WARP0 + 5);
+constexpr int ISSUER2_WARP = ENC_WARP0 + 4;
+constexpr int MLP_THREADS = 32 * (ISSUER2_WARP + 1);
 constexpr int KBLOCK_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int IMAGE_BYTES = 128 * 128;            // packed weight image: 128 output units x one 64-wide K block
 #if SRF_MLP_SPLIT
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
 
   for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
     ptx::mbar_init(&sm.a_ready[0], 4);
     ptx::mbar_init(&sm.a_ready[5], 4);
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     ptx::mbar_init(&sm.v_free, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(&sm.tmem_base, 512);
+  if (warp == ISSUER1_WARP) ptx::tmem_alloc(&sm.tmem_base, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : NUM_STAGES;
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ------------------------------------------------------------ weight producer: one ring stage per schedule step
     if (lane == 0) {
       const int num_steps = sched.num_steps;
@@ -222,13 +229,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         }
       }
     }
-  } else if (warp == 1 || warp == ISSUER2_WARP) {
+  } else if (warp == ISSUER1_WARP || warp == ISSUER2_WARP) {
     // ------------------------------------------------------------ MMA issuers: two warps take alternate steps; each prepares
     // its next step (schedule entry, barrier acquisition, descriptors) while the other one issues, and a named-barrier token
     // keeps the MMAs in schedule order.  The whole warp runs the loop (uniform control flow: descriptors stay in uniform
     // registers), one elected lane issues tcgen05.mma / tcgen05.commit.
     const int num_steps = sched.num_steps;
-    const uint32_t me = warp == 1 ? 0u : 1u;
+    const uint32_t me = warp == ISSUER1_WARP ? 0u : 1u;
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
     const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
     const uint32_t a_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       s += 2;
       while (s >= num_steps) { s -= num_steps; ++t; }
     }
-  } else if (warp >= ENC_WARP0) {
+  } else if (warp >= ENC_WARP0 && warp < ENC_WARP0 + 4) {
     // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
     const int row = (warp - ENC_WARP0) * 32 + lane;
     for (int t = 0; t < my_tiles; ++t) {
@@ -421,19 +428,33 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < COLS; ++j) x[j] = fmaxf(x[j], 0.f);
           }
+          // head partial dot products on the fp32 activations (FFMA2): every row keeps four independent accumulator pairs and the
+          // rows are interleaved, so the dependent chain is 4 packed FMAs deep instead of 16 per row (this epilogue sits on the
+          // tile's critical path); fully unrolled per head width so hacc[] stays in registers
+          auto head_dot = [&](auto rows_tag) {
+            constexpr int ROWS = decltype(rows_tag)::value;
+            float acc[ROWS][8];
 #pragma unroll
-          for (int hr = 0; hr < 4; ++hr) {                         // head partial dot products on the fp32 activations (FFMA2);
-            if (hr >= head_rows) break;                            // unrolled: hacc[] must stay in registers
-            const float4* w4 = reinterpret_cast<const float4*>(hw + hr * n + col0);
-            float a0 = hacc[hr], a1 = 0.f;
+            for (int hr = 0; hr < ROWS; ++hr) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[hr][k] = 0.f;
+            }
 #pragma unroll
             for (int q = 0; q < COLS / 4; ++q) {
-              const float4 w = w4[q];
-              ptx::ffma2(a0, a1, x[4 * q + 0], x[4 * q + 1], w.x, w.y);
-              ptx::ffma2(a0, a1, x[4 * q + 2], x[4 * q + 3], w.z, w.w);
+#pragma unroll
+              for (int hr = 0; hr < ROWS; ++hr) {
+                const float4 w = reinterpret_cast<const float4*>(hw + hr * n + col0)[q];
+                ptx::ffma2(acc[hr][(q & 1) * 4 + 0], acc[hr][(q & 1) * 4 + 1], x[4 * q + 0], x[4 * q + 1], w.x, w.y);
+                ptx::ffma2(acc[hr][(q & 1) * 4 + 2], acc[hr][(q & 1) * 4 + 3], x[4 * q + 2], x[4 * q + 3], w.z, w.w);
+              }
             }
-            hacc[hr] = a0 + a1;
-          }
+#pragma unroll
+            for (int hr = 0; hr < ROWS; ++hr)
+              hacc[hr] += ((acc[hr][0] + acc[hr][1]) + (acc[hr][2] + acc[hr][3])) + ((acc[hr][4] + acc[hr][5]) + (acc[hr][6] + acc[hr][7]));
+          };
+          if (head_rows == 1) head_dot(std::integral_constant<int, 1>{});
+          else if (head_rows == 3) head_dot(std::integral_constant<int, 3>{});
+          else head_dot(std::integral_constant<int, 4>{});
 #pragma unroll
           for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(x[2 * j], x[2 * j + 1]);
         };
@@ -530,7 +551,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (threadIdx.x == EPI_WARP0 * 32 && args.save_acts != nullptr) ptx::bulk_wait_all();   // staged images have left shared memory
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == ISSUER1_WARP) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, 512);
   }
