@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     const int grp = (warp - EPI_WARP0) >> 2;   // column group of every 64-wide block this warp owns
     const int row = quarter * 32 + lane;
     uint32_t layer_count = 0;
+    const uint32_t side_addr = ptx::smem_u32(sm.side), a_ready_addr = ptx::smem_u32(&sm.a_ready[0]), d_full_addr = ptx::smem_u32(&sm.d_full[0]);
     uint32_t d_phase = 0;                // bit b: parity to wait for on d_full[b]
     uint32_t save_count = 0;             // staged activation images so far (selects the staging buffer)
     for (int t = 0; t < my_tiles; ++t) {
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         const MlpLayer& L = prog.layers[l];
         const uint32_t buf = layer_count & 1;
         const int n = L.n, relu = L.relu, write_h = L.write_h, head = L.head;
-        const float* bias = sm.side + L.bias_offset;
+        const uint32_t bias_addr = side_addr + (uint32_t)(L.bias_offset + grp * COLS) * 4u;   // this warp's 32 columns of block 0
         const int head_rows = head == 1 ? 1 : (head == 2 ? 4 : (head == 3 ? 3 : 0));
         const float* hw = sm.side + L.head_offset;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -396,11 +397,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         uint32_t mask_bits = 0;
         auto compute = [&](uint32_t (&v)[COLS], uint32_t (&pk)[COLS / 2], int kb) {
           const int col0 = kb * 64 + grp * COLS;
-          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+          const uint32_t b4 = bias_addr + (uint32_t)kb * 256u;
           float x[COLS];
 #pragma unroll
           for (int q = 0; q < COLS / 4; ++q) {                     // + bias as packed fp32 pairs (FADD2)
-            const float4 b = b4[q];
+            const float4 b = ptx::lds4(b4 + q * 16);
             x[4 * q + 0] = __uint_as_float(v[4 * q + 0]); x[4 * q + 1] = __uint_as_float(v[4 * q + 1]);
             x[4 * q + 2] = __uint_as_float(v[4 * q + 2]); x[4 * q + 3] = __uint_as_float(v[4 * q + 3]);
             ptx::fadd2(x[4 * q + 0], x[4 * q + 1], b.x, b.y);
@@ -468,12 +469,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&sm.a_ready[1 + kb]);
+            if (lane == 0) ptx::mbar_arrive_addr(a_ready_addr + (uint32_t)(1 + kb) * 8u);
           }
           if (save_base != nullptr) {
             // staged through shared memory: a thread owns 64 bytes of a 128-byte image row, so direct global stores touch 32
             // lines per instruction; the swizzled staging image leaves as one 16 KB bulk copy instead
-            uint8_t* stg = sm.w[0] + (size_t)SAVE_STAGES * STAGE_BYTES + (size_t)(save_count & (SAVE_BUFS - 1)) * IMAGE_BYTES;
+            uint8_t* stg = &sm.w[0][0] + (size_t)SAVE_STAGES * STAGE_BYTES + (size_t)(save_count & (SAVE_BUFS - 1)) * IMAGE_BYTES;
 #pragma unroll
             for (int u = 0; u < COLS / 8; ++u)
               *reinterpret_cast<uint4*>(stg + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         for (int kb = 0; kb < nblocks; ++kb) {
           if (kb == 0 || (SRF_MLP_SPLIT && kb == 2)) {            // blocks 2, 3 belong to the second column half
             const uint32_t b = buf * 2 + (SRF_MLP_SPLIT ? (uint32_t)(kb >> 1) : 0u);
-            ptx::mbar_wait(&sm.d_full[b], (d_phase >> b) & 1);
+            ptx::mbar_wait_addr(d_full_addr + b * 8u, (d_phase >> b) & 1);
             d_phase ^= 1u << b;
             ptx::tc_fence_after();
             if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + (kb ? 9 : 0));
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           tmem_load<COLS>(t_row + kb * 64, va);
           ptx::tmem_ld_wait(va);
           if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 1 + 2 * kb);
-          compute(va, pk, kb);
+          compute(va, pk, kb);       // (a compile-time specialisation of this loop for plain hidden layers measured 8 % SLOWER)
           store(pk, kb);
           if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * kb);
         }
