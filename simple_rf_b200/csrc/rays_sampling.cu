@@ -47,7 +47,11 @@ __global__ void __launch_bounds__(RAYGEN_THREADS) raygen_kernel(RaygenParams p) 
   const int nf = min(p.F, MAX_VIEWS_SMEM);
   for (int i = threadIdx.x; i < nf * 27; i += RAYGEN_THREADS) {
     int v = i / 27, e = i % 27;
-    s_cam[i] = e < 9 ? p.k_inv[v * 9 + e] : (e < 25 ? p.c2w[v * 16 + (e - 9)] : p.focal[v * 2 + (e - 25)]);
+    float val = e < 9 ? p.k_inv[v * 9 + e] : (e < 25 ? p.c2w[v * 16 + (e - 9)] : p.focal[v * 2 + (e - 25)]);
+    // the NDC scale factors -1 / (w / (2 fx)), -1 / (h / (2 fy)) (CommonUtils04.py:129-134) depend on the view only: evaluated
+    // once per view here (same operations, same bits) instead of two nested IEEE divisions per ray
+    if (e >= 25) val = __fdiv_rn(-1.f, __fdiv_rn(e == 25 ? p.width : p.height, __fmul_rn(2.f, val)));
+    s_cam[i] = val;
   }
   __syncthreads();
   const long long base = (long long)blockIdx.x * RAYGEN_THREADS;
@@ -65,6 +69,8 @@ __global__ void __launch_bounds__(RAYGEN_THREADS) raygen_kernel(RaygenParams p) 
 #pragma unroll
       for (int e = 0; e < 27; ++e)
         cam[e] = e < 9 ? p.k_inv[img * 9 + e] : (e < 25 ? p.c2w[img * 16 + (e - 9)] : p.focal[img * 2 + (e - 25)]);
+      cam[25] = __fdiv_rn(-1.f, __fdiv_rn(p.width, __fmul_rn(2.f, cam[25])));
+      cam[26] = __fdiv_rn(-1.f, __fdiv_rn(p.height, __fmul_rn(2.f, cam[26])));
     }
     const float* ki = cam;
     const float* m = cam + 9;
@@ -83,14 +89,12 @@ __global__ void __launch_bounds__(RAYGEN_THREADS) raygen_kernel(RaygenParams p) 
     float vsrc[3] = {rd[0], rd[1], rd[2]};
     float on[3] = {0.f, 0.f, 0.f}, dn[3] = {0.f, 0.f, 0.f};
     if (p.ndc) {
-      const float fx = cam[25], fy = cam[26];
+      const float sx = cam[25], sy = cam[26];
       // CommonUtils04.py:124-134, same operation order, no FMA contraction
       const float t = __fdiv_rn(-__fadd_rn(p.near, ro[2]), rd[2]);
       const float ox = __fadd_rn(ro[0], __fmul_rn(t, rd[0]));
       const float oy = __fadd_rn(ro[1], __fmul_rn(t, rd[1]));
       const float oz = __fadd_rn(ro[2], __fmul_rn(t, rd[2]));
-      const float sx = __fdiv_rn(-1.f, __fdiv_rn(p.width, __fmul_rn(2.f, fx)));
-      const float sy = __fdiv_rn(-1.f, __fdiv_rn(p.height, __fmul_rn(2.f, fy)));
       on[0] = __fdiv_rn(__fmul_rn(sx, ox), oz);
       on[1] = __fdiv_rn(__fmul_rn(sy, oy), oz);
       on[2] = __fadd_rn(1.f, __fdiv_rn(p.two_near, oz));
