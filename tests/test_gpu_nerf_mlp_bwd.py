@@ -205,3 +205,32 @@ def test_mlp_backward_vs_autograd(golden_configs, variant, R, S):
     for name in packed.param_names:
         assert err_model[name] <= 5e-2, ('bf16 model', name, err_model[name])
         assert err_fp32[name] <= 0.15, ('fp32', name, err_fp32[name])
+
+
+def test_rows_mlp_backward_with_device_count_matches_exact_size():
+    """The TensoRF colour branch sizes every buffer for the worst case and passes the number of valid rows on the device
+    (srf_mlp_rows_fwd / srf_nerf_mlp_dgrad / srf_nerf_mlp_wgrad `count`): gradients must equal those of an exactly sized call,
+    also for an empty row set and for counts that end inside a tile."""
+    from simple_rf_b200.nerf_program import PackedRowsMLP
+    g = torch.Generator().manual_seed(3)
+    m = PackedRowsMLP(72, 27, 3, prefix='mlp')
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5).to(DEV)
+    params = {'mlp.0.weight': lin(128, 30), 'mlp.0.bias': lin(128, 1)[:, 0], 'mlp.2.weight': lin(128, 128), 'mlp.2.bias': lin(128, 1)[:, 0],
+              'mlp.4.weight': lin(3, 128), 'mlp.4.bias': torch.zeros(3, device=DEV)}
+    m.refresh(params, lin(27, 72))
+    capacity = 128 * 37 + 5
+    rows_all = (torch.randn(capacity, 80, generator=g) * 0.3).to(torch.bfloat16).to(DEV)
+    g_all = torch.randn(capacity, 3, generator=g).to(DEV)
+    for n in (0, 1, 128, 1000, 128 * 20 + 77, capacity):
+        count = torch.tensor([n], dtype=torch.int32, device=DEV)
+        rgb_c, acts_c = m.forward(rows_all, count, capacity, save=True)
+        grads_c, g_rows_c = m.backward(acts_c, rgb_c, g_all, capacity, count=count)
+        if n == 0:
+            assert float(grads_c.abs().max()) == 0.0
+            continue
+        rgb_e, acts_e = m.forward(rows_all[:n].contiguous(), None, n, save=True)
+        grads_e, g_rows_e = m.backward(acts_e, rgb_e, g_all[:n].contiguous(), n)
+        assert torch.equal(rgb_c[:n], rgb_e)
+        assert torch.equal(g_rows_c[:n], g_rows_e[:n])
+        # the weight gradients are sums over tiles in a different CTA split: fp32 reassociation only
+        assert (grads_c - grads_e).abs().max().item() <= 1e-5 * max(1.0, grads_e.abs().max().item()), n
