@@ -254,11 +254,25 @@ int srf_patch_reprojection_masks(const float* rays_o, const float* rays_d, const
  * per-pixel tables at flat index indices[b] (all tables [num_pixels, C], device); image rays (is_sparse_depth[b] == 0, or
  * is_sparse_depth NULL) get pixel_id + target_rgb, sparse-depth rays get pixel_id + depth / reprojection error / 3-D point;
  * fields a ray kind does not carry are -1, as the reference initialises them.  sd_* outputs (and their tables) are nullable.
- * Indices must lie in [0, num_pixels) (they are the reference's own shuffled index arrays). */
+ * Indices must lie in [0, num_pixels) (they are the reference's own shuffled index arrays); a row whose index does not is
+ * filled with -1 and *error_flag (nullable; device-accessible, e.g. mapped pinned host memory) is set to 1 — the reference's
+ * fancy indexing raises IndexError there. */
 int srf_assemble_batch(const int64_t* indices, const uint8_t* is_sparse_depth, int64_t batch, int64_t num_pixels,
                        const int* pixel_table, const float* rgb_table, const float* depth_table, const float* error_table,
                        const float* points_table, int* pixel_id, float* target_rgb, float* sd_depth, float* sd_error,
-                       float* sd_points, void* stream);
+                       float* sd_points, int* error_flag, void* stream);
+
+/* ---- "next" row f4: output tail of a rendered frame.  Replaces retrieve_inference_outputs
+ * (src/data_preprocessors/DataPreprocessor10.py:775-803) with its post_process_output / post_process_image /
+ * post_process_depth helpers (:967-995): instead of copying every tensor of the output dict to the host and converting there,
+ * one kernel writes the record the caller keeps —
+ *   [ image uint8 [num_rays,3] | depth | depth_var | depth_ndc | depth_var_ndc  (fp32 [num_rays] each) ],
+ * every section padded to 16 bytes (srf_frame_record_bytes(num_rays, 4) in total; the two NDC maps are nullable and then left
+ * unwritten) — with numpy's arithmetic: clip(rgb,0,1)*255 rounded half-to-even -> uint8, negative depths -> 0.  All pointers
+ * device, 16-byte aligned. */
+int64_t srf_frame_record_bytes(int64_t num_rays, int num_maps);
+int srf_frame_outputs(const float* rgb, const float* depth, const float* depth_var, const float* depth_ndc,
+                      const float* depth_var_ndc, int64_t num_rays, uint8_t* record, void* stream);
 
 /* ---- "next" row f4: optimiser tail.  One fused Adam step over flat fp32 arrays (device pointers, 16-byte
  * aligned), replacing torch.optim.Adam.step as created by src/optimizers/OptimizerFactory02.py:9-22 and called at

@@ -45,8 +45,10 @@ _SIGNATURES = {
     'srf_wgrad_item_bytes': (c_int, []),
     'srf_nerf_mlp_dgrad': (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_int, _P, c_int, _P]),
     'srf_dgrad_program_bytes': (c_int, []),
-    'srf_assemble_batch': (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'srf_assemble_batch': (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_adam_step': (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
+    'srf_frame_record_bytes': (c_int64, [c_int64, c_int]),
+    'srf_frame_outputs': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P]),
     'srf_composite_bwd': (c_int, [_P] * 17 + [c_int64, c_int, c_int, c_int, c_float, _P, _P, _P]),
 }
 
@@ -79,10 +81,16 @@ def declared_symbols():
     return list(_SIGNATURES.keys())
 
 
+_KEEP = []             # tensors whose raw pointers are in flight between ptr() and the end of the next call()
+
+
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL).  The tensor is kept alive until the next `call()` has returned:
+    `ptr(f32c(x))` on a non-contiguous / non-fp32 `x` creates a temporary, and a temporary freed before the launch can be
+    handed by the caching allocator to the NEXT temporary of the same size, aliasing two kernel arguments."""
     if t is None:
         return None
+    _KEEP.append(t)
     return t.data_ptr()
 
 
@@ -100,7 +108,10 @@ def call(name, *args, work=None):
     if timing:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = getattr(lib, name)(*args)
+    try:
+        rc = getattr(lib, name)(*args)
+    finally:
+        _KEEP.clear()          # the launch is queued: stream order protects the buffers from here on
     if rc != 0:
         raise SimpleRFNativeError(lib.srf_last_error().decode())
     if timing:

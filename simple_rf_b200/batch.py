@@ -7,6 +7,31 @@ import torch
 from . import _lib as L
 
 
+_ERROR_FLAGS = {}
+
+
+def _error_flag(device):
+    """One int32 in mapped pinned host memory per device: the kernel raises it when an index is out of range, the host reads
+    it at the next call without synchronising the stream."""
+    f = _ERROR_FLAGS.get(device)
+    if f is None:
+        f = _ERROR_FLAGS[device] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return f
+
+
+def check_indices_error(device, synchronize=False):
+    """Raises IndexError if a previous assemble_batch() on `device` met an index outside the tables (what the reference's
+    fancy indexing does immediately, DataPreprocessor10.py:538)."""
+    f = _ERROR_FLAGS.get(device)
+    if f is None:
+        return
+    if synchronize:
+        torch.cuda.synchronize(device)
+    if int(f[0]) != 0:
+        f[0] = 0
+        raise IndexError('assemble_batch: a batch index lies outside the cached per-pixel tables')
+
+
 def assemble_batch(indices, mask_sparse_depth, pixel_table, rgb_table, depth_table=None, error_table=None, points_table=None):
     """indices int64 [B] (flat pixel indices), mask_sparse_depth bool [B] or None; tables [N,3] int32 / [N,3] / [N,1] / [N,1] /
     [N,3] fp32, all CUDA.  Returns dict with pixel_id int32 [B,3], target_rgb [B,3] and, when the sparse-depth tables are
@@ -16,6 +41,8 @@ def assemble_batch(indices, mask_sparse_depth, pixel_table, rgb_table, depth_tab
     assert indices.dtype == torch.int64 and pixel_table.dtype == torch.int32
     indices = indices.contiguous()
     dev = indices.device
+    check_indices_error(dev)
+    flag = _error_flag(dev)
     B, N = indices.shape[0], pixel_table.shape[0]
     mask = None if mask_sparse_depth is None else mask_sparse_depth.to(torch.uint8).contiguous()
     out = {'pixel_id': torch.empty((B, 3), dtype=torch.int32, device=dev), 'target_rgb': torch.empty((B, 3), dtype=torch.float32, device=dev)}
@@ -28,5 +55,5 @@ def assemble_batch(indices, mask_sparse_depth, pixel_table, rgb_table, depth_tab
     tables = [pixel_table.contiguous(), f(rgb_table), f(depth_table), f(error_table), f(points_table)]
     L.call('srf_assemble_batch', L.ptr(indices), L.ptr(mask), B, N, *[L.ptr(t) for t in tables], L.ptr(out['pixel_id']),
            L.ptr(out['target_rgb']), L.ptr(out.get('sparse_depth_values')), L.ptr(out.get('sparse_depth_errors')),
-           L.ptr(out.get('sparse_depth_points3d')), L.stream_handle())
+           L.ptr(out.get('sparse_depth_points3d')), flag.data_ptr(), L.stream_handle())
     return out

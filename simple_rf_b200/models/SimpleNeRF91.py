@@ -126,23 +126,34 @@ class SimpleNeRF(torch.nn.Module):
             raise NotImplementedError('learnable cameras are not supported by the fused ray generation')
         if intrinsics is not None:
             return ops.camera_tables(intrinsics, extrinsics, device)
-        if self._camera_tables is None or self._camera_tables[0].device != device:
-            self._camera_tables = ops.camera_tables(self.intrinsics_learner.initial_intrinsics,
-                                                    self.extrinsics_learner.view_matrices(), device)
-        return self._camera_tables
+        # keyed on the camera tensors' storage + version: load_state_dict() copies new cameras in place
+        cams = (self.intrinsics_learner.initial_intrinsics, self.extrinsics_learner.initial_extrinsics,
+                self.extrinsics_learner.r, self.extrinsics_learner.t)
+        key = (str(device),) + tuple((c.data_ptr(), c._version) for c in cams)
+        if self._camera_tables is None or self._camera_tables[0] != key:
+            self._camera_tables = (key, ops.camera_tables(self.intrinsics_learner.initial_intrinsics,
+                                                          self.extrinsics_learner.view_matrices(), device))
+        return self._camera_tables[1]
 
     def render(self, input_dict: dict, *, retraw: bool, mode: str):
         """batchify_rays (SimpleNeRF17.py:133-157): chunks of `chunk` rays in training (keeps the
         reference's random-number order), of `eval_chunk` rays otherwise (results do not depend on it)."""
+        from .. import parallel
         pixel_id = input_dict['pixel_id']
         num_rays = pixel_id.shape[0]
         chunk = self.configs['model']['chunk'] if self.training else max(self.eval_chunk, self.configs['model']['chunk'])
+        # test time on several ranks (one process per GPU): every rank receives the full frame from create_test_data
+        # (DataPreprocessor10.py:736-743), renders its row band and all-gathers the per-ray maps, so Tester07 needs no edit
+        band = None if self.training else parallel.eval_band(num_rays, self.configs['model'])
+        if band is not None:
+            pixel_id = pixel_id[band[0]:band[1]]
         parts = []
-        for i in range(0, num_rays, chunk):
+        for i in range(0, pixel_id.shape[0], chunk):
             parts.append(self.render_rays(pixel_id[i:i + chunk], input_dict, retraw=retraw, mode=mode))
-        if len(parts) == 1:
-            return parts[0]
-        return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+        out = parts[0] if len(parts) == 1 else {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+        if band is not None:
+            out = parallel.gather_ray_outputs(out, num_rays)
+        return out
 
     def render_rays(self, pixel_id, input_dict, *, retraw, mode):
         mc = self.configs['model']
@@ -178,10 +189,18 @@ class SimpleNeRF(torch.nn.Module):
                                        ndc=False, viewdirs_from_ndc=False)[4]
             out['view_dirs'] = view_dirs
         perturb = self.training and mc['perturb']
+        from .. import parallel
+        shard = input_dict.get('srf_shard') if self.training else None
+
+        def cpu_draw(draw):                      # the reference's CPU draw for R rays (this rank's rows of it on several ranks)
+            return parallel.rows_of_global_draw(draw, R, shard, mc['chunk']).to(dev)
+
+        def device_seed():
+            return parallel.rank_seed(int(torch.randint(0, 2 ** 31, (1,)).item()))
         aug_active = self.augmentations_needed and self.training and (mode != 'test_camera_params_optimization')
 
         def run(model, z, tag, prefix=''):
-            noise = model.draw_noise(R * z.shape[1], dev, self.training, self.rng_mode)
+            noise = model.draw_noise(R, z.shape[1], dev, self.training, self.rng_mode, cpu_draw)
             sigma, rgb = model.evaluate(so, sd, z, view_dirs, noise)
             vr = ops.composite(sigma[..., 0], rgb, z, rays_o, rays_d, d_ndc, ndc=self.ndc,
                                white_bkgd=mc['white_bkgd'], per_sample=retraw)
@@ -201,9 +220,9 @@ class SimpleNeRF(torch.nn.Module):
             S = mc['coarse_model']['num_samples']
             ladder = coarse_ladder_on(dev, S, near, far, mc['lindisp'])
             if perturb and self.rng_mode == 'reference':
-                z_coarse = ops.stratified_z(ladder, R, jitter=torch.rand([R, S]).to(dev))       # SimpleNeRF17.py:355
+                z_coarse = ops.stratified_z(ladder, R, jitter=cpu_draw(lambda n: torch.rand([n, S])))       # SimpleNeRF17.py:355
             elif perturb:
-                z_coarse = ops.stratified_z(ladder, R, philox_seed=int(torch.randint(0, 2 ** 31, (1,)).item()))
+                z_coarse = ops.stratified_z(ladder, R, philox_seed=device_seed())
             else:
                 z_coarse = ops.stratified_z(ladder, R)
             out['z_vals_coarse'] = z_coarse
@@ -216,9 +235,9 @@ class SimpleNeRF(torch.nn.Module):
             N = mc['fine_model']['num_samples']
             w_det = weights_coarse.detach()
             if perturb and self.rng_mode == 'reference':
-                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=torch.rand([R, N]).to(dev))   # SimpleNeRF17.py:397
+                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=cpu_draw(lambda n: torch.rand([n, N])))   # SimpleNeRF17.py:397
             elif perturb:
-                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, philox_seed=int(torch.randint(0, 2 ** 31, (1,)).item()))
+                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, philox_seed=device_seed())
             else:
                 z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=_on_device('linspace', int(N), dev, lambda: torch.linspace(0., 1., steps=N)))
             out['z_vals_fine'] = z_fine
@@ -317,16 +336,22 @@ class MLP(torch.nn.Module):
             self._packed_version = version
         return self._packed
 
-    def draw_noise(self, count, device, training, rng_mode):
+    def draw_noise(self, num_rays, num_samples, device, training, rng_mode, cpu_draw=None):
         """sigma pre-activation noise (SimpleNeRF17.py:739-741).  Reference mode draws torch.randn on the CPU
-        generator per `netchunk` points, exactly as the reference's chunk loop does (:460, :740)."""
+        generator per `netchunk` points, exactly as the reference's chunk loop does (:460, :740); `cpu_draw` (several
+        ranks) hands this rank its rows of the global draw."""
         if not (training and self.raw_noise_std > 0.):
             return None
         if rng_mode != 'reference':
-            return torch.randn(count, device=device) * self.raw_noise_std
-        netchunk = self.configs['model']['netchunk'] or count
-        parts = [torch.randn([min(netchunk, count - i), 1]) * self.raw_noise_std for i in range(0, count, netchunk)]
-        return torch.cat(parts, 0).reshape(-1).to(device)
+            return torch.randn(num_rays * num_samples, device=device) * self.raw_noise_std
+
+        def draw(n):
+            count = n * num_samples
+            netchunk = self.configs['model']['netchunk'] or count
+            parts = [torch.randn([min(netchunk, count - i), 1]) * self.raw_noise_std for i in range(0, count, netchunk)]
+            return torch.cat(parts, 0).reshape(n, num_samples)
+        noise = cpu_draw(draw) if cpu_draw is not None else draw(num_rays).to(device)
+        return noise.reshape(-1)
 
     def evaluate(self, rays_o, rays_d, z, view_dirs, noise):
         """-> sigma [R,S,1], rgb [R,S,3]; differentiable w.r.t. the parameters when grad is enabled."""

@@ -139,19 +139,30 @@ class SimpleTensoRF(torch.nn.Module):
             raise NotImplementedError('learnable cameras are not supported by the fused ray generation')
         if intrinsics is not None:
             return ops.camera_tables(intrinsics, extrinsics, device)
-        if self._camera_tables is None or self._camera_tables[0].device != device:
-            self._camera_tables = ops.camera_tables(self.intrinsics_learner.initial_intrinsics,
-                                                    self.extrinsics_learner.view_matrices(), device)
-        return self._camera_tables
+        # keyed on the camera tensors' storage + version: load_state_dict() copies new cameras in place
+        cams = (self.intrinsics_learner.initial_intrinsics, self.extrinsics_learner.initial_extrinsics,
+                self.extrinsics_learner.r, self.extrinsics_learner.t)
+        key = (str(device),) + tuple((c.data_ptr(), c._version) for c in cams)
+        if self._camera_tables is None or self._camera_tables[0] != key:
+            self._camera_tables = (key, ops.camera_tables(self.intrinsics_learner.initial_intrinsics,
+                                                          self.extrinsics_learner.view_matrices(), device))
+        return self._camera_tables[1]
 
     def render(self, input_dict: dict, *, retraw: bool, mode: str):
+        from .. import parallel
         pixel_id = input_dict['pixel_id']
+        num_rays = pixel_id.shape[0]
         chunk = self.configs['model']['chunk'] if self.training else max(self.eval_chunk, self.configs['model']['chunk'])
+        # test time on several ranks: this rank's row band of the frame, then one all-gather of the per-ray maps (SURVEY.md §8e iii)
+        band = None if self.training else parallel.eval_band(num_rays, self.configs['model'])
+        if band is not None:
+            pixel_id = pixel_id[band[0]:band[1]]
         parts = [self.render_rays(pixel_id[i:i + chunk], input_dict, retraw=retraw, mode=mode)
                  for i in range(0, pixel_id.shape[0], chunk)]
-        if len(parts) == 1:
-            return parts[0]
-        return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+        out = parts[0] if len(parts) == 1 else {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+        if band is not None:
+            out = parallel.gather_ray_outputs(out, num_rays)
+        return out
 
     def render_rays(self, pixel_id, input_dict, *, retraw, mode):
         mc = self.configs['model']
@@ -178,10 +189,13 @@ class SimpleTensoRF(torch.nn.Module):
         S = main.host_geometry()['num_samples']
         ladder = coarse_ladder_on(dev, S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp'])
         perturb = self.training and mc['perturb']
+        from .. import parallel
+        shard = input_dict.get('srf_shard') if self.training else None
         if perturb and self.rng_mode == 'reference':
-            z = ops.stratified_z(ladder, R, jitter=torch.rand([R, S]).to(dev))                     # SimpleTensoRF09.py:379
+            jitter = parallel.rows_of_global_draw(lambda n: torch.rand([n, S]), R, shard, mc['chunk'])
+            z = ops.stratified_z(ladder, R, jitter=jitter.to(dev))                                  # SimpleTensoRF09.py:379
         elif perturb:
-            z = ops.stratified_z(ladder, R, philox_seed=int(torch.randint(0, 2 ** 31, (1,)).item()))
+            z = ops.stratified_z(ladder, R, philox_seed=parallel.rank_seed(int(torch.randint(0, 2 ** 31, (1,)).item())))
         else:
             z = ops.stratified_z(ladder, R)
         out['z_vals_coarse'] = z

@@ -26,7 +26,9 @@ class _FlatGroup:
         self.flat_p = torch.zeros(o, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(o, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(o, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(o, dtype=torch.float32, device=dev)
+        # gradient bucket + one 'this rank holds a gradient' flag per parameter behind it: both travel in the SAME all-reduce
+        self.flat_g = torch.zeros(o + -(-len(params) // 4) * 4, dtype=torch.float32, device=dev)
+        self.flags = self.flat_g[o:o + len(params)]
         self.steps = []                                # per parameter, as torch keeps them (they differ after TensoRF's
         for p, off, n in zip(params, self.offsets, self.sizes):       # reconfigure_optimizer deletes states by index)
             st = optimizer.state.get(p, {})
@@ -93,28 +95,37 @@ class FusedFlatAdam:
         world = torch.distributed.get_world_size(self.process_group) if parallel.is_distributed() else 1
         self.bytes_reduced_last = 0
         for group, fg in work:
-            # gather the gradients (one batched copy); parameters without a gradient are skipped like torch does,
-            # unless other ranks may hold one (then they contribute zeros to the all-reduce)
+            # gather the gradients (one batched copy).  A parameter is stepped iff SOME rank holds a gradient for it — what
+            # torch.optim.Adam does on one GPU (parameters whose .grad is None are skipped: the stale planes TensoRF leaves in
+            # the optimiser between shrink_tensor and the next reconfigure_optimizer, SimpleTensoRF09.py:821-830, must not
+            # move, and their step counters must not advance).  The per-parameter 'has gradient' flags ride behind the
+            # bucket in the same all-reduce; they are read back (one synchronisation) only by a rank that itself misses a
+            # gradient — a rank holding all of them already knows the answer.
             have = [p.grad is not None for p in fg.params]
             if not any(have) and world == 1:
                 continue
-            if world > 1:
-                have_step = [True] * len(fg.params)
-            else:
-                have_step = have
             if world > 1 or not all(have):
                 fg.flat_g.zero_()
             dst = [fg.flat_g[o:o + n].view(p.shape) for p, o, n, h in zip(fg.params, fg.offsets, fg.sizes, have) if h]
             src = [p.grad for p, h in zip(fg.params, have) if h]
             if dst:
                 torch._foreach_copy_(dst, src)
+            have_step = have
             if world > 1:
+                if all(have):
+                    fg.flags.fill_(1.0)                  # a kernel, not a pageable host->device copy (which would drain the launch queue)
+                else:
+                    fg.flags.copy_(torch.tensor([1.0 if h else 0.0 for h in have]))
                 torch.distributed.all_reduce(fg.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
-                fg.flat_g.mul_(1.0 / world)
                 self.bytes_reduced_last += fg.flat_g.numel() * 4
+                if not all(have):
+                    have_step = [f > 0 for f in fg.flags.tolist()]
+                fg.flat_g[:fg.total].mul_(1.0 / world)
                 for p, o, n in zip(fg.params, fg.offsets, fg.sizes):          # the averaged gradient stays visible in .grad
                     if p.grad is not None:
                         p.grad.copy_(fg.flat_g[o:o + n].view(p.shape))
+            if not any(have_step):
+                continue
             beta1, beta2 = group['betas']
             for a, b in _runs(have_step, fg.steps):     # one launch per run of stepped parameters with equal step counts
                 step = fg.steps[a] + 1

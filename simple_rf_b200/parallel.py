@@ -113,6 +113,53 @@ def attach_gradient_allreduce(optimizers):
     return [FlatGradAllReduce(opt) for opt in optimizers.values() if opt is not None and getattr(opt, '_srf_fused', None) is None]
 
 
+def gather_ray_outputs(out, num_rays):
+    """All-gather of a dict of per-ray tensors ([rows_of_this_rank, ...], rows = shard_bounds(num_rays, rank, world)) into
+    full-frame tensors on every rank: ONE collective over a [longest_band, total_width] fp32 record (bands differ by at most
+    one row; the pad row is dropped).  This is the only collective of a sharded render and it moves 16-28 B/ray/key."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    spans = [shard_bounds(num_rays, r, world) for r in range(world)]
+    longest = max(e - s for s, e in spans)
+    keys = sorted(out.keys())
+    flat = [out[k].reshape(out[k].shape[0], -1).float() for k in keys]
+    widths = [f.shape[1] for f in flat]
+    rec = torch.zeros((longest, sum(widths)), dtype=torch.float32, device=flat[0].device)
+    rec[:flat[0].shape[0]] = torch.cat(flat, 1)
+    full = torch.empty((world, longest, sum(widths)), dtype=torch.float32, device=rec.device)
+    dist.all_gather_into_tensor(full.view(world * longest, -1), rec)
+    rows = torch.cat([full[r, :e - s] for r, (s, e) in enumerate(spans)], 0)
+    res, o = {}, 0
+    for k, wd in zip(keys, widths):
+        res[k] = rows[:, o:o + wd].reshape((num_rays,) + tuple(out[k].shape[1:])).to(out[k].dtype)
+        o += wd
+    return res
+
+
+def eval_band(num_rays, configs_model):
+    """(start, end) of this rank's row band of a test-time frame, or None when the render is not sharded (single process,
+    `configs['model']['shard_eval_rays'] = False`, or fewer rays than ranks)."""
+    if not is_distributed() or not configs_model.get('shard_eval_rays', True) or num_rays < dist.get_world_size():
+        return None
+    return shard_bounds(num_rays, dist.get_rank(), dist.get_world_size())
+
+
+def rows_of_global_draw(draw, rows_local, shard, chunk):
+    """`draw(n)` makes the reference's CPU random tensor for n rays (first dim n).  On one rank: draw(rows_local).  On several
+    ranks with a `srf_shard` record from DataPreprocessor91 (rank, world, global_rows, row_indices): this rank's rows of the
+    single global draw, i.e. exactly the numbers the same rays get in a single-GPU run — as long as the global
+    batch is one `chunk` (the shipped configuration: 4096 of 4096)."""
+    if shard is None or shard[2] > chunk or len(shard[3]) != rows_local:
+        return draw(rows_local)
+    return draw(shard[2])[torch.from_numpy(shard[3])]
+
+
+def rank_seed(seed):
+    """Decorrelates the in-kernel Philox streams of the ranks (`rng_mode='device'`): every rank draws the same CPU seed."""
+    if not is_distributed():
+        return seed
+    return (seed ^ (dist.get_rank() * 0x5bd1e995)) & 0x7fffffff
+
+
 def render_sharded(model, input_batch, gather_keys=None, **forward_kwargs):
     """Render this rank's band of `input_batch['pixel_id']`; when `gather_keys` is given, all-gather those
     per-ray outputs so every rank (rank 0 included) holds the full-frame tensors."""

@@ -24,7 +24,7 @@ def _i3(t):
 
 
 def _ptrs(tensors):
-    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return (ctypes.c_void_p * len(tensors))(*[L.ptr(t) for t in tensors])
 
 
 def pack_alpha_bits(alpha_volume):

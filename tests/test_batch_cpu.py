@@ -38,7 +38,9 @@ def test_dropin_preprocessor_resolves_through_reference_factory():
     from data_preprocessors.DataPreprocessor10 import DataPreprocessor as Ref
     assert issubclass(cls, Ref) and cls.__module__.startswith('simple_rf_b200.data_preprocessors')
     assert cls.load_nerf_cached_batch is not Ref.load_nerf_cached_batch
-    assert cls.select_batch_indices is Ref.select_batch_indices                     # RNG / shuffling order stays the reference's
+    # single process: the override delegates to the reference (RNG / shuffling order stays the reference's); the multi-rank
+    # slicing is covered by tests/test_parallel_cpu.py::test_preprocessor_rank_sharding_gloo
+    assert cls.generate_indices is Ref.generate_indices
 
 
 def test_assemble_batch_refuses_cpu():

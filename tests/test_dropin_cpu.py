@@ -74,3 +74,33 @@ def test_tensorf_dropin_resolves_and_matches_state_dict():
     assert [g['name'] for g in g_ref] == [g['name'] for g in g_mine]
     assert [[tuple(p.shape) for p in g['params']] for g in g_ref] == [[tuple(p.shape) for p in g['params']] for g in g_mine]
     assert int(mine.coarse_model.num_samples) == int(ref.coarse_model.num_samples)
+
+
+def test_callers_harness_drives_unmodified_trainer_and_tester_on_cpu():
+    """simple_rf_b200/dropin/callers.py (used by tests/test_gpu_reference_callers.py and bench.py --impl reference): the
+    UNMODIFIED Trainer.train_one_iter (src/Trainer10.py:65) and NerfTester.predict_frame (src/Tester07.py:153) run on the
+    analytic synthetic scene with the reference's own classes, on the CPU, at a seconds-scale size."""
+    from simple_rf_b200.dropin import callers as C
+    if not C.available():
+        pytest.skip('upstream tree not present')
+    import numpy
+    cfg = C.complete_configs(C.load_shipped_configs(1142), [0], seed=3)
+    cfg['data_loader']['num_rays'] = 64
+    cfg['data_loader']['sparse_depth']['num_rays'] = 64
+    raw = C.synthetic_raw_data('llff', 3, resolution=(30, 40), sparse_points=100, seed=2)
+    # the scene is consistent: a sparse depth re-projects onto the same colour in the neighbouring view
+    assert raw['nerf_data']['images'].shape == (3, 30, 40, 3) and raw['nerf_data']['images'].dtype == numpy.uint8
+    trainer, model, mc = C.make_trainer(cfg, raw, seed=3)
+    assert mc['resolution'] == [30, 40] and abs(mc['near'] - 1.0) < 1e-6 and mc['near_ndc'] == 0.0
+    losses = trainer.train_one_iter(0)
+    assert set(losses) == {'MSE14', 'SparseDepthMSE14', 'AugmentationsDepthLoss11', 'CoarseFineConsistencyLoss34', 'TotalLoss'}
+    assert all(numpy.isfinite(v) for v in losses.values())
+    tester = C.make_tester(cfg, mc, [0])
+    tester.model.load_state_dict(model.state_dict())
+    tester.model.eval()
+    frame = tester.predict_frame(C.test_pose(raw))
+    assert frame['image'].shape == (30, 40, 3) and frame['image'].dtype == numpy.uint8
+    assert set(frame) == {'image', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc'}
+    names = C.use_dropin(cfg)
+    assert names['model']['name'] == 'SimpleNeRF91' and names['data_loader']['data_preprocessor_name'] == 'DataPreprocessor91'
+    assert [l['name'] for l in names['losses']] == ['MSE14', 'SparseDepthMSE14', 'AugmentationsDepthLoss91', 'CoarseFineConsistencyLoss91']
