@@ -52,3 +52,31 @@ def tensorf_sets(configs, seed, with_alpha):
     return sets
 
 
+
+
+from simple_rf_b200.synthetic import blocky_alpha_volume  # noqa: E402  (shared with bench.py: same mask in tests and bench)
+
+
+def tensorf_full_size_sets(configs, seed, alpha_size=190):
+    """BASELINE.json configs[2]/[3] size: the tensors of `configs` at their configured `num_voxels_initial` (300^3 ->
+    331x368x220 voxels, 1083 samples/ray for the main tensor) with a 190^3 alpha mask on the main tensor — the shapes bench.py
+    times.  Same recipe as tensorf_sets(): seeded 0.1 randn planes, density planes x6."""
+    g = torch.Generator().manual_seed(seed)
+    mc = configs['model']
+
+    def one(cfg, with_alpha):
+        bbox = torch.tensor(cfg['bounding_box'])
+        res = TF.vm_resolution(cfg['num_voxels_initial'], bbox)
+        t = {'params': TF.init_vm_params(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
+             'bbox': bbox, 'resolution': res, 'num_samples': TF.vm_num_samples(res, cfg['num_voxels_per_sample'], cfg['num_samples_max'])}
+        for i in range(3):
+            t['params'][f'matrices_density.{i}'] *= 6.0
+        if with_alpha:
+            vol = blocky_alpha_volume(alpha_size, 10, 0.10, 0.004, g)
+            t['alpha_volume'] = vol.view(1, 1, alpha_size, alpha_size, alpha_size)
+            t['alpha_bbox'] = bbox.clone()
+        return t
+    sets = {'coarse_model': one(mc['coarse_model'], True), 'augmentations': []}
+    for aug in mc.get('augmentations', []):
+        sets['augmentations'].append((aug['name'], aug['coarse_model'], one(aug['coarse_model'], False)))
+    return sets

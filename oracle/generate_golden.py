@@ -231,6 +231,53 @@ def golden_tensorf():
         print(f'tensorf_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f})')
 
 
+def tensorf_full_size_configs():
+    """Shipped train0212 config at the size bench.py times (BASELINE.json configs[2]/[3]): 300^3-voxel main tensor
+    (331x368x220, 1083 samples/ray), 160^3-voxel augmentation tensor, full 576x1024 frames."""
+    configs, model_configs = H.load_configs(212, '00000')
+    configs['model']['coarse_model']['num_voxels_initial'] = 300 ** 3
+    configs['model']['coarse_model']['num_voxels_final'] = 300 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 160 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_final'] = 160 ** 3
+    return configs, model_configs
+
+
+def golden_tensorf_full_size():
+    """The unmodified reference at the benchmarked size.  Per-ray maps, weights and the two masks are stored (bit-packed masks);
+    the remaining per-sample tensors are re-derived by the oracle inside the GPU test (it is pinned bit-exact here)."""
+    configs, model_configs = tensorf_full_size_configs()
+    (OUT / 'tensorf_full_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    assert [int(v) for v in model.coarse_model.resolution] == [331, 368, 220] and int(model.coarse_model.num_samples) == 1083
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    sets = FX.tensorf_full_size_sets(configs, seed=31)
+    load_tensorf_params(model, sets)
+    keys = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility', 'weights', 'raw_sigma', 'raw_rgb')
+    for mode, R, seed in (('eval', 96, 7), ('train', 64, 8)):
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(300 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+        torch.manual_seed(300 + seed)
+        with torch.no_grad():
+            mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        fixture = {'pixel_id': pixel_id, 'param_seed': 31, 'rng_seed': 300 + seed}
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for k in keys:
+                key = f'{pre}{k}_coarse'
+                _check(f'tensorf_full/{mode}/{key}', ref[key], mine[key])
+                if k in ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'weights'):
+                    fixture[key] = ref[key]
+            for m in ('validity_mask', 'surface_mask'):
+                fixture[f'{pre}{m}_coarse_bits'] = np.packbits(mine[f'{pre}{m}_coarse'].numpy().astype(np.uint8).reshape(-1))
+        frac = mine['validity_mask_coarse'].float().mean().item(), mine['surface_mask_coarse'].float().mean().item()
+        np.savez_compressed(OUT / f'tensorf_full_{mode}.npz', **_np(fixture))
+        print(f'tensorf_full_{mode}: oracle == reference at 331x368x220 / 1083 samples (valid {frac[0]:.3f}, surface {frac[1]:.4f})')
+
+
 def patch_loss_inputs(num_rays=6000, h=96, w=128, seed=0):
     """Seeded scene for the patch-reprojection losses: smooth random images, three LLFF-like cameras, rays through random
     pixels, two noisy depth candidates, and a half-random image-ray mask (shared with tests/)."""
@@ -421,6 +468,8 @@ def main():
     golden_sample_pdf()
     golden_composite(copy.deepcopy(configs), model_configs)
     golden_tensorf()
+    if 'full' in sys.argv[1:] or not (OUT / 'tensorf_full_eval.npz').exists():
+        golden_tensorf_full_size()
     golden_patch_loss()
     golden_nerf_training_curve()
     golden_tensorf_training_curve()

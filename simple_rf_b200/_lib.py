@@ -99,7 +99,16 @@ def stream_handle():
 
 
 LAUNCHES = {}          # entry point -> number of successful launches (bench.py reports the total)
-TIMING = None          # when a list: (name, start_event, end_event, work) tuples appended per timed launch
+TIMING = None          # when a list: (name, start_event, end_event, work) tuples appended per timed launch; `work` is the
+                       # algorithmic work of the launch (FLOPs or bytes), either a float or (device count tensor, work per
+                       # counted unit) when the unit count only exists on the device (resolve with resolve_work after a sync)
+
+
+def resolve_work(work):
+    if isinstance(work, tuple):
+        count, per_unit = work
+        return float(count.item()) * per_unit
+    return float(work)
 
 
 def call(name, *args, work=None):

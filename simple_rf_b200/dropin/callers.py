@@ -68,6 +68,22 @@ def install_import_stubs():
     _stub('deepdiff', DeepDiff=lambda a, b, **k: {} if a == b else {'values_changed': True})
 
 
+class force_cpu:
+    """Context manager: the reference picks its device with `torch.cuda.is_available()` (src/utils/CommonUtils04.py:25-26,
+    torch.nn.DataParallel likewise), so hiding CUDA behind that one call runs its unmodified code on the host CPU inside a
+    process that also uses the GPU (bench.py's cpu_baseline)."""
+
+    def __enter__(self):
+        import torch
+        self._saved = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.is_available = self._saved
+
+
 def prepare(install_dropin=True):
     """sys.path + stubs (+ shim directories of the drop-in classes).  Returns the reference root."""
     root = reference_root()

@@ -114,7 +114,9 @@ class _Composite(torch.autograd.Function):
         L.call('srf_composite_fwd', L.ptr(sigma), L.ptr(rgb), L.ptr(z), L.ptr(rays_o), L.ptr(rays_d), L.ptr(rays_d_ndc),
                R, S, int(ndc), int(white_bkgd), float(distance_scale), L.ptr(alpha), L.ptr(vis), L.ptr(weights),
                L.ptr(rgb_map), L.ptr(acc), L.ptr(depth), L.ptr(depth_var), L.ptr(depth_ndc), L.ptr(depth_var_ndc),
-               L.stream_handle())
+               L.stream_handle(),
+               # algorithmic bytes: sigma + z in, weights out (+ rgb in, + alpha & visibility out) per sample
+               work=float(R) * S * (12 + (12 if rgb is not None else 0) + (8 if keep else 0)) + float(R) * 68)
         ctx.cfg = (bool(ndc), bool(white_bkgd), float(distance_scale), rgb is not None)
         ctx.save_for_backward(sigma, rgb, z, vis, rays_o, rays_d, rays_d_ndc, acc, depth, depth_ndc)
         outs = (alpha, vis, weights, rgb_map, acc, depth, depth_var, depth_ndc, depth_var_ndc)
@@ -133,7 +135,9 @@ class _Composite(torch.autograd.Function):
         L.call('srf_composite_bwd', L.ptr(sigma), L.ptr(rgb if gs[0] is not None else None), L.ptr(z), L.ptr(vis),
                L.ptr(rays_o), L.ptr(rays_d), L.ptr(rays_d_ndc), L.ptr(acc), L.ptr(depth), L.ptr(depth_ndc),
                *[L.ptr(g) for g in gs], R, S, int(ndc), int(white), scale, L.ptr(g_sigma), L.ptr(g_rgb_s),
-               L.stream_handle())
+               L.stream_handle(),
+               # sigma, z, visibility (+ rgb) in, g_sigma (+ g_rgb) out (+ a direct weights gradient in) per sample
+               work=float(R) * S * (16 + (12 if gs[0] is not None else 0) + (12 if want_rgb else 0) + (4 if gs[6] is not None else 0)))
         if has_rgb and ctx.needs_input_grad[1] and g_rgb_s is None:
             g_rgb_s = torch.zeros((R, S, 3), dtype=torch.float32, device=sigma.device)
         return g_sigma, g_rgb_s, None, None, None, None, None, None, None, None

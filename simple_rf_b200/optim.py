@@ -116,7 +116,14 @@ class FusedFlatAdam:
                     fg.flags.fill_(1.0)                  # a kernel, not a pageable host->device copy (which would drain the launch queue)
                 else:
                     fg.flags.copy_(torch.tensor([1.0 if h else 0.0 for h in have]))
+                timed = L.TIMING is not None
+                if timed:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 torch.distributed.all_reduce(fg.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+                if timed:                              # NCCL runs on its own stream: the events bracket the wait of the compute stream
+                    e1.record()
+                    L.TIMING.append(('nccl_all_reduce', e0, e1, float(fg.flat_g.numel() * 4)))
                 self.bytes_reduced_last += fg.flat_g.numel() * 4
                 if not all(have):
                     have_step = [f > 0 for f in fg.flags.tolist()]

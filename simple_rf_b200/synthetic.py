@@ -115,3 +115,15 @@ def frame_pixel_ids(height, width, view=0):
     (DataPreprocessor10.py:736-743)."""
     ys, xs = np.meshgrid(np.arange(height, dtype=np.int32), np.arange(width, dtype=np.int32), indexing='ij')
     return np.stack([np.full(xs.size, view, dtype=np.int32), xs.reshape(-1), ys.reshape(-1)], axis=1)
+
+
+def blocky_alpha_volume(size, block, p_block, p_speckle, generator):
+    """[Z,Y,X] float {0,1} occupancy volume from platform-independent ops only (mt19937 `rand`, comparisons, exact
+    nearest-neighbour repetition): blocks of `block`^3 voxels occupied with probability p_block + isolated voxels with
+    probability p_speckle — contiguous occupied regions (what a trained scene gives) with a ragged surface."""
+    import torch
+    n = -(-size // block)
+    coarse = torch.rand(n, n, n, generator=generator) < p_block
+    vol = coarse.repeat_interleave(block, 0).repeat_interleave(block, 1).repeat_interleave(block, 2)[:size, :size, :size]
+    vol = vol | (torch.rand(size, size, size, generator=generator) < p_speckle)
+    return vol.float()

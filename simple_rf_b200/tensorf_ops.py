@@ -69,7 +69,7 @@ def validity_compact(rays_o, rays_d, z, bbox, alpha=None):
     else:
         a_bits, a_res, a_min, a_size = L.ptr(alpha['bits']), _i3(alpha['res']), _f3(alpha['box_min']), _f3(alpha['box_size'])
     L.call('srf_tensorf_mask', L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), R, S, _f3(bbox), a_bits, a_res, a_min, a_size,
-           L.ptr(mask), L.ptr(counts), L.stream_handle())
+           L.ptr(mask), L.ptr(counts), L.stream_handle(), work=float(total) * 5)      # 4 B depth in + 1 B mask out per sample
     idx, count = _compact(mask, counts, total)
     return Compacted(mask.view(torch.bool), idx, count, total)
 
@@ -130,7 +130,8 @@ class _VmDensity(torch.autograd.Function):
         sigma = torch.zeros((R, geom.S, 1), dtype=torch.float32, device=geom.z.device)
         feat = torch.empty((max(comp.total, 1),), dtype=torch.float32, device=geom.z.device)
         L.call('srf_vm_density_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, int(softplus),
-               float(offset), L.ptr(sigma), L.ptr(feat), L.stream_handle())
+               float(offset), L.ptr(sigma), L.ptr(feat), L.stream_handle(),
+               work=(comp.count, 4.0 * 6 * sum(p.shape[1] for p in planes)))        # requested texel bytes: 4 plane + 2 line texels x C floats
         ctx.geom, ctx.comp, ctx.cfg = geom, comp, (int(softplus), float(offset), n_planes)
         ctx.tables = (planes_cl, lines_cl, chans)
         ctx.save_for_backward(feat)
@@ -145,7 +146,8 @@ class _VmDensity(torch.autograd.Function):
         gp = [torch.zeros_like(p) for p in planes_cl]
         gl = [torch.zeros_like(l) for l in lines_cl]
         L.call('srf_vm_density_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, softplus, offset,
-               L.ptr(L.f32c(g_sigma)), L.ptr(feat), _ptrs(gp), _ptrs(gl), L.stream_handle())
+               L.ptr(L.f32c(g_sigma)), L.ptr(feat), _ptrs(gp), _ptrs(gl), L.stream_handle(),
+               work=(comp.count, 2 * 4.0 * 6 * sum(p.shape[2] for p in planes_cl)))   # texel reads + the same again as atomic adds
         grads = [g.permute(2, 0, 1)[None].contiguous() for g in gp] + [g.permute(1, 0)[None, :, :, None].contiguous() for g in gl]
         return (None, None, None, None, None, *grads)
 
@@ -169,7 +171,8 @@ def vm_color_rows(geom, comp, view_dirs, planes, lines):
     pitch = color_row_pitch(sum(p.shape[1] for p in planes))
     rows = torch.empty((max(comp.total, 1), pitch), dtype=torch.bfloat16, device=geom.z.device)
     L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
-           L.ptr(L.f32c(view_dirs)), L.ptr(rows), pitch, L.stream_handle())
+           L.ptr(L.f32c(view_dirs)), L.ptr(rows), pitch, L.stream_handle(),
+           work=(comp.count, 4.0 * 6 * sum(p.shape[1] for p in planes)))
     return rows, (planes_cl, lines_cl, chans)
 
 
@@ -180,7 +183,8 @@ def vm_color_rows_backward(geom, comp, tables, g_rows):
     gl = [torch.zeros_like(l) for l in lines_cl]
     g = L.f32c(g_rows)
     L.call('srf_vm_color_features_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
-           L.ptr(g), g.shape[1], _ptrs(gp), _ptrs(gl), L.stream_handle())
+           L.ptr(g), g.shape[1], _ptrs(gp), _ptrs(gl), L.stream_handle(),
+           work=(comp.count, 2 * 4.0 * 6 * sum(p.shape[2] for p in planes_cl)))
     return ([x.permute(2, 0, 1)[None].contiguous() for x in gp], [x.permute(1, 0)[None, :, :, None].contiguous() for x in gl])
 
 

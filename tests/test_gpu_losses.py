@@ -83,3 +83,20 @@ def test_masks_vs_oracle_at_training_batch_size():
     m1, m2 = PR.patch_reprojection_masks(e('rays_o'), e('rays_d'), e('depth1'), e('depth2'), e('pixel_id'), d('poses'), d('k'), d('images'),
                                          (5, 5), 0.1, True)
     assert m1.shape == (0,)
+
+
+def test_masks_with_non_contiguous_and_non_fp32_inputs():
+    """Strided views (RGBA images sliced `[..., :3]` as DataPreprocessor10.py:812 produces, column slices of wider ray tensors)
+    and fp64 depths: every argument becomes a converted TEMPORARY; the temporaries must all stay alive until the launch
+    (a freed one would be handed to the next same-sized temporary and two kernel arguments would alias)."""
+    from simple_rf_b200.loss_functions import patch_reprojection as PR
+    a = GG.patch_loss_inputs(num_rays=2048, h=120, w=160, seed=5)
+    d = lambda k: a[k].to(DEV)
+    want = PR.patch_reprojection_masks(d('rays_o'), d('rays_d'), d('depth1'), d('depth2'), d('pixel_id'), d('poses'), d('k'), d('images'),
+                                       (5, 5), 0.1, True, return_rmse=True)
+    rgba = torch.cat([d('images'), torch.ones_like(d('images')[..., :1])], -1)
+    wide = torch.cat([d('rays_o'), d('rays_d')], 1)                               # [R,6]: both ray tensors are column slices
+    got = PR.patch_reprojection_masks(wide[:, :3], wide[:, 3:], d('depth1').double(), d('depth2').double(), d('pixel_id'),
+                                      d('poses').double(), d('k'), rgba[..., :3], (5, 5), 0.1, True, return_rmse=True)
+    for w_, g_ in zip(want, got):
+        assert torch.equal(w_, g_) if w_.dtype != torch.float32 else torch.equal(torch.nan_to_num(w_), torch.nan_to_num(g_))

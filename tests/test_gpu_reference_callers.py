@@ -73,7 +73,9 @@ def _run_trainer(cfg, raw, iters, keep_grads_at=0):
 
 def _compare_curves(ref_curve, my_curve, tol):
     worst = {}
+    base = lambda d: {(k[:-2] if k[-2:].isdigit() else k): v for k, v in d.items()}      # AugmentationsDepthLoss11 vs ...91
     for it, (a, b) in enumerate(zip(ref_curve, my_curve)):
+        a, b = base(a), base(b)
         assert a.keys() == b.keys(), (it, a.keys(), b.keys())
         for k in a:
             rel = abs(a[k] - b[k]) / max(abs(a[k]), 1e-8)
@@ -170,7 +172,7 @@ def test_nerf_predict_frame_static_camera_mode():
     for loss in cfg_ref['losses']:
         if 'iter_weights' in loss:
             loss['iter_weights'] = {'0': 0.1}
-    _, _, ref_model, mc, _ = _run_trainer(cfg_ref, raw, 1)
+    _, _, ref_model, mc, _ = _run_trainer(cfg_ref, raw, 3)
     state = copy.deepcopy(ref_model.state_dict())
     pose, view_pose = C.test_pose(raw, 0.2), C.test_pose(raw, 0.7)
     frames = {}
