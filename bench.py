@@ -297,23 +297,20 @@ def reference_shaped_losses(kind, configs, images, resolution):
     depth_keys = ['depth_coarse'] + [f'{n}_depth_coarse' for n in aug_names]
 
     def losses(batch, out, model):
-        m_img, m_sd = batch['indices_mask_nerf'], batch['indices_mask_sparse_depth']
-        target = batch['target_rgb'][m_img]
-        total = sum(torch.square(out[k][m_img] - target).mean() for k in rgb_keys)
-        gt = batch['sparse_depth_values'][:, 0][m_sd]
-        total = total + 0.1 * sum(torch.square(out[k][m_sd] - gt).mean() for k in depth_keys)
+        r_img, r_sd = batch['srf_rows']['nerf'], batch['srf_rows']['sparse_depth']       # index_select: no mask-size read-back
+        target = batch['target_rgb'].index_select(0, r_img)
+        total = sum(torch.square(out[k].index_select(0, r_img) - target).mean() for k in rgb_keys)
+        gt = batch['sparse_depth_values'][:, 0].index_select(0, r_sd)
+        total = total + 0.1 * sum(torch.square(out[k].index_select(0, r_sd) - gt).mean() for k in depth_keys)
         inp = dict(batch, common_data={'images': images, 'resolution': resolution})
         total = total + 0.1 * aug_loss.compute_loss(inp, out, model)['loss_value']
         if cf_loss is not None:
             total = total + 0.1 * cf_loss.compute_loss(inp, out, model)['loss_value']
-        if kind == 'tensorf':
-            tv = 0.0
-            for t in [model.coarse_model] + [a['coarse_model'] for a in model.augmented_models]:
-                for planes in (t.matrices_density, t.matrices_color):
-                    for p in planes:                                   # TotalVariationLoss04.py:97-116
-                        tv = tv + (torch.square(p[:, :, 1:, :] - p[:, :, :-1, :]).sum() / p[:, :, 1:, :].numel() +
-                                   torch.square(p[:, :, :, 1:] - p[:, :, :, :-1]).sum() / p[:, :, :, 1:].numel()) * 2 / p.shape[0]
-            total = total + 0.01 * tv
+        if kind == 'tensorf':                                   # TotalVariationLoss04.py:44-78: the augmented tensors only
+            from simple_rf_b200.loss_functions.TotalVariationLoss91 import tv_loss
+            for a in model.augmented_models:
+                t = a['coarse_model']
+                total = total + 0.01 * tv_loss([*t.matrices_density, *t.matrices_color], 1.0)
         return total
     return losses
 
@@ -328,6 +325,7 @@ def synthetic_batch(rays_img, rays_sd, num_views, h, w, device, seed):
     return {'pixel_id': pid.to(device), 'target_rgb': torch.rand(n, 3, generator=g).to(device),
             'sparse_depth_values': (1.0 + 3.0 * torch.rand(n, 1, generator=g)).to(device),
             'indices_mask_nerf': m_img.to(device), 'indices_mask_sparse_depth': (~m_img).to(device), 'num_frames': num_views,
+            'srf_rows': {'nerf': torch.arange(0, rays_img, device=device), 'sparse_depth': torch.arange(rays_img, n, device=device)},
             'iter_num': 0, 'sub_batch_index': 0}
 
 

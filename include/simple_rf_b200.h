@@ -174,7 +174,7 @@ int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const float* z,
 int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
                               const float* const* planes, const float* const* lines, const int* channels,
-                              const int* resolution, const float* view_dirs, void* rows, int row_pitch, void* stream);
+                              const int* resolution, const float* view_dirs, void* rows, int row_pitch, int z_is_ladder, void* stream);
 int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                               const int* count, int64_t max_count, const float* box_min, const float* box_size,
                               const float* const* planes, const float* const* lines, const int* channels,
@@ -234,6 +234,35 @@ int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* 
                        const int* count, void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream);
 int srf_dgrad_program_bytes(void);
 
+/* ---- fused test-time ray march of one VM tensor (NDC), rows IX-XII + the weights half of VIII of SURVEY.md §8a in one kernel:
+ * sample depths from the shared [num_samples] ladder (src/models/SimpleTensoRF09.py:363-376 at test time) -> points (:263) ->
+ * box test (:705) -> alphaMask test (:707-710, :1342-1349) -> VM density (:1214-1239) -> alpha / transmittance / weights
+ * (:767-790) -> acc, depth, depth_var, depth_ndc, depth_var_ndc (:792-811) -> surface test weights > threshold (:726).
+ * No [num_rays, num_samples] intermediate is read; the surface samples of ray r are appended, in sample order, to row r of
+ * entry_sample / entry_weight ([num_rays, num_samples], first ray_count[r] entries valid).  z_vals, dense sigma / weights are
+ * NOT produced: callers that need them (`retraw`, training) use the unfused entry points above.  num_rays * num_samples < 2^31.
+ * bbox = [min xyz | max xyz], box_size = the tensor's bounding_box_size buffer (host pointers, 6 + 3 floats); alpha_* nullable.
+ *
+ * srf_tensorf_march_compact: the per-ray lists -> one flat list in row-major (ray, sample) order — the order of the
+ * reference's boolean-mask indexing (:1248) — indices[j] = ray * num_samples + sample, weights[j], ray_offset[ray], *count.
+ * scratch: int32[num_rays + srf_tensorf_march_blocks(num_rays)].
+ *
+ * srf_ray_accumulate: rgb_map[r] = sum_k weights[ray_offset[r] + k] * rgb_rows[ray_offset[r] + k] (+ 1 - acc[r] on a white
+ * background): the colour half of volume_render (:813-817) over the surface samples only (rgb is 0 elsewhere, :1271). */
+int srf_tensorf_march(const float* rays_o_ndc, const float* rays_d_ndc, const float* rays_o, const float* rays_d,
+                      const float* ladder, int64_t num_rays, int num_samples, const float* bbox, const float* box_size,
+                      const uint32_t* alpha_bits, const int* alpha_res, const float* alpha_box_min, const float* alpha_box_size,
+                      const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                      int softplus, float density_offset, float distance_scale, float weight_threshold,
+                      float* acc, float* depth, float* depth_var, float* depth_ndc, float* depth_var_ndc,
+                      int* ray_count, int* entry_sample, float* entry_weight, void* stream);
+int srf_tensorf_march_blocks(int64_t num_rays);
+int srf_tensorf_march_compact(const int* ray_count, int64_t num_rays, int num_samples, const int* entry_sample,
+                              const float* entry_weight, int* scratch, int* ray_offset, int* indices, float* weights,
+                              int* count, void* stream);
+int srf_ray_accumulate(const float* rgb_rows, const float* weights, const int* ray_offset, const int* ray_count,
+                       const float* acc, int64_t num_rays, int white_bkgd, float* rgb_map, void* stream);
+
 /* ---- "next" row f1: masks of the patch-reprojection depth losses
  * (src/loss_functions/AugmentationsDepthLoss11.py:105-182, src/loss_functions/CoarseFineConsistencyLoss34.py:89-164,
  * src/utils/CommonUtils04.py:227-253).  For each of num_rays image rays: the two candidate depths are reprojected into
@@ -248,6 +277,14 @@ int srf_patch_reprojection_masks(const float* rays_o, const float* rays_d, const
                                  const float* intrinsics_first, const float* images, int num_views, int height, int width,
                                  int patch_x, int patch_y, float rmse_threshold, int both_invalid_rule, uint8_t* mask1,
                                  uint8_t* mask2, float* rmse1, float* rmse2, void* stream);
+
+/* ---- "next" row f4: total-variation regulariser of VM planes, loss and gradient in one launch.  Replaces
+ * TotalVariationLoss04.compute_tv_loss (src/loss_functions/TotalVariationLoss04.py:97-116) and its autograd: for each of the
+ * num_planes (<= 12) planes [C,H,W] (dims = {C,H,W} per plane; device pointers in host arrays)
+ *   *loss += 2 * (sum_h (x[h+1]-x[h])^2 / max(C (H-1) W, 1) + sum_w (x[w+1]-x[w])^2 / max(C H (W-1), 1)) * iter_weight
+ * (double accumulator, device, caller-zeroed) and grads[i] = d(that plane's term) / d x. */
+int srf_tv_loss(const float* const* planes, float* const* grads, const int* dims, int num_planes, float iter_weight,
+                double* loss, void* stream);
 
 /* ---- "next" row f2: device-side batch assembly.  Replaces load_nerf_cached_batch /
  * load_sparse_depth_cached_batch (src/data_preprocessors/DataPreprocessor10.py:530-549, 568-595): row b takes the cached

@@ -87,3 +87,13 @@ def masked_depth_loss(depth1, depth2, mask1, mask2):
     zero = torch.zeros((), dtype=depth1.dtype)
     loss = (map1.mean() if depth1.numel() > 0 else zero) + (map2.mean() if depth1.numel() > 0 else zero)
     return loss, map1, map2
+
+
+def tv_loss(planes, iter_weight):
+    """src/loss_functions/TotalVariationLoss04.py:97-116 (compute_tv_loss) over a list of [1,C,H,W] planes."""
+    total = 0
+    for c in planes:
+        dh = torch.pow(c[:, :, 1:, :] - c[:, :, :-1, :], 2)
+        dw = torch.pow(c[:, :, :, 1:] - c[:, :, :, :-1], 2)
+        total = total + 2 * (dh.sum() / max(dh.numel(), 1) + dw.sum() / max(dw.numel(), 1)) * iter_weight
+    return total

@@ -36,7 +36,12 @@ _SIGNATURES = {
     'srf_compact': (c_int, [_P, c_int64, _P, _P, _P, _P, _P]),
     'srf_vm_density_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P]),
     'srf_vm_density_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P]),
-    'srf_vm_color_features_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    'srf_vm_color_features_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    'srf_tensorf_march': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float,
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'srf_tensorf_march_blocks': (c_int, [c_int64]),
+    'srf_tensorf_march_compact': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'srf_ray_accumulate': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P]),
     'srf_vm_color_features_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     'srf_scatter_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     'srf_gather_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
@@ -45,6 +50,7 @@ _SIGNATURES = {
     'srf_wgrad_item_bytes': (c_int, []),
     'srf_nerf_mlp_dgrad': (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_int, _P, c_int, _P]),
     'srf_dgrad_program_bytes': (c_int, []),
+    'srf_tv_loss': (c_int, [_P, _P, _P, c_int, c_float, _P, _P]),
     'srf_assemble_batch': (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_adam_step': (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
     'srf_frame_record_bytes': (c_int64, [c_int64, c_int]),

@@ -136,3 +136,75 @@ SRF_API int srf_patch_reprojection_masks(const float* rays_o, const float* rays_
   patch_reprojection_kernel<<<blocks, PATCH_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   return check_launch("srf_patch_reprojection_masks");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "Next" row f4: total-variation regulariser of the VM planes, forward AND gradient in one launch.
+//
+// Replaces TotalVariationLoss04.compute_tv_loss (src/loss_functions/TotalVariationLoss04.py:97-116) and what autograd derives
+// from it: per plane [1,C,H,W]   tv = 2 * (sum (x[h+1]-x[h])^2 / numel_h + sum (x[w+1]-x[w])^2 / numel_w) * iter_weight,
+// which eager PyTorch evaluates as ~25 launches per plane (2 slices, sub, pow, sum, div, and in the backward pass
+// pow-backward, two slice-backward zero fills + copies and the accumulations): ~300 launches for the 12 planes of the
+// shipped model pair, i.e. the training iteration is bound by the host's launch rate, not by the GPU.  Here every element is
+// read once with its right and lower neighbour; the loss is accumulated in double (atomics: the rounding of the fp32
+// result does not depend on the order) and the gradient  d tv / d x  is written in the same pass.
+namespace srf {
+
+struct TvPlane { const float* x; float* grad; int C, H, W; float scale_h, scale_w; };   // scale = 2 * iter_weight / numel
+struct TvParams { TvPlane plane[12]; int n; double* loss; };
+
+__global__ void __launch_bounds__(256) tv_loss_kernel(const TvParams p) {
+  const TvPlane t = p.plane[blockIdx.y];
+  const long long total = (long long)t.C * t.H * t.W;
+  double local = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(e % t.W);
+    const int h = (int)((e / t.W) % t.H);
+    const float x = t.x[e];
+    float g = 0.f;
+    if (h + 1 < t.H) { const float d = t.x[e + t.W] - x; local += (double)(t.scale_h * d * d); g -= 2.f * t.scale_h * d; }
+    if (h > 0) g += 2.f * t.scale_h * (x - t.x[e - t.W]);
+    if (w + 1 < t.W) { const float d = t.x[e + 1] - x; local += (double)(t.scale_w * d * d); g -= 2.f * t.scale_w * d; }
+    if (w > 0) g += 2.f * t.scale_w * (x - t.x[e - 1]);
+    t.grad[e] = g;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+  __shared__ double s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += s_part[k];
+    if (s != 0.0) atomicAdd(p.loss, s);
+  }
+}
+
+}  // namespace srf
+
+SRF_API int srf_tv_loss(const float* const* planes, float* const* grads, const int* dims, int num_planes, float iter_weight,
+                        double* loss, void* stream) {
+  using namespace srf;
+  if (num_planes == 0) return 0;
+  SRF_REQUIRE(planes && grads && dims && loss, "srf_tv_loss", "null pointer");
+  SRF_REQUIRE(num_planes <= 12, "srf_tv_loss", "at most 12 planes per call");
+  TvParams p{};
+  p.n = num_planes; p.loss = loss;
+  long long largest = 0;
+  for (int i = 0; i < num_planes; ++i) {
+    TvPlane& t = p.plane[i];
+    t.x = planes[i]; t.grad = grads[i]; t.C = dims[3 * i]; t.H = dims[3 * i + 1]; t.W = dims[3 * i + 2];
+    SRF_REQUIRE(t.x && t.grad && t.C > 0 && t.H > 0 && t.W > 0, "srf_tv_loss", "bad plane");
+    // numel of the difference tensors, at least 1 (:105-106); the factor 2 of matrix_tv_loss (:109) and iter_weight folded in
+    const double nh = (double)t.C * (t.H - 1) * t.W, nw = (double)t.C * t.H * (t.W - 1);
+    t.scale_h = (float)(2.0 * iter_weight / (nh < 1.0 ? 1.0 : nh));
+    t.scale_w = (float)(2.0 * iter_weight / (nw < 1.0 ? 1.0 : nw));
+    const long long total = (long long)t.C * t.H * t.W;
+    if (total > largest) largest = total;
+  }
+  long long bx = (largest + 255) / 256;
+  const long long cap = (long long)sm_count() * 4;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  tv_loss_kernel<<<dim3((unsigned)bx, (unsigned)num_planes), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("srf_tv_loss");
+}

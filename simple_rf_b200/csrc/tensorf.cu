@@ -13,8 +13,10 @@
 // is 1 bit per voxel (x fastest), i.e. L2/shared-memory sized, and the test reproduces ATen's grid_sampler_3d
 // coordinate arithmetic exactly, so mask and compaction order are bit-identical to the reference.
 #include <cuda_bf16.h>
+#include <limits.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "tensorf_common.cuh"
 
 namespace srf {
 
@@ -31,50 +33,6 @@ __global__ void pack_alpha_kernel(const float* __restrict__ vol, long long n, ui
     if (i < n && vol[i] > 0.f) word |= 1u << b;
   }
   bits[w] = word;
-}
-
-struct MaskParams {
-  const float* rays_o; const float* rays_d; const float* z;
-  const uint32_t* alpha_bits;          // nullptr: no alphaMask
-  uint8_t* mask; int* block_counts;
-  long long total; int S;
-  float bb0[3], bb1[3];                // tensor bounding box
-  float ab0[3], asize[3];              // alpha-volume box: min corner and size (fp32, as the reference stores them)
-  int ax, ay, az;                      // alpha-volume resolution
-};
-
-// trilinear grid_sample(align_corners=True, zero padding) of the {0,1} volume is > 0 iff some in-range corner with a
-// positive fp32 weight product holds a 1 (ATen's evaluation order for coordinates and weights is reproduced exactly)
-__device__ __forceinline__ bool alpha_hit(const MaskParams& p, const float (&pt)[3]) {
-  const int dims[3] = {p.ax, p.ay, p.az};
-  int i0[3];
-  float w[3][2];
-  bool cand[3][2];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    // normalise ((p - b0) / size) * 2 - 1  (:1347-1349), unnormalise ((c + 1) / 2) * (dim - 1) (ATen GridSampler.h);
-    // the division by 2 is an exact scaling, so a multiplication by 0.5 gives the same bits
-    const float c = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(pt[a], -p.ab0[a]), p.asize[a]), 2.f), -1.f);
-    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(c, 1.f), 0.5f), (float)(dims[a] - 1));
-    const float f0 = floorf(ix);
-    i0[a] = (int)f0;
-    w[a][0] = __fadd_rn(__fadd_rn(f0, 1.f), -ix);
-    w[a][1] = __fadd_rn(ix, -f0);
-    cand[a][0] = i0[a] >= 0 && i0[a] < dims[a] && w[a][0] > 0.f;
-    cand[a][1] = i0[a] + 1 >= 0 && i0[a] + 1 < dims[a] && w[a][1] > 0.f;
-  }
-  const int v0 = (i0[2] * p.ay + i0[1]) * p.ax + i0[0];        // < 2^31 voxels (checked by the host)
-  const int sy = p.ax, sz = p.ax * p.ay;
-  bool hit = false;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
-    if (!(cand[0][dx] && cand[1][dy] && cand[2][dz])) continue;
-    if (!(__fmul_rn(__fmul_rn(w[0][dx], w[1][dy]), w[2][dz]) > 0.f)) continue;      // the product itself may underflow to 0
-    const int v = v0 + dx + dy * sy + dz * sz;
-    hit |= (__ldg(p.alpha_bits + (v >> 5)) >> (v & 31)) & 1u;
-  }
-  return hit;
 }
 
 // thread = 4 consecutive samples (normally of one ray): one 16-byte depth load, one 4-byte mask store, ray origin and
@@ -237,94 +195,6 @@ __global__ void __launch_bounds__(256) compact_scatter_kernel(const uint8_t* __r
   if (f3) idx[before] = (int)(i0 + 3);
 }
 
-// ------------------------------------------------------------------------------------------ VM gathers
-struct VmGrid {
-  const float* plane[3];   // channels-last [H][W][C]
-  const float* line[3];    // [L][C]
-  int C[3];                // channels per plane/line pair (multiples of 4)
-  int res[3];              // tensor resolution (X, Y, Z)
-};
-
-struct VmGeom {
-  const float* rays_o; const float* rays_d; const float* z;
-  const int* idx; const int* count;
-  int S;
-  float bb0[3], bsize[3];
-};
-
-// matrix_axes = [[0,1],[0,2],[1,2]], vector_axes = [2,1,0]  (:1131-1132); grid x -> W = res[a0], y -> H = res[a1]
-// (functions, not __constant__ tables: after unrolling the axis is a compile-time constant and nothing is indexed dynamically)
-__host__ __device__ __forceinline__ constexpr int axis0(int i) { return i == 2 ? 1 : 0; }
-__host__ __device__ __forceinline__ constexpr int axis1(int i) { return i == 0 ? 1 : 2; }
-__host__ __device__ __forceinline__ constexpr int axisv(int i) { return 2 - i; }
-
-struct Bilerp {
-  int x0, y0, W, H;
-  float wx0, wx1, wy0, wy1;
-};
-
-__device__ __forceinline__ void normalized_point(const VmGeom& g, int flat, float (&pn)[3]) {
-  const int r = flat / g.S;
-  const float zz = g.z[flat];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float pt = __fadd_rn(g.rays_o[r * 3 + a], __fmul_rn(g.rays_d[r * 3 + a], zz));
-    pn[a] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(pt, -g.bb0[a]), g.bsize[a]), 2.f), -1.f);
-  }
-}
-
-__device__ __forceinline__ float unnorm(float c, int size) { return __fmul_rn(__fdiv_rn(__fadd_rn(c, 1.f), 2.f), (float)(size - 1)); }
-
-__device__ __forceinline__ Bilerp plane_coords(const float (&pn)[3], const int (&res)[3], int i) {
-  Bilerp b;
-  b.W = res[axis0(i)]; b.H = res[axis1(i)];
-  const float ix = unnorm(pn[axis0(i)], b.W), iy = unnorm(pn[axis1(i)], b.H);
-  const float fx = floorf(ix), fy = floorf(iy);
-  b.x0 = (int)fx; b.y0 = (int)fy;
-  b.wx1 = ix - fx; b.wx0 = (fx + 1.f) - ix;
-  b.wy1 = iy - fy; b.wy0 = (fy + 1.f) - iy;
-  return b;
-}
-
-// value of channel group [c, c+4) of a plane at the bilinear position (zeros outside, as grid_sample pads)
-__device__ __forceinline__ float4 plane_fetch4(const float* plane, const Bilerp& b, int C, int c) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
-    if (x < 0 || y < 0 || x >= b.W || y >= b.H) continue;
-    const float w = ((k & 1) ? b.wx1 : b.wx0) * ((k >> 1) ? b.wy1 : b.wy0);
-    const float4 t = __ldg(reinterpret_cast<const float4*>(plane + ((size_t)y * b.W + x) * C + c));
-    acc.x += t.x * w; acc.y += t.y * w; acc.z += t.z * w; acc.w += t.w * w;
-  }
-  return acc;
-}
-
-__device__ __forceinline__ void line_coords(const float (&pn)[3], const int (&res)[3], int i, int& l0, int& L, float& w0, float& w1) {
-  L = res[axisv(i)];
-  const float iy = unnorm(pn[axisv(i)], L);
-  const float fy = floorf(iy);
-  l0 = (int)fy;
-  w1 = iy - fy; w0 = (fy + 1.f) - iy;
-}
-
-__device__ __forceinline__ float4 line_fetch4(const float* line, int l0, int L, float w0, float w1, int C, int c) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (l0 >= 0 && l0 < L) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(line + (size_t)l0 * C + c));
-    acc.x += t.x * w0; acc.y += t.y * w0; acc.z += t.z * w0; acc.w += t.w * w0;
-  }
-  if (l0 + 1 >= 0 && l0 + 1 < L) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(line + (size_t)(l0 + 1) * C + c));
-    acc.x += t.x * w1; acc.y += t.y * w1; acc.z += t.z * w1; acc.w += t.w * w1;
-  }
-  return acc;
-}
-
-__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // density: sigma = act(sum_i sum_c plane_i,c * line_i,c); one thread per compacted sample
 __global__ void __launch_bounds__(256) vm_density_fwd_kernel(VmGeom g, VmGrid t, int softplus, float offset,
                                                              float* __restrict__ sigma, float* __restrict__ feat_out) {
@@ -395,6 +265,128 @@ __global__ void __launch_bounds__(256) vm_density_bwd_kernel(VmGeom g, VmGrid t,
   }
 }
 
+// ---- run-merged backward.  The per-SM issue rate of global reductions is the bound of the scatter (REDG: ~1.3 cycles per
+// lane and 32-bit value, i.e. ~165 cycles per warp-wide red.v4 — the six float4 loads and the arithmetic of a sample are noise
+// next to its six red.v4), so the lever is the NUMBER of reductions.  The compacted list is ray-major and consecutive samples of a
+// ray are half a voxel apart, so consecutive samples mostly share their bilinear footprint: in NDC the rays run along z, the
+// (x, y) plane — 16 of the 24 density channels — keeps the same 2x2 texels for 5-20 samples in a row.  A thread therefore owns
+// a RUN of K consecutive compacted samples and, per (plane, channel group), accumulates the four corner gradients (and the two
+// line gradients) in registers for as long as the footprint stays the same; it emits one red.v4 per corner per footprint
+// instead of one per corner per sample, and re-uses the loaded texels across the streak as well.
+struct Footprint {
+  int x0, y0, l0;
+  float wx0, wx1, wy0, wy1, wl0, wl1;       // the forward's weights, bit for bit: w1 = i - floor(i), w0 = (floor(i) + 1) - i
+};
+
+__device__ __forceinline__ Footprint footprint_of(const float (&pn)[3], const int (&res)[3], int i) {
+  Footprint f;
+  const int W = res[axis0(i)], H = res[axis1(i)], L = res[axisv(i)];
+  const float ix = unnorm(pn[axis0(i)], W), iy = unnorm(pn[axis1(i)], H), il = unnorm(pn[axisv(i)], L);
+  const float fx = floorf(ix), fy = floorf(iy), fl = floorf(il);
+  f.x0 = (int)fx; f.y0 = (int)fy; f.l0 = (int)fl;
+  f.wx1 = ix - fx; f.wy1 = iy - fy; f.wl1 = il - fl;
+  f.wx0 = (fx + 1.f) - ix; f.wy0 = (fy + 1.f) - iy; f.wl0 = (fl + 1.f) - il;
+  return f;
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float s, const float4& b) { a.x += s * b.x; a.y += s * b.y; a.z += s * b.z; a.w += s * b.w; }
+__device__ __forceinline__ bool f4_any(const float4& a) { return a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f; }
+
+template <int K>
+__global__ void __launch_bounds__(128) vm_density_bwd_runs_kernel(VmGeom g, VmGrid t, int softplus, float offset,
+                                                                  const float* __restrict__ g_sigma, const float* __restrict__ feat_in,
+                                                                  float* gp0, float* gp1, float* gp2, float* gl0, float* gl1, float* gl2) {
+  const int n = g.count[0];
+  const int nruns = (n + K - 1) / K;
+  for (int run = blockIdx.x * blockDim.x + threadIdx.x; run < nruns; run += gridDim.x * blockDim.x) {
+    const int j0 = run * K;
+    float pn[K][3], gf[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      gf[k] = 0.f;
+      pn[k][0] = pn[k][1] = pn[k][2] = 0.f;
+      if (j0 + k < n) {
+        const int flat = g.idx[j0 + k];
+        const float feat = feat_in[j0 + k];
+        float v = g_sigma[flat];
+        if (softplus) { const float x = feat + offset; v *= 1.f / (1.f + expf(-x)); }
+        else v = feat > 0.f ? v : 0.f;
+        gf[k] = v;
+        if (v != 0.f) { normalized_point(g, flat, pn[k]); any = true; }
+      }
+    }
+    if (!any) continue;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int C = t.C[i];
+      const int W = t.res[axis0(i)], H = t.res[axis1(i)], L = t.res[axisv(i)];
+      const float* plane = i == 0 ? t.plane[0] : (i == 1 ? t.plane[1] : t.plane[2]);
+      const float* line = i == 0 ? t.line[0] : (i == 1 ? t.line[1] : t.line[2]);
+      float* gplane = i == 0 ? gp0 : (i == 1 ? gp1 : gp2);
+      float* gline = i == 0 ? gl0 : (i == 1 ? gl1 : gl2);
+      for (int c = 0; c < C; c += 4) {
+        int kx = INT_MIN, ky = INT_MIN, kl = INT_MIN;             // footprint the accumulators belong to
+        float4 tex[4], acc[4], ltex[2], lacc[2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { tex[q] = f4_zero(); acc[q] = f4_zero(); }
+        ltex[0] = ltex[1] = lacc[0] = lacc[1] = f4_zero();
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+          const bool live = k < K && gf[k < K ? k : 0] != 0.f;
+          Footprint f;
+          if (live) f = footprint_of(pn[k < K ? k : 0], t.res, i);
+          const bool last = k == K;
+          if (!live && !last) continue;
+          if (last || f.x0 != kx || f.y0 != ky) {                // plane footprint changes: flush, then load the new texels
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int x = kx + (q & 1), y = ky + (q >> 1);
+              if (kx != INT_MIN && x >= 0 && y >= 0 && x < W && y < H && f4_any(acc[q]))
+                red_add4(gplane + ((size_t)y * W + x) * C + c, acc[q].x, acc[q].y, acc[q].z, acc[q].w);
+              acc[q] = f4_zero();
+            }
+            if (!last) {
+              kx = f.x0; ky = f.y0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int x = kx + (q & 1), y = ky + (q >> 1);
+                tex[q] = (x >= 0 && y >= 0 && x < W && y < H) ? ldg4(plane + ((size_t)y * W + x) * C + c) : f4_zero();
+              }
+            }
+          }
+          if (last || f.l0 != kl) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int l = kl + q;
+              if (kl != INT_MIN && l >= 0 && l < L && f4_any(lacc[q])) red_add4(gline + (size_t)l * C + c, lacc[q].x, lacc[q].y, lacc[q].z, lacc[q].w);
+              lacc[q] = f4_zero();
+            }
+            if (!last) {
+              kl = f.l0;
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int l = kl + q;
+                ltex[q] = (l >= 0 && l < L) ? ldg4(line + (size_t)l * C + c) : f4_zero();
+              }
+            }
+          }
+          if (last) continue;
+          const float gk = gf[k < K ? k : 0];
+          const float wl0 = f.wl0;
+          const float w00 = f.wx0 * f.wy0, w10 = f.wx1 * f.wy0, w01 = f.wx0 * f.wy1, w11 = f.wx1 * f.wy1;
+          float4 pv = f4_zero(), lv = f4_zero();
+          f4_fma(pv, w00, tex[0]); f4_fma(pv, w10, tex[1]); f4_fma(pv, w01, tex[2]); f4_fma(pv, w11, tex[3]);
+          f4_fma(lv, wl0, ltex[0]); f4_fma(lv, f.wl1, ltex[1]);
+          f4_fma(acc[0], gk * w00, lv); f4_fma(acc[1], gk * w10, lv); f4_fma(acc[2], gk * w01, lv); f4_fma(acc[3], gk * w11, lv);
+          f4_fma(lacc[0], gk * wl0, pv); f4_fma(lacc[1], gk * f.wl1, pv);
+        }
+      }
+    }
+  }
+}
+
 // appearance: products (plane x line) over all channels -> bf16 rows of `pitch` elements
 // [products (CT = sum C) | view_dirs (3) | zero pad]: the A operand of the tensor-core colour MLP, whose first layer
 // absorbs basis_matrix_color (W0' = [W0[:, :F] B | W0[:, F:]]), so no matrix-vector product is left in this kernel.
@@ -443,7 +435,6 @@ __device__ __forceinline__ uint32_t ptx_pack_bf16(float lo, float hi) {
   return r;
 }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // plane and line values of one 4-channel group at one sample
 __device__ __forceinline__ void fetch_group(const VmGrid& t, const SampleRec& r, int i, int c, float4& pv, float4& lv, int4& po, float4& pw,
@@ -536,6 +527,96 @@ __global__ void __launch_bounds__(CF_WARPS * 32) vm_color_features_bwd_kernel(Vm
   }
 }
 
+// run-merged appearance backward (see vm_density_bwd_runs_kernel for the reasoning: the scatter is bound by the number of
+// global reductions, and consecutive compacted samples share their bilinear footprints).  A warp takes 64 consecutive
+// samples: their records go to shared memory (lane per sample, two rounds), then a lane owns a (run of 8 samples, 4-channel
+// group) item and walks the run with the four corner gradients + two line gradients in registers, emitting reductions only
+// when the footprint changes.  18 groups x 8 runs = 144 items per 64 samples (4.5 rounds of 32 lanes).
+constexpr int CB_WARPS = 4, CB_SAMPLES = 64;
+
+template <int CB_K>
+__global__ void __launch_bounds__(CB_WARPS * 32) vm_color_features_bwd_runs_kernel(VmGeom g, VmGrid t, GroupMap m, const float* __restrict__ g_rows,
+                                                                                   int pitch, float* gp0, float* gp1, float* gp2, float* gl0,
+                                                                                   float* gl1, float* gl2) {
+  __shared__ SampleRec s_rec[CB_WARPS][CB_SAMPLES];
+  const int n = g.count[0];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CB_WARPS + warp, nw = gridDim.x * CB_WARPS;
+  for (int base = gw * CB_SAMPLES; base < n; base += nw * CB_SAMPLES) {
+    const int cnt = min(CB_SAMPLES, n - base);
+    for (int sidx = lane; sidx < cnt; sidx += 32) compute_record(g, t, g.idx[base + sidx], s_rec[warp][sidx]);
+    __syncwarp();
+    const int nrun = (cnt + CB_K - 1) / CB_K;
+    for (int item = lane; item < nrun * m.G; item += 32) {
+      const int run = (int)(((unsigned)item * m.inv) >> 16);          // m.inv describes G groups per run here
+      const int gq = item - run * m.G;
+      const int i = (gq >= m.g0) + (gq >= m.g1);
+      const int c = (gq - (i == 0 ? 0 : (i == 1 ? m.g0 : m.g1))) << 2;
+      const float* pl = (i == 0 ? t.plane[0] : (i == 1 ? t.plane[1] : t.plane[2])) + c;
+      const float* ln = (i == 0 ? t.line[0] : (i == 1 ? t.line[1] : t.line[2])) + c;
+      float* gpl = (i == 0 ? gp0 : (i == 1 ? gp1 : gp2)) + c;
+      float* gln = (i == 0 ? gl0 : (i == 1 ? gl1 : gl2)) + c;
+      int4 kpo = make_int4(-1, -1, -1, -1);
+      int kl0 = -1, kl1 = -1;
+      float4 tex[4], acc[4], ltex[2], lacc[2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { tex[q] = f4_zero(); acc[q] = f4_zero(); }
+      ltex[0] = ltex[1] = lacc[0] = lacc[1] = f4_zero();
+#pragma unroll
+      for (int k = 0; k <= CB_K; ++k) {
+        const int sidx = run * CB_K + k;
+        const bool last = k == CB_K || sidx >= cnt;
+        float4 go = f4_zero();
+        int4 po = kpo, lr = make_int4(kl0, kl1, 0, 0);
+        float4 pw = f4_zero();
+        if (!last) {
+          go = ldg4(g_rows + (size_t)(base + sidx) * pitch + gq * 4);
+          if (!f4_any(go)) continue;
+          const SampleRec& r = s_rec[warp][sidx];
+          po = *reinterpret_cast<const int4*>(r.poff[i]);
+          pw = *reinterpret_cast<const float4*>(r.pw[i]);
+          lr = *reinterpret_cast<const int4*>(r.line[i]);
+        }
+        if (last || po.x != kpo.x || po.y != kpo.y || po.z != kpo.z || po.w != kpo.w) {
+          if (kpo.x >= 0) {
+            if (f4_any(acc[0])) red_add4(gpl + kpo.x, acc[0].x, acc[0].y, acc[0].z, acc[0].w);
+            if (f4_any(acc[1])) red_add4(gpl + kpo.y, acc[1].x, acc[1].y, acc[1].z, acc[1].w);
+            if (f4_any(acc[2])) red_add4(gpl + kpo.z, acc[2].x, acc[2].y, acc[2].z, acc[2].w);
+            if (f4_any(acc[3])) red_add4(gpl + kpo.w, acc[3].x, acc[3].y, acc[3].z, acc[3].w);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = f4_zero();
+          if (!last) {
+            kpo = po;
+            tex[0] = ldg4(pl + po.x); tex[1] = ldg4(pl + po.y); tex[2] = ldg4(pl + po.z); tex[3] = ldg4(pl + po.w);
+          }
+        }
+        if (last || lr.x != kl0 || lr.y != kl1) {
+          if (kl0 >= 0) {
+            if (f4_any(lacc[0])) red_add4(gln + kl0, lacc[0].x, lacc[0].y, lacc[0].z, lacc[0].w);
+            if (f4_any(lacc[1])) red_add4(gln + kl1, lacc[1].x, lacc[1].y, lacc[1].z, lacc[1].w);
+          }
+          lacc[0] = lacc[1] = f4_zero();
+          if (!last) {
+            kl0 = lr.x; kl1 = lr.y;
+            ltex[0] = ldg4(ln + lr.x); ltex[1] = ldg4(ln + lr.y);
+          }
+        }
+        if (last) break;
+        const float w0 = __int_as_float(lr.z), w1 = __int_as_float(lr.w);
+        float4 pv = f4_zero(), lv = f4_zero();
+        f4_fma(pv, pw.x, tex[0]); f4_fma(pv, pw.y, tex[1]); f4_fma(pv, pw.z, tex[2]); f4_fma(pv, pw.w, tex[3]);
+        f4_fma(lv, w0, ltex[0]); f4_fma(lv, w1, ltex[1]);
+        const float4 gpv = make_float4(go.x * lv.x, go.y * lv.y, go.z * lv.z, go.w * lv.w);
+        const float4 glv = make_float4(go.x * pv.x, go.y * pv.y, go.z * pv.z, go.w * pv.w);
+        f4_fma(acc[0], pw.x, gpv); f4_fma(acc[1], pw.y, gpv); f4_fma(acc[2], pw.z, gpv); f4_fma(acc[3], pw.w, gpv);
+        f4_fma(lacc[0], w0, glv); f4_fma(lacc[1], w1, glv);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // scatter compacted rows [n, width] back to the dense [total, width] tensor (the reference's rgb[mask] = ..., :1271)
 __global__ void scatter_rows_kernel(const int* __restrict__ idx, const int* __restrict__ count, const float* __restrict__ src,
                                     int width, float* __restrict__ dst) {
@@ -621,7 +702,7 @@ SRF_API int srf_compact(const uint8_t* mask, int64_t total, int* block_counts, i
 namespace {
 int fill_geom(VmGeom& g, const float* rays_o, const float* rays_d, const float* z, const int* idx, const int* count, int S,
               const float* box_min, const float* box_size) {
-  g.rays_o = rays_o; g.rays_d = rays_d; g.z = z; g.idx = idx; g.count = count; g.S = S;
+  g.rays_o = rays_o; g.rays_d = rays_d; g.z = z; g.idx = idx; g.count = count; g.S = S; g.z_shared = 0;
   for (int a = 0; a < 3; ++a) { g.bb0[a] = box_min[a]; g.bsize[a] = box_size[a]; }
   return 0;
 }
@@ -658,8 +739,25 @@ SRF_API int srf_vm_density_bwd(const float* rays_o, const float* rays_d, const f
   VmGeom g; VmGrid t;
   fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_density_bwd")) return 1;
-  vm_density_bwd_kernel<<<blocks_for(max_count, 256), 256, 0, (cudaStream_t)stream>>>(
-      g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  // run length K of the run-merged scatter, measured on the 331x368x220 training step (profiles/r02_tensorf_scatter.md):
+  // one thread per sample (r1) 1.05 ms, K = 4: 0.41 ms, K = 8: 0.45 ms, K = 16: 0.58 ms (longer runs merge more but leave fewer threads)
+  static const int variant = getenv("SRF_VM_BWD_VARIANT") ? atoi(getenv("SRF_VM_BWD_VARIANT")) : 4;     // 0: one thread per sample (r1)
+  if (variant == 0) {
+    vm_density_bwd_kernel<<<blocks_for(max_count, 256), 256, 0, (cudaStream_t)stream>>>(
+        g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  } else if (variant == 16) {
+    vm_density_bwd_runs_kernel<16><<<blocks_for((max_count + 15) / 16, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+        g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  } else if (variant == 2) {
+    vm_density_bwd_runs_kernel<2><<<blocks_for((max_count + 1) / 2, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+        g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  } else if (variant == 4) {
+    vm_density_bwd_runs_kernel<4><<<blocks_for((max_count + 3) / 4, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+        g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  } else {
+    vm_density_bwd_runs_kernel<8><<<blocks_for((max_count + 7) / 8, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+        g, t, softplus, density_offset, g_sigma, features, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  }
   return check_launch("srf_vm_density_bwd");
 }
 
@@ -675,11 +773,13 @@ static int fill_groups(GroupMap& m, const int* channels, int groups_per_row, con
 SRF_API int srf_vm_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
                                       const int* count, int64_t max_count, const float* box_min, const float* box_size,
                                       const float* const* planes, const float* const* lines, const int* channels,
-                                      const int* resolution, const float* view_dirs, void* rows, int row_pitch, void* stream) {
+                                      const int* resolution, const float* view_dirs, void* rows, int row_pitch, int z_is_ladder,
+                                      void* stream) {
   if (max_count == 0) return 0;
   SRF_REQUIRE(rays_o && rays_d && z && indices && count && view_dirs && rows, "srf_vm_color_features_fwd", "null pointer");
   VmGeom g; VmGrid t; GroupMap m;
   fill_geom(g, rays_o, rays_d, z, indices, count, num_samples, box_min, box_size);
+  g.z_shared = z_is_ladder ? 1 : 0;
   if (fill_grid(t, planes, lines, channels, resolution, "srf_vm_color_features_fwd")) return 1;
   SRF_REQUIRE(row_pitch % 8 == 0 && row_pitch <= 128, "srf_vm_color_features_fwd", "row_pitch must be a multiple of 8, <= 128");
   if (fill_groups(m, channels, row_pitch / 4, "srf_vm_color_features_fwd")) return 1;
@@ -703,8 +803,18 @@ SRF_API int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, 
   SRF_REQUIRE(CT <= 128 && g_row_pitch >= CT && g_row_pitch % 4 == 0, "srf_vm_color_features_bwd",
               "need sum(C) <= 128 and a pitch >= sum(C) that is a multiple of 4");
   if (fill_groups(m, channels, CT / 4, "srf_vm_color_features_bwd")) return 1;
-  vm_color_features_bwd_kernel<<<blocks_for(max_count, CF_WARPS * 32, 16), CF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      g, t, m, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  static const int variant = getenv("SRF_VM_BWD_VARIANT") ? atoi(getenv("SRF_VM_BWD_VARIANT")) : 8;     // 0: one (sample, group) item per lane (r1)
+  static const int color_k = getenv("SRF_VM_CBWD_K") ? atoi(getenv("SRF_VM_CBWD_K")) : 8;
+  if (variant == 0) {
+    vm_color_features_bwd_kernel<<<blocks_for(max_count, CF_WARPS * 32, 16), CF_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        g, t, m, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  } else if (color_k == 4) {
+    vm_color_features_bwd_runs_kernel<4><<<blocks_for(max_count, CB_WARPS * CB_SAMPLES, 12), CB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        g, t, m, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  } else {
+    vm_color_features_bwd_runs_kernel<8><<<blocks_for(max_count, CB_WARPS * CB_SAMPLES, 12), CB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        g, t, m, g_rows, g_row_pitch, g_planes[0], g_planes[1], g_planes[2], g_lines[0], g_lines[1], g_lines[2]);
+  }
   return check_launch("srf_vm_color_features_bwd");
 }
 

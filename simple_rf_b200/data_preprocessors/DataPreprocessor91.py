@@ -57,20 +57,25 @@ class DataPreprocessor(_ReferenceDataPreprocessor):
         the drop-in models use it to consume THEIR rows of the single global CPU random stream (App. B), which makes a
         multi-rank run reproduce the single-GPU batch statistics exactly."""
         from .. import parallel
-        if image_num is not None or not parallel.is_distributed():
+        import numpy
+        if image_num is not None:
             return super().select_batch_indices(iter_num, image_num)
+        if not parallel.is_distributed():
+            n_img = len(self.preprocessed_data_dict['indices'][self.i_batch: self.i_batch + self.num_rays])
+            d = super().select_batch_indices(iter_num, image_num)
+            return self._with_rows(d, n_img, int(d['indices'].shape[0]))
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
         mode = self.configs['data_loader'].get('rank_sharding', 'strong')
         if mode == 'weak':
             picked = None
             for r in range(world):
+                n_img = len(self.preprocessed_data_dict['indices'][self.i_batch: self.i_batch + self.num_rays])
                 d = super().select_batch_indices(iter_num, image_num)
                 if r == rank:
-                    picked = d
+                    picked = self._with_rows(d, n_img, int(d['indices'].shape[0]))
             return picked
         # block sizes from the host-side index arrays (the masks live on the device: reading them would synchronise)
-        import numpy
         n_img = len(self.preprocessed_data_dict['indices'][self.i_batch: self.i_batch + self.num_rays])
         d = super().select_batch_indices(iter_num, image_num)
         n_all = int(d['indices'].shape[0])
@@ -82,7 +87,21 @@ class DataPreprocessor(_ReferenceDataPreprocessor):
         rows_dev = torch.from_numpy(rows).to(d['indices'].device)
         out = {k: (v[rows_dev] if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
         out['srf_shard'] = (rank, world, n_all, rows)
-        return out
+        return self._with_rows(out, len(parts[0]), len(rows))
+
+    def _with_rows(self, d, n_img, n_all):
+        """`srf_rows`: the row indices of the image rays / sparse-depth rays of the batch (they are [0, n_img) and [n_img, n_all)
+        by construction, :520-521) as device index tensors, so the fused losses can index_select instead of boolean-mask
+        indexing, which synchronises the stream once per indexed tensor.  Only when the batch is one sub-batch (the trainer
+        slices tensors per sub-batch, src/Trainer10.py:88-96)."""
+        if n_all <= self.configs.get('sub_batch_size', n_all):
+            dev = d['indices'].device
+            cache = getattr(self, '_srf_rows_cache', None)
+            if cache is None or cache[0] != (n_img, n_all, dev):
+                cache = ((n_img, n_all, dev), {'nerf': torch.arange(0, n_img, device=dev), 'sparse_depth': torch.arange(n_img, n_all, device=dev)})
+                self._srf_rows_cache = cache
+            d['srf_rows'] = dict(cache[1])
+        return d
 
     # ------------------------------------------------------------------ output tail (SURVEY.md §8 f4)
     def retrieve_inference_outputs(self, network_outputs: dict):

@@ -115,7 +115,8 @@ def load_shipped_configs(train_num, scene=None):
 
 
 DROPIN_NAMES = {'SimpleNeRF17': 'SimpleNeRF91', 'SimpleTensoRF09': 'SimpleTensoRF91', 'DataPreprocessor10': 'DataPreprocessor91',
-                'AugmentationsDepthLoss11': 'AugmentationsDepthLoss91', 'CoarseFineConsistencyLoss34': 'CoarseFineConsistencyLoss91'}
+                'AugmentationsDepthLoss11': 'AugmentationsDepthLoss91', 'CoarseFineConsistencyLoss34': 'CoarseFineConsistencyLoss91',
+                'TotalVariationLoss04': 'TotalVariationLoss91'}
 
 
 def use_dropin(configs, preprocessor=True, losses=True):

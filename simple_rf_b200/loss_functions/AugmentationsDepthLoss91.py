@@ -5,7 +5,7 @@ from pathlib import Path
 
 import torch
 
-from .patch_reprojection import consistency_loss_nerf
+from .patch_reprojection import batch_rows as _rows, consistency_loss_nerf
 
 this_filename = Path(__file__).stem
 
@@ -21,7 +21,7 @@ class AugmentationsDepthLoss:
         self.rmse_threshold = self.loss_configs['rmse_threshold']
 
     def compute_loss(self, input_dict: dict, output_dict: dict, model, return_loss_maps: bool = False):
-        total_loss = torch.tensor(0).to(input_dict['target_rgb'])
+        total_loss = torch.zeros((), dtype=input_dict['target_rgb'].dtype, device=input_dict['target_rgb'].device)   # no pageable host->device copy
         loss_maps = {}
         common = (input_dict['indices_mask_nerf'], output_dict['rays_o'], output_dict['rays_d'], output_dict['extrinsics_all'].detach(),
                   input_dict['common_data']['images'], input_dict['pixel_id'], output_dict['intrinsics'].detach())
@@ -35,7 +35,7 @@ class AugmentationsDepthLoss:
                         continue
                     name = aug['name']
                     loss, map1, map2 = consistency_loss_nerf(depth_main, output_dict[f'{name}_depth_{stage}'], *common, self.patch_size,
-                                                             self.rmse_threshold, both_invalid_rule=True)
+                                                             self.rmse_threshold, both_invalid_rule=True, rows_nerf=_rows(input_dict, 'nerf'))
                     total_loss = total_loss + loss
                     if return_loss_maps:
                         loss_maps[f'{this_filename}_{name}_{stage}_main'] = map1

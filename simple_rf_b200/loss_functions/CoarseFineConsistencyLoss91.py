@@ -5,7 +5,7 @@ from pathlib import Path
 
 import torch
 
-from .patch_reprojection import consistency_loss_nerf
+from .patch_reprojection import batch_rows as _rows, consistency_loss_nerf
 
 this_filename = Path(__file__).stem
 
@@ -21,19 +21,25 @@ class CoarseFineConsistencyLoss:
         self.rmse_threshold = self.loss_configs['rmse_threshold']
 
     def compute_loss(self, input_dict: dict, output_dict: dict, model, return_loss_maps: bool = False) -> dict:
-        total_loss = torch.tensor(0).to(input_dict['target_rgb'])
+        total_loss = torch.zeros((), dtype=input_dict['target_rgb'].dtype, device=input_dict['target_rgb'].device)   # no pageable host->device copy
         if not self.coarse_model_needed or not self.fine_model_needed:
             return {'loss_value': total_loss}
         depth_coarse, depth_fine = output_dict['depth_coarse'], output_dict['depth_fine']
         loss, map_coarse, map_fine = consistency_loss_nerf(
             depth_coarse, depth_fine, input_dict['indices_mask_nerf'], output_dict['rays_o'], output_dict['rays_d'],
             output_dict['extrinsics_all'].detach(), input_dict['common_data']['images'], input_dict['pixel_id'],
-            output_dict['intrinsics'].detach(), self.patch_size, self.rmse_threshold, both_invalid_rule=False)
+            output_dict['intrinsics'].detach(), self.patch_size, self.rmse_threshold, both_invalid_rule=False,
+            rows_nerf=_rows(input_dict, 'nerf'))
         total_loss = total_loss + loss
         map_sd = None
         if self.sparse_depth_needed:                     # CoarseFineConsistencyLoss34.py:170-187: the fine depth supervises the coarse one
             mask_sd = input_dict.get('indices_mask_sparse_depth', None)
-            if mask_sd is not None:
+            rows_sd = _rows(input_dict, 'sparse_depth')
+            if rows_sd is not None:
+                map_sd = torch.square(depth_coarse.index_select(0, rows_sd) - depth_fine.index_select(0, rows_sd).detach())
+                if map_sd.numel() > 0:
+                    total_loss = total_loss + map_sd.mean()
+            elif mask_sd is not None:
                 map_sd = torch.square(depth_coarse[mask_sd] - depth_fine[mask_sd].detach())
                 if map_sd.numel() > 0:
                     total_loss = total_loss + map_sd.mean()

@@ -54,11 +54,25 @@ def masked_depth_loss(depth1, depth2, mask1, mask2):
     return map1.mean() + map2.mean(), map1, map2
 
 
+def batch_rows(input_dict, kind):
+    """Row indices of the image rays ('nerf') / sparse-depth rays of the batch when the preprocessor supplied them
+    (`srf_rows` = {'nerf': int64 tensor, 'sparse_depth': int64 tensor}, DataPreprocessor91), else None."""
+    rows = input_dict.get('srf_rows')
+    if rows is None:
+        return None
+    return rows.get(kind)
+
+
 def consistency_loss_nerf(depth1, depth2, indices_mask_nerf, rays_o, rays_d, poses, images, pixel_ids, intrinsics, patch_size,
-                          rmse_threshold, both_invalid_rule):
-    """`compute_loss_nerf` of both reference losses: image rays only (indices_mask_nerf), masks from the fused kernel."""
-    m = indices_mask_nerf
-    d1, d2 = depth1[m], depth2[m]
-    mask1, mask2 = patch_reprojection_masks(rays_o[m], rays_d[m], d1, d2, pixel_ids[m], poses, intrinsics[0], images, patch_size,
+                          rmse_threshold, both_invalid_rule, rows_nerf=None):
+    """`compute_loss_nerf` of both reference losses: image rays only (indices_mask_nerf), masks from the fused kernel.
+    rows_nerf: optional int64 row indices equivalent to the mask (DataPreprocessor91 knows them on the host) — boolean-mask
+    indexing has to read the mask's population count back, i.e. synchronises the stream once per indexed tensor."""
+    if rows_nerf is not None:
+        sel = lambda t: t.index_select(0, rows_nerf)
+    else:
+        sel = lambda t: t[indices_mask_nerf]
+    d1, d2 = sel(depth1), sel(depth2)
+    mask1, mask2 = patch_reprojection_masks(sel(rays_o), sel(rays_d), d1, d2, sel(pixel_ids), poses, intrinsics[0], images, patch_size,
                                             rmse_threshold, both_invalid_rule)
     return masked_depth_loss(d1, d2, mask1, mask2)

@@ -189,6 +189,12 @@ class SimpleTensoRF(torch.nn.Module):
         S = main.host_geometry()['num_samples']
         ladder = coarse_ladder_on(dev, S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp'])
         perturb = self.training and mc['perturb']
+        # test time without per-sample outputs: the depths are ONE ladder for all rays -> fused march, z[R,S] never materialised
+        if not self.training and not retraw and not torch.is_grad_enabled() and mc.get('fused_eval', True):
+            rays = dict(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=o_ndc, rays_d_ndc=d_ndc, view_dirs=view_dirs, z=None, ladder=ladder)
+            for k, v in main(rays, False, white_bkgd=mc['white_bkgd']).items():
+                out[f'{k}_coarse'] = v
+            return out
         from .. import parallel
         shard = input_dict.get('srf_shard') if self.training else None
         if perturb and self.rng_mode == 'reference':
@@ -401,8 +407,26 @@ class VmDecomposedTensor(torch.nn.Module):
         hg = self.host_geometry()
         return T.VmGeometry(rays_o_s, rays_d_s, z, hg['box_min'], hg['box_size'], hg['res'])
 
+    def forward_fused_eval(self, rays: dict, white_bkgd=False):
+        """LowRankTensor.forward (:701-761) at test time through the fused march (csrc/tensorf_march.cu): per-ray maps and the
+        surface list in one pass over the shared depth ladder, colour on the surface samples, per-ray accumulation."""
+        tc = self.tensor_configs
+        hg = self.host_geometry()
+        alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
+        m = T.march(rays['rays_o_ndc'], rays['rays_d_ndc'], rays['rays_o'], rays['rays_d'], rays['ladder'], hg['box'], hg['box_size'], alpha,
+                    list(self.matrices_density), list(self.vectors_density), hg['res'], softplus=self.density_predictor == 'SoftPlus',
+                    offset=tc['density_offset'], distance_scale=tc['distance_scale'], threshold=tc['ray_marching_weight_threshold'])
+        geom = T.VmGeometry(rays['rays_o_ndc'], rays['rays_d_ndc'], rays['ladder'], hg['box_min'], hg['box_size'], hg['res'])
+        rows, _ = T.vm_color_rows(geom, m.surface, rays['view_dirs'], list(self.matrices_color), list(self.vectors_color))
+        rgb_rows = self.color_predictor.packed(self.basis_matrix_color.weight).forward(rows, m.surface.count, rows.shape[0])
+        out = dict(m.maps)
+        out['rgb'] = T.ray_accumulate(rgb_rows, m, white_bkgd)
+        return out
+
     def forward(self, rays: dict, retraw: bool, white_bkgd=False):
         tc = self.tensor_configs
+        if rays.get('z') is None:
+            return self.forward_fused_eval(rays, white_bkgd=white_bkgd)
         z = rays['z']
         R, S = z.shape
         so, sd = rays['rays_o_ndc'], rays['rays_d_ndc']

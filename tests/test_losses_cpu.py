@@ -48,3 +48,16 @@ def test_dropin_losses_refuse_cpu(golden):
     with pytest.raises(RuntimeError):
         PR.patch_reprojection_masks(g['rays_o'], g['rays_d'], g['depth1'], g['depth2'], g['pixel_id'], g['poses'], g['k'], g['images'],
                                     (5, 5), 0.1, True)
+
+
+@pytest.mark.needs_reference
+def test_oracle_tv_loss_equals_reference_class():
+    """oracle.losses.tv_loss against TotalVariationLoss04.compute_tv_loss (static, src/loss_functions/TotalVariationLoss04.py:97)."""
+    from oracle import losses as OL
+    from oracle import reference_harness as H
+    H.import_reference()
+    from loss_functions.TotalVariationLoss04 import TotalVariationLoss
+    g = torch.Generator().manual_seed(0)
+    planes = [torch.randn(1, 4, 13, 17, generator=g), torch.randn(1, 12, 1, 6, generator=g), torch.randn(1, 6, 9, 1, generator=g)]
+    ref = TotalVariationLoss.compute_tv_loss(planes, 0.3, False)['loss_value']
+    assert torch.equal(torch.as_tensor(ref), torch.as_tensor(OL.tv_loss(planes, 0.3)))
