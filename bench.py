@@ -329,7 +329,7 @@ def synthetic_batch(rays_img, rays_sd, num_views, h, w, device, seed):
             'iter_num': 0, 'sub_batch_index': 0}
 
 
-def train_workload(kind, dist, scaling, steps=20, warmup=4):
+def train_workload(kind, dist, scaling, steps=20, warmup=4, use_graph=True):
     """One optimiser step per STEP: forward of every model of the shipped training config + the four (five) reference-shaped
     loss terms + hand-written backward + ONE all-reduce of the flat gradient bucket + fused Adam.  weak: 2048 + 2048 rays per
     rank; strong: 2048 + 2048 rays over all ranks."""
@@ -363,18 +363,30 @@ def train_workload(kind, dist, scaling, steps=20, warmup=4):
     images = torch.rand(3, h, w, 3, generator=torch.Generator().manual_seed(5)).to(device)
     losses = reference_shaped_losses(kind, cfg, images, (h, w))
 
-    def step(i):
+    def step(i=None):
         opt.zero_grad(set_to_none=True)
         out = model(batch)
-        losses(batch, out, model).backward()
+        loss = losses(batch, out, model)
+        loss.backward()
         opt.step()
+        return loss
 
-    ms, _, launches = timed_steps(dist, step, steps, warmup)                      # the reported rate: no per-launch events
+    ms_eager, _, launches = timed_steps(dist, step, steps, warmup)                # one launch per kernel: bound by the host's issue rate
     ms_prof, timing, _ = timed_steps(dist, step, steps, 1, collect=True)          # second pass: per-launch CUDA events for the rooflines
+    ms, graphed, graph_error = ms_eager, False, None
+    if use_graph:
+        try:                                                                      # the whole iteration as ONE CUDA graph (train_graph.py)
+            from simple_rf_b200.train_graph import GraphedStep
+            g = GraphedStep(step, {'optimizer_nerf': opt}, warmup=2)
+            ms, _, _ = timed_steps(dist, lambda i: g.replay(), steps, warmup)
+            graphed = True
+        except Exception as e:
+            graph_error = repr(e)[:300]
     table = kernel_table(timing)
     ms_it = ms / steps
     peaks = measured_peaks()
     res = {'metric': 'train_iters_per_sec', 'value': 1e3 / ms_it, 'unit': 'it/s', 'ms_per_step': ms_it, 'steps': steps, 'warmup': warmup,
+           'cuda_graph': graphed, 'ms_per_step_eager': ms_eager / steps, 'cuda_graph_error': graph_error,
            'scaling': scaling, 'n_gpus': dist.world, 'rays_per_iter_per_gpu': 2 * per_rank, 'global_rays_per_iter': 2 * per_rank * dist.world,
            'rays_per_sec': 2 * per_rank * dist.world * 1e3 / ms_it, 'gpu_launches_per_step': launches / steps,
            'losses': 'MSE + sparse-depth MSE + AugmentationsDepthLoss91 + ' + ('CoarseFineConsistencyLoss91' if kind == 'nerf' else 'TV'),

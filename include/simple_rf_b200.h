@@ -318,6 +318,13 @@ int srf_frame_outputs(const float* rgb, const float* depth, const float* depth_v
 int srf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
+/* Capturable form of the same step (what torch.optim.Adam(capturable=True) provides): the step count (int64, device) and the
+ * learning rate (fp32, device) are read by the kernel, so a CUDA graph holding `srf_adam_advance` (step += 1) followed by
+ * `srf_adam_step_capturable` replays correctly; bias corrections are evaluated in double on the device. */
+int srf_adam_advance(int64_t* step, void* stream);
+int srf_adam_step_capturable(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                             float beta1, float beta2, float eps, float weight_decay, const int64_t* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ _SIGNATURES = {
     'srf_adam_step': (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
     'srf_frame_record_bytes': (c_int64, [c_int64, c_int]),
     'srf_frame_outputs': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P]),
+    'srf_adam_advance': (c_int, [_P, _P]),
+    'srf_adam_step_capturable': (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, _P]),
     'srf_composite_bwd': (c_int, [_P] * 17 + [c_int64, c_int, c_int, c_int, c_float, _P, _P, _P]),
 }
 

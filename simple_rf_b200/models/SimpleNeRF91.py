@@ -12,7 +12,8 @@ checkpoints interchange.  All per-ray arithmetic runs in hand-written CUDA kerne
 Random numbers: in `rng_mode='reference'` (default) the stratified jitter, the sigma noise and the
 inverse-CDF draws are taken from the CPU default generator in the reference's order
 and uploaded, so seeded runs reproduce the reference's samples; `rng_mode='device'` draws them on the
-GPU (Philox) and is not seed-compatible.
+GPU (torch's CUDA generator: no host->device copies, capturable in a CUDA graph, see train_graph.py) and is not
+seed-compatible.
 """
 import numpy
 import torch
@@ -195,8 +196,8 @@ class SimpleNeRF(torch.nn.Module):
         def cpu_draw(draw):                      # the reference's CPU draw for R rays (this rank's rows of it on several ranks)
             return parallel.rows_of_global_draw(draw, R, shard, mc['chunk']).to(dev)
 
-        def device_seed():
-            return parallel.rank_seed(int(torch.randint(0, 2 ** 31, (1,)).item()))
+        if self.rng_mode != 'reference':
+            parallel.decorrelate_device_rng()
         aug_active = self.augmentations_needed and self.training and (mode != 'test_camera_params_optimization')
 
         def run(model, z, tag, prefix=''):
@@ -222,7 +223,7 @@ class SimpleNeRF(torch.nn.Module):
             if perturb and self.rng_mode == 'reference':
                 z_coarse = ops.stratified_z(ladder, R, jitter=cpu_draw(lambda n: torch.rand([n, S])))       # SimpleNeRF17.py:355
             elif perturb:
-                z_coarse = ops.stratified_z(ladder, R, philox_seed=device_seed())
+                z_coarse = ops.stratified_z(ladder, R, jitter=torch.rand([R, S], device=dev))     # torch's CUDA generator: CUDA-graph safe
             else:
                 z_coarse = ops.stratified_z(ladder, R)
             out['z_vals_coarse'] = z_coarse
@@ -237,7 +238,7 @@ class SimpleNeRF(torch.nn.Module):
             if perturb and self.rng_mode == 'reference':
                 z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=cpu_draw(lambda n: torch.rand([n, N])))   # SimpleNeRF17.py:397
             elif perturb:
-                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, philox_seed=device_seed())
+                z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=torch.rand([R, N], device=dev))
             else:
                 z_fine = ops.sample_pdf_merge(z_coarse, w_det, N, u=_on_device('linspace', int(N), dev, lambda: torch.linspace(0., 1., steps=N)))
             out['z_vals_fine'] = z_fine

@@ -201,7 +201,8 @@ class SimpleTensoRF(torch.nn.Module):
             jitter = parallel.rows_of_global_draw(lambda n: torch.rand([n, S]), R, shard, mc['chunk'])
             z = ops.stratified_z(ladder, R, jitter=jitter.to(dev))                                  # SimpleTensoRF09.py:379
         elif perturb:
-            z = ops.stratified_z(ladder, R, philox_seed=parallel.rank_seed(int(torch.randint(0, 2 ** 31, (1,)).item())))
+            parallel.decorrelate_device_rng()
+            z = ops.stratified_z(ladder, R, jitter=torch.rand([R, S], device=dev))     # torch's CUDA generator: CUDA-graph safe
         else:
             z = ops.stratified_z(ladder, R)
         out['z_vals_coarse'] = z
@@ -448,9 +449,13 @@ class VmDecomposedTensor(torch.nn.Module):
             rows, _ = T.vm_color_rows(geom, surface, rays['view_dirs'], list(self.matrices_color), list(self.vectors_color))
             rgb_rows = cp.packed(basis).forward(rows, surface.count, rows.shape[0])
         rgb = T._ScatterRows.apply(surface, rgb_rows, R * S).view(R, S, 3)
-        white = white_bkgd or bool(self.training and (torch.rand((1,)) < 0.5))      # :746
+        device_coin = self.training and not white_bkgd and self.configs['model'].get('rng_mode', 'reference') != 'reference'
+        white = white_bkgd or bool(self.training and not device_coin and (torch.rand((1,)) < 0.5))      # :746
         vr = ops.composite(sigma[..., 0], rgb, z, rays['rays_o'], rays['rays_d'], sd, ndc=True, white_bkgd=white,
                            distance_scale=tc['distance_scale'], per_sample=retraw)      # alpha / visibility are dropped unless retraw
+        if device_coin:          # the background coin (:746) drawn on the device: no host decision inside a captured iteration
+            coin = (torch.rand((), device=z.device) < 0.5).to(vr['rgb'].dtype)
+            vr['rgb'] = vr['rgb'] + coin * (1. - vr['acc'])[:, None]
         out = {k: vr[k] for k in ('acc', 'alpha', 'visibility', 'weights', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'rgb') if k in vr}
         if retraw:
             out['raw_sigma'] = sigma

@@ -64,6 +64,7 @@ class FusedFlatAdam:
         assert supports(optimizer), 'FusedFlatAdam needs a plain torch.optim.Adam over CUDA fp32 parameters'
         self.optimizer = optimizer
         self.process_group = process_group
+        self.capturable = False            # make_capturable(): step count and learning rate move to device memory (CUDA graphs)
         self.groups = [None] * len(optimizer.param_groups)
         self.bytes_reduced_last = 0
         self._torch_step = optimizer.step
@@ -73,6 +74,42 @@ class FusedFlatAdam:
     def detach(self):
         self.optimizer.step = self._torch_step
         self.optimizer._srf_fused = None
+
+    # ---------------------------------------------------------------- CUDA-graph support (train_graph.GraphedStep)
+    def make_capturable(self):
+        """From now on `step()` reads the step count and the learning rate of every group from device memory
+        (srf_adam_advance + srf_adam_step_capturable), so it can sit inside a captured CUDA graph.  Needs one (already
+        performed or pending) flat-buffer build per group, equal step counts inside a group and a gradient on every parameter —
+        the steady state of training.  `sync_hyperparameters()` pushes `param_group['lr']` (the trainer rescales it every
+        iteration, src/Trainer10.py:303-308) to the device; `after_replay()` keeps the host mirrors current."""
+        self.capturable = True
+        return self
+
+    def _device_state(self, fg, group):
+        if getattr(fg, 'step_dev', None) is None:
+            dev = fg.flat_p.device
+            assert len(set(fg.steps)) <= 1, 'capturable mode needs equal step counts inside a parameter group'
+            fg.step_dev = torch.full((1,), fg.steps[0] if fg.steps else 0, dtype=torch.int64, device=dev)
+            fg.lr_dev = torch.full((1,), float(group['lr']), dtype=torch.float32, device=dev)
+        return fg.step_dev, fg.lr_dev
+
+    def sync_hyperparameters(self):
+        """Outside a capture: copy every group's current `lr` into its device scalar (a fill kernel, no host->device copy)."""
+        for group, fg in zip(self.optimizer.param_groups, self.groups):
+            if fg is not None and getattr(fg, 'lr_dev', None) is not None:
+                fg.lr_dev.fill_(float(group['lr']))
+
+    def after_replay(self):
+        """A captured step ran without this Python code: advance the host-side step mirrors and bump the parameters' version
+        counters (the packed-weight / channels-last caches of the models are keyed on them)."""
+        params = []
+        for fg in self.groups:
+            if fg is None or getattr(fg, 'step_dev', None) is None:
+                continue
+            fg.steps = [s + 1 for s in fg.steps]
+            params.extend(fg.params)
+        if params:
+            torch.autograd.graph.increment_version(params)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -134,6 +171,19 @@ class FusedFlatAdam:
             if not any(have_step):
                 continue
             beta1, beta2 = group['betas']
+            if self.capturable:
+                assert all(have_step), 'capturable mode: every parameter of the group needs a gradient'
+                step_dev, lr_dev = self._device_state(fg, group)
+                if not torch.cuda.is_current_stream_capturing():
+                    lr_dev.fill_(float(group['lr']))
+                L.call('srf_adam_advance', L.ptr(step_dev), L.stream_handle())
+                L.call('srf_adam_step_capturable', L.ptr(fg.flat_p), L.ptr(fg.flat_g), L.ptr(fg.flat_m), L.ptr(fg.flat_v), fg.total,
+                       L.ptr(lr_dev), float(beta1), float(beta2), float(group['eps']), float(group['weight_decay']), L.ptr(step_dev),
+                       L.stream_handle())
+                if not torch.cuda.is_current_stream_capturing():      # a capture only records: GraphedStep.after_replay keeps the mirrors
+                    fg.steps = [st + 1 for st in fg.steps]
+                    torch.autograd.graph.increment_version(fg.params)
+                continue
             for a, b in _runs(have_step, fg.steps):     # one launch per run of stepped parameters with equal step counts
                 step = fg.steps[a] + 1
                 lo = fg.offsets[a]

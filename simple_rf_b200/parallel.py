@@ -153,6 +153,20 @@ def rows_of_global_draw(draw, rows_local, shard, chunk):
     return draw(shard[2])[torch.from_numpy(shard[3])]
 
 
+_DEVICE_RNG_DECORRELATED = False
+
+
+def decorrelate_device_rng():
+    """`rng_mode='device'` draws jitter / noise from torch's CUDA generator; every rank seeds it identically
+    (init_seeds, src/Trainer10.py:443-450), which would give different rays the same random numbers on every rank.
+    Offsets the generator of this process by its rank, once."""
+    global _DEVICE_RNG_DECORRELATED
+    if _DEVICE_RNG_DECORRELATED or not is_distributed() or not torch.cuda.is_available():
+        return
+    torch.cuda.manual_seed(torch.cuda.initial_seed() + 7919 * dist.get_rank())
+    _DEVICE_RNG_DECORRELATED = True
+
+
 def rank_seed(seed):
     """Decorrelates the in-kernel Philox streams of the ranks (`rng_mode='device'`): every rank draws the same CPU seed."""
     if not is_distributed():

@@ -23,5 +23,6 @@ for name in sys.argv[1:] or ['tensorf_train']:
     else:
         raise SystemExit(f'unknown workload {name}')
     print(json.dumps({'workload': name, 'ms_per_step': r['ms_per_step'], 'value': r['value'], 'unit': r['unit'],
+                      'ms_per_step_eager': r.get('ms_per_step_eager'), 'cuda_graph': r.get('cuda_graph'), 'cuda_graph_error': r.get('cuda_graph_error'),
                       'kernels_ms_per_step': r['kernels_ms_per_step'],
                       'fracs': {k: round(v['frac'], 3) for k, v in r.get('rooflines', {}).items()}}), flush=True)
