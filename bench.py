@@ -198,12 +198,16 @@ def build_render_setup(device, local):
         del pre
         tester = C.make_tester(cfg, mc, [local])
         tester.model.eval()
+        # main line = one INDEPENDENT frame per rank (weak scaling): the drop-in's test-time row-band sharding (on by default under
+        # torch.distributed, for an unedited Tester07 on several ranks) is measured separately by sharded_frame()
+        tester.model.module.configs['model']['shard_eval_rays'] = False
         return {'model': tester.model.module, 'tester': tester, 'raw': raw, 'model_configs': mc, 'pose': lambda t: C.test_pose(raw, t)}
     from simple_rf_b200.models.SimpleNeRF91 import SimpleNeRF
     configs = synthetic.nerf_configs()
     mc = synthetic.scene_model_configs('llff', num_views=2)
     torch.manual_seed(0)
     model = SimpleNeRF(configs, mc).to(device).eval()
+    model.configs['model']['shard_eval_rays'] = False
     return {'model': model, 'tester': None, 'raw': None, 'model_configs': mc,
             'pose': lambda t: np.asarray(synthetic.trajectory_pose(mc, t), dtype=np.float32)}
 
@@ -435,6 +439,7 @@ def tensorf_trajectory(dist, frames=6, warmup=2):
     mc = synthetic.scene_model_configs('re10k', num_views=3)
     torch.manual_seed(0)
     model = SimpleTensoRF(cfg, mc).to(device).eval()
+    model.configs['model']['shard_eval_rays'] = False        # the ranks render different frames of the trajectory (weak scaling)
     t = model.coarse_model
     with torch.no_grad():
         for p_ in t.matrices_density:

@@ -187,6 +187,32 @@ int srf_scatter_rows(const int* indices, const int* count, int64_t max_count, co
 int srf_gather_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
                     void* stream);
 
+/* ---- "next" row f3: grid surgery (csrc/tensorf_surgery.cu).
+ * Alpha-mask rebuild, LowRankTensor.update_alpha_mask (SimpleTensoRF09.py:849-876) without any fp32 volume:
+ *   1. srf_alpha_grid_occupancy: for every voxel of the (X,Y,Z) = resolution grid, world point = (coord_x[x], coord_y[y],
+ *      coord_z[z]) (DEVICE arrays holding bb0 (1 - s) + bb1 s, s = linspace(0, 1, n), :850-855), previous alpha-mask test
+ *      (prev_bits nullable; :879-883), normalise (:763-765), VM density (:1214-1239), alpha = 1 - exp(-sigma step_size) (:895),
+ *      clamp (:862) and `>= threshold` -> raw_words [Z][Y][ceil(X/32)] (bit x & 31 of word x >> 5; srf_alpha_grid_words words).
+ *   2. srf_alpha_grid_dilate: the 3x3x3 max-pool of :864-865 as a bit dilation (max over a window >= t <=> any member >= t)
+ *      -> volume uint8 {0,1} [Z,Y,X] (the new AlphaGridMask.alpha_volume, :869) and projection uint32[ceil(X/32) + Y + Z]
+ *      (CALLER-zeroed): the occupied set projected on each axis — x as row-layout bit words, then one flag per y, per z —
+ *      from which the host takes the new bounding box (:871-875: amin / amax of the occupied voxels' coordinates).
+ * box_min / box_size / prev_box_* / resolution / prev_res / channels are HOST arrays; planes / lines as for srf_vm_density_fwd. */
+int srf_alpha_grid_words(const int* resolution);
+int srf_alpha_grid_occupancy(const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                             const float* box_min, const float* box_size, const float* coord_x, const float* coord_y,
+                             const float* coord_z, const uint32_t* prev_bits, const int* prev_res, const float* prev_box_min,
+                             const float* prev_box_size, int softplus, float density_offset, float step_size, float threshold,
+                             uint32_t* raw_words, void* stream);
+int srf_alpha_grid_dilate(const uint32_t* raw_words, const int* resolution, uint8_t* volume, uint32_t* projection, void* stream);
+/* srf_pack_alpha_bits for a bool / uint8 volume (the in-memory form of the drop-in's AlphaGridMask.alpha_volume). */
+int srf_pack_alpha_bits_u8(const uint8_t* volume, int64_t num_voxels, uint32_t* bits, void* stream);
+/* dst [C, out_height, out_width] = bilinear resampling (F.interpolate(mode='bilinear', align_corners=True), ATen's
+ * upsample_bilinear2d arithmetic; SimpleTensoRF09.py:1284-1295) of the window [y0, y0+h) x [x0, x0+w) of src [C, height, width];
+ * with (out_height, out_width) == (h, w) it is the window copy of shrink_tensor (:1303-1319). */
+int srf_resample_plane(const float* src, int channels, int height, int width, int y0, int x0, int h, int w, float* dst,
+                       int out_height, int out_width, void* stream);
+
 /* Colour MLP on the tensor cores: same kernel and program format as srf_nerf_mlp_fwd, but regions 0 and 5 are filled from
  * precomputed bf16 rows [max_rows, row_pitch] (columns 0..63 / 64..row_pitch-1, zero beyond) instead of encodings (views_degree = -2 in the
  * program; -1 when only region 0 is used); the row count is read from the device. */

@@ -80,3 +80,34 @@ def tensorf_full_size_sets(configs, seed, alpha_size=190):
     for aug in mc.get('augmentations', []):
         sets['augmentations'].append((aug['name'], aug['coarse_model'], one(aug['coarse_model'], False)))
     return sets
+
+
+def sparsify_density(t, floor=0.6):
+    """Random-init planes put sigma above the alpha-mask threshold almost everywhere (after the 3^3 pooling: everywhere).  A
+    constant negative density component (channel 0 of plane 0 = -floor, of line 0 = 1) leaves a few per cent of the voxels
+    occupied, so the rebuilt mask, its dilation and the shrunk bounding box are non-trivial."""
+    t['params']['matrices_density.0'][:, 0] = -floor
+    t['params']['vectors_density.0'][:, 0] = 1.0
+    return t
+
+
+def carve_empty_border(t, margins=((0.15, 0.1), (0.1, 0.2), (0.2, 0.12))):
+    """Push the density far below zero near the faces of the box (per axis: fraction of the extent at the low / high side),
+    so the occupied voxels do not touch the box and shrink_tensor has something to cut."""
+    res = [int(r) for r in t['resolution']]
+    for a, (lo, hi) in enumerate(margins):
+        n = res[a]
+        ramp = torch.zeros(n)
+        ramp[: int(lo * n)] = 1.0
+        ramp[n - int(hi * n):] = 1.0
+        i = TF.VECTOR_AXES.index(a)                      # the line running along axis a
+        t['params'][f'vectors_density.{i}'][0, 1, :, 0] = ramp
+        t['params'][f'matrices_density.{i}'][0, 1] = -50.0
+    return t
+
+
+def surgery_sets(configs, seed=41):
+    """Tensors for the grid-surgery fixtures (alpha-mask rebuild, shrink, upsampling): tensorf_sets() + sparse density."""
+    sets = tensorf_sets(configs, seed, with_alpha=False)
+    carve_empty_border(sparsify_density(sets['coarse_model']))
+    return sets

@@ -22,6 +22,7 @@ from . import nerf_mlp as M
 from . import pipeline as P
 from . import reference_harness as H
 from . import sampling as SP
+from . import surgery as SG
 from . import tensorf as TF
 
 OUT = Path(__file__).resolve().parent.parent / 'tests' / 'golden'
@@ -459,6 +460,83 @@ def golden_batch_assembly():
     print('batch_assembly: oracle == reference')
 
 
+def surgery_configs():
+    """Shipped TensoRF config shrunk for the CPU: 48^3-voxel main tensor, one upsampling step to 64^3."""
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    cm = configs['model']['coarse_model']
+    cm['num_voxels_initial'], cm['num_voxels_final'] = 48 ** 3, 64 ** 3
+    cm['tensor_upsampling_iters'] = [4]
+    cm['alpha_mask_update_iters'] = [2, 6]
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 20 ** 3
+    return configs, model_configs
+
+
+def _pack(volume):
+    return np.packbits(volume.reshape(-1).numpy().astype(np.uint8))
+
+
+def golden_surgery():
+    """f3: the reference's own update_alpha_mask / shrink_tensor / upsample_model_resolution on the seeded sparse tensor, in the
+    order of its schedule (rebuild + shrink, upsample, rebuild against the previous mask at the old resolution); the oracle
+    (oracle/surgery.py) must reproduce every volume, window, box and plane bit-exactly."""
+    configs, model_configs = surgery_configs()
+    (OUT / 'tensorf_surgery_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    sets = FX.surgery_sets(configs, seed=41)
+    load_tensorf_params(model, sets)
+    t = model.coarse_model
+    t.train()
+    cfg = configs['model']['coarse_model']
+    thr = cfg['alpha_mask_threshold']
+    params = {k: v.clone() for k, v in sets['coarse_model']['params'].items()}
+    geo = SG.tensor_geometry(sets['coarse_model']['resolution'], sets['coarse_model']['bbox'], cfg['num_voxels_per_sample'], cfg['num_samples_max'])
+    fixture = {'param_seed': 41}
+    with torch.no_grad():
+        # 1. first rebuild (no previous mask) + shrink
+        box_ref = t.update_alpha_mask(2)
+        vol, box = SG.update_alpha_mask(params, geo, thr)
+        _check('surgery/volume1', t.alpha_mask.alpha_volume[0, 0], vol)
+        _check('surgery/box1', box_ref, box)
+        fixture.update(volume1_bits=_pack(vol), volume1_shape=torch.tensor(vol.shape), box1=box_ref.clone(), occupied1=vol.mean())
+        alpha_res = t.alpha_mask.resolution.clone()
+        t.shrink_tensor(box_ref)
+        t_l, b_r, box_s = SG.shrink_window(geo, box, alpha_res)
+        params = SG.shrink_params(params, t_l, b_r)
+        geo = SG.tensor_geometry(b_r - t_l, box_s, cfg['num_voxels_per_sample'], cfg['num_samples_max'])
+        _check('surgery/shrink/resolution', t.resolution, geo['resolution'])
+        _check('surgery/shrink/bbox', t.bounding_box, geo['bbox'])
+        assert int(t.num_samples) == geo['num_samples']
+        for k, v in dict(t.named_parameters()).items():
+            if k.startswith(('matrices', 'vectors')):
+                _check(f'surgery/shrink/{k}', v, params[k])
+        fixture.update(window_lo=t_l, window_hi=b_r, shrink_resolution=t.resolution.clone(), shrink_bbox=t.bounding_box.clone(),
+                       shrink_num_samples=int(t.num_samples))
+        # 2. upsampling
+        t.upsample_model_resolution(4)
+        nv = SG.new_num_voxels(4, cfg['tensor_upsampling_iters'], cfg['num_voxels_initial'], cfg['num_voxels_final'])
+        new_res = TF.vm_resolution(nv, geo['bbox'])
+        params = SG.upsample_params(params, new_res)
+        geo = SG.tensor_geometry(new_res, geo['bbox'], cfg['num_voxels_per_sample'], cfg['num_samples_max'])
+        _check('surgery/upsample/resolution', t.resolution, geo['resolution'])
+        for k, v in dict(t.named_parameters()).items():
+            if k.startswith(('matrices', 'vectors')):
+                _check(f'surgery/upsample/{k}', v, params[k])
+        fixture.update(upsample_resolution=t.resolution.clone(), upsample_num_samples=int(t.num_samples),
+                       upsampled_matrices_density_0=params['matrices_density.0'], upsampled_vectors_color_2=params['vectors_color.2'],
+                       upsampled_matrices_color_1_sum=params['matrices_color.1'].double().sum())
+        # 3. second rebuild: previous mask at the old resolution and the old (pre-shrink) box
+        prev_vol, prev_box = t.alpha_mask.alpha_volume.clone(), t.alpha_mask.bounding_box.clone()
+        box_ref2 = t.update_alpha_mask(6)
+        vol2, box2 = SG.update_alpha_mask(params, geo, thr, prev_vol, prev_box)
+        _check('surgery/volume2', t.alpha_mask.alpha_volume[0, 0], vol2)
+        _check('surgery/box2', box_ref2, box2)
+        fixture.update(volume2_bits=_pack(vol2), volume2_shape=torch.tensor(vol2.shape), box2=box_ref2.clone(), occupied2=vol2.mean())
+    np.savez_compressed(OUT / 'tensorf_surgery.npz', **_np(fixture))
+    print(f'tensorf_surgery: oracle == reference (grid {list(vol.shape)} {vol.mean():.3f} occupied -> window {t_l.tolist()}..{b_r.tolist()} '
+          f'-> {geo["resolution"].tolist()}, second mask {vol2.mean():.3f} occupied)')
+
+
 def main():
     if not H.available():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
@@ -474,6 +552,7 @@ def main():
     golden_nerf_training_curve()
     golden_tensorf_training_curve()
     golden_batch_assembly()
+    golden_surgery()
 
 
 if __name__ == '__main__':

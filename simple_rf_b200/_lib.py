@@ -57,6 +57,11 @@ _SIGNATURES = {
     'srf_frame_outputs': (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P]),
     'srf_adam_advance': (c_int, [_P, _P]),
     'srf_adam_step_capturable': (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, _P]),
+    'srf_alpha_grid_words': (c_int, [_P]),
+    'srf_alpha_grid_occupancy': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, _P, _P]),
+    'srf_alpha_grid_dilate': (c_int, [_P, _P, _P, _P, _P]),
+    'srf_pack_alpha_bits_u8': (c_int, [_P, c_int64, _P, _P]),
+    'srf_resample_plane': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     'srf_composite_bwd': (c_int, [_P] * 17 + [c_int64, c_int, c_int, c_int, c_float, _P, _P, _P]),
 }
 

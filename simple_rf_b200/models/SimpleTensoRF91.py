@@ -10,15 +10,15 @@ state-dict compatible names (`coarse_model.matrices_density.0`, `coarse_model.al
 Per-ray arithmetic (ray generation, stratified depths, occupancy test, compaction, VM density / appearance
 gathers, colour MLP, compositing) runs in hand-written CUDA kernels; planes stay `nn.Parameter`s of logical
 shape [1,C,H,W] (TotalVariationLoss04.py:85-95 differentiates them directly), channels-last and bit-packed
-copies are derived per call.  Grid surgery (5 iterations out of 25 000) uses the same kernels for the dense
-density evaluation and plain tensor ops for the pooling / resampling.
+copies are derived per call.  Grid surgery (5 iterations out of 25 000) is a precomputed plan executed on the kernels of
+csrc/tensorf_surgery.cu (grid_surgery.py).
 """
 import numpy
 import torch
-import torch.nn.functional as F
 from torch.nn import ModuleDict, ModuleList
 
 from .. import _lib as L
+from .. import grid_surgery as GS
 from .. import ops
 from .. import tensorf_ops as T
 from ..nerf_program import PackedRowsMLP
@@ -222,33 +222,25 @@ class SimpleTensoRF(torch.nn.Module):
 
 
 class AlphaGridMask(torch.nn.Module):
-    """SimpleTensoRF09.py:1323-1367: binary occupancy volume [1,1,Z,Y,X] (fp32 in memory, bool in checkpoints)."""
+    """Binary occupancy volume [1,1,Z,Y,X] + the box it was built on (SimpleTensoRF09.py:1323-1367).  Buffer names, shapes and
+    the bool checkpoint form are the reference's; in memory the volume stays bool (the reference keeps fp32 only because
+    `grid_sample` needs it) and the kernels read a 1-bit-per-voxel cache derived from it."""
 
     def __init__(self, alpha_volume, bounding_box):
         super().__init__()
-        self.register_buffer('alpha_volume', torch.tensor(0, dtype=bool))
-        self.register_buffer('bounding_box', torch.zeros(size=(2, 3)))
-        self.register_buffer('bounding_box_size', torch.zeros(size=(3,)))
-        self.register_buffer('resolution', torch.zeros(size=(3,), dtype=torch.long))
-        self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
-        self.bounding_box = bounding_box
-        self.bounding_box_size = self.bounding_box[1] - self.bounding_box[0]
-        self.resolution = torch.LongTensor([alpha_volume.shape[-1], alpha_volume.shape[-2], alpha_volume.shape[-3]]).to(alpha_volume.device)
-        self._register_state_dict_hook(self._save_hook)
-        self._register_load_state_dict_pre_hook(self._load_hook)
+        volume = alpha_volume if alpha_volume.dtype == torch.bool else alpha_volume > 0
+        z, y, x = volume.shape[-3:]
+        self.register_buffer('alpha_volume', volume.reshape(1, 1, z, y, x))
+        self.register_buffer('bounding_box', bounding_box)
+        self.register_buffer('bounding_box_size', bounding_box[1] - bounding_box[0])
+        self.register_buffer('resolution', torch.tensor([x, y, z], dtype=torch.long, device=volume.device))
         self._bits = None
 
-    def _save_hook(self, obj, state, prefix, *args, **kwargs):
-        state[f'{prefix}alpha_volume'] = state[f'{prefix}alpha_volume'].bool()
-
-    def _load_hook(self, state, prefix, *args, **kwargs):
-        state[f'{prefix}alpha_volume'] = state[f'{prefix}alpha_volume'].float()
-
     def packed(self):
-        """1 bit / voxel derived cache + host-side box description for the mask kernel."""
+        """1 bit / voxel derived cache + host-side box description for the occupancy tests."""
         key = (self.alpha_volume.data_ptr(), self.alpha_volume._version)
         if self._bits is None or self._bits[0] != key:
-            self._bits = (key, {'bits': T.pack_alpha_bits(self.alpha_volume.float()), 'res': self.resolution.tolist(),
+            self._bits = (key, {'bits': T.pack_alpha_bits(self.alpha_volume), 'res': self.resolution.tolist(),
                                 'box_min': self.bounding_box[0].tolist(), 'box_size': self.bounding_box_size.tolist()})
         return self._bits[1]
 
@@ -362,6 +354,7 @@ class VmDecomposedTensor(torch.nn.Module):
         self.voxel_length = self.bounding_box_size / (self.resolution - 1)
         self.step_size = torch.mean(self.voxel_length) * self.tensor_configs['num_voxels_per_sample']
         self.num_samples = self.compute_num_samples(self.resolution, self.tensor_configs['num_voxels_per_sample'])
+        self._host_geom = None          # freed buffers may be re-allocated at the same address: do not trust the pointer key here
 
     def create_decomposed_tensor(self, comps, resolution, scale):
         mats, vecs = [], []
@@ -385,10 +378,8 @@ class VmDecomposedTensor(torch.nn.Module):
     def _load_hook(self, state, prefix, *args, **kwargs):
         """:946-961 + :1196-1212: rebuild the alpha mask and resize planes/lines before loading."""
         if f'{prefix}alpha_mask.alpha_volume' in state:
-            self.alpha_mask = AlphaGridMask(state[f'{prefix}alpha_mask.alpha_volume'].float(), state[f'{prefix}alpha_mask.bounding_box'])
-        new_res = state[f'{prefix}resolution']
-        self.matrices_density, self.vectors_density = self.upsample_vectors_and_matrices(self.matrices_density, self.vectors_density, new_res)
-        self.matrices_color, self.vectors_color = self.upsample_vectors_and_matrices(self.matrices_color, self.vectors_color, new_res)
+            self.alpha_mask = AlphaGridMask(state[f'{prefix}alpha_mask.alpha_volume'], state[f'{prefix}alpha_mask.bounding_box'])
+        self._resize_parameters(state[f'{prefix}resolution'])
 
     # ---------------------------------------------------------------- forward (:701-761)
     def host_geometry(self):
@@ -462,117 +453,52 @@ class VmDecomposedTensor(torch.nn.Module):
             out['raw_rgb'] = rgb
         return out
 
-    # ---------------------------------------------------------------- dense density for surgery (:878-897)
-    @torch.no_grad()
-    def compute_alpha(self, xyz, length=1):
-        """alpha = 1 - exp(-sigma * length) at world points xyz [N,3]: each point is a zero-direction 'ray'."""
-        n = xyz.shape[0]
-        out = torch.empty((n,), dtype=torch.float32, device=xyz.device)
-        step = 1 << 22
-        zero_d = torch.zeros((min(step, n), 3), dtype=torch.float32, device=xyz.device)
-        zero_z = torch.zeros((min(step, n), 1), dtype=torch.float32, device=xyz.device)
-        alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
-        for i in range(0, n, step):
-            p = xyz[i:i + step].contiguous()
-            m = p.shape[0]
-            # the reference tests only the alpha mask here, not the box (:879-883)
-            comp = T.validity_compact(p, zero_d[:m], zero_z[:m], [[-3e38] * 3, [3e38] * 3], alpha)
-            geom = self._geometry(p, zero_d[:m], zero_z[:m])
-            sigma = T.vm_density(geom, comp, list(self.matrices_density), list(self.vectors_density),
-                                 softplus=self.density_predictor == 'SoftPlus', offset=self.tensor_configs['density_offset'])
-            out[i:i + m] = 1 - torch.exp(-sigma.view(-1) * length)
-        return out
-
-    # ---------------------------------------------------------------- model surgery (:821-944, :1277-1320)
+    # ---------------------------------------------------------------- grid surgery (grid_surgery.py; reference :821-944, :1277-1320)
     def run_model_modifications(self, iter_num):
-        tc = self.tensor_configs
-        if self.training and iter_num in tc['alpha_mask_update_iters']:
-            new_box = self.update_alpha_mask(iter_num)
-            if iter_num == tc['alpha_mask_update_iters'][0]:
-                self.shrink_tensor(new_box)
-        if self.training and iter_num in tc['tensor_upsampling_iters']:
-            self.upsample_model_resolution(iter_num)
-            self.reconfigure_optimizer()
+        """Execute this iteration's steps of the precomputed plan (training only, :822,:827)."""
+        if not self.training:
+            return
+        if getattr(self, '_surgery_plan', None) is None:
+            self._surgery_plan = GS.build_plan(self.tensor_configs)
+        for step, arg in self._surgery_plan.get(iter_num, ()):
+            if step == 'occupancy':
+                occupied_box = self.rebuild_alpha_mask()
+                if arg:
+                    self.crop_to(occupied_box)
+            else:
+                self.resample_to(self.compute_resolution_in_voxels(arg, self.bounding_box))
+                self.regroup_optimizer()
 
-    def get_new_num_voxels(self, iter_num):
-        iters = self.tensor_configs['tensor_upsampling_iters']
-        if iter_num not in iters:
-            raise RuntimeError('get_new_num_voxels() called at invalid iteration number')
-        k = iters.index(iter_num) + 1
-        lo, hi = numpy.log(self.tensor_configs['num_voxels_initial']), numpy.log(self.tensor_configs['num_voxels_final'])
-        return int(numpy.round(numpy.exp(lo + (hi - lo) * k / len(iters))))
+    def rebuild_alpha_mask(self):
+        """New occupancy mask on the current grid (:849-876) -> bounding box of the occupied voxels."""
+        hg = self.host_geometry()
+        volume, occupied_box = GS.rebuild_occupancy(
+            self.matrices_density, self.vectors_density,
+            {'box': self.bounding_box, 'box_min': hg['box_min'], 'box_size': hg['box_size'], 'res': hg['res']},
+            step_size=float(self.step_size), threshold=self.tensor_configs['alpha_mask_threshold'],
+            softplus=self.density_predictor == 'SoftPlus', density_offset=self.tensor_configs['density_offset'],
+            previous=self.alpha_mask.packed() if self.alpha_mask is not None else None)
+        self.alpha_mask = AlphaGridMask(volume, self.bounding_box)
+        return occupied_box
 
-    @torch.no_grad()
-    def update_alpha_mask(self, iter_num):
+    def crop_to(self, occupied_box):
+        """Cut the tensor down to the voxel window around `occupied_box` (:899-914, :1299-1320)."""
+        lo, hi, box = GS.crop_window(self.bounding_box, self.voxel_length, self.resolution, occupied_box, self.alpha_mask.resolution)
         dev = self.bounding_box.device
-        gs = tuple(int(v) for v in self.resolution.tolist())
-        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gs[0]), torch.linspace(0, 1, gs[1]), torch.linspace(0, 1, gs[2]),
-                                             indexing='ij'), -1).to(dev)
-        dense_xyz = self.bounding_box[0] * (1 - samples) + self.bounding_box[1] * samples
-        alpha = self.compute_alpha(dense_xyz.view(-1, 3), self.step_size).view(gs)
-        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
-        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
-        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gs[::-1])
-        thr = self.tensor_configs['alpha_mask_threshold']
-        alpha = (alpha >= thr).float()
-        self.alpha_mask = AlphaGridMask(alpha, self.bounding_box)
-        valid_xyz = dense_xyz[alpha > 0.5]
-        return torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
+        self.matrices_density, self.vectors_density = GS.crop_vm(self.matrices_density, self.vectors_density, lo, hi)
+        self.matrices_color, self.vectors_color = GS.crop_vm(self.matrices_color, self.vectors_color, lo, hi)
+        self.update_tensor_params((hi - lo).to(dev), box.to(dev))
 
-    @torch.no_grad()
-    def shrink_tensor(self, new_box):
-        lo, hi = new_box
-        t_l, b_r = (lo - self.bounding_box[0]) / self.voxel_length, (hi - self.bounding_box[0]) / self.voxel_length
-        t_l, b_r = torch.round(torch.round(t_l)).long(), torch.round(b_r).long() + 1
-        b_r = torch.stack([b_r, self.resolution]).amin(0)
-        if not torch.equal(self.alpha_mask.resolution, self.resolution):
-            t_l_r, b_r_r = t_l / (self.resolution - 1), (b_r - 1) / (self.resolution - 1)
-            box = torch.zeros_like(new_box)
-            box[0] = (1 - t_l_r) * self.bounding_box[0] + t_l_r * self.bounding_box[1]
-            box[1] = (1 - b_r_r) * self.bounding_box[0] + b_r_r * self.bounding_box[1]
-            new_box = box
-        self.update_tensor_params(b_r - t_l, new_box)
-        for i in range(3):
-            v = self.vector_axes[i]
-            a0, a1 = self.matrix_axes[i]
-            for vecs, mats in ((self.vectors_density, self.matrices_density), (self.vectors_color, self.matrices_color)):
-                vecs[i] = torch.nn.Parameter(vecs[i].data[..., t_l[v]:b_r[v], :])
-                mats[i] = torch.nn.Parameter(mats[i].data[..., t_l[a1]:b_r[a1], t_l[a0]:b_r[a0]])
+    def _resize_parameters(self, resolution):
+        self.matrices_density, self.vectors_density = GS.resample_vm(self.matrices_density, self.vectors_density, resolution)
+        self.matrices_color, self.vectors_color = GS.resample_vm(self.matrices_color, self.vectors_color, resolution)
 
-    def upsample_model_resolution(self, iter_num):
-        res = self.compute_resolution_in_voxels(self.get_new_num_voxels(iter_num), self.bounding_box)
-        self.update_tensor_params(res, self.bounding_box)
-        self.matrices_density, self.vectors_density = self.upsample_vectors_and_matrices(self.matrices_density, self.vectors_density, self.resolution)
-        self.matrices_color, self.vectors_color = self.upsample_vectors_and_matrices(self.matrices_color, self.vectors_color, self.resolution)
+    def resample_to(self, resolution):
+        """Bilinear resampling of every plane / line to `resolution` voxels (:832-835, :1277-1297)."""
+        self.update_tensor_params(resolution, self.bounding_box)
+        self._resize_parameters(self.resolution)
 
-    def upsample_vectors_and_matrices(self, matrices, vectors, new_res):
-        mats, vecs = [], []
-        for i in range(3):
-            a0, a1 = self.matrix_axes[i]
-            v = self.vector_axes[i]
-            mats.append(torch.nn.Parameter(F.interpolate(matrices[i].data, size=(int(new_res[a1]), int(new_res[a0])), mode='bilinear',
-                                                         align_corners=True)))
-            vecs.append(torch.nn.Parameter(F.interpolate(vectors[i].data, size=(int(new_res[v]), 1), mode='bilinear', align_corners=True)))
-        return torch.nn.ParameterList(mats), torch.nn.ParameterList(vecs)
-
-    def reconfigure_optimizer(self):
-        """:916-944, quirks included: groups are re-added with the INITIAL learning rates."""
-        optimizer = self.optimizers['optimizer_nerf']
-        opt_cfg = next(filter(lambda c: c['name'] == 'optimizer_main', self.configs['optimizers']))
-        groups = self.get_trainable_parameters(opt_cfg)
-        for group in groups:
-            index = 0
-            for i, existing in enumerate(optimizer.param_groups):
-                count = len(existing['params'])
-                if existing['name'] == group['name']:
-                    del optimizer.param_groups[i]
-                    for _ in range(count):
-                        keys = list(optimizer.state.keys())
-                        if index < len(keys):
-                            del optimizer.state[keys[index]]
-                        else:
-                            print(f'Unable to delete item at {index} since list has only {len(keys)} elements')
-                else:
-                    index += count
-        for group in groups:
-            optimizer.add_param_group(group)
+    def regroup_optimizer(self):
+        """The trainer's optimiser must now hold the new Parameter objects (:916-944)."""
+        opt_cfg = next(c for c in self.configs['optimizers'] if c['name'] == 'optimizer_main')
+        GS.regroup_optimizer(self.optimizers['optimizer_nerf'], self.get_trainable_parameters(opt_cfg))

@@ -28,12 +28,17 @@ def _ptrs(tensors):
 
 
 def pack_alpha_bits(alpha_volume):
-    """fp32 {0,1} volume [..., Z, Y, X] (AlphaGridMask.alpha_volume) -> uint32 words, 1 bit per voxel."""
+    """{0,1} volume [..., Z, Y, X] (AlphaGridMask.alpha_volume: bool / uint8 in the drop-in, fp32 in the reference's memory
+    form) -> uint32 words, 1 bit per voxel, x fastest."""
     L.require_cuda(alpha_volume)
-    vol = L.f32c(alpha_volume).reshape(-1)
-    n = vol.numel()
-    bits = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=vol.device)
-    L.call('srf_pack_alpha_bits', L.ptr(vol), n, L.ptr(bits), L.stream_handle())
+    n = alpha_volume.numel()
+    bits = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=alpha_volume.device)
+    if alpha_volume.dtype in (torch.bool, torch.uint8):
+        vol = alpha_volume.contiguous().view(torch.uint8).reshape(-1)
+        L.call('srf_pack_alpha_bits_u8', L.ptr(vol), n, L.ptr(bits), L.stream_handle())
+    else:
+        vol = L.f32c(alpha_volume).reshape(-1)
+        L.call('srf_pack_alpha_bits', L.ptr(vol), n, L.ptr(bits), L.stream_handle())
     return bits
 
 
