@@ -109,6 +109,10 @@ typedef struct {
   int32_t views_degree;       /* <= 4, or < 0 when the variant has no view branch */
   int32_t side_count;
   srf_mlp_layer layers[12];
+  /* 0: bf16 operands (fp32 accumulate).  > 0: split-bf16 operands for the 1e-3 fp32 contract (inference only): activations and
+   * weights are pairs hi = bf16(x), lo = bf16(x - hi), a K block contributes A_hi W_hi + A_lo W_hi + A_hi W_lo, and the lo image
+   * of the weight image at byte offset o of `weights` sits at o + lo_offset (a multiple of 16). */
+  int64_t lo_offset;
 } srf_mlp_program;
 
 /*   rays_o, rays_d [R,3]: origin / direction the sample points are built from (the NDC pair when ndc);

@@ -46,6 +46,10 @@ struct MlpProgram {
   int32_t views_degree;         // of the view directions (<= 4); < 0: no view branch
   int32_t side_count;           // floats in the side table
   MlpLayer layers[MLP_MAX_LAYERS];
+  // 0: bf16 operands.  > 0: split-bf16 ("bf16x3") operands for the fp32 contract: every activation and weight is a pair
+  // hi = bf16(x), lo = bf16(x - hi); a K block contributes A_hi W_hi + A_lo W_hi + A_hi W_lo (relative error ~2^-16 per
+  // product instead of 2^-8); the lo image of the weight image at byte offset o of the blob sits at o + lo_offset
+  int64_t lo_offset;
 };
 
 struct MlpArgs {
@@ -116,8 +120,11 @@ constexpr int SAVE_BUFS = 4;
 constexpr int SAVE_STAGES = NUM_STAGES - SAVE_BUFS * IMAGE_BYTES / STAGE_BYTES;
 constexpr int A_REGIONS = 2;                      // E and V only; the hidden activations live in tensor memory
 constexpr int V_REGION = 1;
+// split-bf16 mode: the lo parts of E and V take the last two ring stages (the ring shrinks to NUM_STAGES - 2)
+constexpr int LO_STAGES = 2 * KBLOCK_BYTES / STAGE_BYTES;
+constexpr int E_LO_STAGE = NUM_STAGES - LO_STAGES, V_LO_STAGE = E_LO_STAGE + KBLOCK_BYTES / STAGE_BYTES;
 constexpr int MAX_SIDE = 4096;                    // floats
-constexpr int MAX_STEPS = 2 * MLP_MAX_LAYERS * MLP_MAX_KBLOCKS;
+constexpr int MAX_STEPS = 224;                    // bf16: <= 74 steps for the shipped variants; split-bf16 issues three per K block
 
 // One step of the MMA issuers = the (up to) four K=16 MMAs of one 64-wide K block [of one 128-column half].  The host
 // flattens the layer program into this schedule and passes it as a kernel parameter (constant bank); the producer streams
@@ -166,9 +173,28 @@ __device__ __forceinline__ void encode_octaves(float x, int k0, int count, F&& e
   }
 }
 
+// split-bf16 mode: one accurate sincosf per octave (2^k x is exact in fp32; the doubling recurrence above loses ~1 bit per octave,
+// invisible under bf16 rounding but not against the 1e-3 fp32 contract)
+template <typename F>
+__device__ __forceinline__ void encode_octaves_exact(float x, int count, F&& emit) {
+  for (int k = 0; k < count; ++k) {
+    float s, c;
+    sincosf(ldexpf(x, k), &s, &c);
+    emit(k, s, c);
+  }
+}
+
 __device__ __forceinline__ void store_bf16(uint8_t* block, int row, int col, float v) {
   const uint32_t off = ptx::sw128_offset(row, col >> 3) + ((col & 7) << 1);
   *reinterpret_cast<__nv_bfloat16*>(block + off) = __float2bfloat16_rn(v);
+}
+
+// split-bf16: hi into `block`, the bf16 of the remainder into `block_lo`
+__device__ __forceinline__ void store_bf16_split(uint8_t* block, uint8_t* block_lo, int row, int col, float v) {
+  const uint32_t off = ptx::sw128_offset(row, col >> 3) + ((col & 7) << 1);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(block + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(block_lo + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 template <int N>
@@ -207,7 +233,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
   const int num_tiles = (int)((total + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : NUM_STAGES;
+  const bool split = prog.lo_offset != 0;          // split-bf16 operands (launcher: never together with save_acts / rows)
+  const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : (split ? (uint32_t)E_LO_STAGE : NUM_STAGES);
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
   if (warp == PRODUCER_WARP) {
@@ -312,16 +339,30 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(E + ptx::sw128_offset(row, u)) = x[u];
       } else {
         const int deg = prog.points_degree;
+        if (split) {
+          uint8_t* E_lo = sm.w[E_LO_STAGE];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          store_bf16(E, row, c, p[c]);
-          if (deg > 0)
-            encode_octaves(p[c], 0, deg, [&](int k, float s, float co) {
-              store_bf16(E, row, 3 + 6 * k + c, s);
-              store_bf16(E, row, 6 + 6 * k + c, co);
-            });
+          for (int c = 0; c < 3; ++c) {
+            store_bf16_split(E, E_lo, row, c, p[c]);
+            if (deg > 0)
+              encode_octaves_exact(p[c], deg, [&](int k, float s, float co) {
+                store_bf16_split(E, E_lo, row, 3 + 6 * k + c, s);
+                store_bf16_split(E, E_lo, row, 6 + 6 * k + c, co);
+              });
+          }
+          for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16_split(E, E_lo, row, c, 0.f);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            store_bf16(E, row, c, p[c]);
+            if (deg > 0)
+              encode_octaves(p[c], 0, deg, [&](int k, float s, float co) {
+                store_bf16(E, row, 3 + 6 * k + c, s);
+                store_bf16(E, row, 6 + 6 * k + c, co);
+              });
+          }
+          for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
         }
-        for (int c = 3 + 6 * deg; c < 64; ++c) store_bf16(E, row, c, 0.f);
       }
       if (args.save_acts != nullptr) {                 // each thread re-reads the row it just wrote
         uint8_t* dst = args.save_acts + ((size_t)tile * act_tile_images(args.act_slots) + args.e_slot) * KBLOCK_BYTES;
@@ -343,16 +384,30 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 #pragma unroll
           for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(V + ptx::sw128_offset(row, u)) = x[8 + u];
         } else {
+          if (split) {
+            uint8_t* V_lo = sm.w[V_LO_STAGE];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            store_bf16(V, row, c, vd[c]);
-            if (vdeg > 0)
-              encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
-                store_bf16(V, row, 3 + 6 * k + c, s);
-                store_bf16(V, row, 6 + 6 * k + c, co);
-              });
+            for (int c = 0; c < 3; ++c) {
+              store_bf16_split(V, V_lo, row, c, vd[c]);
+              if (vdeg > 0)
+                encode_octaves_exact(vd[c], vdeg, [&](int k, float s, float co) {
+                  store_bf16_split(V, V_lo, row, 3 + 6 * k + c, s);
+                  store_bf16_split(V, V_lo, row, 6 + 6 * k + c, co);
+                });
+            }
+            for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16_split(V, V_lo, row, c, 0.f);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              store_bf16(V, row, c, vd[c]);
+              if (vdeg > 0)
+                encode_octaves(vd[c], 0, vdeg, [&](int k, float s, float co) {
+                  store_bf16(V, row, 3 + 6 * k + c, s);
+                  store_bf16(V, row, 6 + 6 * k + c, co);
+                });
+            }
+            for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16(V, row, c, 0.f);
           }
-          for (int c = 3 + 6 * vdeg; c < 32; ++c) store_bf16(V, row, c, 0.f);
         }
         if (args.save_acts != nullptr) {
           uint8_t* dst = args.save_acts + ((size_t)tile * act_tile_images(args.act_slots) + args.v_slot) * KBLOCK_BYTES;
@@ -395,6 +450,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 
         // bias + activation (+ head partial dot products) on one COLS-column slice, packed to bf16 pairs
         uint32_t mask_bits = 0;
+        uint32_t pk_lo[COLS / 2];                                  // split-bf16: bf16 of the remainders x - float(bf16(x))
+        auto split_pairs = [&](const float (&x)[COLS], uint32_t (&pk)[COLS / 2]) {
+#pragma unroll
+          for (int j = 0; j < COLS / 2; ++j) {
+            const uint32_t h = ptx::pack_bf16(x[2 * j], x[2 * j + 1]);
+            pk[j] = h;
+            pk_lo[j] = ptx::pack_bf16(x[2 * j] - __uint_as_float(h << 16), x[2 * j + 1] - __uint_as_float(h & 0xffff0000u));
+          }
+        };
         auto compute = [&](uint32_t (&v)[COLS], uint32_t (&pk)[COLS / 2], int kb) {
           const int col0 = kb * 64 + grp * COLS;
           const uint32_t b4 = bias_addr + (uint32_t)kb * 256u;
@@ -414,6 +478,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 #pragma unroll
             for (int i = COLS - 1; i >= 0; --i) bits = __funnelshift_l(0u - __float_as_uint(x[i]), bits, 1);
             mask_bits = bits;
+          }
+          if (head_rows == 0 && split) {
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < COLS; ++j) x[j] = fmaxf(x[j], 0.f);
+            }
+            split_pairs(x, pk);
+            return;
           }
           if (head_rows == 0) {                                    // plain hidden layer: ReLU rides on the bf16 conversion (F2FP.RELU)
             if (relu) {
@@ -456,6 +528,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           if (head_rows == 1) head_dot(std::integral_constant<int, 1>{});
           else if (head_rows == 3) head_dot(std::integral_constant<int, 3>{});
           else head_dot(std::integral_constant<int, 4>{});
+          if (split) { split_pairs(x, pk); return; }
 #pragma unroll
           for (int j = 0; j < COLS / 2; ++j) pk[j] = ptx::pack_bf16(x[2 * j], x[2 * j + 1]);
         };
@@ -466,6 +539,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained: K block kb of the
             // next layer's A operand never leaves tensor memory
             ptx::tmem_st16(t_row + kb * 64, pk);
+            if (split) ptx::tmem_st16(t_row + kb * 64 + 16, pk_lo);      // the other 16 columns of the drained slice
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
@@ -602,6 +676,11 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
   MmaSchedule sc{};
   int ns = 0, last_e = -1, last_v = -1;
   uint32_t seen = 0;
+  const bool split = prog.lo_offset != 0;
+  // split-bf16: a K block is three steps (A_hi W_hi, A_lo W_hi, A_hi W_lo).  The lo halves of a hidden block sit 16 columns
+  // behind the hi halves in tensor memory; the lo images of E / V occupy the last ring stages.
+  const uint32_t smem_lo[2] = {(uint32_t)(offsetof(MlpSmem, w) + (size_t)E_LO_STAGE * STAGE_BYTES - offsetof(MlpSmem, a)) >> 4,
+                               (uint32_t)(offsetof(MlpSmem, w) + (size_t)V_LO_STAGE * STAGE_BYTES - offsetof(MlpSmem, a)) >> 4};
   for (int l = 0; l < prog.num_layers; ++l) {
     const MlpLayer& L = prog.layers[l];
     const int halves = SRF_MLP_SPLIT ? L.n >> 7 : 1;
@@ -611,20 +690,27 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
     // only need the first K blocks of the previous layer's output
     for (int c0 = 0; c0 < L.num_kblocks; c0 += SRF_MLP_CHUNK)
     for (int h = 0; h < halves; ++h) {
-      for (int kb = c0; kb < L.num_kblocks && kb < c0 + SRF_MLP_CHUNK; ++kb, ++ns) {
-        MmaStep& st = sc.steps[ns];
+      for (int kb = c0; kb < L.num_kblocks && kb < c0 + SRF_MLP_CHUNK; ++kb) {
         const int reg = L.kblock_region[kb];
-        st.a_off = reg == 0 ? 0u : (reg == 5 ? (uint32_t)(V_REGION * KBLOCK_BYTES) >> 4 : (uint32_t)(reg - 1) * 64u);
-        st.idesc = ptx::make_idesc_bf16(128, (uint32_t)(128 * images));
-        const bool wait = !((seen >> reg) & 1);
-        seen |= 1u << reg;
-        st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 ? 8u : 0u) | (kb == L.num_kblocks - 1 ? 0x10u : 0u) | ((uint32_t)h << 7) |
-                  (wait ? (uint32_t)(reg + 1) << 8 : 0u) | ((uint32_t)(l & 1) << 12) | (reg >= 1 && reg <= 4 ? 0x2000u : 0u) |
-                  ((uint32_t)images << 16) | ((uint32_t)L.num_kblocks << 18);
-        // blob order: [layer][128-row half][K block]
-        st.w_off = (uint32_t)((L.weight_offset + (int64_t)(h * L.num_kblocks + kb) * IMAGE_BYTES) >> 4);
-        if (reg == 0) last_e = ns;
-        if (reg == 5) last_v = ns;
+        const int terms = split ? 3 : 1;
+        for (int term = 0; term < terms; ++term, ++ns) {
+          MmaStep& st = sc.steps[ns];
+          const bool a_lo = term == 1, w_lo = term == 2;
+          if (reg == 0) st.a_off = a_lo ? smem_lo[0] : 0u;
+          else if (reg == 5) st.a_off = a_lo ? smem_lo[1] : (uint32_t)(V_REGION * KBLOCK_BYTES) >> 4;
+          else st.a_off = (uint32_t)(reg - 1) * 64u + (a_lo ? 16u : 0u);
+          st.idesc = ptx::make_idesc_bf16(128, (uint32_t)(128 * images));
+          const bool wait = !((seen >> reg) & 1);
+          seen |= 1u << reg;
+          st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 && term == 0 ? 8u : 0u) |
+                    (kb == L.num_kblocks - 1 && term == terms - 1 ? 0x10u : 0u) | ((uint32_t)h << 7) |
+                    (wait ? (uint32_t)(reg + 1) << 8 : 0u) | ((uint32_t)(l & 1) << 12) | (reg >= 1 && reg <= 4 ? 0x2000u : 0u) |
+                    ((uint32_t)images << 16) | ((uint32_t)L.num_kblocks << 18);
+          // blob order: [layer][128-row half][K block]
+          st.w_off = (uint32_t)((L.weight_offset + (int64_t)(h * L.num_kblocks + kb) * IMAGE_BYTES + (w_lo ? prog.lo_offset : 0)) >> 4);
+          if (reg == 0) last_e = ns;
+          if (reg == 5) last_v = ns;
+        }
       }
     }
     if (L.write_h) seen &= ~0x1Eu;          // the epilogue of this layer rewrites H: re-acquire its blocks
@@ -644,8 +730,17 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
   return sc;
 }
 
+int schedule_steps(const MlpProgram& prog) {
+  int n = 0;
+  for (int l = 0; l < prog.num_layers; ++l) n += prog.layers[l].num_kblocks * (SRF_MLP_SPLIT ? prog.layers[l].n >> 7 : 1);
+  return n * (prog.lo_offset != 0 ? 3 : 1);
+}
+
 int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, void* stream, const char* where) {
   const size_t smem = sizeof(MlpSmem);
+  SRF_REQUIRE(schedule_steps(prog) <= MAX_STEPS, where, "layer program needs more MMA steps than the schedule holds");
+  SRF_REQUIRE(prog.lo_offset == 0 || (prog.lo_offset > 0 && (prog.lo_offset & 15) == 0 && a.save_acts == nullptr && a.rows == nullptr),
+              where, "split-bf16 programs (lo_offset != 0) are inference-only: no saved activation tiles, no rows mode");
   const MmaSchedule sched = make_schedule(prog);
   static bool configured = false;
   if (!configured) {

@@ -355,12 +355,16 @@ class MLP(torch.nn.Module):
         return noise.reshape(-1)
 
     def evaluate(self, rays_o, rays_d, z, view_dirs, noise):
-        """-> sigma [R,S,1], rgb [R,S,3]; differentiable w.r.t. the parameters when grad is enabled."""
+        """-> sigma [R,S,1], rgb [R,S,3]; differentiable w.r.t. the parameters when grad is enabled.
+        `configs['model']['mlp_precision']`: 'bf16' (default: bf16 operands, fp32 accumulation; stated looser tolerance) or
+        'bf16x3' (split-bf16 operands: fp32-contract accuracy at three MMAs per K block; gradient-free evaluation only —
+        a differentiable call keeps the bf16 program, whose saved tiles the backward kernels read)."""
         packed = self.packed()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             names = packed.param_names
             return _FusedMLP.apply(self, rays_o, rays_d, z, view_dirs, noise, *[self.named_param_dict()[n] for n in names])
-        return packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise)
+        split = self.configs['model'].get('mlp_precision', 'bf16') == 'bf16x3'
+        return packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise, split=split)
 
 
 class _FusedMLP(torch.autograd.Function):

@@ -28,7 +28,7 @@ class MlpLayer(ctypes.Structure):
 
 class MlpProgram(ctypes.Structure):
     _fields_ = [('num_layers', ctypes.c_int32), ('points_degree', ctypes.c_int32), ('views_degree', ctypes.c_int32),
-                ('side_count', ctypes.c_int32), ('layers', MlpLayer * MAX_LAYERS)]
+                ('side_count', ctypes.c_int32), ('layers', MlpLayer * MAX_LAYERS), ('lo_offset', ctypes.c_int64)]
 
 
 def _enc_width(degree):
@@ -139,6 +139,11 @@ class PackedMLP:
         self.blob = None
         self.side = None
         self.offs = offs
+        # split-bf16 ("bf16x3") inference program for the 1e-3 fp32 contract: same layers, lo weight images behind the hi images
+        self.program_split = MlpProgram.from_buffer_copy(self.program)
+        self.program_split.lo_offset = self.blob_elems * 2
+        self.program_split.act_slots, self.program_split.v_slot = self.program.act_slots, self.program.v_slot
+        self.blob_split = None
         self.backward_plan = build_backward_plan(layers, shapes, offs, zero, self.program)
         macs = 0
         for name, n, kbs, *_ in layers:
@@ -160,13 +165,23 @@ class PackedMLP:
         self.flat = flat
         self.blob = flat[self._gather].to(torch.bfloat16).contiguous()
         self.side = flat[self._side_idx].contiguous()
+        self.blob_split = None
         return self
 
-    def forward(self, rays_o, rays_d, z, view_dirs=None, noise=None, save=False):
+    def split_blob(self):
+        """[hi images | lo images]: lo = bf16(w - float(bf16(w))), built on first use after a refresh."""
+        if self.blob_split is None:
+            w = self.flat[self._gather]
+            self.blob_split = torch.cat([self.blob, (w - self.blob.float()).to(torch.bfloat16)]).contiguous()
+        return self.blob_split
+
+    def forward(self, rays_o, rays_d, z, view_dirs=None, noise=None, save=False, split=False):
         """rays_o/rays_d [R,3] (the origin/direction the sample points are built from), z [R,S].
         Returns sigma [R,S,1], rgb [R,S,3] (post-activation, as MLP.forward returns them); with save=True also
-        acts uint8 [tiles, act_slots, 16384] (the saved activation tile images) for the backward kernels."""
+        acts uint8 [tiles, act_slots, 16384] (the saved activation tile images) for the backward kernels.
+        split=True: split-bf16 operands (three MMAs per K block, fp32-contract accuracy; inference only)."""
         assert self.blob is not None, 'call refresh(params) first'
+        assert not (split and save), 'the split-bf16 program is inference-only'
         L.require_cuda(rays_o, rays_d, z, view_dirs, noise)
         rays_o, rays_d, z = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z)
         view_dirs, noise = L.f32c(view_dirs), L.f32c(noise)
@@ -176,14 +191,15 @@ class PackedMLP:
         if self.use_views and view_dirs is None:
             raise L.SimpleRFNativeError('this MLP variant needs view_dirs')
         acts = None
-        prog = self.program
+        prog = self.program_split if split else self.program
+        blob = self.split_blob() if split else self.blob
         if save:
             tiles = (R * S + 127) // 128
             acts = torch.empty((tiles, act_tile_images(prog.act_slots), 16384), dtype=torch.uint8, device=z.device)
-        L.call('srf_nerf_mlp_fwd', ctypes.addressof(prog), L.ptr(self.blob), L.ptr(self.side), L.ptr(rays_o),
+        L.call('srf_nerf_mlp_fwd', ctypes.addressof(prog), L.ptr(blob), L.ptr(self.side), L.ptr(rays_o),
                L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs if self.use_views else None), L.ptr(noise), R, S,
                L.ptr(sigma), L.ptr(rgb), L.ptr(acts), prog.act_slots if save else 0, 0, max(prog.v_slot, 0),
-               L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)
+               L.stream_handle(), work=2.0 * self.macs_per_sample * R * S)    # algorithmic FLOPs (the split program issues 3x the MMAs)
         if save:
             return sigma, rgb, acts
         return sigma, rgb

@@ -82,3 +82,58 @@ def test_mlp_is_row_independent_at_scale(golden_configs):
     s2, c2 = packed.forward(o[perm], d[perm], z[perm], vd[perm])
     assert torch.equal(s1[perm], s2) and torch.equal(c1[perm], c2)
     assert torch.isfinite(s1).all() and torch.isfinite(c1).all()
+
+
+def _sharpened(params, gain=4.0, head=2.0):
+    """Default-initialised weights pushed towards what training produces (sigma of 10^1 - 10^3, saturated
+    colours): the default initialisation shrinks activations by ~0.4 per layer, a gain of 4 makes them grow by ~1.6 per layer
+    (hidden activations of 10^1 - 10^2 at the heads), and the sigma bias keeps the field occupied."""
+    out = {k: v.clone() for k, v in params.items()}
+    for k in out:
+        if k.startswith('pts_linears') and k.endswith('weight'):
+            out[k] *= gain
+    out['pts_output_linear.weight'] *= head
+    out['pts_output_linear.bias'][0] += 30.0
+    if 'views_output_linear.weight' in out:
+        out['views_output_linear.weight'] *= 4.0
+    return out
+
+
+@pytest.mark.parametrize('variant', ['main', 'points_augmentation', 'views_augmentation'])
+@pytest.mark.parametrize('R,S', [(300, 192), (41, 64), (1, 1)])
+def test_split_bf16_program_meets_the_fp32_contract(golden_configs, variant, R, S):
+    """`mlp_precision = 'bf16x3'`: sigma / rgb within 1e-3 of the fp32 reference arithmetic (evaluated in fp64) on a sharpened
+    field where the plain bf16 program is 30-100x further away."""
+    from simple_rf_b200 import nerf_program
+    configs, mc, variants = _variants(golden_configs)
+    cfg = variants[variant]
+    g = torch.Generator().manual_seed(7 + R)
+    params = _sharpened(M.init_mlp_params(cfg, g))
+    K = torch.tensor(mc['intrinsics']); E = torch.tensor(mc['extrinsics'])
+    h, w = mc['resolution']
+    pid = FX.random_pixels(R, K.shape[0], h, w, seed=R + 1)
+    ro, rd = RY.camera_rays(pid, K, E, half_pixel=False, flip_x=False)
+    img = pid[:, 0].long()
+    on, dn = RY.ndc_rays(ro, rd, h, w, K[img, 0, 0], K[img, 1, 1], mc['near'])
+    vd = RY.view_dirs(rd)
+    z = SP.stratified_depths(SP.coarse_depths(S, 0., 1.), R, torch.rand(R, S, generator=g))
+    pts = (on[:, None, :] + dn[:, None, :] * z[..., None]).reshape(-1, 3)
+    vflat = vd[:, None].expand(R, S, 3).reshape(-1, 3)
+    ref = M.mlp_forward({k: v.double() for k, v in params.items()}, cfg, pts.double(), vflat.double() if cfg['use_view_dirs'] else None, None)
+    ref32 = M.mlp_forward(params, cfg, pts, vflat if cfg['use_view_dirs'] else None, None)
+    packed = nerf_program.PackedMLP(cfg).refresh({k: v.to(DEV) for k, v in params.items()})
+    errs = {}
+    for tag, split in (('bf16', False), ('bf16x3', True)):
+        sigma, rgb = packed.forward(on.to(DEV), dn.to(DEV), z.to(DEV), vd.to(DEV), None, split=split)
+        torch.cuda.synchronize()
+        errs[tag] = ((sigma.cpu().reshape(-1, 1).double() - ref['sigma']).abs().max().item(),
+                     (rgb.cpu().reshape(-1, 3).double() - ref['rgb']).abs().max().item())
+    smax = ref['sigma'].max().item()
+    fp32_noise = ((ref32['sigma'].double() - ref['sigma']).abs().max().item(), (ref32['rgb'].double() - ref['rgb']).abs().max().item())
+    print(f'{variant} R={R} S={S}: sigma max {smax:.1f}; |d sigma|, |d rgb|: bf16 {errs["bf16"][0]:.2e} {errs["bf16"][1]:.2e}  '
+          f'bf16x3 {errs["bf16x3"][0]:.2e} {errs["bf16x3"][1]:.2e}  (fp32 CPU vs fp64: {fp32_noise[0]:.1e} {fp32_noise[1]:.1e})')
+    assert errs['bf16x3'][0] <= 1e-3 * max(1.0, smax), errs
+    assert errs['bf16x3'][1] <= 1e-3, errs
+    if R * S > 1000:
+        assert smax > 10.0                                            # the field really is sharp
+        assert errs['bf16x3'][0] * 20 < errs['bf16'][0] and errs['bf16x3'][1] * 20 < errs['bf16'][1], errs

@@ -51,6 +51,25 @@ def test_dropin_forward_vs_reference_golden(golden, golden_configs, mode):
     assert expect <= set(out.keys())
 
 
+def test_dropin_eval_split_bf16_meets_the_fp32_contract(golden, golden_configs):
+    """`configs['model']['mlp_precision'] = 'bf16x3'`: every map and per-sample tensor of the test-time render within 1e-3 of the
+    unmodified fp32 reference (north_star's bound for fp32 paths), fine depths included."""
+    g = golden('nerf_eval')
+    model, configs, mc = _model(golden_configs, int(g['param_seed']))
+    model.configs['model']['mlp_precision'] = 'bf16x3'
+    model.eval()
+    with torch.no_grad():
+        out = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+    worst = {}
+    for k, ref in g.items():
+        if k not in out or ref.dtype != torch.float32:
+            continue
+        worst[k] = (out[k].cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        assert worst[k] <= 1e-3, (k, worst[k])
+    print('bf16x3 worst:', sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    assert {'rgb_fine', 'depth_fine', 'weights_fine', 'raw_sigma_coarse', 'z_vals_fine'} <= set(worst)
+
+
 def test_dropin_retraw_false_drops_per_sample_outputs(golden, golden_configs):
     g = golden('nerf_eval')
     model, *_ = _model(golden_configs, int(g['param_seed']))

@@ -70,28 +70,40 @@ def main():
     ys, xs = numpy.meshgrid(numpy.arange(0, h, 2, dtype=numpy.int32), numpy.arange(0, w, 2, dtype=numpy.int32), indexing='ij')
     pid = torch.from_numpy(numpy.stack([numpy.ones(xs.size, dtype=numpy.int32), xs.reshape(-1), ys.reshape(-1)], 1)).cuda()
     outs = {}
-    for tag, cfg in (('dropin', configs(True, 'reference')), ('reference', configs(False, None))):
+    for tag, cfg in (('dropin', configs(True, 'reference')), ('dropin_bf16x3', configs(True, 'reference')), ('reference', configs(False, None))):
+        if tag == 'dropin_bf16x3':
+            cfg['model']['mlp_precision'] = 'bf16x3'             # split-bf16 operands: the fp32-contract program
         tester = C.make_tester(cfg, mc, [0])
         tester.model.load_state_dict(state)
         tester.model.eval()
         with torch.no_grad():
             outs[tag] = tester.model.module({'pixel_id': pid, 'num_frames': 3}, retraw=True)
         del tester
-    a, b = outs['dropin'], outs['reference']
-    ev = {}
-    for k in ('rgb_coarse', 'rgb_fine', 'acc_fine', 'depth_fine', 'depth_ndc_fine', 'depth_ndc_coarse', 'weights_fine', 'weights_coarse',
-              'raw_sigma_fine', 'raw_sigma_coarse', 'raw_rgb_fine', 'z_vals_fine'):
-        ev.update(stats(a[k], b[k], k))
+    b = outs['reference']
     sig = b['raw_sigma_fine'].float()
-    ev['sigma_fine_p50'], ev['sigma_fine_p99'], ev['sigma_fine_max'] = (float(torch.quantile(sig.flatten()[:4_000_000], q)) for q in (0.5, 0.99, 1.0))
-    ev['weights_fine_peak_median'] = float(b['weights_fine'].max(dim=1)[0].median())
-    # sigma error where it matters: relative to max(sigma, 1) on samples carrying weight
-    wmask = b['weights_fine'] > 1e-3
-    rel = ((a['raw_sigma_fine'][..., 0] - sig[..., 0]).abs() / sig[..., 0].clamp_min(1.0))[wmask]
-    ev['sigma_rel_err_on_weighted_samples_max'] = float(rel.max()) if rel.numel() else 0.0
-    ev['sigma_rel_err_on_weighted_samples_p99'] = float(torch.quantile(rel[:4_000_000], 0.99)) if rel.numel() else 0.0
-    report['eval'] = ev
-    print(json.dumps(ev, indent=1), flush=True)
+    for tag, key in (('dropin', 'eval'), ('dropin_bf16x3', 'eval_bf16x3')):
+        a = outs[tag]
+        ev = {}
+        for k in ('rgb_coarse', 'rgb_fine', 'acc_fine', 'depth_fine', 'depth_ndc_fine', 'depth_ndc_coarse', 'weights_fine', 'weights_coarse',
+                  'raw_sigma_fine', 'raw_sigma_coarse', 'raw_rgb_fine', 'raw_rgb_coarse', 'z_vals_fine'):
+            ev.update(stats(a[k], b[k], k))
+        ev['sigma_fine_p50'], ev['sigma_fine_p99'], ev['sigma_fine_max'] = (float(torch.quantile(sig.flatten()[:4_000_000], q)) for q in (0.5, 0.99, 1.0))
+        ev['weights_fine_peak_median'] = float(b['weights_fine'].max(dim=1)[0].median())
+        # rays whose fine depths coincide (the inverse-CDF resampling is discontinuous: a coarse weight moving by 1e-6 can move
+        # a fine sample to the neighbouring bin) carry the clean per-sample comparison of the fine stage
+        same = (a['z_vals_fine'] - b['z_vals_fine']).abs().amax(dim=1) <= 1e-6
+        ev['rays_with_identical_fine_depths'] = float(same.float().mean())
+        if same.any():
+            for k in ('rgb_fine', 'depth_fine', 'weights_fine', 'raw_sigma_fine', 'raw_rgb_fine'):
+                ev.update(stats(a[k][same], b[k][same], f'same_z_{k}'))
+        # sigma error where it matters: relative to max(sigma, 1) on samples carrying weight
+        wmask = b['weights_coarse'] > 1e-3
+        sc = b['raw_sigma_coarse'].float()[..., 0]
+        rel = ((a['raw_sigma_coarse'][..., 0] - sc).abs() / sc.clamp_min(1.0))[wmask]
+        ev['sigma_coarse_rel_err_on_weighted_samples_max'] = float(rel.max()) if rel.numel() else 0.0
+        ev['sigma_coarse_rel_err_on_weighted_samples_p99'] = float(torch.quantile(rel[:4_000_000], 0.99)) if rel.numel() else 0.0
+        report[key] = ev
+        print(tag, json.dumps(ev, indent=1), flush=True)
     del outs, a, b
 
     # ---- gradients of one training iteration on the trained weights: same batch, same CPU random stream
