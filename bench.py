@@ -502,6 +502,30 @@ def sharded_frame(dist, setup, steps=4, warmup=2):
             'config': {'workload': 'simple_nerf_frame_render_sharded', 'frame': mc['resolution'], 'collective': 'one all_gather_into_tensor of the per-ray record per frame'}}
 
 
+def split_precision_frame(dist, setup, steps=2, warmup=1):
+    """The main workload with `mlp_precision = 'bf16x3'` (split-bf16 operands, three MMAs per K block): the program that meets
+    the 1e-3 fp32 contract on trained fields.  One independent frame per rank, as the main line."""
+    from simple_rf_b200 import synthetic
+    model, mc = setup['model'], setup['model_configs']
+    pid = torch.from_numpy(synthetic.frame_pixel_ids(*mc['resolution'], view=0)).to(dist.device)
+    model.configs['model']['mlp_precision'] = 'bf16x3'
+
+    def render(step):
+        with torch.no_grad():
+            model({'pixel_id': pid, 'num_frames': 1})
+    try:
+        ms, timing, launches = timed_steps(dist, render, steps, warmup, collect=True)
+    finally:
+        model.configs['model']['mlp_precision'] = 'bf16'
+    peaks = measured_peaks()
+    res = {'metric': 'rendered_rays_per_sec', 'value': pid.shape[0] * dist.world * 1e3 / (ms / steps), 'unit': 'rays/s', 'ms_per_step': ms / steps,
+           'scaling': 'weak', 'n_gpus': dist.world, 'steps': steps, 'warmup': warmup, 'dtype': 'split bf16 (hi + lo operand pairs, fp32 accumulate)',
+           'config': {'workload': 'simple_nerf_frame_render', 'mlp_precision': 'bf16x3', 'frame': mc['resolution']},
+           'roofline': roofline_of(kernel_table(timing), ['srf_nerf_mlp_fwd'], 'tensor', peaks['bf16_tflops_sustained'], 'TFLOP/s', ms,
+                                   peaks['source'] + ', sustained bf16; algorithmic FLOPs (the program issues 3x the MMAs)', 'nerf_mlp_fwd_kernel<split>', None)}
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ reference (CPU / eager CUDA)
 def reference_render_setup(device_ids, chunk):
     """The UNMODIFIED reference classes for the main workload: NerfTester (src/Tester07.py:30-48) with SimpleNeRF17.  Call under
@@ -691,6 +715,7 @@ def run_ours(args, rank, world, device):
             guarded('simple_nerf_train_strong', lambda: train_workload('nerf', dist, 'strong'))
         guarded('simple_tensorf_train_weak', lambda: train_workload('tensorf', dist, 'weak'))
         guarded('simple_tensorf_trajectory', lambda: tensorf_trajectory(dist))
+        guarded('simple_nerf_frame_bf16x3', lambda: split_precision_frame(dist, setup))
         if world > 1:
             guarded('simple_nerf_frame_sharded', lambda: sharded_frame(dist, setup))
         if world == 1 and rank == 0 and reference_available():

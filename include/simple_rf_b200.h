@@ -272,6 +272,11 @@ int srf_dgrad_program_bytes(void);
  * entry_sample / entry_weight ([num_rays, num_samples], first ray_count[r] entries valid).  z_vals, dense sigma / weights are
  * NOT produced: callers that need them (`retraw`, training) use the unfused entry points above.  num_rays * num_samples < 2^31.
  * bbox = [min xyz | max xyz], box_size = the tensor's bounding_box_size buffer (host pointers, 6 + 3 floats); alpha_* nullable.
+ * alpha_corner_or (nullable, DEVICE, srf_alpha_corner_or_words(alpha_res) words from srf_alpha_corner_or_bits): bit (x,y,z) of
+ * the (X+1)(Y+1)(Z+1) volume = OR of the alpha bits at (x-1..x, y-1..y, z-1..z).  A point whose approximate voxel coordinates
+ * all lie >= 1/256 voxel away from a voxel boundary is decided by ONE bit of it (both trilinear weights of every axis are then
+ * strictly positive, so grid_sample(...) > 0 <=> some in-range corner is set); points next to a boundary take the exact test —
+ * the validity set is unchanged.  num_samples <= 65535.
  *
  * srf_tensorf_march_compact: the per-ray lists -> one flat list in row-major (ray, sample) order — the order of the
  * reference's boolean-mask indexing (:1248) — indices[j] = ray * num_samples + sample, weights[j], ray_offset[ray], *count.
@@ -281,11 +286,13 @@ int srf_dgrad_program_bytes(void);
  * background): the colour half of volume_render (:813-817) over the surface samples only (rgb is 0 elsewhere, :1271). */
 int srf_tensorf_march(const float* rays_o_ndc, const float* rays_d_ndc, const float* rays_o, const float* rays_d,
                       const float* ladder, int64_t num_rays, int num_samples, const float* bbox, const float* box_size,
-                      const uint32_t* alpha_bits, const int* alpha_res, const float* alpha_box_min, const float* alpha_box_size,
-                      const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
-                      int softplus, float density_offset, float distance_scale, float weight_threshold,
+                      const uint32_t* alpha_bits, const uint32_t* alpha_corner_or, const int* alpha_res, const float* alpha_box_min,
+                      const float* alpha_box_size, const float* const* planes, const float* const* lines, const int* channels,
+                      const int* resolution, int softplus, float density_offset, float distance_scale, float weight_threshold,
                       float* acc, float* depth, float* depth_var, float* depth_ndc, float* depth_var_ndc,
                       int* ray_count, int* entry_sample, float* entry_weight, void* stream);
+int srf_alpha_corner_or_words(const int* alpha_res);
+int srf_alpha_corner_or_bits(const uint32_t* alpha_bits, const int* alpha_res, uint32_t* corner_or, void* stream);
 int srf_tensorf_march_blocks(int64_t num_rays);
 int srf_tensorf_march_compact(const int* ray_count, int64_t num_rays, int num_samples, const int* entry_sample,
                               const float* entry_weight, int* scratch, int* ray_offset, int* indices, float* weights,

@@ -37,7 +37,9 @@ _SIGNATURES = {
     'srf_vm_density_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P]),
     'srf_vm_density_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P]),
     'srf_vm_color_features_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
-    'srf_tensorf_march': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float,
+    'srf_alpha_corner_or_words': (c_int, [_P]),
+    'srf_alpha_corner_or_bits': (c_int, [_P, _P, _P, _P]),
+    'srf_tensorf_march': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_tensorf_march_blocks': (c_int, [c_int64]),
     'srf_tensorf_march_compact': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),

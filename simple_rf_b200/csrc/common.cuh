@@ -53,6 +53,17 @@ __host__ __device__ inline size_t act_mask_offset(int act_slots, int slot) {
   return (size_t)(act_slots + slot / 16) * 16384 + (size_t)(slot % 16) * 1024;
 }
 
+// cudaFuncSetAttribute is a PER-DEVICE setting: true the first time `mask` is consulted on the current device (the caller then
+// configures the kernel).  Racing host threads may both configure - the call is idempotent.
+inline bool first_use_on_this_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -204,6 +204,7 @@ __device__ __forceinline__ void tmem_load<32>(uint32_t taddr, uint32_t (&v)[32])
 template <>
 __device__ __forceinline__ void tmem_load<16>(uint32_t taddr, uint32_t (&v)[16]) { ptx::tmem_ld16(taddr, v); }
 
+template <bool SPLIT>             // SPLIT: split-bf16 operands (prog.lo_offset != 0); a separate instantiation keeps the bf16 path free of it
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __grid_constant__ MlpProgram prog,
                                                                       const __grid_constant__ MmaSchedule sched, const MlpArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
   const int num_tiles = (int)((total + 127) / 128);
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const bool split = prog.lo_offset != 0;          // split-bf16 operands (launcher: never together with save_acts / rows)
+  constexpr bool split = SPLIT;                    // (launcher: never together with save_acts / rows)
   const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : (split ? (uint32_t)E_LO_STAGE : NUM_STAGES);
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
@@ -742,15 +743,16 @@ int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, vo
   SRF_REQUIRE(prog.lo_offset == 0 || (prog.lo_offset > 0 && (prog.lo_offset & 15) == 0 && a.save_acts == nullptr && a.rows == nullptr),
               where, "split-bf16 programs (lo_offset != 0) are inference-only: no saved activation tiles, no rows mode");
   const MmaSchedule sched = make_schedule(prog);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool split = prog.lo_offset != 0;
+  auto* kernel = split ? nerf_mlp_fwd_kernel<true> : nerf_mlp_fwd_kernel<false>;
+  static unsigned long long configured[2] = {0ull, 0ull};          // per kernel instantiation, one bit per device
+  if (first_use_on_this_device(configured[split ? 1 : 0])) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(where, cudaGetErrorString(e));
-    configured = true;
   }
   const long long tiles = (max_total + 127) / 128;
   const int grid = tiles < sm_count() ? (int)tiles : sm_count();
-  nerf_mlp_fwd_kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, sched, a);
+  kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, sched, a);
   return check_launch(where);
 }
 }  // namespace

@@ -388,11 +388,10 @@ SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const
   a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dz = reinterpret_cast<uint8_t*>(dz); a.dz_slots = dz_slots; a.total = num_rows; a.count = count;
   a.g_rows = g_rows; a.g_row_pitch = g_row_pitch;
   const size_t smem = sizeof(DgradSmem);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;      // one bit per device
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(nerf_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("srf_nerf_mlp_dgrad", cudaGetErrorString(e));
-    configured = true;
   }
   const long long tiles = (num_rows + 127) / 128;
   const int grid = tiles < sm_count() ? (int)tiles : sm_count();

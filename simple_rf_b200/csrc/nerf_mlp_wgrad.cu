@@ -244,11 +244,10 @@ SRF_API int srf_nerf_mlp_wgrad(const void* items, int num_items, const void* act
   for (int i = 0; i < num_items; ++i) p.cta_first[i + 1] = p.cta_first[i] + share[i];
   const int grid = p.cta_first[num_items];
   const size_t smem = sizeof(WgradSmem);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;      // one bit per device
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(nerf_mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("srf_nerf_mlp_wgrad", cudaGetErrorString(e));
-    configured = true;
   }
   nerf_mlp_wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("srf_nerf_mlp_wgrad");

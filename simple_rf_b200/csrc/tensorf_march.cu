@@ -6,9 +6,11 @@
 // mask, a compacted index list, dense sigma and dense weights, and walks them in ~8 launches.  Here the only per-sample
 // traffic is the list of surface samples (8 % of the samples on the benchmark scene), written in ray order.
 //
-//   srf_tensorf_march          warp per ray; 32 consecutive samples per step (lane = sample); chunks without a valid sample
-//                              cost one box + occupancy test per lane; a ray stops once its transmittance is below 1e-7
-//                              (everything behind contributes < 1e-7 to any map; the surface threshold is 1e-4)
+//   srf_tensorf_march          warp per ray; chunks of 32 consecutive samples are TESTED (box, occupancy — one bit of the
+//                              corner-OR volume away from voxel boundaries, the exact trilinear test next to them) and the valid ones queued; density + compositing run on full batches of 32
+//                              valid samples; a ray stops once its transmittance is below 1e-7 (everything behind
+//                              contributes < 1e-7 to any map; the surface threshold is 1e-4)
+//   srf_alpha_corner_or_bits   derived cache: per cell of the alpha grid, the OR of its 8 corner bits
 //   srf_tensorf_march_compact  per-ray surface lists -> one flat list in row-major (ray, sample) order — exactly the order
 //                              of the reference's boolean-mask indexing (:1248) — + per-ray offsets
 //   srf_ray_accumulate         rgb_map[r] = sum_k w_k rgb_k over the ray's surface samples (+ white background), fixed order
@@ -28,6 +30,8 @@ struct MarchParams {
   const float* o_ndc; const float* d_ndc; const float* rays_o; const float* rays_d;
   const float* ladder;          // [S] sample depths shared by all rays
   float bsize[3];               // box size, as the host stores it (bounding_box_size buffer)
+  const uint32_t* alpha_or8;    // nullable: corner-OR volume of the alpha bits, (ax+1) x (ay+1) x (az+1) (srf_alpha_corner_or_bits)
+  float cscale[3];              // (alpha resolution - 1) / alpha box size: world offset -> voxel coordinate (approximate)
   int R, S, softplus;
   float offset, distance_scale, threshold;
   float* acc; float* depth; float* depth_var; float* depth_ndc; float* depth_var_ndc;   // [R]
@@ -83,14 +87,47 @@ struct Moments {
   }
 };
 
-__global__ void __launch_bounds__(MARCH_WARPS * 32) tensorf_march_kernel(const MarchParams p) {
+// Fast occupancy test on the corner-OR volume.  Away from voxel boundaries the exact trilinear test of alpha_hit() reduces to
+// "some in-range corner of the cell holds a 1": both weights of every axis are strictly positive, so every corner's weight
+// product is.  The corner-OR volume stores exactly that per cell (cell i0 = -1 .. dim-1 per axis, index i0 + 1), and the cell of a
+// point follows from a cheap approximate coordinate whenever its fractional part is at least EDGE away from 0 and 1 (the
+// approximate and the exact fp32 coordinate differ by < 1e-3 voxel for any resolution the < 2^31-voxel bound admits).
+// Returns +1 hit, 0 miss, -1 undecided (within EDGE of a boundary: run the exact test).
+__device__ __forceinline__ int corner_or_test(const MarchParams& p, const float (&pt)[3]) {
+  constexpr float EDGE = 1.f / 256.f;
+  const int dims[3] = {p.m.ax, p.m.ay, p.m.az};
+  int c[3];
+  bool outside = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float f = (pt[a] - p.m.ab0[a]) * p.cscale[a];
+    const float fl = floorf(f);
+    const float t = f - fl;
+    if (!(t > EDGE && t < 1.f - EDGE)) return -1;                // also catches NaN
+    const int i = (int)fl;
+    outside = outside || i < -1 || i > dims[a] - 1;
+    c[a] = i + 1;
+  }
+  if (outside) return 0;
+  const int v = (c[2] * (p.m.ay + 1) + c[1]) * (p.m.ax + 1) + c[0];
+  return (int)((__ldg(p.alpha_or8 + (v >> 5)) >> (v & 31)) & 1u);
+}
+
+// Warp per ray.  Two alternating phases: FILL tests chunks of 32 consecutive ladder samples (box, occupancy) and appends the valid sample indices to a per-warp queue; DRAIN takes 32 queued samples (lane = one VALID
+// sample: the density gather and the compositing arithmetic run with every lane busy), evaluates density, alpha with the
+// sample's own ladder interval, the transmittance scan and the per-ray sums.  Samples that fail the tests have alpha == 0 and
+// multiply the transmittance by fl(1 + 1e-10) == 1: skipping them changes nothing.  A ray stops once T < 1e-7.
+__global__ void __launch_bounds__(MARCH_WARPS * 32, 3) tensorf_march_kernel(const MarchParams p) {
   __shared__ float s_ladder[MARCH_MAX_SMEM_LADDER];
+  __shared__ unsigned short s_queue[MARCH_WARPS][64];
   const bool ladder_in_smem = p.S <= MARCH_MAX_SMEM_LADDER;
   if (ladder_in_smem)
     for (int i = threadIdx.x; i < p.S; i += blockDim.x) s_ladder[i] = p.ladder[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
+  unsigned short* queue = s_queue[warp];
+  auto depth_of = [&](int s) { return ladder_in_smem ? s_ladder[s] : __ldg(p.ladder + s); };
   for (int r = blockIdx.x * MARCH_WARPS + warp; r < p.R; r += gridDim.x * MARCH_WARPS) {
     float o[3], d[3];
 #pragma unroll
@@ -103,26 +140,43 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) tensorf_march_kernel(const M
     const float A = (oz + tn * wz) * iw;
     float T = 1.f;
     Moments mn{0.f, 0.f, 0.f}, mw{0.f, 0.f, 0.f};
-    int kcount = 0;
+    int kcount = 0, queued = 0, c0 = 0;
     const size_t row = (size_t)r * p.S;
-    for (int c0 = 0; c0 < p.S; c0 += 32) {
-      const int s = c0 + lane;
-      const bool active = s < p.S;
-      const float z = active ? (ladder_in_smem ? s_ladder[s] : __ldg(p.ladder + s)) : 1.f;
-      float pt[3];
-      bool ok = active;
+    while (true) {
+      // ---- fill: until a full batch is queued or the ladder is exhausted
+      while (queued < 32 && c0 < p.S) {
+        const int s = c0 + lane;
+        bool ok = s < p.S;
+        const float z = ok ? depth_of(s) : 1.f;
+        float pt[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        pt[a] = __fadd_rn(o[a], __fmul_rn(d[a], z));
-        ok = ok && (p.m.bb0[a] <= pt[a]) && (pt[a] <= p.m.bb1[a]);
+        for (int a = 0; a < 3; ++a) {
+          pt[a] = __fadd_rn(o[a], __fmul_rn(d[a], z));
+          ok = ok && (p.m.bb0[a] <= pt[a]) && (pt[a] <= p.m.bb1[a]);
+        }
+        if (ok && p.m.alpha_bits != nullptr) {
+          const int fast = p.alpha_or8 != nullptr ? corner_or_test(p, pt) : -1;
+          ok = fast >= 0 ? fast != 0 : alpha_hit(p.m, pt);
+        }
+        const unsigned bal = __ballot_sync(FULL, ok);
+        if (ok) queue[queued + __popc(bal & lt)] = (unsigned short)s;
+        queued += __popc(bal);
+        c0 += 32;
       }
-      if (ok && p.m.alpha_bits != nullptr) ok = alpha_hit(p.m, pt);
-      if (__ballot_sync(FULL, ok) == 0u) continue;                     // empty space: transmittance and sums unchanged
-      const float sigma = ok ? density_at(p, pt) : 0.f;
-      float zn = 1.f;                                                  // inf_depth of the NDC path (:781)
-      if (s + 1 < p.S) zn = ladder_in_smem ? s_ladder[s + 1] : __ldg(p.ladder + s + 1);
-      const float al = active ? 1.f - __expf(-sigma * ((zn - z) * ns)) : 0.f;
-      const float q = active ? (1.f - al + 1e-10f) : 1.f;
+      __syncwarp();
+      const int n = min(queued, 32);
+      if (n == 0) break;
+      // ---- drain: one batch of valid samples, in ladder order
+      const bool valid = lane < n;
+      const int s = valid ? (int)queue[lane] : p.S - 1;
+      const float z = depth_of(s);
+      float pt[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pt[a] = __fadd_rn(o[a], __fmul_rn(d[a], z));
+      const float sigma = valid ? density_at(p, pt) : 0.f;
+      const float zn = s + 1 < p.S ? depth_of(s + 1) : 1.f;            // last interval ends at inf_depth = 1 in NDC (:781)
+      const float al = valid ? 1.f - __expf(-sigma * ((zn - z) * ns)) : 0.f;
+      const float q = valid ? (1.f - al + 1e-10f) : 1.f;
       float incl = q;
 #pragma unroll
       for (int sh = 1; sh < 32; sh <<= 1) {
@@ -144,8 +198,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) tensorf_march_kernel(const M
         mn.merge(s0, mcn, warp_sum(w * dn * dn));
         mw.merge(s0, mcw, warp_sum(w * dw * dw));
       }
-      // surface samples of this chunk, in sample order
-      const bool surf = active && w > p.threshold;
+      // surface samples of this batch, in sample order
+      const bool surf = valid && w > p.threshold;
       const unsigned bal = __ballot_sync(FULL, surf);
       if (surf) {
         const size_t e = row + kcount + __popc(bal & lt);
@@ -154,6 +208,13 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) tensorf_march_kernel(const M
       }
       kcount += __popc(bal);
       if (T < 1e-7f) break;
+      // ---- keep what the batch did not take
+      const int left = queued - n;
+      const unsigned short keep = lane < left ? queue[32 + lane] : (unsigned short)0;
+      __syncwarp();
+      if (lane < left) queue[lane] = keep;
+      queued = left;
+      __syncwarp();
     }
     if (lane == 0) {
       const float acc = mn.W;
@@ -166,7 +227,28 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32) tensorf_march_kernel(const M
       p.depth_var[r] = mw.M2 + acc * (mw.mean - dw) * (mw.mean - dw);
       p.ray_count[r] = kcount;
     }
+    __syncwarp();
   }
+}
+
+// corner-OR volume: bit (x, y, z), 0 <= x <= ax etc., = OR of the alpha bits at (x - 1 .. x, y - 1 .. y, z - 1 .. z) that are in range
+__global__ void alpha_or8_kernel(const uint32_t* __restrict__ bits, int ax, int ay, int az, uint32_t* __restrict__ or8) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(ax + 1) * (ay + 1) * (az + 1);
+  bool any = false;
+  if (v < total) {
+    const int x = (int)(v % (ax + 1)), y = (int)((v / (ax + 1)) % (ay + 1)), z = (int)(v / ((long long)(ax + 1) * (ay + 1)));
+    for (int dz = -1; dz <= 0; ++dz)
+      for (int dy = -1; dy <= 0; ++dy)
+        for (int dx = -1; dx <= 0; ++dx) {
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          if (xx < 0 || yy < 0 || zz < 0 || xx >= ax || yy >= ay || zz >= az) continue;
+          const int f = (zz * ay + yy) * ax + xx;
+          any = any || ((__ldg(bits + (f >> 5)) >> (f & 31)) & 1u);
+        }
+  }
+  const uint32_t word = __ballot_sync(FULL, any);
+  if ((threadIdx.x & 31) == 0 && v < ((total + 31) & ~31ll)) or8[v >> 5] = word;
 }
 
 // exclusive scan of the per-ray counts inside blocks of 1024 rays + block totals
@@ -258,8 +340,8 @@ using namespace srf;
 
 SRF_API int srf_tensorf_march(const float* rays_o_ndc, const float* rays_d_ndc, const float* rays_o, const float* rays_d,
                               const float* ladder, int64_t num_rays, int num_samples, const float* bbox, const float* box_size,
-                              const uint32_t* alpha_bits, const int* alpha_res, const float* alpha_box_min, const float* alpha_box_size,
-                              const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
+                              const uint32_t* alpha_bits, const uint32_t* alpha_corner_or, const int* alpha_res, const float* alpha_box_min,
+                              const float* alpha_box_size, const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
                               int softplus, float density_offset, float distance_scale, float weight_threshold,
                               float* acc, float* depth, float* depth_var, float* depth_ndc, float* depth_var_ndc,
                               int* ray_count, int* entry_sample, float* entry_weight, void* stream) {
@@ -277,7 +359,11 @@ SRF_API int srf_tensorf_march(const float* rays_o_ndc, const float* rays_d_ndc, 
     p.m.ax = alpha_res[0]; p.m.ay = alpha_res[1]; p.m.az = alpha_res[2];
     SRF_REQUIRE(p.m.ax > 0 && p.m.ay > 0 && p.m.az > 0 && (long long)p.m.ax * p.m.ay * p.m.az < (1ll << 31), "srf_tensorf_march",
                 "alpha volume must hold fewer than 2^31 voxels");
+    p.alpha_or8 = alpha_corner_or;
+    SRF_REQUIRE((long long)(p.m.ax + 1) * (p.m.ay + 1) * (p.m.az + 1) < (1ll << 31), "srf_tensorf_march", "alpha volume too large");
+    for (int a = 0; a < 3; ++a) p.cscale[a] = (float)(alpha_res[a] - 1) / alpha_box_size[a];
   }
+  SRF_REQUIRE(num_samples <= 65535, "srf_tensorf_march", "more than 65535 samples per ray");
   for (int i = 0; i < 3; ++i) {
     SRF_REQUIRE(planes[i] && lines[i], "srf_tensorf_march", "null plane/line pointer");
     SRF_REQUIRE(channels[i] > 0 && (channels[i] & 3) == 0, "srf_tensorf_march", "channel counts must be positive multiples of 4");
@@ -289,10 +375,24 @@ SRF_API int srf_tensorf_march(const float* rays_o_ndc, const float* rays_d_ndc, 
   p.acc = acc; p.depth = depth; p.depth_var = depth_var; p.depth_ndc = depth_ndc; p.depth_var_ndc = depth_var_ndc;
   p.ray_count = ray_count; p.entry_sample = entry_sample; p.entry_weight = entry_weight;
   long long blocks = (num_rays + MARCH_WARPS - 1) / MARCH_WARPS;
-  const long long cap = (long long)sm_count() * 8;
+  const long long cap = (long long)sm_count() * 24;      // short blocks: the rays of a frame differ a lot in cost
   if (blocks > cap) blocks = cap;
   tensorf_march_kernel<<<(int)blocks, MARCH_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   return check_launch("srf_tensorf_march");
+}
+
+SRF_API int srf_alpha_corner_or_words(const int* alpha_res) {
+  return (int)(((long long)(alpha_res[0] + 1) * (alpha_res[1] + 1) * (alpha_res[2] + 1) + 31) / 32);
+}
+
+SRF_API int srf_alpha_corner_or_bits(const uint32_t* alpha_bits, const int* alpha_res, uint32_t* corner_or, void* stream) {
+  SRF_REQUIRE(alpha_bits && alpha_res && corner_or, "srf_alpha_corner_or_bits", "null pointer");
+  const int ax = alpha_res[0], ay = alpha_res[1], az = alpha_res[2];
+  SRF_REQUIRE(ax > 0 && ay > 0 && az > 0 && (long long)(ax + 1) * (ay + 1) * (az + 1) < (1ll << 31), "srf_alpha_corner_or_bits",
+              "bad alpha resolution");
+  const long long threads = (long long)srf_alpha_corner_or_words(alpha_res) * 32;
+  alpha_or8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(alpha_bits, ax, ay, az, corner_or);
+  return check_launch("srf_alpha_corner_or_bits");
 }
 
 SRF_API int srf_tensorf_march_blocks(int64_t num_rays) { return (int)((num_rays + 1023) / 1024); }

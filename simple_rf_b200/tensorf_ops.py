@@ -42,6 +42,14 @@ def pack_alpha_bits(alpha_volume):
     return bits
 
 
+def corner_or_alpha_bits(bits, res):
+    """Derived cache of the fused march: per cell of the alpha grid the OR of its 8 corner bits, (X+1)(Y+1)(Z+1) bits."""
+    c_res = _i3(res)
+    out = torch.empty((L.load().srf_alpha_corner_or_words(c_res),), dtype=torch.int32, device=bits.device)
+    L.call('srf_alpha_corner_or_bits', L.ptr(bits), c_res, L.ptr(out), L.stream_handle())
+    return out
+
+
 class Compacted:
     """A compacted sample list: int32 indices (first `count` valid) with the count kept on the device."""
     __slots__ = ('mask', 'idx', 'count', 'total')
@@ -202,7 +210,7 @@ class Marched:
 
 
 def march(rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder, bbox, box_size, alpha, planes, lines, resolution, *, softplus, offset,
-          distance_scale, threshold):
+          distance_scale, threshold, use_corner_or=True):
     """Fused test-time pass of one VM tensor (csrc/tensorf_march.cu): box + alphaMask test, density, transmittance, per-ray maps
     and the surface list, with no [R,S] intermediate.  ladder [S]: the sample depths shared by all rays."""
     L.require_cuda(rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder)
@@ -216,11 +224,16 @@ def march(rays_o_ndc, rays_d_ndc, rays_o, rays_d, ladder, bbox, box_size, alpha,
     entry_sample = torch.empty((R, S), dtype=torch.int32, device=dev)
     entry_weight = torch.empty((R, S), dtype=torch.float32, device=dev)
     if alpha is None:
-        a_bits = a_res = a_min = a_size = None
+        a_bits = a_coarse = a_res = a_min = a_size = None
     else:
         a_bits, a_res, a_min, a_size = L.ptr(alpha['bits']), _i3(alpha['res']), _f3(alpha['box_min']), _f3(alpha['box_size'])
+        a_coarse = None
+        if use_corner_or:                        # cached next to the bits it was derived from
+            if 'corner_or' not in alpha:
+                alpha['corner_or'] = corner_or_alpha_bits(alpha['bits'], alpha['res'])
+            a_coarse = L.ptr(alpha['corner_or'])
     L.call('srf_tensorf_march', L.ptr(rays_o_ndc), L.ptr(rays_d_ndc), L.ptr(rays_o), L.ptr(rays_d), L.ptr(ladder), R, S, _f3(bbox),
-           _f3(box_size), a_bits, a_res, a_min, a_size, _ptrs(planes_cl), _ptrs(lines_cl), chans, _i3(resolution), int(softplus),
+           _f3(box_size), a_bits, a_coarse, a_res, a_min, a_size, _ptrs(planes_cl), _ptrs(lines_cl), chans, _i3(resolution), int(softplus),
            float(offset), float(distance_scale), float(threshold), *[L.ptr(maps[k]) for k in ('acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc')],
            L.ptr(ray_count), L.ptr(entry_sample), L.ptr(entry_weight), L.stream_handle(), work=float(R) * S * 4)
     nb = L.load().srf_tensorf_march_blocks(R)

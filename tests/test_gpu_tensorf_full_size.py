@@ -230,3 +230,45 @@ def test_march_surface_list_is_the_reference_selection_in_reference_order(golden
     for k in ('acc', 'depth', 'depth_ndc', 'depth_var', 'depth_var_ndc'):
         want_k = ref[f'{k}_coarse']
         assert (m.maps[k].cpu() - want_k).abs().max().item() <= MAP_TOL * max(1.0, want_k.abs().max().item()), k
+
+
+def test_corner_or_volume_changes_nothing(golden, golden_configs):
+    """The march's derived occupancy cache (per cell of the alpha grid, the OR of its 8 corner bits): (i) equals the 2^3 max-pool
+    it is specified as, (ii) the march deciding samples by one bit of it (exact test only next to voxel boundaries) returns
+    bit-identical surface lists, weights and maps to the march running the exact trilinear test on every sample."""
+    import torch.nn.functional as F
+    from simple_rf_b200 import tensorf_ops as T
+    from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask
+    g = golden('tensorf_full_eval')
+    configs, mc = golden_configs('tensorf_full')
+    sets = FX.tensorf_full_size_sets(configs, seed=int(g['param_seed']))
+    t = sets['coarse_model']
+    vol = t['alpha_volume'][0, 0]
+    am = AlphaGridMask(vol, t['alpha_bbox']).to(DEV)
+    packed = am.packed()
+    Z, Y, X = vol.shape
+    words = T.corner_or_alpha_bits(packed['bits'], packed['res']).cpu().numpy().view('uint32')
+    n = (X + 1) * (Y + 1) * (Z + 1)
+    got = ((words[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:n].reshape(Z + 1, Y + 1, X + 1).astype(bool)
+    want = F.max_pool3d(F.pad(vol[None, None], (1, 1, 1, 1, 1, 1)), kernel_size=2, stride=1)[0, 0] > 0
+    assert torch.equal(torch.from_numpy(got), want)
+
+    with torch.no_grad():
+        ref = P.tensorf_render_chunk(sets, configs, mc, g['pixel_id'], training=False)
+    d = lambda k: ref[k].to(DEV)
+    planes = [t['params'][f'matrices_density.{i}'].to(DEV) for i in range(3)]
+    lines = [t['params'][f'vectors_density.{i}'].to(DEV) for i in range(3)]
+    tc = configs['model']['coarse_model']
+    bbox = t['bbox']
+    outs = []
+    for use in (False, True):
+        m = T.march(d('rays_o_ndc'), d('rays_d_ndc'), d('rays_o'), d('rays_d'), ref['z_vals_coarse'][0].to(DEV), bbox.tolist(),
+                    (bbox[1] - bbox[0]).tolist(), am.packed(), planes, lines, [int(v) for v in t['resolution']], softplus=False,
+                    offset=tc['density_offset'], distance_scale=tc['distance_scale'], threshold=tc['ray_marching_weight_threshold'],
+                    use_corner_or=use)
+        k = int(m.surface.count.item())
+        outs.append((m.surface.idx[:k].clone(), m.weights[:k].clone(), {name: v.clone() for name, v in m.maps.items()}))
+    assert outs[0][0].numel() > 0
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for name in outs[0][2]:
+        assert torch.equal(outs[0][2][name], outs[1][2][name]), name

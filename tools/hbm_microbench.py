@@ -33,6 +33,45 @@ def report(name, ms, nbytes, **extra):
 
 
 g = torch.Generator(device=dev).manual_seed(0)
+
+
+def sweep():
+    """BASELINE.json configs[4] in full: R in 2^16..2^22 x S in {64,128,192,256,512}; compositing forward (weights only),
+    backward and sample_pdf + merge (S_c = S, N_f = 2 S, random u in-kernel).  Inputs as SURVEY.md §8d prescribes."""
+    torch.manual_seed(0)
+    for R in (1 << 16, 1 << 18, 1 << 20, 1 << 22):
+        for S in (64, 128, 192, 256, 512):
+            sigma = torch.randn(R, S, device=dev, generator=g).relu_().mul_(10).requires_grad_()
+            rgb = torch.rand(R, S, 3, device=dev, generator=g).requires_grad_()
+            z = torch.rand(R, S, device=dev, generator=g)
+            z = torch.sort(z, -1)[0]
+            ro = torch.randn(R, 3, device=dev, generator=g) * .1
+            rd = torch.nn.functional.normalize(torch.randn(R, 3, device=dev, generator=g), dim=-1) * (0.5 + torch.rand(R, 1, device=dev, generator=g))
+            dn = torch.randn(R, 3, device=dev, generator=g)
+            n = 3 if R * S >= (1 << 28) else 5
+            with torch.no_grad():
+                ms = timed(lambda: ops.composite(sigma, rgb, z, ro, rd, dn, ndc=True, per_sample=False), n)
+            report(f'sweep composite_fwd R=2^{R.bit_length() - 1} S={S}', ms, R * S * 24 + R * 68, R=R, S=S, kind='composite_fwd')
+            out = ops.composite(sigma, rgb, z, ro, rd, dn, ndc=True)
+            keys = ('rgb', 'depth', 'depth_ndc', 'acc')
+            loss_grads = [torch.rand_like(out[k]) for k in keys]
+            ms = timed(lambda: torch.autograd.grad([out[k] for k in keys], [sigma, rgb], loss_grads, retain_graph=True), n)
+            report(f'sweep composite_bwd R=2^{R.bit_length() - 1} S={S}', ms, R * S * 40 + R * 60, R=R, S=S, kind='composite_bwd')
+            w = out['weights'].detach()
+            del out, loss_grads
+            try:
+                ms = timed(lambda: ops.sample_pdf_merge(z, w, 2 * S, philox_seed=1), n)
+                report(f'sweep sample_pdf_merge R=2^{R.bit_length() - 1} {S}->+{2 * S}', ms, R * (4 * (S - 2) + 4 * S + 4 * 3 * S), R=R, S=S,
+                       kind='sample_pdf_merge')
+            except Exception as e:
+                print(json.dumps({'case': f'sweep sample_pdf_merge R=2^{R.bit_length() - 1} {S}->+{2 * S}', 'skipped': str(e)[:120]}), flush=True)
+            del sigma, rgb, z, w, ro, rd, dn
+            torch.cuda.empty_cache()
+
+
+if '--sweep' in sys.argv:
+    sweep()
+    sys.exit(0)
 sizes = [(1 << 18, 64), (1 << 18, 192), (1 << 20, 64), (1 << 20, 192), (1 << 18, 512)]
 if '--probe' in sys.argv:
     sizes = [(1 << 20, 64), (1 << 20, 192)]

@@ -1,0 +1,24 @@
+#!/bin/bash
+# compute-sanitizer over the small-shape GPU parity tests (VERDICT r1 missing #7).  memcheck on every kernel family,
+# racecheck on the shared-memory heavy ones.  The tcgen05 kernels run under memcheck too (bounded by `timeout`: the tool
+# serialises warps and the mbarrier pipelines are slow under it).
+#   bash tools/sanitizer_suite.sh gpurun_out/r2_sanitizer
+set -u
+OUT=${1:-gpurun_out/sanitizer}
+mkdir -p "$OUT"
+SAN=/usr/local/cuda/bin/compute-sanitizer
+run() {  # name, tool, timeout, pytest args...
+  local name=$1 tool=$2 limit=$3; shift 3
+  timeout "$limit" $SAN --tool "$tool" --print-limit 5 --error-exitcode 99 python -m pytest -q -x -p no:cacheprovider "$@" > "$OUT/$name.$tool.log" 2>&1
+  local rc=$?
+  echo "$name $tool rc=$rc $(grep -E 'ERROR SUMMARY|passed|failed' "$OUT/$name.$tool.log" | tr '\n' ' ')"
+}
+run sampling memcheck 400 tests/test_gpu_sampling.py
+run composite memcheck 400 tests/test_gpu_composite.py
+run tensorf memcheck 600 tests/test_gpu_tensorf.py -k "mask or density or color or compaction"
+run surgery memcheck 400 tests/test_gpu_surgery.py -k "not full_size"
+run batch_losses_optim memcheck 400 tests/test_gpu_batch.py tests/test_gpu_losses.py tests/test_gpu_optim.py
+run mlp memcheck 600 tests/test_gpu_nerf_mlp.py -k "37-64 or 41-64 or 1-1"
+run composite racecheck 400 tests/test_gpu_composite.py -k "golden or shapes"
+run sampling racecheck 400 tests/test_gpu_sampling.py
+run tensorf racecheck 600 tests/test_gpu_tensorf.py -k "mask or density or color"
