@@ -451,10 +451,13 @@ using namespace srf;
 // samples per lane and step: 2 (64 per warp step, 64-bit pieces) or 4 (128 per step, 128-bit pieces) - whichever
 // covers the ray with fewer idle lane slots; longer runs win unless they idle more than 15 % extra (fewer scans).
 // Every piece a lane loads or stores is contiguous with its neighbours', so all accesses are fully coalesced.
+#ifndef SRF_CMP_L4_PCT
+#define SRF_CMP_L4_PCT 115
+#endif
 static int run_length(int S) {
   const long long s2 = (long long)((S + (S % 2) + 63) / 64) * 64;
   const long long s4 = (long long)((S + (S % 4 ? 3 : 0) + 127) / 128) * 128;
-  return s4 * 100 <= s2 * 115 ? 4 : 2;
+  return s4 * 100 <= s2 * SRF_CMP_L4_PCT ? 4 : 2;
 }
 
 template <typename... Ts>

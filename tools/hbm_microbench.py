@@ -73,8 +73,8 @@ if '--sweep' in sys.argv:
     sweep()
     sys.exit(0)
 sizes = [(1 << 18, 64), (1 << 18, 192), (1 << 20, 64), (1 << 20, 192), (1 << 18, 512)]
-if '--probe' in sys.argv:
-    sizes = [(1 << 20, 64), (1 << 20, 192)]
+if '--probe' in sys.argv:          # one shape per run (ncu groups launches by kernel + grid): --probe [S]
+    sizes = [(1 << 20, int(sys.argv[sys.argv.index('--probe') + 1]) if len(sys.argv) > sys.argv.index('--probe') + 1 else 192)]
 if '--big' in sys.argv:
     sizes += [(1 << 22, 64), (1 << 22, 192), (1 << 20, 512)]
 for R, S in sizes:

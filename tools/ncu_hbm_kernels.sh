@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu counters of the HBM / L2-bound kernels (north_star: "achieved HBM GB/s for the gather and
 # compositing kernels"): dram bytes, L2 bytes, duration per launch of every srf:: kernel of
-#   (a) the compositing micro-benchmark at 2^20 x {64, 192}            (composite_fwd / _bwd)
+#   (a) the compositing micro-benchmark at 2^20 x 64 and 2^20 x 192    (composite_fwd / _bwd; one shape per run)
 #   (b) two Simple-TensoRF training iterations at 331x368x220          (tensorf_mask, vm_density_*, vm_color_features_*, composite, tv, adam)
 #   (c) one Simple-TensoRF test frame                                  (tensorf_march, vm_color_features_fwd, mlp rows)
 # Run on the GPU box:  bash tools/ncu_hbm_kernels.sh gpurun_out/r2_ncu     then here:  python tools/ncu_table.py gpurun_out/r2_ncu
@@ -16,6 +16,7 @@ run() {  # name, skip, count, command...
   timeout 600 ncu --metrics $M --clock-control none -k regex:"$K" -s "$skip" -c "$count" --csv --log-file "$OUT/$name.csv" "$@" > "$OUT/$name.log" 2>&1
   echo "$name rc=$?"
 }
-run composite 0 200 python tools/hbm_microbench.py --probe
+run composite_S64 0 120 python tools/hbm_microbench.py --probe 64
+run composite_S192 0 120 python tools/hbm_microbench.py --probe 192
 run tensorf_train 0 400 python tools/tensorf_train_step.py 2
 run tensorf_frame 0 200 python tools/tensorf_render.py 1

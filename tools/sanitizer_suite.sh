@@ -13,12 +13,18 @@ run() {  # name, tool, timeout, pytest args...
   local rc=$?
   echo "$name $tool rc=$rc $(grep -E 'ERROR SUMMARY|passed|failed' "$OUT/$name.$tool.log" | tr '\n' ' ')"
 }
-run sampling memcheck 400 tests/test_gpu_sampling.py
-run composite memcheck 400 tests/test_gpu_composite.py
-run tensorf memcheck 600 tests/test_gpu_tensorf.py -k "mask or density or color or compaction"
-run surgery memcheck 400 tests/test_gpu_surgery.py -k "not full_size"
-run batch_losses_optim memcheck 400 tests/test_gpu_batch.py tests/test_gpu_losses.py tests/test_gpu_optim.py
-run mlp memcheck 600 tests/test_gpu_nerf_mlp.py -k "37-64 or 41-64 or 1-1"
-run composite racecheck 400 tests/test_gpu_composite.py -k "golden or shapes"
-run sampling racecheck 400 tests/test_gpu_sampling.py
-run tensorf racecheck 600 tests/test_gpu_tensorf.py -k "mask or density or color"
+run sampling memcheck 240 tests/test_gpu_sampling.py
+run composite memcheck 240 tests/test_gpu_composite.py
+run tensorf memcheck 300 tests/test_gpu_tensorf.py -k "mask or density or color or compaction"
+run surgery memcheck 240 tests/test_gpu_surgery.py -k "not full_size and not 48-368"
+run batch_losses_optim memcheck 240 tests/test_gpu_batch.py tests/test_gpu_losses.py tests/test_gpu_optim.py
+run composite racecheck 240 tests/test_gpu_composite.py -k "golden"
+run sampling racecheck 240 tests/test_gpu_sampling.py
+run tensorf racecheck 240 tests/test_gpu_tensorf.py -k "mask or density"
+run mlp memcheck 240 tests/test_gpu_nerf_mlp.py -k "37-64 or 41-64 or 1-1"
+run mlp_bwd memcheck 300 tests/test_gpu_nerf_mlp_bwd.py
+run nerf_model memcheck 300 tests/test_gpu_nerf_model.py -k "golden or split or retraw or gradients"
+run tensorf_model memcheck 300 tests/test_gpu_tensorf.py -k "dropin or golden"
+run composite_all racecheck 240 tests/test_gpu_composite.py
+run surgery racecheck 240 tests/test_gpu_surgery.py -k "not full_size and not 48-368"
+run mlp racecheck 240 tests/test_gpu_nerf_mlp.py -k "37-64 or 41-64 or 1-1"
