@@ -752,7 +752,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    rays_per_step = 4096
+    rays_per_step = 16384        # ~3 s of host work per step: the per-step frame set-up (create_test_data of 762 048 pixel ids) stays < 3 %
     if reference_available():
         from simple_rf_b200.dropin import callers
         callers.force_cpu().__enter__()                       # for the rest of this process: the reference arm is the host-CPU arm
