@@ -43,6 +43,13 @@ int srf_raygen(const int32_t* pixel_id, int64_t num_rays, const float* k_inv, co
 int srf_stratified_z(const float* ladder, int num_samples, int64_t num_rays, const float* jitter,
                      int use_philox, uint64_t seed, float* z, void* stream);
 
+/* Box-march depths of Simple-TensoRF without NDC.  Replaces src/models/SimpleTensoRF09.py:388-400: entry distance of the ray into
+ * the tensor's bounding box (zero direction components replaced by 1e-6), clamped to [near, far], then
+ *   z[r, s] = t_entry[r] + step_size * (s + jitter[r])      (jitter [R] = the reference's one torch.rand per ray, or NULL).
+ * bbox HOST [2,3] = [min xyz | max xyz]; rays_o / rays_d are the WORLD rays; z [R,S].  Bit-exact w.r.t. the reference's fp32 ops. */
+int srf_box_march_z(const float* rays_o, const float* rays_d, int64_t num_rays, int num_samples, const float* bbox,
+                    float near, float far, float step_size, const float* jitter, float* z, void* stream);
+
 /* Hierarchical resampling + merge.  Replaces src/models/SimpleNeRF17.py:360-371 (get_z_vals_fine) and
  * :385-417 (sample_pdf).  Bit-exact against the reference's CPU path given identical inputs.
  *   z_coarse, weights [R,S];  u [R,N] (u_row_stride = N), one shared row [N] (u_row_stride = 0, the

@@ -232,6 +232,59 @@ def golden_tensorf():
         print(f'tensorf_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f})')
 
 
+def tensorf_world_configs():
+    """The shipped train0212 config with `ndc = False` (no shipped run selects it; SimpleTensoRF09.py:388-400 is the box-marching
+    sampler it switches on): world-space tensor boxes in front of the cameras, near / far in world units."""
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    configs['data_loader']['ndc'] = False
+    box = [[-2.0, -1.8, -7.0], [2.0, 1.8, -1.0]]
+    configs['model']['coarse_model']['num_voxels_initial'] = 40 ** 3
+    configs['model']['coarse_model']['bounding_box'] = box
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 20 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['bounding_box'] = box
+    model_configs['near'], model_configs['far'] = 0.75, 9.0
+    return configs, model_configs
+
+
+def golden_tensorf_world():
+    """Simple-TensoRF without NDC: box-march depths (bit-exact), world-space points / view directions, compositing with the last
+    interval to 1e10 — the unmodified reference, eval (with an alpha mask) and train (per-ray jitter, augmentation tensor)."""
+    configs, model_configs = tensorf_world_configs()
+    (OUT / 'tensorf_world_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    keys = ('rgb', 'acc', 'depth', 'depth_var', 'alpha', 'visibility', 'weights', 'raw_sigma', 'raw_rgb')
+    for mode, R, seed, with_alpha in (('eval', 40, 15, True), ('train', 32, 16, False)):
+        sets = FX.tensorf_sets(configs, seed=23, with_alpha=with_alpha)
+        load_tensorf_params(model, sets)
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(400 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+        torch.manual_seed(400 + seed)
+        with torch.no_grad():
+            mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        assert 'depth_ndc_coarse' not in ref and 'rays_o_ndc' not in ref
+        fixture = {'pixel_id': pixel_id, 'param_seed': 23, 'rng_seed': 400 + seed, 'with_alpha': with_alpha}
+        for k in ('rays_o', 'rays_d', 'view_dirs', 'z_vals_coarse'):
+            _check(f'tensorf_world/{mode}/{k}', ref[k], mine[k])
+            fixture[k] = ref[k]
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for k in keys:
+                key = f'{pre}{k}_coarse'
+                _check(f'tensorf_world/{mode}/{key}', ref[key], mine[key])
+                fixture[key] = ref[key]
+            fixture[f'{pre}validity_mask_coarse'] = mine[f'{pre}validity_mask_coarse']
+            fixture[f'{pre}surface_mask_coarse'] = mine[f'{pre}surface_mask_coarse']
+        frac = mine['validity_mask_coarse'].float().mean().item(), mine['surface_mask_coarse'].float().mean().item()
+        np.savez_compressed(OUT / f'tensorf_world_{mode}.npz', **_np(fixture))
+        print(f'tensorf_world_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f}, acc mean {ref["acc_coarse"].mean():.3f})')
+
+
 def tensorf_full_size_configs():
     """Shipped train0212 config at the size bench.py times (BASELINE.json configs[2]/[3]): 300^3-voxel main tensor
     (331x368x220, 1083 samples/ray), 160^3-voxel augmentation tensor, full 576x1024 frames."""
@@ -553,6 +606,7 @@ def main():
     golden_tensorf_training_curve()
     golden_batch_assembly()
     golden_surgery()
+    golden_tensorf_world()
 
 
 if __name__ == '__main__':

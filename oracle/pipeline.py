@@ -106,23 +106,35 @@ def tensorf_render_chunk(tensors, configs, model_configs, pixel_id, *, training,
     h, w = model_configs['resolution']
     R = pixel_id.shape[0]
     out = {}
+    ndc = bool(configs['data_loader']['ndc'])
     rays_o, rays_d = RY.camera_rays(pixel_id, K, E, half_pixel=True, flip_x=True)
-    img = pixel_id[:, 0].long()
-    o_ndc, d_ndc = RY.ndc_rays(rays_o, rays_d, h, w, K[img, 0, 0], K[img, 1, 1], model_configs['near'])
-    vd = RY.view_dirs(d_ndc)
-    out.update(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=o_ndc, rays_d_ndc=d_ndc, view_dirs=vd)
     main = tensors['coarse_model']
     S = main['num_samples']
-    ladder = SP.coarse_depths(S, model_configs['near_ndc'], model_configs['far_ndc'], mc['lindisp'])
     perturb = training and mc['perturb']
-    jitter = torch.rand([R, S]) if perturb else None
-    z = SP.stratified_depths(ladder, R, jitter)
+    if ndc:
+        img = pixel_id[:, 0].long()
+        o_ndc, d_ndc = RY.ndc_rays(rays_o, rays_d, h, w, K[img, 0, 0], K[img, 1, 1], model_configs['near'])
+        vd = RY.view_dirs(d_ndc)
+        out.update(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=o_ndc, rays_d_ndc=d_ndc, view_dirs=vd)
+        ladder = SP.coarse_depths(S, model_configs['near_ndc'], model_configs['far_ndc'], mc['lindisp'])
+        jitter = torch.rand([R, S]) if perturb else None
+        z = SP.stratified_depths(ladder, R, jitter)
+        pts = o_ndc[..., None, :] + d_ndc[..., None, :] * z[..., :, None]
+    else:
+        # world-space box marching (SimpleTensoRF09.py:388-400): one jitter draw per ray, steps of the MAIN tensor's step_size
+        d_ndc = None
+        vd = RY.view_dirs(rays_d)
+        out.update(rays_o=rays_o, rays_d=rays_d, view_dirs=vd)
+        res = main['resolution'].long()
+        step_size = torch.mean((main['bbox'][1] - main['bbox'][0]).float() / (res - 1)) * mc['coarse_model']['num_voxels_per_sample']
+        jitter = torch.rand([R, 1]) if perturb else None
+        z = SP.box_march_depths(rays_o, rays_d, main['bbox'], model_configs['near'], model_configs['far'], step_size, S, jitter)
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
     out['z_vals_coarse'] = z
-    pts = o_ndc[..., None, :] + d_ndc[..., None, :] * z[..., :, None]
 
     def run(t, cfg, prefix):
         white = mc['white_bkgd'] or bool(training and (torch.rand((1,)) < 0.5))
-        res = TF.tensor_forward(t['params'], t['bbox'], pts, z, rays_o, rays_d, d_ndc, vd, ndc=True,
+        res = TF.tensor_forward(t['params'], t['bbox'], pts, z, rays_o, rays_d, d_ndc, vd, ndc=ndc,
                                 alpha_volume=t.get('alpha_volume'), alpha_bbox=t.get('alpha_bbox'),
                                 distance_scale=cfg['distance_scale'],
                                 weight_threshold=cfg['ray_marching_weight_threshold'], white_bkgd=white,

@@ -22,6 +22,7 @@ _SIGNATURES = {
     'srf_raygen': (c_int, [_P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int,
                            _P, _P, _P, _P, _P, _P]),
     'srf_stratified_z': (c_int, [_P, c_int, c_int64, _P, c_int, c_uint64, _P, _P]),
+    'srf_box_march_z': (c_int, [_P, _P, c_int64, c_int, _P, c_float, c_float, c_float, _P, _P, _P]),
     'srf_sample_pdf_merge': (c_int, [_P, _P, _P, c_int64, c_uint64, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     'srf_composite_fwd': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -153,6 +153,33 @@ __global__ void stratified_kernel(const float* __restrict__ ladder, int S, long 
 }
 
 // ------------------------------------------------------------------------------------------
+// box-march depths (Simple-TensoRF without NDC): z[r, s] = clamp(t_entry(r), near, far) + step_size * (s + jitter[r])
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) box_march_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                        const float* __restrict__ jitter, float b0x, float b0y, float b0z,
+                                                        float b1x, float b1y, float b1z, float near, float far, float step_size,
+                                                        int S, long long R, float* __restrict__ z) {
+  const long long total = R * S;
+  const float b0[3] = {b0x, b0y, b0z}, b1[3] = {b1x, b1y, b1z};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / S;
+    const int s = (int)(i - r * S);
+    float t_min = -__int_as_float(0x7f800000);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float o = __ldg(rays_o + r * 3 + a), d = __ldg(rays_d + r * 3 + a);
+      const float vec = d == 0.f ? 1e-6f : d;
+      const float ra = __fdiv_rn(__fadd_rn(b1[a], -o), vec), rb = __fdiv_rn(__fadd_rn(b0[a], -o), vec);
+      t_min = fmaxf(t_min, fminf(ra, rb));
+    }
+    t_min = fminf(fmaxf(t_min, near), far);
+    float rng = (float)s;
+    if (jitter != nullptr) rng = __fadd_rn(rng, __ldg(jitter + r));
+    z[i] = __fadd_rn(t_min, __fmul_rn(step_size, rng));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // sample_pdf + merge: one warp per ray.
 // shared memory per warp (floats): zc[S] | cdf[S] (first holds w/pdf) | bins[S] | sortbuf[npad]
 // ------------------------------------------------------------------------------------------
@@ -440,6 +467,20 @@ SRF_API int srf_stratified_z(const float* ladder, int num_samples, int64_t num_r
   stratified_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(ladder, num_samples, total, jitter,
                                                                              use_philox, seed, z);
   return check_launch("srf_stratified_z");
+}
+
+SRF_API int srf_box_march_z(const float* rays_o, const float* rays_d, int64_t num_rays, int num_samples, const float* bbox,
+                            float near, float far, float step_size, const float* jitter, float* z, void* stream) {
+  if (num_rays == 0) return 0;
+  SRF_REQUIRE(rays_o && rays_d && bbox && z, "srf_box_march_z", "null pointer");
+  SRF_REQUIRE(num_samples > 0 && num_rays >= 0, "srf_box_march_z", "bad sizes");
+  const long long total = (long long)num_rays * num_samples;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  box_march_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, jitter, bbox[0], bbox[1], bbox[2], bbox[3], bbox[4],
+                                                                       bbox[5], near, far, step_size, num_samples, num_rays, z);
+  return check_launch("srf_box_march_z");
 }
 
 SRF_API int srf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int64_t u_row_stride,

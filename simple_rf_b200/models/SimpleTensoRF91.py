@@ -30,9 +30,7 @@ class SimpleTensoRF(torch.nn.Module):
         super().__init__()
         self.configs = configs
         self.model_configs = model_configs
-        self.ndc = self.configs['data_loader']['ndc']
-        if not self.ndc:
-            raise NotImplementedError('only the NDC path (every shipped config) is implemented')
+        self.ndc = self.configs['data_loader']['ndc']          # False: world-space box marching (SimpleTensoRF09.py:388-400)
         mc = self.configs['model']
         self.coarse_model_needed = 'coarse_model' in mc
         self.fine_model_needed = 'fine_model' in mc
@@ -169,9 +167,10 @@ class SimpleTensoRF(torch.nn.Module):
         dev = pixel_id.device
         R = pixel_id.shape[0]
         h, w = self.model_configs['resolution']
+        ndc = self.ndc
         rays_o, rays_d, o_ndc, d_ndc, view_dirs = ops.raygen(
-            pixel_id, self._tables(dev), h, w, self.model_configs['near'], half_pixel=True, flip_x=True, ndc=True,
-            viewdirs_from_ndc=True)
+            pixel_id, self._tables(dev), h, w, self.model_configs['near'], half_pixel=True, flip_x=True, ndc=ndc,
+            viewdirs_from_ndc=ndc)
         if mode == 'static_camera':                                          # SimpleTensoRF09.py:222-233
             cd = input_dict['common_data']
             pose = cd['processed_view_pose']
@@ -182,13 +181,17 @@ class SimpleTensoRF(torch.nn.Module):
             nviews = self.intrinsics_learner.initial_intrinsics.shape[0]
             ks = self.intrinsics_learner.initial_intrinsics.detach() if k_view is None else k_view[None].expand(nviews, 3, 3)
             tabs = self._tables(dev, ks, pose[None].expand(nviews, 4, 4))
-            view_dirs = ops.raygen(pixel_id, tabs, h, w, self.model_configs['near'], half_pixel=False, flip_x=False, ndc=True,
-                                   viewdirs_from_ndc=True)[4]
-        out = {'rays_o': rays_o, 'rays_d': rays_d, 'rays_o_ndc': o_ndc, 'rays_d_ndc': d_ndc, 'view_dirs': view_dirs}
+            view_dirs = ops.raygen(pixel_id, tabs, h, w, self.model_configs['near'], half_pixel=False, flip_x=False, ndc=ndc,
+                                   viewdirs_from_ndc=ndc)[4]
+        out = {'rays_o': rays_o, 'rays_d': rays_d, 'view_dirs': view_dirs}
+        if ndc:
+            out['rays_o_ndc'], out['rays_d_ndc'] = o_ndc, d_ndc
         main = self.coarse_model
         S = main.host_geometry()['num_samples']
-        ladder = coarse_ladder_on(dev, S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp'])
         perturb = self.training and mc['perturb']
+        if not ndc:
+            return self._render_rays_world(out, pixel_id, input_dict, S, perturb, retraw=retraw, mode=mode)
+        ladder = coarse_ladder_on(dev, S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp'])
         # test time without per-sample outputs: the depths are ONE ladder for all rays -> fused march, z[R,S] never materialised
         if not self.training and not retraw and not torch.is_grad_enabled() and mc.get('fused_eval', True):
             rays = dict(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=o_ndc, rays_d_ndc=d_ndc, view_dirs=view_dirs, z=None, ladder=ladder)
@@ -212,6 +215,39 @@ class SimpleTensoRF(torch.nn.Module):
         if self.augmentations_needed and self.training and mode != 'test_camera_params_optimization':
             for aug in self.augmented_models:
                 if aug['coarse_model'] is not None:                        # same z_vals as the main tensor (:283-296)
+                    for k, v in aug['coarse_model'](rays, retraw, white_bkgd=mc['white_bkgd']).items():
+                        out[f"{aug['name']}_{k}_coarse"] = v
+        if not retraw:
+            for k in [k for k in out if k.startswith('z_vals_') or '_alpha_' in f'_{k}' or '_visibility_' in f'_{k}'
+                      or '_weights_' in f'_{k}']:
+                del out[k]
+        return out
+
+    def _render_rays_world(self, out, pixel_id, input_dict, S, perturb, *, retraw, mode):
+        """`data_loader.ndc = False` (SimpleTensoRF09.py:388-400, :263): every ray marches from its entry into the main tensor's
+        box in steps of the tensor's `step_size`; sample points, view directions and compositing (last interval to 1e10) live in
+        world space.  Depths differ per ray, so test time takes the same per-sample path as training."""
+        from .. import parallel
+        mc = self.configs['model']
+        main = self.coarse_model
+        rays_o, rays_d = out['rays_o'], out['rays_d']
+        R = pixel_id.shape[0]
+        jitter = None
+        if perturb and self.rng_mode == 'reference':          # one draw per ray on the CPU generator (:397-398)
+            shard = input_dict.get('srf_shard') if self.training else None
+            jitter = parallel.rows_of_global_draw(lambda n: torch.rand([n, 1]), R, shard, mc['chunk']).to(rays_o.device)
+        elif perturb:
+            parallel.decorrelate_device_rng()
+            jitter = torch.rand([R, 1], device=rays_o.device)
+        z = ops.box_march_z(rays_o, rays_d, S, main.host_geometry()['box'], self.model_configs['near'], self.model_configs['far'],
+                            float(main.step_size), jitter)
+        out['z_vals_coarse'] = z
+        rays = dict(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=None, rays_d_ndc=None, view_dirs=out['view_dirs'], z=z)
+        for k, v in main(rays, retraw, white_bkgd=mc['white_bkgd']).items():
+            out[f'{k}_coarse'] = v
+        if self.augmentations_needed and self.training and mode != 'test_camera_params_optimization':
+            for aug in self.augmented_models:
+                if aug['coarse_model'] is not None:
                     for k, v in aug['coarse_model'](rays, retraw, white_bkgd=mc['white_bkgd']).items():
                         out[f"{aug['name']}_{k}_coarse"] = v
         if not retraw:
@@ -421,14 +457,15 @@ class VmDecomposedTensor(torch.nn.Module):
             return self.forward_fused_eval(rays, white_bkgd=white_bkgd)
         z = rays['z']
         R, S = z.shape
-        so, sd = rays['rays_o_ndc'], rays['rays_d_ndc']
+        ndc = self.ndc
+        so, sd = (rays['rays_o_ndc'], rays['rays_d_ndc']) if ndc else (rays['rays_o'], rays['rays_d'])     # what the samples ride on (:263)
         alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
         valid = T.validity_compact(so, sd, z, self.host_geometry()['box'], alpha)
         geom = self._geometry(so, sd, z)
         sigma = T.vm_density(geom, valid, list(self.matrices_density), list(self.vectors_density),
                              softplus=self.density_predictor == 'SoftPlus', offset=tc['density_offset'])
         with torch.no_grad():                                               # weights only decide where colour is read (:726)
-            w0 = ops.composite(sigma.detach()[..., 0], None, z, rays['rays_o'], rays['rays_d'], sd, ndc=True,
+            w0 = ops.composite(sigma.detach()[..., 0], None, z, rays['rays_o'], rays['rays_d'], sd if ndc else None, ndc=ndc,
                                distance_scale=tc['distance_scale'], per_sample=False)['weights']
         surface = T.threshold_compact(w0, tc['ray_marching_weight_threshold'])
         cp = self.color_predictor
@@ -442,7 +479,7 @@ class VmDecomposedTensor(torch.nn.Module):
         rgb = T._ScatterRows.apply(surface, rgb_rows, R * S).view(R, S, 3)
         device_coin = self.training and not white_bkgd and self.configs['model'].get('rng_mode', 'reference') != 'reference'
         white = white_bkgd or bool(self.training and not device_coin and (torch.rand((1,)) < 0.5))      # :746
-        vr = ops.composite(sigma[..., 0], rgb, z, rays['rays_o'], rays['rays_d'], sd, ndc=True, white_bkgd=white,
+        vr = ops.composite(sigma[..., 0], rgb, z, rays['rays_o'], rays['rays_d'], sd if ndc else None, ndc=ndc, white_bkgd=white,
                            distance_scale=tc['distance_scale'], per_sample=retraw)      # alpha / visibility are dropped unless retraw
         if device_coin:          # the background coin (:746) drawn on the device: no host decision inside a captured iteration
             coin = (torch.rand((), device=z.device) < 0.5).to(vr['rgb'].dtype)

@@ -61,6 +61,20 @@ def stratified_z(ladder, num_rays, jitter=None, philox_seed=None):
     return z
 
 
+def box_march_z(rays_o, rays_d, num_samples, bbox, near, far, step_size, jitter=None):
+    """Simple-TensoRF depths without NDC (SimpleTensoRF09.py:388-400): box entry clamped to [near, far] + step_size * (s + jitter[r]).
+    bbox: [[min xyz], [max xyz]] host values; jitter: [R] or [R,1] device tensor (one draw per ray) or None."""
+    import ctypes
+    L.require_cuda(rays_o, rays_d, jitter)
+    rays_o, rays_d, jitter = L.f32c(rays_o), L.f32c(rays_d), L.f32c(jitter)
+    R = rays_o.shape[0]
+    z = _empty((R, int(num_samples)), rays_o)
+    box = (ctypes.c_float * 6)(*[float(v) for row in bbox for v in row])
+    L.call('srf_box_march_z', L.ptr(rays_o), L.ptr(rays_d), R, int(num_samples), box, float(near), float(far), float(step_size),
+           L.ptr(None if jitter is None else jitter.reshape(-1)), L.ptr(z), L.stream_handle())
+    return z
+
+
 def sample_pdf_merge(z_coarse, weights, num_fine, u=None, philox_seed=0, return_indices=False):
     """u: [R,N] tensor, [N] shared row (deterministic linspace) or None (in-kernel Philox).
     Returns z_fine [R,S+N] (+ samples, below, above when return_indices)."""

@@ -98,6 +98,26 @@ def test_tensorf_pipeline_matches_reference_golden(golden, golden_configs, mode)
             assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
 
 
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_tensorf_world_space_pipeline_matches_reference_golden(golden, golden_configs, mode):
+    """`data_loader.ndc = False`: box-march depths (SimpleTensoRF09.py:388-400), world-space points, last interval to 1e10."""
+    g = golden(f'tensorf_world_{mode}')
+    configs, model_configs = golden_configs('tensorf_world')
+    assert configs['data_loader']['ndc'] is False
+    sets = FX.tensorf_sets(configs, seed=int(g['param_seed']), with_alpha=bool(g['with_alpha']))
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = P.tensorf_render_chunk(sets, configs, model_configs, g['pixel_id'], training=(mode == 'train'))
+    for k in ('rays_o', 'rays_d', 'view_dirs', 'z_vals_coarse'):
+        assert torch.equal(out[k], g[k]), k
+    assert torch.equal(out['validity_mask_coarse'], g['validity_mask_coarse'])
+    assert torch.equal(out['surface_mask_coarse'], g['surface_mask_coarse'])
+    assert not any('ndc' in k for k in out)
+    for k in g:
+        if k in out and g[k].dtype == torch.float32:
+            assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
+
+
 @pytest.mark.parametrize('n', [1, 3, 5, 7, 8, 35, 62, 64, 190, 462, 1081, 2312])
 def test_aten_row_sum_order(n):
     torch.manual_seed(n)
