@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         };
         // the slice becomes part of K block `kb` of the next layer's A operand (in place over the old H:
         // every MMA of this layer has retired once d_full fired)
-        auto store = [&](const uint32_t (&pk)[COLS / 2], int kb) {
+        auto publish = [&](const uint32_t (&pk)[COLS / 2], int kb) {
           if (write_h) {
             // packed pairs go back over the first 16 of the 32 accumulator columns this warp just drained: K block kb of the
             // next layer's A operand never leaves tensor memory
@@ -546,45 +546,78 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_addr(a_ready_addr + (uint32_t)(1 + kb) * 8u);
           }
-          if (save_base != nullptr) {
-            // staged through shared memory: a thread owns 64 bytes of a 128-byte image row, so direct global stores touch 32
-            // lines per instruction; the swizzled staging image leaves as one 16 KB bulk copy instead
-            uint8_t* stg = &sm.w[0][0] + (size_t)SAVE_STAGES * STAGE_BYTES + (size_t)(save_count & (SAVE_BUFS - 1)) * IMAGE_BYTES;
+        };
+        // training: the same packed pairs of TWO K blocks go to HBM as tile images, AFTER both blocks have been published to the
+        // tensor core (the next layer's MMAs are what the tile waits for; the copies ride under them).  Staged through shared
+        // memory: a thread owns 64 bytes of a 128-byte image row, so direct global stores touch 32 lines per instruction; the
+        // swizzled staging images leave as 16 KB bulk copies instead, one barrier and one bulk group per pair of blocks.
+        auto save_pair = [&](const uint32_t (&pa)[COLS / 2], uint32_t ma, const uint32_t (&pb)[COLS / 2], uint32_t mb, int kb) {
+          uint8_t* stg = &sm.w[0][0] + (size_t)SAVE_STAGES * STAGE_BYTES + (size_t)(save_count & 1u) * 2 * IMAGE_BYTES;
 #pragma unroll
-            for (int u = 0; u < COLS / 8; ++u)
-              *reinterpret_cast<uint4*>(stg + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
-                  make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-            // one mask word per thread, 128 bytes per warp (the dgrad chain reads these instead of the 64-byte activation row)
-            *reinterpret_cast<uint32_t*>(tile_base + act_mask_offset(args.act_slots, save_slot + kb) + grp * 512 + row * 4) = mask_bits;
-            ptx::fence_proxy_async_smem();
-            // the buffer the NEXT block will use was handed to the copy engine SAVE_BUFS - 1 blocks ago: at most
-            // SAVE_BUFS - 2 newer groups may still be reading when everybody passes the barrier below
-            if (threadIdx.x == EPI_WARP0 * 32) ptx::bulk_wait_read<SAVE_BUFS - 2>();
-            epi_bar_sync();
-            if (threadIdx.x == EPI_WARP0 * 32) {
-              ptx::bulk_s2g(save_base + (size_t)kb * KBLOCK_BYTES, stg, IMAGE_BYTES);
-              ptx::bulk_commit();
-            }
-            ++save_count;
+          for (int u = 0; u < COLS / 8; ++u) {
+            *reinterpret_cast<uint4*>(stg + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
+                make_uint4(pa[4 * u], pa[4 * u + 1], pa[4 * u + 2], pa[4 * u + 3]);
+            *reinterpret_cast<uint4*>(stg + IMAGE_BYTES + ptx::sw128_offset(row, grp * (COLS / 8) + u)) =
+                make_uint4(pb[4 * u], pb[4 * u + 1], pb[4 * u + 2], pb[4 * u + 3]);
           }
+          // one mask word per thread and block, 128 bytes per warp (the dgrad chain reads these instead of the 64-byte activation row)
+          *reinterpret_cast<uint32_t*>(tile_base + act_mask_offset(args.act_slots, save_slot + kb) + grp * 512 + row * 4) = ma;
+          *reinterpret_cast<uint32_t*>(tile_base + act_mask_offset(args.act_slots, save_slot + kb + 1) + grp * 512 + row * 4) = mb;
+          ptx::fence_proxy_async_smem();
+          // the pair of buffers the NEXT pair will use was handed to the copy engine one bulk group ago: it must have been read
+          // out by the time everybody passes the barrier below
+          if (threadIdx.x == EPI_WARP0 * 32) ptx::bulk_wait_read<0>();
+          epi_bar_sync();
+          if (threadIdx.x == EPI_WARP0 * 32) {
+            ptx::bulk_s2g(save_base + (size_t)kb * KBLOCK_BYTES, stg, 2 * IMAGE_BYTES);      // slots kb, kb + 1 are contiguous in the tile
+            ptx::bulk_commit();
+          }
+          ++save_count;
         };
 
         const int nblocks = n >> 6;
         uint32_t va[COLS], pk[COLS / 2];
-        for (int kb = 0; kb < nblocks; ++kb) {
-          if (kb == 0 || (SRF_MLP_SPLIT && kb == 2)) {            // blocks 2, 3 belong to the second column half
-            const uint32_t b = buf * 2 + (SRF_MLP_SPLIT ? (uint32_t)(kb >> 1) : 0u);
-            ptx::mbar_wait_addr(d_full_addr + b * 8u, (d_phase >> b) & 1);
-            d_phase ^= 1u << b;
-            ptx::tc_fence_after();
-            if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + (kb ? 9 : 0));
+        if (save_base == nullptr) {
+          for (int kb = 0; kb < nblocks; ++kb) {
+            if (kb == 0 || (SRF_MLP_SPLIT && kb == 2)) {            // blocks 2, 3 belong to the second column half
+              const uint32_t b = buf * 2 + (SRF_MLP_SPLIT ? (uint32_t)(kb >> 1) : 0u);
+              ptx::mbar_wait_addr(d_full_addr + b * 8u, (d_phase >> b) & 1);
+              d_phase ^= 1u << b;
+              ptx::tc_fence_after();
+              if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + (kb ? 9 : 0));
+            }
+            tmem_load<COLS>(t_row + kb * 64, va);
+            ptx::tmem_ld_wait(va);
+            if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 1 + 2 * kb);
+            compute(va, pk, kb);       // (a compile-time specialisation of this loop for plain hidden layers measured 8 % SLOWER)
+            publish(pk, kb);
+            if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * kb);
           }
-          tmem_load<COLS>(t_row + kb * 64, va);
-          ptx::tmem_ld_wait(va);
-          if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 1 + 2 * kb);
-          compute(va, pk, kb);       // (a compile-time specialisation of this loop for plain hidden layers measured 8 % SLOWER)
-          store(pk, kb);
-          if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * kb);
+        } else {
+          // training: blocks in pairs (layer widths are multiples of 128) - publish both, then save both
+          uint32_t pk2[COLS / 2];
+          for (int kb = 0; kb < nblocks; kb += 2) {
+            if (kb == 0 || SRF_MLP_SPLIT) {
+              const uint32_t b = buf * 2 + (SRF_MLP_SPLIT ? (uint32_t)(kb >> 1) : 0u);
+              ptx::mbar_wait_addr(d_full_addr + b * 8u, (d_phase >> b) & 1);
+              d_phase ^= 1u << b;
+              ptx::tc_fence_after();
+              if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + (kb ? 9 : 0));
+            }
+            tmem_load<COLS>(t_row + kb * 64, va);
+            ptx::tmem_ld_wait(va);
+            compute(va, pk, kb);
+            const uint32_t m0 = mask_bits;
+            publish(pk, kb);
+            if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * kb);
+            tmem_load<COLS>(t_row + (kb + 1) * 64, va);
+            ptx::tmem_ld_wait(va);
+            compute(va, pk2, kb + 1);
+            const uint32_t m1 = mask_bits;
+            publish(pk2, kb + 1);
+            if (warp == EPI_WARP0 && lane == 0) TRACE(1024 + l * 16 + 2 + 2 * (kb + 1));
+            save_pair(pk, m0, pk2, m1, kb);
+          }
         }
         ptx::tc_fence_before();
         if (head_rows > 0) {
