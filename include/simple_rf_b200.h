@@ -138,6 +138,10 @@ int srf_nerf_mlp_fwd(const void* program, const void* weights, const float* side
                      int64_t num_rays, int num_samples, float* sigma, float* rgb, void* save_acts,
                      int act_slots, int e_slot, int v_slot, void* stream);
 int srf_nerf_mlp_program_bytes(void);   /* sizeof(srf_mlp_program) as compiled, for binding self-checks */
+/* bf16 inference launches of srf_nerf_mlp_fwd as clusters of two CTAs sharing every MMA (tcgen05 cta_group::2, M = 256, each CTA
+ * holding half of every weight image): 1 on, 0 off, -1 back to the default (environment SRF_MLP_PAIR, else off).  Returns the
+ * previous setting.  Results are bit-identical either way. */
+int srf_mlp_set_pairing(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Simple-TensoRF vector-matrix tensor.  Small parameter blocks marked HOST are host pointers read at launch.

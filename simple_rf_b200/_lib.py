@@ -28,6 +28,7 @@ _SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_nerf_mlp_fwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, c_int, c_int, c_int, _P]),
     'srf_nerf_mlp_program_bytes': (c_int, []),
+    'srf_mlp_set_pairing': (c_int, [c_int]),
     'srf_pack_alpha_bits': (c_int, [_P, c_int64, _P, _P]),
     'srf_compaction_blocks': (c_int, [c_int64]),
     'srf_tensorf_mask': (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -17,6 +17,7 @@
 //   epilogue warps: tcgen05.ld -> +bias, ReLU -> bf16 pairs -> tcgen05.st over the accumulator columns just drained = the
 //                   next layer's A operand, signalled per 64-column K-block so the next layer's MMAs start while the rest
 //                   of the epilogue is still running; the 1/3/4-wide heads are thread-local dot products.
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -92,6 +93,12 @@ __device__ long long g_mlp_trace[4096];
 #ifndef SRF_MLP_CHUNK
 #define SRF_MLP_CHUNK 2
 #endif
+#ifndef SRF_PAIR_CLUSTER_ACQUIRE
+#define SRF_PAIR_CLUSTER_ACQUIRE 0
+#endif
+#ifndef SRF_MLP_PAIR_DEFAULT
+#define SRF_MLP_PAIR_DEFAULT 0
+#endif
 constexpr int GROUPS = 2;                         // column groups per 64-wide block = epilogue warps per TMEM lane quarter
 constexpr int COLS = 64 / GROUPS;                 // columns of a 64-wide block owned by one epilogue warp
 constexpr int EPI_THREADS = 128 * GROUPS;
@@ -152,6 +159,7 @@ struct alignas(1024) MlpSmem {
   float side[MAX_SIDE];
   float part[2][GROUPS][128][4];          // head partial sums of each column group
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
+  uint64_t pair_full[NUM_STAGES];         // CTA pair: the PEER CTA's half of the stage's weight image has landed (leader only)
   uint64_t a_ready[6];                    // per A region (0 E, 1..4 H blocks, 5 V): written and visible to the tensor core
   uint64_t d_full[4];                     // [accumulator buffer][column half] complete
   uint64_t e_free, v_free;                // every MMA reading region 0 / 5 of the current tile has retired
@@ -204,7 +212,13 @@ __device__ __forceinline__ void tmem_load<32>(uint32_t taddr, uint32_t (&v)[32])
 template <>
 __device__ __forceinline__ void tmem_load<16>(uint32_t taddr, uint32_t (&v)[16]) { ptx::tmem_ld16(taddr, v); }
 
-template <bool SPLIT>             // SPLIT: split-bf16 operands (prog.lo_offset != 0); a separate instantiation keeps the bf16 path free of it
+// SPLIT: split-bf16 operands (prog.lo_offset != 0); a separate instantiation keeps the bf16 path free of it.
+// PAIR: launched as clusters of two CTAs (the two SMs of a TPC) that share every MMA (tcgen05 cta_group::2, M = 256): each CTA keeps
+// its own tile, encoder, epilogue and tensor memory, but holds only HALF of every weight image (64 of the step's 128 output units) -
+// the shared-memory traffic of the weight stream, which is what bounds this kernel, halves in both directions, and so does the L2
+// stream.  The leader CTA's issuers drive the MMAs of both tiles; the peer's arrivals reach the leader's barriers through
+// shared::cluster addresses, completions come back as multicast commits.
+template <bool SPLIT, bool PAIR>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __grid_constant__ MlpProgram prog,
                                                                       const __grid_constant__ MmaSchedule sched, const MlpArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -214,18 +228,27 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
 
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader_cta = cta_rank == 0u;
+  constexpr uint32_t CTAS = PAIR ? 2u : 1u;
   for (int i = threadIdx.x; i < prog.side_count; i += MLP_THREADS) sm.side[i] = args.side[i];
   if (warp == PRODUCER_WARP && lane == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
-    ptx::mbar_init(&sm.a_ready[0], 4);
-    ptx::mbar_init(&sm.a_ready[5], 4);
-    for (int r = 1; r < 5; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * GROUPS);
+    for (int s = 0; s < NUM_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); ptx::mbar_init(&sm.pair_full[s], 1); }
+    ptx::mbar_init(&sm.a_ready[0], 4 * CTAS);                    // the leader's barriers collect both CTAs' arrivals
+    ptx::mbar_init(&sm.a_ready[5], 4 * CTAS);
+    for (int r = 1; r < 5; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * GROUPS * CTAS);
     for (int b = 0; b < 4; ++b) ptx::mbar_init(&sm.d_full[b], 1);
     ptx::mbar_init(&sm.e_free, 1);
     ptx::mbar_init(&sm.v_free, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == ISSUER1_WARP) ptx::tmem_alloc(&sm.tmem_base, 512);
+  if constexpr (PAIR) {
+    __syncthreads();
+    ptx::cluster_sync_all();                                     // both CTAs' barriers exist before anything arrives remotely
+    if (warp == ISSUER1_WARP) ptx::tmem_alloc_pair(&sm.tmem_base, 512);
+  } else {
+    if (warp == ISSUER1_WARP) ptx::tmem_alloc(&sm.tmem_base, 512);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -233,7 +256,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   long long total = args.total;
   if (args.count != nullptr) { const long long c = *args.count; total = c < total ? c : total; }
   const int num_tiles = (int)((total + 127) / 128);
-  const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // persistent loop: CTA b takes tiles b, b + grid, ...; a CTA pair takes the tile pairs (2j, 2j + 1) the same way (a missing second tile
+  // of the last pair is processed as an all-invalid tile: both CTAs must run the same steps)
+  const int units = PAIR ? (num_tiles + 1) / 2 : num_tiles;
+  const int unit0 = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x, unit_stride = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int my_tiles = units > unit0 ? (units - unit0 + unit_stride - 1) / unit_stride : 0;
+  auto tile_of = [&](int t) { return (long long)(unit0 + t * unit_stride) * (long long)CTAS + cta_rank; };
   constexpr bool split = SPLIT;                    // (launcher: never together with save_acts / rows)
   const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : (split ? (uint32_t)E_LO_STAGE : NUM_STAGES);
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
@@ -248,11 +276,42 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           const MmaStep st = sched.steps[s];
           const uint32_t images = (st.meta >> 16) & 3u;
           ptx::mbar_wait(&sm.w_empty[stage], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&sm.w_full[stage], images * IMAGE_BYTES);
-          const uint32_t half_stride = ((st.meta >> 18) & 7u) * IMAGE_BYTES;     // blob order: [layer][128-row half][K block]
-          for (uint32_t i = 0; i < images; ++i)
-            ptx::bulk_g2s(sm.w[stage] + i * IMAGE_BYTES, args.weights + ((size_t)st.w_off << 4) + (size_t)i * half_stride, IMAGE_BYTES,
+          if constexpr (PAIR) {
+#if SRF_MLP_SPLIT
+            // N = 128 steps: this CTA's half of the image, output units 64 * rank .. 64 * rank + 63 = eight 1 KB swizzle atoms, contiguous
+            ptx::mbar_arrive_expect_tx(&sm.w_full[stage], IMAGE_BYTES / 2);
+            ptx::bulk_g2s(sm.w[stage], args.weights + ((size_t)st.w_off << 4) + (size_t)cta_rank * (IMAGE_BYTES / 2), IMAGE_BYTES / 2,
                           &sm.w_full[stage]);
+#else
+            // N = 256 steps: the leader holds the image of output units 0..127, the peer the image of units 128..255
+            const uint32_t half_stride = ((st.meta >> 18) & 7u) * IMAGE_BYTES;
+            const uint32_t mine = images > 1 ? cta_rank : 0u;
+            ptx::mbar_arrive_expect_tx(&sm.w_full[stage], images > 1 ? IMAGE_BYTES : IMAGE_BYTES / 2);
+            if (images > 1) ptx::bulk_g2s(sm.w[stage], args.weights + ((size_t)st.w_off << 4) + (size_t)mine * half_stride, IMAGE_BYTES, &sm.w_full[stage]);
+            else ptx::bulk_g2s(sm.w[stage], args.weights + ((size_t)st.w_off << 4) + (size_t)cta_rank * (IMAGE_BYTES / 2), IMAGE_BYTES / 2, &sm.w_full[stage]);
+#endif
+          } else {
+            ptx::mbar_arrive_expect_tx(&sm.w_full[stage], images * IMAGE_BYTES);
+            const uint32_t half_stride = ((st.meta >> 18) & 7u) * IMAGE_BYTES;     // blob order: [layer][128-row half][K block]
+            for (uint32_t i = 0; i < images; ++i)
+              ptx::bulk_g2s(sm.w[stage] + i * IMAGE_BYTES, args.weights + ((size_t)st.w_off << 4) + (size_t)i * half_stride, IMAGE_BYTES,
+                            &sm.w_full[stage]);
+          }
+          if (++stage == num_stages) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (PAIR && !leader_cta && (warp == ISSUER1_WARP || warp == ISSUER2_WARP)) {
+    // ------------------------------------------------------------ peer CTA: no MMA issue.  One warp tells the leader, stage by stage,
+    // that this CTA's half of the weight image has landed (the leader's MMA reads it from here)
+    if (warp == ISSUER1_WARP) {
+      const int num_steps = sched.num_steps;
+      const uint32_t remote = ptx::map_to_cta(ptx::smem_u32(&sm.pair_full[0]), 0u);
+      uint32_t stage = 0, ph = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int s = 0; s < num_steps; ++s) {
+          ptx::mbar_wait(&sm.w_full[stage], ph);
+          if (lane == 0) ptx::mbar_arrive_cluster_relaxed(remote + stage * 8u);     // the bytes were landed by the copy engine, not by this thread
           if (++stage == num_stages) { stage = 0; ph ^= 1; }
         }
       }
@@ -268,6 +327,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     const uint32_t w_lo = (ptx::smem_u32(sm.w[0]) >> 4) & 0x3FFF;
     const uint32_t a_lo = (ptx::smem_u32(sm.a[0]) >> 4) & 0x3FFF;
     const uint32_t bar_full = ptx::smem_u32(&sm.w_full[0]), bar_empty = ptx::smem_u32(&sm.w_empty[0]);
+    const uint32_t bar_pair = ptx::smem_u32(&sm.pair_full[0]);
     const uint32_t bar_a = ptx::smem_u32(&sm.a_ready[0]), bar_d = ptx::smem_u32(&sm.d_full[0]);
     const uint32_t bar_e = ptx::smem_u32(&sm.e_free), bar_v = ptx::smem_u32(&sm.v_free);
     const uint4* steps = reinterpret_cast<const uint4*>(sched.steps);
@@ -282,7 +342,19 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       const uint32_t meta = st.z;
       const uint32_t wr = (meta >> 8) & 15u;
       const uint32_t tp = (uint32_t)t & 1u;
-      if (wr) ptx::mbar_wait_addr(bar_a + (wr - 1) * 8, ((meta >> 14) ^ ((meta >> 15) & tp)) & 1u);
+      if constexpr (PAIR) {
+#if SRF_PAIR_CLUSTER_ACQUIRE
+        if (wr) ptx::mbar_wait_addr_cluster(bar_a + (wr - 1) * 8, ((meta >> 14) ^ ((meta >> 15) & tp)) & 1u);
+        ptx::mbar_wait_addr_cluster(bar_pair + stage * 8, ph);
+#else
+        // CTA-scope waits: nothing the peer wrote is read by THIS thread - the consumers are the tensor cores (async proxy), and the
+        // producers ordered their writes with tcgen05.wait::st / fence.proxy.async before arriving
+        if (wr) ptx::mbar_wait_addr(bar_a + (wr - 1) * 8, ((meta >> 14) ^ ((meta >> 15) & tp)) & 1u);
+        ptx::mbar_wait_addr(bar_pair + stage * 8, ph);
+#endif
+      } else {
+        if (wr) ptx::mbar_wait_addr(bar_a + (wr - 1) * 8, ((meta >> 14) ^ ((meta >> 15) & tp)) & 1u);
+      }
       if (lane == 0) TRACE(16 + s * 4 + 0);
       ptx::mbar_wait_addr(bar_full + stage * 8, ph);
       if (lane == 0) TRACE(16 + s * 4 + 1);
@@ -296,11 +368,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       // token (inside the statement): every MMA of the previous step has been issued by the other warp
       if (meta & 0x2000u) {          // A = H block of the previous layer, packed in the other accumulator buffer's columns
         const uint32_t a_t = tmem + (buf ^ 1u) * 256 + st.x;
-        if (me == 0) ptx::umma4_step<2, 3, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
-        else ptx::umma4_step<3, 2, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        if constexpr (PAIR) {
+          if (me == 0) ptx::umma4_step_pair<2, 3, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+          else ptx::umma4_step_pair<3, 2, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        } else {
+          if (me == 0) ptx::umma4_step<2, 3, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+          else ptx::umma4_step<3, 2, true>(issue, d_addr, a_t, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        }
       } else {
-        if (me == 0) ptx::umma4_step<2, 3, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
-        else ptx::umma4_step<3, 2, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        if constexpr (PAIR) {
+          if (me == 0) ptx::umma4_step_pair<2, 3, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+          else ptx::umma4_step_pair<3, 2, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        } else {
+          if (me == 0) ptx::umma4_step<2, 3, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+          else ptx::umma4_step<3, 2, false>(issue, d_addr, a_lo + st.x, b_lo, desc_hi, st.y, acc, ksteps, bar_empty + stage * 8, bx, by, bz);
+        }
       }
       if (lane == 0) TRACE(16 + s * 4 + 2);
       stage += 2;
@@ -312,7 +394,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
     const int row = (warp - ENC_WARP0) * 32 + lane;
     for (int t = 0; t < my_tiles; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long tile = tile_of(t);
       const long long m = tile * 128 + row;
       const bool valid = m < total;
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
@@ -375,7 +457,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm.a_ready[0]);
+      if (lane == 0) {
+        // (pair) the peer signals the LEADER's barrier.  A relaxed arrive: what it announces was written to THIS SM's shared memory and
+        // is read by THIS SM's tensor core; fence.proxy.async + __syncwarp above ordered it.  (release.cluster costs ~1000 cycles here.)
+        if (PAIR && !leader_cta) ptx::mbar_arrive_cluster_relaxed(ptx::map_to_cta(ptx::smem_u32(&sm.a_ready[0]), 0u));
+        else ptx::mbar_arrive(&sm.a_ready[0]);
+      }
       if (warp == ENC_WARP0 && lane == 0) TRACE(1);
       if (has_views) {
         ptx::mbar_wait(&sm.v_free, (t & 1) ^ 1);
@@ -420,7 +507,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&sm.a_ready[5]);
+        if (lane == 0) {
+          if (PAIR && !leader_cta) ptx::mbar_arrive_cluster_relaxed(ptx::map_to_cta(ptx::smem_u32(&sm.a_ready[5]), 0u));
+          else ptx::mbar_arrive(&sm.a_ready[5]);
+        }
       }
     }
   } else {
@@ -429,11 +519,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     const int grp = (warp - EPI_WARP0) >> 2;   // column group of every 64-wide block this warp owns
     const int row = quarter * 32 + lane;
     uint32_t layer_count = 0;
-    const uint32_t side_addr = ptx::smem_u32(sm.side), a_ready_addr = ptx::smem_u32(&sm.a_ready[0]), d_full_addr = ptx::smem_u32(&sm.d_full[0]);
+    const uint32_t side_addr = ptx::smem_u32(sm.side), d_full_addr = ptx::smem_u32(&sm.d_full[0]);
+    const bool remote_arrive = PAIR && !leader_cta;              // the peer's epilogue signals the LEADER's barriers
+    const uint32_t a_ready_addr = remote_arrive ? ptx::map_to_cta(ptx::smem_u32(&sm.a_ready[0]), 0u) : ptx::smem_u32(&sm.a_ready[0]);
     uint32_t d_phase = 0;                // bit b: parity to wait for on d_full[b]
     uint32_t save_count = 0;             // staged activation images so far (selects the staging buffer)
     for (int t = 0; t < my_tiles; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long tile = tile_of(t);
       const long long m = tile * 128 + row;
       const bool valid = m < total;
       for (int l = 0; l < prog.num_layers; ++l, ++layer_count) {
@@ -544,7 +636,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_addr(a_ready_addr + (uint32_t)(1 + kb) * 8u);
+            if (lane == 0) {
+              // (pair, peer CTA) relaxed: the tensor-memory stores completed at tcgen05.wait::st and were fenced above
+              if (remote_arrive) ptx::mbar_arrive_cluster_relaxed(a_ready_addr + (uint32_t)(1 + kb) * 8u);
+              else ptx::mbar_arrive_addr(a_ready_addr + (uint32_t)(1 + kb) * 8u);
+            }
           }
         };
         // training: the same packed pairs of TWO K blocks go to HBM as tile images, AFTER both blocks have been published to the
@@ -660,9 +756,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   if (threadIdx.x == EPI_WARP0 * 32 && args.save_acts != nullptr) ptx::bulk_wait_all();   // staged images have left shared memory
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();        // the peer may still be reading / being written by the pair's last MMAs
   if (warp == ISSUER1_WARP) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 512);
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem, 512);
+    else ptx::tmem_dealloc(tmem, 512);
   }
 }
 
@@ -671,6 +769,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
 using namespace srf;
 
 namespace {
+int g_pair_mode = -1;          // -1: not decided yet (environment / build default), 0: one CTA per tile, 1: CTA pairs
+
 int validate_program(const MlpProgram& prog, const char* where, bool rows_mode) {
   SRF_REQUIRE(prog.num_layers >= 1 && prog.num_layers <= MLP_MAX_LAYERS, where, "bad layer count");
   SRF_REQUIRE(prog.points_degree >= 0 && prog.points_degree <= 10 && prog.views_degree <= 4, where,
@@ -706,7 +806,7 @@ int validate_program(const MlpProgram& prog, const char* where, bool rows_mode) 
 }
 
 // flatten the layer program into the MMA issuer's K-block steps
-MmaSchedule make_schedule(const MlpProgram& prog) {
+MmaSchedule make_schedule(const MlpProgram& prog, bool pair) {
   MmaSchedule sc{};
   int ns = 0, last_e = -1, last_v = -1;
   uint32_t seen = 0;
@@ -733,7 +833,7 @@ MmaSchedule make_schedule(const MlpProgram& prog) {
           if (reg == 0) st.a_off = a_lo ? smem_lo[0] : 0u;
           else if (reg == 5) st.a_off = a_lo ? smem_lo[1] : (uint32_t)(V_REGION * KBLOCK_BYTES) >> 4;
           else st.a_off = (uint32_t)(reg - 1) * 64u + (a_lo ? 16u : 0u);
-          st.idesc = ptx::make_idesc_bf16(128, (uint32_t)(128 * images));
+          st.idesc = ptx::make_idesc_bf16(pair ? 256 : 128, (uint32_t)(128 * images));      // a CTA pair issues M = 256 (128 rows per CTA)
           const bool wait = !((seen >> reg) & 1);
           seen |= 1u << reg;
           st.meta = (uint32_t)L.kblock_ksteps[kb] | (kb == 0 && term == 0 ? 8u : 0u) |
@@ -775,15 +875,32 @@ int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, vo
   SRF_REQUIRE(schedule_steps(prog) <= MAX_STEPS, where, "layer program needs more MMA steps than the schedule holds");
   SRF_REQUIRE(prog.lo_offset == 0 || (prog.lo_offset > 0 && (prog.lo_offset & 15) == 0 && a.save_acts == nullptr && a.rows == nullptr),
               where, "split-bf16 programs (lo_offset != 0) are inference-only: no saved activation tiles, no rows mode");
-  const MmaSchedule sched = make_schedule(prog);
   const bool split = prog.lo_offset != 0;
-  auto* kernel = split ? nerf_mlp_fwd_kernel<true> : nerf_mlp_fwd_kernel<false>;
-  static unsigned long long configured[2] = {0ull, 0ull};          // per kernel instantiation, one bit per device
-  if (first_use_on_this_device(configured[split ? 1 : 0])) {
+  const long long tiles = (max_total + 127) / 128;
+  // CTA pairs (cta_group::2) for the bf16 inference forward: srf_mlp_set_pairing(), else the environment (SRF_MLP_PAIR), else the
+  // build default.  Same results bit for bit; measured throughput-neutral under the board's power cap
+  if (g_pair_mode < 0) { const char* e = getenv("SRF_MLP_PAIR"); g_pair_mode = e != nullptr ? (atoi(e) != 0) : SRF_MLP_PAIR_DEFAULT; }
+  const bool pair = g_pair_mode && !split && a.save_acts == nullptr && a.rows == nullptr && tiles >= 2;
+  const MmaSchedule sched = make_schedule(prog, pair);
+  auto* kernel = pair ? nerf_mlp_fwd_kernel<false, true> : (split ? nerf_mlp_fwd_kernel<true, false> : nerf_mlp_fwd_kernel<false, false>);
+  static unsigned long long configured[3] = {0ull, 0ull, 0ull};          // per kernel instantiation, one bit per device
+  if (first_use_on_this_device(configured[pair ? 2 : (split ? 1 : 0)])) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(where, cudaGetErrorString(e));
   }
-  const long long tiles = (max_total + 127) / 128;
+  if (pair) {
+    const long long pairs = (tiles + 1) / 2;
+    const int clusters = pairs < sm_count() / 2 ? (int)pairs : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(MLP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, prog, sched, a);
+    if (e != cudaSuccess) return fail(where, cudaGetErrorString(e));
+    return check_launch(where);
+  }
   const int grid = tiles < sm_count() ? (int)tiles : sm_count();
   kernel<<<grid, MLP_THREADS, smem, (cudaStream_t)stream>>>(prog, sched, a);
   return check_launch(where);
@@ -837,6 +954,12 @@ SRF_API int srf_mlp_rows_fwd(const void* program, const void* weights, const flo
 }
 
 SRF_API int srf_nerf_mlp_program_bytes(void) { return (int)sizeof(MlpProgram); }
+
+SRF_API int srf_mlp_set_pairing(int mode) {
+  const int before = g_pair_mode;
+  g_pair_mode = mode < 0 ? -1 : (mode != 0);
+  return before;
+}
 
 #if SRF_MLP_TRACE
 extern "C" __attribute__((visibility("default"))) int srf_debug_mlp_trace(long long* host_out) {

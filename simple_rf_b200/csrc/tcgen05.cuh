@@ -274,6 +274,148 @@ __device__ __forceinline__ void umma4_step(uint32_t issue, uint32_t d_tmem, uint
         : "memory");
   }
 }
+// ---------------------------------------------------------------- CTA pair (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) execute ONE MMA: M = 256 (128 rows per CTA, A from each CTA's own tensor or
+// shared memory), B split between the CTAs' shared memories (N / 2 rows each, same offset), D in each CTA's tensor memory at
+// the same address.  Only the leader (cluster rank 0) issues; completion is multicast to the same barrier offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// no ordering of this thread's own writes implied (a pure signal)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr_cluster(uint32_t bar_smem_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar_smem_addr), "r"(parity)
+      : "memory");
+}
+// one warp of EACH CTA of the pair, same warp index, same shared-memory offset for the result
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// umma4_step for the leader of a CTA pair: cta_group::2 MMAs, commits multicast to both CTAs (mask 0b11)
+template <int SYNC_ID, int ARRIVE_ID, bool TS>
+__device__ __forceinline__ void umma4_step_pair(uint32_t issue, uint32_t d_tmem, uint32_t a, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t accumulate, uint32_t ksteps, uint32_t bar_empty,
+                                           uint32_t bar_x, uint32_t bar_y, uint32_t bar_z) {
+  if constexpr (TS) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, ptrue, q0, q1, q2, q3, cx, cy, cz;\n\t"
+        ".reg .b16 both;\n\t"
+        "mov.b16 both, 3;\n\t"
+        ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 db0, db1, db2, db3;\n\t"
+        "setp.ne.b32 pacc, %5, 0;\n\t"
+        "setp.eq.b32 ptrue, 0, 0;\n\t"
+        "setp.ne.b32 q0, %6, 0;\n\t"
+        "setp.gt.and.u32 q1, %7, 1, q0;\n\t"
+        "setp.gt.and.u32 q2, %7, 2, q0;\n\t"
+        "setp.gt.and.u32 q3, %7, 3, q0;\n\t"
+        "setp.ne.and.b32 cx, %9, 0, q0;\n\t"
+        "setp.ne.and.b32 cy, %10, 0, q0;\n\t"
+        "setp.ne.and.b32 cz, %11, 0, q0;\n\t"
+        "add.u32 a1, %1, 8;\n\t"
+        "add.u32 a2, %1, 32;\n\t"
+        "add.u32 a3, %1, 40;\n\t"
+        "add.u32 b1, %2, 2;\n\t"
+        "add.u32 b2, %2, 4;\n\t"
+        "add.u32 b3, %2, 6;\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "bar.sync %12, 64;\n\t"
+        "tcgen05.fence::after_thread_sync;\n\t"
+        "@q0 tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db0, %4, pacc;\n\t"
+        "@q1 tcgen05.mma.cta_group::2.kind::f16 [%0], [a1], db1, %4, ptrue;\n\t"
+        "@q2 tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], db2, %4, ptrue;\n\t"
+        "@q3 tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], db3, %4, ptrue;\n\t"
+        "@q0 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], both;\n\t"
+        "@cx tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], both;\n\t"
+        "@cy tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%10], both;\n\t"
+        "@cz tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%11], both;\n\t"
+        "tcgen05.fence::before_thread_sync;\n\t"
+        "bar.arrive %13, 64;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps), "r"(bar_empty), "r"(bar_x),
+        "r"(bar_y), "r"(bar_z), "n"(SYNC_ID), "n"(ARRIVE_ID)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, ptrue, q0, q1, q2, q3, cx, cy, cz;\n\t"
+        ".reg .b16 both;\n\t"
+        "mov.b16 both, 3;\n\t"
+        ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "setp.ne.b32 pacc, %5, 0;\n\t"
+        "setp.eq.b32 ptrue, 0, 0;\n\t"
+        "setp.ne.b32 q0, %6, 0;\n\t"
+        "setp.gt.and.u32 q1, %7, 1, q0;\n\t"
+        "setp.gt.and.u32 q2, %7, 2, q0;\n\t"
+        "setp.gt.and.u32 q3, %7, 3, q0;\n\t"
+        "setp.ne.and.b32 cx, %9, 0, q0;\n\t"
+        "setp.ne.and.b32 cy, %10, 0, q0;\n\t"
+        "setp.ne.and.b32 cz, %11, 0, q0;\n\t"
+        "add.u32 a1, %1, 2;\n\t"
+        "add.u32 a2, %1, 4;\n\t"
+        "add.u32 a3, %1, 6;\n\t"
+        "add.u32 b1, %2, 2;\n\t"
+        "add.u32 b2, %2, 4;\n\t"
+        "add.u32 b3, %2, 6;\n\t"
+        "mov.b64 da0, {%1, %3};\n\t"
+        "mov.b64 da1, {a1, %3};\n\t"
+        "mov.b64 da2, {a2, %3};\n\t"
+        "mov.b64 da3, {a3, %3};\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "bar.sync %12, 64;\n\t"
+        "tcgen05.fence::after_thread_sync;\n\t"
+        "@q0 tcgen05.mma.cta_group::2.kind::f16 [%0], da0, db0, %4, pacc;\n\t"
+        "@q1 tcgen05.mma.cta_group::2.kind::f16 [%0], da1, db1, %4, ptrue;\n\t"
+        "@q2 tcgen05.mma.cta_group::2.kind::f16 [%0], da2, db2, %4, ptrue;\n\t"
+        "@q3 tcgen05.mma.cta_group::2.kind::f16 [%0], da3, db3, %4, ptrue;\n\t"
+        "@q0 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], both;\n\t"
+        "@cx tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], both;\n\t"
+        "@cy tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%10], both;\n\t"
+        "@cz tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%11], both;\n\t"
+        "tcgen05.fence::before_thread_sync;\n\t"
+        "bar.arrive %13, 64;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue), "r"(ksteps), "r"(bar_empty), "r"(bar_x),
+        "r"(bar_y), "r"(bar_z), "n"(SYNC_ID), "n"(ARRIVE_ID)
+        : "memory");
+  }
+}
 // thread i of the warp writes 16 consecutive 32-bit columns of lane (lane base + i)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(

@@ -137,3 +137,32 @@ def test_split_bf16_program_meets_the_fp32_contract(golden_configs, variant, R, 
     if R * S > 1000:
         assert smax > 10.0                                            # the field really is sharp
         assert errs['bf16x3'][0] * 20 < errs['bf16'][0] and errs['bf16x3'][1] * 20 < errs['bf16'][1], errs
+
+
+@pytest.mark.parametrize('variant', ['main', 'points_augmentation', 'views_augmentation'])
+@pytest.mark.parametrize('R,S', [(513, 192), (3, 64), (1, 2)])
+def test_cta_pair_launch_is_bit_identical(golden_configs, variant, R, S):
+    """`srf_mlp_set_pairing(1)`: clusters of two CTAs share every MMA (tcgen05 cta_group::2, half of each weight image per CTA, the
+    peer's arrivals on the leader's barriers, multicast commits).  Same arithmetic in the same order: outputs must not change by a
+    bit, for odd tile counts (a pair with a missing second tile) and single-tile launches (which fall back to one CTA) alike."""
+    from simple_rf_b200 import _lib, nerf_program
+    configs, mc, variants = _variants(golden_configs)
+    cfg = variants[variant]
+    g = torch.Generator().manual_seed(3 * R + S)
+    params = {k: v.to(DEV) for k, v in M.init_mlp_params(cfg, g).items()}
+    packed = nerf_program.PackedMLP(cfg).refresh(params)
+    o = (torch.rand(R, 3, generator=g) - 0.5).to(DEV)
+    d = (torch.rand(R, 3, generator=g) - 0.5).to(DEV)
+    vd = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).to(DEV)
+    z = torch.rand(R, S, generator=g).to(DEV)
+    lib = _lib.load()
+    before = lib.srf_mlp_set_pairing(0)
+    try:
+        s0, c0 = packed.forward(o, d, z, vd)
+        lib.srf_mlp_set_pairing(1)
+        s1, c1 = packed.forward(o, d, z, vd)
+        torch.cuda.synchronize()
+    finally:
+        lib.srf_mlp_set_pairing(before)
+    assert torch.equal(s0, s1) and torch.equal(c0, c1)
+    assert torch.isfinite(s1).all() and torch.isfinite(c1).all()
