@@ -30,5 +30,5 @@ echo "## excerpt: bulk-copy (TMA) weight producer of nerf_mlp_fwd_kernel"
 awk '/Function : .*nerf_mlp_fwd_kernel/ {f=1} f && /UBLKCP/ {print; n++} n>=4 {exit}' "$TMP" | sed 's/^ *//' | cut -c1-150
 rm -f "$TMP"
 echo
-echo "## CTA-pair instantiation nerf_mlp_fwd_kernel<false, true>: cta_group::2 MMAs and multicast commits"
-awk '/Function : .*nerf_mlp_fwd_kernelILb0ELb1/ {f=1; next} /Function : / {f=0} f && /2CTA/ {print}' "$TMP" | sed 's/^ *//; s/ *\/\* 0x[0-9a-f]* \*\/ *$//' | sed 's/\/\*[0-9a-f]*\*\/ *//' | sort | uniq -c | sort -rn | head -12
+echo "## CTA-pair instantiation nerf_mlp_fwd_kernel<false, true>: cta_group::2 MMAs and multicast commits (mnemonic counts)"
+awk '/Function : .*nerf_mlp_fwd_kernelILb0ELb1/ {f=1; next} /Function : / {f=0} f && /2CTA/ {for (i = 1; i <= NF; i++) if ($i ~ /2CTA/) {c[$i]++; break}} END {for (k in c) print c[k], k}' "$TMP" | sort -rn
