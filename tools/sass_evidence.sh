@@ -28,7 +28,7 @@ awk '/Function : .*nerf_mlp_fwd_kernel/ {f=1} f && /UTCHMMA/ {n++} f && n>=1 && 
 echo
 echo "## excerpt: bulk-copy (TMA) weight producer of nerf_mlp_fwd_kernel"
 awk '/Function : .*nerf_mlp_fwd_kernel/ {f=1} f && /UBLKCP/ {print; n++} n>=4 {exit}' "$TMP" | sed 's/^ *//' | cut -c1-150
-rm -f "$TMP"
 echo
 echo "## CTA-pair instantiation nerf_mlp_fwd_kernel<false, true>: cta_group::2 MMAs and multicast commits (mnemonic counts)"
 awk '/Function : .*nerf_mlp_fwd_kernelILb0ELb1/ {f=1; next} /Function : / {f=0} f && /2CTA/ {for (i = 1; i <= NF; i++) if ($i ~ /2CTA/) {c[$i]++; break}} END {for (k in c) print c[k], k}' "$TMP" | sort -rn
+rm -f "$TMP"
