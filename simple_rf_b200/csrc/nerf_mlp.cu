@@ -125,6 +125,12 @@ constexpr int NUM_STAGES = 5;
 // 16 KB staging images, written by the epilogue warps and drained to HBM by bulk async copies
 constexpr int SAVE_BUFS = 4;
 constexpr int SAVE_STAGES = NUM_STAGES - SAVE_BUFS * IMAGE_BYTES / STAGE_BYTES;
+// rows mode (TensoRF colour MLP: <= 4 MMA steps per tile): the weight images stay RESIDENT in the first ROWS_RING stages (loaded once per
+// CTA, the ring protocol keeps cycling without copies), and the input rows of the next tiles are staged by bulk async copies into
+// ROW_BUF_BYTES buffers behind them: three tiles ahead at test time, one when the saved-tile staging images take stages SAVE_STAGES..
+constexpr int ROWS_RING = 4;
+constexpr int ROW_BUFS = 3;
+constexpr int ROW_BUF_BYTES = 128 * 256;          // 128 rows x (at most) 16 units of 16 bytes
 constexpr int A_REGIONS = 2;                      // E and V only; the hidden activations live in tensor memory
 constexpr int V_REGION = 1;
 // split-bf16 mode: the lo parts of E and V take the last two ring stages (the ring shrinks to NUM_STAGES - 2)
@@ -159,6 +165,7 @@ struct alignas(1024) MlpSmem {
   float side[MAX_SIDE];
   float part[2][GROUPS][128][4];          // head partial sums of each column group
   uint64_t w_full[NUM_STAGES], w_empty[NUM_STAGES];
+  uint64_t rows_full[ROW_BUFS];           // rows mode: the bulk copy of a tile's input rows has landed in its staging buffer
   uint64_t pair_full[NUM_STAGES];         // CTA pair: the PEER CTA's half of the stage's weight image has landed (leader only)
   uint64_t a_ready[6];                    // per A region (0 E, 1..4 H blocks, 5 V): written and visible to the tensor core
   uint64_t d_full[4];                     // [accumulator buffer][column half] complete
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     for (int b = 0; b < 4; ++b) ptx::mbar_init(&sm.d_full[b], 1);
     ptx::mbar_init(&sm.e_free, 1);
     ptx::mbar_init(&sm.v_free, 1);
+    for (int b = 0; b < ROW_BUFS; ++b) ptx::mbar_init(&sm.rows_full[b], 1);
     ptx::fence_barrier_init();
   }
   if constexpr (PAIR) {
@@ -263,7 +271,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   const int my_tiles = units > unit0 ? (units - unit0 + unit_stride - 1) / unit_stride : 0;
   auto tile_of = [&](int t) { return (long long)(unit0 + t * unit_stride) * (long long)CTAS + cta_rank; };
   constexpr bool split = SPLIT;                    // (launcher: never together with save_acts / rows)
-  const uint32_t num_stages = args.save_acts != nullptr ? SAVE_STAGES : (split ? (uint32_t)E_LO_STAGE : NUM_STAGES);
+  const bool rows_mode = args.rows != nullptr;
+  // rows mode: one ring stage per step of the tile, so stage s always holds step s's image and nothing is ever re-loaded
+  const uint32_t num_stages = rows_mode ? (uint32_t)sched.num_steps
+                                        : (args.save_acts != nullptr ? SAVE_STAGES : (split ? (uint32_t)E_LO_STAGE : NUM_STAGES));
   const bool has_views = prog.views_degree >= 0 || (args.rows != nullptr && prog.views_degree == -2);   // -2: rows mode, 2 blocks
 
   if (warp == PRODUCER_WARP) {
@@ -290,6 +301,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             if (images > 1) ptx::bulk_g2s(sm.w[stage], args.weights + ((size_t)st.w_off << 4) + (size_t)mine * half_stride, IMAGE_BYTES, &sm.w_full[stage]);
             else ptx::bulk_g2s(sm.w[stage], args.weights + ((size_t)st.w_off << 4) + (size_t)cta_rank * (IMAGE_BYTES / 2), IMAGE_BYTES / 2, &sm.w_full[stage]);
 #endif
+          } else if (rows_mode && t > 0) {
+            ptx::mbar_arrive(&sm.w_full[stage]);        // resident image: the stage is "refilled" without a copy
           } else {
             ptx::mbar_arrive_expect_tx(&sm.w_full[stage], images * IMAGE_BYTES);
             const uint32_t half_stride = ((st.meta >> 18) & 7u) * IMAGE_BYTES;     // blob order: [layer][128-row half][K block]
@@ -393,16 +406,36 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
   } else if (warp >= ENC_WARP0 && warp < ENC_WARP0 + 4) {
     // ------------------------------------------------------------ encoding warps: region 0 (E) and 5 (V), one tile ahead
     const int row = (warp - ENC_WARP0) * 32 + lane;
+    // rows mode: tile t's rows arrive in staging buffer t % row_bufs by ONE bulk copy issued row_bufs tiles earlier (the rows of a tile
+    // are contiguous); a thread fetching its own row from global memory one tile ahead left the ~2 us load latency exposed on every
+    // tile (4500 cycles per tile against ~1000 of MMA work)
+    const int row_bufs = args.save_acts != nullptr ? 1 : ROW_BUFS;
+    uint8_t* row_stage = &sm.w[0][0] + (size_t)ROWS_RING * STAGE_BYTES;
+    auto fetch_rows = [&](int t) {                    // one thread: bulk copy of tile t's rows (clamped to the rows array)
+      const long long row0 = tile_of(t) * 128;
+      const long long avail = args.total - row0;
+      const uint32_t bytes = (uint32_t)(avail < 128 ? (avail > 0 ? avail : 0) : 128) * (uint32_t)args.row_units * 16u;
+      const int b = t % row_bufs;
+      if (bytes == 0) { ptx::mbar_arrive(&sm.rows_full[b]); return; }
+      ptx::mbar_arrive_expect_tx(&sm.rows_full[b], bytes);
+      ptx::bulk_g2s(row_stage + (size_t)b * ROW_BUF_BYTES, args.rows + row0 * args.row_units, bytes, &sm.rows_full[b]);
+    };
+    if (rows_mode && warp == ENC_WARP0 && lane == 0)
+      for (int t = 0; t < row_bufs && t < my_tiles; ++t) fetch_rows(t);
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = tile_of(t);
       const long long m = tile * 128 + row;
       const bool valid = m < total;
       float p[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 1.f};
       uint4 x[16];
-      if (args.rows != nullptr) {
+      if (rows_mode) {
+        const int b = t % row_bufs;
+        ptx::mbar_wait(&sm.rows_full[b], (uint32_t)(t / row_bufs) & 1u);
+        const uint4* mine = reinterpret_cast<const uint4*>(row_stage + (size_t)b * ROW_BUF_BYTES) + row * args.row_units;
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-          x[q] = (valid && q < args.row_units) ? __ldg(args.rows + m * args.row_units + q) : make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 16; ++q) x[q] = (valid && q < args.row_units) ? mine[q] : make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("bar.sync 4, 128;" ::: "memory");           // every encoder thread holds its row: the buffer may be refilled
+        if (warp == ENC_WARP0 && lane == 0 && t + row_bufs < my_tiles) fetch_rows(t + row_bufs);
       } else if (valid) {
         const long long r = m / args.S;
         const float zz = args.z[m];
@@ -881,6 +914,8 @@ int launch_mlp(const MlpProgram& prog, const MlpArgs& a, long long max_total, vo
   // build default.  Same results bit for bit; measured throughput-neutral under the board's power cap
   if (g_pair_mode < 0) { const char* e = getenv("SRF_MLP_PAIR"); g_pair_mode = e != nullptr ? (atoi(e) != 0) : SRF_MLP_PAIR_DEFAULT; }
   const bool pair = g_pair_mode && !split && a.save_acts == nullptr && a.rows == nullptr && tiles >= 2;
+  SRF_REQUIRE(a.rows == nullptr || (schedule_steps(prog) <= ROWS_RING && a.row_units <= 16), where,
+              "rows mode keeps the weight images resident: at most 4 MMA steps per tile, rows of at most 256 bytes");
   const MmaSchedule sched = make_schedule(prog, pair);
   auto* kernel = pair ? nerf_mlp_fwd_kernel<false, true> : (split ? nerf_mlp_fwd_kernel<true, false> : nerf_mlp_fwd_kernel<false, false>);
   static unsigned long long configured[3] = {0ull, 0ull, 0ull};          // per kernel instantiation, one bit per device
