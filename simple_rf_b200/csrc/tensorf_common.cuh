@@ -87,7 +87,8 @@ __device__ __forceinline__ void normalized_point(const VmGeom& g, int flat, floa
   }
 }
 
-__device__ __forceinline__ float unnorm(float c, int size) { return __fmul_rn(__fdiv_rn(__fadd_rn(c, 1.f), 2.f), (float)(size - 1)); }
+// ATen: ((c + 1) / 2) * (size - 1); the division by 2 is an exact scaling, so a multiplication by 0.5 gives the same bits
+__device__ __forceinline__ float unnorm(float c, int size) { return __fmul_rn(__fmul_rn(__fadd_rn(c, 1.f), 0.5f), (float)(size - 1)); }
 
 __device__ __forceinline__ Bilerp plane_coords(const float (&pn)[3], const int (&res)[3], int i) {
   Bilerp b;
