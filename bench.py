@@ -16,8 +16,9 @@ independent units, no data-path collective — so scaling is weak and `value` is
             duration of each launch, against the measured bf16 peak in MEASURED_PEAKS.json.
 `workloads`: the rest of BASELINE.json's `metric`, measured in the same run at every N, each with its own roofline:
             Simple-NeRF training it/s (weak: 4096 rays per rank; strong: 4096 global), Simple-TensoRF training it/s,
-            Simple-TensoRF trajectory frames/s, and a single frame sharded over the ranks — training steps go through the fused
-            flat Adam with ONE NCCL all-reduce of the gradient bucket (its bytes and time are reported).
+            Simple-TensoRF trajectory frames/s, the main frame with `mlp_precision='bf16x3'` (the fp32-contract program), and a single
+            frame sharded over the ranks — training steps are ONE CUDA graph each and go through the fused flat Adam with ONE NCCL
+            all-reduce of the gradient bucket (its bytes and time are reported).
 `cpu_baseline` / `--impl reference`: the UNMODIFIED reference classes from baseline/_ref (tools/install_reference.sh) on the host
             CPU (kind "reference"); the CPU oracle port (kind "port") only if no upstream tree is installed.
 `gpu_reference_bar`: the reference's own eager PyTorch path on the same B200 (N = 1 only) — the bar the kernels must beat.
