@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
     if (lane == 0) {
       const int num_steps = sched.num_steps;
       uint32_t stage = 0, ph = 0;
+      const uint64_t keep = ptx::l2_policy_evict_last();      // weight images are re-read per tile by every CTA: keep them in L2
       for (int t = 0; t < my_tiles; ++t) {
         for (int s = 0; s < num_steps; ++s) {
           const MmaStep st = sched.steps[s];
@@ -307,8 +308,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
             ptx::mbar_arrive_expect_tx(&sm.w_full[stage], images * IMAGE_BYTES);
             const uint32_t half_stride = ((st.meta >> 18) & 7u) * IMAGE_BYTES;     // blob order: [layer][128-row half][K block]
             for (uint32_t i = 0; i < images; ++i)
-              ptx::bulk_g2s(sm.w[stage] + i * IMAGE_BYTES, args.weights + ((size_t)st.w_off << 4) + (size_t)i * half_stride, IMAGE_BYTES,
-                            &sm.w_full[stage]);
+              ptx::bulk_g2s_hint(sm.w[stage] + i * IMAGE_BYTES, args.weights + ((size_t)st.w_off << 4) + (size_t)i * half_stride, IMAGE_BYTES,
+                                 &sm.w_full[stage], keep);
           }
           if (++stage == num_stages) { stage = 0; ph ^= 1; }
         }
@@ -693,12 +694,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
           *reinterpret_cast<uint32_t*>(tile_base + act_mask_offset(args.act_slots, save_slot + kb) + grp * 512 + row * 4) = ma;
           *reinterpret_cast<uint32_t*>(tile_base + act_mask_offset(args.act_slots, save_slot + kb + 1) + grp * 512 + row * 4) = mb;
           ptx::fence_proxy_async_smem();
-          // the pair of buffers the NEXT pair will use was handed to the copy engine one bulk group ago: it must have been read
-          // out by the time everybody passes the barrier below
-          if (threadIdx.x == EPI_WARP0 * 32) ptx::bulk_wait_read<0>();
-          epi_bar_sync();
-          if (threadIdx.x == EPI_WARP0 * 32) {
-            ptx::bulk_s2g(save_base + (size_t)kb * KBLOCK_BYTES, stg, 2 * IMAGE_BYTES);      // slots kb, kb + 1 are contiguous in the tile
+          // the 32 rows of a lane quarter are 4 KB of each image, written by the TWO warps of that quarter (same SM sub-partition):
+          // they meet at their own 64-thread barrier and one of them ships the quarter of both images - no CTA-wide epilogue barrier.
+          // The pair of buffers the NEXT pair will use was handed to the copy engine one bulk group ago: it must have been read out by
+          // the time both warps pass the barrier.
+          const bool q_leader = grp == 0 && lane == 0;
+          if (q_leader) ptx::bulk_wait_read<0>();
+          asm volatile("bar.sync %0, 64;" ::"r"(5 + quarter) : "memory");
+          if (q_leader) {
+            const uint64_t once = ptx::l2_policy_evict_first();          // read once, by the backward kernels, much later
+            ptx::bulk_s2g_hint(save_base + (size_t)kb * KBLOCK_BYTES + quarter * 4096, stg + quarter * 4096, 4096, once);
+            ptx::bulk_s2g_hint(save_base + (size_t)(kb + 1) * KBLOCK_BYTES + quarter * 4096, stg + IMAGE_BYTES + quarter * 4096, 4096, once);
             ptx::bulk_commit();
           }
           ++save_count;
@@ -786,7 +792,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_fwd_kernel(const __gr
       }
     }
   }
-  if (threadIdx.x == EPI_WARP0 * 32 && args.save_acts != nullptr) ptx::bulk_wait_all();   // staged images have left shared memory
+  // staged images have left shared memory: every lane quarter's shipping thread drains its own bulk groups
+  if (args.save_acts != nullptr && warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 && lane == 0) ptx::bulk_wait_all();
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) ptx::cluster_sync_all();        // the peer may still be reading / being written by the pair's last MMAs
