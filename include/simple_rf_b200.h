@@ -196,6 +196,29 @@ int srf_vm_color_features_bwd(const float* rays_o, const float* rays_d, const fl
                               const int* resolution, const float* g_rows, int g_row_pitch, float* const* g_planes,
                               float* const* g_lines, void* stream);
 
+/* CANDECOMP/PARAFAC tensor (csrc/tensorf_cp.cu; `decomposition_type = "CandecompParafac"`, SimpleTensoRF09.py:537-539, :964-1124 —
+ * selected by no shipped configuration).  Same contracts as the four VM calls above with lines only: `lines` is a HOST array of 3
+ * device pointers to channels-last [L_i][components] lines, line i running along axis vector_axes[i] = 2 - i (:969), `components` a
+ * multiple of 4 (<= 128 for the appearance calls).
+ *   srf_cp_density_fwd / _bwd          :1043-1062: sigma[idx] = act(sum_c line_0,c line_1,c line_2,c), and its autograd
+ *   srf_cp_color_features_fwd / _bwd   :1064-1078: bf16 rows [products (components) | 3 view_dirs | zero pad], and the scatter of
+ *                                      g_rows[:, :components] into zero-initialised line gradients */
+int srf_cp_density_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices, const int* count,
+                       int64_t max_count, const float* box_min, const float* box_size, const float* const* lines, int components,
+                       const int* resolution, int softplus, float density_offset, float* sigma, float* features, void* stream);
+int srf_cp_density_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices, const int* count,
+                       int64_t max_count, const float* box_min, const float* box_size, const float* const* lines, int components,
+                       const int* resolution, int softplus, float density_offset, const float* g_sigma, const float* features,
+                       float* const* g_lines, void* stream);
+int srf_cp_color_features_fwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                              const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                              const float* const* lines, int components, const int* resolution, const float* view_dirs, void* rows,
+                              int row_pitch, void* stream);
+int srf_cp_color_features_bwd(const float* rays_o, const float* rays_d, const float* z, int num_samples, const int* indices,
+                              const int* count, int64_t max_count, const float* box_min, const float* box_size,
+                              const float* const* lines, int components, const int* resolution, const float* g_rows,
+                              int g_row_pitch, float* const* g_lines, void* stream);
+
 /* dst[indices[j], :] = src[j, :] (the scatter-back of :1238 / :1271) and its transpose. */
 int srf_scatter_rows(const int* indices, const int* count, int64_t max_count, const float* src, int width, float* dst,
                      void* stream);
@@ -212,7 +235,8 @@ int srf_gather_rows(const int* indices, const int* count, int64_t max_count, con
  *      -> volume uint8 {0,1} [Z,Y,X] (the new AlphaGridMask.alpha_volume, :869) and projection uint32[ceil(X/32) + Y + Z]
  *      (CALLER-zeroed): the occupied set projected on each axis — x as row-layout bit words, then one flag per y, per z —
  *      from which the host takes the new bounding box (:871-875: amin / amax of the occupied voxels' coordinates).
- * box_min / box_size / prev_box_* / resolution / prev_res / channels are HOST arrays; planes / lines as for srf_vm_density_fwd. */
+ * box_min / box_size / prev_box_* / resolution / prev_res / channels are HOST arrays; planes / lines as for srf_vm_density_fwd.
+ * planes == NULL evaluates a CANDECOMP/PARAFAC tensor instead (:1043-1062): lines only, channels[0] components in every line. */
 int srf_alpha_grid_words(const int* resolution);
 int srf_alpha_grid_occupancy(const float* const* planes, const float* const* lines, const int* channels, const int* resolution,
                              const float* box_min, const float* box_size, const float* coord_x, const float* coord_y,

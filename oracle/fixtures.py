@@ -35,11 +35,18 @@ def tensorf_sets(configs, seed, with_alpha):
     def one(cfg):
         bbox = torch.tensor(cfg['bounding_box'])
         res = TF.vm_resolution(cfg['num_voxels_initial'], bbox)
-        t = {'params': TF.init_vm_params(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
+        cp = cfg['decomposition_type'] == 'CandecompParafac'
+        init = TF.init_cp_params if cp else TF.init_vm_params
+        t = {'params': init(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
              'bbox': bbox, 'resolution': res, 'num_samples': TF.vm_num_samples(res, cfg['num_voxels_per_sample'], cfg['num_samples_max'])}
         # random-init planes give sigma ~ 0; scale density up so weights cross the 1e-4 surface threshold
+        # (CP: the feature is a sum of products of THREE 0.1 randn factors)
         for i in range(3):
-            t['params'][f'matrices_density.{i}'] *= 6.0
+            if cp:
+                t['params'][f'vectors_density.{i}'] *= 4.5
+                t['params'][f'vectors_color.{i}'] *= 2.2          # products of the size the VM fixture has (0.1 x 0.1)
+            else:
+                t['params'][f'matrices_density.{i}'] *= 6.0
         if with_alpha:
             X, Y, Z = [int(r) for r in res]
             vol = (torch.rand(Z, Y, X, generator=g) < 0.35).float()
@@ -85,7 +92,13 @@ def tensorf_full_size_sets(configs, seed, alpha_size=190):
 def sparsify_density(t, floor=0.6):
     """Random-init planes put sigma above the alpha-mask threshold almost everywhere (after the 3^3 pooling: everywhere).  A
     constant negative density component (channel 0 of plane 0 = -floor, of line 0 = 1) leaves a few per cent of the voxels
-    occupied, so the rebuilt mask, its dilation and the shrunk bounding box are non-trivial."""
+    occupied, so the rebuilt mask, its dilation and the shrunk bounding box are non-trivial.  (CP: component 0 of the three
+    lines = -floor, 1, 1.)"""
+    if TF.is_cp(t['params']):
+        t['params']['vectors_density.0'][:, 0] = -floor
+        t['params']['vectors_density.1'][:, 0] = 1.0
+        t['params']['vectors_density.2'][:, 0] = 1.0
+        return t
     t['params']['matrices_density.0'][:, 0] = -floor
     t['params']['vectors_density.0'][:, 0] = 1.0
     return t
@@ -93,7 +106,8 @@ def sparsify_density(t, floor=0.6):
 
 def carve_empty_border(t, margins=((0.15, 0.1), (0.1, 0.2), (0.2, 0.12))):
     """Push the density far below zero near the faces of the box (per axis: fraction of the extent at the low / high side),
-    so the occupied voxels do not touch the box and shrink_tensor has something to cut."""
+    so the occupied voxels do not touch the box and shrink_tensor has something to cut.  (CP: component 1 + a carries the ramp
+    of axis a in its line, -50 and 1 in the other two lines.)"""
     res = [int(r) for r in t['resolution']]
     for a, (lo, hi) in enumerate(margins):
         n = res[a]
@@ -101,6 +115,12 @@ def carve_empty_border(t, margins=((0.15, 0.1), (0.1, 0.2), (0.2, 0.12))):
         ramp[: int(lo * n)] = 1.0
         ramp[n - int(hi * n):] = 1.0
         i = TF.VECTOR_AXES.index(a)                      # the line running along axis a
+        if TF.is_cp(t['params']):
+            j, k = [q for q in range(3) if q != i]
+            t['params'][f'vectors_density.{i}'][0, 1 + a, :, 0] = ramp
+            t['params'][f'vectors_density.{j}'][0, 1 + a, :, 0] = -50.0
+            t['params'][f'vectors_density.{k}'][0, 1 + a, :, 0] = 1.0
+            continue
         t['params'][f'vectors_density.{i}'][0, 1, :, 0] = ramp
         t['params'][f'matrices_density.{i}'][0, 1] = -50.0
     return t

@@ -232,6 +232,60 @@ def golden_tensorf():
         print(f'tensorf_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f})')
 
 
+def as_cp(configs, comps_density=24, comps_color=48):
+    """Switch every tensor of a Simple-TensoRF config to the CANDECOMP/PARAFAC decomposition (SimpleTensoRF09.py:537-539; selected
+    by no shipped config).  One component count per tensor: every line holds num_components[0] components (:992) and
+    basis_matrix_color takes sum(num_components_color) inputs (:986)."""
+    tensors = [configs['model']['coarse_model']] + [a['coarse_model'] for a in configs['model'].get('augmentations', [])]
+    for cfg in tensors:
+        cfg['decomposition_type'] = 'CandecompParafac'
+        cfg['num_components_density'] = [comps_density]
+        cfg['num_components_color'] = [comps_color]
+    return configs
+
+
+def golden_tensorf_cp():
+    """The CP tensor through the unmodified reference: eval (with an alpha mask) and train (jitter, augmentation tensor)."""
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    as_cp(configs)
+    configs['model']['coarse_model']['num_voxels_initial'] = 40 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 20 ** 3
+    (OUT / 'tensorf_cp_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    assert type(model.coarse_model).__name__ == 'CpDecomposedTensor'
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    keys = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility', 'weights',
+            'raw_sigma', 'raw_rgb')
+    for mode, R, seed, with_alpha in (('eval', 40, 25, True), ('train', 32, 26, False)):
+        sets = FX.tensorf_sets(configs, seed=27, with_alpha=with_alpha)
+        load_tensorf_params(model, sets)
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(500 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+        torch.manual_seed(500 + seed)
+        with torch.no_grad():
+            mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        fixture = {'pixel_id': pixel_id, 'param_seed': 27, 'rng_seed': 500 + seed, 'with_alpha': with_alpha}
+        for k in ('rays_o', 'rays_d', 'rays_o_ndc', 'rays_d_ndc', 'view_dirs', 'z_vals_coarse'):
+            _check(f'tensorf_cp/{mode}/{k}', ref[k], mine[k])
+            fixture[k] = ref[k]
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for k in keys:
+                key = f'{pre}{k}_coarse'
+                _check(f'tensorf_cp/{mode}/{key}', ref[key], mine[key])
+                fixture[key] = ref[key]
+            fixture[f'{pre}validity_mask_coarse'] = mine[f'{pre}validity_mask_coarse']
+            fixture[f'{pre}surface_mask_coarse'] = mine[f'{pre}surface_mask_coarse']
+        frac = mine['validity_mask_coarse'].float().mean().item(), mine['surface_mask_coarse'].float().mean().item()
+        np.savez_compressed(OUT / f'tensorf_cp_{mode}.npz', **_np(fixture))
+        print(f'tensorf_cp_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f}, acc mean {ref["acc_coarse"].mean():.3f})')
+
+
 def tensorf_world_configs():
     """The shipped train0212 config with `ndc = False` (no shipped run selects it; SimpleTensoRF09.py:388-400 is the box-marching
     sampler it switches on): world-space tensor boxes in front of the cameras, near / far in world units."""
@@ -513,10 +567,12 @@ def golden_batch_assembly():
     print('batch_assembly: oracle == reference')
 
 
-def surgery_configs():
+def surgery_configs(cp=False):
     """Shipped TensoRF config shrunk for the CPU: 48^3-voxel main tensor, one upsampling step to 64^3."""
     configs, model_configs = H.load_configs(212, '00000')
     model_configs = H.shrink(model_configs, 4)
+    if cp:
+        as_cp(configs)
     cm = configs['model']['coarse_model']
     cm['num_voxels_initial'], cm['num_voxels_final'] = 48 ** 3, 64 ** 3
     cm['tensor_upsampling_iters'] = [4]
@@ -529,12 +585,13 @@ def _pack(volume):
     return np.packbits(volume.reshape(-1).numpy().astype(np.uint8))
 
 
-def golden_surgery():
+def golden_surgery(cp=False):
     """f3: the reference's own update_alpha_mask / shrink_tensor / upsample_model_resolution on the seeded sparse tensor, in the
     order of its schedule (rebuild + shrink, upsample, rebuild against the previous mask at the old resolution); the oracle
     (oracle/surgery.py) must reproduce every volume, window, box and plane bit-exactly."""
-    configs, model_configs = surgery_configs()
-    (OUT / 'tensorf_surgery_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    tag = 'tensorf_cp_surgery' if cp else 'tensorf_surgery'
+    configs, model_configs = surgery_configs(cp)
+    (OUT / f'{tag}_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
     model = H.build_model(configs, model_configs)
     sets = FX.surgery_sets(configs, seed=41)
     load_tensorf_params(model, sets)
@@ -576,8 +633,12 @@ def golden_surgery():
             if k.startswith(('matrices', 'vectors')):
                 _check(f'surgery/upsample/{k}', v, params[k])
         fixture.update(upsample_resolution=t.resolution.clone(), upsample_num_samples=int(t.num_samples),
-                       upsampled_matrices_density_0=params['matrices_density.0'], upsampled_vectors_color_2=params['vectors_color.2'],
-                       upsampled_matrices_color_1_sum=params['matrices_color.1'].double().sum())
+                       upsampled_vectors_color_2=params['vectors_color.2'])
+        if cp:
+            fixture.update(upsampled_vectors_density_0=params['vectors_density.0'])
+        else:
+            fixture.update(upsampled_matrices_density_0=params['matrices_density.0'],
+                           upsampled_matrices_color_1_sum=params['matrices_color.1'].double().sum())
         # 3. second rebuild: previous mask at the old resolution and the old (pre-shrink) box
         prev_vol, prev_box = t.alpha_mask.alpha_volume.clone(), t.alpha_mask.bounding_box.clone()
         box_ref2 = t.update_alpha_mask(6)
@@ -585,8 +646,8 @@ def golden_surgery():
         _check('surgery/volume2', t.alpha_mask.alpha_volume[0, 0], vol2)
         _check('surgery/box2', box_ref2, box2)
         fixture.update(volume2_bits=_pack(vol2), volume2_shape=torch.tensor(vol2.shape), box2=box_ref2.clone(), occupied2=vol2.mean())
-    np.savez_compressed(OUT / 'tensorf_surgery.npz', **_np(fixture))
-    print(f'tensorf_surgery: oracle == reference (grid {list(vol.shape)} {vol.mean():.3f} occupied -> window {t_l.tolist()}..{b_r.tolist()} '
+    np.savez_compressed(OUT / f'{tag}.npz', **_np(fixture))
+    print(f'{tag}: oracle == reference (grid {list(vol.shape)} {vol.mean():.3f} occupied -> window {t_l.tolist()}..{b_r.tolist()} '
           f'-> {geo["resolution"].tolist()}, second mask {vol2.mean():.3f} occupied)')
 
 
@@ -595,6 +656,10 @@ def main():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if 'cp' in sys.argv[1:]:                     # only the CANDECOMP/PARAFAC fixtures
+        golden_tensorf_cp()
+        golden_surgery(cp=True)
+        return
     configs, model_configs = golden_nerf()
     golden_sample_pdf()
     golden_composite(copy.deepcopy(configs), model_configs)
@@ -607,6 +672,8 @@ def main():
     golden_batch_assembly()
     golden_surgery()
     golden_tensorf_world()
+    golden_tensorf_cp()
+    golden_surgery(cp=True)
 
 
 if __name__ == '__main__':

@@ -40,7 +40,7 @@ def compute_alpha(params, bbox, xyz, length, prev_volume=None, prev_bbox=None, d
     sigma = torch.zeros(xyz.shape[:-1])
     if live.any():
         pn = TF.normalize(xyz, bbox)
-        sigma = TF.vm_density(params, pn, live, density_predictor, density_offset)
+        sigma = TF.density(params, pn, live, density_predictor, density_offset)
     return 1 - torch.exp(-sigma * length).view(xyz.shape[:-1])
 
 
@@ -75,14 +75,15 @@ def shrink_window(geometry, new_bbox, alpha_resolution):
 
 
 def shrink_params(params, t_l, b_r):
-    """SimpleTensoRF09.py:1299-1320: window slices of every plane / line."""
+    """SimpleTensoRF09.py:1299-1320 (VM) / :1113-1124 (CP): window slices of every plane / line."""
     out = dict(params)
     for kind in ('density', 'color'):
         for i in range(3):
             v = TF.VECTOR_AXES[i]
             a0, a1 = TF.MATRIX_AXES[i]
             out[f'vectors_{kind}.{i}'] = params[f'vectors_{kind}.{i}'][..., t_l[v]:b_r[v], :]
-            out[f'matrices_{kind}.{i}'] = params[f'matrices_{kind}.{i}'][..., t_l[a1]:b_r[a1], t_l[a0]:b_r[a0]]
+            if f'matrices_{kind}.{i}' in params:
+                out[f'matrices_{kind}.{i}'] = params[f'matrices_{kind}.{i}'][..., t_l[a1]:b_r[a1], t_l[a0]:b_r[a0]]
     return out
 
 
@@ -96,14 +97,15 @@ def new_num_voxels(iter_num, upsampling_iters, num_voxels_initial, num_voxels_fi
 
 
 def upsample_params(params, new_resolution):
-    """SimpleTensoRF09.py:1284-1297: bilinear, align_corners=True."""
+    """SimpleTensoRF09.py:1284-1297 (VM) / :1101-1111 (CP): bilinear, align_corners=True."""
     out = dict(params)
     res = [int(v) for v in new_resolution]
     for kind in ('density', 'color'):
         for i in range(3):
             a0, a1 = TF.MATRIX_AXES[i]
             v = TF.VECTOR_AXES[i]
-            out[f'matrices_{kind}.{i}'] = F.interpolate(params[f'matrices_{kind}.{i}'], size=(res[a1], res[a0]), mode='bilinear', align_corners=True)
+            if f'matrices_{kind}.{i}' in params:
+                out[f'matrices_{kind}.{i}'] = F.interpolate(params[f'matrices_{kind}.{i}'], size=(res[a1], res[a0]), mode='bilinear', align_corners=True)
             out[f'vectors_{kind}.{i}'] = F.interpolate(params[f'vectors_{kind}.{i}'], size=(res[v], 1), mode='bilinear', align_corners=True)
     return out
 

@@ -1,9 +1,10 @@
-"""Oracle: Simple-TensoRF vector-matrix (VM) tensor evaluation (test infrastructure).
+"""Oracle: Simple-TensoRF vector-matrix (VM) and CANDECOMP/PARAFAC (CP) tensor evaluation (test infrastructure).
 
 Follows src/models/SimpleTensoRF09.py:701-761 (LowRankTensor.forward), :763-765
 (normalize_points), :1214-1239 (VmDecomposedTensor.get_volume_density), :1241-1272
 (get_color), :1342-1349 (AlphaGridMask.sample_alpha / normalize_points) and :1370-1421
-(MlpFeaturesColorPredictor, PE degree 0 == identity).  Parameters are passed as a dict with
+(MlpFeaturesColorPredictor, PE degree 0 == identity); for the CP tensor :1043-1062 (CpDecomposedTensor.get_volume_density)
+and :1064-1089 (get_color).  A parameter dict without `matrices_*` entries is a CP tensor.  Parameters are passed as a dict with
 the reference's state-dict names (`matrices_density.0`, `vectors_color.2`,
 `basis_matrix_color.weight`, `color_predictor.mlp.0.weight`, ...).
 """
@@ -69,6 +70,40 @@ def vm_density(params, pts_norm, mask, density_predictor='ReLU', density_offset=
     return sigma
 
 
+def is_cp(params):
+    return 'matrices_density.0' not in params
+
+
+def cp_products(params, kind, p):
+    """SimpleTensoRF09.py:1053-1058 / :1074-1079: product of the three 1-D grid_samples, [C, N]."""
+    _, cl = _plane_line_coords(p)
+    out = F.grid_sample(params[f'vectors_{kind}.0'], cl[[0]], align_corners=True).view(-1, p.shape[0])
+    out = out * F.grid_sample(params[f'vectors_{kind}.1'], cl[[1]], align_corners=True).view(-1, p.shape[0])
+    out = out * F.grid_sample(params[f'vectors_{kind}.2'], cl[[2]], align_corners=True).view(-1, p.shape[0])
+    return out
+
+
+def cp_density(params, pts_norm, mask, density_predictor='ReLU', density_offset=-10.0):
+    """SimpleTensoRF09.py:1043-1062."""
+    sigma = torch.zeros([*pts_norm.shape[:-1], 1], dtype=pts_norm.dtype)
+    p = pts_norm[mask]
+    if p.any():
+        feat = torch.sum(cp_products(params, 'density', p), dim=0)
+        val = F.relu(feat) if density_predictor == 'ReLU' else F.softplus(feat + density_offset)
+        sigma[mask] = val[..., None]
+    return sigma
+
+
+def density(params, pts_norm, mask, density_predictor='ReLU', density_offset=-10.0):
+    fn = cp_density if is_cp(params) else vm_density
+    return fn(params, pts_norm, mask, density_predictor, density_offset)
+
+
+def color_products(params, p):
+    """The input of basis_matrix_color, [N, in_features]."""
+    return cp_products(params, 'color', p).T if is_cp(params) else vm_color_products(params, p)
+
+
 def vm_color_products(params, p):
     """SimpleTensoRF09.py:1252-1262: (plane*line)^T [N, sum(C)], the input of basis_matrix_color."""
     cp, cl = _plane_line_coords(p)
@@ -81,7 +116,7 @@ def vm_color_products(params, p):
 
 def vm_color_features(params, p):
     """SimpleTensoRF09.py:1252-1263: products -> basis matrix -> [N, 27]."""
-    return F.linear(vm_color_products(params, p), params['basis_matrix_color.weight'])
+    return F.linear(color_products(params, p), params['basis_matrix_color.weight'])
 
 
 def color_mlp(params, features, view_dirs):
@@ -105,11 +140,11 @@ def vm_color(params, pts_norm, mask, view_dirs):
 def tensor_forward(params, bbox, pts, z, rays_o, rays_d, rays_d_ndc, view_dirs, *, ndc=True,
                    alpha_volume=None, alpha_bbox=None, distance_scale=25.0, weight_threshold=1e-4,
                    white_bkgd=False, density_predictor='ReLU', density_offset=-10.0):
-    """SimpleTensoRF09.py:701-761 for one VM tensor: mask -> density -> weights -> surface mask
+    """SimpleTensoRF09.py:701-761 for one VM or CP tensor: mask -> density -> weights -> surface mask
     -> colour -> composite.  `white_bkgd` folds in the training-time coin of :746."""
     mask = validity_mask(pts, bbox, alpha_volume, alpha_bbox)
     pn = normalize(pts, bbox)
-    sigma = vm_density(params, pn, mask, density_predictor, density_offset)
+    sigma = density(params, pn, mask, density_predictor, density_offset)
     vr = composite(sigma[..., 0], None, z, rays_o, rays_d, rays_d_ndc, ndc=ndc, distance_scale=distance_scale)
     surface = vr['weights'] > weight_threshold
     rgb = vm_color(params, pn, surface, view_dirs)
@@ -148,13 +183,29 @@ def init_vm_params(resolution, comps_density, comps_color, feat_dim=27, units=12
             p[f'matrices_{kind}.{i}'] = scale * torch.randn(1, comps[i], res[a1], res[a0], generator=generator)
             p[f'vectors_{kind}.{i}'] = scale * torch.randn(1, comps[i], res[VECTOR_AXES[i]], 1, generator=generator)
 
+    _init_color_network(p, sum(comps_color), feat_dim, units, generator)
+    return p
+
+
+def _init_color_network(p, in_features, feat_dim, units, generator):
+    """basis_matrix_color (:1151 / :986) + MlpFeaturesColorPredictor (:1389-1393), torch.nn.Linear-style uniform init."""
     def lin(o, i, bias=True):
         b = 1.0 / i ** 0.5
         w = (torch.rand(o, i, generator=generator) * 2 - 1) * b
         return w, ((torch.rand(o, generator=generator) * 2 - 1) * b if bias else None)
-    p['basis_matrix_color.weight'], _ = lin(feat_dim, sum(comps_color), bias=False)
+    p['basis_matrix_color.weight'], _ = lin(feat_dim, in_features, bias=False)
     p['color_predictor.mlp.0.weight'], p['color_predictor.mlp.0.bias'] = lin(units, feat_dim + 3)
     p['color_predictor.mlp.2.weight'], p['color_predictor.mlp.2.bias'] = lin(units, units)
     p['color_predictor.mlp.4.weight'], _ = lin(3, units)
     p['color_predictor.mlp.4.bias'] = torch.zeros(3)
+
+
+def init_cp_params(resolution, comps_density, comps_color, feat_dim=27, units=128, generator=None, scale=0.1):
+    """Shapes of SimpleTensoRF09.py:979-996 (every line holds num_components[0] components) + the shared colour predictor."""
+    res = [int(r) for r in resolution]
+    p = {}
+    for kind, comps in (('density', comps_density), ('color', comps_color)):
+        for i in range(3):
+            p[f'vectors_{kind}.{i}'] = scale * torch.randn(1, comps[0], res[VECTOR_AXES[i]], 1, generator=generator)
+    _init_color_network(p, sum(comps_color), feat_dim, units, generator)
     return p

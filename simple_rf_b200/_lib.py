@@ -47,6 +47,10 @@ _SIGNATURES = {
     'srf_tensorf_march_compact': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'srf_ray_accumulate': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P]),
     'srf_vm_color_features_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    'srf_cp_density_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, c_int, _P, c_int, c_float, _P, _P, _P]),
+    'srf_cp_density_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, c_int, _P, c_int, c_float, _P, _P, _P, _P]),
+    'srf_cp_color_features_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, c_int, _P, _P, _P, c_int, _P]),
+    'srf_cp_color_features_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, c_int, _P, _P, c_int, _P, _P]),
     'srf_scatter_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     'srf_gather_rows': (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     'srf_mlp_rows_fwd': (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, _P, _P, c_int, c_int, c_int, _P]),

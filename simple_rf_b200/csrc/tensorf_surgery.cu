@@ -3,7 +3,8 @@
 //
 // Replaces (reference file:line, relative to the upstream checkout):
 //   srf_alpha_grid_occupancy   src/models/SimpleTensoRF09.py:849-859 (dense grid of world points, compute_alpha :878-897:
-//                              previous-mask test, normalise, get_volume_density, 1 - exp(-sigma * step)), :862 clamp and the
+//                              previous-mask test, normalise, get_volume_density of the VM (:1214-1239) or CP (:1043-1062) tensor,
+//                              1 - exp(-sigma * step)), :862 clamp and the
 //                              threshold of :866-867 applied BEFORE the pooling (max over a window >= t  <=>  any member >= t)
 //   srf_alpha_grid_dilate      :864-865 (3x3x3 max-pool, stride 1, -inf padding) on the 1-bit volume, :869 (the new
 //                              AlphaGridMask volume), :871-875 (per-axis projection of the occupied voxels -> new bounding box)
@@ -56,18 +57,32 @@ __global__ void __launch_bounds__(256) alpha_occupancy_kernel(const OccupancyPar
 #pragma unroll
       for (int a = 0; a < 3; ++a) pn[a] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(pt[a], -p.bb0[a]), p.bsize[a]), 2.f), -1.f);
       float feat = 0.f;
+      if (p.grid.plane[0] == nullptr) {
+        // CANDECOMP/PARAFAC tensor (:1043-1062): sum over components of the product of the three line factors
+        int l0[3], L[3]; float w0[3], w1[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const Bilerp b = plane_coords(pn, p.grid.res, i);
-        int l0, L; float w0, w1;
-        line_coords(pn, p.grid.res, i, l0, L, w0, w1);
-        float part = 0.f;
-        for (int c = 0; c < p.grid.C[i]; c += 4) {
-          const float4 pv = plane_fetch4(p.grid.plane[i], b, p.grid.C[i], c);
-          const float4 lv = line_fetch4(p.grid.line[i], l0, L, w0, w1, p.grid.C[i], c);
-          part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+        for (int i = 0; i < 3; ++i) line_coords(pn, p.grid.res, i, l0[i], L[i], w0[i], w1[i]);
+        const int C = p.grid.C[0];
+        for (int c = 0; c < C; c += 4) {
+          const float4 a = line_fetch4(p.grid.line[0], l0[0], L[0], w0[0], w1[0], C, c);
+          const float4 b = line_fetch4(p.grid.line[1], l0[1], L[1], w0[1], w1[1], C, c);
+          const float4 d = line_fetch4(p.grid.line[2], l0[2], L[2], w0[2], w1[2], C, c);
+          feat += (a.x * b.x * d.x + a.y * b.y * d.y) + (a.z * b.z * d.z + a.w * b.w * d.w);
         }
-        feat += part;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const Bilerp b = plane_coords(pn, p.grid.res, i);
+          int l0, L; float w0, w1;
+          line_coords(pn, p.grid.res, i, l0, L, w0, w1);
+          float part = 0.f;
+          for (int c = 0; c < p.grid.C[i]; c += 4) {
+            const float4 pv = plane_fetch4(p.grid.plane[i], b, p.grid.C[i], c);
+            const float4 lv = line_fetch4(p.grid.line[i], l0, L, w0, w1, p.grid.C[i], c);
+            part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+          }
+          feat += part;
+        }
       }
       if (p.softplus) { const float v = feat + p.offset; sigma = v > 20.f ? v : log1pf(expf(v)); }
       else sigma = fmaxf(feat, 0.f);
@@ -169,13 +184,16 @@ SRF_API int srf_alpha_grid_occupancy(const float* const* planes, const float* co
                                      const float* coord_z, const uint32_t* prev_bits, const int* prev_res, const float* prev_box_min,
                                      const float* prev_box_size, int softplus, float density_offset, float step_size,
                                      float threshold, uint32_t* raw_words, void* stream) {
-  SRF_REQUIRE(planes && lines && channels && resolution && box_min && box_size && coord_x && coord_y && coord_z && raw_words,
+  // planes == NULL: a CANDECOMP/PARAFAC tensor (lines only, channels[0] components in each of the three lines)
+  SRF_REQUIRE(lines && channels && resolution && box_min && box_size && coord_x && coord_y && coord_z && raw_words,
               "srf_alpha_grid_occupancy", "null pointer");
   SRF_REQUIRE(prev_bits == nullptr || (prev_res && prev_box_min && prev_box_size), "srf_alpha_grid_occupancy", "previous alpha box missing");
+  SRF_REQUIRE(planes != nullptr || (channels[1] == channels[0] && channels[2] == channels[0]), "srf_alpha_grid_occupancy",
+              "a CP tensor has the same component count in all three lines");
   OccupancyParams p{};
   for (int i = 0; i < 3; ++i) {
-    p.grid.plane[i] = planes[i]; p.grid.line[i] = lines[i]; p.grid.C[i] = channels[i]; p.grid.res[i] = resolution[i];
-    SRF_REQUIRE(planes[i] && lines[i], "srf_alpha_grid_occupancy", "null plane/line pointer");
+    p.grid.plane[i] = planes ? planes[i] : nullptr; p.grid.line[i] = lines[i]; p.grid.C[i] = channels[i]; p.grid.res[i] = resolution[i];
+    SRF_REQUIRE((planes == nullptr || planes[i]) && lines[i], "srf_alpha_grid_occupancy", "null plane/line pointer");
     SRF_REQUIRE(channels[i] > 0 && !(channels[i] & 3), "srf_alpha_grid_occupancy", "channel counts must be positive multiples of 4");
     SRF_REQUIRE(resolution[i] > 0, "srf_alpha_grid_occupancy", "empty grid");
     p.bb0[i] = box_min[i]; p.bsize[i] = box_size[i]; p.n[i] = resolution[i];

@@ -61,26 +61,30 @@ def axis_coordinates(bounding_box, resolution):
 
 @torch.no_grad()
 def rebuild_occupancy(planes, lines, geometry, *, step_size, threshold, softplus, density_offset, previous=None):
-    """-> (bool volume [Z,Y,X], new bounding box [2,3]).  planes / lines: the density parameters ([1,C,H,W] / [1,C,L,1]);
+    """-> (bool volume [Z,Y,X], new bounding box [2,3]).  planes / lines: the density parameters ([1,C,H,W] / [1,C,L,1]; planes None:
+    a CP tensor);
     geometry: dict(box [2,3] tensor, box_min, box_size, res) of the tensor; previous: AlphaGridMask.packed() or None."""
     box = geometry['box']
     dev = box.device
     res = [int(v) for v in geometry['res']]
-    cl_planes, cl_lines = T.to_channels_last(list(planes), list(lines))
+    if planes is None:                       # CANDECOMP/PARAFAC tensor: the three lines only (:1043-1062)
+        cl_planes, cl_lines = None, T.lines_channels_last(list(lines))
+    else:
+        cl_planes, cl_lines = T.to_channels_last(list(planes), list(lines))
     coords = axis_coordinates(box, res)
     c_res = T._i3(res)
     words = L.load().srf_alpha_grid_words(c_res)
     raw = torch.empty((words,), dtype=torch.int32, device=dev)
-    channels = (ctypes.c_int * 3)(*[p.shape[-1] for p in cl_planes])
+    channels = (ctypes.c_int * 3)(*[l.shape[-1] for l in cl_lines])
     if previous is None:
         p_bits = p_res = p_min = p_size = None
     else:
         p_bits, p_res, p_min, p_size = L.ptr(previous['bits']), T._i3(previous['res']), T._f3(previous['box_min']), T._f3(previous['box_size'])
     n_vox = res[0] * res[1] * res[2]
-    L.call('srf_alpha_grid_occupancy', T._ptrs(cl_planes), T._ptrs(cl_lines), channels, c_res, T._f3(geometry['box_min']),
+    L.call('srf_alpha_grid_occupancy', T._ptrs(cl_planes) if cl_planes is not None else None, T._ptrs(cl_lines), channels, c_res, T._f3(geometry['box_min']),
            T._f3(geometry['box_size']), L.ptr(coords[0]), L.ptr(coords[1]), L.ptr(coords[2]), p_bits, p_res, p_min, p_size,
            int(bool(softplus)), float(density_offset), float(step_size), float(threshold), L.ptr(raw), L.stream_handle(),
-           work=float(n_vox) * 576.0)                                 # requested texel bytes per voxel (SURVEY.md §8d)
+           work=float(n_vox) * (576.0 if cl_planes is not None else 4.0 * 6 * cl_lines[0].shape[-1]))     # requested texel bytes per voxel (SURVEY.md §8d)
     volume = torch.empty((res[2], res[1], res[0]), dtype=torch.uint8, device=dev)
     pitch = (res[0] + 31) // 32
     projection = torch.zeros((pitch + res[1] + res[2],), dtype=torch.int32, device=dev)
@@ -148,6 +152,19 @@ def crop_vm(matrices, vectors, lo, hi):
 def resample_vm(matrices, vectors, new_res):
     res = [int(v) for v in new_res]
     return map_vm_parameters(matrices, vectors, lambda m, a0, a1: resample(m, (res[a1], res[a0])), lambda v, a: resample(v, (res[a], 1)))
+
+
+def crop_lines(vectors, lo, hi):
+    """CP tensor (:1113-1124): the window of each line."""
+    lo, hi = [int(v) for v in lo], [int(v) for v in hi]
+    return torch.nn.ParameterList([torch.nn.Parameter(resample(vectors[i], (hi[a] - lo[a], 1), (lo[a], 0, hi[a] - lo[a], 1)))
+                                   for i, a in enumerate(T.VECTOR_AXES)])
+
+
+def resample_lines(vectors, new_res):
+    """CP tensor (:1101-1111)."""
+    res = [int(v) for v in new_res]
+    return torch.nn.ParameterList([torch.nn.Parameter(resample(vectors[i], (res[a], 1))) for i, a in enumerate(T.VECTOR_AXES)])
 
 
 # ---------------------------------------------------------------------------------------------------- optimiser

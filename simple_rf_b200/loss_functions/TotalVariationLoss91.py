@@ -59,6 +59,16 @@ class TotalVariationLoss:
     def get_iter_weight(self, iter_num):
         return self.lr_decay_ratio ** ((iter_num + 1) / self.lr_decay_iters)
 
+    @staticmethod
+    def get_components(tensor):
+        """:85-95: the regularised factors are the lines of a CP tensor ([1,C,L,1]: only the difference along L exists, the empty
+        one contributes 0 over max(numel, 1)) and the planes of a VM tensor."""
+        if tensor.__class__.__name__ == 'CpDecomposedTensor':
+            return tensor.vectors_density, tensor.vectors_color
+        if tensor.__class__.__name__ == 'VmDecomposedTensor':
+            return tensor.matrices_density, tensor.matrices_color
+        raise RuntimeError
+
     def compute_loss(self, input_dict: dict, output_dict: dict, model, return_loss_maps: bool = False):
         total_loss = torch.zeros((), dtype=torch.float32, device=input_dict['target_rgb'].device)
         iter_weight = self.get_iter_weight(input_dict['iter_num'])
@@ -72,13 +82,12 @@ class TotalVariationLoss:
                     if tag not in aug_cfg:
                         continue
                     tensor = matches[0][tag]
-                    if tensor.__class__.__name__ != 'VmDecomposedTensor':
-                        raise RuntimeError
+                    density, color = self.get_components(tensor)
                     wd, wc = self.loss_configs['weight_density'], self.loss_configs['weight_color']
                     if wd == wc:
-                        total_loss = total_loss + wd * tv_loss([*tensor.matrices_density, *tensor.matrices_color], iter_weight)
+                        total_loss = total_loss + wd * tv_loss([*density, *color], iter_weight)
                     else:
-                        total_loss = total_loss + wd * tv_loss(tensor.matrices_density, iter_weight) + wc * tv_loss(tensor.matrices_color, iter_weight)
+                        total_loss = total_loss + wd * tv_loss(density, iter_weight) + wc * tv_loss(color, iter_weight)
         loss_dict = {'loss_value': total_loss}
         if return_loss_maps:
             loss_dict['loss_maps'] = {}

@@ -56,7 +56,7 @@ class SimpleTensoRF(torch.nn.Module):
     def build_nerf(self):
         mc = self.configs['model']
         if self.coarse_model_needed:
-            self.coarse_model = VmDecomposedTensor('coarse_model', self.configs, mc['coarse_model'], self.model_configs)
+            self.coarse_model = get_tensor_model('coarse_model', self.configs, mc['coarse_model'], self.model_configs)
         self.intrinsics_learner = IntrinsicsLearner(numpy.array(self.model_configs['intrinsics']),
                                                     learn_focal=mc['learn_camera_focal_length'])
         self.extrinsics_learner = ExtrinsicsLearner(numpy.array(self.model_configs['extrinsics']),
@@ -67,8 +67,8 @@ class SimpleTensoRF(torch.nn.Module):
                 nn_dict = ModuleDict()
                 entry = {'name': aug['name'], 'coarse_model': None, 'fine_model': None}
                 if 'coarse_model' in aug:
-                    entry['coarse_model'] = VmDecomposedTensor(f"{aug['name']}_coarse_model", self.configs, aug['coarse_model'],
-                                                               self.model_configs)
+                    entry['coarse_model'] = get_tensor_model(f"{aug['name']}_coarse_model", self.configs, aug['coarse_model'],
+                                                             self.model_configs)
                     nn_dict['coarse_model'] = entry['coarse_model']
                 if 'fine_model' in aug:
                     raise NotImplementedError
@@ -193,7 +193,7 @@ class SimpleTensoRF(torch.nn.Module):
             return self._render_rays_world(out, pixel_id, input_dict, S, perturb, retraw=retraw, mode=mode)
         ladder = coarse_ladder_on(dev, S, self.model_configs['near_ndc'], self.model_configs['far_ndc'], mc['lindisp'])
         # test time without per-sample outputs: the depths are ONE ladder for all rays -> fused march, z[R,S] never materialised
-        if not self.training and not retraw and not torch.is_grad_enabled() and mc.get('fused_eval', True):
+        if not self.training and not retraw and not torch.is_grad_enabled() and mc.get('fused_eval', True) and main.has_fused_march:
             rays = dict(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=o_ndc, rays_d_ndc=d_ndc, view_dirs=view_dirs, z=None, ladder=ladder)
             for k, v in main(rays, False, white_bkgd=mc['white_bkgd']).items():
                 out[f'{k}_coarse'] = v
@@ -310,20 +310,24 @@ class MlpFeaturesColorPredictor(torch.nn.Module):
 
 class _VmColor(torch.autograd.Function):
     """The appearance branch on the compacted surface samples, forward and backward hand-written:
-    VM gather (srf_vm_color_features_fwd) -> basis o colour MLP on the tensor cores (srf_mlp_rows_fwd, activations saved
-    as tile images) | data-gradient chain + weight gradients on the tensor cores (srf_nerf_mlp_dgrad / _wgrad) -> scatter
-    of d loss / d products into the planes / lines (srf_vm_color_features_bwd).  What autograd derives for
-    SimpleTensoRF09.py:1241-1272 + :1411-1421."""
+    gather (srf_vm_color_features_fwd, or srf_cp_color_features_fwd when n_planes == 0: a CP tensor's three lines) -> basis o
+    colour MLP on the tensor cores (srf_mlp_rows_fwd, activations saved as tile images) | data-gradient chain + weight gradients
+    on the tensor cores (srf_nerf_mlp_dgrad / _wgrad) -> scatter of d loss / d products into the planes / lines.  What autograd
+    derives for SimpleTensoRF09.py:1241-1272 (VM) / :1064-1089 (CP) + :1411-1421."""
 
     @staticmethod
     def forward(ctx, predictor, geom, comp, view_dirs, n_planes, basis, *params):
-        planes, lines, mlp = params[:n_planes], params[n_planes:2 * n_planes], params[2 * n_planes:]
         # the surface count stays on the device (no read-back: a synchronisation here drains the launch queue twice per
         # iteration); every buffer is sized for the worst case comp.total and every kernel stops at the device-side count
-        rows, tables = T.vm_color_rows(geom, comp, view_dirs, list(planes), list(lines))
+        if n_planes == 0:
+            mlp = params[3:]
+            rows, tables = T.cp_color_rows(geom, comp, view_dirs, list(params[:3]))
+        else:
+            planes, lines, mlp = params[:n_planes], params[n_planes:2 * n_planes], params[2 * n_planes:]
+            rows, tables = T.vm_color_rows(geom, comp, view_dirs, list(planes), list(lines))
         packed = predictor.packed(basis)
         rgb, acts = packed.forward(rows, comp.count, rows.shape[0], save=True)
-        ctx.packed, ctx.flat, ctx.geom, ctx.comp, ctx.tables = packed, packed.flat, geom, comp, tables
+        ctx.packed, ctx.flat, ctx.geom, ctx.comp, ctx.tables, ctx.n_planes = packed, packed.flat, geom, comp, tables, n_planes
         ctx.save_for_backward(rgb, acts, basis, mlp[0])
         return rgb
 
@@ -332,14 +336,30 @@ class _VmColor(torch.autograd.Function):
         rgb, acts, basis, w0 = ctx.saved_tensors
         packed = ctx.packed
         g_flat, g_rows = packed.backward(acts, rgb, g_rgb, rgb.shape[0], flat=ctx.flat, count=ctx.comp.count)
-        gp, gl = T.vm_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
+        if ctx.n_planes == 0:
+            g_tensor = T.cp_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
+        else:
+            gp, gl = T.vm_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
+            g_tensor = [*gp, *gl]
         g_w0, g_basis = packed.split_first_layer_grad(g_flat, w0.detach().float(), basis.detach().float())
         g_mlp = [g_w0] + [packed.grad_of(g_flat, nm) for nm in packed.names[1:]]
-        return (None, None, None, None, None, g_basis, *gp, *gl, *g_mlp)
+        return (None, None, None, None, None, g_basis, *g_tensor, *g_mlp)
 
 
-class VmDecomposedTensor(torch.nn.Module):
-    """SimpleTensoRF09.py:582-961 (LowRankTensor) + :1126-1320 (VmDecomposedTensor)."""
+def get_tensor_model(name, configs, tensor_configs, model_configs):
+    """SimpleTensoRF09.py:535-544."""
+    kind = tensor_configs['decomposition_type']
+    if kind == 'VectorMatrix':
+        return VmDecomposedTensor(name, configs, tensor_configs, model_configs)
+    if kind == 'CandecompParafac':
+        return CpDecomposedTensor(name, configs, tensor_configs, model_configs)
+    raise RuntimeError(f'Unknown tensor decomposition: {kind}')
+
+
+class LowRankTensor(torch.nn.Module):
+    """SimpleTensoRF09.py:582-961: what the two decompositions share (geometry bookkeeping, the forward orchestration, the grid
+    surgery schedule, the colour predictor).  Subclasses provide the factor parameters and their gathers."""
+    has_fused_march = False
 
     def __init__(self, name, configs, tensor_configs, model_configs):
         super().__init__()
@@ -349,8 +369,6 @@ class VmDecomposedTensor(torch.nn.Module):
         self.model_configs = model_configs
         self.ndc = configs['data_loader']['ndc']
         self.predict_visibility = tensor_configs['predict_visibility']
-        if tensor_configs['decomposition_type'] != 'VectorMatrix':
-            raise NotImplementedError('CandecompParafac is never selected by a shipped config (SURVEY.md App. C9)')
         for buf, val in (('bounding_box', torch.zeros(2, 3)), ('resolution', torch.zeros(3)), ('num_samples', torch.tensor(0)),
                          ('bounding_box_size', torch.zeros(3)), ('voxel_length', torch.zeros(3)), ('step_size', torch.tensor(0))):
             self.register_buffer(buf, val)
@@ -361,8 +379,7 @@ class VmDecomposedTensor(torch.nn.Module):
         self.optimizers = None
         self.update_tensor_params(self.compute_resolution_in_voxels(tensor_configs['num_voxels_initial'], bbox), bbox)
         tc = tensor_configs
-        self.matrices_density, self.vectors_density = self.create_decomposed_tensor(tc['num_components_density'], self.resolution, 0.1)
-        self.matrices_color, self.vectors_color = self.create_decomposed_tensor(tc['num_components_color'], self.resolution, 0.1)
+        self.build_tensor()
         self.basis_matrix_color = torch.nn.Linear(sum(tc['num_components_color']), tc['features_dimension_color'], bias=False)
         if tc['density_predictor'] not in ('ReLU', 'SoftPlus'):
             raise NotImplementedError
@@ -371,6 +388,15 @@ class VmDecomposedTensor(torch.nn.Module):
             raise NotImplementedError
         self.color_predictor = MlpFeaturesColorPredictor(tc, tc['features_dimension_color'], tc['num_units_color_predictor'])
         self._register_load_state_dict_pre_hook(self._load_hook)
+
+    def get_trainable_parameters(self, optimizer_configs):
+        tensor_params, network_params = torch.nn.ParameterList(), torch.nn.ParameterList()
+        for group in self.tensor_parameter_lists():
+            tensor_params.extend(group)
+        network_params.extend(self.basis_matrix_color.parameters())
+        network_params.extend(self.color_predictor.parameters())
+        return [{'name': f'{self.name}_tensor_params', 'params': tensor_params, 'lr': optimizer_configs['lr_initial_tensor']},
+                {'name': f'{self.name}_network_params', 'params': network_params, 'lr': optimizer_configs['lr_initial_network']}]
 
     # ---------------------------------------------------------------- geometry bookkeeping (:625-665)
     @staticmethod
@@ -391,25 +417,6 @@ class VmDecomposedTensor(torch.nn.Module):
         self.step_size = torch.mean(self.voxel_length) * self.tensor_configs['num_voxels_per_sample']
         self.num_samples = self.compute_num_samples(self.resolution, self.tensor_configs['num_voxels_per_sample'])
         self._host_geom = None          # freed buffers may be re-allocated at the same address: do not trust the pointer key here
-
-    def create_decomposed_tensor(self, comps, resolution, scale):
-        mats, vecs = [], []
-        for i in range(3):
-            a0, a1 = self.matrix_axes[i]
-            mats.append(torch.nn.Parameter(scale * torch.randn((1, comps[i], resolution[a1], resolution[a0]))))
-            vecs.append(torch.nn.Parameter(scale * torch.randn((1, comps[i], resolution[self.vector_axes[i]], 1))))
-        return torch.nn.ParameterList(mats), torch.nn.ParameterList(vecs)
-
-    def get_trainable_parameters(self, optimizer_configs):
-        tensor_params, network_params = torch.nn.ParameterList(), torch.nn.ParameterList()
-        tensor_params.extend(self.vectors_density)
-        tensor_params.extend(self.matrices_density)
-        tensor_params.extend(self.vectors_color)
-        tensor_params.extend(self.matrices_color)
-        network_params.extend(self.basis_matrix_color.parameters())
-        network_params.extend(self.color_predictor.parameters())
-        return [{'name': f'{self.name}_tensor_params', 'params': tensor_params, 'lr': optimizer_configs['lr_initial_tensor']},
-                {'name': f'{self.name}_network_params', 'params': network_params, 'lr': optimizer_configs['lr_initial_network']}]
 
     def _load_hook(self, state, prefix, *args, **kwargs):
         """:946-961 + :1196-1212: rebuild the alpha mask and resize planes/lines before loading."""
@@ -435,22 +442,6 @@ class VmDecomposedTensor(torch.nn.Module):
         hg = self.host_geometry()
         return T.VmGeometry(rays_o_s, rays_d_s, z, hg['box_min'], hg['box_size'], hg['res'])
 
-    def forward_fused_eval(self, rays: dict, white_bkgd=False):
-        """LowRankTensor.forward (:701-761) at test time through the fused march (csrc/tensorf_march.cu): per-ray maps and the
-        surface list in one pass over the shared depth ladder, colour on the surface samples, per-ray accumulation."""
-        tc = self.tensor_configs
-        hg = self.host_geometry()
-        alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
-        m = T.march(rays['rays_o_ndc'], rays['rays_d_ndc'], rays['rays_o'], rays['rays_d'], rays['ladder'], hg['box'], hg['box_size'], alpha,
-                    list(self.matrices_density), list(self.vectors_density), hg['res'], softplus=self.density_predictor == 'SoftPlus',
-                    offset=tc['density_offset'], distance_scale=tc['distance_scale'], threshold=tc['ray_marching_weight_threshold'])
-        geom = T.VmGeometry(rays['rays_o_ndc'], rays['rays_d_ndc'], rays['ladder'], hg['box_min'], hg['box_size'], hg['res'])
-        rows, _ = T.vm_color_rows(geom, m.surface, rays['view_dirs'], list(self.matrices_color), list(self.vectors_color))
-        rgb_rows = self.color_predictor.packed(self.basis_matrix_color.weight).forward(rows, m.surface.count, rows.shape[0])
-        out = dict(m.maps)
-        out['rgb'] = T.ray_accumulate(rgb_rows, m, white_bkgd)
-        return out
-
     def forward(self, rays: dict, retraw: bool, white_bkgd=False):
         tc = self.tensor_configs
         if rays.get('z') is None:
@@ -462,19 +453,19 @@ class VmDecomposedTensor(torch.nn.Module):
         alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
         valid = T.validity_compact(so, sd, z, self.host_geometry()['box'], alpha)
         geom = self._geometry(so, sd, z)
-        sigma = T.vm_density(geom, valid, list(self.matrices_density), list(self.vectors_density),
-                             softplus=self.density_predictor == 'SoftPlus', offset=tc['density_offset'])
+        sigma = self.density(geom, valid)
         with torch.no_grad():                                               # weights only decide where colour is read (:726)
             w0 = ops.composite(sigma.detach()[..., 0], None, z, rays['rays_o'], rays['rays_d'], sd if ndc else None, ndc=ndc,
                                distance_scale=tc['distance_scale'], per_sample=False)['weights']
         surface = T.threshold_compact(w0, tc['ray_marching_weight_threshold'])
         cp = self.color_predictor
         basis = self.basis_matrix_color.weight
-        color_params = [*self.matrices_color, *self.vectors_color, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)]]
+        factors = self.color_factors()                                      # planes then lines (VM) / the three lines (CP)
+        color_params = [*factors, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)]]
         if torch.is_grad_enabled() and any(p.requires_grad for p in [basis] + color_params):
-            rgb_rows = _VmColor.apply(cp, geom, surface, rays['view_dirs'], len(self.matrices_color), basis, *color_params)
+            rgb_rows = _VmColor.apply(cp, geom, surface, rays['view_dirs'], self.num_color_planes, basis, *color_params)
         else:
-            rows, _ = T.vm_color_rows(geom, surface, rays['view_dirs'], list(self.matrices_color), list(self.vectors_color))
+            rows, _ = self.color_rows(geom, surface, rays['view_dirs'])
             rgb_rows = cp.packed(basis).forward(rows, surface.count, rows.shape[0])
         rgb = T._ScatterRows.apply(surface, rgb_rows, R * S).view(R, S, 3)
         device_coin = self.training and not white_bkgd and self.configs['model'].get('rng_mode', 'reference') != 'reference'
@@ -509,8 +500,9 @@ class VmDecomposedTensor(torch.nn.Module):
     def rebuild_alpha_mask(self):
         """New occupancy mask on the current grid (:849-876) -> bounding box of the occupied voxels."""
         hg = self.host_geometry()
+        planes, lines = self.density_factors()
         volume, occupied_box = GS.rebuild_occupancy(
-            self.matrices_density, self.vectors_density,
+            planes, lines,
             {'box': self.bounding_box, 'box_min': hg['box_min'], 'box_size': hg['box_size'], 'res': hg['res']},
             step_size=float(self.step_size), threshold=self.tensor_configs['alpha_mask_threshold'],
             softplus=self.density_predictor == 'SoftPlus', density_offset=self.tensor_configs['density_offset'],
@@ -519,19 +511,14 @@ class VmDecomposedTensor(torch.nn.Module):
         return occupied_box
 
     def crop_to(self, occupied_box):
-        """Cut the tensor down to the voxel window around `occupied_box` (:899-914, :1299-1320)."""
+        """Cut the tensor down to the voxel window around `occupied_box` (:899-914, :1299-1320 / :1113-1124)."""
         lo, hi, box = GS.crop_window(self.bounding_box, self.voxel_length, self.resolution, occupied_box, self.alpha_mask.resolution)
         dev = self.bounding_box.device
-        self.matrices_density, self.vectors_density = GS.crop_vm(self.matrices_density, self.vectors_density, lo, hi)
-        self.matrices_color, self.vectors_color = GS.crop_vm(self.matrices_color, self.vectors_color, lo, hi)
+        self._crop_parameters(lo, hi)
         self.update_tensor_params((hi - lo).to(dev), box.to(dev))
 
-    def _resize_parameters(self, resolution):
-        self.matrices_density, self.vectors_density = GS.resample_vm(self.matrices_density, self.vectors_density, resolution)
-        self.matrices_color, self.vectors_color = GS.resample_vm(self.matrices_color, self.vectors_color, resolution)
-
     def resample_to(self, resolution):
-        """Bilinear resampling of every plane / line to `resolution` voxels (:832-835, :1277-1297)."""
+        """Bilinear resampling of every plane / line to `resolution` voxels (:832-835, :1277-1297 / :1094-1111)."""
         self.update_tensor_params(resolution, self.bounding_box)
         self._resize_parameters(self.resolution)
 
@@ -539,3 +526,104 @@ class VmDecomposedTensor(torch.nn.Module):
         """The trainer's optimiser must now hold the new Parameter objects (:916-944)."""
         opt_cfg = next(c for c in self.configs['optimizers'] if c['name'] == 'optimizer_main')
         GS.regroup_optimizer(self.optimizers['optimizer_nerf'], self.get_trainable_parameters(opt_cfg))
+
+
+class VmDecomposedTensor(LowRankTensor):
+    """SimpleTensoRF09.py:1126-1320: three (plane, line) pairs per quantity."""
+    has_fused_march = True
+    num_color_planes = 3
+
+    def build_tensor(self):
+        tc = self.tensor_configs
+        self.matrices_density, self.vectors_density = self.create_decomposed_tensor(tc['num_components_density'], self.resolution, 0.1)
+        self.matrices_color, self.vectors_color = self.create_decomposed_tensor(tc['num_components_color'], self.resolution, 0.1)
+
+    def create_decomposed_tensor(self, comps, resolution, scale):
+        mats, vecs = [], []
+        for i in range(3):
+            a0, a1 = self.matrix_axes[i]
+            mats.append(torch.nn.Parameter(scale * torch.randn((1, comps[i], resolution[a1], resolution[a0]))))
+            vecs.append(torch.nn.Parameter(scale * torch.randn((1, comps[i], resolution[self.vector_axes[i]], 1))))
+        return torch.nn.ParameterList(mats), torch.nn.ParameterList(vecs)
+
+    def tensor_parameter_lists(self):                       # group order of :1170-1173
+        return (self.vectors_density, self.matrices_density, self.vectors_color, self.matrices_color)
+
+    def density(self, geom, comp):
+        return T.vm_density(geom, comp, list(self.matrices_density), list(self.vectors_density),
+                            softplus=self.density_predictor == 'SoftPlus', offset=self.tensor_configs['density_offset'])
+
+    def density_factors(self):
+        return self.matrices_density, self.vectors_density
+
+    def color_factors(self):
+        return [*self.matrices_color, *self.vectors_color]
+
+    def color_rows(self, geom, comp, view_dirs):
+        return T.vm_color_rows(geom, comp, view_dirs, list(self.matrices_color), list(self.vectors_color))
+
+    def forward_fused_eval(self, rays: dict, white_bkgd=False):
+        """LowRankTensor.forward (:701-761) at test time through the fused march (csrc/tensorf_march.cu): per-ray maps and the
+        surface list in one pass over the shared depth ladder, colour on the surface samples, per-ray accumulation."""
+        tc = self.tensor_configs
+        hg = self.host_geometry()
+        alpha = self.alpha_mask.packed() if self.alpha_mask is not None else None
+        m = T.march(rays['rays_o_ndc'], rays['rays_d_ndc'], rays['rays_o'], rays['rays_d'], rays['ladder'], hg['box'], hg['box_size'], alpha,
+                    list(self.matrices_density), list(self.vectors_density), hg['res'], softplus=self.density_predictor == 'SoftPlus',
+                    offset=tc['density_offset'], distance_scale=tc['distance_scale'], threshold=tc['ray_marching_weight_threshold'])
+        geom = T.VmGeometry(rays['rays_o_ndc'], rays['rays_d_ndc'], rays['ladder'], hg['box_min'], hg['box_size'], hg['res'])
+        rows, _ = T.vm_color_rows(geom, m.surface, rays['view_dirs'], list(self.matrices_color), list(self.vectors_color))
+        rgb_rows = self.color_predictor.packed(self.basis_matrix_color.weight).forward(rows, m.surface.count, rows.shape[0])
+        out = dict(m.maps)
+        out['rgb'] = T.ray_accumulate(rgb_rows, m, white_bkgd)
+        return out
+
+    def _crop_parameters(self, lo, hi):
+        self.matrices_density, self.vectors_density = GS.crop_vm(self.matrices_density, self.vectors_density, lo, hi)
+        self.matrices_color, self.vectors_color = GS.crop_vm(self.matrices_color, self.vectors_color, lo, hi)
+
+    def _resize_parameters(self, resolution):
+        self.matrices_density, self.vectors_density = GS.resample_vm(self.matrices_density, self.vectors_density, resolution)
+        self.matrices_color, self.vectors_color = GS.resample_vm(self.matrices_color, self.vectors_color, resolution)
+
+
+class CpDecomposedTensor(LowRankTensor):
+    """SimpleTensoRF09.py:964-1124 (`decomposition_type = "CandecompParafac"`; selected by no shipped configuration): three line
+    factors per component, `num_components[0]` components in every line (:992), on the kernels of csrc/tensorf_cp.cu.  Test time
+    takes the per-sample path (there is no fused march for this decomposition)."""
+    num_color_planes = 0
+
+    def build_tensor(self):
+        tc = self.tensor_configs
+        if tc['num_components_density'][0] % 4 or tc['num_components_color'][0] % 4:
+            raise NotImplementedError('CP component counts must be multiples of 4 (16-byte texel vectors)')
+        self.vectors_density = self.create_decomposed_tensor(tc['num_components_density'], self.resolution, 0.1)
+        self.vectors_color = self.create_decomposed_tensor(tc['num_components_color'], self.resolution, 0.1)
+
+    def create_decomposed_tensor(self, comps, resolution, scale):
+        return torch.nn.ParameterList([torch.nn.Parameter(scale * torch.randn((1, comps[0], resolution[self.vector_axes[i]], 1)))
+                                       for i in range(3)])
+
+    def tensor_parameter_lists(self):                       # :1002-1003
+        return (self.vectors_density, self.vectors_color)
+
+    def density(self, geom, comp):
+        return T.cp_density(geom, comp, list(self.vectors_density), softplus=self.density_predictor == 'SoftPlus',
+                            offset=self.tensor_configs['density_offset'])
+
+    def density_factors(self):
+        return None, self.vectors_density
+
+    def color_factors(self):
+        return list(self.vectors_color)
+
+    def color_rows(self, geom, comp, view_dirs):
+        return T.cp_color_rows(geom, comp, view_dirs, list(self.vectors_color))
+
+    def _crop_parameters(self, lo, hi):
+        self.vectors_density = GS.crop_lines(self.vectors_density, lo, hi)
+        self.vectors_color = GS.crop_lines(self.vectors_color, lo, hi)
+
+    def _resize_parameters(self, resolution):
+        self.vectors_density = GS.resample_lines(self.vectors_density, resolution)
+        self.vectors_color = GS.resample_lines(self.vectors_color, resolution)

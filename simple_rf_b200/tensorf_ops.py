@@ -160,8 +160,9 @@ class _VmDensity(torch.autograd.Function):
         planes_cl, lines_cl, chans = ctx.tables
         gp = [torch.zeros_like(p) for p in planes_cl]
         gl = [torch.zeros_like(l) for l in lines_cl]
+        g = L.f32c(g_sigma)                      # bound to a local: a converted copy must outlive the launch call
         L.call('srf_vm_density_bwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res, softplus, offset,
-               L.ptr(L.f32c(g_sigma)), L.ptr(feat), _ptrs(gp), _ptrs(gl), L.stream_handle(),
+               L.ptr(g), L.ptr(feat), _ptrs(gp), _ptrs(gl), L.stream_handle(),
                work=(comp.count, 2 * 4.0 * 6 * sum(p.shape[2] for p in planes_cl)))   # texel reads + the same again as atomic adds
         grads = [g.permute(2, 0, 1)[None].contiguous() for g in gp] + [g.permute(1, 0)[None, :, :, None].contiguous() for g in gl]
         return (None, None, None, None, None, *grads)
@@ -185,8 +186,9 @@ def vm_color_rows(geom, comp, view_dirs, planes, lines, max_rows=None):
     chans = _i3([p.shape[1] for p in planes])
     pitch = color_row_pitch(sum(p.shape[1] for p in planes))
     rows = torch.empty((max(comp.total if max_rows is None else max_rows, 1), pitch), dtype=torch.bfloat16, device=geom.z.device)
+    vd = L.f32c(view_dirs)
     L.call('srf_vm_color_features_fwd', *geom.args(comp), _ptrs(planes_cl), _ptrs(lines_cl), chans, geom.res,
-           L.ptr(L.f32c(view_dirs)), L.ptr(rows), pitch, int(geom.z_is_ladder), L.stream_handle(),
+           L.ptr(vd), L.ptr(rows), pitch, int(geom.z_is_ladder), L.stream_handle(),
            work=(comp.count, 4.0 * 6 * sum(p.shape[1] for p in planes)))
     return rows, (planes_cl, lines_cl, chans)
 
@@ -201,6 +203,75 @@ def vm_color_rows_backward(geom, comp, tables, g_rows):
            L.ptr(g), g.shape[1], _ptrs(gp), _ptrs(gl), L.stream_handle(),
            work=(comp.count, 2 * 4.0 * 6 * sum(p.shape[2] for p in planes_cl)))
     return ([x.permute(2, 0, 1)[None].contiguous() for x in gp], [x.permute(1, 0)[None, :, :, None].contiguous() for x in gl])
+
+
+# ---------------------------------------------------------------------------------------------------- CANDECOMP/PARAFAC tensor
+def lines_channels_last(lines):
+    """[1,C,L,1] -> [L,C] derived caches of a CP tensor's three lines (to_channels_last without planes)."""
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in lines)
+    slot = ('cp', lines[0].device, lines[0].shape[1], id(lines[0]))
+    hit = _CL_CACHE.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = [l.detach()[0, :, :, 0].permute(1, 0).contiguous() for l in lines]
+    if len(_CL_CACHE) > 64:
+        _CL_CACHE.clear()
+    _CL_CACHE[slot] = (key, val)
+    return val
+
+
+class _CpDensity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geom, comp, softplus, offset, *lines):
+        lines_cl = lines_channels_last(lines)
+        C = lines[0].shape[1]
+        R = geom.z.shape[0]
+        sigma = torch.zeros((R, geom.S, 1), dtype=torch.float32, device=geom.z.device)
+        feat = torch.empty((max(comp.total, 1),), dtype=torch.float32, device=geom.z.device)
+        L.call('srf_cp_density_fwd', *geom.args(comp), _ptrs(lines_cl), C, geom.res, int(softplus), float(offset), L.ptr(sigma),
+               L.ptr(feat), L.stream_handle(), work=(comp.count, 4.0 * 6 * C))           # requested bytes: 6 line texels x C floats
+        ctx.geom, ctx.comp, ctx.cfg, ctx.tables = geom, comp, (int(softplus), float(offset), C), lines_cl
+        ctx.save_for_backward(feat)
+        return sigma
+
+    @staticmethod
+    def backward(ctx, g_sigma):
+        (feat,) = ctx.saved_tensors
+        geom, comp, lines_cl = ctx.geom, ctx.comp, ctx.tables
+        softplus, offset, C = ctx.cfg
+        gl = [torch.zeros_like(l) for l in lines_cl]
+        g = L.f32c(g_sigma)
+        L.call('srf_cp_density_bwd', *geom.args(comp), _ptrs(lines_cl), C, geom.res, softplus, offset, L.ptr(g), L.ptr(feat), _ptrs(gl),
+               L.stream_handle(), work=(comp.count, 2 * 4.0 * 6 * C))
+        return (None, None, None, None, *[x.permute(1, 0)[None, :, :, None].contiguous() for x in gl])
+
+
+def cp_density(geom, comp, lines, softplus=False, offset=0.0):
+    """sigma [R,S,1] (zeros where the mask is false) of a CP tensor, differentiable w.r.t. the three lines [1,C,L,1]."""
+    return _CpDensity.apply(geom, comp, softplus, offset, *lines)
+
+
+def cp_color_rows(geom, comp, view_dirs, lines, max_rows=None):
+    """rows [total, pitch] bf16 = [line products (C) | view_dirs (3) | 0] of a CP tensor (the A operand of the colour MLP) + the
+    channels-last tables for cp_color_rows_backward."""
+    lines_cl = lines_channels_last(lines)
+    C = lines[0].shape[1]
+    pitch = color_row_pitch(C)
+    rows = torch.empty((max(comp.total if max_rows is None else max_rows, 1), pitch), dtype=torch.bfloat16, device=geom.z.device)
+    vd = L.f32c(view_dirs)
+    L.call('srf_cp_color_features_fwd', *geom.args(comp), _ptrs(lines_cl), C, geom.res, L.ptr(vd), L.ptr(rows), pitch, L.stream_handle(),
+           work=(comp.count, 4.0 * 6 * C))
+    return rows, (lines_cl, C)
+
+
+def cp_color_rows_backward(geom, comp, tables, g_rows):
+    """g_rows [>= count, >= C] fp32 -> gradients of the three lines ([1,C,L,1])."""
+    lines_cl, C = tables
+    gl = [torch.zeros_like(l) for l in lines_cl]
+    g = L.f32c(g_rows)
+    L.call('srf_cp_color_features_bwd', *geom.args(comp), _ptrs(lines_cl), C, geom.res, L.ptr(g), g.shape[1], _ptrs(gl), L.stream_handle(),
+           work=(comp.count, 2 * 4.0 * 6 * C))
+    return [x.permute(1, 0)[None, :, :, None].contiguous() for x in gl]
 
 
 class Marched:
@@ -253,21 +324,24 @@ def ray_accumulate(rgb_rows, marched, white_bkgd):
     """rgb_map [R,3] = sum of weight * colour over every ray's surface samples (+ 1 - acc on a white background)."""
     R = marched.ray_count.shape[0]
     rgb_map = torch.empty((R, 3), dtype=torch.float32, device=rgb_rows.device)
-    L.call('srf_ray_accumulate', L.ptr(L.f32c(rgb_rows)), L.ptr(marched.weights), L.ptr(marched.ray_offset), L.ptr(marched.ray_count),
+    rgb_rows = L.f32c(rgb_rows)
+    L.call('srf_ray_accumulate', L.ptr(rgb_rows), L.ptr(marched.weights), L.ptr(marched.ray_offset), L.ptr(marched.ray_count),
            L.ptr(marched.maps['acc']), R, int(bool(white_bkgd)), L.ptr(rgb_map), L.stream_handle())
     return rgb_map
 
 
 def scatter_rows(comp, src, width, total):
     dst = torch.zeros((total, width), dtype=torch.float32, device=src.device)
-    L.call('srf_scatter_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(L.f32c(src)), width, L.ptr(dst), L.stream_handle())
+    src = L.f32c(src)
+    L.call('srf_scatter_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(src), width, L.ptr(dst), L.stream_handle())
     return dst
 
 
 def gather_rows(comp, src, width, nrows=None):
     """nrows: rows of the result when the caller knows count <= nrows (default: the worst case comp.total)."""
     dst = torch.zeros((max(comp.total if nrows is None else nrows, 1), width), dtype=torch.float32, device=src.device)
-    L.call('srf_gather_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(L.f32c(src)), width, L.ptr(dst), L.stream_handle())
+    src = L.f32c(src)
+    L.call('srf_gather_rows', L.ptr(comp.idx), L.ptr(comp.count), comp.total, L.ptr(src), width, L.ptr(dst), L.stream_handle())
     return dst
 
 

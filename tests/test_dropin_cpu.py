@@ -49,12 +49,16 @@ def test_nerf_dropin_refuses_cpu(golden_configs):
 
 
 @pytest.mark.needs_reference
-def test_tensorf_dropin_resolves_and_matches_state_dict():
+@pytest.mark.parametrize('decomposition', ['VectorMatrix', 'CandecompParafac'])
+def test_tensorf_dropin_resolves_and_matches_state_dict(decomposition):
     from oracle import reference_harness as H
     from simple_rf_b200 import dropin
     get_model, _ = H.import_reference()
     dropin.install()
     configs, model_configs = H.load_configs(212, '00000')
+    if decomposition == 'CandecompParafac':                    # SimpleTensoRF09.py:537-539; one component count per tensor (:992, :986)
+        for cfg in (configs['model']['coarse_model'], configs['model']['augmentations'][0]['coarse_model']):
+            cfg.update(decomposition_type=decomposition, num_components_density=[24], num_components_color=[48])
     configs['model']['coarse_model']['num_voxels_initial'] = 30 ** 3
     configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 16 ** 3
     models = []
@@ -74,6 +78,7 @@ def test_tensorf_dropin_resolves_and_matches_state_dict():
     assert [g['name'] for g in g_ref] == [g['name'] for g in g_mine]
     assert [[tuple(p.shape) for p in g['params']] for g in g_ref] == [[tuple(p.shape) for p in g['params']] for g in g_mine]
     assert int(mine.coarse_model.num_samples) == int(ref.coarse_model.num_samples)
+    assert type(mine.coarse_model).__name__ == type(ref.coarse_model).__name__          # TotalVariationLoss04.py:87 dispatches on it
 
 
 def test_callers_harness_drives_unmodified_trainer_and_tester_on_cpu():

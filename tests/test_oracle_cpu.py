@@ -118,6 +118,26 @@ def test_tensorf_world_space_pipeline_matches_reference_golden(golden, golden_co
             assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
 
 
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_tensorf_cp_pipeline_matches_reference_golden(golden, golden_configs, mode):
+    """`decomposition_type = "CandecompParafac"` (SimpleTensoRF09.py:964-1124): three line factors per component."""
+    g = golden(f'tensorf_cp_{mode}')
+    configs, model_configs = golden_configs('tensorf_cp')
+    assert configs['model']['coarse_model']['decomposition_type'] == 'CandecompParafac'
+    sets = FX.tensorf_sets(configs, seed=int(g['param_seed']), with_alpha=bool(g['with_alpha']))
+    assert TF.is_cp(sets['coarse_model']['params'])
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = P.tensorf_render_chunk(sets, configs, model_configs, g['pixel_id'], training=(mode == 'train'))
+    assert torch.equal(out['z_vals_coarse'], g['z_vals_coarse'])
+    assert torch.equal(out['validity_mask_coarse'], g['validity_mask_coarse'])
+    assert torch.equal(out['surface_mask_coarse'], g['surface_mask_coarse'])
+    assert 0.2 < g['surface_mask_coarse'].float().mean() < 0.8                       # the fixture exercises the colour branch
+    for k in g:
+        if k in out and g[k].dtype == torch.float32:
+            assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
+
+
 @pytest.mark.parametrize('n', [1, 3, 5, 7, 8, 35, 62, 64, 190, 462, 1081, 2312])
 def test_aten_row_sum_order(n):
     torch.manual_seed(n)

@@ -30,6 +30,23 @@ def test_oracle_reproduces_reference_surgery(golden, golden_configs):
     assert 0.01 < float(g['occupied1']) < 0.5 and float(g['occupied2']) > 0       # the fixture is neither empty nor full
 
 
+def test_oracle_reproduces_reference_surgery_cp(golden, golden_configs):
+    """The same schedule on a CANDECOMP/PARAFAC tensor (lines only: SimpleTensoRF09.py:1094-1124)."""
+    g = golden('tensorf_cp_surgery')
+    configs, _ = golden_configs('tensorf_cp_surgery')
+    o = run_oracle_schedule(configs)
+    assert TF.is_cp(o['params0'])
+    assert torch.equal(_bits(o['vol1']), g['volume1_bits']) and list(o['vol1'].shape) == g['volume1_shape'].tolist()
+    assert torch.equal(o['box1'], g['box1'])
+    assert torch.equal(o['lo'], g['window_lo']) and torch.equal(o['hi'], g['window_hi'])
+    assert torch.equal(o['geo1']['resolution'], g['shrink_resolution']) and torch.equal(o['geo1']['bbox'], g['shrink_bbox'])
+    assert torch.equal(o['geo2']['resolution'], g['upsample_resolution']) and o['geo2']['num_samples'] == int(g['upsample_num_samples'])
+    assert torch.equal(o['params2']['vectors_density.0'], g['upsampled_vectors_density_0'])
+    assert torch.equal(o['params2']['vectors_color.2'], g['upsampled_vectors_color_2'])
+    assert torch.equal(_bits(o['vol2']), g['volume2_bits']) and torch.equal(o['box2'], g['box2'])
+    assert 0.01 < float(g['occupied1']) < 0.5 and float(g['occupied2']) > 0
+
+
 def test_plan_matches_the_reference_schedule():
     tc = {'tensor_upsampling_iters': [2000, 3000, 4000, 5500], 'alpha_mask_update_iters': [2500, 4000],
           'num_voxels_initial': 2097156, 'num_voxels_final': 262144000}
