@@ -27,6 +27,12 @@ def test_header_declares_entry_points():
     assert 'srf_composite_fwd' in syms and 'srf_sample_pdf_merge' in syms and len(syms) >= 7
 
 
+def test_integration_guide_maps_every_entry_point():
+    """INTEGRATION.md's table names the reference lines each exported symbol replaces (or says that it has no counterpart)."""
+    guide = (ROOT / 'INTEGRATION.md').read_text()
+    assert [s for s in header_symbols() if f'`{s}`' not in guide] == []
+
+
 def test_library_exports_every_declared_symbol(lib_path):
     lib = ctypes.CDLL(str(lib_path))
     for s in header_symbols():
