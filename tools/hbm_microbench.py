@@ -14,12 +14,16 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def timed(fn, n=5):
+    """Median device time of fn() with a cold L2.  The GPU first evicts L2 and then spins for ~1 ms (torch.cuda._sleep) while the host
+    enqueues the start event, fn's launches and the stop event: without that head start the interval between the two events of a
+    sub-100-us launch is the HOST time of the Python wrapper (allocations, ctypes call), not the kernel's."""
     for _ in range(3):
         fn()
     ts = []
     for _ in range(n):
-        flush.zero_()                       # evict L2 (256 MB > 126 MB)
         torch.cuda.synchronize()
+        flush.zero_()                       # evict L2 (256 MB > 126 MB)
+        torch.cuda._sleep(2_000_000)        # ~1 ms of GPU spinning: the launches below are queued before it ends
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
