@@ -188,26 +188,37 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(Composite
   const long long first = r * S;
   const int lead = (int)(first & (G - 1));       // elements of the previous ray in this ray's first run
   const int nchunks = (lead + S + 32 * L - 1) / (32 * L);
-  const RayConsts k = ray_consts(p, r);
   const bool vec = p.vec != 0;
   const bool has_rgb = p.rgb != nullptr;
-  const float ns = k.nrm * p.distance_scale;
+  const float far_z = p.ndc ? 1.f : 1e10f;
 
   float carry = 1.f;
   float red[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // acc, sum w z, sum w z_world, r, g, b
   constexpr int KEEP = NC > 0 ? NC : 1;
   float wk[KEEP][L], zk[KEEP][L], zwk[KEEP][L];
+  float sgk[KEEP][L], colk[KEEP][3 * L], znk[KEEP];
 
-  auto step = [&](int c, float (&w)[L], float (&zi)[L], float (&zw)[L]) {
+  // Single-step rays (NC > 0): the sample loads are issued BEFORE anything that waits for the per-ray constants (direction norm, NDC
+  // terms).  In program order they used to follow ray_consts(), and the fast / slow branches around every run kept the scheduler from
+  // hoisting them over its square root: two dependent memory round trips per ray instead of one (128-sample rays: 0.73 -> 0.81-0.83
+  // of the copy bandwidth; the same reordering in the backward spilled under its register cap and lost 10-20 %: not done there).
+  auto load = [&](int c, float (&sg)[L], float (&zi)[L], float (&col)[3 * L], float& zn_raw) {
     const int i0 = c * 32 * L + lane * L - lead;              // local index of the run's first element
     const long long e0 = first + i0;
     const bool fast = vec && i0 >= 0 && i0 + L <= S;
-    float sg[L], col[3 * L];
     load_run<L, 1>(p.sigma + e0, fast, i0, S, sg);
     load_run<L, 1>(p.z + e0, fast, i0, S, zi);
     if (has_rgb) load_run<3 * L, 3>(p.rgb + e0 * 3, fast, i0, S, col);
+    zn_raw = (lane == 31 && i0 + L < S) ? __ldg(p.z + e0 + L) : far_z;      // the depth behind the warp's last run
+  };
+  auto compute = [&](int c, const RayConsts& k, const float (&sg)[L], const float (&zi)[L], const float (&col)[3 * L], float zn_raw,
+                     float (&w)[L], float (&zw)[L]) {
+    const int i0 = c * 32 * L + lane * L - lead;
+    const long long e0 = first + i0;
+    const bool fast = vec && i0 >= 0 && i0 + L <= S;
+    const float ns = k.nrm * p.distance_scale;
     float znext = __shfl_down_sync(FULL, zi[0], 1);
-    if (lane == 31) znext = (i0 + L < S) ? __ldg(p.z + e0 + L) : k.far_z;
+    if (lane == 31) znext = zn_raw;
     float q[L], al[L];
     float P = 1.f;
 #pragma unroll
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(Composite
       const int i = i0 + j;
       const bool ok = (unsigned)i < (unsigned)S;
       float zn = j < L - 1 ? zi[j < L - 1 ? j + 1 : j] : znext;
-      if (i + 1 >= S) zn = k.far_z;
+      if (i + 1 >= S) zn = far_z;
       const float ex = __expf(-sg[j] * ((zn - zi[j]) * ns));
       al[j] = ok ? 1.f - ex : 0.f;
       q[j] = ok ? (1.f - al[j] + 1e-10f) : 1.f;
@@ -250,11 +261,20 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(Composite
     if (p.visibility) store_run<L, 1>(p.visibility + e0, fast, i0, S, vis);
   };
 
+  RayConsts k;
   if (NC > 0) {               // unconditional: a step beyond the ray is fully masked (no loads, no stores)
 #pragma unroll
-    for (int c = 0; c < KEEP; ++c) step(c, wk[c], zk[c], zwk[c]);
+    for (int c = 0; c < KEEP; ++c) load(c, sgk[c], zk[c], colk[c], znk[c]);
+    k = ray_consts(p, r);
+#pragma unroll
+    for (int c = 0; c < KEEP; ++c) compute(c, k, sgk[c], zk[c], colk[c], znk[c], wk[c], zwk[c]);
   } else {
-    for (int c = 0; c < nchunks; ++c) step(c, wk[0], zk[0], zwk[0]);
+    // several steps per ray: the constants first (keeping a step's samples live across them cost 5-14 registers and 2-3 % here)
+    k = ray_consts(p, r);
+    for (int c = 0; c < nchunks; ++c) {
+      load(c, sgk[0], zk[0], colk[0], znk[0]);
+      compute(c, k, sgk[0], zk[0], colk[0], znk[0], wk[0], zwk[0]);
+    }
   }
 
   const float mine = warp_reduce8(red, lane);
@@ -334,8 +354,14 @@ struct CompositeBwd {
 
 // Backward: one reverse pass with the same run layout; sum_{k>i} g_w[k] w_k is a sequential suffix sum inside the run
 // plus one shuffle suffix scan per step (closed form in oracle/composite.py).
+#ifndef SRF_CMP_BWD_MINB2
+#define SRF_CMP_BWD_MINB2 5
+#endif
+#ifndef SRF_CMP_BWD_MINB4
+#define SRF_CMP_BWD_MINB4 4
+#endif
 template <int L>
-__global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? 5 : 4) composite_bwd_kernel(CompositeBwd p) {
+__global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? SRF_CMP_BWD_MINB2 : SRF_CMP_BWD_MINB4) composite_bwd_kernel(CompositeBwd p) {
   constexpr int G = L % 4 == 0 ? 4 : 2;
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
@@ -379,8 +405,10 @@ __global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? 5 : 4) composite_bwd_
     load_run<L, 1>(p.visibility + e0, fast, i0, S, T);
     if (has_rgb) load_run<3 * L, 3>(p.rgb + e0 * 3, fast, i0, S, col);
     if (p.g_weights) load_run<L, 1>(p.g_weights + e0, fast, i0, S, gwt);
+    // the depth behind the warp's last run: requested together with the runs, not after the shuffle that waits for them
+    const float zn_raw = (lane == 31 && i0 + L < S) ? __ldg(p.z + e0 + L) : k.far_z;
     float znext = __shfl_down_sync(FULL, zi[0], 1);
-    if (lane == 31) znext = (i0 + L < S) ? __ldg(p.z + e0 + L) : k.far_z;
+    if (lane == 31) znext = zn_raw;
     float gw[L], gww[L], w[L], q[L], de[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) {
