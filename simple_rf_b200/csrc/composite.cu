@@ -179,11 +179,8 @@ __device__ __forceinline__ RayConsts ray_consts(const P& p, long long r) {
 // pass re-reads what the lane wrote (L2 hits).  Keeping 2-4 steps in registers was measured slower (512 samples: 47 % ->
 // 60 % of HBM peak without it): the registers cost more occupancy than the re-read costs bandwidth.
 template <int L, int NC>
-__global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(CompositeFwd p) {
+__device__ __forceinline__ void composite_fwd_ray(const CompositeFwd& p, long long r, int lane) {
   constexpr int G = L % 4 == 0 ? 4 : 2;          // alignment granule of a run (floats)
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
-  if (r >= p.R) return;
   const int S = p.S;
   const long long first = r * S;
   const int lead = (int)(first & (G - 1));       // elements of the previous ray in this ray's first run
@@ -332,6 +329,21 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(Composite
   }
 }
 
+// LOOP: a warp walks rays r, r + (warps of the grid), ... under a grid capped by the host at CMP_FWD_WAVES CTAs per SM, so that a launch over
+// millions of short rays is not paced by the block scheduler's CTA turnover (64-sample rays: 0.58 -> 0.67-0.69 of the copy bandwidth, two-step
+// 256-sample rays 0.67 -> 0.71).  The single-step 4-sample-run kernel (128-sample rays) keeps one warp per ray: inside the loop it lost
+// the early issue of its loads (0.82 -> 0.73).
+template <int L, int NC, bool LOOP>
+__global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(CompositeFwd p) {
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const long long r0 = (long long)blockIdx.x * CMP_WARPS + warp;
+  if constexpr (LOOP) {
+    for (long long r = r0; r < p.R; r += (long long)gridDim.x * CMP_WARPS) composite_fwd_ray<L, NC>(p, r, lane);
+  } else {
+    if (r0 < p.R) composite_fwd_ray<L, NC>(p, r0, lane);
+  }
+}
+
 struct CompositeBwd {
   const float* sigma; const float* rgb; const float* z; const float* visibility;
   const float* rays_o; const float* rays_d; const float* rays_d_ndc;
@@ -361,11 +373,8 @@ struct CompositeBwd {
 #define SRF_CMP_BWD_MINB4 4
 #endif
 template <int L>
-__global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? SRF_CMP_BWD_MINB2 : SRF_CMP_BWD_MINB4) composite_bwd_kernel(CompositeBwd p) {
+__device__ __forceinline__ void composite_bwd_ray(const CompositeBwd& p, long long r, int lane) {
   constexpr int G = L % 4 == 0 ? 4 : 2;
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
-  if (r >= p.R) return;
   const int S = p.S;
   const long long first = r * S;
   const int lead = (int)(first & (G - 1));
@@ -472,6 +481,14 @@ __global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? SRF_CMP_BWD_MINB2 : S
   }
 }
 
+// (one warp per ray: walking several rays per warp under a capped grid, which helps the forward, measured 3-12 % slower here)
+template <int L>
+__global__ void __launch_bounds__(CMP_WARPS * 32, L == 2 ? SRF_CMP_BWD_MINB2 : SRF_CMP_BWD_MINB4) composite_bwd_kernel(CompositeBwd p) {
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const long long r = (long long)blockIdx.x * CMP_WARPS + warp;
+  if (r < p.R) composite_bwd_ray<L>(p, r, lane);
+}
+
 }  // namespace srf
 
 using namespace srf;
@@ -482,6 +499,7 @@ using namespace srf;
 #ifndef SRF_CMP_L4_PCT
 #define SRF_CMP_L4_PCT 115
 #endif
+constexpr unsigned CMP_FWD_WAVES = 32;     // CTAs per SM in the grid of the looping forward kernels (8 are resident at a time)
 static int run_length(int S) {
   const long long s2 = (long long)((S + (S % 2) + 63) / 64) * 64;
   const long long s4 = (long long)((S + (S % 4 ? 3 : 0) + 127) / 128) * 128;
@@ -510,6 +528,8 @@ SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float*
   CompositeFwd p{sigma, rgb, z, rays_o, rays_d, rays_d_ndc, alpha, visibility, weights, rgb_map, acc, depth,
                  depth_var, depth_ndc, depth_var_ndc, num_rays, num_samples, ndc, white_bkgd, distance_scale, vec};
   const unsigned blocks = (unsigned)((num_rays + CMP_WARPS - 1) / CMP_WARPS);
+  const unsigned cap = (unsigned)sm_count() * CMP_FWD_WAVES;
+  const unsigned looped = blocks < cap ? blocks : cap;
   const dim3 blk(CMP_WARPS * 32);
   const cudaStream_t st = (cudaStream_t)stream;
   const int L = run_length(num_samples);
@@ -517,11 +537,11 @@ SRF_API int srf_composite_fwd(const float* sigma, const float* rgb, const float*
   const int span = num_samples + (num_samples % G != 0 ? G - 1 : 0);       // worst case with the leading partial run
   const int steps = (span + 32 * L - 1) / (32 * L);
   if (L == 2) {
-    if (steps <= 1) composite_fwd_kernel<2, 1><<<blocks, blk, 0, st>>>(p);
-    else composite_fwd_kernel<2, 0><<<blocks, blk, 0, st>>>(p);
+    if (steps <= 1) composite_fwd_kernel<2, 1, true><<<looped, blk, 0, st>>>(p);
+    else composite_fwd_kernel<2, 0, true><<<looped, blk, 0, st>>>(p);
   } else {
-    if (steps <= 1) composite_fwd_kernel<4, 1><<<blocks, blk, 0, st>>>(p);
-    else composite_fwd_kernel<4, 0><<<blocks, blk, 0, st>>>(p);
+    if (steps <= 1) composite_fwd_kernel<4, 1, false><<<blocks, blk, 0, st>>>(p);
+    else composite_fwd_kernel<4, 0, true><<<looped, blk, 0, st>>>(p);
   }
   return check_launch("srf_composite_fwd");
 }
