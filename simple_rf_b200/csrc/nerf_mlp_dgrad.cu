@@ -77,6 +77,7 @@ constexpr int DG_THREADS = 32 * (DG_INIT_WARP0 + 4);
 constexpr int DG_KBLOCK = 128 * 128;
 constexpr int DG_STAGE = 2 * DG_KBLOCK;
 constexpr int DG_STAGES = 3;
+constexpr int DG_RING_MAX = 2 * DG_STAGES;     // resident mode: one 16 KB half-stage per K block of the tile
 constexpr int DG_OUT_BUFS = 3;             // staging images of the dZ tiles on their way to HBM
 constexpr int DG_MAX_SIDE = 2048;
 
@@ -86,7 +87,7 @@ struct alignas(1024) DgradSmem {
   uint8_t out[DG_OUT_BUFS][DG_KBLOCK];
   float side[DG_MAX_SIDE];
   float dsig[2][128];                      // d_sigma_raw per row, double-buffered over tiles (the init warps run a tile ahead)
-  uint64_t w_full[DG_STAGES], w_empty[DG_STAGES];
+  uint64_t w_full[DG_RING_MAX], w_empty[DG_RING_MAX];
   uint64_t a_ready[4];        // K block of the next layer's A operand written to tensor memory by the epilogue
   uint64_t top_ready;         // H blocks written by the init warps
   uint64_t h_free;            // every MMA of the tile's FIRST layer (the only reader of `h`) has retired
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   for (int i = threadIdx.x; i < prog.side_count; i += DG_THREADS) sm.side[i] = args.side[i];
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < DG_STAGES; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
+    for (int s = 0; s < DG_RING_MAX; ++s) { ptx::mbar_init(&sm.w_full[s], 1); ptx::mbar_init(&sm.w_empty[s], 1); }
     for (int r = 0; r < 4; ++r) ptx::mbar_init(&sm.a_ready[r], 4 * DG_GROUPS);
     ptx::mbar_init(&sm.top_ready, 4);
     ptx::mbar_init(&sm.h_free, 1);
@@ -130,6 +131,16 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
   const int my_tiles = num_tiles > (int)blockIdx.x ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int NL = prog.num_layers;
   const size_t act_stride = (size_t)act_tile_images(args.act_slots) * DG_KBLOCK;
+  // Resident weights (the TensoRF colour MLP: two 128-wide layers, four 16 KB transposed images): when every layer is 128 wide and the
+  // tile's K blocks fit the ring as 16 KB half-stages, step s of a tile always uses half-stage s - the images are copied once per CTA
+  // and the ring protocol keeps cycling without copies (a 3-stage ring of 32 KB stages made the second K block of every layer wait
+  // ~750 cycles for its image, tools/dgrad_rows_trace.py)
+  int steps_per_tile = 0;
+  bool narrow = true;
+  for (int l = 0; l < NL; ++l) { steps_per_tile += prog.layers[l].num_kblocks; narrow = narrow && prog.layers[l].n_out == 128; }
+  const bool resident = narrow && steps_per_tile <= DG_RING_MAX;
+  const uint32_t ring = resident ? (uint32_t)steps_per_tile : (uint32_t)DG_STAGES;
+  const uint32_t stage_bytes = resident ? (uint32_t)DG_KBLOCK : (uint32_t)DG_STAGE;
 
   if (warp == 0) {
     // ------------------------------------------------------------ transposed-weight producer
@@ -140,13 +151,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
         for (int l = 0; l < NL; ++l) {
           const DgradLayer& L = prog.layers[l];
           for (int kb = 0; kb < L.num_kblocks; ++kb, ++it) {
-            const uint32_t st = it % DG_STAGES, ph = (it / DG_STAGES) & 1;
+            const uint32_t st = it % ring, ph = (it / ring) & 1;
             const int halves = L.n_out >> 7;
             ptx::mbar_wait(&sm.w_empty[st], ph ^ 1);
+            if (resident && t > 0) { ptx::mbar_arrive(&sm.w_full[st]); continue; }       // the image is already there
             ptx::mbar_arrive_expect_tx(&sm.w_full[st], halves * DG_KBLOCK);
             for (int nh = 0; nh < halves; ++nh)
-              ptx::bulk_g2s_hint(sm.w[st] + nh * DG_KBLOCK, args.weights_t + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * DG_KBLOCK,
-                                 DG_KBLOCK, &sm.w_full[st], keep);
+              ptx::bulk_g2s_hint(&sm.w[0][0] + (size_t)st * stage_bytes + nh * DG_KBLOCK,
+                                 args.weights_t + L.weight_offset + (size_t)(nh * L.num_kblocks + kb) * DG_KBLOCK, DG_KBLOCK, &sm.w_full[st], keep);
           }
         }
     }
@@ -177,10 +189,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
           ptx::tc_fence_after();
           const uint32_t issue = ptx::elect_one();
           if (l > 0)
-            ptx::umma4_bf16_ts_if(issue, d_addr, tmem + (buf ^ 1u) * 256 + (uint32_t)kb * 64, 32u, w_lo + st * (DG_STAGE >> 4), desc_hi,
+            ptx::umma4_bf16_ts_if(issue, d_addr, tmem + (buf ^ 1u) * 256 + (uint32_t)kb * 64, 32u, w_lo + st * (stage_bytes >> 4), desc_hi,
                                   idesc, kb == 0 ? 0u : 1u, 4u);
           else
-            ptx::umma4_bf16_if(issue, d_addr, h_lo + (uint32_t)kb * (DG_KBLOCK >> 4), w_lo + st * (DG_STAGE >> 4), desc_hi, idesc,
+            ptx::umma4_bf16_if(issue, d_addr, h_lo + (uint32_t)kb * (DG_KBLOCK >> 4), w_lo + st * (stage_bytes >> 4), desc_hi, idesc,
                                kb == 0 ? 0u : 1u, 4u);
           ptx::umma_commit_if(issue, &sm.w_empty[st]);
           if (kb == nkb - 1) {
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
             if (l == 0) ptx::umma_commit_if(issue, &sm.h_free);
           }
           if (lane == 0) DTRACE(16 + (l * 4 + kb) * 4 + 2);
-          if (++st == DG_STAGES) { st = 0; ph ^= 1; }
+          if (++st == ring) { st = 0; ph ^= 1; }
         }
       }
     }
@@ -313,8 +325,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
                               ? __ldg(reinterpret_cast<const uint32_t*>(nrec + act_mask_offset(args.act_slots, N.mask_slot + kb) + grp * 512 + row * 4))
                               : 0xFFFFFFFFu;
         }
-        const long long m_row = tile * 128 + row;
-        float* grow = (L.rows_cols > 0 && args.g_rows != nullptr && m_row < total_rows) ? args.g_rows + (size_t)m_row * args.g_row_pitch : nullptr;
+        const bool rows_out = L.rows_cols > 0 && args.g_rows != nullptr;
         ptx::mbar_wait(&sm.d_full[buf], (d_phase >> buf) & 1);
         d_phase ^= 1u << buf;
         ptx::tc_fence_after();
@@ -327,12 +338,28 @@ __global__ void __launch_bounds__(DG_THREADS, 1) nerf_mlp_dgrad_kernel(const __g
           ptx::tmem_ld32(t_row + kb * 64, v);
           ptx::tmem_ld_wait(v);
           const int col0 = kb * 64 + grp * DG_COLS;
-          if (grow != nullptr) {                      // fp32 input gradient: 32 consecutive columns of this thread's row
+          if (rows_out && col0 < L.rows_cols) {
+            // fp32 input gradient (d loss / d product rows).  A thread owns a row, so storing its 32 columns directly makes every
+            // 128-bit store instruction of the warp touch 32 different lines (~1 400 cycles per block, tools/dgrad_rows_trace.py).
+            // The warp's 32 x 32 block goes through 4 KB of shared memory instead (16-byte units XOR-swizzled by the row: both
+            // phases are conflict-free) and leaves as row segments: 8 lanes write 128 contiguous bytes, 4 rows per instruction.
+            // The staging area is h[2..3], unused here: a chain with a row output has a 128-wide top (checked by the host).
+            float* stg = reinterpret_cast<float*>(&sm.h[2][0]) + (warp - DG_EPI_WARP0) * 1024;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              if (col0 + 4 * q + 4 <= L.rows_cols)
-                *reinterpret_cast<float4*>(grow + col0 + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                             __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            __syncwarp();
+            const long long row0 = tile * 128 + quarter * 32;
+            const int u = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              const float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((u ^ (rr & 7)) << 2));
+              if (row0 + rr < total_rows && col0 + 4 * u + 4 <= L.rows_cols)
+                *reinterpret_cast<float4*>(args.g_rows + (size_t)(row0 + rr) * args.g_row_pitch + col0 + 4 * u) = x;
+            }
+            __syncwarp();
           }
           if (wsig != nullptr) {
             const float4* w4 = reinterpret_cast<const float4*>(wsig + col0);
@@ -422,7 +449,8 @@ SRF_API int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const
     SRF_REQUIRE(L.dz_slot >= 0 || l == prog.num_layers - 1, "srf_nerf_mlp_dgrad", "only the last layer may skip its dZ images");
     SRF_REQUIRE(L.rank1_offset < 0 || ((L.rank1_offset & 3) == 0 && L.n_out == 256), "srf_nerf_mlp_dgrad", "rank-1 offset must be a multiple of 4 (256-wide layers)");
     SRF_REQUIRE(L.rows_cols == 0 || (l == prog.num_layers - 1 && g_rows != nullptr && L.rows_cols % 4 == 0 && L.rows_cols <= L.n_out &&
-                                     L.rows_cols <= g_row_pitch && g_row_pitch % 4 == 0), "srf_nerf_mlp_dgrad", "bad fp32 row output");
+                                     L.rows_cols <= g_row_pitch && g_row_pitch % 4 == 0 && prog.top_width == 128),
+                "srf_nerf_mlp_dgrad", "bad fp32 row output (last layer only, multiples of 4, a 128-wide top: the rows are staged in the upper half of h)");
   }
   SRF_REQUIRE(prog.top_mask_slot >= 0 && prog.top_mask_slot + prog.top_width / 64 <= act_slots, "srf_nerf_mlp_dgrad", "bad top mask slot");
   SRF_REQUIRE(prog.head_slot >= 0 && prog.head_slot + 2 <= dz_slots && prog.top_slot >= 0 && prog.top_slot + prog.top_width / 64 <= dz_slots,
