@@ -293,3 +293,49 @@ def test_tv_loss_on_cp_lines():
     assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
     for l, r in zip(lines, ref_lines):
         assert (l.grad.cpu().double() - r.grad).abs().max().item() <= 1e-6 * r.grad.abs().max().item()
+
+
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_dropin_cp_world_space_vs_oracle(golden_configs, mode):
+    """CP tensors without NDC (`data_loader.ndc = False`: box-march depths, world-space points): the combination has no golden of its own —
+    the drop-in is compared with the CPU oracle, whose CP path and world-space path are each pinned bit-exact against the unmodified reference."""
+    import copy
+    from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask, CpDecomposedTensor, SimpleTensoRF
+    configs, mc = copy.deepcopy(golden_configs('tensorf_world'))
+    for cfg in [configs['model']['coarse_model']] + [a['coarse_model'] for a in configs['model']['augmentations']]:
+        cfg.update(decomposition_type='CandecompParafac', num_components_density=[24], num_components_color=[48])
+    with_alpha = mode == 'eval'
+    sets = FX.tensorf_sets(configs, seed=31, with_alpha=with_alpha)
+    model = SimpleTensoRF(configs, mc)
+    assert isinstance(model.coarse_model, CpDecomposedTensor) and model.ndc is False
+    for module, t in [(model.coarse_model, sets['coarse_model'])] + [(a['coarse_model'], s[2]) for a, s in zip(model.augmented_models, sets['augmentations'])]:
+        named = dict(module.named_parameters())
+        assert set(named) == set(t['params'])
+        for k, v in t['params'].items():
+            named[k].data.copy_(v)
+        module.alpha_mask = AlphaGridMask(t['alpha_volume'][0, 0], t['alpha_bbox']) if 'alpha_volume' in t else None
+    model = model.to(DEV)
+    model.train(mode == 'train')
+    h, w = mc['resolution']
+    pid = FX.random_pixels(48, 3, h, w, seed=33)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        out = model({'pixel_id': pid.to(DEV), 'num_frames': 3, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        ref = P.tensorf_render_chunk(sets, configs, mc, pid, training=(mode == 'train'))
+    assert not any('ndc' in k for k in out)
+    assert (out['z_vals_coarse'].cpu() - ref['z_vals_coarse']).abs().max().item() <= 1e-5 * max(1.0, ref['z_vals_coarse'].abs().max().item())
+    assert 0.05 < ref['surface_mask_coarse'].float().mean() < 0.95
+    prefixes = [''] + (['points_augmentation_'] if mode == 'train' else [])
+    worst = {}
+    for pre in prefixes:
+        for k in ('rgb', 'acc', 'depth', 'depth_var', 'weights', 'raw_sigma', 'raw_rgb'):
+            key = f'{pre}{k}_coarse'
+            got, want = out[key].cpu(), ref[key]
+            assert got.shape == want.shape, key
+            worst[key] = (got - want).abs().max().item() / max(1.0, want.abs().max().item())
+            assert worst[key] <= (MLP_TOL if 'rgb' in k else TOL), (key, worst[key])
+    mismatch = ((out['raw_sigma_coarse'][..., 0] > 0).cpu() & ~ref['validity_mask_coarse']).sum().item()
+    assert mismatch <= 2, mismatch          # a sample exactly on a box face may change side when the ray differs in its last bit
+    print('CP world', mode, 'worst:', sorted(worst.items(), key=lambda kv: -kv[1])[:4])
