@@ -58,8 +58,10 @@ def _tensorf_configs():
     return cfg
 
 
-def _run_trainer(cfg, raw, iters, keep_grads_at=0):
+def _run_trainer(cfg, raw, iters, keep_grads_at=0, prepare=None):
     trainer, model, mc = C.make_trainer(cfg, raw, seed=cfg['seed'])
+    if prepare is not None:
+        prepare(model.module)
     curve, grads = [], None
     for it in range(iters):
         losses = trainer.train_one_iter(it)
@@ -237,4 +239,75 @@ def test_tensorf_predict_frame_unmodified_tester():
         errs[k] = float(numpy.abs(ref[k] - mine[k]).max() / scale)
         assert errs[k] <= 3e-3, (k, errs[k])
     _report('tensorf_predict_frame', errs)
+    print(errs)
+
+
+# ---------------------------------------------------------------------------------------------------- CANDECOMP/PARAFAC tensors
+def _tensorf_cp_configs():
+    """The shipped Simple-TensoRF config with `decomposition_type = "CandecompParafac"` (SimpleTensoRF09.py:537-539; one component count per
+    tensor, :992 / :986), on the compressed surgery schedule of _tensorf_configs(): line upsampling at iterations 2 and 5, alpha-mask
+    rebuild + crop at 3, optimiser re-grouping."""
+    cfg = _tensorf_configs()
+    for t in [cfg['model']['coarse_model']] + [a['coarse_model'] for a in cfg['model']['augmentations']]:
+        t.update(decomposition_type='CandecompParafac', num_components_density=[24], num_components_color=[48])
+    return cfg
+
+
+def _densify_cp(model):
+    """0.1 randn line factors give a density of ~1e-3 (a product of three): nothing would reach the surface threshold and the colour
+    branch would never run.  The same in-place scaling on both sides."""
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if 'vectors_density' in name:
+                p.mul_(4.5)
+            elif 'vectors_color' in name:
+                p.mul_(2.2)
+
+
+def test_tensorf_cp_train_one_iter_unmodified_trainer():
+    raw = C.synthetic_raw_data('re10k', 3, resolution=(144, 256), sparse_points=600, seed=7, tensorf=True)
+    cfg_ref = _tensorf_cp_configs()
+    cfg_mine = C.use_dropin(cfg_ref)
+    ref_curve, ref_grads, ref_model, _, _ = _run_trainer(cfg_ref, raw, 7, keep_grads_at=0, prepare=_densify_cp)
+    my_curve, my_grads, my_model, _, _ = _run_trainer(cfg_mine, raw, 7, keep_grads_at=0, prepare=_densify_cp)
+    assert type(my_model.module.coarse_model).__name__ == type(ref_model.module.coarse_model).__name__ == 'CpDecomposedTensor'
+    assert type(my_model.module).__module__.startswith('simple_rf_b200.models')
+    worst = _compare_curves(ref_curve, my_curve, tol=5e-3)
+    rels = _compare_grads(ref_grads, my_grads, tol=0.1)
+    assert any('vectors_color' in n for n in rels) and any('vectors_density' in n for n in rels)
+    t_ref, t_mine = ref_model.module.coarse_model, my_model.module.coarse_model
+    assert t_ref.resolution.tolist() == t_mine.resolution.tolist() and t_mine.resolution.tolist() != [0, 0, 0]
+    assert [tuple(p.shape) for p in t_ref.vectors_density] == [tuple(p.shape) for p in t_mine.vectors_density]      # upsampled, cropped, upsampled
+    assert torch.equal(t_ref.bounding_box.cpu(), t_mine.bounding_box.cpu())
+    va, vb = t_ref.alpha_mask.alpha_volume.bool().cpu(), t_mine.alpha_mask.alpha_volume.bool().cpu()
+    assert va.shape == vb.shape and float((va != vb).float().mean()) <= 1e-2, float((va != vb).float().mean())
+    assert list(ref_model.state_dict().keys()) == list(my_model.state_dict().keys())
+    _report('tensorf_cp_train', {'loss_curve_reference': ref_curve, 'loss_curve_dropin': my_curve, 'worst_relative_loss_deviation': worst,
+                                 'gradient_relative_l2': rels, 'final_grid': t_mine.resolution.tolist()})
+    print('CP worst loss deviation', worst, 'worst gradient rel-L2', max(rels.values()))
+
+
+def test_tensorf_cp_predict_frame_unmodified_tester():
+    raw = C.synthetic_raw_data('re10k', 3, resolution=(144, 256), sparse_points=300, seed=8, tensorf=True)
+    cfg_ref = _tensorf_cp_configs()
+    _, _, ref_model, mc, _ = _run_trainer(cfg_ref, raw, 5, prepare=_densify_cp)           # crosses an upsampling and the alpha-mask rebuild
+    state = copy.deepcopy(ref_model.state_dict())
+    assert any(k.endswith('alpha_mask.alpha_volume') for k in state)                      # (the reference's load hook requires one)
+    pose = C.test_pose(raw)
+    frames = {}
+    for tag, cfg in (('reference', cfg_ref), ('dropin', C.use_dropin(cfg_ref))):
+        tester = C.make_tester(cfg, mc, [0])
+        tester.model.load_state_dict(state)                                               # the load hook resizes the lines first
+        tester.model.eval()
+        frames[tag] = tester.predict_frame(pose)
+    ref, mine = frames['reference'], frames['dropin']
+    img_err = numpy.abs(ref['image'].astype(numpy.int32) - mine['image'].astype(numpy.int32))
+    errs = {'image_levels_max': int(img_err.max()), 'image_levels_mean': float(img_err.mean())}
+    assert img_err.max() <= 2, img_err.max()
+    for k in ('depth', 'depth_ndc'):
+        scale = max(1.0, float(numpy.abs(ref[k]).max()))
+        errs[k] = float(numpy.abs(ref[k] - mine[k]).max() / scale)
+        assert errs[k] <= 3e-3, (k, errs[k])
+    assert float(ref['image'].std()) > 1.0                                                # not a blank frame
+    _report('tensorf_cp_predict_frame', errs)
     print(errs)
