@@ -339,3 +339,33 @@ def test_dropin_cp_world_space_vs_oracle(golden_configs, mode):
     mismatch = ((out['raw_sigma_coarse'][..., 0] > 0).cpu() & ~ref['validity_mask_coarse']).sum().item()
     assert mismatch <= 2, mismatch          # a sample exactly on a box face may change side when the ray differs in its last bit
     print('CP world', mode, 'worst:', sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+
+
+def test_cp_kernels_on_empty_and_single_ray_inputs(golden_configs):
+    """Edge cases the reference handles by masking: no valid sample at all (every point outside the box: sigma stays zero, no gradient reaches the
+    lines, the colour rows call touches nothing) and a single ray."""
+    from simple_rf_b200 import tensorf_ops as T
+    configs, mc, t, a = _scene(golden_configs, 3, seed=9, with_alpha=False)
+    lines_d = [t['params'][f'vectors_density.{i}'].to(DEV).requires_grad_() for i in range(3)]
+    lines_c = [t['params'][f'vectors_color.{i}'].to(DEV) for i in range(3)]
+    box_min, box_size = t['bbox'][0], t['bbox'][1] - t['bbox'][0]
+    far = a['on'].to(DEV) + 100.0                                          # every sample far outside the box
+    comp = T.validity_compact(far, a['dn'].to(DEV), a['z'].to(DEV), t['bbox'], None)
+    assert int(comp.count.item()) == 0
+    geom = T.VmGeometry(far, a['dn'].to(DEV), a['z'].to(DEV), box_min, box_size, t['resolution'])
+    sigma = T.cp_density(geom, comp, lines_d)
+    assert sigma.shape == (3, a['z'].shape[1], 1) and float(sigma.detach().abs().max()) == 0.0
+    sigma.sum().backward()
+    assert all(float(l.grad.abs().max()) == 0.0 for l in lines_d)
+    rows, tables = T.cp_color_rows(geom, comp, a['vd'].to(DEV), lines_c)
+    gl = T.cp_color_rows_backward(geom, comp, tables, torch.ones((rows.shape[0], 48), device=DEV))
+    assert all(float(g.abs().max()) == 0.0 for g in gl)
+    # one ray
+    one = {k: v[:1] for k, v in a.items()}
+    pts = one['on'][:, None, :] + one['dn'][:, None, :] * one['z'][..., None]
+    mask = TF.validity_mask(pts, t['bbox'])
+    ref = TF.cp_density({k: v for k, v in t['params'].items() if 'density' in k}, TF.normalize(pts, t['bbox']), mask)
+    comp1 = T.validity_compact(one['on'].to(DEV), one['dn'].to(DEV), one['z'].to(DEV), t['bbox'], None)
+    geom1 = T.VmGeometry(one['on'].to(DEV), one['dn'].to(DEV), one['z'].to(DEV), box_min, box_size, t['resolution'])
+    got = T.cp_density(geom1, comp1, [l.detach() for l in lines_d])
+    assert (got.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
