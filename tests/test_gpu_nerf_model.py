@@ -156,3 +156,25 @@ def test_training_curve_follows_reference(golden, golden_configs, fused_adam, mo
     rel_n = ((norms - g['coarse_param_norms']).abs() / g['coarse_param_norms'].clamp_min(1e-6)).max().item()
     print(f'worst relative loss deviation {worst:.2e}, worst relative parameter-norm deviation {rel_n:.2e}')
     assert rel_n <= 1e-3
+
+
+def test_camera_tables_follow_load_state_dict(golden, golden_configs):
+    """The per-view camera tables the ray-generation kernel reads are a derived cache: a checkpoint loaded into a model that already
+    rendered (`load_state_dict` copies new cameras in place) must move the rays (SimpleNeRF17.py:119-131 rebuilds per call)."""
+    import copy
+    g = golden('nerf_eval')
+    model, configs, mc = _model(golden_configs, int(g['param_seed']))
+    model.eval()
+    pid = g['pixel_id'][:16].to(DEV)
+    with torch.no_grad():
+        before = model({'pixel_id': pid, 'num_frames': 3})
+    state = copy.deepcopy(model.state_dict())
+    key = 'extrinsics_learner.initial_extrinsics'
+    assert key in state
+    state[key][:, :3, 3] += 0.25                                  # translate every camera
+    model.load_state_dict(state)
+    with torch.no_grad():
+        after = model({'pixel_id': pid, 'num_frames': 3})
+    shift = (after['rays_o'] - before['rays_o']).abs().max().item()
+    assert shift > 0.1, shift
+    assert torch.equal(after['rays_d'], before['rays_d'])         # same rotations, same directions
