@@ -469,11 +469,11 @@ def tensorf_trajectory(dist, frames=6, warmup=2):
            'config': {'workload': 'simple_tensorf_trajectory_render', 'frame': [h, w], 'grid': [int(v) for v in t.resolution.tolist()],
                       'samples_per_ray': S, 'alpha_mask': '190^3, ~14 % occupied', 'outputs': 'rgb + depth'},
            'kernels_ms_per_step': {n: round(v[0] / frames, 4) for n, v in sorted(table.items(), key=lambda kv: -kv[1][0])},
-           # the frame's dominant memory-bound kernel against the bound that applies to it: requested texel bytes of the colour gather
-           # (1728 B per surface sample, planes resident in L2) against the measured L2-resident read bandwidth
-           'roofline': roofline_of(table, ['srf_vm_color_features_fwd'], 'hbm', L2_GBS, 'GB/s', ms_prof,
-                                   'requested texel bytes against the measured L2-resident read bandwidth (tools/l2_probe.py)',
-                                   'vm_color_features_fwd_kernel'),
+           # the kernel of the frame that has a hardware peak to be held against: the colour MLP on the tensor cores (the march is
+           # issue-bound, and the colour gather re-uses texels in registers along runs of consecutive samples, so its requested texel
+           # bytes per second are no longer bounded by the L2 figure - see `rooflines`)
+           'roofline': roofline_of(table, ['srf_mlp_rows_fwd'], 'tensor', peaks['bf16_tflops_sustained'], 'TFLOP/s', ms_prof,
+                                   peaks['source'] + ', sustained bf16', 'nerf_mlp_fwd_kernel (rows mode)'),
            # compulsory HBM bytes of the whole frame (SURVEY.md §8d i): per sample 4 B depth in; per ray 72 B rays + 28 B maps out —
            # the fused march never materialises the [R,S] depths, so this is a bound nobody is near: reported for the record
            'compulsory_hbm': {'bytes_per_frame': rays * S * 4.0 + rays * 100.0, 'GB/s': (rays * S * 4.0 + rays * 100.0) / (ms_f * 1e-3) / 1e9,
@@ -481,6 +481,8 @@ def tensorf_trajectory(dist, frames=6, warmup=2):
            'rooflines': {n: roofline_of(table, [n], 'hbm', L2_GBS, 'GB/s', ms_prof, 'L2-resident (requested texel bytes)', n) for n in gathers}}
     res['rooflines']['mlp_rows_fwd'] = roofline_of(table, ['srf_mlp_rows_fwd'], 'tensor', peaks['bf16_tflops_sustained'], 'TFLOP/s', ms_prof,
                                                    peaks['source'] + ', sustained bf16', 'nerf_mlp_fwd_kernel (rows mode)')
+    res['rooflines']['srf_vm_color_features_fwd']['note'] = ('requested bytes (1728 B per surface sample); the run-merged gather re-loads a texel only when '
+                                                             'the footprint of consecutive samples changes, so this rate may exceed the L2 figure')
     del model
     torch.cuda.empty_cache()
     return res
