@@ -97,6 +97,56 @@ def golden_nerf():
     return configs, model_configs
 
 
+def nerf_variant_configs():
+    """The shipped train1142 config with the switches no shipped run flips: world-space sampling (`data_loader.ndc = False`, near / far in
+    world units), depths linear in disparity (`lindisp`), white background, a smaller noise level."""
+    configs, model_configs = H.load_configs(1142, 'fern')
+    model_configs = H.shrink(model_configs, 4)
+    configs['model']['netchunk'] = 2048
+    configs['data_loader']['ndc'] = False
+    configs['model']['lindisp'] = True
+    configs['model']['white_bkgd'] = True
+    configs['model']['raw_noise_std'] = 0.25
+    return configs, model_configs
+
+
+def golden_nerf_variants():
+    """Simple-NeRF in world space with lindisp depths and a white background through the unmodified reference, eval and train."""
+    configs, model_configs = nerf_variant_configs()
+    (OUT / 'nerf_variant_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    sets = FX.nerf_param_sets(configs, seed=13)
+    load_nerf_params(model, sets)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    per_tag = ('rgb', 'acc', 'depth', 'depth_var', 'alpha', 'visibility', 'weights', 'raw_sigma', 'raw_rgb')
+    for mode, R, seed in (('eval', 48, 7), ('train', 40, 8)):
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(600 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+        torch.manual_seed(600 + seed)
+        with torch.no_grad():
+            mine = P.nerf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        assert 'rays_o_ndc' not in ref and 'depth_ndc_coarse' not in ref
+        fixture = {'pixel_id': pixel_id, 'param_seed': 13, 'rng_seed': 600 + seed}
+        for k in ('rays_o', 'rays_d', 'view_dirs', 'z_vals_coarse', 'z_vals_fine'):
+            _check(f'nerf_variant/{mode}/{k}', ref[k], mine[k])
+            fixture[k] = ref[k]
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for tag in ('coarse', 'fine'):
+                if pre and tag == 'fine':
+                    continue
+                for k in per_tag:
+                    key = f'{pre}{k}_{tag}'
+                    _check(f'nerf_variant/{mode}/{key}', ref[key], mine[key])
+                    fixture[key] = ref[key]
+        np.savez_compressed(OUT / f'nerf_variant_{mode}.npz', **_np(fixture))
+        print(f'nerf_variant_{mode}: {len(fixture)} arrays, oracle == reference (acc mean {ref["acc_fine"].mean():.3f})')
+
+
 def golden_sample_pdf():
     """Stage-wise: the reference's own static sample_pdf + get_z_vals_fine on seeded inputs, both
     the deterministic (eval) and the random-u (train) form, S in {64, 37}."""
@@ -656,6 +706,9 @@ def main():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if 'nerf_variants' in sys.argv[1:]:
+        golden_nerf_variants()
+        return
     if 'cp' in sys.argv[1:]:                     # only the CANDECOMP/PARAFAC fixtures
         golden_tensorf_cp()
         golden_surgery(cp=True)
@@ -674,6 +727,7 @@ def main():
     golden_tensorf_world()
     golden_tensorf_cp()
     golden_surgery(cp=True)
+    golden_nerf_variants()
 
 
 if __name__ == '__main__':

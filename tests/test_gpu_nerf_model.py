@@ -178,3 +178,50 @@ def test_camera_tables_follow_load_state_dict(golden, golden_configs):
     shift = (after['rays_o'] - before['rays_o']).abs().max().item()
     assert shift > 0.1, shift
     assert torch.equal(after['rays_d'], before['rays_d'])         # same rotations, same directions
+
+
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_dropin_variant_config_vs_reference_golden(golden, golden_configs, mode):
+    """The switches no shipped run flips — world-space sampling (`data_loader.ndc = False`), `lindisp`, `white_bkgd`, another noise level —
+    against the unmodified reference (tests/golden/nerf_variant_*.npz)."""
+    from simple_rf_b200.models.SimpleNeRF91 import SimpleNeRF
+    g = golden(f'nerf_variant_{mode}')
+    configs, mc = golden_configs('nerf_variant')
+    model = SimpleNeRF(configs, mc)
+    sets = FX.nerf_param_sets(configs, seed=int(g['param_seed']))
+    model.coarse_model.load_state_dict(sets['coarse_model'])
+    model.fine_model.load_state_dict(sets['fine_model'])
+    for aug, (_, _, params) in zip(model.augmented_models, sets['augmentations']):
+        aug['coarse_model'].load_state_dict(params)
+    model = model.to(DEV)
+    model.train(mode == 'train')
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+    assert not any('ndc' in k for k in out)
+    for k in ('rays_o', 'rays_d', 'view_dirs'):
+        assert (out[k].cpu() - g[k]).abs().max().item() <= EXACT_TOL * max(1.0, g[k].abs().max().item()), k
+    assert torch.equal(out['z_vals_coarse'].cpu(), g['z_vals_coarse'])          # lindisp ladder + CPU jitter: same arithmetic
+    worst = {}
+    for k, ref in g.items():
+        if k not in out or ref.dtype != torch.float32 or k.startswith('z_vals') or k.startswith('rays') or k == 'view_dirs':
+            continue
+        got = out[k].cpu()
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        worst[k] = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        # disparity-linear world depths put intervals of up to ~0.5 at the far end (0.02 in the NDC fixture): alpha = 1 - exp(-sigma * delta)
+        # is that much more sensitive to the bf16 rounding of sigma.  Stated bf16 bound here: 1e-2 (the trained-field bound of DESIGN.md §5);
+        # the fp32-contract program below must stay within 1e-3 on the same inputs, which separates rounding from a defect.
+        assert worst[k] <= 1e-2, (k, worst[k])
+    assert (out['z_vals_fine'].cpu() - g['z_vals_fine']).abs().max().item() <= 1e-2 * max(1.0, g['z_vals_fine'].abs().max().item())
+    print('variant', mode, 'bf16 worst:', sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+    if mode == 'eval':
+        model.configs['model']['mlp_precision'] = 'bf16x3'
+        with torch.no_grad():
+            out = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+        worst = {}
+        for k, ref in g.items():
+            if k.endswith('_coarse') and ref.dtype == torch.float32 and k in out:          # coarse pass: same depths on both sides
+                worst[k] = (out[k].cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+                assert worst[k] <= 1e-3, (k, worst[k])
+        print('variant eval bf16x3 worst (coarse):', sorted(worst.items(), key=lambda kv: -kv[1])[:4])

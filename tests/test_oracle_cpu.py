@@ -33,6 +33,24 @@ def test_nerf_pipeline_matches_reference_golden(golden, golden_configs, mode):
             assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
 
 
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_nerf_variant_pipeline_matches_reference_golden(golden, golden_configs, mode):
+    """World-space sampling (`ndc = False`), depths linear in disparity, white background (oracle/generate_golden.py::nerf_variant_configs)."""
+    g = golden(f'nerf_variant_{mode}')
+    configs, model_configs = golden_configs('nerf_variant')
+    assert configs['data_loader']['ndc'] is False and configs['model']['lindisp'] and configs['model']['white_bkgd']
+    sets = FX.nerf_param_sets(configs, seed=int(g['param_seed']))
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = P.nerf_render_chunk(sets, configs, model_configs, g['pixel_id'], training=(mode == 'train'))
+    for k in ('rays_o', 'rays_d', 'z_vals_coarse'):
+        assert torch.equal(out[k], g[k]), k
+    assert not any('ndc' in k for k in out)
+    for k in g:
+        if k in out and g[k].dtype == torch.float32:
+            assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
+
+
 def test_sample_pdf_matches_reference_golden(golden):
     g = golden('sample_pdf')
     for tag in 'abc':
