@@ -37,7 +37,7 @@ def tensorf_sets(configs, seed, with_alpha):
         res = TF.vm_resolution(cfg['num_voxels_initial'], bbox)
         cp = cfg['decomposition_type'] == 'CandecompParafac'
         init = TF.init_cp_params if cp else TF.init_vm_params
-        t = {'params': init(res, cfg['num_components_density'], cfg['num_components_color'], generator=g),
+        t = {'params': init(res, cfg['num_components_density'], cfg['num_components_color'], generator=g, use_views=cfg['use_view_dirs']),
              'bbox': bbox, 'resolution': res, 'num_samples': TF.vm_num_samples(res, cfg['num_voxels_per_sample'], cfg['num_samples_max'])}
         # random-init planes give sigma ~ 0; scale density up so weights cross the 1e-4 surface threshold
         # (CP: the feature is a sum of products of THREE 0.1 randn factors)

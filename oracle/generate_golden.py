@@ -336,6 +336,55 @@ def golden_tensorf_cp():
         print(f'tensorf_cp_{mode}: oracle == reference (valid {frac[0]:.3f}, surface {frac[1]:.3f}, acc mean {ref["acc_coarse"].mean():.3f})')
 
 
+def tensorf_variant_configs():
+    """The shipped train0212 config with the switches no shipped run flips: SoftPlus density (`density_offset` -1), another `distance_scale`,
+    a white background, and a view-INdependent colour predictor on the augmentation tensor (`use_view_dirs` / `view_dependent_color` false,
+    SimpleTensoRF09.py:732, :1267, :1384, :1414)."""
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    main, aug = configs['model']['coarse_model'], configs['model']['augmentations'][0]['coarse_model']
+    main['num_voxels_initial'], aug['num_voxels_initial'] = 40 ** 3, 20 ** 3
+    main.update(density_predictor='SoftPlus', density_offset=-1.0, distance_scale=10)
+    aug.update(use_view_dirs=False, view_dependent_color=False)
+    configs['model']['white_bkgd'] = True
+    return configs, model_configs
+
+
+def golden_tensorf_variants():
+    configs, model_configs = tensorf_variant_configs()
+    (OUT / 'tensorf_variant_configs.json').write_text(json.dumps({'configs': configs, 'model_configs': model_configs}, indent=1))
+    model = H.build_model(configs, model_configs)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    keys = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility', 'weights', 'raw_sigma', 'raw_rgb')
+    for mode, R, seed, with_alpha in (('eval', 40, 35, True), ('train', 32, 36, False)):
+        sets = FX.tensorf_sets(configs, seed=29, with_alpha=with_alpha)
+        load_tensorf_params(model, sets)
+        pixel_id = FX.random_pixels(R, nviews, h, w, seed)
+        model.train(mode == 'train')
+        torch.manual_seed(700 + seed)
+        with torch.no_grad():
+            ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+        torch.manual_seed(700 + seed)
+        with torch.no_grad():
+            mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=(mode == 'train'))
+        fixture = {'pixel_id': pixel_id, 'param_seed': 29, 'rng_seed': 700 + seed, 'with_alpha': with_alpha}
+        for k in ('rays_o', 'rays_d', 'rays_o_ndc', 'rays_d_ndc', 'view_dirs', 'z_vals_coarse'):
+            _check(f'tensorf_variant/{mode}/{k}', ref[k], mine[k])
+            fixture[k] = ref[k]
+        prefixes = [''] + ([f"{a[0]}_" for a in sets['augmentations']] if mode == 'train' else [])
+        for pre in prefixes:
+            for k in keys:
+                key = f'{pre}{k}_coarse'
+                _check(f'tensorf_variant/{mode}/{key}', ref[key], mine[key])
+                fixture[key] = ref[key]
+            fixture[f'{pre}validity_mask_coarse'] = mine[f'{pre}validity_mask_coarse']
+            fixture[f'{pre}surface_mask_coarse'] = mine[f'{pre}surface_mask_coarse']
+        frac = mine['surface_mask_coarse'].float().mean().item()
+        np.savez_compressed(OUT / f'tensorf_variant_{mode}.npz', **_np(fixture))
+        print(f'tensorf_variant_{mode}: oracle == reference (surface {frac:.3f}, acc mean {ref["acc_coarse"].mean():.3f})')
+
+
 def tensorf_world_configs():
     """The shipped train0212 config with `ndc = False` (no shipped run selects it; SimpleTensoRF09.py:388-400 is the box-marching
     sampler it switches on): world-space tensor boxes in front of the cameras, near / far in world units."""
@@ -709,6 +758,9 @@ def main():
     if 'nerf_variants' in sys.argv[1:]:
         golden_nerf_variants()
         return
+    if 'tensorf_variants' in sys.argv[1:]:
+        golden_tensorf_variants()
+        return
     if 'cp' in sys.argv[1:]:                     # only the CANDECOMP/PARAFAC fixtures
         golden_tensorf_cp()
         golden_surgery(cp=True)
@@ -728,6 +780,7 @@ def main():
     golden_tensorf_cp()
     golden_surgery(cp=True)
     golden_nerf_variants()
+    golden_tensorf_variants()
 
 
 if __name__ == '__main__':

@@ -134,7 +134,8 @@ def tensorf_render_chunk(tensors, configs, model_configs, pixel_id, *, training,
 
     def run(t, cfg, prefix):
         white = mc['white_bkgd'] or bool(training and (torch.rand((1,)) < 0.5))
-        res = TF.tensor_forward(t['params'], t['bbox'], pts, z, rays_o, rays_d, d_ndc, vd, ndc=ndc,
+        views = vd if (cfg['use_view_dirs'] and cfg['view_dependent_color']) else None       # SimpleTensoRF09.py:732, :1267, :1414
+        res = TF.tensor_forward(t['params'], t['bbox'], pts, z, rays_o, rays_d, d_ndc, views, ndc=ndc,
                                 alpha_volume=t.get('alpha_volume'), alpha_bbox=t.get('alpha_bbox'),
                                 distance_scale=cfg['distance_scale'],
                                 weight_threshold=cfg['ray_marching_weight_threshold'], white_bkgd=white,

@@ -120,19 +120,20 @@ def vm_color_features(params, p):
 
 
 def color_mlp(params, features, view_dirs):
-    """SimpleTensoRF09.py:1389-1393, :1411-1421 with both PE degrees 0 (identity encodings)."""
-    x = torch.cat([features, view_dirs], dim=-1)
+    """SimpleTensoRF09.py:1389-1393, :1411-1421 with both PE degrees 0 (identity encodings); view_dirs None: `use_view_dirs` /
+    `view_dependent_color` false (:1384, :1414)."""
+    x = features if view_dirs is None else torch.cat([features, view_dirs], dim=-1)
     x = F.relu(F.linear(x, params['color_predictor.mlp.0.weight'], params['color_predictor.mlp.0.bias']))
     x = F.relu(F.linear(x, params['color_predictor.mlp.2.weight'], params['color_predictor.mlp.2.bias']))
     return torch.sigmoid(F.linear(x, params['color_predictor.mlp.4.weight'], params['color_predictor.mlp.4.bias']))
 
 
 def vm_color(params, pts_norm, mask, view_dirs):
-    """SimpleTensoRF09.py:1241-1272.  view_dirs [R,3] (expanded per sample, :733-736)."""
+    """SimpleTensoRF09.py:1241-1272.  view_dirs [R,3] (expanded per sample, :733-736) or None."""
     rgb = torch.zeros([*pts_norm.shape[:-1], 3], dtype=pts_norm.dtype)
     if mask.any():
         p = pts_norm[mask]
-        vd = view_dirs[:, None].expand(pts_norm.shape)[mask]
+        vd = None if view_dirs is None else view_dirs[:, None].expand(pts_norm.shape)[mask]
         rgb[mask] = color_mlp(params, vm_color_features(params, p), vd)
     return rgb
 
@@ -173,7 +174,7 @@ def vm_num_samples(resolution, voxels_per_sample=0.5, num_samples_max=1e6):
     return int(min(num_samples_max, n))
 
 
-def init_vm_params(resolution, comps_density, comps_color, feat_dim=27, units=128, generator=None, scale=0.1):
+def init_vm_params(resolution, comps_density, comps_color, feat_dim=27, units=128, generator=None, scale=0.1, use_views=True):
     """Shapes of SimpleTensoRF09.py:1154-1165 + :1151 + :1389-1393 (0.1*randn planes/lines)."""
     res = [int(r) for r in resolution]
     p = {}
@@ -183,29 +184,29 @@ def init_vm_params(resolution, comps_density, comps_color, feat_dim=27, units=12
             p[f'matrices_{kind}.{i}'] = scale * torch.randn(1, comps[i], res[a1], res[a0], generator=generator)
             p[f'vectors_{kind}.{i}'] = scale * torch.randn(1, comps[i], res[VECTOR_AXES[i]], 1, generator=generator)
 
-    _init_color_network(p, sum(comps_color), feat_dim, units, generator)
+    _init_color_network(p, sum(comps_color), feat_dim, units, generator, use_views)
     return p
 
 
-def _init_color_network(p, in_features, feat_dim, units, generator):
+def _init_color_network(p, in_features, feat_dim, units, generator, use_views=True):
     """basis_matrix_color (:1151 / :986) + MlpFeaturesColorPredictor (:1389-1393), torch.nn.Linear-style uniform init."""
     def lin(o, i, bias=True):
         b = 1.0 / i ** 0.5
         w = (torch.rand(o, i, generator=generator) * 2 - 1) * b
         return w, ((torch.rand(o, generator=generator) * 2 - 1) * b if bias else None)
     p['basis_matrix_color.weight'], _ = lin(feat_dim, in_features, bias=False)
-    p['color_predictor.mlp.0.weight'], p['color_predictor.mlp.0.bias'] = lin(units, feat_dim + 3)
+    p['color_predictor.mlp.0.weight'], p['color_predictor.mlp.0.bias'] = lin(units, feat_dim + (3 if use_views else 0))
     p['color_predictor.mlp.2.weight'], p['color_predictor.mlp.2.bias'] = lin(units, units)
     p['color_predictor.mlp.4.weight'], _ = lin(3, units)
     p['color_predictor.mlp.4.bias'] = torch.zeros(3)
 
 
-def init_cp_params(resolution, comps_density, comps_color, feat_dim=27, units=128, generator=None, scale=0.1):
+def init_cp_params(resolution, comps_density, comps_color, feat_dim=27, units=128, generator=None, scale=0.1, use_views=True):
     """Shapes of SimpleTensoRF09.py:979-996 (every line holds num_components[0] components) + the shared colour predictor."""
     res = [int(r) for r in resolution]
     p = {}
     for kind, comps in (('density', comps_density), ('color', comps_color)):
         for i in range(3):
             p[f'vectors_{kind}.{i}'] = scale * torch.randn(1, comps[0], res[VECTOR_AXES[i]], 1, generator=generator)
-    _init_color_network(p, sum(comps_color), feat_dim, units, generator)
+    _init_color_network(p, sum(comps_color), feat_dim, units, generator, use_views)
     return p

@@ -383,3 +383,42 @@ def test_dropin_world_space_vs_reference_golden(golden, golden_configs, mode):
         with torch.no_grad():
             lean = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3})
         assert 'weights_coarse' not in lean and (lean['rgb_coarse'].cpu() - g['rgb_coarse']).abs().max().item() <= MLP_TOL
+
+
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_dropin_variant_config_vs_reference_golden(golden, golden_configs, mode):
+    """The switches no shipped run flips — SoftPlus density with its offset, another distance scale, a white background, a
+    view-independent colour predictor on the augmentation tensor — against the unmodified reference (tests/golden/tensorf_variant_*.npz)."""
+    from simple_rf_b200.models.SimpleTensoRF91 import AlphaGridMask, SimpleTensoRF
+    g = golden(f'tensorf_variant_{mode}')
+    configs, mc = golden_configs('tensorf_variant')
+    sets = FX.tensorf_sets(configs, seed=int(g['param_seed']), with_alpha=bool(g['with_alpha']))
+    model = SimpleTensoRF(configs, mc)
+    for module, t in [(model.coarse_model, sets['coarse_model'])] + [(a['coarse_model'], s[2]) for a, s in zip(model.augmented_models, sets['augmentations'])]:
+        named = dict(module.named_parameters())
+        assert set(named) == set(t['params'])
+        for k, v in t['params'].items():
+            assert named[k].shape == v.shape, k
+            named[k].data.copy_(v)
+        module.alpha_mask = AlphaGridMask(t['alpha_volume'][0, 0], t['alpha_bbox']) if 'alpha_volume' in t else None
+    model = model.to(DEV)
+    model.train(mode == 'train')
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+    assert torch.equal(out['z_vals_coarse'].cpu(), g['z_vals_coarse'])
+    worst = {}
+    for k, ref in g.items():
+        if k not in out or ref.dtype != torch.float32 or k in ('z_vals_coarse', 'view_dirs') or k.startswith('rays'):
+            continue
+        got = out[k].cpu()
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        worst[k] = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        assert worst[k] <= (MLP_TOL if 'rgb' in k else TOL), (k, worst[k])
+    print('variant', mode, 'worst:', sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+    if mode == 'eval':          # the fused test-time march takes the same switches
+        with torch.no_grad():
+            lean = model({'pixel_id': g['pixel_id'].to(DEV), 'num_frames': 3})
+        for k in ('rgb_coarse', 'acc_coarse', 'depth_coarse', 'depth_ndc_coarse'):
+            err = (lean[k].cpu() - g[k]).abs().max().item() / max(1.0, g[k].abs().max().item())
+            assert err <= (MLP_TOL if 'rgb' in k else TOL), (k, err)

@@ -137,6 +137,25 @@ def test_tensorf_world_space_pipeline_matches_reference_golden(golden, golden_co
 
 
 @pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_tensorf_variant_pipeline_matches_reference_golden(golden, golden_configs, mode):
+    """SoftPlus density, another distance scale, white background, a view-independent colour predictor on the augmentation tensor."""
+    g = golden(f'tensorf_variant_{mode}')
+    configs, model_configs = golden_configs('tensorf_variant')
+    assert configs['model']['coarse_model']['density_predictor'] == 'SoftPlus' and configs['model']['white_bkgd']
+    assert configs['model']['augmentations'][0]['coarse_model']['use_view_dirs'] is False
+    sets = FX.tensorf_sets(configs, seed=int(g['param_seed']), with_alpha=bool(g['with_alpha']))
+    assert sets['augmentations'][0][2]['params']['color_predictor.mlp.0.weight'].shape[1] == 27
+    torch.manual_seed(int(g['rng_seed']))
+    with torch.no_grad():
+        out = P.tensorf_render_chunk(sets, configs, model_configs, g['pixel_id'], training=(mode == 'train'))
+    assert torch.equal(out['z_vals_coarse'], g['z_vals_coarse'])
+    assert torch.equal(out['validity_mask_coarse'], g['validity_mask_coarse'])
+    for k in g:
+        if k in out and g[k].dtype == torch.float32:
+            assert _close(out[k], g[k], 2e-4 * max(1.0, g[k].abs().max().item())), k
+
+
+@pytest.mark.parametrize('mode', ['eval', 'train'])
 def test_tensorf_cp_pipeline_matches_reference_golden(golden, golden_configs, mode):
     """`decomposition_type = "CandecompParafac"` (SimpleTensoRF09.py:964-1124): three line factors per component."""
     g = golden(f'tensorf_cp_{mode}')
