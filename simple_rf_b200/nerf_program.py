@@ -41,10 +41,14 @@ class PackedMLP:
     `param_names` is the flat parameter order the gather indices refer to; `refresh(params)` takes the
     live fp32 tensors (dict name -> tensor on the device) and rebuilds the packed blob + side table."""
 
-    def __init__(self, mlp_configs, width=256, views_width=128, depth=8, skips=(4,)):
+    def __init__(self, mlp_configs, width=256, views_width=128, depth=None, skips=(4,)):
         cfg = mlp_configs
         assert width == 256 and cfg['points_net_width'] == 256, 'kernel is specialised for 256-wide trunks'
-        assert cfg['points_net_depth'] == depth
+        # any trunk depth the layer program holds (the shipped models use 8; the skip connection after layer 4 exists from depth 6 on,
+        # SimpleNeRF17.py:638-647); depth + feature layer + view layer <= MAX_LAYERS
+        depth = int(cfg['points_net_depth']) if depth is None else depth
+        assert cfg['points_net_depth'] == depth and 2 <= depth <= MAX_LAYERS - 2, 'trunk depth must be 2..10'
+        assert depth != 5, 'a 5-layer trunk concatenates the encoding behind its LAST layer and fails upstream too (SimpleNeRF17.py:732-733, :652)'
         self.cfg = cfg
         self.pdeg = cfg['points_positional_encoding_degree']
         full = _enc_width(self.pdeg)

@@ -166,3 +166,50 @@ def test_cta_pair_launch_is_bit_identical(golden_configs, variant, R, S):
         lib.srf_mlp_set_pairing(before)
     assert torch.equal(s0, s1) and torch.equal(c0, c1)
     assert torch.isfinite(s1).all() and torch.isfinite(c1).all()
+
+
+@pytest.mark.parametrize('variant', ['main', 'views_augmentation'])
+@pytest.mark.parametrize('depth', [2, 4, 6, 10])
+def test_mlp_other_trunk_depths(golden_configs, variant, depth):
+    """`points_net_depth` other than the shipped 8 (the layer program holds trunks of 2..10 layers; the skip connection after layer 4 exists from
+    depth 6 on, SimpleNeRF17.py:638-647): forward against the fp32 oracle, parameter gradients against fp32 autograd."""
+    import copy
+    from simple_rf_b200 import nerf_program as NP
+    configs, mc, variants = _variants(golden_configs)
+    cfg = copy.deepcopy(variants[variant])
+    cfg['points_net_depth'] = depth
+    g = torch.Generator().manual_seed(100 * depth + len(variant))
+    params = M.init_mlp_params(cfg, g)
+    params['pts_output_linear.bias'][0] += 1.0
+    assert (f'pts_linears.{depth - 1}.weight' in params) and (f'pts_linears.{depth}.weight' not in params)
+    assert (params['pts_linears.5.weight'].shape[1] > 256) if depth >= 6 else True          # the skip layer takes [encoding | h]
+    R, S = 41, 64
+    o = torch.rand(R, 3, generator=g) - .5
+    d = torch.rand(R, 3, generator=g) - .5
+    vd = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    z = torch.rand(R, S, generator=g)
+    pts = (o[:, None] + d[:, None] * z[..., None]).reshape(-1, 3)
+    vflat = vd[:, None].expand(R, S, 3).reshape(-1, 3)
+    leaves = {k: v.clone().requires_grad_() for k, v in params.items()}
+    ref = M.mlp_forward(leaves, cfg, pts, vflat if cfg['use_view_dirs'] else None, None)
+    g_sigma = torch.randn(R, S, 1, generator=g) * 0.1
+    g_rgb = torch.randn(R, S, 3, generator=g)
+    ((ref['sigma'] * g_sigma.reshape(-1, 1)).sum() + (ref['rgb'] * g_rgb.reshape(-1, 3)).sum()).backward()
+
+    packed = NP.PackedMLP(cfg).refresh({k: v.to(DEV) for k, v in params.items()})
+    sigma, rgb, acts = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV), save=True)
+    es = (sigma.cpu().reshape(-1, 1) - ref['sigma'].detach()).abs().max().item()
+    er = (rgb.cpu().reshape(-1, 3) - ref['rgb'].detach()).abs().max().item()
+    assert es <= SIGMA_TOL * max(1.0, ref['sigma'].abs().max().item()) and er <= RGB_TOL, (es, er)
+    s2, r2 = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV))                       # inference program: same numbers
+    assert torch.equal(s2, sigma) and torch.equal(r2, rgb)
+    flat_grad, _ = NP.mlp_backward(packed, packed.flat, acts, sigma, rgb, g_sigma.to(DEV), g_rgb.to(DEV))
+    off, worst = 0, 0.0
+    for name in packed.param_names:
+        n = leaves[name].numel()
+        got = flat_grad[off:off + n].view(leaves[name].shape).cpu()
+        off += n
+        rel = ((got - leaves[name].grad).norm() / leaves[name].grad.norm().clamp_min(1e-12)).item()
+        worst = max(worst, rel)
+        assert rel <= 0.15, (name, rel)
+    print(f'{variant} depth {depth}: max|d sigma| {es:.2e} max|d rgb| {er:.2e} worst gradient rel-L2 {worst:.3f}')
