@@ -41,8 +41,12 @@ class PackedMLP:
     `param_names` is the flat parameter order the gather indices refer to; `refresh(params)` takes the
     live fp32 tensors (dict name -> tensor on the device) and rebuilds the packed blob + side table."""
 
-    def __init__(self, mlp_configs, width=256, views_width=128, depth=None, skips=(4,)):
+    def __init__(self, mlp_configs, width=256, views_width=None, depth=None, skips=(4,)):
         cfg = mlp_configs
+        if views_width is None:                       # the view layer may be 128 (shipped) or 256 wide: both are layer widths of the kernel
+            views_width = int(cfg.get('views_net_width', 128)) if cfg.get('use_view_dirs') else 128
+        assert views_width in (128, 256), 'the view layer must be 128 or 256 wide'
+
         assert width == 256 and cfg['points_net_width'] == 256, 'kernel is specialised for 256-wide trunks'
         # any trunk depth the layer program holds (the shipped models use 8; the skip connection after layer 4 exists from depth 6 on,
         # SimpleNeRF17.py:638-647); depth + feature layer + view layer <= MAX_LAYERS

@@ -213,3 +213,43 @@ def test_mlp_other_trunk_depths(golden_configs, variant, depth):
         worst = max(worst, rel)
         assert rel <= 0.15, (name, rel)
     print(f'{variant} depth {depth}: max|d sigma| {es:.2e} max|d rgb| {er:.2e} worst gradient rel-L2 {worst:.3f}')
+
+
+def test_mlp_wide_view_layer(golden_configs):
+    """`views_net_width = 256` (shipped: 128): the view layer is a 256-wide layer of the program, the rgb head a 3 x 256 dot product."""
+    import copy
+    from simple_rf_b200 import nerf_program as NP
+    configs, mc, variants = _variants(golden_configs)
+    cfg = copy.deepcopy(variants['main'])
+    cfg['views_net_width'] = 256
+    g = torch.Generator().manual_seed(77)
+    params = M.init_mlp_params(cfg, g)
+    assert params['views_linears.0.weight'].shape[0] == 256 and params['views_output_linear.weight'].shape == (3, 256)
+    params['pts_output_linear.bias'][0] += 1.0
+    R, S = 41, 64
+    o = torch.rand(R, 3, generator=g) - .5
+    d = torch.rand(R, 3, generator=g) - .5
+    vd = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    z = torch.rand(R, S, generator=g)
+    pts = (o[:, None] + d[:, None] * z[..., None]).reshape(-1, 3)
+    vflat = vd[:, None].expand(R, S, 3).reshape(-1, 3)
+    leaves = {k: v.clone().requires_grad_() for k, v in params.items()}
+    ref = M.mlp_forward(leaves, cfg, pts, vflat, None)
+    g_sigma = torch.randn(R, S, 1, generator=g) * 0.1
+    g_rgb = torch.randn(R, S, 3, generator=g)
+    ((ref['sigma'] * g_sigma.reshape(-1, 1)).sum() + (ref['rgb'] * g_rgb.reshape(-1, 3)).sum()).backward()
+    packed = NP.PackedMLP(cfg).refresh({k: v.to(DEV) for k, v in params.items()})
+    sigma, rgb, acts = packed.forward(o.to(DEV), d.to(DEV), z.to(DEV), vd.to(DEV), save=True)
+    es = (sigma.cpu().reshape(-1, 1) - ref['sigma'].detach()).abs().max().item()
+    er = (rgb.cpu().reshape(-1, 3) - ref['rgb'].detach()).abs().max().item()
+    assert es <= SIGMA_TOL * max(1.0, ref['sigma'].abs().max().item()) and er <= RGB_TOL, (es, er)
+    flat_grad, _ = NP.mlp_backward(packed, packed.flat, acts, sigma, rgb, g_sigma.to(DEV), g_rgb.to(DEV))
+    off, worst = 0, 0.0
+    for name in packed.param_names:
+        n = leaves[name].numel()
+        got = flat_grad[off:off + n].view(leaves[name].shape).cpu()
+        off += n
+        rel = ((got - leaves[name].grad).norm() / leaves[name].grad.norm().clamp_min(1e-12)).item()
+        worst = max(worst, rel)
+        assert rel <= 0.15, (name, rel)
+    print(f'views_net_width 256: max|d sigma| {es:.2e} max|d rgb| {er:.2e} worst gradient rel-L2 {worst:.3f}')
