@@ -299,6 +299,25 @@ int srf_nerf_mlp_dgrad(const void* program, const void* weights_t, const float* 
                        const int* count, void* dz, int dz_slots, float* g_rows, int g_row_pitch, void* stream);
 int srf_dgrad_program_bytes(void);
 
+/* Gradient of one fused-MLP evaluation with respect to its INPUTS, for learnable cameras (the pose correction r, t of
+ * src/models/SimpleNeRF17.py:817-842 receives its gradient through the rays: pts = o + z d at :210-214 and view_dirs at :190; autograd
+ * derives it through the positional encoding :669-693 and the first / skip / view layers :726-765).  Reads the dZ images
+ * srf_nerf_mlp_dgrad wrote and the fp32 parameter vector: for every layer that consumes an encoding image (`sources`, HOST array),
+ * g_enc[row, j] += sum_n dZ[row, n] W[n, cols[j]]; then the encoding backward
+ * g_x[c] = g_enc[c] + sum_k 2^k (cos(2^k x_c) g_enc[3 + 6k + c] - sin(2^k x_c) g_enc[6 + 6k + c]).
+ * Writes g_points [num_rows, 3] and g_views [num_rows, 3] (nullable when no source has target 1); rays_o / rays_d [num_rows / num_samples, 3],
+ * z [num_rows] and view_dirs are the arrays srf_nerf_mlp_fwd was given.  Off the hot path of every shipped configuration (cameras frozen). */
+typedef struct {
+  int32_t dz_slot, dz_images, in_total, target;   /* target 0: points encoding image, 1: view encoding image (32 columns) */
+  int64_t w_offset;                               /* element offset of the weight matrix [64 * dz_images, in_total] in params */
+  int32_t cols[64];                               /* encoding image column -> weight column, -1: not consumed */
+} srf_input_grad_source;
+int srf_nerf_mlp_input_grad(const void* sources, int num_sources, const float* params, const void* dz, int dz_slots,
+                            const float* rays_o, const float* rays_d, const float* z, const float* view_dirs,
+                            int64_t num_rows, int num_samples, int points_degree, int views_degree,
+                            float* g_points, float* g_views, void* stream);
+int srf_input_grad_source_bytes(void);
+
 /* ---- fused test-time ray march of one VM tensor (NDC), rows IX-XII + the weights half of VIII of SURVEY.md §8a in one kernel:
  * sample depths from the shared [num_samples] ladder (src/models/SimpleTensoRF09.py:363-376 at test time) -> points (:263) ->
  * box test (:705) -> alphaMask test (:707-710, :1342-1349) -> VM density (:1214-1239) -> alpha / transmittance / weights

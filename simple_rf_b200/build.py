@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / 'csrc'
 LIB = HERE / 'libsimple_rf_b200.so'
-SOURCES = ['rays_sampling.cu', 'composite.cu', 'nerf_mlp.cu', 'nerf_mlp_wgrad.cu', 'nerf_mlp_dgrad.cu', 'tensorf.cu', 'tensorf_march.cu', 'tensorf_surgery.cu', 'tensorf_cp.cu', 'losses.cu', 'optim.cu', 'batch.cu', 'output.cu']
+SOURCES = ['rays_sampling.cu', 'composite.cu', 'nerf_mlp.cu', 'nerf_mlp_wgrad.cu', 'nerf_mlp_dgrad.cu', 'nerf_mlp_input_grad.cu', 'tensorf.cu', 'tensorf_march.cu', 'tensorf_surgery.cu', 'tensorf_cp.cu', 'losses.cu', 'optim.cu', 'batch.cu', 'output.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 

@@ -121,10 +121,8 @@ class SimpleNeRF(torch.nn.Module):
         return out
 
     def _tables(self, device, intrinsics=None, extrinsics=None):
-        """Per-view K^-1 / c2w / focal tables for the raygen kernel (cameras are frozen in every shipped
-        config; learnable cameras would need gradients through ray generation, out of scope)."""
-        if self.extrinsics_learner.learn_rotation or self.extrinsics_learner.learn_translation:
-            raise NotImplementedError('learnable cameras are not supported by the fused ray generation')
+        """Per-view K^-1 / c2w / focal tables for the raygen kernel (cameras are frozen in every shipped config; with learnable
+        cameras and gradients enabled `_rays` attaches the rays to the learner's autograd graph instead, camera_grad.py)."""
         if intrinsics is not None:
             return ops.camera_tables(intrinsics, extrinsics, device)
         # keyed on the camera tensors' storage + version: load_state_dict() copies new cameras in place
@@ -135,6 +133,24 @@ class SimpleNeRF(torch.nn.Module):
             self._camera_tables = (key, ops.camera_tables(self.intrinsics_learner.initial_intrinsics,
                                                           self.extrinsics_learner.view_matrices(), device))
         return self._camera_tables[1]
+
+    def _rays(self, pixel_id, h, w):
+        """get_rays_tr + get_ndc_rays_tr + get_view_dirs_tr (SimpleNeRF17.py:170-190) in one launch.  Learnable cameras under autograd:
+        same kernel, same values, attached to the graph of ExtrinsicsLearner.forward (:817-842) so that r / t receive gradients."""
+        flags = dict(half_pixel=False, flip_x=False, ndc=self.ndc, viewdirs_from_ndc=False)
+        learner = self.extrinsics_learner
+        if torch.is_grad_enabled() and (learner.r.requires_grad or learner.t.requires_grad):
+            from .. import camera_grad
+            dev = pixel_id.device
+            k = self.intrinsics_learner.initial_intrinsics
+            key = (str(dev), k.data_ptr(), k._version)
+            if getattr(self, '_intrinsic_tables', None) is None or self._intrinsic_tables[0] != key:
+                k_inv, _, focal = ops.camera_tables(k, torch.eye(4)[None].expand(k.shape[0], 4, 4), dev)
+                self._intrinsic_tables = (key, k_inv, focal)
+            views = learner(torch.arange(learner.num_frames, device=dev))          # [V, 4, 4], differentiable w.r.t. r and t
+            return camera_grad.rays_with_camera_gradient(views, pixel_id, k, self._intrinsic_tables[1], self._intrinsic_tables[2], h, w,
+                                                         self.model_configs['near'], **flags)
+        return ops.raygen(pixel_id, self._tables(pixel_id.device), h, w, self.model_configs['near'], **flags)
 
     def render(self, input_dict: dict, *, retraw: bool, mode: str):
         """batchify_rays (SimpleNeRF17.py:133-157): chunks of `chunk` rays in training (keeps the
@@ -162,9 +178,7 @@ class SimpleNeRF(torch.nn.Module):
         R = pixel_id.shape[0]
         h, w = self.model_configs['resolution']
         out = {}
-        rays_o, rays_d, o_ndc, d_ndc, view_dirs = ops.raygen(
-            pixel_id, self._tables(dev), h, w, self.model_configs['near'], half_pixel=False, flip_x=False,
-            ndc=self.ndc, viewdirs_from_ndc=False)
+        rays_o, rays_d, o_ndc, d_ndc, view_dirs = self._rays(pixel_id, h, w)
         out['rays_o'], out['rays_d'] = rays_o, rays_d
         if self.ndc:
             out['rays_o_ndc'], out['rays_d_ndc'] = o_ndc, d_ndc
@@ -361,7 +375,8 @@ class MLP(torch.nn.Module):
         a differentiable call keeps the bf16 program, whose saved tiles the backward kernels read)."""
         params = self.named_param_dict()        # ONE walk of the module tree per call (it costs ~0.1 ms of host time)
         packed = self.packed(params)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params.values()):
+        rays_grad = any(t is not None and t.requires_grad for t in (rays_o, rays_d, view_dirs))        # learnable cameras
+        if torch.is_grad_enabled() and (rays_grad or any(p.requires_grad for p in params.values())):
             return _FusedMLP.apply(packed, rays_o, rays_d, z, view_dirs, noise, *[params[n] for n in packed.param_names])
         split = self.configs['model'].get('mlp_precision', 'bf16') == 'bf16x3'
         return packed.forward(rays_o, rays_d, z, view_dirs if packed.use_views else None, noise, split=split)
@@ -377,14 +392,19 @@ class _FusedMLP(torch.autograd.Function):
         ctx.packed = packed
         ctx.flat = packed.flat
         ctx.shapes = [p.shape for p in params]
-        ctx.save_for_backward(acts, sigma, rgb)
+        ctx.rays_grad = any(t is not None and t.requires_grad for t in (rays_o, rays_d, view_dirs))
+        ctx.save_for_backward(acts, sigma, rgb, *((rays_o, rays_d, z, view_dirs) if ctx.rays_grad else ()))
         return sigma, rgb
 
     @staticmethod
     def backward(ctx, g_sigma, g_rgb):
         from ..nerf_program import mlp_backward
-        acts, sigma, rgb = ctx.saved_tensors
-        flat_grad, _ = mlp_backward(ctx.packed, ctx.flat, acts, sigma, rgb, g_sigma, g_rgb)
+        acts, sigma, rgb, *rays = ctx.saved_tensors
+        flat_grad, dz = mlp_backward(ctx.packed, ctx.flat, acts, sigma, rgb, g_sigma, g_rgb)
+        g_o = g_d = g_v = None
+        if ctx.rays_grad:                   # learnable cameras: the gradient of the sample points / view directions (SimpleNeRF17.py:210-214)
+            from ..nerf_program import mlp_input_backward
+            g_o, g_d, g_v = mlp_input_backward(ctx.packed, ctx.flat, dz, *rays)
         grads, o = [], 0
         for shp in ctx.shapes:
             n = 1
@@ -392,7 +412,7 @@ class _FusedMLP(torch.autograd.Function):
                 n *= d
             grads.append(flat_grad[o:o + n].view(shp))
             o += n
-        return (None, None, None, None, None, None, *grads)
+        return (None, g_o, g_d, None, g_v, None, *grads)
 
 
 class IntrinsicsLearner(torch.nn.Module):

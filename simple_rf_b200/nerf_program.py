@@ -455,9 +455,16 @@ class DgradProgram(ctypes.Structure):
                 ('pad_', ctypes.c_int32), ('layers', DgradLayer * MAX_LAYERS)]
 
 
+class InputGradSource(ctypes.Structure):
+    """One layer that consumes an encoding image (csrc/nerf_mlp_input_grad.cu): its dZ images, its fp32 weight matrix in the flat
+    parameter vector, and which weight column every column of the encoding image multiplies."""
+    _fields_ = [('dz_slot', ctypes.c_int32), ('dz_images', ctypes.c_int32), ('in_total', ctypes.c_int32), ('target', ctypes.c_int32),
+                ('w_offset', ctypes.c_int64), ('cols', ctypes.c_int32 * 64)]
+
+
 class BackwardPlan:
     """Everything the dgrad / wgrad kernels need for one MLP variant (built once from the forward layer list)."""
-    __slots__ = ('program', 'dz_slots', 'items', 'gather_t', 'side_idx', '_dev', '_gather', '_side')
+    __slots__ = ('program', 'dz_slots', 'items', 'gather_t', 'side_idx', '_dev', '_gather', '_side', 'input_sources')
 
 
 def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
@@ -548,6 +555,17 @@ def build_backward_plan(layers, shapes, offs, zero, fwd_prog):
         items.append(WgradItem(0, 2, fwd_prog.layers[top].save_slot, 4, 4, 0, 256, 0, 256, 1,
                                offs['pts_output_linear.weight'], offs['pts_output_linear.bias']))
     plan.items = items
+    # ---- consumers of the encoding images (input gradients: only learnable cameras ask for them)
+    sources = []
+    for f in range(nl):
+        name, n, kbs, relu, write_h, head = layers[f]
+        for reg, cols in kbs:
+            if reg in (0, 5):
+                src = InputGradSource(dz_of[f], n // 64, shapes[name][1], 0 if reg == 0 else 1, offs[name])
+                for j in range(64):
+                    src.cols[j] = cols[j]
+                sources.append(src)
+    plan.input_sources = sources
     plan._dev = None
     return plan
 
@@ -574,3 +592,25 @@ def mlp_backward(packed, params_flat, acts, sigma, rgb, g_sigma, g_rgb):
     grads = torch.zeros(packed.flat_size, dtype=torch.float32, device=dev)
     run_wgrad(plan.items, acts, dz, grads)
     return grads, dz
+
+
+def mlp_input_backward(packed, params_flat, dz, rays_o, rays_d, z, view_dirs):
+    """Gradient of one fused-MLP evaluation w.r.t. what its sample points and view directions were built from (learnable cameras,
+    SimpleNeRF17.py:817-842): `dz` are the dZ images `mlp_backward` returned.  pts = o + z d, so
+    g_o = sum_s g_pts, g_d = sum_s z g_pts, g_view_dirs = sum_s g_views.  Returns (g_rays_o, g_rays_d, g_view_dirs or None), each [R, 3]."""
+    plan = packed.backward_plan
+    R, S = z.shape
+    rows = R * S
+    rays_o, rays_d, z = L.f32c(rays_o.detach()), L.f32c(rays_d.detach()), L.f32c(z.detach())
+    use_views = packed.use_views and view_dirs is not None
+    view_dirs = L.f32c(view_dirs.detach()) if use_views else None
+    g_pts = torch.empty((R, S, 3), dtype=torch.float32, device=z.device)
+    g_views = torch.empty((R, S, 3), dtype=torch.float32, device=z.device) if use_views else None
+    sources = plan.input_sources if use_views else [s for s in plan.input_sources if s.target == 0]
+    arr = (InputGradSource * len(sources))(*sources)
+    L.call('srf_nerf_mlp_input_grad', ctypes.addressof(arr), len(sources), L.ptr(params_flat), L.ptr(dz), dz.shape[1],
+           L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs), rows, S, int(packed.pdeg), int(packed.vdeg),
+           L.ptr(g_pts), L.ptr(g_views), L.stream_handle())
+    g_o = g_pts.sum(1)
+    g_d = (g_pts * z[..., None]).sum(1)
+    return g_o, g_d, (g_views.sum(1) if use_views else None)

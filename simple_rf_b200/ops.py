@@ -107,16 +107,17 @@ def sample_pdf_merge(z_coarse, weights, num_fine, u=None, philox_seed=0, return_
 # ------------------------------------------------------------------------------------------------
 class _Composite(torch.autograd.Function):
     """Outputs: alpha, visibility, weights, rgb_map, acc, depth, depth_var, depth_ndc, depth_var_ndc.
-    Differentiable w.r.t. sigma and rgb (depths and rays carry no gradient in the reference:
-    z_samples.detach(), SimpleNeRF17.py:368; frozen cameras)."""
+    Differentiable w.r.t. sigma and rgb by the hand-written backward kernel (sample depths carry no gradient in the reference:
+    z_samples.detach(), SimpleNeRF17.py:368).  With learnable cameras (SimpleNeRF17.py:817-842; no shipped config) the rays carry
+    gradient too: `_composite_ray_gradients` below adds the two places the rays enter compositing directly."""
 
     @staticmethod
     def forward(ctx, sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc, white_bkgd, distance_scale, per_sample):
         L.require_cuda(sigma, rgb, z, rays_o, rays_d, rays_d_ndc)
+        needs_grad = any(t is not None and t.requires_grad for t in (sigma, rgb, rays_o, rays_d, rays_d_ndc))
         sigma, rgb, z = L.f32c(sigma), L.f32c(rgb), L.f32c(z)
         rays_o, rays_d, rays_d_ndc = L.f32c(rays_o), L.f32c(rays_d), L.f32c(rays_d_ndc)
         R, S = sigma.shape
-        needs_grad = sigma.requires_grad or (rgb is not None and rgb.requires_grad)
         keep = per_sample or needs_grad
         weights = _empty((R, S), sigma)
         alpha = _empty((R, S), sigma) if keep else None
@@ -154,7 +155,45 @@ class _Composite(torch.autograd.Function):
                work=float(R) * S * (16 + (12 if gs[0] is not None else 0) + (12 if want_rgb else 0) + (4 if gs[6] is not None else 0)))
         if has_rgb and ctx.needs_input_grad[1] and g_rgb_s is None:
             g_rgb_s = torch.zeros((R, S, 3), dtype=torch.float32, device=sigma.device)
-        return g_sigma, g_rgb_s, None, None, None, None, None, None, None, None
+        g_o = g_d = g_dn = None
+        if any(ctx.needs_input_grad[3:6]):
+            g_o, g_d, g_dn = _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc, scale, g_sigma,
+                                                      g_depth=gs[2], g_depth_var=gs[4])
+        return g_sigma, g_rgb_s, None, g_o, g_d, g_dn, None, None, None, None
+
+
+def _ndc_to_world_depth(z_ndc, rays_o, rays_d):
+    """SimpleNeRF17.py:541-559 (near plane hard-coded to 1 there as well)."""
+    oz, dz = rays_o[..., 2:3], rays_d[..., 2:3]
+    tn = -(1 + oz) / dz
+    guard = torch.where(z_ndc == 1., 1e-3, 0.)
+    return (oz + tn * dz) / dz * (1 / (1 - z_ndc + guard) - 1) + tn
+
+
+def _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc, scale, g_sigma, g_depth, g_depth_var):
+    """Learnable cameras only: gradient of the compositing outputs w.r.t. the rays, sigma / rgb / z held fixed.  The rays enter in two places
+    (SimpleNeRF17.py:486-516): (1) delta = dists * |d| — alpha = 1 - exp(-sigma delta) is symmetric in sigma and |d|, so
+    dL/d|d| = sum_s g_sigma sigma / |d| with the g_sigma the backward kernel just produced for ALL outputs; (2) with NDC the world depths
+    z = convert_depth_from_ndc(z_ndc, rays_o, rays_d) under `depth` / `depth_var`.  [R, S] elementwise torch ops inside backward(): the
+    path exists for the test-time pose refinement of Tester07.py:62-111, not for training throughput."""
+    with torch.enable_grad():
+        ro = rays_o.detach().requires_grad_(True) if rays_o is not None else None
+        rd = rays_d.detach().requires_grad_(True)
+        rdn = rays_d_ndc.detach().requires_grad_(True) if (ndc and rays_d_ndc is not None) else None
+        norm = torch.norm(rdn if ndc else rd, dim=-1)
+        total = ((g_sigma * sigma).sum(-1) / norm.detach() * norm).sum()
+        if ndc and (g_depth is not None or g_depth_var is not None):
+            dists = torch.cat([z[:, 1:], torch.ones_like(z[:, :1])], -1) - z
+            weights = (1. - torch.exp(-sigma * dists * norm.detach()[:, None] * scale)) * vis
+            z_world = _ndc_to_world_depth(z, ro, rd)
+            depth = torch.sum(weights * z_world, dim=-1) / (acc + 1e-6)
+            if g_depth is not None:
+                total = total + (g_depth * depth).sum()
+            if g_depth_var is not None:
+                total = total + (g_depth_var * torch.sum(weights * torch.square(z_world - depth[..., None]), dim=-1)).sum()
+        wrt = [t for t in (ro, rd, rdn) if t is not None]
+        grads = dict(zip(map(id, wrt), torch.autograd.grad(total, wrt, allow_unused=True)))
+    return tuple(None if t is None else grads[id(t)] for t in (ro, rd, rdn))
 
 
 def composite(sigma, rgb, z, rays_o, rays_d, rays_d_ndc=None, *, ndc, white_bkgd=False, distance_scale=1.0,

@@ -1,0 +1,98 @@
+"""Learnable cameras, host-side pieces on the CPU (the kernels they sit next to are covered by tests/test_gpu_camera_grad.py):
+the differentiable ray restatement used by the backward of `_RaysFromCameras` and the ray gradients of compositing, both against
+autograd through the oracle's restatement of the reference (oracle/rays.py, oracle/composite.py)."""
+import pytest
+import torch
+
+from oracle import composite as OC
+from oracle import fixtures as FX
+from oracle import rays as RY
+
+
+def _cameras(golden_configs):
+    configs, mc = golden_configs('nerf')
+    return torch.tensor(mc['intrinsics']).float(), torch.tensor(mc['extrinsics']).float(), mc
+
+
+@pytest.mark.parametrize('flip_x,half_pixel,ndc,from_ndc', [(False, False, True, False), (True, True, True, True), (False, False, False, False)])
+def test_rays_from_cameras_matches_oracle(golden_configs, flip_x, half_pixel, ndc, from_ndc):
+    from simple_rf_b200 import camera_grad as CG
+    K, E, mc = _cameras(golden_configs)
+    h, w = mc['resolution']
+    pid = FX.random_pixels(257, K.shape[0], h, w, seed=3)
+    ro, rd, on, dn, vd = CG.rays_from_cameras(E, pid, K, h, w, mc['near'], half_pixel=half_pixel, flip_x=flip_x, ndc=ndc,
+                                              viewdirs_from_ndc=from_ndc)
+    ro_ref, rd_ref = RY.camera_rays(pid, K, E, half_pixel=half_pixel, flip_x=flip_x)
+    assert torch.equal(ro, ro_ref) and torch.allclose(rd, rd_ref, rtol=0, atol=1e-7)
+    if ndc:
+        img = pid[:, 0].long()
+        on_ref, dn_ref = RY.ndc_rays(ro_ref, rd_ref, h, w, K[img, 0, 0], K[img, 1, 1], mc['near'])
+        assert torch.allclose(on, on_ref, rtol=1e-6, atol=1e-6) and torch.allclose(dn, dn_ref, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(vd, RY.view_dirs(dn_ref if from_ndc else rd_ref), rtol=1e-6, atol=1e-6)
+    else:
+        assert on is None and dn is None
+        assert torch.allclose(vd, RY.view_dirs(rd_ref), rtol=1e-6, atol=1e-6)
+
+
+def test_rays_from_cameras_carries_gradient_to_the_pose_correction(golden_configs):
+    """r, t of the drop-in's ExtrinsicsLearner (SimpleNeRF17.py:817-842) receive the gradient autograd derives through the reference formulas."""
+    from simple_rf_b200 import camera_grad as CG
+    from simple_rf_b200.models.SimpleNeRF91 import ExtrinsicsLearner
+    K, E, mc = _cameras(golden_configs)
+    h, w = mc['resolution']
+    learner = ExtrinsicsLearner(E.numpy(), learn_rotation=True, learn_translation=True)
+    g = torch.Generator().manual_seed(1)
+    learner.r.data.copy_(torch.randn(learner.r.shape, generator=g) * 0.02)
+    learner.t.data.copy_(torch.randn(learner.t.shape, generator=g) * 0.05)
+    pid = FX.random_pixels(64, K.shape[0], h, w, seed=4)
+    views = learner(torch.arange(learner.num_frames))
+    outs = CG.rays_from_cameras(views, pid, K, h, w, mc['near'], half_pixel=False, flip_x=False, ndc=True, viewdirs_from_ndc=False)
+    probes = [torch.randn(o.shape, generator=g) for o in outs]
+    sum((o * p).sum() for o, p in zip(outs, probes)).backward()
+    got_r, got_t = learner.r.grad.clone(), learner.t.grad.clone()
+    # the same through the oracle's per-ray formulas on per-ray matrices, as the reference evaluates them (SimpleNeRF17.py:113-114, :170-176)
+    learner.zero_grad()
+    img = pid[:, 0].long()
+    per_ray = learner(img)
+    x = torch.cat([pid[:, 1:].float(), torch.ones(pid.shape[0], 1)], 1)
+    dirs = (torch.linalg.inv(K)[img] @ x[:, :, None])[:, :, 0] * torch.tensor([1., -1., -1.])
+    rd = (dirs[:, None, :] * per_ray[:, :3, :3]).sum(-1)
+    ro = per_ray[:, :3, 3]
+    on, dn = RY.ndc_rays(ro, rd, h, w, K[img, 0, 0], K[img, 1, 1], mc['near'])
+    ref = (ro, rd, on, dn, RY.view_dirs(rd))
+    sum((o * p).sum() for o, p in zip(ref, probes)).backward()
+    assert torch.allclose(got_r, learner.r.grad, rtol=1e-4, atol=1e-5) and torch.allclose(got_t, learner.t.grad, rtol=1e-4, atol=1e-5)
+    assert float(got_r.abs().max()) > 0 and float(got_t.abs().max()) > 0
+
+
+@pytest.mark.parametrize('ndc,scale', [(True, 1.0), (False, 1.0), (False, 25.0)])
+def test_composite_ray_gradients_match_autograd(ndc, scale):
+    """ops._composite_ray_gradients from the g_sigma of the backward kernel (here: autograd's) == autograd through the rays."""
+    from simple_rf_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    R, S = 33, 24
+    sigma = torch.relu(torch.randn(R, S, generator=g) * 3).double().requires_grad_()
+    rgb = torch.rand(R, S, 3, generator=g).double()
+    z = torch.sort(torch.rand(R, S, generator=g).double() * (0.98 if ndc else 4.0) + (0.0 if ndc else 2.0), dim=-1).values
+    rays_o = (torch.randn(R, 3, generator=g).double() * 0.3 - torch.tensor([0., 0., 0.5])).requires_grad_()
+    rays_d = (torch.randn(R, 3, generator=g).double() * 0.3 - torch.tensor([0., 0., 1.0])).requires_grad_()
+    rays_dn = (torch.randn(R, 3, generator=g).double() * 0.5 + torch.tensor([0., 0., 1.5])).requires_grad_() if ndc else None
+    out = OC.composite(sigma, rgb, z, rays_o, rays_d, rays_dn, ndc=ndc, distance_scale=scale)
+    keys = ['rgb', 'acc', 'depth', 'depth_var'] + (['depth_ndc', 'depth_var_ndc'] if ndc else [])
+    probes = {k: torch.randn(out[k].shape, generator=g).double() for k in keys}
+    probes['weights'] = torch.randn(R, S, generator=g).double()
+    loss = sum((out[k] * p).sum() for k, p in probes.items())
+    wrt = [sigma, rays_o, rays_d] + ([rays_dn] if ndc else [])
+    grads = torch.autograd.grad(loss, wrt, allow_unused=True)
+    g_sigma = grads[0]
+    got = ops._composite_ray_gradients(sigma.detach(), z, out['visibility'].detach(), rays_o.detach(), rays_d.detach(),
+                                       None if rays_dn is None else rays_dn.detach(), out['acc'].detach(), ndc, scale, g_sigma,
+                                       g_depth=probes['depth'], g_depth_var=probes['depth_var'])
+    want = [grads[1], grads[2], grads[3] if ndc else None]
+    for name, a, b in zip(('rays_o', 'rays_d', 'rays_d_ndc'), got, want):
+        if b is None:
+            assert a is None or float(a.abs().max()) == 0.0, name
+            continue
+        if a is None:
+            a = torch.zeros_like(b)
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-10), (name, float((a - b).abs().max()))
