@@ -306,7 +306,10 @@ int srf_dgrad_program_bytes(void);
  * g_enc[row, j] += sum_n dZ[row, n] W[n, cols[j]]; then the encoding backward
  * g_x[c] = g_enc[c] + sum_k 2^k (cos(2^k x_c) g_enc[3 + 6k + c] - sin(2^k x_c) g_enc[6 + 6k + c]).
  * Writes g_points [num_rows, 3] and g_views [num_rows, 3] (nullable when no source has target 1); rays_o / rays_d [num_rows / num_samples, 3],
- * z [num_rows] and view_dirs are the arrays srf_nerf_mlp_fwd was given.  Off the hot path of every shipped configuration (cameras frozen). */
+ * z [num_rows] and view_dirs are the arrays srf_nerf_mlp_fwd was given.  Rows mode (num_samples == 0: the TensoRF colour MLP of
+ * src/models/SimpleTensoRF09.py:1411-1421 fed by srf_mlp_rows_fwd; rays_o / rays_d / z may be NULL): no encoding, g_points[row, c] = g_enc[c]
+ * for the three weight columns a source maps to image columns 0..2 (the view directions behind the products); `count` (device,
+ * nullable) = number of valid rows, rows beyond it are written as zero.  Off the hot path of every shipped configuration (cameras frozen). */
 typedef struct {
   int32_t dz_slot, dz_images, in_total, target;   /* target 0: points encoding image, 1: view encoding image (32 columns) */
   int64_t w_offset;                               /* element offset of the weight matrix [64 * dz_images, in_total] in params */
@@ -314,7 +317,7 @@ typedef struct {
 } srf_input_grad_source;
 int srf_nerf_mlp_input_grad(const void* sources, int num_sources, const float* params, const void* dz, int dz_slots,
                             const float* rays_o, const float* rays_d, const float* z, const float* view_dirs,
-                            int64_t num_rows, int num_samples, int points_degree, int views_degree,
+                            int64_t num_rows, const int* count, int num_samples, int points_degree, int views_degree,
                             float* g_points, float* g_views, void* stream);
 int srf_input_grad_source_bytes(void);
 

@@ -58,7 +58,7 @@ _SIGNATURES = {
     'srf_wgrad_item_bytes': (c_int, []),
     'srf_nerf_mlp_dgrad': (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_int, _P, c_int, _P]),
     'srf_dgrad_program_bytes': (c_int, []),
-    'srf_nerf_mlp_input_grad': (c_int, [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    'srf_nerf_mlp_input_grad': (c_int, [_P, c_int, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, _P, _P, _P]),
     'srf_input_grad_source_bytes': (c_int, []),
     'srf_tv_loss': (c_int, [_P, _P, _P, c_int, c_float, _P, _P]),
     'srf_assemble_batch': (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

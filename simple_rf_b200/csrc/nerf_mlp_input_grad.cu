@@ -8,7 +8,9 @@
 //   g_enc[row, j]  = sum over the layers f that consume encoding column j:  sum_n dZ_f[row, n] * W_f[n, cols_f[j]]      (fp32 weights)
 //   g_x[c]         = g_enc[c] + sum_k 2^k ( cos(2^k x_c) g_enc[3 + 6k + c] - sin(2^k x_c) g_enc[6 + 6k + c] )            (encoding backward)
 //
-// with the encoding column order of the forward kernel (nerf_mlp.cu, encoding warps).  The encodings were rounded to bf16 for the tensor
+// with the encoding column order of the forward kernel (nerf_mlp.cu, encoding warps).  Rows mode (num_samples == 0, the TensoRF colour MLP whose
+// A operand is precomputed rows, SimpleTensoRF09.py:1411-1421): no encoding, g_points[row, c] = g_enc[c] of whatever three weight columns the
+// source maps to image columns 0..2 (the view directions behind the products), rows >= *count written as zero.  The encodings were rounded to bf16 for the tensor
 // cores; the derivative is taken of the unrounded encoding (straight-through), as the bf16 weight operands are in the other kernels.
 #include <cuda_bf16.h>
 
@@ -37,6 +39,7 @@ struct InputGradParams {
   int dz_slots;
   const float* rays_o; const float* rays_d; const float* z; const float* view_dirs;
   long long total;
+  const int* count;     // device, nullable: number of valid rows (the buffers are sized for a worst case)
   int S, points_degree, views_degree;
   float* g_points; float* g_views;
   long long num_tiles;
@@ -84,7 +87,19 @@ __device__ __forceinline__ float encoding_backward(const float (&g)[N], int c, f
 __global__ void __launch_bounds__(IG_THREADS) nerf_mlp_input_grad_kernel(const __grid_constant__ InputGradParams p) {
   __shared__ __align__(16) float ws[64][64];          // one 64-unit slice of a weight matrix, columns mapped to encoding columns
   const int row = threadIdx.x;
+  const long long valid_rows = p.count != nullptr ? min((long long)__ldg(p.count), p.total) : p.total;
   for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    if (tile * 128 >= valid_rows) {                    // nothing but padding: the dZ images of such tiles were never written
+      const long long m = tile * 128 + row;
+      if (m < p.total) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          p.g_points[m * 3 + c] = 0.f;
+          if (p.g_views != nullptr) p.g_views[m * 3 + c] = 0.f;
+        }
+      }
+      continue;
+    }
     float ge[64], gv[32];
 #pragma unroll
     for (int i = 0; i < 64; ++i) ge[i] = 0.f;
@@ -107,7 +122,13 @@ __global__ void __launch_bounds__(IG_THREADS) nerf_mlp_input_grad_kernel(const _
       }
     }
     const long long m = tile * 128 + row;
-    if (m < p.total) {
+    if (m < p.total && (p.S == 0 || m >= valid_rows)) {        // rows mode: the mapped columns as they are; padding rows: zero
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        p.g_points[m * 3 + c] = m < valid_rows ? ge[c] : 0.f;
+        if (p.g_views != nullptr) p.g_views[m * 3 + c] = m < valid_rows ? gv[c] : 0.f;
+      }
+    } else if (m < p.total) {
       const long long r = m / p.S;
       const float zz = p.z[m];
 #pragma unroll
@@ -131,13 +152,14 @@ SRF_API int srf_input_grad_source_bytes(void) { return (int)sizeof(InputGradSour
 
 SRF_API int srf_nerf_mlp_input_grad(const void* sources, int num_sources, const float* params, const void* dz, int dz_slots,
                                     const float* rays_o, const float* rays_d, const float* z, const float* view_dirs,
-                                    int64_t num_rows, int num_samples, int points_degree, int views_degree,
+                                    int64_t num_rows, const int* count, int num_samples, int points_degree, int views_degree,
                                     float* g_points, float* g_views, void* stream) {
   const char* where = "srf_nerf_mlp_input_grad";
   if (num_rows == 0) return 0;
-  SRF_REQUIRE(sources && params && dz && rays_o && rays_d && z && g_points, where, "null pointer");
+  SRF_REQUIRE(sources && params && dz && g_points, where, "null pointer");
+  SRF_REQUIRE(num_samples == 0 || (rays_o && rays_d && z), where, "rays_o, rays_d, z required unless num_samples == 0 (rows mode)");
   SRF_REQUIRE(num_sources >= 1 && num_sources <= IG_MAX_SOURCES, where, "1..6 encoding consumers expected");
-  SRF_REQUIRE(num_samples >= 1 && num_rows % num_samples == 0, where, "rows must be rays x samples");
+  SRF_REQUIRE(num_samples >= 0 && (num_samples == 0 || num_rows % num_samples == 0), where, "rows must be rays x samples");
   SRF_REQUIRE(points_degree >= 0 && points_degree <= 10 && views_degree <= 4, where, "encoding degree out of range (points <= 10, views <= 4)");
   SRF_REQUIRE((g_views == nullptr) || (view_dirs != nullptr && views_degree >= 0), where, "g_views needs view_dirs and a view encoding");
   InputGradParams p{};
@@ -158,7 +180,7 @@ SRF_API int srf_nerf_mlp_input_grad(const void* sources, int num_sources, const 
   SRF_REQUIRE(!any_view || g_views != nullptr, where, "a view-encoding consumer needs g_views");
   p.num_sources = num_sources; p.params = params; p.dz = reinterpret_cast<const uint8_t*>(dz); p.dz_slots = dz_slots;
   p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.view_dirs = view_dirs;
-  p.total = num_rows; p.S = num_samples; p.points_degree = points_degree; p.views_degree = views_degree < 0 ? 0 : views_degree;
+  p.total = num_rows; p.count = count; p.S = num_samples; p.points_degree = points_degree; p.views_degree = views_degree < 0 ? 0 : views_degree;
   p.g_points = g_points; p.g_views = g_views;
   p.num_tiles = (num_rows + 127) / 128;
   long long grid = (long long)sm_count() * 8;

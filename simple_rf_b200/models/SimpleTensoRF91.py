@@ -132,9 +132,30 @@ class SimpleTensoRF(torch.nn.Module):
         for t in self._tensors():
             t.run_model_modifications(iter_num)
 
+    def _rays(self, pixel_id, h, w):
+        """get_rays_tr (+0.5 px, x flip) + get_ndc_rays_tr + get_view_dirs_tr (SimpleTensoRF09.py:205-239) in one launch.  Learnable cameras under
+        autograd: same kernel, same values, attached to the graph of ExtrinsicsLearner.forward (camera_grad.py); the gradient reaches the pose
+        through the view directions of the colour MLP, |d| under delta and the NDC -> world depths (the grid coordinates are detached upstream,
+        :1054, :1075)."""
+        ndc = self.ndc
+        flags = dict(half_pixel=True, flip_x=True, ndc=ndc, viewdirs_from_ndc=ndc)
+        learner = self.extrinsics_learner
+        if torch.is_grad_enabled() and (learner.r.requires_grad or learner.t.requires_grad):
+            if not ndc:
+                raise NotImplementedError('learnable cameras without NDC: the box-march depths (SimpleTensoRF09.py:388-400) depend on the rays')
+            from .. import camera_grad
+            dev = pixel_id.device
+            k = self.intrinsics_learner.initial_intrinsics
+            key = (str(dev), k.data_ptr(), k._version)
+            if getattr(self, '_intrinsic_tables', None) is None or self._intrinsic_tables[0] != key:
+                k_inv, _, focal = ops.camera_tables(k, torch.eye(4)[None].expand(k.shape[0], 4, 4), dev)
+                self._intrinsic_tables = (key, k_inv, focal)
+            views = learner(torch.arange(learner.num_frames, device=dev))
+            return camera_grad.rays_with_camera_gradient(views, pixel_id, k, self._intrinsic_tables[1], self._intrinsic_tables[2], h, w,
+                                                         self.model_configs['near'], **flags)
+        return ops.raygen(pixel_id, self._tables(pixel_id.device), h, w, self.model_configs['near'], **flags)
+
     def _tables(self, device, intrinsics=None, extrinsics=None):
-        if self.extrinsics_learner.learn_rotation or self.extrinsics_learner.learn_translation:
-            raise NotImplementedError('learnable cameras are not supported by the fused ray generation')
         if intrinsics is not None:
             return ops.camera_tables(intrinsics, extrinsics, device)
         # keyed on the camera tensors' storage + version: load_state_dict() copies new cameras in place
@@ -168,9 +189,7 @@ class SimpleTensoRF(torch.nn.Module):
         R = pixel_id.shape[0]
         h, w = self.model_configs['resolution']
         ndc = self.ndc
-        rays_o, rays_d, o_ndc, d_ndc, view_dirs = ops.raygen(
-            pixel_id, self._tables(dev), h, w, self.model_configs['near'], half_pixel=True, flip_x=True, ndc=ndc,
-            viewdirs_from_ndc=ndc)
+        rays_o, rays_d, o_ndc, d_ndc, view_dirs = self._rays(pixel_id, h, w)
         if mode == 'static_camera':                                          # SimpleTensoRF09.py:222-233
             cd = input_dict['common_data']
             pose = cd['processed_view_pose']
@@ -328,6 +347,7 @@ class _VmColor(torch.autograd.Function):
         packed = predictor.packed(basis)
         rgb, acts = packed.forward(rows, comp.count, rows.shape[0], save=True)
         ctx.packed, ctx.flat, ctx.geom, ctx.comp, ctx.tables, ctx.n_planes = packed, packed.flat, geom, comp, tables, n_planes
+        ctx.view_grad = (view_dirs.shape[0], geom.z.shape[1]) if (view_dirs is not None and view_dirs.requires_grad and packed.num_view == 3) else None
         ctx.save_for_backward(rgb, acts, basis, mlp[0])
         return rgb
 
@@ -335,7 +355,13 @@ class _VmColor(torch.autograd.Function):
     def backward(ctx, g_rgb):
         rgb, acts, basis, w0 = ctx.saved_tensors
         packed = ctx.packed
-        g_flat, g_rows = packed.backward(acts, rgb, g_rgb, rgb.shape[0], flat=ctx.flat, count=ctx.comp.count)
+        g_flat, g_rows, dz = packed.backward(acts, rgb, g_rgb, rgb.shape[0], flat=ctx.flat, count=ctx.comp.count, return_dz=True)
+        g_view = None
+        if ctx.view_grad is not None:     # learnable cameras: every surface sample hands its view-direction gradient to its ray
+            num_rays, num_samples = ctx.view_grad
+            per_row = packed.view_dirs_backward(dz, rgb.shape[0], flat=ctx.flat, count=ctx.comp.count)       # zero beyond the count
+            ray = torch.div(ctx.comp.idx[:per_row.shape[0]].long(), num_samples, rounding_mode='floor').clamp_(0, num_rays - 1)
+            g_view = torch.zeros((num_rays, 3), dtype=torch.float32, device=per_row.device).index_add_(0, ray, per_row)
         if ctx.n_planes == 0:
             g_tensor = T.cp_color_rows_backward(ctx.geom, ctx.comp, ctx.tables, g_rows)
         else:
@@ -343,7 +369,7 @@ class _VmColor(torch.autograd.Function):
             g_tensor = [*gp, *gl]
         g_w0, g_basis = packed.split_first_layer_grad(g_flat, w0.detach().float(), basis.detach().float())
         g_mlp = [g_w0] + [packed.grad_of(g_flat, nm) for nm in packed.names[1:]]
-        return (None, None, None, None, None, g_basis, *g_tensor, *g_mlp)
+        return (None, None, None, g_view, None, g_basis, *g_tensor, *g_mlp)
 
 
 def get_tensor_model(name, configs, tensor_configs, model_configs):
@@ -462,7 +488,7 @@ class LowRankTensor(torch.nn.Module):
         basis = self.basis_matrix_color.weight
         factors = self.color_factors()                                      # planes then lines (VM) / the three lines (CP)
         color_params = [*factors, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)]]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in [basis] + color_params):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in [basis, rays['view_dirs']] + color_params):
             rgb_rows = _VmColor.apply(cp, geom, surface, rays['view_dirs'], self.num_color_planes, basis, *color_params)
         else:
             rows, _ = self.color_rows(geom, surface, rays['view_dirs'])

@@ -375,7 +375,7 @@ class PackedRowsMLP:
                L.stream_handle(), work=(count, 2.0 * self.macs_per_row) if count is not None else 2.0 * self.macs_per_row * max_rows)
         return (rgb, acts) if save else rgb
 
-    def backward(self, acts, rgb, g_rgb, num_rows, flat=None, count=None):
+    def backward(self, acts, rgb, g_rgb, num_rows, flat=None, count=None, return_dz=False):
         """Hand-written backward on the tensor cores (nerf_mlp_dgrad.cu / nerf_mlp_wgrad.cu) of a forward(save=True) over
         num_rows rows (count: device int32[1] with the number of valid rows when num_rows is a worst-case capacity): returns (flat gradient in the layout [W0' | b0 | W1 | b1 | W2 | b2], g_rows fp32
         [num_rows, pitch4] whose first num_products columns are d loss / d product rows)."""
@@ -397,7 +397,22 @@ class PackedRowsMLP:
                work=2.0 * (2 * self.units * self.units) * num_rows)
         grads = torch.zeros(self.flat_size, dtype=torch.float32, device=dev)
         run_wgrad(plan.items, acts, dz, grads, count=count)
-        return grads, g_rows
+        return (grads, g_rows, dz) if return_dz else (grads, g_rows)
+
+    def view_dirs_backward(self, dz, num_rows, flat=None, count=None):
+        """d loss / d view_dirs per ROW [num_rows, 3] (zero beyond `count`) from the dZ0 images `backward(return_dz=True)` left in HBM:
+        dZ0 W0'[:, sum(C):sum(C)+3] (learnable cameras only: the view directions are what ties the colour branch to the pose,
+        SimpleTensoRF09.py:236-239, :1417-1418)."""
+        assert self.num_view == 3
+        flat = self.flat if flat is None else flat
+        src = InputGradSource(4, self.units // 64, self.in_cols, 0, self.offs[self.names[0]])
+        for j in range(64):
+            src.cols[j] = self.num_products + j if j < 3 else -1
+        arr = (InputGradSource * 1)(src)
+        g = torch.empty((max(num_rows, 1), 3), dtype=torch.float32, device=dz.device)
+        L.call('srf_nerf_mlp_input_grad', ctypes.addressof(arr), 1, L.ptr(flat), L.ptr(dz), dz.shape[1], None, None, None, None,
+               num_rows, L.ptr(count), 0, 0, -1, L.ptr(g), None, L.stream_handle())
+        return g
 
     def split_first_layer_grad(self, g_flat, w0, basis):
         """(dW0, dB) from dW0' = d loss / d [W0[:, :F] B | W0[:, F:]] (chain rule through composed_first_layer)."""
@@ -609,7 +624,7 @@ def mlp_input_backward(packed, params_flat, dz, rays_o, rays_d, z, view_dirs):
     sources = plan.input_sources if use_views else [s for s in plan.input_sources if s.target == 0]
     arr = (InputGradSource * len(sources))(*sources)
     L.call('srf_nerf_mlp_input_grad', ctypes.addressof(arr), len(sources), L.ptr(params_flat), L.ptr(dz), dz.shape[1],
-           L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs), rows, S, int(packed.pdeg), int(packed.vdeg),
+           L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(view_dirs), rows, None, S, int(packed.pdeg), int(packed.vdeg),
            L.ptr(g_pts), L.ptr(g_views), L.stream_handle())
     g_o = g_pts.sum(1)
     g_d = (g_pts * z[..., None]).sum(1)

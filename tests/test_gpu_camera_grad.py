@@ -95,3 +95,98 @@ def test_learnable_cameras_pose_gradients_vs_reference_trainer():
                                        't_grad_reference': ref_grads['extrinsics_learner.t'].tolist(),
                                        't_grad_dropin': my_grads['extrinsics_learner.t'].tolist()})
     print('pose-correction gradients rel-L2:', {k: v for k, v in rels.items() if 'extrinsics' in k}, 'worst', max(rels.values()))
+
+
+def test_tensorf_learnable_cameras_pose_gradients_vs_reference_trainer():
+    """Simple-TensoRF (NDC): the pose correction receives its gradient through the view directions of the colour MLP, |d| under delta and the
+    NDC -> world depths (grid coordinates are detached upstream, SimpleTensoRF09.py:1054, :1075).  One unmodified `train_one_iter`, every
+    gradient incl. r / t against the reference's eager autograd."""
+    from simple_rf_b200.dropin import callers as C
+    if not C.available():
+        pytest.skip('upstream tree not installed (tools/install_reference.sh)')
+    from test_gpu_reference_callers import _compare_curves, _compare_grads, _report, _run_trainer, _tensorf_configs
+    raw = C.synthetic_raw_data('re10k', 3, resolution=(144, 256), sparse_points=600, seed=9, tensorf=True)
+    cfg_ref = _tensorf_configs()
+    cfg_ref['model']['learn_camera_rotation'] = True
+    cfg_ref['model']['learn_camera_translation'] = True
+    cfg_mine = C.use_dropin(cfg_ref)
+
+    def perturb(module):
+        g = torch.Generator().manual_seed(15)
+        lr = module.extrinsics_learner
+        lr.r.data.copy_((torch.randn(lr.r.shape, generator=g) * 0.01).to(lr.r.device))
+        lr.t.data.copy_((torch.randn(lr.t.shape, generator=g) * 0.02).to(lr.t.device))
+
+    ref_curve, ref_grads, _, _, _ = _run_trainer(cfg_ref, raw, 1, prepare=perturb)
+    my_curve, my_grads, my_model, _, _ = _run_trainer(cfg_mine, raw, 1, prepare=perturb)
+    assert type(my_model.module).__module__.startswith('simple_rf_b200.models')
+    for name in ('extrinsics_learner.r', 'extrinsics_learner.t'):
+        assert name in ref_grads and float(ref_grads[name].norm()) > 0, name
+    worst = _compare_curves(ref_curve, my_curve, tol=5e-3)
+    rels = _compare_grads(ref_grads, my_grads, tol=0.1)
+    _report('tensorf_learnable_cameras', {'loss_deviation': worst, 'gradient_relative_l2': rels,
+                                          'r_grad_reference': ref_grads['extrinsics_learner.r'].tolist(),
+                                          'r_grad_dropin': my_grads['extrinsics_learner.r'].tolist(),
+                                          't_grad_reference': ref_grads['extrinsics_learner.t'].tolist(),
+                                          't_grad_dropin': my_grads['extrinsics_learner.t'].tolist()})
+    print('pose-correction gradients rel-L2:', {k: v for k, v in rels.items() if 'extrinsics' in k}, 'worst', max(rels.values()))
+
+
+def _refine_pose(cfg, mc, state, raw, seed, iterations):
+    """The reference's UNMODIFIED `NerfTester.optimize_test_camera_params` (src/Tester07.py:62-125) on view 1 of the scene, starting from a
+    perturbed pose: -> (pose before, pose after)."""
+    import numpy
+    from simple_rf_b200.dropin import callers as C
+    C.prepare()
+    import Trainer10
+    tester = C.make_tester(cfg, mc, cfg['device'])
+    tester.model.load_state_dict(state)
+    tester.test_configs['optimize_camera_params'] = {'num_iterations': iterations}
+    nd = raw['nerf_data']
+    poses, ks = numpy.asarray(nd['extrinsics'], dtype=numpy.float64), numpy.asarray(nd['intrinsics'], dtype=numpy.float64)
+    noisy = poses.copy()
+    c, s = numpy.cos(0.02), numpy.sin(0.02)
+    noisy[1] = noisy[1] @ numpy.array([[c, -s, 0, 0.03], [s, c, 0, -0.02], [0, 0, 1, 0.01], [0, 0, 0, 1]])
+    Trainer10.init_seeds(seed)
+    _, after = tester.optimize_test_camera_params(numpy.asarray(nd['images'])[1], ks[1], poses[1], poses, noisy)
+    return after
+
+
+def _pose_refinement_configs(device):
+    from test_gpu_reference_callers import _nerf_configs
+    cfg = _nerf_configs()
+    cfg['device'] = device
+    cfg['model']['learn_camera_rotation'] = True
+    cfg['model']['learn_camera_translation'] = True
+    main = next(o for o in cfg['optimizers'] if o['name'] == 'optimizer_main')
+    cfg['optimizers'].append(dict(main, name='optimizer_extrinsics', lr_initial=1e-3))
+    return cfg
+
+
+def test_test_time_pose_refinement_through_unmodified_tester():
+    """`NerfTester.optimize_test_camera_params` (src/Tester07.py:62-125: test-optimization preprocessor, `rebuild_camera_params_learners`,
+    whole-image batches in `mode='test_camera_params_optimization'`, an Adam optimiser over r / t, `mode='camera_params_only'` read-back)
+    drives the drop-in and the reference model from the same briefly trained weights.  Adam's first steps are sign steps of size lr, so
+    the two refined poses are compared through the direction they moved in and the worst-case bound of a flipped sign."""
+    import numpy
+    from simple_rf_b200.dropin import callers as C
+    if not C.available():
+        pytest.skip('upstream tree not installed (tools/install_reference.sh)')
+    from test_gpu_reference_callers import _report, _run_trainer
+    raw = C.synthetic_raw_data('llff', 3, resolution=(126, 168), sparse_points=400, seed=6)
+    cfg_ref = _pose_refinement_configs([0])
+    cfg_mine = C.use_dropin(cfg_ref)
+    _, _, model, mc, _ = _run_trainer(cfg_mine, raw, 60)                 # a field with some structure, trained by the drop-in
+    state = copy.deepcopy(model.state_dict())
+    iterations, lr = 4, 1e-3
+    after_ref = _refine_pose(copy.deepcopy(cfg_ref), mc, state, raw, 21, iterations)
+    after_mine = _refine_pose(copy.deepcopy(cfg_mine), mc, state, raw, 21, iterations)
+    before = _refine_pose(copy.deepcopy(cfg_mine), mc, state, raw, 21, 0)
+    move_ref, move_mine = (after_ref - before)[:3].reshape(-1), (after_mine - before)[:3].reshape(-1)
+    assert float(numpy.abs(move_ref).max()) > 0.5 * lr and float(numpy.abs(move_mine).max()) > 0.5 * lr, 'the pose did not move'
+    cosine = float(move_ref @ move_mine / (numpy.linalg.norm(move_ref) * numpy.linalg.norm(move_mine)))
+    worst = float(numpy.abs(after_ref - after_mine).max())
+    _report('nerf_pose_refinement', {'before': before.tolist(), 'after_reference': after_ref.tolist(), 'after_dropin': after_mine.tolist(),
+                                     'cosine_of_moves': cosine, 'max_abs_difference': worst})
+    print('pose refinement: cosine of the two moves', cosine, 'max |difference|', worst)
+    assert cosine >= 0.7 and worst <= 2.5 * lr * iterations, (cosine, worst)

@@ -127,7 +127,8 @@ def test_vm_color_rows_and_mlp(golden_configs):
     wts = torch.rand(a['z'].shape, generator=g) ** 6
     surf = wts > 1e-4
     prods = TF.vm_color_products(params, pn[surf])
-    vd = a['vd'][:, None].expand(pts.shape)[surf]
+    vd_leaf = a['vd'].clone().requires_grad_()       # learnable cameras: the view directions carry gradient (SimpleTensoRF09.py:236-239)
+    vd = vd_leaf[:, None].expand(pts.shape)[surf]
     up = torch.rand(prods.shape, generator=g)
     (prods * up).sum().backward()
     gref_tables = {k: params[k].grad.clone() for k in params if k.startswith(('matrices_color', 'vectors_color'))}
@@ -146,7 +147,7 @@ def test_vm_color_rows_and_mlp(golden_configs):
     # products are computed in fp32 and rounded once to bf16 (2^-9 relative), view directions likewise
     ref_b = prods.detach()
     assert ((rows[:n, :CT].float().cpu() - ref_b).abs() <= 2.0 ** -8 * ref_b.abs() + 1e-6).all()
-    assert torch.equal(rows[:n, CT:CT + 3].cpu(), vd.to(torch.bfloat16))
+    assert torch.equal(rows[:n, CT:CT + 3].cpu(), vd.detach().to(torch.bfloat16))
     assert (rows[:n, CT + 3:] == 0).all()
     g_rows = torch.zeros((rows.shape[0], CT), device=DEV)
     g_rows[:n] = up.to(DEV)
@@ -168,7 +169,8 @@ def test_vm_color_rows_and_mlp(golden_configs):
     mlp_params = [dict(cp.named_parameters())[nm] for nm in names]
     for nm, p_ in zip(names, mlp_params):
         dp[f'color_predictor.{nm}'] = p_
-    rgb = _VmColor.apply(cp, geom, comp, a['vd'].to(DEV), 3, dp['basis_matrix_color.weight'], *planes, *lines, *mlp_params)
+    vd_dev = a['vd'].to(DEV).requires_grad_()
+    rgb = _VmColor.apply(cp, geom, comp, vd_dev, 3, dp['basis_matrix_color.weight'], *planes, *lines, *mlp_params)
     err = (rgb[:n].cpu() - rgb_ref.detach()).abs().max().item()
     print('colour branch max abs err', err)
     assert err <= MLP_TOL
@@ -187,6 +189,10 @@ def test_vm_color_rows_and_mlp(golden_configs):
         # (measured: 0.2-2.8 % rel-L2 here, up to 5 % on the sparsely hit augmentation tensor of the model test)
         print(k, round(err, 4), round(l2, 4))
         assert err <= 1.5e-1 and l2 <= 8e-2, (k, err, l2)
+    # per-ray view-direction gradient (srf_nerf_mlp_input_grad in rows mode + the row -> ray reduction): same stated bound
+    l2 = ((vd_dev.grad.cpu() - vd_leaf.grad).norm() / vd_leaf.grad.norm()).item()
+    print('view_dirs', round(l2, 4))
+    assert float(vd_leaf.grad.norm()) > 0 and l2 <= 8e-2, l2
 
 
 def _model(golden_configs, g):
