@@ -32,3 +32,5 @@ run surgery racecheck 240 tests/test_gpu_surgery.py -k "not full_size and not 48
 run mlp racecheck 240 tests/test_gpu_nerf_mlp.py -k "37-64 or 41-64 or 1-1"
 run cp_tensor memcheck 300 tests/test_gpu_tensorf_cp.py
 run cp_tensor racecheck 300 tests/test_gpu_tensorf_cp.py -k "density or color_rows or schedule"
+run camera_grad memcheck 300 tests/test_gpu_camera_grad.py tests/test_gpu_tensorf.py -k "input_gradients or struct or color_rows_and_mlp"
+run camera_grad racecheck 300 tests/test_gpu_camera_grad.py -k "input_gradients and main"
