@@ -750,11 +750,100 @@ def golden_surgery(cp=False):
           f'-> {geo["resolution"].tolist()}, second mask {vol2.mean():.3f} occupied)')
 
 
+def _pose_probe(num_views, seed):
+    """A small non-zero pose correction (axis-angle r, translation t) for every view."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(num_views, 3, generator=g) * 0.01, torch.randn(num_views, 3, generator=g) * 0.02
+
+
+def _probe_loss(out, keys, seed):
+    """A fixed random linear functional of the listed outputs (so that every one of them contributes to the pose gradient)."""
+    g = torch.Generator().manual_seed(seed)
+    return sum((out[k] * torch.randn(out[k].shape, generator=g)).sum() for k in keys)
+
+
+def golden_learnable_cameras():
+    """Learnable cameras (`learn_camera_rotation / learn_camera_translation`, SimpleNeRF17.py:817-842; no shipped run turns them on): the
+    gradient of a fixed linear functional of the rendered maps w.r.t. the pose correction r, t, through the unmodified reference models in
+    training mode (Simple-NeRF: NDC, coarse + fine + augmentations; Simple-TensoRF: NDC, main + augmentation tensor)."""
+    from . import rays as RY
+    fixtures = {}
+    # ---- Simple-NeRF
+    configs, model_configs = H.load_configs(1142, 'fern')
+    model_configs = H.shrink(model_configs, 4)
+    configs['model']['netchunk'] = 2048
+    configs['model']['learn_camera_rotation'] = True
+    configs['model']['learn_camera_translation'] = True
+    model = H.build_model(configs, model_configs)
+    sets = FX.nerf_param_sets(configs, seed=11)
+    load_nerf_params(model, sets)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    r0, t0 = _pose_probe(nviews, 31)
+    model.extrinsics_learner.r.data.copy_(r0)
+    model.extrinsics_learner.t.data.copy_(t0)
+    pixel_id = FX.random_pixels(40, nviews, h, w, 9)
+    keys = ('rgb_coarse', 'rgb_fine', 'depth_coarse', 'depth_fine', 'depth_ndc_fine', 'acc_fine', 'rays_o', 'rays_d_ndc', 'view_dirs')
+    model.train(True)
+    torch.manual_seed(909)
+    ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+    _probe_loss(ref, keys, 77).backward()
+    g_r, g_t = model.extrinsics_learner.r.grad.clone(), model.extrinsics_learner.t.grad.clone()
+    r1, t1 = r0.clone().requires_grad_(), t0.clone().requires_grad_()
+    torch.manual_seed(909)
+    mine = P.nerf_render_chunk(sets, configs, model_configs, pixel_id, training=True,
+                               extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r1, t1))
+    _probe_loss(mine, keys, 77).backward()
+    _check('learnable_cameras/nerf/rgb_fine', ref['rgb_fine'].detach(), mine['rgb_fine'].detach(), exact=False, tol=2e-6)
+    _check('learnable_cameras/nerf/r.grad', g_r, r1.grad, exact=False, tol=1e-4 * float(g_r.abs().max()))
+    _check('learnable_cameras/nerf/t.grad', g_t, t1.grad, exact=False, tol=1e-4 * float(g_t.abs().max()))
+    fixtures.update({'nerf_pixel_id': pixel_id, 'nerf_r': r0, 'nerf_t': t0, 'nerf_r_grad': g_r, 'nerf_t_grad': g_t,
+                     'nerf_rgb_fine': ref['rgb_fine'].detach(), 'nerf_depth_fine': ref['depth_fine'].detach()})
+    print(f'learnable cameras, Simple-NeRF: |r.grad| {float(g_r.norm()):.4f} |t.grad| {float(g_t.norm()):.4f}, oracle == reference')
+    # ---- Simple-TensoRF (NDC)
+    configs, model_configs = H.load_configs(212, '00000')
+    model_configs = H.shrink(model_configs, 4)
+    configs['model']['coarse_model']['num_voxels_initial'] = 40 ** 3
+    configs['model']['augmentations'][0]['coarse_model']['num_voxels_initial'] = 20 ** 3
+    configs['model']['learn_camera_rotation'] = True
+    configs['model']['learn_camera_translation'] = True
+    model = H.build_model(configs, model_configs)
+    sets = FX.tensorf_sets(configs, seed=21, with_alpha=False)
+    load_tensorf_params(model, sets)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    r0, t0 = _pose_probe(nviews, 32)
+    model.extrinsics_learner.r.data.copy_(r0)
+    model.extrinsics_learner.t.data.copy_(t0)
+    pixel_id = FX.random_pixels(32, nviews, h, w, 10)
+    keys = ('rgb_coarse', 'depth_coarse', 'depth_ndc_coarse', 'acc_coarse', 'view_dirs', 'rays_d')
+    model.train(True)
+    torch.manual_seed(910)
+    ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+    _probe_loss(ref, keys, 78).backward()
+    g_r, g_t = model.extrinsics_learner.r.grad.clone(), model.extrinsics_learner.t.grad.clone()
+    r1, t1 = r0.clone().requires_grad_(), t0.clone().requires_grad_()
+    torch.manual_seed(910)
+    mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=True,
+                                  extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r1, t1))
+    _probe_loss(mine, keys, 78).backward()
+    _check('learnable_cameras/tensorf/rgb', ref['rgb_coarse'].detach(), mine['rgb_coarse'].detach(), exact=False, tol=2e-6)
+    _check('learnable_cameras/tensorf/r.grad', g_r, r1.grad, exact=False, tol=1e-4 * float(g_r.abs().max()))
+    _check('learnable_cameras/tensorf/t.grad', g_t, t1.grad, exact=False, tol=1e-4 * float(g_t.abs().max()))
+    fixtures.update({'tensorf_pixel_id': pixel_id, 'tensorf_r': r0, 'tensorf_t': t0, 'tensorf_r_grad': g_r, 'tensorf_t_grad': g_t,
+                     'tensorf_rgb': ref['rgb_coarse'].detach(), 'tensorf_depth': ref['depth_coarse'].detach()})
+    print(f'learnable cameras, Simple-TensoRF: |r.grad| {float(g_r.norm()):.4f} |t.grad| {float(g_t.norm()):.4f}, oracle == reference')
+    np.savez_compressed(OUT / 'learnable_cameras.npz', **_np(fixtures))
+
+
 def main():
     if not H.available():
         sys.exit('reference checkout not available: goldens can only be regenerated in the build container')
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if 'learnable_cameras' in sys.argv[1:]:
+        golden_learnable_cameras()
+        return
     if 'nerf_variants' in sys.argv[1:]:
         golden_nerf_variants()
         return
@@ -781,6 +870,7 @@ def main():
     golden_surgery(cp=True)
     golden_nerf_variants()
     golden_tensorf_variants()
+    golden_learnable_cameras()
 
 
 if __name__ == '__main__':

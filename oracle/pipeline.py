@@ -35,14 +35,15 @@ def _run_mlp_chunked(params, cfg, pts, view_dirs, netchunk, noise_std, training)
     return {k: torch.cat(v, 0).reshape(R, S, -1) for k, v in outs.items()}
 
 
-def nerf_render_chunk(models, configs, model_configs, pixel_id, *, training, retraw=True):
+def nerf_render_chunk(models, configs, model_configs, pixel_id, *, training, retraw=True, extrinsics=None):
     """models: {'coarse_model': params, 'fine_model': params,
                 'augmentations': [(name, cfg, params), ...]}  (aug models are coarse-only, as shipped).
-    Mirrors SimpleNeRF.render_rays for ndc=True/False, no visibility prediction."""
+    Mirrors SimpleNeRF.render_rays for ndc=True/False, no visibility prediction.  `extrinsics` [V,4,4]: the (differentiable) view
+    matrices of a learnable pose correction (RY.pose_correction) instead of the fixed ones of model_configs."""
     mc = configs['model']
     ndc = configs['data_loader']['ndc']
     K = torch.tensor(model_configs['intrinsics'], dtype=torch.float32)
-    E = torch.tensor(model_configs['extrinsics'], dtype=torch.float32)
+    E = torch.tensor(model_configs['extrinsics'], dtype=torch.float32) if extrinsics is None else extrinsics
     h, w = model_configs['resolution']
     R = pixel_id.shape[0]
     out = {}
@@ -95,14 +96,14 @@ def nerf_render_chunk(models, configs, model_configs, pixel_id, *, training, ret
     return out
 
 
-def tensorf_render_chunk(tensors, configs, model_configs, pixel_id, *, training, retraw=True):
+def tensorf_render_chunk(tensors, configs, model_configs, pixel_id, *, training, retraw=True, extrinsics=None):
     """tensors: {'coarse_model': dict(params=, bbox=, num_samples=, alpha_volume=None, alpha_bbox=None),
                  'augmentations': [(name, cfg, dict(...)), ...]}.  NDC path of SimpleTensoRF.render_rays
     (SimpleTensoRF09.py:194-296): half-pixel rays, x-flip, view dirs from the NDC direction, samples
     from the MAIN tensor's num_samples for every tensor, background coin per tensor in training."""
     mc = configs['model']
     K = torch.tensor(model_configs['intrinsics'], dtype=torch.float32)
-    E = torch.tensor(model_configs['extrinsics'], dtype=torch.float32)
+    E = torch.tensor(model_configs['extrinsics'], dtype=torch.float32) if extrinsics is None else extrinsics     # as in nerf_render_chunk
     h, w = model_configs['resolution']
     R = pixel_id.shape[0]
     out = {}

@@ -58,3 +58,20 @@ def depth_from_ndc(z_ndc, rays_o, rays_d):
     tn = -(1 + oz) / dz
     eps = torch.where(z_ndc == 1., 1e-3, 0.)
     return (oz + tn * dz) / dz * (1 / (1 - z_ndc + eps) - 1) + tn
+
+
+def pose_correction(initial_extrinsics, r, t):
+    """ExtrinsicsLearner.forward for every view (SimpleNeRF17.py:831-842, :868-912): the learnable pose correction
+    inv([Exp(r) | t; 0 0 0 1]) applied from the right to the initial camera-to-world matrices.  r (axis-angle), t: [V, 3];
+    Exp is Rodrigues' formula with the reference's 1e-15 guard on |r|.  Differentiable w.r.t. r and t."""
+    zero = torch.zeros((r.shape[0], 1), dtype=torch.float32)
+    k0 = torch.cat([zero, -r[:, 2:3], r[:, 1:2]], dim=1)
+    k1 = torch.cat([r[:, 2:3], zero, -r[:, 0:1]], dim=1)
+    k2 = torch.cat([-r[:, 1:2], r[:, 0:1], zero], dim=1)
+    skew = torch.stack([k0, k1, k2], dim=2)
+    n = r.norm(dim=1) + 1e-15
+    rot = torch.eye(3)[None] + (torch.sin(n) / n)[:, None, None] * skew + ((1 - torch.cos(n)) / n ** 2)[:, None, None] * (skew @ skew)
+    top = torch.cat([rot, t.unsqueeze(2)], dim=2)
+    bottom = torch.zeros_like(top[:, 0:1])
+    bottom[:, 0, 3] = 1.0
+    return initial_extrinsics.float() @ torch.linalg.inv(torch.cat([top, bottom], dim=1))

@@ -45,9 +45,11 @@ def validity_mask(pts, bbox, alpha_volume=None, alpha_bbox=None):
 
 
 def _plane_line_coords(p):
-    plane = torch.stack([p[..., MATRIX_AXES[0]], p[..., MATRIX_AXES[1]], p[..., MATRIX_AXES[2]]]).view(3, -1, 1, 2)
+    """Grid coordinates are DETACHED (SimpleTensoRF09.py:1224-1228, :1251-1253; CP: :1054, :1075): with learnable cameras the sample points
+    carry no gradient into the tensors' interpolation."""
+    plane = torch.stack([p[..., MATRIX_AXES[0]], p[..., MATRIX_AXES[1]], p[..., MATRIX_AXES[2]]]).detach().view(3, -1, 1, 2)
     line = torch.stack([p[..., VECTOR_AXES[0]], p[..., VECTOR_AXES[1]], p[..., VECTOR_AXES[2]]])
-    line = torch.stack([torch.zeros_like(line), line], dim=-1).view(3, -1, 1, 2)
+    line = torch.stack([torch.zeros_like(line), line], dim=-1).detach().view(3, -1, 1, 2)
     return plane, line
 
 

@@ -218,3 +218,60 @@ def test_trilinear_positive_restatement():
     ref = TF.sample_alpha(vol.view(1, 1, Z, Y, X), bbox, pts) > 0
     mine = AO.trilinear_positive(vol.numpy(), bbox.numpy(), pts.numpy())
     assert np.array_equal(mine, ref.numpy())
+
+
+def _probe_loss(out, keys, seed):
+    g = torch.Generator().manual_seed(seed)
+    return sum((out[k] * torch.randn(out[k].shape, generator=g)).sum() for k in keys)
+
+
+def test_learnable_camera_gradients_match_reference_golden(golden, golden_configs):
+    """Pose-correction gradients (SimpleNeRF17.py:817-842) of a fixed linear functional of the rendered maps: the oracle pipeline fed with
+    `rays.pose_correction(...)` against r.grad / t.grad of the unmodified reference models (oracle/generate_golden.py::golden_learnable_cameras)."""
+    from oracle import rays as RY
+    g = golden('learnable_cameras')
+    # Simple-NeRF: NDC, coarse + fine + augmentation MLPs in training mode
+    configs, model_configs = golden_configs('nerf')
+    sets = FX.nerf_param_sets(configs, seed=11)
+    r, t = g['nerf_r'].clone().requires_grad_(), g['nerf_t'].clone().requires_grad_()
+    torch.manual_seed(909)
+    out = P.nerf_render_chunk(sets, configs, model_configs, g['nerf_pixel_id'], training=True,
+                              extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r, t))
+    keys = ('rgb_coarse', 'rgb_fine', 'depth_coarse', 'depth_fine', 'depth_ndc_fine', 'acc_fine', 'rays_o', 'rays_d_ndc', 'view_dirs')
+    _probe_loss(out, keys, 77).backward()
+    assert _close(out['rgb_fine'].detach(), g['nerf_rgb_fine'], 2e-4)
+    for got, want in ((r.grad, g['nerf_r_grad']), (t.grad, g['nerf_t_grad'])):
+        assert float(want.abs().max()) > 0
+        assert _close(got, want, 2e-3 * float(want.abs().max())), float((got - want).abs().max() / want.abs().max())
+    # Simple-TensoRF: NDC; the grid coordinates are detached upstream, the pose is reached through view_dirs, |d| and the world depths
+    configs, model_configs = golden_configs('tensorf')
+    sets = FX.tensorf_sets(configs, seed=21, with_alpha=False)
+    r, t = g['tensorf_r'].clone().requires_grad_(), g['tensorf_t'].clone().requires_grad_()
+    torch.manual_seed(910)
+    out = P.tensorf_render_chunk(sets, configs, model_configs, g['tensorf_pixel_id'], training=True,
+                                 extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r, t))
+    _probe_loss(out, ('rgb_coarse', 'depth_coarse', 'depth_ndc_coarse', 'acc_coarse', 'view_dirs', 'rays_d'), 78).backward()
+    assert _close(out['rgb_coarse'].detach(), g['tensorf_rgb'], 2e-4)
+    for got, want in ((r.grad, g['tensorf_r_grad']), (t.grad, g['tensorf_t_grad'])):
+        assert float(want.abs().max()) > 0
+        assert _close(got, want, 2e-3 * float(want.abs().max())), float((got - want).abs().max() / want.abs().max())
+
+
+def test_pose_correction_matches_the_dropin_learner(golden_configs):
+    """oracle.rays.pose_correction == the drop-in's ExtrinsicsLearner.forward (the class Trainer10 / Tester07 optimise), values and gradients."""
+    from oracle import rays as RY
+    from simple_rf_b200.models.SimpleNeRF91 import ExtrinsicsLearner
+    _, model_configs = golden_configs('nerf')
+    E = torch.tensor(model_configs['extrinsics']).float()
+    learner = ExtrinsicsLearner(E.numpy(), learn_rotation=True, learn_translation=True)
+    gen = torch.Generator().manual_seed(3)
+    learner.r.data.copy_(torch.randn(learner.r.shape, generator=gen) * 0.05)
+    learner.t.data.copy_(torch.randn(learner.t.shape, generator=gen) * 0.05)
+    r, t = learner.r.detach().clone().requires_grad_(), learner.t.detach().clone().requires_grad_()
+    a = learner(torch.arange(learner.num_frames))
+    b = RY.pose_correction(E, r, t)
+    assert torch.allclose(a, b, rtol=0, atol=1e-6)
+    probe = torch.randn(a.shape, generator=gen)
+    (a * probe).sum().backward()
+    (b * probe).sum().backward()
+    assert torch.allclose(learner.r.grad, r.grad, rtol=1e-5, atol=1e-6) and torch.allclose(learner.t.grad, t.grad, rtol=1e-5, atol=1e-6)
