@@ -62,3 +62,43 @@ def test_one_block_rows_program():
     m = PackedRowsMLP(24, 27, 3, prefix='mlp')                 # 27 input columns: a single K block, no region 5
     assert m.program.views_degree == -1 and m.v_slot == -1 and m.act_slots == 5
     assert len(m.backward_plan.items) == 3
+
+
+def test_input_gradient_sources_cover_every_encoding_consumer(golden_configs):
+    """Learnable cameras: the table `srf_nerf_mlp_input_grad` walks (nerf_program.build_backward_plan) names, for every layer that reads
+    an encoding image, the dZ images of that layer and the weight column every image column multiplies — checked against the layer
+    shapes of the three shipped MLP variants (SimpleNeRF17.py:616-667; the sigma-encoding variant routes the upper octaves to the view layer)."""
+    from simple_rf_b200.nerf_program import PackedMLP
+    configs, _ = golden_configs('nerf')
+    m = configs['model']
+    variants = [m['coarse_model'], m['augmentations'][0]['coarse_model'], m['augmentations'][1]['coarse_model']]
+    seen_split = False
+    for cfg in variants:
+        packed = PackedMLP(cfg)
+        plan = packed.backward_plan
+        full = 3 * (2 * cfg['points_positional_encoding_degree'] + 1)
+        pts_in = 3 * (2 * cfg['points_sigma_positional_encoding_degree'] + 1) if 'points_sigma_positional_encoding_degree' in cfg else full
+        extra = full - pts_in
+        seen_split = seen_split or extra > 0
+        by_weight = {}
+        for s in plan.input_sources:
+            name = next(n for n, o in packed.offs.items() if o == s.w_offset and n.endswith('.weight'))
+            assert s.in_total == packed.shapes[name][1] and s.dz_images * 64 == packed.shapes[name][0]
+            assert 0 <= s.dz_slot and s.dz_slot + s.dz_images <= plan.dz_slots
+            cols = list(s.cols)
+            if s.target == 1:
+                assert all(c < 0 for c in cols[32:]), 'the view image holds 32 columns'
+            by_weight.setdefault(name, []).append((s.target, cols))
+        want = {'pts_linears.0.weight': [(0, list(range(pts_in)) + [-1] * (64 - pts_in))]}
+        skip_layer = 'pts_linears.5.weight'
+        if packed.shapes.get(skip_layer, (0, 0))[1] == 256 + pts_in:
+            want[skip_layer] = [(0, list(range(pts_in)) + [-1] * (64 - pts_in))]          # cat([input_pts, h]): encoding first
+        if packed.use_views:
+            v = 3 * (2 * cfg['views_positional_encoding_degree'] + 1)
+            entries = []
+            if extra > 0:
+                entries.append((0, [-1] * pts_in + [256 + i for i in range(extra)] + [-1] * (64 - full)))
+            entries.append((1, [256 + extra + j for j in range(v)] + [-1] * (64 - v)))
+            want['views_linears.0.weight'] = entries
+        assert by_weight == want, (cfg, by_weight.keys())
+    assert seen_split
