@@ -833,6 +833,37 @@ def golden_learnable_cameras():
     fixtures.update({'tensorf_pixel_id': pixel_id, 'tensorf_r': r0, 'tensorf_t': t0, 'tensorf_r_grad': g_r, 'tensorf_t_grad': g_t,
                      'tensorf_rgb': ref['rgb_coarse'].detach(), 'tensorf_depth': ref['depth_coarse'].detach()})
     print(f'learnable cameras, Simple-TensoRF: |r.grad| {float(g_r.norm()):.4f} |t.grad| {float(g_t.norm()):.4f}, oracle == reference')
+    # ---- Simple-TensoRF in world space: the box-march depths start at the ray's entry into the box, so they move with the pose (:388-400)
+    configs, model_configs = tensorf_world_configs()
+    configs['model']['learn_camera_rotation'] = True
+    configs['model']['learn_camera_translation'] = True
+    model = H.build_model(configs, model_configs)
+    sets = FX.tensorf_sets(configs, seed=23, with_alpha=False)
+    load_tensorf_params(model, sets)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    r0, t0 = _pose_probe(nviews, 33)
+    model.extrinsics_learner.r.data.copy_(r0)
+    model.extrinsics_learner.t.data.copy_(t0)
+    pixel_id = FX.random_pixels(32, nviews, h, w, 11)
+    keys = ('rgb_coarse', 'depth_coarse', 'depth_var_coarse', 'acc_coarse', 'view_dirs', 'rays_d', 'z_vals_coarse')
+    model.train(True)
+    torch.manual_seed(911)
+    ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 1, 'sub_batch_index': 1}, retraw=True)
+    _probe_loss(ref, keys, 79).backward()
+    g_r, g_t = model.extrinsics_learner.r.grad.clone(), model.extrinsics_learner.t.grad.clone()
+    r1, t1 = r0.clone().requires_grad_(), t0.clone().requires_grad_()
+    torch.manual_seed(911)
+    mine = P.tensorf_render_chunk(sets, configs, model_configs, pixel_id, training=True,
+                                  extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r1, t1))
+    _probe_loss(mine, keys, 79).backward()
+    _check('learnable_cameras/tensorf_world/rgb', ref['rgb_coarse'].detach(), mine['rgb_coarse'].detach(), exact=False, tol=2e-6)
+    _check('learnable_cameras/tensorf_world/r.grad', g_r, r1.grad, exact=False, tol=1e-4 * float(g_r.abs().max()))
+    _check('learnable_cameras/tensorf_world/t.grad', g_t, t1.grad, exact=False, tol=1e-4 * float(g_t.abs().max()))
+    fixtures.update({'tensorf_world_pixel_id': pixel_id, 'tensorf_world_r': r0, 'tensorf_world_t': t0, 'tensorf_world_r_grad': g_r,
+                     'tensorf_world_t_grad': g_t, 'tensorf_world_rgb': ref['rgb_coarse'].detach(),
+                     'tensorf_world_depth': ref['depth_coarse'].detach()})
+    print(f'learnable cameras, Simple-TensoRF world space: |r.grad| {float(g_r.norm()):.4f} |t.grad| {float(g_t.norm()):.4f}, oracle == reference')
     np.savez_compressed(OUT / 'learnable_cameras.npz', **_np(fixtures))
 
 

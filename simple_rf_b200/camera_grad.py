@@ -84,3 +84,13 @@ def rays_with_camera_gradient(c2w_all, pixel_id, intrinsics, k_inv, focal, heigh
     if ndc:
         return out
     return out[0], out[1], None, None, out[2]
+
+
+def box_entry_depth(rays_o, rays_d, bbox, near, far):
+    """The differentiable part of the world-space box march (SimpleTensoRF09.py:390-394): depth at which the ray enters the tensor's
+    bounding box, clamped to [near, far].  bbox: [[min xyz], [max xyz]] host values.  `z = z_kernel + (t - t.detach())[:, None]` ties the
+    depths `srf_box_march_z` produced to the rays without changing their values (the steps behind the entry do not depend on the ray)."""
+    box = torch.as_tensor(bbox, dtype=rays_o.dtype, device=rays_o.device)
+    safe_d = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+    rate_a, rate_b = (box[1] - rays_o) / safe_d, (box[0] - rays_o) / safe_d
+    return torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)

@@ -135,14 +135,12 @@ class SimpleTensoRF(torch.nn.Module):
     def _rays(self, pixel_id, h, w):
         """get_rays_tr (+0.5 px, x flip) + get_ndc_rays_tr + get_view_dirs_tr (SimpleTensoRF09.py:205-239) in one launch.  Learnable cameras under
         autograd: same kernel, same values, attached to the graph of ExtrinsicsLearner.forward (camera_grad.py); the gradient reaches the pose
-        through the view directions of the colour MLP, |d| under delta and the NDC -> world depths (the grid coordinates are detached upstream,
-        :1054, :1075)."""
+        through the view directions of the colour MLP, |d| under delta and the NDC -> world depths — in world space: the entry depth of the
+        box march, `_render_rays_world` — (the grid coordinates are detached upstream, :1054, :1075)."""
         ndc = self.ndc
         flags = dict(half_pixel=True, flip_x=True, ndc=ndc, viewdirs_from_ndc=ndc)
         learner = self.extrinsics_learner
         if torch.is_grad_enabled() and (learner.r.requires_grad or learner.t.requires_grad):
-            if not ndc:
-                raise NotImplementedError('learnable cameras without NDC: the box-march depths (SimpleTensoRF09.py:388-400) depend on the rays')
             from .. import camera_grad
             dev = pixel_id.device
             k = self.intrinsics_learner.initial_intrinsics
@@ -260,6 +258,10 @@ class SimpleTensoRF(torch.nn.Module):
             jitter = torch.rand([R, 1], device=rays_o.device)
         z = ops.box_march_z(rays_o, rays_d, S, main.host_geometry()['box'], self.model_configs['near'], self.model_configs['far'],
                             float(main.step_size), jitter)
+        if rays_o.requires_grad or rays_d.requires_grad:       # learnable cameras: the entry depth moves with the pose (:390-394)
+            from .. import camera_grad
+            t = camera_grad.box_entry_depth(rays_o, rays_d, main.host_geometry()['box'], self.model_configs['near'], self.model_configs['far'])
+            z = z + (t - t.detach())[:, None]
         out['z_vals_coarse'] = z
         rays = dict(rays_o=rays_o, rays_d=rays_d, rays_o_ndc=None, rays_d_ndc=None, view_dirs=out['view_dirs'], z=z)
         for k, v in main(rays, retraw, white_bkgd=mc['white_bkgd']).items():

@@ -155,11 +155,11 @@ class _Composite(torch.autograd.Function):
                work=float(R) * S * (16 + (12 if gs[0] is not None else 0) + (12 if want_rgb else 0) + (4 if gs[6] is not None else 0)))
         if has_rgb and ctx.needs_input_grad[1] and g_rgb_s is None:
             g_rgb_s = torch.zeros((R, S, 3), dtype=torch.float32, device=sigma.device)
-        g_o = g_d = g_dn = None
-        if any(ctx.needs_input_grad[3:6]):
-            g_o, g_d, g_dn = _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc, scale, g_sigma,
-                                                      g_depth=gs[2], g_depth_var=gs[4])
-        return g_sigma, g_rgb_s, None, g_o, g_d, g_dn, None, None, None, None
+        g_z = g_o = g_d = g_dn = None
+        if any(ctx.needs_input_grad[2:6]):
+            g_o, g_d, g_dn, g_z = _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc, scale, g_sigma,
+                                                           g_depth=gs[2], g_depth_var=gs[4], want_z=ctx.needs_input_grad[2])
+        return g_sigma, g_rgb_s, g_z, g_o, g_d, g_dn, None, None, None, None
 
 
 def _ndc_to_world_depth(z_ndc, rays_o, rays_d):
@@ -170,12 +170,17 @@ def _ndc_to_world_depth(z_ndc, rays_o, rays_d):
     return (oz + tn * dz) / dz * (1 / (1 - z_ndc + guard) - 1) + tn
 
 
-def _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc, scale, g_sigma, g_depth, g_depth_var):
+def _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc, scale, g_sigma, g_depth, g_depth_var, want_z=False):
     """Learnable cameras only: gradient of the compositing outputs w.r.t. the rays, sigma / rgb / z held fixed.  The rays enter in two places
     (SimpleNeRF17.py:486-516): (1) delta = dists * |d| — alpha = 1 - exp(-sigma delta) is symmetric in sigma and |d|, so
     dL/d|d| = sum_s g_sigma sigma / |d| with the g_sigma the backward kernel just produced for ALL outputs; (2) with NDC the world depths
     z = convert_depth_from_ndc(z_ndc, rays_o, rays_d) under `depth` / `depth_var`.  [R, S] elementwise torch ops inside backward(): the
-    path exists for the test-time pose refinement of Tester07.py:62-111, not for training throughput."""
+    path exists for the test-time pose refinement of Tester07.py:62-111, not for training throughput.
+    want_z (world space only: the box-march depths of Simple-TensoRF start at the ray's entry into the box, SimpleTensoRF09.py:388-400, so
+    they depend on the pose): also the gradient w.r.t. the sample depths — through the intervals (dL/d dist = g_sigma sigma / dist, the same
+    symmetry) and through `depth` / `depth_var` with the weights held fixed.  Returns (g_rays_o, g_rays_d, g_rays_d_ndc, g_z)."""
+    if want_z and ndc:
+        raise NotImplementedError('depth gradients are only derived for world-space compositing (NDC depths never depend on the cameras)')
     with torch.enable_grad():
         ro = rays_o.detach().requires_grad_(True) if rays_o is not None else None
         rd = rays_d.detach().requires_grad_(True)
@@ -191,9 +196,22 @@ def _composite_ray_gradients(sigma, z, vis, rays_o, rays_d, rays_d_ndc, acc, ndc
                 total = total + (g_depth * depth).sum()
             if g_depth_var is not None:
                 total = total + (g_depth_var * torch.sum(weights * torch.square(z_world - depth[..., None]), dim=-1)).sum()
-        wrt = [t for t in (ro, rd, rdn) if t is not None]
+        zz = None
+        if want_z:
+            zz = z.detach().requires_grad_(True)
+            dists = torch.cat([zz[:, 1:], torch.full_like(zz[:, :1], 1e10)], -1) - zz
+            d0 = dists.detach()
+            per_interval = torch.where(d0 != 0, g_sigma * sigma / torch.where(d0 != 0, d0, torch.ones_like(d0)), torch.zeros_like(d0))
+            total = total + (per_interval * dists).sum()
+            weights = (1. - torch.exp(-sigma * d0 * norm.detach()[:, None] * scale)) * vis
+            depth = torch.sum(weights * zz, dim=-1) / (acc + 1e-6)
+            if g_depth is not None:
+                total = total + (g_depth * depth).sum()
+            if g_depth_var is not None:
+                total = total + (g_depth_var * torch.sum(weights * torch.square(zz - depth[..., None]), dim=-1)).sum()
+        wrt = [t for t in (ro, rd, rdn, zz) if t is not None]
         grads = dict(zip(map(id, wrt), torch.autograd.grad(total, wrt, allow_unused=True)))
-    return tuple(None if t is None else grads[id(t)] for t in (ro, rd, rdn))
+    return tuple(None if t is None else grads[id(t)] for t in (ro, rd, rdn, zz))
 
 
 def composite(sigma, rgb, z, rays_o, rays_d, rays_d_ndc=None, *, ndc, white_bkgd=False, distance_scale=1.0,

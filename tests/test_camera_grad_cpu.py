@@ -74,6 +74,8 @@ def test_composite_ray_gradients_match_autograd(ndc, scale):
     sigma = torch.relu(torch.randn(R, S, generator=g) * 3).double().requires_grad_()
     rgb = torch.rand(R, S, 3, generator=g).double()
     z = torch.sort(torch.rand(R, S, generator=g).double() * (0.98 if ndc else 4.0) + (0.0 if ndc else 2.0), dim=-1).values
+    if not ndc:
+        z.requires_grad_()               # world space: the box-march depths depend on the pose (SimpleTensoRF09.py:388-400)
     rays_o = (torch.randn(R, 3, generator=g).double() * 0.3 - torch.tensor([0., 0., 0.5])).requires_grad_()
     rays_d = (torch.randn(R, 3, generator=g).double() * 0.3 - torch.tensor([0., 0., 1.0])).requires_grad_()
     rays_dn = (torch.randn(R, 3, generator=g).double() * 0.5 + torch.tensor([0., 0., 1.5])).requires_grad_() if ndc else None
@@ -82,17 +84,84 @@ def test_composite_ray_gradients_match_autograd(ndc, scale):
     probes = {k: torch.randn(out[k].shape, generator=g).double() for k in keys}
     probes['weights'] = torch.randn(R, S, generator=g).double()
     loss = sum((out[k] * p).sum() for k, p in probes.items())
-    wrt = [sigma, rays_o, rays_d] + ([rays_dn] if ndc else [])
+    wrt = [sigma, rays_o, rays_d] + ([rays_dn] if ndc else [z])
     grads = torch.autograd.grad(loss, wrt, allow_unused=True)
     g_sigma = grads[0]
-    got = ops._composite_ray_gradients(sigma.detach(), z, out['visibility'].detach(), rays_o.detach(), rays_d.detach(),
+    got = ops._composite_ray_gradients(sigma.detach(), z.detach(), out['visibility'].detach(), rays_o.detach(), rays_d.detach(),
                                        None if rays_dn is None else rays_dn.detach(), out['acc'].detach(), ndc, scale, g_sigma,
-                                       g_depth=probes['depth'], g_depth_var=probes['depth_var'])
-    want = [grads[1], grads[2], grads[3] if ndc else None]
-    for name, a, b in zip(('rays_o', 'rays_d', 'rays_d_ndc'), got, want):
+                                       g_depth=probes['depth'], g_depth_var=probes['depth_var'], want_z=not ndc)
+    want = [grads[1], grads[2], grads[3] if ndc else None, None if ndc else grads[3]]
+    assert ndc or float(want[3].abs().max()) > 0
+    for name, a, b in zip(('rays_o', 'rays_d', 'rays_d_ndc', 'z'), got, want):
         if b is None:
             assert a is None or float(a.abs().max()) == 0.0, name
             continue
         if a is None:
             a = torch.zeros_like(b)
         assert torch.allclose(a, b, rtol=1e-8, atol=1e-10), (name, float((a - b).abs().max()))
+
+
+def test_world_space_tensorf_pose_gradient_decomposition(golden_configs):
+    """Simple-TensoRF without NDC and with learnable cameras: the drop-in never differentiates the whole render; it adds up (i) the view-direction
+    gradient of the colour branch, (ii) `ops._composite_ray_gradients` (|d|, and the sample depths), (iii) the entry depth of the box march
+    (`camera_grad.box_entry_depth`) and (iv) rays -> view matrices (`camera_grad.rays_from_cameras`).  Here every kernel is replaced by the
+    oracle stage it is tested against, and the sum is compared with autograd through the oracle's whole render (which
+    tests/test_oracle_cpu.py pins to r.grad / t.grad of the unmodified reference)."""
+    from oracle import sampling as SP
+    from oracle import tensorf as TF
+    from simple_rf_b200 import camera_grad as CG
+    from simple_rf_b200 import ops
+    configs, mc = golden_configs('tensorf_world')
+    cfg = configs['model']['coarse_model']
+    t = FX.tensorf_sets(configs, seed=23, with_alpha=False)['coarse_model']
+    K, E = torch.tensor(mc['intrinsics']).float(), torch.tensor(mc['extrinsics']).float()
+    h, w = mc['resolution']
+    pid = FX.random_pixels(24, K.shape[0], h, w, seed=12)
+    gen = torch.Generator().manual_seed(2)
+    r0, t0 = torch.randn(K.shape[0], 3, generator=gen) * 0.01, torch.randn(K.shape[0], 3, generator=gen) * 0.02
+    res = t['resolution'].long()
+    step = torch.mean((t['bbox'][1] - t['bbox'][0]).float() / (res - 1)) * cfg['num_voxels_per_sample']
+    S, near, far = t['num_samples'], mc['near'], mc['far']
+    flags = dict(half_pixel=True, flip_x=True, ndc=False, viewdirs_from_ndc=False)
+    kw = dict(ndc=False, distance_scale=cfg['distance_scale'], weight_threshold=cfg['ray_marching_weight_threshold'])
+    keys = ('rgb', 'depth', 'depth_var', 'acc')
+    probes = {k: torch.randn((24, 3) if k == 'rgb' else (24,), generator=gen) for k in keys}
+
+    # ---- the whole render under autograd (oracle)
+    r, tt = r0.clone().requires_grad_(), t0.clone().requires_grad_()
+    ro, rd = RY.camera_rays(pid, K, RY.pose_correction(E, r, tt), half_pixel=True, flip_x=True)
+    z = SP.box_march_depths(ro, rd, t['bbox'], near, far, step, S)
+    pts = ro[:, None, :] + rd[:, None, :] * z[..., None]
+    out = TF.tensor_forward(t['params'], t['bbox'], pts, z, ro, rd, None, RY.view_dirs(rd), **kw)
+    sum((out[k] * probes[k]).sum() for k in keys).backward()
+    want_r, want_t = r.grad.clone(), tt.grad.clone()
+    assert float(out['surface_mask'].float().mean()) > 0.01
+
+    # ---- the drop-in's decomposition
+    r, tt = r0.clone().requires_grad_(), t0.clone().requires_grad_()
+    rays_o, rays_d, _, _, view_dirs = CG.rays_from_cameras(RY.pose_correction(E, r, tt), pid, K, h, w, near, **flags)      # (iv)
+    ro_l, rd_l, vd_l = (x.detach().requires_grad_() for x in (rays_o, rays_d, view_dirs))
+    z_values = SP.box_march_depths(ro_l.detach(), rd_l.detach(), t['bbox'], near, far, step, S)                             # srf_box_march_z
+    entry = CG.box_entry_depth(ro_l, rd_l, t['bbox'].tolist(), near, far)                                                  # (iii)
+    z_attached = z_values + (entry - entry.detach())[:, None]
+    assert torch.equal(z_attached.detach(), z_values)
+    pts = ro_l.detach()[:, None, :] + rd_l.detach()[:, None, :] * z_values[..., None]                                       # kernels see raw values
+    mask = TF.validity_mask(pts, t['bbox'])
+    pn = TF.normalize(pts, t['bbox'])
+    sigma = TF.density(t['params'], pn, mask)[..., 0].detach().requires_grad_()
+    with torch.no_grad():
+        surface = OC.composite(sigma, None, z_values, ro_l, rd_l, None, ndc=False, distance_scale=cfg['distance_scale'])['weights'] > kw['weight_threshold']
+    rgb = TF.vm_color(t['params'], pn, surface, vd_l)                                                                      # colour branch, (i)
+    rgb_l = rgb.detach().requires_grad_()
+    vr = OC.composite(sigma, rgb_l, z_values, ro_l.detach(), rd_l.detach(), None, ndc=False, distance_scale=cfg['distance_scale'])
+    g_sigma, g_rgb = torch.autograd.grad(sum((vr[k] * probes[k]).sum() for k in keys), [sigma, rgb_l])                     # srf_composite_bwd
+    g_o, g_d, _, g_z = ops._composite_ray_gradients(sigma.detach(), z_values, vr['visibility'].detach(), ro_l.detach(), rd_l.detach(), None,
+                                                    vr['acc'].detach(), False, cfg['distance_scale'], g_sigma,
+                                                    g_depth=probes['depth'], g_depth_var=probes['depth_var'], want_z=True)  # (ii)
+    torch.autograd.backward([rgb, z_attached], [g_rgb, g_z])                 # -> vd_l.grad, and ro_l.grad / rd_l.grad through the entry depth
+    g_rays_o = ro_l.grad + (g_o if g_o is not None else 0)
+    g_rays_d = rd_l.grad + g_d
+    torch.autograd.backward([rays_o, rays_d, view_dirs], [g_rays_o, g_rays_d, vd_l.grad])
+    for name, got, want in (('r', r.grad, want_r), ('t', tt.grad, want_t)):
+        rel = float((got - want).norm() / want.norm())
+        assert rel <= 1e-3, (name, rel)

@@ -257,6 +257,24 @@ def test_learnable_camera_gradients_match_reference_golden(golden, golden_config
         assert _close(got, want, 2e-3 * float(want.abs().max())), float((got - want).abs().max() / want.abs().max())
 
 
+def test_learnable_camera_gradients_world_space_tensorf(golden, golden_configs):
+    """Simple-TensoRF without NDC: the box-march depths start where the ray enters the box (SimpleTensoRF09.py:388-400), so the pose is also
+    reached through z (depth, depth_var, the intervals)."""
+    from oracle import rays as RY
+    g = golden('learnable_cameras')
+    configs, model_configs = golden_configs('tensorf_world')
+    sets = FX.tensorf_sets(configs, seed=23, with_alpha=False)
+    r, t = g['tensorf_world_r'].clone().requires_grad_(), g['tensorf_world_t'].clone().requires_grad_()
+    torch.manual_seed(911)
+    out = P.tensorf_render_chunk(sets, configs, model_configs, g['tensorf_world_pixel_id'], training=True,
+                                 extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r, t))
+    _probe_loss(out, ('rgb_coarse', 'depth_coarse', 'depth_var_coarse', 'acc_coarse', 'view_dirs', 'rays_d', 'z_vals_coarse'), 79).backward()
+    assert _close(out['rgb_coarse'].detach(), g['tensorf_world_rgb'], 2e-4)
+    for got, want in ((r.grad, g['tensorf_world_r_grad']), (t.grad, g['tensorf_world_t_grad'])):
+        assert float(want.abs().max()) > 0
+        assert _close(got, want, 2e-3 * float(want.abs().max())), float((got - want).abs().max() / want.abs().max())
+
+
 def test_pose_correction_matches_the_dropin_learner(golden_configs):
     """oracle.rays.pose_correction == the drop-in's ExtrinsicsLearner.forward (the class Trainer10 / Tester07 optimise), values and gradients."""
     from oracle import rays as RY
