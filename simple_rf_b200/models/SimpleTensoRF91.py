@@ -490,7 +490,7 @@ class LowRankTensor(torch.nn.Module):
         basis = self.basis_matrix_color.weight
         factors = self.color_factors()                                      # planes then lines (VM) / the three lines (CP)
         color_params = [*factors, *[cp.mlp[i].weight if j == 0 else cp.mlp[i].bias for i in (0, 2, 4) for j in (0, 1)]]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in [basis, rays['view_dirs']] + color_params):
+        if torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in [basis, rays['view_dirs']] + color_params):
             rgb_rows = _VmColor.apply(cp, geom, surface, rays['view_dirs'], self.num_color_planes, basis, *color_params)
         else:
             rows, _ = self.color_rows(geom, surface, rays['view_dirs'])
