@@ -800,6 +800,36 @@ def golden_learnable_cameras():
     fixtures.update({'nerf_pixel_id': pixel_id, 'nerf_r': r0, 'nerf_t': t0, 'nerf_r_grad': g_r, 'nerf_t_grad': g_t,
                      'nerf_rgb_fine': ref['rgb_fine'].detach(), 'nerf_depth_fine': ref['depth_fine'].detach()})
     print(f'learnable cameras, Simple-NeRF: |r.grad| {float(g_r.norm()):.4f} |t.grad| {float(g_t.norm()):.4f}, oracle == reference')
+    # ---- Simple-NeRF in world space (lindisp depths, white background): the rays enter through pts, view_dirs and |d| under delta
+    configs, model_configs = nerf_variant_configs()
+    configs['model']['learn_camera_rotation'] = True
+    configs['model']['learn_camera_translation'] = True
+    model = H.build_model(configs, model_configs)
+    sets = FX.nerf_param_sets(configs, seed=13)
+    load_nerf_params(model, sets)
+    h, w = model_configs['resolution']
+    nviews = len(model_configs['intrinsics'])
+    r0, t0 = _pose_probe(nviews, 34)
+    model.extrinsics_learner.r.data.copy_(r0)
+    model.extrinsics_learner.t.data.copy_(t0)
+    pixel_id = FX.random_pixels(40, nviews, h, w, 12)
+    keys = ('rgb_coarse', 'rgb_fine', 'depth_coarse', 'depth_fine', 'depth_var_fine', 'acc_fine', 'rays_d', 'view_dirs')
+    model.train(True)
+    torch.manual_seed(912)
+    ref = model({'pixel_id': pixel_id, 'num_frames': nviews, 'iter_num': 0, 'sub_batch_index': 0}, retraw=True)
+    _probe_loss(ref, keys, 80).backward()
+    g_r, g_t = model.extrinsics_learner.r.grad.clone(), model.extrinsics_learner.t.grad.clone()
+    r1, t1 = r0.clone().requires_grad_(), t0.clone().requires_grad_()
+    torch.manual_seed(912)
+    mine = P.nerf_render_chunk(sets, configs, model_configs, pixel_id, training=True,
+                               extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r1, t1))
+    _probe_loss(mine, keys, 80).backward()
+    _check('learnable_cameras/nerf_world/rgb_fine', ref['rgb_fine'].detach(), mine['rgb_fine'].detach(), exact=False, tol=2e-6)
+    _check('learnable_cameras/nerf_world/r.grad', g_r, r1.grad, exact=False, tol=1e-4 * float(g_r.abs().max()))
+    _check('learnable_cameras/nerf_world/t.grad', g_t, t1.grad, exact=False, tol=1e-4 * float(g_t.abs().max()))
+    fixtures.update({'nerf_world_pixel_id': pixel_id, 'nerf_world_r': r0, 'nerf_world_t': t0, 'nerf_world_r_grad': g_r, 'nerf_world_t_grad': g_t,
+                     'nerf_world_rgb_fine': ref['rgb_fine'].detach()})
+    print(f'learnable cameras, Simple-NeRF world space: |r.grad| {float(g_r.norm()):.4f} |t.grad| {float(g_t.norm()):.4f}, oracle == reference')
     # ---- Simple-TensoRF (NDC)
     configs, model_configs = H.load_configs(212, '00000')
     model_configs = H.shrink(model_configs, 4)

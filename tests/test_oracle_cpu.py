@@ -257,6 +257,23 @@ def test_learnable_camera_gradients_match_reference_golden(golden, golden_config
         assert _close(got, want, 2e-3 * float(want.abs().max())), float((got - want).abs().max() / want.abs().max())
 
 
+def test_learnable_camera_gradients_world_space_nerf(golden, golden_configs):
+    """Simple-NeRF with `ndc = False`, lindisp depths, white background and learnable cameras (oracle/generate_golden.py::nerf_variant_configs)."""
+    from oracle import rays as RY
+    g = golden('learnable_cameras')
+    configs, model_configs = golden_configs('nerf_variant')
+    sets = FX.nerf_param_sets(configs, seed=13)
+    r, t = g['nerf_world_r'].clone().requires_grad_(), g['nerf_world_t'].clone().requires_grad_()
+    torch.manual_seed(912)
+    out = P.nerf_render_chunk(sets, configs, model_configs, g['nerf_world_pixel_id'], training=True,
+                              extrinsics=RY.pose_correction(torch.tensor(model_configs['extrinsics']), r, t))
+    _probe_loss(out, ('rgb_coarse', 'rgb_fine', 'depth_coarse', 'depth_fine', 'depth_var_fine', 'acc_fine', 'rays_d', 'view_dirs'), 80).backward()
+    assert _close(out['rgb_fine'].detach(), g['nerf_world_rgb_fine'], 2e-4)
+    for got, want in ((r.grad, g['nerf_world_r_grad']), (t.grad, g['nerf_world_t_grad'])):
+        assert float(want.abs().max()) > 0
+        assert _close(got, want, 2e-3 * float(want.abs().max())), float((got - want).abs().max() / want.abs().max())
+
+
 def test_learnable_camera_gradients_world_space_tensorf(golden, golden_configs):
     """Simple-TensoRF without NDC: the box-march depths start where the ray enters the box (SimpleTensoRF09.py:388-400), so the pose is also
     reached through z (depth, depth_var, the intervals)."""
